@@ -1,0 +1,365 @@
+// DSP stages of FlowHighSR.generate as CUDA kernels: polyphase resampler + peak normalise
+// (flowhighsr.py:68-69), log-mel front end (melvoco.py:56-86) and the STFT-domain
+// post-processing (postprocessing.py:18-41).  All HBM-bound; one CTA per STFT frame with the
+// 2048-point FFT staged in shared memory.
+#include <stdarg.h>
+#include <atomic>
+#include "common.cuh"
+
+namespace fh {
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch(int n) { g_launches += n; }
+}  // namespace fh
+
+extern "C" __attribute__((visibility("default"))) int fh_version(void) { return 1; }
+extern "C" __attribute__((visibility("default"))) const char* fh_last_error_string(void) { return fh::g_err; }
+extern "C" __attribute__((visibility("default"))) int64_t fh_launch_count(void) { return (int64_t)fh::g_launches.load(); }
+
+namespace {
+
+// ------------------------------------------------------------------------------ utilities
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__device__ __forceinline__ void block_absmax_atomic(float v, uint32_t* dst) {
+  __shared__ float red[32];
+  v = fh::warp_max(v);
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    int nw = (blockDim.x + 31) >> 5;
+    float m = lane < nw ? red[lane] : 0.f;
+    m = fh::warp_max(m);
+    if (lane == 0) atomicMax(dst, __float_as_uint(m));
+  }
+}
+
+// ------------------------------------------------------------------------------ resampler
+__global__ void resample_poly_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                     const float* __restrict__ h, uint32_t* absmax, int T_in, int T_out,
+                                     int ntaps, int up, int down, int n_pre_pad, int n_pre_remove) {
+  const int b = blockIdx.y;
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  float acc = 0.f;
+  if (m < T_out) {
+    const long long n = (long long)(m + n_pre_remove) * down - n_pre_pad;  // tap index for i = 0
+    if (n >= 0) {
+      long long lo = n - ntaps + 1;
+      int i_lo = lo > 0 ? (int)((lo + up - 1) / up) : 0;
+      int i_hi = (int)(n / up);
+      if (i_hi > T_in - 1) i_hi = T_in - 1;
+      const float* xb = x + (size_t)b * T_in;
+      for (int i = i_lo; i <= i_hi; ++i) acc = fmaf(__ldg(xb + i), __ldg(h + (n - (long long)i * up)), acc);
+    }
+    y[(size_t)b * T_out + m] = acc;
+  }
+  if (absmax) block_absmax_atomic(fabsf(acc), absmax + b);
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, uint32_t* absmax, int T) {
+  const int b = blockIdx.y;
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[(size_t)b * T + i]));
+  block_absmax_atomic(m, absmax + b);
+}
+
+__global__ void scale_by_absmax_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                       const uint32_t* __restrict__ absmax, float scale, int T) {
+  const int b = blockIdx.y;
+  const float mx = __uint_as_float(absmax[b]);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < T; i += gridDim.x * blockDim.x) {
+    float v = x[(size_t)b * T + i] / mx;  // IEEE division, as numpy / torch
+    y[(size_t)b * T + i] = scale == 1.0f ? v : v * scale;
+  }
+}
+
+// ------------------------------------------------------------------------------ 2048-point FFT
+// Stockham autosort radix-2, ping-pong between two shared buffers; returns the buffer that
+// holds the result in natural order.  Forward: exp(-2 pi i jk/n); inverse: conjugate, unscaled.
+template <typename T>
+struct Cplx {
+  T x, y;
+};
+template <typename T>
+__device__ __forceinline__ Cplx<T> cmul(Cplx<T> a, Cplx<T> b) {
+  return {a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x};
+}
+
+template <typename T>
+__device__ __forceinline__ Cplx<T> twiddle(const float2* __restrict__ tw, int idx);  // exp(-2 pi i idx / 2048)
+template <>
+__device__ __forceinline__ Cplx<float> twiddle<float>(const float2* __restrict__ tw, int idx) {
+  float2 w = __ldg(tw + idx);
+  return {w.x, w.y};
+}
+template <>
+__device__ __forceinline__ Cplx<double> twiddle<double>(const float2* __restrict__, int idx) {
+  double s, c;
+  sincospi(-(double)idx / 1024.0, &s, &c);
+  return {c, s};
+}
+
+template <typename T, bool INVERSE>
+__device__ Cplx<T>* fft2048(Cplx<T>* a, Cplx<T>* b, const float2* __restrict__ tw) {
+#pragma unroll 1
+  for (int Ns = 1, sh = 10; Ns < 2048; Ns <<= 1, --sh) {
+    for (int j = threadIdx.x; j < 1024; j += blockDim.x) {
+      const int k = j & (Ns - 1);
+      Cplx<T> w = twiddle<T>(tw, k << sh);
+      if (INVERSE) w.y = -w.y;
+      const Cplx<T> u = a[j];
+      const Cplx<T> v = cmul(a[j + 1024], w);
+      const int j0 = ((j - k) << 1) + k;
+      b[j0] = {u.x + v.x, u.y + v.y};
+      b[j0 + Ns] = {u.x - v.x, u.y - v.y};
+    }
+    __syncthreads();
+    Cplx<T>* t = a;
+    a = b;
+    b = t;
+  }
+  return a;
+}
+
+// ------------------------------------------------------------------------------ log-mel
+template <typename T>
+__global__ void __launch_bounds__(256) stft_logmel_kernel(const float* __restrict__ audio, float* __restrict__ mel,
+                                                          const float* __restrict__ window,
+                                                          const float2* __restrict__ tw,
+                                                          const int* __restrict__ mel_start,
+                                                          const int* __restrict__ mel_len,
+                                                          const float* __restrict__ mel_w, int mel_stride, int Tlen,
+                                                          int N) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cplx<T>* a = reinterpret_cast<Cplx<T>*>(smem_raw);
+  Cplx<T>* b = a + 2048;
+  const int n = blockIdx.x, bi = blockIdx.y;
+  const float* x = audio + (size_t)bi * Tlen;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+    int pos = n * 480 + i - 784;  // reflect pad 784 (melvoco.py:74)
+    if (pos < 0) pos = -pos;
+    if (pos >= Tlen) pos = 2 * (Tlen - 1) - pos;
+    const float v = __ldg(x + pos) * __ldg(window + i);  // fp32 product, as torch.stft
+    a[i] = {(T)v, (T)0};
+  }
+  __syncthreads();
+  Cplx<T>* r = fft2048<T, false>(a, b, tw);
+  float* mag = reinterpret_cast<float*>(r == a ? b : a);
+  for (int f = threadIdx.x; f <= 1024; f += blockDim.x) {
+    const float re = (float)r[f].x, im = (float)r[f].y;
+    mag[f] = sqrtf(re * re + im * im + 1e-9f);
+  }
+  __syncthreads();
+  for (int m = threadIdx.x; m < 256; m += blockDim.x) {
+    const int s = mel_start[m], len = mel_len[m];
+    const float* w = mel_w + (size_t)m * mel_stride;
+    float acc = 0.f;
+    for (int i = 0; i < len; ++i) acc = fmaf(__ldg(w + i), mag[s + i], acc);
+    mel[((size_t)bi * N + n) * 256 + m] = logf(fmaxf(acc, 1e-5f));
+  }
+}
+
+// ------------------------------------------------------------------------------ post-processing
+__global__ void __launch_bounds__(256) stft_center_kernel(const float* __restrict__ xin, float2* __restrict__ spec,
+                                                          const float* __restrict__ window,
+                                                          const float2* __restrict__ tw, int Tlen, int NT) {
+  __shared__ __align__(16) Cplx<float> sa[2048];
+  __shared__ __align__(16) Cplx<float> sb[2048];
+  const int n = blockIdx.x, bi = blockIdx.y;
+  const float* x = xin + (size_t)bi * Tlen;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+    const int pos = n * 480 + i - 1024;  // center=True, pad_mode='constant' (postprocessing.py:7)
+    const float v = (pos >= 0 && pos < Tlen) ? __ldg(x + pos) * __ldg(window + i) : 0.f;
+    sa[i] = {v, 0.f};
+  }
+  __syncthreads();
+  Cplx<float>* r = fft2048<float, false>(sa, sb, tw);
+  float2* out = spec + ((size_t)bi * NT + n) * 1025;
+  for (int f = threadIdx.x; f <= 1024; f += blockDim.x) out[f] = make_float2(r[f].x, r[f].y);
+}
+
+// energy[b,f] = sum_t |S[b,t,f]|  (fixed order -> deterministic cutoff)
+__global__ void pp_energy_kernel(const float2* __restrict__ spec, float* __restrict__ energy, int NT) {
+  const int bi = blockIdx.y;
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f > 1024) return;
+  const float2* s = spec + (size_t)bi * NT * 1025 + f;
+  double acc = 0.0;
+  for (int t = 0; t < NT; ++t) {
+    const float2 v = s[(size_t)t * 1025];
+    acc += (double)hypotf(v.x, v.y);
+  }
+  energy[(size_t)bi * 1025 + f] = (float)acc;
+}
+
+__global__ void pp_cutoff_kernel(const float* __restrict__ energy, int* __restrict__ cutoff, float threshold) {
+  // sequential fp32 cumsum like torch.cumsum on CPU; scan from the top, never testing bin 0
+  __shared__ float cum[1025];
+  const int bi = blockIdx.x;
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int f = 0; f <= 1024; ++f) {
+      acc += energy[(size_t)bi * 1025 + f];
+      cum[f] = acc;
+    }
+    const float thr = cum[1024] * threshold;
+    int cr = 0;
+    for (int idx = 1024; idx >= 1; --idx)
+      if (cum[idx] < thr) {
+        cr = idx;
+        break;
+      }
+    cutoff[bi] = cr;
+  }
+}
+
+__global__ void __launch_bounds__(256) pp_splice_istft_kernel(const float2* __restrict__ sp, const float2* __restrict__ ss,
+                                                              const int* __restrict__ cutoff, float* __restrict__ frames,
+                                                              const float* __restrict__ window,
+                                                              const float2* __restrict__ tw, int NT) {
+  __shared__ __align__(16) Cplx<float> sa[2048];
+  __shared__ __align__(16) Cplx<float> sb[2048];
+  const int n = blockIdx.x, bi = blockIdx.y;
+  const int cr = cutoff[bi];
+  const size_t base = ((size_t)bi * NT + n) * 1025;
+  for (int k = threadIdx.x; k < 2048; k += blockDim.x) {
+    const int f = k <= 1024 ? k : 2048 - k;
+    float2 v = f < cr ? ss[base + f] : sp[base + f];
+    if (f == 0 || f == 1024) v.y = 0.f;  // c2r ignores the imaginary part of DC / Nyquist
+    if (k > 1024) v.y = -v.y;
+    sa[k] = {v.x, v.y};
+  }
+  __syncthreads();
+  Cplx<float>* r = fft2048<float, true>(sa, sb, tw);
+  float* out = frames + ((size_t)bi * NT + n) * 2048;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) out[i] = r[i].x * (1.0f / 2048.0f) * __ldg(window + i);
+}
+
+__global__ void pp_overlap_add_kernel(const float* __restrict__ frames, float* __restrict__ y,
+                                      const float* __restrict__ window, uint32_t* absmax, int NT, int length) {
+  const int bi = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  float v = 0.f;
+  if (t < length) {
+    const int p = t + 1024;
+    int n_hi = p / 480;
+    if (n_hi > NT - 1) n_hi = NT - 1;
+    int n_lo = p - 2047 > 0 ? (p - 2047 + 479) / 480 : 0;
+    float acc = 0.f, env = 0.f;
+    for (int n = n_lo; n <= n_hi; ++n) {
+      const int i = p - 480 * n;
+      acc += frames[((size_t)bi * NT + n) * 2048 + i];
+      const float w = __ldg(window + i);
+      env = fmaf(w, w, env);
+    }
+    v = env > 1e-11f ? acc / env : 0.f;
+    y[(size_t)bi * length + t] = v;
+  }
+  if (absmax) block_absmax_atomic(fabsf(v), absmax + bi);
+}
+
+}  // namespace
+
+// ================================================================================ C ABI
+extern "C" __attribute__((visibility("default"))) int fh_fill_u32(uint32_t* p, uint32_t v, int64_t n, void* stream) {
+  if (n <= 0) return FH_OK;
+  fill_u32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, v, n);
+  return fh::check_launch("fh_fill_u32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_resample_poly_f32(const float* x, float* y, const float* h, uint32_t* absmax_bits, int B, int T_in,
+                                    int T_out, int ntaps, int up, int down, int n_pre_pad, int n_pre_remove,
+                                    void* stream) {
+  FH_REQUIRE(B > 0 && T_in > 0 && T_out > 0 && ntaps > 0 && up > 0 && down > 0, FH_ERR_BAD_SHAPE,
+             "fh_resample_poly_f32: bad shape B=%d T_in=%d T_out=%d", B, T_in, T_out);
+  dim3 grid((T_out + 255) / 256, B);
+  resample_poly_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, y, h, absmax_bits, T_in, T_out, ntaps, up, down,
+                                                               n_pre_pad, n_pre_remove);
+  return fh::check_launch("fh_resample_poly_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_absmax_f32(const float* x, uint32_t* absmax_bits, int B, int T, void* stream) {
+  FH_REQUIRE(B > 0 && T > 0, FH_ERR_BAD_SHAPE, "fh_absmax_f32: bad shape");
+  int bx = (T + 256 * 8 - 1) / (256 * 8);
+  if (bx > 1024) bx = 1024;
+  absmax_kernel<<<dim3(bx, B), 256, 0, (cudaStream_t)stream>>>(x, absmax_bits, T);
+  return fh::check_launch("fh_absmax_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_scale_by_absmax_f32(const float* x, float* y, const uint32_t* absmax_bits, float scale, int B, int T,
+                                      void* stream) {
+  FH_REQUIRE(B > 0 && T > 0, FH_ERR_BAD_SHAPE, "fh_scale_by_absmax_f32: bad shape");
+  int bx = (T + 256 * 4 - 1) / (256 * 4);
+  if (bx > 2048) bx = 2048;
+  scale_by_absmax_kernel<<<dim3(bx, B), 256, 0, (cudaStream_t)stream>>>(x, y, absmax_bits, scale, T);
+  return fh::check_launch("fh_scale_by_absmax_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_stft_logmel_f32(const float* audio, float* mel, const float* window, const float* twiddle,
+                                  const int* mel_start, const int* mel_len, const float* mel_w, int mel_stride, int B,
+                                  int T, int N, int precise, void* stream) {
+  FH_REQUIRE(B > 0 && N > 0 && T >= 785, FH_ERR_BAD_SHAPE,
+             "fh_stft_logmel_f32: need T >= 785 for the 784-sample reflect pad (got T=%d)", T);
+  FH_REQUIRE(N == (T + 1568 - 2048) / 480 + 1, FH_ERR_BAD_SHAPE, "fh_stft_logmel_f32: N=%d does not match T=%d", N, T);
+  dim3 grid(N, B);
+  if (precise) {
+    const int smem = 2 * 2048 * sizeof(double) * 2;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(stft_logmel_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+      attr_set = true;
+    }
+    stft_logmel_kernel<double><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        audio, mel, window, (const float2*)twiddle, mel_start, mel_len, mel_w, mel_stride, T, N);
+  } else {
+    const int smem = 2 * 2048 * sizeof(float) * 2;
+    stft_logmel_kernel<float><<<grid, 256, smem, (cudaStream_t)stream>>>(
+        audio, mel, window, (const float2*)twiddle, mel_start, mel_len, mel_w, mel_stride, T, N);
+  }
+  return fh::check_launch("fh_stft_logmel_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_stft_center_f32(const float* x, float* spec, float* energy, const float* window,
+                                  const float* twiddle, int B, int T, int NT, void* stream) {
+  FH_REQUIRE(B > 0 && T > 0 && NT == 1 + T / 480, FH_ERR_BAD_SHAPE, "fh_stft_center_f32: NT=%d does not match T=%d", NT,
+             T);
+  stft_center_kernel<<<dim3(NT, B), 256, 0, (cudaStream_t)stream>>>(x, (float2*)spec, window, (const float2*)twiddle, T,
+                                                                    NT);
+  int rc = fh::check_launch("fh_stft_center_f32");
+  if (rc != FH_OK || !energy) return rc;
+  pp_energy_kernel<<<dim3((1025 + 127) / 128, B), 128, 0, (cudaStream_t)stream>>>((const float2*)spec, energy, NT);
+  return fh::check_launch("fh_stft_center_f32(energy)");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_pp_cutoff(const float* energy, int* cutoff, int B, float threshold, void* stream) {
+  FH_REQUIRE(B > 0, FH_ERR_BAD_SHAPE, "fh_pp_cutoff: bad shape");
+  pp_cutoff_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(energy, cutoff, threshold);
+  return fh::check_launch("fh_pp_cutoff");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_pp_splice_istft_f32(const float* spec_pred, const float* spec_src, const int* cutoff, float* frames,
+                                      const float* window, const float* twiddle, int B, int NT, void* stream) {
+  FH_REQUIRE(B > 0 && NT > 0, FH_ERR_BAD_SHAPE, "fh_pp_splice_istft_f32: bad shape");
+  pp_splice_istft_kernel<<<dim3(NT, B), 256, 0, (cudaStream_t)stream>>>(
+      (const float2*)spec_pred, (const float2*)spec_src, cutoff, frames, window, (const float2*)twiddle, NT);
+  return fh::check_launch("fh_pp_splice_istft_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_pp_overlap_add_f32(const float* frames, float* y, const float* window, uint32_t* absmax_bits, int B,
+                                     int NT, int length, void* stream) {
+  FH_REQUIRE(B > 0 && NT > 0 && length > 0, FH_ERR_BAD_SHAPE, "fh_pp_overlap_add_f32: bad shape");
+  pp_overlap_add_kernel<<<dim3((length + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(frames, y, window, absmax_bits,
+                                                                                       NT, length);
+  return fh::check_launch("fh_pp_overlap_add_f32");
+}

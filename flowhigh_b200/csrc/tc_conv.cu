@@ -1,0 +1,518 @@
+// tcgen05 / TMEM implicit-GEMM tapped convolution for sm_100a.
+//
+// One kernel serves every GEMM-shaped op of the hot path: the BigVGAN Conv1d / dilated Conv1d
+// (bigvgan/models.py:27-43), the ConvTranspose1d upsamplers in polyphase form (models.py:140-146)
+// and the backbone Linear layers (k = 1; flow.py:239,261, attend.py:176,189, transformer.py:100-103).
+//
+// Data layout ("chunked"): an activation [L, C] is stored as [C/8][Lp][8] bf16, so the 8 channels
+// of one time step are one 16-byte row and 8 consecutive time steps x 8 channels are one
+// contiguous 128-byte tcgen05 core matrix (no-swizzle, K-major canonical layout
+// ((8,m),(8,2)):((16B,SBO=128B),(1,LBO))).  Consequences:
+//   * a (128 + halo)-row window of one chunk is ONE cp.async.bulk (UBLKCP) of contiguous bytes;
+//   * every convolution tap reads the SAME shared-memory window through a descriptor whose start
+//     address is shifted by tap_offset*16 B -- the activation tile is fetched once per k taps;
+//   * the two 8-channel halves of a K=16 MMA step are addressed by LBO, so no im2col, no swizzle.
+// Weights are pre-packed on the host into the exact shared-memory image (packing.py), one bulk
+// copy per stage.  Accumulators live in TMEM (2 x bn columns, double buffered across tiles);
+// the epilogue (bias, alpha, residual, accumulate, GEGLU, bf16/fp32, chunked or row-major output)
+// reads them with tcgen05.ld.  Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer +
+// TMEM allocator, warps 2..5 = epilogue.  Persistent CTAs, static tile striding.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxTapOff = 64;
+constexpr int kARowsPad = 192;                 // rows reserved per chunk window in an A slot
+constexpr int kASlotBytes = 2 * kARowsPad * 16;  // two 8-channel chunks
+constexpr int kMaxStages = 8;
+constexpr int kThreads = 192;                  // 6 warps
+
+struct TcParams {
+  const __nv_bfloat16* a;
+  const __nv_bfloat16* w;
+  const float* bias;
+  const void* res;
+  void* out;
+  long long a_batch, a_chunk;
+  long long out_batch, out_chunk, out_row;
+  long long res_batch, res_chunk, res_row;
+  int a_row0;
+  int out_is_bf16, res_is_bf16, accumulate, geglu;
+  float alpha, beta_res;
+  int B, L, Cin, Cout, ntaps, P, bn;
+  int m_tiles, n_tiles, total_tiles;
+  int ci_pairs;        // Cin / 16
+  int tg, n_groups;    // taps per smem stage, groups per ci-pair
+  int wrows;           // rows fetched per chunk window: 128 + (max_off - min_off)
+  int stages, stage_bytes;
+  int min_off[16];
+  int tap_off[kMaxTapOff];
+  unsigned int* err_flag;
+};
+
+// ------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug becomes a trap (reported as a launch failure), not a hung GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err_flag, int code) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      if (err_flag) atomicExch(err_flag, (unsigned)code);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor):
+// start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout_type=0 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
+// K-major A/B, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+struct TileCoord {
+  int b, p, mt, nt;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int id) {
+  TileCoord c;
+  c.nt = id % P.n_tiles;
+  id /= P.n_tiles;
+  c.mt = id % P.m_tiles;
+  id /= P.m_tiles;
+  c.p = id % P.P;
+  c.b = id / P.P;
+  return c;
+}
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// ------------------------------------------------------------------------------ the kernel
+__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  // [0,256): barriers; [256,260): tmem base; stages from 1024
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
+  const uint32_t tfull0 = empty0 + 8 * kMaxStages, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxStages + 4));
+  const uint32_t stage0 = smem_u32(smem + 1024);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = P.stages;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(full0 + 8 * i, 1);
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int steps_per_tile = P.ci_pairs * P.n_groups;
+  const uint32_t b_tap_bytes = (uint32_t)P.bn * 32u;  // one tap: 2 chunks x bn rows x 16 B
+
+  if (warp == 0) {
+    // ===================================================================== producer
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(P, tile);
+        const long long row = (long long)P.a_row0 + (long long)tc.mt * 128 + P.min_off[tc.p];
+        const __nv_bfloat16* a_base = P.a + (long long)tc.b * P.a_batch + row * 8;
+        // packed weights: [p][nt][cp][tap][2][bn][8]
+        const __nv_bfloat16* w_base =
+            P.w + ((long long)(tc.p * P.n_tiles + tc.nt) * P.ci_pairs) * ((long long)P.ntaps * P.bn * 16);
+        for (int cp = 0; cp < P.ci_pairs; ++cp) {
+          for (int g = 0; g < P.n_groups; ++g) {
+            const int tap0 = g * P.tg;
+            const int nt_g = min(P.tg, P.ntaps - tap0);
+            mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 1);
+            const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
+            const uint32_t fb = full0 + 8 * stage;
+            const uint32_t a_bytes = (uint32_t)P.wrows * 16u;
+            mbar_expect_tx(fb, 2u * a_bytes + (uint32_t)nt_g * b_tap_bytes);
+            bulk_g2s(sa, a_base + (long long)(2 * cp) * P.a_chunk, a_bytes, fb);
+            bulk_g2s(sa + kARowsPad * 16, a_base + (long long)(2 * cp + 1) * P.a_chunk, a_bytes, fb);
+            bulk_g2s(sa + kASlotBytes, w_base + ((long long)cp * P.ntaps + tap0) * ((long long)P.bn * 16),
+                     (uint32_t)nt_g * b_tap_bytes, fb);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0, phase = 0, as = 0, aphase = 0;
+      const uint32_t idesc = make_idesc(P.bn);
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(P, tile);
+        mbar_wait(tempty0 + 8 * as, aphase ^ 1, P.err_flag, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * P.bn);
+        const int* offs = P.tap_off + tc.p * P.ntaps;
+        const int mn = P.min_off[tc.p];
+        uint32_t first = 1;
+        for (int step = 0; step < steps_per_tile; ++step) {
+          const int g = step % P.n_groups;
+          const int tap0 = g * P.tg;
+          const int nt_g = min(P.tg, P.ntaps - tap0);
+          mbar_wait(full0 + 8 * stage, phase, P.err_flag, 3);
+          tc_fence_after();
+          const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
+          const uint32_t sb = sa + kASlotBytes;
+          for (int j = 0; j < nt_g; ++j) {
+            const uint64_t adesc = make_desc(sa + (uint32_t)(offs[tap0 + j] - mn) * 16u, kARowsPad * 16, 128);
+            const uint64_t bdesc = make_desc(sb + (uint32_t)j * b_tap_bytes, (uint32_t)P.bn * 16u, 128);
+            umma_bf16(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
+            first = 0;
+          }
+          umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tfull0 + 8 * as);  // accumulator complete -> epilogue
+        if (++as == 2) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int lane_grp = warp & 3;  // TMEM lanes 32*lane_grp .. +31 are accessible to this warp
+    const int r = lane_grp * 32 + lane;
+    int as = 0, aphase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(P, tile);
+      mbar_wait(tfull0 + 8 * as, aphase, P.err_flag, 4);
+      tc_fence_after();
+      const int t = tc.mt * 128 + r;
+      const bool row_ok = t < P.L;
+      const long long orow = (long long)t * P.P + tc.p;
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(as * P.bn);
+      const int n_base = tc.nt * P.bn;
+      for (int c0 = 0; c0 < P.bn; c0 += 16) {
+        if (n_base + c0 >= P.Cout) break;  // warp-uniform
+        uint32_t v[16];
+        tmem_ld16(taddr + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+        if (P.geglu) {
+          // columns (2i, 2i+1) = (x_i, gate_i) -> gelu(gate) * x ; 16 columns -> one 8-channel chunk
+          const int n_out = (n_base + c0) >> 1;
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int n = n_base + c0 + 2 * i;
+            float xv = __uint_as_float(v[2 * i]), gv = __uint_as_float(v[2 * i + 1]);
+            if (P.bias) {
+              xv += __ldg(P.bias + n);
+              gv += __ldg(P.bias + n + 1);
+            }
+            o[i] = gelu_f(gv) * xv;
+          }
+          const long long idx = (long long)tc.b * P.out_batch + (long long)(n_out >> 3) * P.out_chunk + orow * P.out_row;
+          if (P.out_is_bf16) {
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+            *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
+          } else {
+            float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          }
+          continue;
+        }
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int n0 = n_base + c0 + hh * 8;
+          if (n0 >= P.Cout) break;
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float acc = __uint_as_float(v[hh * 8 + i]);
+            if (P.bias) acc += __ldg(P.bias + n0 + i);
+            o[i] = acc * P.alpha;
+          }
+          if (P.res) {
+            const long long ridx =
+                (long long)tc.b * P.res_batch + (long long)(n0 >> 3) * P.res_chunk + orow * P.res_row;
+            if (P.res_is_bf16) {
+              const uint4 raw = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)P.res + ridx);
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __bfloat1622float2(h[i]);
+                o[2 * i] = fmaf(P.beta_res, f.x, o[2 * i]);
+                o[2 * i + 1] = fmaf(P.beta_res, f.y, o[2 * i + 1]);
+              }
+            } else {
+              const float4* rp = reinterpret_cast<const float4*>((const float*)P.res + ridx);
+              const float4 r0 = rp[0], r1 = rp[1];
+              o[0] = fmaf(P.beta_res, r0.x, o[0]);
+              o[1] = fmaf(P.beta_res, r0.y, o[1]);
+              o[2] = fmaf(P.beta_res, r0.z, o[2]);
+              o[3] = fmaf(P.beta_res, r0.w, o[3]);
+              o[4] = fmaf(P.beta_res, r1.x, o[4]);
+              o[5] = fmaf(P.beta_res, r1.y, o[5]);
+              o[6] = fmaf(P.beta_res, r1.z, o[6]);
+              o[7] = fmaf(P.beta_res, r1.w, o[7]);
+            }
+          }
+          const long long idx = (long long)tc.b * P.out_batch + (long long)(n0 >> 3) * P.out_chunk + orow * P.out_row;
+          if (P.out_is_bf16) {
+            __nv_bfloat162 h[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+            *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
+          } else {
+            float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
+            if (P.accumulate) {
+              const float4 p0 = dst[0], p1 = dst[1];
+              o[0] += p0.x, o[1] += p0.y, o[2] += p0.z, o[3] += p0.w;
+              o[4] += p1.x, o[5] += p1.y, o[6] += p1.z, o[7] += p1.w;
+            }
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      }
+      // all TMEM reads of this warp are complete (wait::ld above) -> release the accumulator
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------ layout helpers
+__global__ void to_chunked_bf16_kernel(const float* __restrict__ src, long long src_batch, long long src_c,
+                                       long long src_t, __nv_bfloat16* __restrict__ dst, long long dst_batch,
+                                       long long dst_chunk, int dst_row0, int C, int L) {
+  // one thread per (t, chunk): gathers 8 channels, writes one 16-byte row
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nch = (C + 7) >> 3;
+  const int b = blockIdx.y;
+  if (i >= (long long)nch * L) return;
+  int t, ch;
+  if (src_t == 1) {  // planar source: adjacent threads walk along t
+    t = (int)(i % L);
+    ch = (int)(i / L);
+  } else {  // row-major source: adjacent threads walk along channels
+    ch = (int)(i % nch);
+    t = (int)(i / nch);
+  }
+  const float* s = src + (long long)b * src_batch + (long long)t * src_t;
+  __nv_bfloat162 h[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c0 = ch * 8 + 2 * k;
+    const float f0 = c0 < C ? s[(long long)c0 * src_c] : 0.f;
+    const float f1 = c0 + 1 < C ? s[(long long)(c0 + 1) * src_c] : 0.f;
+    h[k] = __floats2bfloat162_rn(f0, f1);
+  }
+  *reinterpret_cast<uint4*>(dst + (long long)b * dst_batch + (long long)ch * dst_chunk + (long long)(dst_row0 + t) * 8) =
+      *reinterpret_cast<uint4*>(h);
+}
+
+}  // namespace
+
+// ================================================================================ C ABI
+extern "C" __attribute__((visibility("default"))) int64_t fh_tc_packed_weight_bytes(int Cin, int Cout, int ntaps, int P, int bn) {
+  if (Cin <= 0 || Cout <= 0 || ntaps <= 0 || P <= 0 || bn <= 0 || (Cin % 16) || (bn % 16)) return -1;
+  const int64_t n_tiles = (Cout + bn - 1) / bn;
+  return (int64_t)P * n_tiles * (Cin / 16) * ntaps * bn * 32;
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_tc_conv_bf16(const fh_tc_conv_args* a, void* stream) {
+  FH_REQUIRE(a != nullptr, FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: null args");
+  FH_REQUIRE(a->B > 0 && a->L > 0 && a->Cin > 0 && a->Cout > 0, FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: bad shape");
+  FH_REQUIRE(a->Cin % 16 == 0, FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: Cin=%d must be a multiple of 16", a->Cin);
+  FH_REQUIRE(a->Cout % 8 == 0, FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: Cout=%d must be a multiple of 8", a->Cout);
+  FH_REQUIRE(a->bn % 16 == 0 && a->bn >= 16 && a->bn <= 256, FH_ERR_UNSUPPORTED_CFG,
+             "fh_tc_conv_bf16: bn=%d must be a multiple of 16 in [16,256]", a->bn);
+  FH_REQUIRE(a->P >= 1 && a->P <= 16 && a->ntaps >= 1 && a->P * a->ntaps <= kMaxTapOff, FH_ERR_UNSUPPORTED_CFG,
+             "fh_tc_conv_bf16: P=%d ntaps=%d unsupported", a->P, a->ntaps);
+  FH_REQUIRE(!(a->geglu && (a->res || a->accumulate || (a->Cout % 16))), FH_ERR_UNSUPPORTED_CFG,
+             "fh_tc_conv_bf16: geglu epilogue excludes residual/accumulate and needs Cout %% 16 == 0");
+  FH_REQUIRE(!(a->accumulate && a->out_is_bf16), FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv_bf16: accumulate needs fp32 out");
+  FH_REQUIRE(((uintptr_t)a->a % 16) == 0 && ((uintptr_t)a->w % 16) == 0 && ((uintptr_t)a->out % 16) == 0 &&
+                 ((uintptr_t)a->res % 16) == 0,
+             FH_ERR_BAD_ALIGN, "fh_tc_conv_bf16: pointers must be 16-byte aligned");
+  FH_REQUIRE(a->a_chunk % 8 == 0 && a->a_batch % 8 == 0, FH_ERR_BAD_ALIGN, "fh_tc_conv_bf16: A strides must be x8");
+  const int esz_shift = a->out_is_bf16 ? 3 : 2;  // 16-byte alignment in elements
+  FH_REQUIRE((a->out_batch % (1 << esz_shift)) == 0 && (a->out_chunk % (1 << esz_shift)) == 0 &&
+                 (a->out_row % (1 << esz_shift)) == 0,
+             FH_ERR_BAD_ALIGN, "fh_tc_conv_bf16: output strides break 16-byte alignment");
+
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.a = (const __nv_bfloat16*)a->a;
+  p.w = (const __nv_bfloat16*)a->w;
+  p.bias = a->bias;
+  p.res = a->res;
+  p.out = a->out;
+  p.a_batch = a->a_batch, p.a_chunk = a->a_chunk, p.a_row0 = a->a_row0;
+  p.out_batch = a->out_batch, p.out_chunk = a->out_chunk, p.out_row = a->out_row;
+  p.res_batch = a->res_batch, p.res_chunk = a->res_chunk, p.res_row = a->res_row;
+  p.out_is_bf16 = a->out_is_bf16, p.res_is_bf16 = a->res_is_bf16;
+  p.accumulate = a->accumulate, p.geglu = a->geglu;
+  p.alpha = a->alpha, p.beta_res = a->beta_res;
+  p.B = a->B, p.L = a->L, p.Cin = a->Cin, p.Cout = a->Cout, p.ntaps = a->ntaps, p.P = a->P, p.bn = a->bn;
+  p.m_tiles = (a->L + 127) / 128;
+  p.n_tiles = (a->Cout + a->bn - 1) / a->bn;
+  const long long total = (long long)p.B * p.P * p.m_tiles * p.n_tiles;
+  FH_REQUIRE(total < (1ll << 31), FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: too many tiles");
+  p.total_tiles = (int)total;
+  p.ci_pairs = a->Cin / 16;
+  int span = 0;
+  for (int ph = 0; ph < a->P; ++ph) {
+    int mn = a->tap_off[ph * a->ntaps], mx = mn;
+    for (int m = 0; m < a->ntaps; ++m) {
+      const int o = a->tap_off[ph * a->ntaps + m];
+      p.tap_off[ph * a->ntaps + m] = o;
+      mn = o < mn ? o : mn;
+      mx = o > mx ? o : mx;
+    }
+    p.min_off[ph] = mn;
+    span = (mx - mn) > span ? (mx - mn) : span;
+    FH_REQUIRE(a->a_row0 + mn >= 0, FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: left halo %d too small for tap offset %d",
+               a->a_row0, mn);
+  }
+  p.wrows = 128 + span;
+  FH_REQUIRE(p.wrows <= kARowsPad, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv_bf16: tap span %d exceeds %d rows", span,
+             kARowsPad - 128);
+  // taps per stage: keep a B slot <= 32 KB
+  int tg = 32768 / (a->bn * 32);
+  if (tg < 1) tg = 1;
+  if (tg > a->ntaps) tg = a->ntaps;
+  p.tg = tg;
+  p.n_groups = (a->ntaps + tg - 1) / tg;
+  p.stage_bytes = kASlotBytes + tg * a->bn * 32;
+  p.stage_bytes = (p.stage_bytes + 127) & ~127;
+  const int budget = 200 * 1024;
+  int stages = (budget - 1024) / p.stage_bytes;
+  if (stages > kMaxStages) stages = kMaxStages;
+  FH_REQUIRE(stages >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv_bf16: stage of %d bytes does not fit twice", p.stage_bytes);
+  p.stages = stages;
+  p.err_flag = nullptr;
+  const int smem = 1024 + stages * p.stage_bytes;
+
+  static int num_sms = 0;
+  static int smem_set = 0;
+  if (!num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (num_sms <= 0) num_sms = 148;
+  }
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv_bf16: cannot opt in to %d bytes of smem: %s", smem,
+               cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  tc_conv_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  return fh::check_launch("fh_tc_conv_bf16");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_to_chunked_bf16(const float* src, int64_t src_batch, int64_t src_c, int64_t src_t, void* dst,
+                                  int64_t dst_batch, int64_t dst_chunk, int dst_row0, int B, int C, int L,
+                                  void* stream) {
+  FH_REQUIRE(B > 0 && C > 0 && L > 0 && B <= 65535, FH_ERR_BAD_SHAPE, "fh_to_chunked_bf16: bad shape");
+  const long long n = (long long)((C + 7) / 8) * L;
+  to_chunked_bf16_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(
+      src, src_batch, src_c, src_t, (__nv_bfloat16*)dst, dst_batch, dst_chunk, dst_row0, C, L);
+  return fh::check_launch("fh_to_chunked_bf16");
+}

@@ -1,0 +1,240 @@
+// fp32 CUDA-core kernels of the BigVGAN generator (models/bigvgan/models.py:172-194) on the
+// reference's [B, C, L] layout: generic tapped convolution (Conv1d with dilation and the
+// polyphase form of ConvTranspose1d), the fused anti-aliased Snake/SnakeBeta activation
+// (alias_free_torch/act.py:23-28) and the conv_post + tanh tail.  This is the fp32 parity path.
+#include "common.cuh"
+
+namespace {
+
+constexpr int CT_CO = 64, CT_T = 64, CT_CI = 8;
+
+// out[b, co, P*t+p] = alpha*(bias[co] + sum_{ci,m} w[p][co][ci][m] * x[b,ci,t+off[p][m]]) + beta_res*res + acc
+__global__ void __launch_bounds__(256) conv1d_taps_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, const int* __restrict__ off,
+                                                          const float* __restrict__ res, float beta_res, float alpha,
+                                                          int accumulate, float* __restrict__ out, int Cin, int Cout,
+                                                          int L, int ntaps, int P) {
+  extern __shared__ __align__(16) float csm[];
+  __shared__ int soff[32];
+  const int p = blockIdx.z % P, bi = blockIdx.z / P;
+  const int t0 = blockIdx.x * CT_T, co0 = blockIdx.y * CT_CO;
+  if (threadIdx.x < ntaps) soff[threadIdx.x] = off[p * ntaps + threadIdx.x];
+  __syncthreads();
+  int mn = soff[0], mx = soff[0];
+  for (int m = 1; m < ntaps; ++m) {
+    mn = min(mn, soff[m]);
+    mx = max(mx, soff[m]);
+  }
+  const int span = CT_T + (mx - mn);          // x window length
+  float* Xs = csm;                            // [CT_CI][span]
+  float* Ws = csm + CT_CI * span;             // [CT_CI][ntaps][CT_CO]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // tx -> t (4 each), ty -> co (4 each)
+  const float* xb = x + (size_t)bi * Cin * L;
+  const float* wp = w + (size_t)p * Cout * Cin * ntaps;
+  float acc[4][4] = {};
+  for (int ci0 = 0; ci0 < Cin; ci0 += CT_CI) {
+    for (int i = threadIdx.x; i < CT_CI * span; i += 256) {
+      const int c = i / span, tt = i % span;
+      const int t = t0 + mn + tt, ci = ci0 + c;
+      Xs[i] = (ci < Cin && t >= 0 && t < L) ? __ldg(xb + (size_t)ci * L + t) : 0.f;
+    }
+    for (int i = threadIdx.x; i < CT_CO * CT_CI * ntaps; i += 256) {
+      const int co = i / (CT_CI * ntaps), r = i % (CT_CI * ntaps);  // r = c*ntaps + m, contiguous in w
+      const int c = r / ntaps, m = r % ntaps;
+      const int cog = co0 + co, ci = ci0 + c;
+      Ws[(c * ntaps + m) * CT_CO + co] =
+          (cog < Cout && ci < Cin) ? __ldg(wp + ((size_t)cog * Cin + ci) * ntaps + m) : 0.f;
+    }
+    __syncthreads();
+    for (int c = 0; c < CT_CI; ++c) {
+      for (int m = 0; m < ntaps; ++m) {
+        const float* wr = Ws + (c * ntaps + m) * CT_CO + ty * 4;
+        const float* xr = Xs + c * span + tx * 4 + (soff[m] - mn);
+        float wv[4], xv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wv[i] = wr[i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) xv[j] = xr[j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+      }
+    }
+    __syncthreads();
+  }
+  const int Lout = L * P;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + ty * 4 + i;
+    if (co >= Cout) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + tx * 4 + j;
+      if (t >= L) continue;
+      const size_t o = ((size_t)bi * Cout + co) * Lout + (size_t)t * P + p;
+      float v = acc[i][j];
+      if (bias) v += bias[co];
+      v *= alpha;
+      if (res) v = fmaf(beta_res, res[o], v);
+      if (accumulate) v += out[o];
+      out[o] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ anti-aliased snake
+// y[q] = sum_k f[k] * s~[2q+k-5],  s[m] = u[m] + inv_b*sin^2(a*u[m]),  u[m] = 2*sum_i x~[i] f[m+5-2i]
+constexpr int SN_T = 256;
+__global__ void __launch_bounds__(SN_T) snake_aa_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                        const float* __restrict__ a, const float* __restrict__ inv_b,
+                                                        const float* __restrict__ filt, int C, int L) {
+  __shared__ float xs[SN_T + 10];
+  __shared__ float ss[2 * SN_T + 12];
+  __shared__ float f[12];
+  const int ntile = (L + SN_T - 1) / SN_T;
+  const int row = blockIdx.x / ntile;  // b*C + c
+  const int c = row % C;
+  const int q0 = (blockIdx.x % ntile) * SN_T;
+  const float* xr = x + (size_t)row * L;
+  if (threadIdx.x < 12) f[threadIdx.x] = filt[threadIdx.x];
+  for (int i = threadIdx.x; i < SN_T + 10; i += SN_T) {
+    int t = q0 - 5 + i;
+    t = min(max(t, 0), L - 1);  // replicate
+    xs[i] = __ldg(xr + t);
+  }
+  __syncthreads();
+  const float al = a[c], ib = inv_b[c];
+  // s window: m in [2*q0-5, 2*q0 + 2*SN_T + 6]; clamped to [0, 2L-1] (replicate pad of the 2x signal)
+  for (int i = threadIdx.x; i < 2 * SN_T + 11; i += SN_T) {
+    int m = 2 * q0 - 5 + i;
+    m = min(max(m, 0), 2 * L - 1);
+    const int q = m >> 1;
+    float u = 0.f;
+    if (m & 1) {  // odd: i' = q+d, d in -2..3, tap 6-2d
+#pragma unroll
+      for (int d = -2; d <= 3; ++d) {
+        const int xi = min(max(q + d, 0), L - 1) - (q0 - 5);
+        u = fmaf(xs[xi], f[6 - 2 * d], u);
+      }
+    } else {  // even: d in -3..2, tap 5-2d
+#pragma unroll
+      for (int d = -3; d <= 2; ++d) {
+        const int xi = min(max(q + d, 0), L - 1) - (q0 - 5);
+        u = fmaf(xs[xi], f[5 - 2 * d], u);
+      }
+    }
+    u *= 2.0f;
+    const float sn = sinf(u * al);
+    ss[i] = u + ib * (sn * sn);
+  }
+  __syncthreads();
+  const int q = q0 + threadIdx.x;
+  if (q < L) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) acc = fmaf(f[k], ss[2 * threadIdx.x + k], acc);
+    y[(size_t)row * L + q] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------ conv_post + tanh
+__global__ void convpost_tanh_kernel(const float* __restrict__ x, const float* __restrict__ w, float bias,
+                                     float* __restrict__ y, int C, int L) {
+  const int bi = blockIdx.y;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= L) return;
+  const float* xb = x + (size_t)bi * C * L;
+  float acc = bias;
+  for (int c = 0; c < C; ++c) {
+#pragma unroll
+    for (int j = 0; j < 7; ++j) {
+      const int tt = t + j - 3;
+      if (tt >= 0 && tt < L) acc = fmaf(__ldg(w + c * 7 + j), __ldg(xb + (size_t)c * L + tt), acc);
+    }
+  }
+  y[(size_t)bi * L + t] = tanhf(acc);
+}
+
+// ------------------------------------------------------------------------------ layout helpers
+__global__ void transpose_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int Cc) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const float* s = src + (size_t)b * R * Cc;
+  float* d = dst + (size_t)b * R * Cc;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < R && c < Cc) ? s[(size_t)r * Cc + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < R && c < Cc) d[(size_t)c * R + r] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    __nv_bfloat162 h[2] = {__floats2bfloat162_rn(v.x, v.y), __floats2bfloat162_rn(v.z, v.w)};
+    *reinterpret_cast<uint2*>(dst + i) = *reinterpret_cast<uint2*>(h);
+  } else {
+    for (long long k = i; k < n; ++k) dst[k] = __float2bfloat16(src[k]);
+  }
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int fh_conv1d_taps_f32(const float* x, const float* w, const float* bias, const int* off, const float* res,
+                                  float beta_res, float alpha, int accumulate, float* out, int B, int Cin, int Cout,
+                                  int L, int ntaps, int P, void* stream) {
+  FH_REQUIRE(B > 0 && Cin > 0 && Cout > 0 && L > 0 && ntaps > 0 && ntaps <= 32 && P > 0, FH_ERR_BAD_SHAPE,
+             "fh_conv1d_taps_f32: bad shape (ntaps must be <= 32)");
+  FH_REQUIRE((int64_t)B * P <= 65535 && (Cout + CT_CO - 1) / CT_CO <= 65535, FH_ERR_BAD_SHAPE,
+             "fh_conv1d_taps_f32: B*P too large");
+  // worst-case window: offsets are bounded by the caller's halo; size smem for span <= CT_T + 512
+  const int max_span = CT_T + 512;
+  const int smem = (CT_CI * max_span + CT_CI * ntaps * CT_CO) * (int)sizeof(float);
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaFuncSetAttribute(conv1d_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    smem_set = smem;
+  }
+  dim3 grid((L + CT_T - 1) / CT_T, (Cout + CT_CO - 1) / CT_CO, B * P);
+  conv1d_taps_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, off, res, beta_res, alpha, accumulate, out,
+                                                                Cin, Cout, L, ntaps, P);
+  return fh::check_launch("fh_conv1d_taps_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_snake_aa_f32(const float* x, float* y, const float* a, const float* inv_b, const float* filt, int B,
+                               int C, int L, void* stream) {
+  const int64_t nblk = (int64_t)((L + SN_T - 1) / SN_T) * B * C;
+  FH_REQUIRE(B > 0 && C > 0 && L > 0 && nblk <= 2147483647LL, FH_ERR_BAD_SHAPE, "fh_snake_aa_f32: bad shape");
+  dim3 grid((unsigned)nblk);
+  snake_aa_kernel<<<grid, SN_T, 0, (cudaStream_t)stream>>>(x, y, a, inv_b, filt, C, L);
+  return fh::check_launch("fh_snake_aa_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_convpost_tanh_f32(const float* x, const float* w, float bias, float* y, int B, int C, int L,
+                                    void* stream) {
+  FH_REQUIRE(B > 0 && C > 0 && L > 0 && B <= 65535, FH_ERR_BAD_SHAPE, "fh_convpost_tanh_f32: bad shape");
+  convpost_tanh_kernel<<<dim3((L + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(x, w, bias, y, C, L);
+  return fh::check_launch("fh_convpost_tanh_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_transpose_f32(const float* src, float* dst, int B, int R, int Cc, void* stream) {
+  FH_REQUIRE(B > 0 && R > 0 && Cc > 0 && B <= 65535 && (R + 31) / 32 <= 65535, FH_ERR_BAD_SHAPE,
+             "fh_transpose_f32: bad shape");
+  transpose_f32_kernel<<<dim3((Cc + 31) / 32, (R + 31) / 32, B), dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, R, Cc);
+  return fh::check_launch("fh_transpose_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (n <= 0) return FH_OK;
+  FH_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, FH_ERR_BAD_ALIGN, "fh_cast_f32_bf16: alignment");
+  const long long nthreads = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+  return fh::check_launch("fh_cast_f32_bf16");
+}

@@ -1,0 +1,542 @@
+"""Host-side orchestration of the FLowHigh hot path on one B200.
+
+Python here only owns buffers (torch tensors as device memory), packs weights once, and
+sequences kernel launches through the C ABI (flowhigh_b200/_lib.py).  No torch operator runs
+on the per-clip path: every stage of `FlowHighSR.generate` (flowhighsr.py:51-102) is one of
+the hand-written kernels.
+
+Two numeric modes:
+  * precision='fp32' -- CUDA-core fp32 kernels on the reference's layouts; the parity path
+    (waveform max-abs <= 1e-4 / mel L1 <= 1e-4 against the reference's fp32 implementation).
+  * precision='bf16' -- tcgen05/TMEM implicit-GEMM kernels on chunked bf16 operands with fp32
+    accumulators and an fp32 residual stream; the throughput path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib, packing, tables
+from .config import BackboneConfig, MelConfig, VocoderConfig
+from .weights import FH, VOC
+
+HALO = 32  # zero rows on each side of a chunked vocoder sequence (>= max dilated reach 25)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class _TcWeight:
+    __slots__ = ("packed", "bias", "off", "off_c", "P", "ntaps", "cin", "cout", "cin_pad", "cout_pad", "bn")
+
+
+class _F32Weight:
+    __slots__ = ("w", "off", "bias", "P", "ntaps", "cin", "cout")
+
+
+class Engine:
+    def __init__(self, sd: Dict[str, torch.Tensor], vcfg: VocoderConfig, bcfg: BackboneConfig = BackboneConfig(),
+                 device="cuda:0", precision: str = "bf16", precise_mel: Optional[bool] = None):
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("flowhigh_b200 has no CPU path: a CUDA (sm_100a) device is required")
+        vcfg.validate()
+        self.lib = _lib.load()
+        self.vcfg, self.bcfg, self.mcfg = vcfg, bcfg, MelConfig()
+        self.precision = precision
+        self.tc = precision == "bf16"
+        self.precise_mel = (precision == "fp32") if precise_mel is None else precise_mel
+        self._bufs: Dict[tuple, torch.Tensor] = {}
+        self._time_cache: Dict[float, dict] = {}
+        dev = self.device
+        with torch.cuda.device(dev):
+            self.sd = {k: v.detach().to(dev, torch.float32).contiguous() for k, v in sd.items()}
+            # ---- DSP tables
+            self.window = torch.hann_window(2048, dtype=torch.float32).to(dev)
+            self.twiddle = torch.from_numpy(tables.fft_twiddles()).to(dev)
+            ms, ml, mw, self.mel_stride = tables.mel_filterbank_sparse()
+            self.mel_start = torch.from_numpy(ms).to(dev)
+            self.mel_len = torch.from_numpy(ml).to(dev)
+            self.mel_w = torch.from_numpy(mw).to(dev)
+            self._resample_taps: Dict[tuple, tuple] = {}
+            self._prep_backbone()
+            self._prep_vocoder()
+        torch.cuda.synchronize(dev)
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def buf(self, name: str, shape, dtype=torch.float32, zero: bool = True) -> torch.Tensor:
+        key = (name, tuple(int(s) for s in shape), dtype)
+        t = self._bufs.get(key)
+        if t is None:
+            t = (torch.zeros if zero else torch.empty)(key[1], dtype=dtype, device=self.device)
+            self._bufs[key] = t
+        return t
+
+    def _call(self, name, *args):
+        _lib.check(getattr(self.lib, name)(*args), name)
+
+    # ------------------------------------------------------------------ weight preparation
+    def _mk_f32(self, tconv: packing.TappedConv) -> _F32Weight:
+        r = _F32Weight()
+        r.w, r.off = packing.f32_conv_buffers(tconv, self.device)
+        r.bias = None if tconv.bias is None else tconv.bias.to(self.device).float().contiguous()
+        r.P, r.ntaps, r.cin, r.cout = tconv.P, tconv.ntaps, tconv.cin, tconv.cout
+        return r
+
+    def _mk_tc(self, tconv: packing.TappedConv, cin_pad=None, cout_pad=None, bn=None) -> _TcWeight:
+        r = _TcWeight()
+        r.packed, r.cin_pad, r.cout_pad, r.bn = packing.pack_tc(tconv, self.device, cin_pad, cout_pad, bn)
+        r.bias = None if tconv.bias is None else packing.pad_vec(tconv.bias.to(self.device), r.cout_pad)
+        r.off = tconv.off.copy()
+        r.off_c = (C.c_int * r.off.size)(*[int(v) for v in r.off.flatten()])
+        r.P, r.ntaps, r.cin, r.cout = tconv.P, tconv.ntaps, tconv.cin, tconv.cout
+        return r
+
+    def _prep_backbone(self):
+        sd, b = self.sd, self.bcfg
+        self.inner = b.ff_inner
+        self.inner_pad = packing.round_up(self.inner, 16)
+        if not self.tc:
+            return
+        L = {}
+        L["to_embed"] = self._mk_tc(packing.linear_taps(sd[FH + "to_embed.weight"], sd[FH + "to_embed.bias"]))
+        L["to_pred"] = self._mk_tc(packing.linear_taps(sd[FH + "to_pred.weight"], None))
+        for l in range(b.depth):
+            p = FH + f"transformer.layers.{l}."
+            L[f"qkv{l}"] = self._mk_tc(packing.linear_taps(sd[p + "3.to_qkv.weight"], None))
+            L[f"out{l}"] = self._mk_tc(packing.linear_taps(sd[p + "3.to_out.weight"], None))
+            # FF in: interleave (x_i, gate_i) rows so that GEGLU is a column-pair epilogue; pad inner to x16
+            w1, b1 = sd[p + "5.0.weight"], sd[p + "5.0.bias"]
+            ip = self.inner_pad
+            wi = torch.zeros(2 * ip, b.dim, device=w1.device)
+            bi = torch.zeros(2 * ip, device=w1.device)
+            wi[0:2 * self.inner:2] = w1[: self.inner]
+            wi[1:2 * self.inner:2] = w1[self.inner:]
+            bi[0:2 * self.inner:2] = b1[: self.inner]
+            bi[1:2 * self.inner:2] = b1[self.inner:]
+            L[f"ff1{l}"] = self._mk_tc(packing.linear_taps(wi, bi), bn=256)
+            w2 = torch.zeros(b.dim, ip, device=w1.device)
+            w2[:, : self.inner] = sd[p + "5.3.weight"]
+            L[f"ff2{l}"] = self._mk_tc(packing.linear_taps(w2, sd[p + "5.3.bias"]))
+        self.bb_tc = L
+
+    def _snake_params(self, prefix: str, cpad: int):
+        sd, v = self.sd, self.vcfg
+        alpha = sd[prefix + "act.alpha"].cpu()
+        beta = sd[prefix + "act.beta"].cpu() if v.activation == "snakebeta" else alpha
+        if v.snake_logscale:
+            alpha, beta = torch.exp(alpha), torch.exp(beta)
+        inv_b = 1.0 / (beta + 1e-9)
+        a = packing.pad_vec(alpha, cpad, 1.0).to(self.device)
+        ib = packing.pad_vec(inv_b, cpad, 0.0).to(self.device)
+        filt_up = sd[prefix + "upsample.filter"].flatten()
+        filt_dn = sd[prefix + "downsample.lowpass.filter"].flatten()
+        if not torch.equal(filt_up, filt_dn):
+            raise ValueError("up/down anti-alias filters differ; the fused snake kernel expects one 12-tap filter")
+        return a, ib, filt_up.contiguous()
+
+    def _prep_vocoder(self):
+        sd, v = self.sd, self.vcfg
+        mk = self._mk_tc if self.tc else self._mk_f32
+        pad = (lambda c: packing.round_up(c, 16)) if self.tc else (lambda c: c)
+        self.cpad = pad
+        V = {}
+        C0 = v.upsample_initial_channel
+        kw = dict(cin_pad=pad(v.num_mels), cout_pad=pad(C0)) if self.tc else {}
+        V["conv_pre"] = mk(packing.conv1d_taps(sd[VOC + "conv_pre.weight"], sd[VOC + "conv_pre.bias"]), **kw)
+        nk = v.num_kernels
+        for s, (u, k) in enumerate(zip(v.upsample_rates, v.upsample_kernel_sizes)):
+            cin, cout = C0 // (2 ** s), v.stage_channels(s)
+            kw = dict(cin_pad=pad(cin), cout_pad=pad(cout)) if self.tc else {}
+            V[f"up{s}"] = mk(packing.conv_transpose1d_taps(sd[VOC + f"ups.{s}.0.weight"], sd[VOC + f"ups.{s}.0.bias"], u),
+                             **kw)
+            for j, (kk, dil) in enumerate(zip(v.resblock_kernel_sizes, v.resblock_dilation_sizes)):
+                p = VOC + f"resblocks.{s * nk + j}."
+                kw = dict(cin_pad=pad(cout), cout_pad=pad(cout)) if self.tc else {}
+                for i, d in enumerate(dil):
+                    if v.resblock == "1":
+                        V[f"r{s}.{j}.c1.{i}"] = mk(packing.conv1d_taps(sd[p + f"convs1.{i}.weight"],
+                                                                       sd[p + f"convs1.{i}.bias"], d), **kw)
+                        V[f"r{s}.{j}.c2.{i}"] = mk(packing.conv1d_taps(sd[p + f"convs2.{i}.weight"],
+                                                                       sd[p + f"convs2.{i}.bias"], 1), **kw)
+                        V[f"r{s}.{j}.a1.{i}"] = self._snake_params(p + f"activations.{2 * i}.", pad(cout))
+                        V[f"r{s}.{j}.a2.{i}"] = self._snake_params(p + f"activations.{2 * i + 1}.", pad(cout))
+                    else:
+                        V[f"r{s}.{j}.c1.{i}"] = mk(packing.conv1d_taps(sd[p + f"convs.{i}.weight"],
+                                                                       sd[p + f"convs.{i}.bias"], d), **kw)
+                        V[f"r{s}.{j}.a1.{i}"] = self._snake_params(p + f"activations.{i}.", pad(cout))
+        clast = v.stage_channels(v.num_stages - 1)
+        V["post_act"] = self._snake_params(VOC + "activation_post.", pad(clast))
+        wpost = torch.zeros(pad(clast), 7, device=self.device)
+        wpost[:clast] = sd[VOC + "conv_post.weight"][0]
+        V["post_w"] = wpost.contiguous()
+        V["post_b"] = float(sd[VOC + "conv_post.bias"].item())
+        self.voc = V
+
+    # ------------------------------------------------------------------ stage: resample + normalise
+    def resample_normalise(self, x: torch.Tensor, sr_in: int, sr_out: int = 48000) -> torch.Tensor:
+        """x [B, T_in] fp32 on device -> cond [B, T] = resample_poly(x) / max|.|  (flowhighsr.py:68-69)."""
+        B, T_in = x.shape
+        plan = tables.resample_plan(sr_in, sr_out)
+        absmax = self.buf("rs_absmax", (B,), torch.int32)
+        self._call("fh_fill_u32", absmax.data_ptr(), 0, B, self.stream)
+        if plan is None:
+            y, T_out = x, T_in
+            self._call("fh_absmax_f32", y.data_ptr(), absmax.data_ptr(), B, T_out, self.stream)
+        else:
+            h, up, down, npp, npr = plan
+            key = (sr_in, sr_out)
+            if key not in self._resample_taps:
+                self._resample_taps[key] = torch.from_numpy(h).to(self.device)
+            hd = self._resample_taps[key]
+            T_out = tables.resample_out_len(T_in, up, down)
+            y = self.buf("rs_y", (B, T_out), zero=False)
+            self._call("fh_resample_poly_f32", x.data_ptr(), y.data_ptr(), hd.data_ptr(), absmax.data_ptr(), B, T_in,
+                       T_out, hd.numel(), up, down, npp, npr, self.stream)
+        cond = torch.empty((B, T_out), dtype=torch.float32, device=self.device)
+        self._call("fh_scale_by_absmax_f32", y.data_ptr(), cond.data_ptr(), absmax.data_ptr(), 1.0, B, T_out, self.stream)
+        return cond
+
+    # ------------------------------------------------------------------ stage: log-mel
+    def encode(self, audio: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """MelVoco.encode (melvoco.py:56-86): audio [B,T] -> log-mel [B,N,256]."""
+        B, T = audio.shape
+        if T < 785:
+            raise ValueError("audio shorter than 785 samples cannot be reflect-padded by 784 (melvoco.py:74)")
+        N = (T + 1568 - 2048) // 480 + 1
+        mel = out if out is not None else torch.empty((B, N, 256), dtype=torch.float32, device=self.device)
+        self._call("fh_stft_logmel_f32", audio.data_ptr(), mel.data_ptr(), self.window.data_ptr(), self.twiddle.data_ptr(),
+                   self.mel_start.data_ptr(), self.mel_len.data_ptr(), self.mel_w.data_ptr(), self.mel_stride, B, T, N,
+                   1 if self.precise_mel else 0, self.stream)
+        return mel
+
+    # ------------------------------------------------------------------ stage: backbone
+    def _time_cond(self, t: float) -> dict:
+        """time embedding + the 4 (gamma, beta) pairs for time t (flow.py:242, transformer.py:82-88).
+        t only takes the values of the ODE grid, so results are cached per value."""
+        key = float(np.float32(t))
+        hit = self._time_cache.get(key)
+        if hit is not None:
+            return hit
+        sd, b = self.sd, self.bcfg
+        D = b.dim
+        four = torch.empty(D, device=self.device)
+        temb = torch.empty(D, device=self.device)
+        self._call("fh_sincos_embed_f32", sd[FH + "sinu_pos_emb.0.weights"].data_ptr(), key, four.data_ptr(), D // 2,
+                   self.stream)
+        self._call("fh_gemv_f32", sd[FH + "sinu_pos_emb.1.weight"].data_ptr(), four.data_ptr(),
+                   sd[FH + "sinu_pos_emb.1.bias"].data_ptr(), temb.data_ptr(), D, D, 1, self.stream)
+        out = {}
+        for l in range(b.depth):
+            for idx in (2, 4):
+                p = FH + f"transformer.layers.{l}.{idx}."
+                for nm in ("gamma", "beta"):
+                    v = torch.empty(D, device=self.device)
+                    self._call("fh_gemv_f32", sd[p + f"to_{nm}.weight"].data_ptr(), temb.data_ptr(),
+                               sd[p + f"to_{nm}.bias"].data_ptr(), v.data_ptr(), D, D, 0, self.stream)
+                    out[(l, idx, nm)] = v
+        self._time_cache[key] = out
+        return out
+
+    def _tc_conv(self, rec: _TcWeight, a, a_batch, a_chunk, a_row0, out, out_strides, out_bf16, B, L, res=None,
+                 res_strides=(0, 0, 0), res_bf16=0, alpha=1.0, beta=0.0, accumulate=0, geglu=0):
+        args = _lib.TcConvArgs()
+        args.a, args.a_batch, args.a_chunk, args.a_row0 = a.data_ptr(), a_batch, a_chunk, a_row0
+        args.w, args.bias = rec.packed.data_ptr(), _ptr(rec.bias)
+        args.res, args.out = _ptr(res), out.data_ptr()
+        args.out_batch, args.out_chunk, args.out_row = out_strides
+        args.res_batch, args.res_chunk, args.res_row = res_strides
+        args.out_is_bf16, args.res_is_bf16 = int(out_bf16), int(res_bf16)
+        args.alpha, args.beta_res, args.accumulate, args.geglu = alpha, beta, int(accumulate), int(geglu)
+        args.B, args.L, args.Cin, args.Cout = B, L, rec.cin_pad, rec.cout_pad
+        args.ntaps, args.P, args.tap_off, args.bn = rec.ntaps, rec.P, rec.off_c, rec.bn
+        _lib.check(self.lib.fh_tc_conv_bf16(C.byref(args), self.stream), "fh_tc_conv_bf16")
+
+    def _sgemm(self, A, lda, W, ldw, bias, res, ldr, beta, alpha, out, ldc, M, N, K):
+        self._call("fh_sgemm_nt_f32", A.data_ptr(), lda, W.data_ptr() if isinstance(W, torch.Tensor) else W, ldw,
+                   _ptr(bias), _ptr(res), ldr, beta, alpha, out.data_ptr(), ldc, M, N, K, self.stream)
+
+    def vector_field_step(self, x: torch.Tensor, cond: torch.Tensor, t: float, base: torch.Tensor, coef: float,
+                          out: torch.Tensor, cond_packed: bool = False):
+        """out = base + coef * v(t, x | cond)   -- one NFE with the CFM update folded into the
+        to_pred GEMM epilogue (flow.py:180-274 + torchdiffeq euler/midpoint step)."""
+        sd, b = self.sd, self.bcfg
+        B, N, Din = x.shape
+        M, D, H, Dh = B * N, b.dim, b.heads, b.dim_head
+        tcnd = self._time_cond(t)
+        st = self.stream
+        E = self.buf("bb_E", (M, D), zero=False)
+        h = self.buf("bb_h", (M, D), zero=False)
+        q = self.buf("bb_q", (B, H, N, Dh), zero=False)
+        k = self.buf("bb_k", (B, H, N, Dh), zero=False)
+        v = self.buf("bb_v", (B, H, N, Dh), zero=False)
+        qkv = self.buf("bb_qkv", (M, 3 * D), zero=False)
+        if self.tc:
+            Mp = packing.round_up(M, 128) + 64
+            xc = self.buf("bb_xc", (2 * Din // 8, Mp, 8), torch.bfloat16)
+            act = self.buf("bb_act", (D // 8, Mp, 8), torch.bfloat16)
+            g = self.buf("bb_g", (self.inner_pad // 8, Mp, 8), torch.bfloat16)
+            cs = Mp * 8
+            self._call("fh_to_chunked_bf16", x.data_ptr(), 0, 1, Din, xc.data_ptr(), 0, cs, 0, 1, Din, M, st)
+            if not cond_packed:
+                self._call("fh_to_chunked_bf16", cond.data_ptr(), 0, 1, Din, xc.data_ptr() + (Din // 8) * cs * 2, 0, cs,
+                           0, 1, Din, M, st)
+            L = self.bb_tc
+            rm = lambda ld: (0, 8, ld)  # row-major fp32 output strides (batch, chunk, row)
+            self._tc_conv(L["to_embed"], xc, 0, cs, 0, E, rm(D), 0, 1, M)
+        else:
+            We = sd[FH + "to_embed.weight"]
+            self._sgemm(x, Din, We, 2 * Din, sd[FH + "to_embed.bias"], None, 0, 0.0, 1.0, E, D, M, D, Din)
+            self._sgemm(cond, Din, We.data_ptr() + Din * 4, 2 * Din, None, E, D, 1.0, 1.0, E, D, M, D, Din)
+        wc = sd[FH + "conv_embed.dw_conv1d.0.weight"]
+        self._call("fh_dwconv_gelu_res_f32", E.data_ptr(), wc.data_ptr(), sd[FH + "conv_embed.dw_conv1d.0.bias"].data_ptr(),
+                   h.data_ptr(), B, N, D, wc.shape[-1], st)
+        for l in range(b.depth):
+            p = FH + f"transformer.layers.{l}."
+            if self.tc:
+                self._call("fh_rmsnorm_f32", h.data_ptr(), tcnd[(l, 2, "gamma")].data_ptr(), tcnd[(l, 2, "beta")].data_ptr(),
+                           act.data_ptr(), 1, Mp, M, D, st)
+                self._tc_conv(L[f"qkv{l}"], act, 0, cs, 0, qkv, rm(3 * D), 0, 1, M)
+            else:
+                a = self.buf("bb_a", (M, D), zero=False)
+                self._call("fh_rmsnorm_f32", h.data_ptr(), tcnd[(l, 2, "gamma")].data_ptr(), tcnd[(l, 2, "beta")].data_ptr(),
+                           a.data_ptr(), 0, 0, M, D, st)
+                self._sgemm(a, D, sd[p + "3.to_qkv.weight"], D, None, None, 0, 0.0, 1.0, qkv, 3 * D, M, 3 * D, D)
+            self._call("fh_qknorm_rope_f32", qkv.data_ptr(), sd[p + "3.q_norm.gamma"].data_ptr(),
+                       sd[p + "3.k_norm.gamma"].data_ptr(), sd[FH + "transformer.rotary_emb.inv_freq"].data_ptr(),
+                       q.data_ptr(), k.data_ptr(), v.data_ptr(), B, N, H, Dh, st)
+            if self.tc:
+                self._call("fh_attention_f32", q.data_ptr(), k.data_ptr(), v.data_ptr(), act.data_ptr(), 1, Mp, B, H, N, Dh,
+                           float(b.qk_norm_scale), st)
+                self._tc_conv(L[f"out{l}"], act, 0, cs, 0, h, rm(D), 0, 1, M, res=h, res_strides=rm(D), beta=1.0)
+                self._call("fh_rmsnorm_f32", h.data_ptr(), tcnd[(l, 4, "gamma")].data_ptr(), tcnd[(l, 4, "beta")].data_ptr(),
+                           act.data_ptr(), 1, Mp, M, D, st)
+                self._tc_conv(L[f"ff1{l}"], act, 0, cs, 0, g, (0, cs, 8), 1, 1, M, geglu=1)
+                self._tc_conv(L[f"ff2{l}"], g, 0, cs, 0, h, rm(D), 0, 1, M, res=h, res_strides=rm(D), beta=1.0)
+            else:
+                o = self.buf("bb_o", (M, D), zero=False)
+                self._call("fh_attention_f32", q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), 0, 0, B, H, N, Dh,
+                           float(b.qk_norm_scale), st)
+                self._sgemm(o, D, sd[p + "3.to_out.weight"], D, None, h, D, 1.0, 1.0, h, D, M, D, D)
+                f = self.buf("bb_a", (M, D), zero=False)
+                self._call("fh_rmsnorm_f32", h.data_ptr(), tcnd[(l, 4, "gamma")].data_ptr(), tcnd[(l, 4, "beta")].data_ptr(),
+                           f.data_ptr(), 0, 0, M, D, st)
+                u = self.buf("bb_u", (M, 2 * self.inner), zero=False)
+                self._sgemm(f, D, sd[p + "5.0.weight"], D, sd[p + "5.0.bias"], None, 0, 0.0, 1.0, u, 2 * self.inner, M,
+                            2 * self.inner, D)
+                gg = self.buf("bb_gg", (M, self.inner), zero=False)
+                self._call("fh_geglu_f32", u.data_ptr(), gg.data_ptr(), 0, 0, M, self.inner, self.inner, st)
+                self._sgemm(gg, self.inner, sd[p + "5.3.weight"], self.inner, sd[p + "5.3.bias"], h, D, 1.0, 1.0, h, D, M,
+                            D, self.inner)
+        gam = sd[FH + "transformer.final_norm.gamma"]
+        if self.tc:
+            self._call("fh_rmsnorm_f32", h.data_ptr(), gam.data_ptr(), None, act.data_ptr(), 1, Mp, M, D, st)
+            self._tc_conv(L["to_pred"], act, 0, cs, 0, out, rm(Din), 0, 1, M, res=base, res_strides=rm(Din), alpha=coef,
+                          beta=1.0)
+        else:
+            a = self.buf("bb_a", (M, D), zero=False)
+            self._call("fh_rmsnorm_f32", h.data_ptr(), gam.data_ptr(), None, a.data_ptr(), 0, 0, M, D, st)
+            self._sgemm(a, D, sd[FH + "to_pred.weight"], D, None, base, Din, 1.0, coef, out, Din, M, Din, D)
+
+    def sample_mel(self, cond_mel: torch.Tensor, eps: torch.Tensor, *, steps: int, ode_method: str, cfm_method: str,
+                   sigma: float, cond_scale: float = 1.0) -> torch.Tensor:
+        """CFM sampler (cfm_superresolution.py:162-284 up to `sampled`): prior + fixed-grid ODE."""
+        if cond_scale != 1.0:
+            raise NotImplementedError("classifier-free guidance (cond_scale != 1) is a SURVEY 8f 'next' row")
+        if ode_method not in ("euler", "midpoint"):
+            raise ValueError(f"unsupported ODE method {ode_method!r} (euler|midpoint)")
+        B, N, Din = cond_mel.shape
+        n = cond_mel.numel()
+        y = torch.empty_like(cond_mel)
+        if cfm_method == "basic_cfm":
+            self._call("fh_axpby_f32", eps.data_ptr(), None, 1.0, 0.0, y.data_ptr(), n, self.stream)
+        elif cfm_method in ("independent_cfm_adaptive", "independent_cfm_constant"):
+            # std_1 / std_2 quirk (cfm_superresolution.py:180-183): y0 = cond * 1 + eps * sigma
+            self._call("fh_axpby_f32", cond_mel.data_ptr(), eps.data_ptr(), 1.0, float(sigma), y.data_ptr(), n, self.stream)
+        else:
+            raise NotImplementedError(f"cfm_method {cfm_method!r}: the mel-cutoff splice is a SURVEY 8f 'next' row")
+        tgrid = np.linspace(0.0, 1.0, steps + 1, dtype=np.float32)  # torch.linspace(0,1,steps+1) fp32
+        ymid = torch.empty_like(y) if ode_method == "midpoint" else None
+        packed = False
+        for i in range(steps):
+            t0, t1 = tgrid[i], tgrid[i + 1]
+            dt = np.float32(t1 - t0)
+            if ode_method == "euler":
+                self.vector_field_step(y, cond_mel, float(t0), y, float(dt), y, cond_packed=packed)
+            else:
+                half = np.float32(0.5) * dt
+                self.vector_field_step(y, cond_mel, float(t0), y, float(half), ymid, cond_packed=packed)
+                packed = self.tc
+                self.vector_field_step(ymid, cond_mel, float(np.float32(t0 + half)), y, float(dt), y, cond_packed=packed)
+            packed = self.tc
+        return y
+
+    # ------------------------------------------------------------------ stage: vocoder
+    def vocoder(self, mel: torch.Tensor) -> torch.Tensor:
+        """MelVoco.decode (melvoco.py:114-121): mel [B,N,256] -> wave [B, 480 N]."""
+        return self._vocoder_tc(mel) if self.tc else self._vocoder_f32(mel)
+
+    def _conv_f32(self, rec: _F32Weight, x, out, B, L, res=None, beta=0.0, alpha=1.0, accumulate=0):
+        self._call("fh_conv1d_taps_f32", x.data_ptr(), rec.w.data_ptr(), _ptr(rec.bias), rec.off.data_ptr(), _ptr(res),
+                   beta, alpha, int(accumulate), out.data_ptr(), B, rec.cin, rec.cout, L, rec.ntaps, rec.P, self.stream)
+
+    def _vocoder_f32(self, mel: torch.Tensor) -> torch.Tensor:
+        v, V, st = self.vcfg, self.voc, self.stream
+        B, N, nm = mel.shape
+        melT = self.buf("vf_melT", (B, nm, N), zero=False)
+        self._call("fh_transpose_f32", mel.data_ptr(), melT.data_ptr(), B, N, nm, st)
+        C0 = v.upsample_initial_channel
+        x = self.buf("vf_pre", (B, C0, N), zero=False)
+        self._conv_f32(V["conv_pre"], melT, x, B, N)
+        L = N
+        nk = v.num_kernels
+        for s, u in enumerate(v.upsample_rates):
+            ch = v.stage_channels(s)
+            Lo = L * u
+            X = self.buf(f"vf_X{s}", (B, ch, Lo), zero=False)
+            self._conv_f32(V[f"up{s}"], x, X, B, L)
+            L = Lo
+            XJ = self.buf(f"vf_XJ{s}", (B, ch, L), zero=False)
+            Y = self.buf(f"vf_Y{s}", (B, ch, L), zero=False)
+            A = self.buf(f"vf_A{s}", (B, ch, L), zero=False)
+            XS = self.buf(f"vf_XS{s}", (B, ch, L), zero=False)
+            for j, dil in enumerate(v.resblock_dilation_sizes):
+                cur = X
+                for i in range(len(dil)):
+                    last = i == len(dil) - 1
+                    a1, ib1, f1 = V[f"r{s}.{j}.a1.{i}"]
+                    self._call("fh_snake_aa_f32", cur.data_ptr(), A.data_ptr(), a1.data_ptr(), ib1.data_ptr(), f1.data_ptr(),
+                               B, ch, L, st)
+                    if v.resblock == "1":
+                        self._conv_f32(V[f"r{s}.{j}.c1.{i}"], A, Y, B, L)
+                        a2, ib2, f2 = V[f"r{s}.{j}.a2.{i}"]
+                        self._call("fh_snake_aa_f32", Y.data_ptr(), A.data_ptr(), a2.data_ptr(), ib2.data_ptr(),
+                                   f2.data_ptr(), B, ch, L, st)
+                        conv = V[f"r{s}.{j}.c2.{i}"]
+                    else:
+                        conv = V[f"r{s}.{j}.c1.{i}"]
+                    if last:  # fold the mean over resblocks (models.py:181-187) into the last epilogue
+                        self._conv_f32(conv, A, XS, B, L, res=cur, beta=1.0 / nk, alpha=1.0 / nk, accumulate=j > 0)
+                    else:
+                        self._conv_f32(conv, A, XJ, B, L, res=cur, beta=1.0)
+                        cur = XJ
+            x = XS
+        ch = v.stage_channels(v.num_stages - 1)
+        a, ib, f = V["post_act"]
+        A = self.buf("vf_Apost", (B, ch, L), zero=False)
+        self._call("fh_snake_aa_f32", x.data_ptr(), A.data_ptr(), a.data_ptr(), ib.data_ptr(), f.data_ptr(), B, ch, L, st)
+        wave = torch.empty((B, L), dtype=torch.float32, device=self.device)
+        self._call("fh_convpost_tanh_f32", A.data_ptr(), V["post_w"].data_ptr(), V["post_b"], wave.data_ptr(), B, ch, L, st)
+        return wave
+
+    def _geom(self, C: int, L: int):
+        """chunked geometry: rows per chunk, elements per chunk / batch."""
+        Lp = HALO + packing.round_up(L, 128) + 64
+        cs = Lp * 8
+        return Lp, cs, (C // 8) * cs
+
+    def _cbuf(self, name, B, C, L, dtype):
+        Lp, cs, bs = self._geom(C, L)
+        t = self.buf(name, (B * bs + 4096,), dtype)  # zero-initialised: halos stay zero forever
+        return t, cs, bs
+
+    def _vocoder_tc(self, mel: torch.Tensor) -> torch.Tensor:
+        v, V, st = self.vcfg, self.voc, self.stream
+        B, N, nm = mel.shape
+        bf, f32 = torch.bfloat16, torch.float32
+        melc, mcs, mbs = self._cbuf("vt_mel", B, nm, N, bf)
+        self._call("fh_to_chunked_bf16", mel.data_ptr(), N * nm, 1, nm, melc.data_ptr(), mbs, mcs, HALO, B, nm, N, st)
+        C0 = self.cpad(v.upsample_initial_channel)
+        xb, xcs, xbs = self._cbuf("vt_pre", B, C0, N, bf)
+        self._tc_conv(V["conv_pre"], melc, mbs, mcs, HALO, xb[HALO * 8:], (xbs, xcs, 8), 1, B, N)
+        L = N
+        nk = v.num_kernels
+        a_in, a_cs, a_bs = xb, xcs, xbs
+        for s, u in enumerate(v.upsample_rates):
+            ch = self.cpad(v.stage_channels(s))
+            Lo = L * u
+            X, cs, bs = self._cbuf(f"vt_X{s}", B, ch, Lo, f32)
+            XJ, _, _ = self._cbuf(f"vt_XJ{s}", B, ch, Lo, f32)
+            Y, _, _ = self._cbuf(f"vt_Y{s}", B, ch, Lo, f32)
+            XS, _, _ = self._cbuf(f"vt_XS{s}", B, ch, Lo, f32)
+            A, _, _ = self._cbuf(f"vt_A{s}", B, ch, Lo, bf)
+            o = HALO * 8  # element offset of row t = 0
+            strides = (bs, cs, 8)
+            self._tc_conv(V[f"up{s}"], a_in, a_bs, a_cs, HALO, X[o:], strides, 0, B, L)
+            L = Lo
+            for j, dil in enumerate(v.resblock_dilation_sizes):
+                cur = X
+                for i in range(len(dil)):
+                    last = i == len(dil) - 1
+                    a1, ib1, f1 = V[f"r{s}.{j}.a1.{i}"]
+                    self._call("fh_snake_aa_chunked", cur.data_ptr(), A.data_ptr(), a1.data_ptr(), ib1.data_ptr(),
+                               f1.data_ptr(), bs, cs, HALO, B, ch, L, 1, st)
+                    if v.resblock == "1":
+                        self._tc_conv(V[f"r{s}.{j}.c1.{i}"], A, bs, cs, HALO, Y[o:], strides, 0, B, L)
+                        a2, ib2, f2 = V[f"r{s}.{j}.a2.{i}"]
+                        self._call("fh_snake_aa_chunked", Y.data_ptr(), A.data_ptr(), a2.data_ptr(), ib2.data_ptr(),
+                                   f2.data_ptr(), bs, cs, HALO, B, ch, L, 1, st)
+                        conv = V[f"r{s}.{j}.c2.{i}"]
+                    else:
+                        conv = V[f"r{s}.{j}.c1.{i}"]
+                    if last:
+                        self._tc_conv(conv, A, bs, cs, HALO, XS[o:], strides, 0, B, L, res=cur[o:], res_strides=strides,
+                                      alpha=1.0 / nk, beta=1.0 / nk, accumulate=j > 0)
+                    else:
+                        self._tc_conv(conv, A, bs, cs, HALO, XJ[o:], strides, 0, B, L, res=cur[o:], res_strides=strides,
+                                      beta=1.0)
+                        cur = XJ
+            if s + 1 < v.num_stages:
+                XB, _, _ = self._cbuf(f"vt_XB{s}", B, ch, L, bf)
+                self._call("fh_cast_f32_bf16", XS.data_ptr(), XB.data_ptr(), B * bs, st)
+                a_in, a_cs, a_bs = XB, cs, bs
+        a, ib, f = V["post_act"]
+        AP, _, _ = self._cbuf("vt_AP", B, ch, L, f32)
+        self._call("fh_snake_aa_chunked", XS.data_ptr(), AP.data_ptr(), a.data_ptr(), ib.data_ptr(), f.data_ptr(), bs, cs,
+                   HALO, B, ch, L, 0, st)
+        wave = torch.empty((B, L), dtype=torch.float32, device=self.device)
+        self._call("fh_convpost_tanh_chunked", AP.data_ptr(), bs, cs, HALO, V["post_w"].data_ptr(), V["post_b"],
+                   wave.data_ptr(), B, ch, L, st)
+        return wave
+
+    # ------------------------------------------------------------------ stage: post-processing
+    def postprocess(self, pred: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
+        """PostProcessing.post_processing (postprocessing.py:18-41) per clip: pred [B,Tp], src [B,T] -> [B,T]."""
+        B, T = src.shape
+        Tp = pred.shape[1]
+        NT, NTp = 1 + T // 480, 1 + Tp // 480
+        nt = min(NT, NTp)
+        st = self.stream
+        sp = self.buf("pp_sp", (B, NTp, 1025, 2), zero=False)
+        ss = self.buf("pp_ss", (B, NT, 1025, 2), zero=False)
+        en = self.buf("pp_en", (B, 1025), zero=False)
+        cut = self.buf("pp_cut", (B,), torch.int32)
+        self._call("fh_stft_center_f32", pred.data_ptr(), sp.data_ptr(), None, self.window.data_ptr(),
+                   self.twiddle.data_ptr(), B, Tp, NTp, st)
+        self._call("fh_stft_center_f32", src.data_ptr(), ss.data_ptr(), en.data_ptr(), self.window.data_ptr(),
+                   self.twiddle.data_ptr(), B, T, NT, st)
+        self._call("fh_pp_cutoff", en.data_ptr(), cut.data_ptr(), B, 0.99, st)
+        if NT != NTp:
+            raise ValueError("post-processing expects pred and src to span the same number of STFT frames")
+        frames = self.buf("pp_fr", (B, nt, 2048), zero=False)
+        self._call("fh_pp_splice_istft_f32", sp.data_ptr(), ss.data_ptr(), cut.data_ptr(), frames.data_ptr(),
+                   self.window.data_ptr(), self.twiddle.data_ptr(), B, nt, st)
+        y = self.buf("pp_y", (B, T), zero=False)
+        absmax = self.buf("pp_absmax", (B,), torch.int32)
+        self._call("fh_fill_u32", absmax.data_ptr(), 0, B, st)
+        self._call("fh_pp_overlap_add_f32", frames.data_ptr(), y.data_ptr(), self.window.data_ptr(), absmax.data_ptr(), B,
+                   nt, T, st)
+        out = torch.empty((B, T), dtype=torch.float32, device=self.device)
+        self._call("fh_scale_by_absmax_f32", y.data_ptr(), out.data_ptr(), absmax.data_ptr(), 0.99, B, T, st)
+        return out

@@ -1,0 +1,316 @@
+"""Drop-in Python surface of the reference (`from flowhigh import FlowHighSR`).
+
+Mirrors src/flowhigh/flowhighsr.py:21-149 (constructor knobs, `from_local`, `from_pretrained`,
+`generate`, `set_cfm_method`), cfm_superresolution.py:95-131,162-175 (`sample`, `load`, `device`)
+and the sub-module call surface used for per-stage checks (`model.flowhigh.audio_enc_dec.encode /
+.decode`, `model.flowhigh.forward_with_cond_scale`, `model.postproc.post_processing`).  The classes
+are `nn.Module`s only as parameter containers: `state_dict()` / `load_state_dict()` use the
+reference's exact key layout (flowhigh_b200/weights.py), while every computation goes to the CUDA
+kernels through flowhigh_b200.engine.Engine.  There is no CPU path.
+
+Reference quirks kept on purpose: `from_local` builds the wrapper with the
+constructor defaults (basic_cfm + midpoint + sigma 0); the adaptive/constant prior is
+`cond + sigma * eps` whatever `std_2` is passed; `audio.max() > 1` triggers the /32768 scaling;
+an unknown `cfm_method` passed to `sample` silently falls back to `self.cfm_method`.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Dict, List, Optional, Sequence, Union
+
+import numpy as np
+import torch
+from torch import nn
+
+from .config import BackboneConfig, CFM_METHODS, VocoderConfig
+from .engine import Engine
+from .weights import FH, VOC, fold_weight_norm, random_state_dict, state_dict_spec
+
+REPO_ID = "ResembleAI/FlowHigh"
+
+
+class _Tree(nn.Module):
+    """Parameter container that reproduces a dotted state_dict key layout."""
+
+    def _put(self, path: List[str], tensor: torch.Tensor, as_buffer: bool):
+        if len(path) == 1:
+            if as_buffer:
+                self.register_buffer(path[0], tensor)
+            else:
+                self.register_parameter(path[0], nn.Parameter(tensor, requires_grad=False))
+            return
+        child = self._modules.get(path[0])
+        if child is None:
+            child = _Tree()
+            self.add_module(path[0], child)
+        child._put(path[1:], tensor, as_buffer)
+
+
+def _is_buffer(key: str) -> bool:
+    return key.endswith(".filter") or key.endswith("inv_freq")
+
+
+class MelVoco(_Tree):
+    """models/melvoco.py:16-46: log-mel encoder + BigVGAN decoder (parameters under `.vocoder`)."""
+
+    def __init__(self, *, vocoder_config: Union[str, Path, VocoderConfig, None] = None, vocoder_path=None,
+                 n_mels=256, sampling_rate=48000, f_max=24000, f_min=20, n_fft=2048, win_length=2048, hop_length=480,
+                 vocoder="bigvgan", log=True):
+        super().__init__()
+        if vocoder != "bigvgan":
+            raise ValueError("unsuitable vocoder name")
+        if (n_mels, sampling_rate, f_max, f_min, n_fft, win_length, hop_length) != (256, 48000, 24000, 20, 2048, 2048, 480):
+            raise ValueError("the B200 front-end kernels are specialised for the 48 kHz / 2048 / 480 / 256-mel setup")
+        if isinstance(vocoder_config, VocoderConfig):
+            self.vcfg = vocoder_config
+        elif vocoder_config is None:
+            self.vcfg = VocoderConfig.assumed_48k()
+        else:
+            self.vcfg = VocoderConfig.from_json(vocoder_config)
+        self.vcfg.validate()
+        self.n_mels, self.n_fft, self.hop_length, self.win_length = n_mels, n_fft, hop_length, win_length
+        self.sampling_rate, self.f_min, self.f_max = sampling_rate, f_min, f_max
+        self._pending_generator = None
+        if vocoder_path is not None:  # init_vocoder.py:14-17: load ['generator'], fold weight norm
+            ckpt = torch.load(str(vocoder_path), map_location="cpu")
+            self._pending_generator = fold_weight_norm(ckpt["generator"])
+        self._owner = None
+
+    @property
+    def latent_dim(self):
+        return self.n_mels
+
+    def encode(self, audio: torch.Tensor) -> torch.Tensor:
+        return self._owner()._engine().encode(audio.to(self._owner().device, torch.float32).contiguous())
+
+    def decode(self, mel: torch.Tensor) -> torch.Tensor:
+        eng = self._owner()._engine()
+        return eng.vocoder(mel.to(eng.device, torch.float32).contiguous()).unsqueeze(1)
+
+
+class FLowHigh(_Tree):
+    """models/flow.py:55-142 (transformer architecture only; convnext is a SURVEY 8f row)."""
+
+    def __init__(self, *, audio_enc_dec: Optional[MelVoco] = None, dim_in=None, dim=1024, depth=24, dim_head=64,
+                 heads=16, ff_mult=4, conv_pos_embed_kernel_size=31, attn_qk_norm=True, architecture="transformer",
+                 **unused):
+        super().__init__()
+        if architecture != "transformer":
+            raise NotImplementedError("architecture='convnext' is not part of the accelerated path")
+        if not attn_qk_norm:
+            raise NotImplementedError("the attention kernels implement the qk-norm variant the checkpoint uses")
+        if audio_enc_dec is None:
+            raise ValueError("audio_enc_dec (MelVoco) is required")
+        dim_in = dim if dim_in is None else dim_in
+        self.bcfg = BackboneConfig(dim_in=dim_in, dim=dim, depth=depth, heads=heads, dim_head=dim_head,
+                                   ff_mult=ff_mult, conv_pos_kernel=conv_pos_embed_kernel_size)
+        if (dim_in, dim, heads, dim_head) != (256, 1024, 16, 64):
+            raise ValueError("kernels are specialised for dim_in 256, dim 1024, 16 heads x 64")
+        self.audio_enc_dec = audio_enc_dec
+        self._owner = None
+
+    def forward_with_cond_scale(self, x, *, times, cond, cond_scale=1.0, cond_mask=None, self_attn_mask=None):
+        """flow.py:165-178: returns the vector field v(times, x | cond)."""
+        if cond_scale != 1.0:
+            raise NotImplementedError("cond_scale != 1 (classifier-free guidance) is a SURVEY 8f 'next' row")
+        eng = self._owner()._engine()
+        x = x.to(eng.device, torch.float32).contiguous()
+        cond = cond.to(eng.device, torch.float32).contiguous()
+        zero = torch.zeros_like(x)
+        out = torch.empty_like(x)
+        eng.vector_field_step(x, cond, float(times), zero, 1.0, out)
+        return out
+
+    forward = forward_with_cond_scale
+
+
+class PostProcessing:
+    """postprocessing.py:5-41."""
+
+    def __init__(self, owner):
+        self._owner = owner
+
+    def post_processing(self, pred: torch.Tensor, src: torch.Tensor, length: int) -> torch.Tensor:
+        assert pred.dim() == 2 and src.dim() == 2
+        if length != src.shape[-1]:
+            raise ValueError("length must equal src.size(-1) (the only way the reference calls it)")
+        eng = self._owner()._engine()
+        return eng.postprocess(pred.to(eng.device, torch.float32).contiguous(), src.to(eng.device, torch.float32).contiguous())
+
+
+class FlowHighSR(nn.Module):
+    def __init__(self, flowhigh: FLowHigh, sigma=0.0, ode_atol=1e-5, ode_rtol=1e-5, use_torchode=False,
+                 cfm_method="basic_cfm", torchdiffeq_ode_method="midpoint", torchode_method_klass=None,
+                 cond_drop_prob=0.0, upsampling_method="scipy", precision: str = "bf16"):
+        super().__init__()
+        if use_torchode:
+            raise NotImplementedError("adaptive-step torchode sampling is a SURVEY 8f 'next' row")
+        self.sigma = sigma
+        self.flowhigh = flowhigh
+        self.cond_drop_prob = cond_drop_prob
+        self.use_torchode = use_torchode
+        self.cfm_method = cfm_method
+        self.odeint_kwargs = dict(atol=ode_atol, rtol=ode_rtol, method=torchdiffeq_ode_method)
+        self.upsampling_method = upsampling_method
+        self.precision = precision
+        self._eng: Optional[Engine] = None
+        import weakref
+        ref = weakref.ref(self)
+        flowhigh._owner = ref
+        flowhigh.audio_enc_dec._owner = ref
+        self.postproc = PostProcessing(ref)
+        # parameters: random init of the named architecture until a checkpoint is loaded
+        vcfg, bcfg = flowhigh.audio_enc_dec.vcfg, flowhigh.bcfg
+        init = random_state_dict(bcfg, vcfg, seed=0, vocoder_gain=0.7)
+        pend = flowhigh.audio_enc_dec._pending_generator
+        if pend is not None:
+            for k, v in pend.items():
+                init[VOC + k] = v.float()
+        for key, t in init.items():
+            path = key.split(".")
+            assert path[0] == "flowhigh"
+            flowhigh._put(path[1:], t.clone(), _is_buffer(key))
+
+    # ------------------------------------------------------------------ nn.Module protocol
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def _apply(self, fn, *a, **k):
+        self._eng = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **kw):
+        self._eng = None
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    def load(self, path, strict=True):
+        path = Path(path)
+        assert path.exists()
+        pkg = torch.load(str(path), map_location="cpu")
+        self.load_state_dict(pkg["model"], strict=strict)
+        return pkg
+
+    def _engine(self) -> Engine:
+        if self._eng is None:
+            dev = self.device
+            if dev.type != "cuda":
+                raise RuntimeError("FlowHighSR (B200) needs its parameters on a CUDA device: call .cuda() / .to('cuda')")
+            self._eng = Engine(self.state_dict(), self.flowhigh.audio_enc_dec.vcfg, self.flowhigh.bcfg, device=dev,
+                               precision=self.precision)
+        return self._eng
+
+    def set_precision(self, precision: str):
+        self.precision = precision
+        self._eng = None
+
+    # ------------------------------------------------------------------ reference API
+    def set_cfm_method(self, cfm_method):
+        self.cfm_method = cfm_method
+
+    def _noise_like(self, cond_mel: torch.Tensor, eps: Optional[torch.Tensor]) -> torch.Tensor:
+        if eps is not None:
+            return eps.to(cond_mel.device, torch.float32).reshape(cond_mel.shape).contiguous()
+        return torch.randn_like(cond_mel)  # same draw the reference makes (cfm_superresolution.py:220)
+
+    @torch.inference_mode()
+    def sample(self, *, cond=None, cond_mask=None, time_steps=4, cond_scale=1.0, decode_to_audio=True, std_1=None,
+               std_2=None, mel_pp=False, cfm_method=None, eps: Optional[torch.Tensor] = None):
+        if cfm_method not in CFM_METHODS:
+            cfm_method = self.cfm_method
+        if mel_pp:
+            raise NotImplementedError("mel_pp (mel-domain low-band replacement) is a SURVEY 8f 'next' row")
+        eng = self._engine()
+        cond = cond.to(eng.device, torch.float32).contiguous()
+        is_audio = cond.dim() == 2 or (cond.dim() == 3 and cond.shape[1] == 1)
+        if is_audio:
+            cond = eng.encode(cond.reshape(cond.shape[0], -1))
+        mel = eng.sample_mel(cond, self._noise_like(cond, eps), steps=int(time_steps),
+                             ode_method=self.odeint_kwargs["method"], cfm_method=cfm_method, sigma=float(self.sigma),
+                             cond_scale=float(cond_scale))
+        if not decode_to_audio:
+            return mel
+        return eng.vocoder(mel).unsqueeze(1)
+
+    def _prep_input(self, audio) -> np.ndarray:
+        if isinstance(audio, torch.Tensor):
+            audio = audio.detach().cpu().numpy()
+        audio = np.asarray(audio)
+        if audio.ndim == 2:
+            audio = audio.squeeze(0)
+        if audio.max() > 1:  # flowhighsr.py:62-63 (any dtype)
+            audio = audio / 32768.0
+        return np.ascontiguousarray(audio, dtype=np.float32)
+
+    @torch.no_grad()
+    def generate(self, audio, sr: int, target_sampling_rate=48000, timestep=1, eps: Optional[torch.Tensor] = None):
+        """flowhighsr.py:51-102: one clip in, `[1, T]` fp32 tensor on the model device out."""
+        out = self.generate_batch([audio], sr, target_sampling_rate, timestep, eps=None if eps is None else [eps])
+        return out[0]
+
+    @torch.no_grad()
+    def generate_batch(self, audios: Sequence, sr: Union[int, Sequence[int]], target_sampling_rate=48000, timestep=1,
+                       eps: Optional[Sequence[torch.Tensor]] = None, pinned: bool = False) -> List[torch.Tensor]:
+        """Batched `generate`: every clip is processed exactly as the reference processes it alone
+        (per-clip peak normalisation, attention, cutoff and output normalisation).
+        Clips sharing (sr, length) run as one batch through every kernel."""
+        if self.upsampling_method != "scipy":
+            raise NotImplementedError("upsampling_method='librosa' (soxr_hq) is a SURVEY 8f 'next' row")
+        eng = self._engine()
+        srs = [sr] * len(audios) if isinstance(sr, int) else list(sr)
+        prepped = [self._prep_input(a) for a in audios]
+        groups: Dict[tuple, List[int]] = {}
+        for i, (a, s) in enumerate(zip(prepped, srs)):
+            groups.setdefault((int(s), a.shape[0]), []).append(i)
+        results: List[Optional[torch.Tensor]] = [None] * len(audios)
+        for (s, n), idxs in groups.items():
+            host = torch.from_numpy(np.stack([prepped[i] for i in idxs]))
+            if pinned:
+                host = host.pin_memory()
+            x = host.to(eng.device, non_blocking=True)
+            cond = eng.resample_normalise(x, s, target_sampling_rate)
+            cond_mel = eng.encode(cond)
+            e = None if eps is None else torch.cat([eps[i].reshape(1, *cond_mel.shape[1:]) for i in idxs]).to(eng.device)
+            mel = eng.sample_mel(cond_mel, self._noise_like(cond_mel, e), steps=int(timestep),
+                                 ode_method=self.odeint_kwargs["method"], cfm_method=self.cfm_method,
+                                 sigma=float(self.sigma))
+            wave = eng.vocoder(mel)
+            out = eng.postprocess(wave, cond)
+            for j, i in enumerate(idxs):
+                results[i] = out[j: j + 1]
+        return results  # type: ignore[return-value]
+
+    # ------------------------------------------------------------------ loaders
+    @classmethod
+    def from_local(cls, ckpt_dir, device="cuda", precision: str = "bf16") -> "FlowHighSR":
+        """flowhighsr.py:109-137: expects bigvgan_48khz_256band.{json,pt} and FLowHigh_basic_400k.pt."""
+        ckpt_dir = Path(ckpt_dir)
+        voc = MelVoco(vocoder_config=ckpt_dir / "bigvgan_48khz_256band.json",
+                      vocoder_path=ckpt_dir / "bigvgan_48khz_256band.pt")
+        net = FLowHigh(dim_in=voc.n_mels, audio_enc_dec=voc, depth=2)
+        model = cls(flowhigh=net, precision=precision)  # defaults: basic_cfm / midpoint / sigma 0 (F4)
+        ckpt = torch.load(ckpt_dir / "FLowHigh_basic_400k.pt", map_location="cpu")
+        model.load_state_dict(ckpt["model"])
+        return model.to(device).eval()
+
+    @classmethod
+    def from_pretrained(cls, device="cuda", precision: str = "bf16") -> "FlowHighSR":
+        """flowhighsr.py:139-149 (needs network access to the HF hub)."""
+        from huggingface_hub import hf_hub_download
+        local_path = None
+        for fpath in ["FLowHigh_basic_400k.json", "bigvgan_48khz_256band.json", "FLowHigh_basic_400k.pt",
+                      "bigvgan_48khz_256band.pt"]:
+            local_path = hf_hub_download(repo_id=REPO_ID, filename=fpath)
+        return cls.from_local(Path(local_path).parent, device, precision=precision)
+
+    @classmethod
+    def from_random(cls, vcfg: Optional[VocoderConfig] = None, device="cuda", seed: int = 0, precision: str = "bf16",
+                    vocoder_gain: float = 0.7, depth: int = 2, **kw) -> "FlowHighSR":
+        """Random-init weights of the named architecture (no checkpoints offline)."""
+        vcfg = vcfg or VocoderConfig.assumed_48k()
+        voc = MelVoco(vocoder_config=vcfg)
+        net = FLowHigh(dim_in=voc.n_mels, audio_enc_dec=voc, depth=depth)
+        model = cls(flowhigh=net, precision=precision, **kw)
+        model.load_state_dict(random_state_dict(net.bcfg, vcfg, seed=seed, vocoder_gain=vocoder_gain))
+        return model.to(device).eval()

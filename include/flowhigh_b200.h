@@ -1,0 +1,181 @@
+/* flowhigh_b200 -- C ABI of the B200-native FLowHigh inference kernels (sm_100a).
+ *
+ * The reference (resemble-ai/flowhigh) has no FFI / plugin interface: its hot path is pure
+ * PyTorch.  The drop-in boundary is therefore the Python class API (flowhigh_b200.FlowHighSR
+ * mirrors src/flowhigh/flowhighsr.py:21-149); THIS header is the boundary underneath it, the
+ * set of entry points the Python host code binds with ctypes (flowhigh_b200/_lib.py), and the
+ * ones a maintainer of the reference would bind to replace the cited torch/scipy calls
+ * (INTEGRATION.md shows the ctypes stubs).
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE address (tensor.data_ptr()); the caller owns every buffer,
+ *     including workspaces; no entry point allocates or synchronises.
+ *   - `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ *   - return value: 0 = ok, negative = FH_ERR_*; fh_last_error_string() gives the reason
+ *     (thread-local).  There is no CPU fallback anywhere.
+ *   - fp32 tensors use the reference's layouts; "chunked" tensors are [rows-of-8-channels]:
+ *     element (t, c) of a [L, C] activation lives at ((c/8) * Lp + t) * 8 + c%8, i.e. the
+ *     tcgen05 no-swizzle K-major core-matrix layout, so an implicit-GEMM tap is a row shift.
+ */
+#ifndef FLOWHIGH_B200_H
+#define FLOWHIGH_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FH_OK 0
+#define FH_ERR_BAD_SHAPE (-1)
+#define FH_ERR_BAD_ALIGN (-2)
+#define FH_ERR_UNSUPPORTED_CFG (-3)
+#define FH_ERR_CUDA (-4)
+
+int fh_version(void);
+const char* fh_last_error_string(void);
+/* number of kernel launches issued through this library by the calling process */
+int64_t fh_launch_count(void);
+
+/* ---------------------------------------------------------------- resampler + peak normalise
+ * replaces scipy.signal.resample_poly + `cond /= max|cond|`   flowhighsr.py:68-69
+ *   y[b,m] = sum_i x[b,i] * h[(m + n_pre_remove)*down - n_pre_pad - i*up]
+ * absmax[b] (may be NULL) receives max|y[b,:]| via atomicMax on the fp32 bit pattern; it must be
+ * zeroed by the caller (fh_fill_f32). */
+int fh_resample_poly_f32(const float* x, float* y, const float* h, uint32_t* absmax_bits,
+                         int B, int T_in, int T_out, int ntaps, int up, int down,
+                         int n_pre_pad, int n_pre_remove, void* stream);
+/* y[b,:] = x[b,:] / absmax[b] * scale   (true division, like numpy / torch) */
+int fh_scale_by_absmax_f32(const float* x, float* y, const uint32_t* absmax_bits, float scale,
+                           int B, int T, void* stream);
+int fh_absmax_f32(const float* x, uint32_t* absmax_bits, int B, int T, void* stream);
+int fh_fill_u32(uint32_t* p, uint32_t v, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- log-mel front end
+ * replaces MelVoco.encode   models/melvoco.py:56-86  (+ librosa.filters.mel, modules.py:31-36)
+ *   audio [B,T] fp32 -> mel [B,N,256] fp32,  N = T/480 (T >= 785)
+ * window [2048] fp32; twiddle [1024] float2 = exp(-2 pi i k / 2048); sparse mel filterbank:
+ * mel_start[256] (first bin), mel_len[256], mel_w [256*mel_stride] fp32.
+ * precise != 0 runs the FFT in fp64 (fp32-parity path: the reference's own fp32 noise floor in
+ * the empty bands is at the tolerance). */
+int fh_stft_logmel_f32(const float* audio, float* mel, const float* window, const float* twiddle,
+                       const int* mel_start, const int* mel_len, const float* mel_w, int mel_stride,
+                       int B, int T, int N, int precise, void* stream);
+
+/* ---------------------------------------------------------------- post-processing
+ * replaces PostProcessing.post_processing   postprocessing.py:18-41
+ * fh_stft_center: complex STFT (n_fft = win = 2048, hop 480, periodic Hann, center, ZERO pad):
+ *   x [B,T] -> spec [B, NT, 1025] float2, NT = 1 + T/480; energy (may be NULL) [B,1025] gets
+ *   sum_t |S[f,t]| accumulated with atomics (caller zeroes it). */
+int fh_stft_center_f32(const float* x, float* spec, float* energy, const float* window,
+                       const float* twiddle, int B, int T, int NT, void* stream);
+/* cutoff[b] = postprocessing.py:10-16 applied to energy[b,:] (cumsum, 0.99 threshold) */
+int fh_pp_cutoff(const float* energy, int* cutoff, int B, float threshold, void* stream);
+/* frames [B,NT,2048] = window * irfft(f < cutoff[b] ? spec_src : spec_pred) */
+int fh_pp_splice_istft_f32(const float* spec_pred, const float* spec_src, const int* cutoff,
+                           float* frames, const float* window, const float* twiddle,
+                           int B, int NT, void* stream);
+/* y[b,t] = OLA(frames)[t+1024] / OLA(window^2)[t+1024] for t < length (torch.istft semantics) */
+int fh_pp_overlap_add_f32(const float* frames, float* y, const float* window, uint32_t* absmax_bits,
+                          int B, int NT, int length, void* stream);
+
+/* ---------------------------------------------------------------- backbone, fp32 path
+ * out[M,N] (ldc) = alpha * (A[M,K](lda) . W[N,K](ldw)^T + bias[N]) + beta_res * res[M,N](ldr)
+ * replaces nn.Linear at flow.py:239,261; attend.py:176,189; transformer.py:100-103.
+ * With alpha = dt, res = y this is the fused Euler / midpoint CFM update of
+ * torchdiffeq.odeint (cfm_superresolution.py:243). */
+int fh_sgemm_nt_f32(const float* A, int lda, const float* W, int ldw, const float* bias,
+                    const float* res, int ldr, float beta_res, float alpha,
+                    float* out, int ldc, int M, int N, int K, void* stream);
+/* out[N] = act(W[N,K] . x[K] + b[N]);  act: 0 none, 1 SiLU  (flow.py:92-96, transformer.py:85) */
+int fh_gemv_f32(const float* W, const float* x, const float* b, float* out, int N, int K, int act,
+                void* stream);
+/* out[2*half] = [sin(2 pi t w), cos(2 pi t w)]     pos_emb.py:22-26 */
+int fh_sincos_embed_f32(const float* w, float t, float* out, int half, void* stream);
+/* out = E + gelu(dwconv_k(E) + b) over time, E [B,N,C], w [C,k]   transformer.py:33-46, flow.py:240 */
+int fh_dwconv_gelu_res_f32(const float* E, const float* w, const float* b, float* out,
+                           int B, int N, int C, int k, void* stream);
+/* out = x / max(||x||,1e-12) * sqrt(C) * gamma + beta (beta may be NULL)   transformer.py:49-59,82-88
+ * out_mode 0: fp32 row-major [M,C];  1: bf16 chunked [C/8][Mp][8] (row pitch out_rows). */
+int fh_rmsnorm_f32(const float* x, const float* gamma, const float* beta, void* out, int out_mode,
+                   int64_t out_rows, int M, int C, void* stream);
+/* qkv [B*N, 3*H*D] -> q,k,v [B,H,N,D]; q,k: l2norm * gamma[h,d] * sqrt(D), rotary (halves)
+ * attend.py:144-151,179-184; pos_emb.py:45-60 */
+int fh_qknorm_rope_f32(const float* qkv, const float* qg, const float* kg, const float* inv_freq,
+                       float* q, float* k, float* v, int B, int N, int H, int D, void* stream);
+/* out[B*N, H*D] = softmax(scale q k^T) v   attend.py:123-137 (no mask)
+ * out_mode as in fh_rmsnorm_f32. */
+int fh_attention_f32(const float* q, const float* k, const float* v, void* out, int out_mode,
+                     int64_t out_rows, int B, int H, int N, int D, float scale, void* stream);
+/* g[M,inner] = gelu(u[M, inner + i]) * u[M, i]    transformer.py:92-95 */
+int fh_geglu_f32(const float* u, void* g, int out_mode, int64_t out_rows, int M, int inner, int inner_pad,
+                 void* stream);
+/* y = a*x + b*z  elementwise (prior: y0 = cond + sigma*eps, cfm_superresolution.py:222-230) */
+int fh_axpby_f32(const float* x, const float* z, float a, float b, float* y, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- vocoder, fp32 path  [B,C,L]
+ * Generic tapped convolution: for phase p in [0,P):
+ *   out[b, co, P*t + p] = alpha * ( bias[co] + sum_m sum_ci w[p][co][ci][m] * x[b, ci, t + off[p][m]] )
+ *                         + beta_res * res[b,co,P*t+p] + (accumulate ? out : 0)
+ * P = 1: Conv1d with dilation (bigvgan/models.py:27-43) ; P = stride: ConvTranspose1d polyphase
+ * (models.py:140-146).  x is zero outside [0,L).  w [P][Cout][Cin][ntaps], off [P][ntaps]. */
+int fh_conv1d_taps_f32(const float* x, const float* w, const float* bias, const int* off,
+                       const float* res, float beta_res, float alpha, int accumulate, float* out,
+                       int B, int Cin, int Cout, int L, int ntaps, int P, void* stream);
+/* anti-aliased Snake / SnakeBeta: Activation1d.forward  alias_free_torch/act.py:23-28
+ * x [B,C,L] -> y [B,C,L]; a = alpha (exp'd if logscale), inv_b = 1/(beta+1e-9) per channel. */
+int fh_snake_aa_f32(const float* x, float* y, const float* a, const float* inv_b, const float* filt,
+                    int B, int C, int L, void* stream);
+/* y[b,t] = tanh(bias + sum_ci sum_j w[ci,j] x[b,ci,t+j-3])   models.py:190-192 */
+int fh_convpost_tanh_f32(const float* x, const float* w, float bias, float* y, int B, int C, int L,
+                         void* stream);
+/* [B,R,C] -> [B,C,R]  (the `b n d -> b d n` rearrange at melvoco.py:115) */
+int fh_transpose_f32(const float* src, float* dst, int B, int R, int C, void* stream);
+/* elementwise fp32 -> bf16 (whole chunked buffers, halos included) */
+int fh_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------- tensor-core path (tcgen05)
+ * Implicit-GEMM tapped convolution on chunked operands, bf16 x bf16 -> fp32 in TMEM.
+ *   A: activations, chunked bf16 [B][Cin/8][Lp_a][8] with >= halo zero rows each side of [0,L)
+ *   W: packed by fh_tc_pack_* (host side, flowhigh_b200/packing.py) into the smem image
+ *   out(t, n) at out + b*out_batch + (n/8)*out_chunk + (P*t+p)*out_row + n%8, fp32 or bf16
+ * A Linear layer is the k = 1 case with L = number of tokens. */
+typedef struct {
+  const void* a;          /* chunked bf16 activations */
+  int64_t a_batch;        /* elements between batches */
+  int64_t a_chunk;        /* elements between 8-channel chunks (= Lp_a * 8) */
+  int a_row0;             /* row index of t = 0 inside a chunk (left halo) */
+  const void* w;          /* packed weights */
+  const float* bias;      /* [Cout] or NULL */
+  const void* res;        /* residual, addressed like out (res_is_bf16 selects type) or NULL */
+  void* out;
+  int64_t out_batch, out_chunk, out_row;
+  int64_t res_batch, res_chunk, res_row;
+  int out_is_bf16, res_is_bf16;
+  float alpha, beta_res;
+  int accumulate;         /* out += ... (fp32 out only) */
+  int geglu;              /* epilogue pairs columns (2i, 2i+1) -> gelu(col 2i+1) * col 2i */
+  int B, L, Cin, Cout;    /* Cin multiple of 16, Cout multiple of 8 */
+  int ntaps, P;           /* taps per phase, phases (output stride) */
+  const int* tap_off;     /* HOST pointer [P][ntaps] row offsets */
+  int bn;                 /* N tile, multiple of 16, <= 256 */
+} fh_tc_conv_args;
+int fh_tc_conv_bf16(const fh_tc_conv_args* args, void* stream);
+/* bytes of the packed weight image for given shape (host helper, no GPU work) */
+int64_t fh_tc_packed_weight_bytes(int Cin, int Cout, int ntaps, int P, int bn);
+
+/* fp32 [B,C,L] planar or [M,C] row-major -> chunked bf16; src strides in elements */
+int fh_to_chunked_bf16(const float* src, int64_t src_batch, int64_t src_c, int64_t src_t,
+                       void* dst, int64_t dst_batch, int64_t dst_chunk, int dst_row0,
+                       int B, int C, int L, void* stream);
+/* chunked anti-aliased snake: x chunked fp32 -> y chunked bf16 (same geometry) */
+int fh_snake_aa_chunked(const float* x, void* y, const float* a, const float* inv_b, const float* filt,
+                        int64_t batch_stride, int64_t chunk_stride, int row0, int B, int C, int L,
+                        int out_is_bf16, void* stream);
+int fh_convpost_tanh_chunked(const float* x, int64_t batch_stride, int64_t chunk_stride, int row0,
+                             const float* w, float bias, float* y, int B, int C, int L, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLOWHIGH_B200_H */

@@ -1,0 +1,310 @@
+"""GPU parity tests (run with -m gpu on a B200): every CUDA stage, called through the C ABI via the
+engine, against the oracle restatement on the same seeded inputs and against the committed
+reference golden vectors."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from flowhigh_b200 import FlowHighSR, VocoderConfig, packing
+from flowhigh_b200.config import BackboneConfig
+from flowhigh_b200.engine import Engine, HALO
+from flowhigh_b200.synth import synth_speech
+from flowhigh_b200.weights import random_state_dict
+from oracle import dsp, model, pipeline
+from util import golden_weights, load_golden, lsd_db, snr_db
+
+pytestmark = pytest.mark.gpu
+
+_ENG = {}
+
+
+def engine(name, precision):
+    key = (name, precision)
+    if key not in _ENG:
+        g = load_golden(name)
+        sd, vcfg = golden_weights(g)
+        _ENG[key] = (Engine(sd, vcfg, device="cuda:0", precision=precision), sd, vcfg, g)
+    return _ENG[key]
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).to("cuda:0")
+
+
+# ------------------------------------------------------------------ DSP
+@pytest.mark.parametrize("sr", [8000, 12000, 16000, 24000, 22050, 44100])
+def test_resample_normalise(cuda_device, sr):
+    eng, *_ = engine("gen_basic_midpoint", "fp32")
+    g = load_golden("frontend")
+    x = dev(g[f"wav_{sr}"])[None]
+    y = eng.resample_normalise(x, sr).cpu().numpy()[0]
+    assert y.shape == g[f"cond_{sr}"].shape
+    assert np.abs(y - g[f"cond_{sr}"]).max() <= 5e-6  # fp32 summation order only
+
+
+def test_resample_batch_ragged_is_per_clip(cuda_device):
+    eng, *_ = engine("gen_basic_midpoint", "fp32")
+    xs = np.stack([synth_speech(4000, 16000, s) * (0.2 + 0.3 * s) for s in range(3)])
+    y = eng.resample_normalise(dev(xs), 16000).cpu().numpy()
+    for i in range(3):
+        assert np.abs(y[i] - dsp.preprocess_audio(xs[i], 16000)).max() <= 5e-6
+        assert abs(np.abs(y[i]).max() - 1.0) < 1e-6
+
+
+@pytest.mark.parametrize("sr", [8000, 24000])
+@pytest.mark.parametrize("precise", [True, False])
+def test_logmel(cuda_device, sr, precise):
+    eng, *_ = engine("gen_basic_midpoint", "fp32")
+    g = load_golden("frontend")
+    eng.precise_mel = precise
+    a = eng.encode(dev(g[f"cond_{sr}"])[None]).cpu()
+    eng.precise_mel = True
+    ref32, ref64 = torch.from_numpy(g[f"logmel_{sr}"]), torch.from_numpy(g[f"logmel64_{sr}"])
+    floor = float((ref32 - ref64).abs().mean())  # the reference's own fp32 noise
+    l1_ref = float((a - ref32).abs().mean())
+    l1_64 = float((a - ref64).abs().mean())
+    print(f"logmel sr={sr} precise={precise}: L1 vs ref32 {l1_ref:.3g}, vs fp64 {l1_64:.3g}, ref floor {floor:.3g}")
+    assert float((a[..., :128] - ref32[..., :128]).abs().max()) <= 1e-4  # occupied bands: tight
+    if precise:
+        assert l1_64 <= 2e-6                 # we are at the fp64 answer
+        assert l1_ref <= 1e-4 + floor        # so the distance to the reference is the reference's noise
+    else:
+        assert l1_64 <= 3 * floor + 1e-5
+
+
+def test_postprocess(cuda_device):
+    eng, *_ = engine("gen_basic_midpoint", "fp32")
+    torch.manual_seed(0)
+    for T in (480 * 30, 480 * 30 + 123):
+        src = torch.from_numpy(np.stack([synth_speech(T, 48000, 3), synth_speech(T, 48000, 4) * 0.5]))
+        pred = torch.randn(2, 480 * 30) * 0.1
+        out = eng.postprocess(pred.cuda(), src.cuda()).cpu()
+        for i in range(2):
+            ref = dsp.postprocess(pred[i:i + 1], src[i:i + 1], T)
+            assert float((out[i:i + 1] - ref).abs().max()) <= 2e-5
+            assert abs(float(out[i].abs().max()) - 0.99) < 1e-6
+
+
+# ------------------------------------------------------------------ fp32 kernels
+def test_snake_f32(cuda_device):
+    eng, sd, vcfg, _ = engine("gen_basic_midpoint", "fp32")
+    torch.manual_seed(1)
+    for (B, Cc, L) in [(2, 16, 700), (1, 8, 3), (1, 8, 13)]:
+        x = torch.randn(B, Cc, L) * 2
+        alpha, beta = torch.randn(Cc) * 0.3, torch.randn(Cc) * 0.3
+        filt = torch.from_numpy(np.ascontiguousarray(eng.sd["flowhigh.audio_enc_dec.vocoder.activation_post.upsample.filter"].cpu().numpy()))
+        ref = model.aa_activation(x, alpha, beta, filt, filt, True)
+        y = torch.empty_like(x).cuda()
+        a = torch.exp(alpha).cuda()
+        ib = (1.0 / (torch.exp(beta) + 1e-9)).cuda()
+        eng._call("fh_snake_aa_f32", x.cuda().data_ptr(), y.data_ptr(), a.data_ptr(), ib.data_ptr(),
+                  filt.flatten().cuda().data_ptr(), B, Cc, L, eng.stream)
+        assert float((y.cpu() - ref).abs().max()) <= 5e-6
+
+
+@pytest.mark.parametrize("k,d", [(3, 1), (7, 3), (11, 5)])
+def test_conv_f32(cuda_device, k, d):
+    eng, *_ = engine("gen_basic_midpoint", "fp32")
+    torch.manual_seed(2)
+    B, Ci, Co, L = 2, 20, 70, 333
+    x, w, b = torch.randn(B, Ci, L), torch.randn(Co, Ci, k) * 0.1, torch.randn(Co)
+    rec = eng._mk_f32(packing.conv1d_taps(w, b, d))
+    res = torch.randn(B, Co, L)
+    out = torch.zeros(B, Co, L).cuda()
+    eng._conv_f32(rec, x.cuda(), out, B, L, res=res.cuda(), beta=0.5, alpha=2.0)
+    ref = 2.0 * F.conv1d(x, w, b, dilation=d, padding=(k * d - d) // 2) + 0.5 * res
+    assert float((out.cpu() - ref).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("u,k", [(5, 11), (4, 8), (3, 7), (2, 4), (10, 20)])
+def test_conv_transpose_f32(cuda_device, u, k):
+    eng, *_ = engine("gen_basic_midpoint", "fp32")
+    torch.manual_seed(3)
+    B, Ci, Co, L = 2, 24, 12, 77
+    x, w, b = torch.randn(B, Ci, L), torch.randn(Ci, Co, k) * 0.1, torch.randn(Co)
+    rec = eng._mk_f32(packing.conv_transpose1d_taps(w, b, u))
+    out = torch.zeros(B, Co, L * u).cuda()
+    eng._conv_f32(rec, x.cuda(), out, B, L)
+    ref = F.conv_transpose1d(x, w, b, stride=u, padding=(k - u) // 2)
+    assert float((out.cpu() - ref).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["voc_resblock2_snake", "voc_resblock1_snakebeta"])
+def test_vocoder_f32_golden(cuda_device, name):
+    eng, sd, vcfg, g = engine(name, "fp32")
+    out = eng.vocoder(dev(g["mel"])).cpu()
+    ref = torch.from_numpy(g["ref_vocoder"]).squeeze(1)
+    err = float((out - ref).abs().max())
+    print(f"vocoder fp32 {name}: max-abs vs reference {err:.3g}")
+    assert err <= 1e-4  # north_star fp32 bar
+
+
+@pytest.mark.parametrize("name", ["gen_c1_adaptive_euler", "gen_basic_midpoint"])
+def test_vector_field_f32(cuda_device, name):
+    eng, sd, vcfg, g = engine(name, "fp32")
+    eps, cond_mel = dev(g["eps"]), dev(g["ref_cond_mel"])
+    out = torch.empty_like(eps)
+    eng.vector_field_step(eps, cond_mel, 0.5, torch.zeros_like(eps), 1.0, out)
+    ref32, ref64 = torch.from_numpy(g["ref_vfield_t05"]), torch.from_numpy(g["f64_vfield_t05"])
+    floor = float((ref32 - ref64).abs().max())
+    e64 = float((out.cpu() - ref64).abs().max())
+    print(f"vector field fp32 {name}: max-abs vs fp64 {e64:.3g}; reference's own {floor:.3g}; vs ref32 "
+          f"{float((out.cpu() - ref32).abs().max()):.3g}")
+    assert e64 <= 3 * floor + 1e-5
+    assert float((out.cpu() - ref64).abs().mean()) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["gen_c1_adaptive_euler", "gen_basic_midpoint", "gen_basic_euler4"])
+def test_generate_f32_golden(cuda_device, name):
+    g = load_golden(name)
+    sd, vcfg = golden_weights(g)
+    m = FlowHighSR.from_random(vcfg, device="cuda:0", precision="fp32", sigma=float(g["sigma"]),
+                               cfm_method=str(g["cfm_method"]), torchdiffeq_ode_method=str(g["ode_method"]))
+    m.load_state_dict(sd)
+    m = m.cuda()
+    out = m.generate(g["wav"], int(g["sr"]), 48000, timestep=int(g["steps"]), eps=torch.from_numpy(g["eps"])).cpu()
+    ref32, ref64 = torch.from_numpy(g["ref_final"]), torch.from_numpy(g["f64_final"])
+    assert out.shape == ref32.shape
+    floor = float((ref32 - ref64).abs().max())
+    e64, e32 = float((out - ref64).abs().max()), float((out - ref32).abs().max())
+    print(f"generate fp32 {name}: max-abs vs fp64 {e64:.3g} (reference's own {floor:.3g}), vs ref32 {e32:.3g}")
+    assert e64 <= 3 * floor + 2e-5
+    # stage-wise: mel L1 and vocoder from the reference's mel
+    eng = m._engine()
+    mel = eng.sample_mel(dev(g["ref_cond_mel"]), dev(g["eps"]), steps=int(g["steps"]), ode_method=str(g["ode_method"]),
+                         cfm_method=str(g["cfm_method"]), sigma=float(g["sigma"])).cpu()
+    l1 = float((mel - torch.from_numpy(g["f64_mel"])).abs().mean())
+    l1_ref = float((torch.from_numpy(g["ref_mel"]) - torch.from_numpy(g["f64_mel"])).abs().mean())
+    print(f"   mel L1 vs fp64 {l1:.3g} (reference's own {l1_ref:.3g})")
+    assert l1 <= 1e-4 + 2 * l1_ref
+    voc = eng.vocoder(dev(g["ref_mel"])).cpu()
+    assert float((voc - torch.from_numpy(g["ref_vocoder"])).abs().max()) <= 1e-4
+
+
+# ------------------------------------------------------------------ tcgen05 kernels
+def _tc_run(eng, tconv, x, B, L, res=None, alpha=1.0, beta=0.0, out_bf16=False, geglu=False, bn=None):
+    """x [B,Cin,L] fp32 host -> runs fh_tc_conv_bf16 on chunked buffers -> [B,Cout,L*P] fp32 host."""
+    rec = eng._mk_tc(tconv, bn=bn)
+    cin, cout = rec.cin_pad, rec.cout_pad
+    Lp, cs, bs = eng._geom(cin, L)
+    a = torch.zeros(B * bs + 4096, dtype=torch.bfloat16, device="cuda:0")
+    eng._call("fh_to_chunked_bf16", x.cuda().contiguous().data_ptr(), x.shape[1] * L, L, 1, a.data_ptr(), bs, cs, HALO, B,
+              x.shape[1], L, eng.stream)
+    Lo = L * rec.P
+    cout_o = cout // 2 if geglu else cout
+    Lpo, cso, bso = eng._geom(cout_o, Lo)
+    out = torch.zeros(B * bso + 4096, dtype=torch.bfloat16 if out_bf16 else torch.float32, device="cuda:0")
+    r = None
+    if res is not None:
+        rp = torch.zeros(B, cout, Lo)
+        rp[:, : res.shape[1]] = res
+        rbuf = torch.zeros(B, cout // 8, Lpo, 8)
+        rbuf[:, :, HALO: HALO + Lo] = rp.reshape(B, cout // 8, 8, Lo).permute(0, 1, 3, 2)
+        r = torch.cat([rbuf.flatten(), torch.zeros(4096)]).cuda()
+    o = HALO * 8
+    eng._tc_conv(rec, a, bs, cs, HALO, out[o:], (bso, cso, 8), out_bf16, B, L, res=None if r is None else r[o:],
+                 res_strides=(bso, cso, 8), alpha=alpha, beta=beta, geglu=geglu)
+    torch.cuda.synchronize()
+    full = out[: B * bso].float().cpu().reshape(B, cout_o // 8, Lpo, 8)
+    assert full[:, :, :HALO].abs().max() == 0 and full[:, :, HALO + Lo:].abs().max() == 0, "halo rows were written"
+    return full[:, :, HALO: HALO + Lo].permute(0, 1, 3, 2).reshape(B, cout_o, Lo)
+
+
+def _bf(x):
+    return x.bfloat16().float()
+
+
+@pytest.mark.parametrize("k,d,Ci,Co,L,bn", [(1, 1, 64, 64, 128, None), (3, 1, 32, 48, 300, None), (7, 3, 96, 96, 1000, None),
+                                            (11, 5, 48, 32, 517, None), (3, 1, 384, 384, 700, 192),
+                                            (7, 1, 256, 512, 260, 256), (11, 1, 768, 768, 200, 256)])
+def test_tc_conv1d(cuda_device, k, d, Ci, Co, L, bn):
+    eng, *_ = engine("gen_basic_midpoint", "bf16")
+    torch.manual_seed(k * 100 + d)
+    B = 2
+    x, w, b = torch.randn(B, Ci, L), torch.randn(Co, Ci, k) / (Ci * k) ** 0.5, torch.randn(Co)
+    res = torch.randn(B, Co, L)
+    got = _tc_run(eng, packing.conv1d_taps(w, b, d), x, B, L, res=res, alpha=0.5, beta=2.0, bn=bn)[:, :Co]
+    ref = 0.5 * F.conv1d(_bf(x), _bf(w), b, dilation=d, padding=(k * d - d) // 2) + 2.0 * res
+    err = float((got - ref).abs().max())
+    print(f"tc conv k={k} d={d} Ci={Ci} Co={Co} L={L}: max err {err:.3g}")
+    assert err <= 2e-3
+
+
+@pytest.mark.parametrize("u,k,Ci,Co", [(5, 11, 64, 32), (4, 8, 32, 16), (3, 7, 48, 24), (2, 4, 32, 16), (10, 20, 32, 16)])
+def test_tc_conv_transpose(cuda_device, u, k, Ci, Co):
+    eng, *_ = engine("gen_basic_midpoint", "bf16")
+    torch.manual_seed(u)
+    B, L = 2, 150
+    x, w, b = torch.randn(B, Ci, L), torch.randn(Ci, Co, k) / (Ci * k / u) ** 0.5, torch.randn(Co)
+    got = _tc_run(eng, packing.conv_transpose1d_taps(w, b, u), x, B, L)[:, :Co]
+    ref = F.conv_transpose1d(_bf(x), _bf(w), b, stride=u, padding=(k - u) // 2)
+    assert float((got - ref).abs().max()) <= 2e-3
+
+
+def test_tc_linear_shapes_and_bf16_out(cuda_device):
+    eng, *_ = engine("gen_basic_midpoint", "bf16")
+    torch.manual_seed(5)
+    for (M, K, N) in [(300, 1024, 3072), (1000, 512, 1024), (130, 2736, 1024)]:
+        x, w = torch.randn(1, K, M), torch.randn(N, K) / K ** 0.5
+        got = _tc_run(eng, packing.linear_taps(w, None), x, 1, M, out_bf16=True)
+        ref = F.conv1d(_bf(x), _bf(w)[:, :, None])
+        assert float((got - ref).abs().max()) <= 0.03  # bf16 output rounding of O(1) values
+
+
+def test_tc_geglu_epilogue(cuda_device):
+    eng, *_ = engine("gen_basic_midpoint", "bf16")
+    torch.manual_seed(6)
+    M, K, inner = 200, 256, 88
+    x = torch.randn(1, K, M)
+    w, b = torch.randn(2 * inner, K) / K ** 0.5, torch.randn(2 * inner) * 0.1
+    ip = packing.round_up(inner, 16)
+    wi, bi = torch.zeros(2 * ip, K), torch.zeros(2 * ip)
+    wi[0:2 * inner:2], wi[1:2 * inner:2] = w[:inner], w[inner:]
+    bi[0:2 * inner:2], bi[1:2 * inner:2] = b[:inner], b[inner:]
+    got = _tc_run(eng, packing.linear_taps(wi, bi), x, 1, M, geglu=True)[:, :inner]
+    u = F.conv1d(_bf(x), _bf(w)[:, :, None], b)
+    ref = F.gelu(u[:, inner:]) * u[:, :inner]
+    assert float((got - ref).abs().max()) <= 2e-3
+
+
+@pytest.mark.parametrize("name", ["voc_resblock2_snake", "voc_resblock1_snakebeta"])
+def test_vocoder_bf16_golden(cuda_device, name):
+    eng, sd, vcfg, g = engine(name, "bf16")
+    out = eng.vocoder(dev(g["mel"])).cpu()
+    ref = torch.from_numpy(g["ref_vocoder"]).squeeze(1)
+    s, l = snr_db(ref, out), lsd_db(ref, out)
+    print(f"vocoder bf16 {name}: SNR {s:.1f} dB, LSD {l:.3f} dB, max-abs {float((out - ref).abs().max()):.3g}")
+    assert s >= 40.0
+
+
+@pytest.mark.parametrize("name", ["gen_c1_adaptive_euler", "gen_basic_midpoint", "gen_basic_euler4"])
+def test_generate_bf16_golden(cuda_device, name):
+    g = load_golden(name)
+    sd, vcfg = golden_weights(g)
+    m = FlowHighSR.from_random(vcfg, device="cuda:0", precision="bf16", sigma=float(g["sigma"]),
+                               cfm_method=str(g["cfm_method"]), torchdiffeq_ode_method=str(g["ode_method"]))
+    m.load_state_dict(sd)
+    m = m.cuda()
+    out = m.generate(g["wav"], int(g["sr"]), 48000, timestep=int(g["steps"]), eps=torch.from_numpy(g["eps"])).cpu()
+    ref = torch.from_numpy(g["ref_final"])
+    eng = m._engine()
+    mel = eng.sample_mel(dev(g["ref_cond_mel"]), dev(g["eps"]), steps=int(g["steps"]), ode_method=str(g["ode_method"]),
+                         cfm_method=str(g["cfm_method"]), sigma=float(g["sigma"])).cpu()
+    voc = eng.vocoder(dev(g["ref_mel"])).cpu()
+    refv = torch.from_numpy(g["ref_vocoder"])
+    print(f"generate bf16 {name}: final SNR {snr_db(ref, out):.1f} dB LSD {lsd_db(ref, out):.3f} dB | mel SNR "
+          f"{snr_db(torch.from_numpy(g['ref_mel']), mel):.1f} dB | vocoder(ref mel) SNR {snr_db(refv, voc):.1f} dB "
+          f"LSD {lsd_db(refv, voc):.3f} dB")
+    assert snr_db(refv, voc) >= 40.0  # pre-postproc vocoder output (postproc would mask errors)
+    assert snr_db(ref, out) >= 40.0
+
+
+def test_no_cpu_fallback_and_launch_counter(cuda_device):
+    from flowhigh_b200 import _lib
+    eng, *_ = engine("gen_basic_midpoint", "fp32")
+    n0 = _lib.launch_count()
+    eng.encode(torch.zeros(1, 4800, device="cuda:0"))
+    assert _lib.launch_count() == n0 + 1
+    with pytest.raises(ValueError):
+        eng.encode(torch.zeros(1, 500, device="cuda:0"))  # shorter than the 784-sample reflect pad

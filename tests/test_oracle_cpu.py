@@ -1,0 +1,192 @@
+"""CPU suite: the oracle restatement against the committed golden vectors (outputs of the
+unmodified reference, tests/golden/make_golden.py), against the installed scipy, and the host
+logic / ABI surface of the product.  No GPU work."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from flowhigh_b200 import tables
+from flowhigh_b200.config import BackboneConfig, VocoderConfig
+from flowhigh_b200.synth import synth_speech
+from flowhigh_b200.weights import kaiser_sinc_filter12, random_state_dict, state_dict_spec, fold_weight_norm
+from oracle import dsp, model, pipeline
+from util import golden_weights, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ------------------------------------------------------------------ resampler
+@pytest.mark.parametrize("sr", [8000, 12000, 16000, 24000, 22050, 44100])
+def test_resample_restatement_matches_scipy(sr):
+    import scipy.signal
+    x = synth_speech(sr // 3 + 11, sr, seed=1)
+    for dt, tol in ((np.float32, 1e-6), (np.float64, 1e-12)):
+        a = scipy.signal.resample_poly(x.astype(dt), 48000, sr)
+        b = dsp.resample_poly(x.astype(dt), 48000, sr)
+        assert a.shape == b.shape and a.dtype == b.dtype
+        assert np.abs(a - b).max() <= tol
+
+
+@pytest.mark.parametrize("sr", [8000, 12000, 16000, 24000, 22050, 44100])
+def test_resample_golden(sr):
+    g = load_golden("frontend")
+    y = dsp.preprocess_audio(g[f"wav_{sr}"], sr)
+    assert np.abs(y - g[f"cond_{sr}"]).max() <= 2e-6
+
+
+def test_resample_int16_quirk_golden():
+    g = load_golden("frontend")
+    y = dsp.preprocess_audio(g["wav_int16"], 16000)  # max > 1 -> /32768 in fp64 (flowhighsr.py:62-63)
+    assert y.dtype == np.float64
+    assert np.abs(y - g["cond_int16"]).max() <= 1e-6
+
+
+def test_resample_taps_table_matches_oracle():
+    for sr in (8000, 12000, 16000, 24000, 22050):
+        h, up, down, npp, npr = tables.resample_plan(sr, 48000)
+        u2, d2, half, npp2, npr2 = dsp.resample_poly_params(sr, 48000)
+        assert (up, down, npp, npr) == (u2, d2, npp2, npr2)
+        ho = (dsp.firwin_kaiser_lowpass(2 * half + 1, 1.0 / max(up, down)).astype(np.float32) * np.float32(up))
+        assert np.abs(h - ho).max() <= 1e-7
+
+
+# ------------------------------------------------------------------ mel
+def test_mel_filterbank_structure():
+    a = dsp.mel_filterbank()
+    b = tables.mel_filterbank_dense()
+    assert a.shape == b.shape == (256, 1025) and a.dtype == np.float32
+    assert np.abs(a - b).max() <= 1e-7
+    assert (a >= 0).all() and int((a > 0).sum()) == 2030
+    start, length, w, stride = tables.mel_filterbank_sparse()
+    dense = np.zeros_like(b)
+    for m in range(256):
+        dense[m, start[m]: start[m] + length[m]] = w[m, : length[m]]
+    assert np.array_equal(dense, b) and length.max() <= 33
+
+
+@pytest.mark.parametrize("sr", [8000, 24000])
+def test_logmel_golden(sr):
+    g = load_golden("frontend")
+    a = dsp.encode_logmel(torch.from_numpy(g[f"cond_{sr}"])[None])
+    assert a.shape == g[f"logmel_{sr}"].shape
+    assert (a - torch.from_numpy(g[f"logmel_{sr}"])).abs().max() <= 1e-5  # same torch build -> identical
+
+
+def test_aa_filter_constants():
+    f = kaiser_sinc_filter12()
+    ref = np.array([0.00202896, 0.00938947, -0.02554346, -0.05765738, 0.12857258, 0.44320980, 0.44320980, 0.12857258,
+                    -0.05765738, -0.02554346, 0.00938947, 0.00202896], np.float32)  # SURVEY.md A.5 [probe]
+    assert np.abs(f - ref).max() <= 1e-7 and abs(f.sum() - 1) < 1e-6
+
+
+# ------------------------------------------------------------------ networks vs reference goldens
+@pytest.mark.parametrize("name", ["gen_c1_adaptive_euler", "gen_basic_midpoint", "gen_basic_euler4"])
+def test_generate_golden(name):
+    g = load_golden(name)
+    sd, vcfg = golden_weights(g)
+    eps = torch.from_numpy(g["eps"])
+    cond_mel = dsp.encode_logmel(torch.from_numpy(g["ref_cond"]))
+    assert (cond_mel - torch.from_numpy(g["ref_cond_mel"])).abs().max() <= 1e-5
+    v = model.vector_field(sd, eps, cond_mel, torch.tensor(0.5))
+    # two fp32 evaluation orders of the same network: compare with the reference's own distance to fp64
+    floor = float(np.abs(g["ref_vfield_t05"] - g["f64_vfield_t05"]).max())
+    assert float((v - torch.from_numpy(g["f64_vfield_t05"])).abs().max()) <= 3 * floor + 1e-5
+    o = pipeline.OracleFlowHigh(sd, vcfg, sigma=float(g["sigma"]), cfm_method=str(g["cfm_method"]),
+                                ode_method=str(g["ode_method"]))
+    out, st = o.generate(g["wav"], int(g["sr"]), eps, timestep=int(g["steps"]), return_stages=True)
+    assert np.abs(st["cond"].numpy() - g["ref_cond"]).max() <= 2e-6
+    floor = float(np.abs(g["ref_final"] - g["f64_final"]).max())
+    assert float((out - torch.from_numpy(g["f64_final"])).abs().max()) <= 3 * floor + 1e-5
+    # vocoder alone, from the reference's own mel: tight
+    voc = model.vocoder_forward(sd, vcfg, torch.from_numpy(g["ref_mel"])).squeeze(1)
+    assert (voc - torch.from_numpy(g["ref_vocoder"])).abs().max() <= 2e-5
+
+
+@pytest.mark.parametrize("name", ["voc_resblock2_snake", "voc_resblock1_snakebeta"])
+def test_vocoder_golden(name):
+    g = load_golden(name)
+    sd, vcfg = golden_weights(g)
+    out = model.vocoder_forward(sd, vcfg, torch.from_numpy(g["mel"]))
+    assert out.shape == g["ref_vocoder"].shape
+    assert (out - torch.from_numpy(g["ref_vocoder"])).abs().max() <= 2e-5
+
+
+def test_postprocess_properties():
+    torch.manual_seed(0)
+    T = 480 * 20 + 123  # T % 480 != 0: pred is shorter than src (postprocessing.py:30-34)
+    src = torch.from_numpy(synth_speech(T, 48000, 3))[None]
+    pred = torch.randn(1, 480 * 20) * 0.1
+    out = dsp.postprocess(pred, src, T)
+    assert out.shape == (1, T) and abs(float(out.abs().max()) - 0.99) < 1e-6
+    spec = dsp._stft_center_zero(src)
+    cr = dsp.cutoff_index(spec)
+    assert 1 <= cr <= 1024
+    # degenerate: all energy in bin 0 -> loop never tests index 0 -> returns 0
+    e = torch.zeros(1, 1025, 5, dtype=torch.complex64)
+    e[:, 0] = 1
+    assert dsp.cutoff_index(e) == 0
+
+
+# ------------------------------------------------------------------ host logic
+def test_state_dict_layout_and_determinism():
+    for vcfg in (VocoderConfig.tiny(), VocoderConfig.tiny(resblock="2", activation="snake", logscale=False)):
+        a = random_state_dict(BackboneConfig(), vcfg, seed=3)
+        b = random_state_dict(BackboneConfig(), vcfg, seed=3)
+        assert list(a) == [k for k, _, _ in state_dict_spec(BackboneConfig(), vcfg)]
+        assert all(torch.equal(a[k], b[k]) for k in a)
+    n = len(state_dict_spec(BackboneConfig(), VocoderConfig.assumed_48k()))
+    assert n == 711
+
+
+def test_fold_weight_norm_matches_torch():
+    torch.manual_seed(0)
+    conv = torch.nn.utils.weight_norm(torch.nn.Conv1d(6, 4, 3))
+    convt = torch.nn.utils.weight_norm(torch.nn.ConvTranspose1d(6, 4, 4, 2))
+    gen = {"a." + k: v.detach().clone() for k, v in conv.state_dict().items()}
+    gen.update({"b." + k: v.detach().clone() for k, v in convt.state_dict().items()})
+    folded = fold_weight_norm(gen)
+    torch.nn.utils.remove_weight_norm(conv)
+    torch.nn.utils.remove_weight_norm(convt)
+    assert torch.allclose(folded["a.weight"], conv.weight, atol=1e-6)
+    assert torch.allclose(folded["b.weight"], convt.weight, atol=1e-6)
+
+
+def test_vocoder_config_validation():
+    with pytest.raises(ValueError):
+        VocoderConfig(upsample_rates=(4, 4, 4, 4), upsample_kernel_sizes=(8, 8, 8, 8)).validate()
+    with pytest.raises(ValueError):
+        VocoderConfig(upsample_rates=(5, 4, 3, 2, 2, 2), upsample_kernel_sizes=(10, 8, 7, 4, 4, 4)).validate()
+    VocoderConfig.assumed_48k().validate()
+
+
+def test_api_surface_cpu():
+    from flowhigh_b200 import FlowHighSR
+    m = FlowHighSR.from_random(VocoderConfig.tiny(), device="cpu")
+    assert m.cfm_method == "basic_cfm" and m.odeint_kwargs["method"] == "midpoint" and m.sigma == 0.0  # F4
+    m.set_cfm_method("independent_cfm_adaptive")
+    assert m.cfm_method == "independent_cfm_adaptive"
+    sd = m.state_dict()
+    m.load_state_dict(sd, strict=True)
+    with pytest.raises(RuntimeError):  # no CPU fallback
+        m.generate(np.zeros(2000, np.float32), 16000)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """The shared library loads and exports exactly the symbols include/flowhigh_b200.h declares."""
+    from flowhigh_b200 import _lib
+    from flowhigh_b200.build import build
+    path = build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "flowhigh_b200.h")).read()
+    declared = set(re.findall(r"\b(fh_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.fh_version() == 1
+    lib.fh_tc_packed_weight_bytes.restype = ctypes.c_int64
+    assert lib.fh_tc_packed_weight_bytes(32, 48, 3, 1, 48) == 1 * 1 * 2 * 3 * 48 * 32

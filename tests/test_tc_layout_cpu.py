@@ -1,0 +1,103 @@
+"""CPU emulation of fh_tc_conv_bf16's addressing (tile decode, chunk windows, packed weight image,
+tap-shifted descriptors, epilogue indexing) against the plain tapped convolution.  This pins the
+host-side packing (flowhigh_b200/packing.py) and the index arithmetic of csrc/tc_conv.cu; the
+tensor-core semantics themselves are checked on the GPU (tests/test_gpu_kernels.py)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from flowhigh_b200 import packing
+
+HALO = 32
+
+
+def emulate_tc_conv(a_chunked, a_bs, a_cs, a_row0, packed, rec_off, P, ntaps, cin_pad, cout_pad, bn, B, L,
+                    out, o_bs, o_cs, o_row, bias=None):
+    """Follows tc_conv_kernel step by step (fp32 arithmetic on the bf16-rounded operands)."""
+    m_tiles, n_tiles, ci_pairs = -(-L // 128), -(-cout_pad // bn), cin_pad // 16
+    a = a_chunked.float().numpy()
+    w = packed.float().numpy().reshape(P, n_tiles, ci_pairs, ntaps, 2, bn, 8)
+    for b in range(B):
+        for p in range(P):
+            offs = rec_off[p]
+            mn = int(offs.min())
+            wrows = 128 + int(offs.max() - offs.min())
+            for mt in range(m_tiles):
+                for nt in range(n_tiles):
+                    D = np.zeros((128, bn), np.float32)
+                    row = a_row0 + mt * 128 + mn
+                    for cp in range(ci_pairs):
+                        slot = np.zeros((2, wrows, 8), np.float32)
+                        for c in range(2):
+                            base = b * a_bs + (2 * cp + c) * a_cs + row * 8
+                            slot[c] = a[base: base + wrows * 8].reshape(wrows, 8)
+                        for j in range(ntaps):
+                            sh = int(offs[j]) - mn
+                            A = np.concatenate([slot[0, sh: sh + 128], slot[1, sh: sh + 128]], axis=1)  # [128,16]
+                            Bm = np.concatenate([w[p, nt, cp, j, 0], w[p, nt, cp, j, 1]], axis=1)      # [bn,16]
+                            D += A @ Bm.T
+                    for r in range(128):
+                        t = mt * 128 + r
+                        if t >= L:
+                            continue
+                        for n in range(bn):
+                            ng = nt * bn + n
+                            if ng >= cout_pad:
+                                continue
+                            v = D[r, n] + (0.0 if bias is None else float(bias[ng]))
+                            out[b * o_bs + (ng // 8) * o_cs + (t * P + p) * o_row + ng % 8] = v
+
+
+def to_chunked(x, cpad, Lp, row0):
+    """x [B,C,L] -> flat chunked bf16 buffer [B][cpad/8][Lp][8]."""
+    B, C, L = x.shape
+    buf = torch.zeros(B, cpad // 8, Lp, 8)
+    xp = torch.zeros(B, cpad, L)
+    xp[:, :C] = x
+    buf[:, :, row0: row0 + L, :] = xp.reshape(B, cpad // 8, 8, L).permute(0, 1, 3, 2)
+    return buf.to(torch.bfloat16).flatten()
+
+
+def from_chunked(flat, B, C, cpad, Lp, row0, L):
+    t = torch.from_numpy(flat).reshape(B, cpad // 8, Lp, 8)[:, :, row0: row0 + L, :]
+    return t.permute(0, 1, 3, 2).reshape(B, cpad, L)[:, :C]
+
+
+@pytest.mark.parametrize("kind", ["conv_d1", "conv_d5", "convT_5_11", "convT_2_4", "linear"])
+def test_tc_addressing_matches_conv(kind):
+    torch.manual_seed(0)
+    B, Cin, Cout, L = 2, 24, 40, 150
+    x = torch.randn(B, Cin, L)
+    bias = torch.randn(Cout)
+    if kind.startswith("conv_d"):
+        d = int(kind[-1])
+        w = torch.randn(Cout, Cin, 7) * 0.2
+        tc = packing.conv1d_taps(w, bias, d)
+        ref = F.conv1d(x.bfloat16().float(), w.bfloat16().float(), bias, dilation=d, padding=(7 * d - d) // 2)
+    elif kind.startswith("convT"):
+        _, u, k = kind.split("_")
+        u, k = int(u), int(k)
+        w = torch.randn(Cin, Cout, k) * 0.2
+        tc = packing.conv_transpose1d_taps(w, bias, u)
+        ref = F.conv_transpose1d(x.bfloat16().float(), w.bfloat16().float(), bias, stride=u, padding=(k - u) // 2)
+    else:
+        w = torch.randn(Cout, Cin) * 0.2
+        tc = packing.linear_taps(w, bias)
+        ref = F.conv1d(x.bfloat16().float(), w.bfloat16().float()[:, :, None], bias)
+    packed, cin_pad, cout_pad, bn = packing.pack_tc(tc, "cpu", bn=32)
+    assert packed.numel() * 2 == tc.P * (-(-cout_pad // bn)) * (cin_pad // 16) * tc.ntaps * bn * 32
+    Lp_in = HALO + packing.round_up(L, 128) + 64
+    Lo = L * tc.P
+    Lp_out = HALO + packing.round_up(Lo, 128) + 64
+    a = to_chunked(x, cin_pad, Lp_in, HALO)
+    a = torch.cat([a, torch.zeros(4096, dtype=a.dtype)])
+    out = np.zeros(B * (cout_pad // 8) * Lp_out * 8, np.float32)
+    emulate_tc_conv(a, (cin_pad // 8) * Lp_in * 8, Lp_in * 8, HALO, packed, tc.off, tc.P, tc.ntaps, cin_pad, cout_pad, bn,
+                    B, L, out[HALO * 8:], (cout_pad // 8) * Lp_out * 8, Lp_out * 8, 8,
+                    bias=packing.pad_vec(bias, cout_pad).numpy())
+    got = from_chunked(out, B, Cout, cout_pad, Lp_out, HALO, Lo)
+    assert torch.allclose(got, ref, atol=2e-3, rtol=1e-3), (got - ref).abs().max()
+    # halo rows were never written
+    full = torch.from_numpy(out).reshape(B, cout_pad // 8, Lp_out, 8)
+    assert full[:, :, :HALO].abs().max() == 0 and full[:, :, HALO + Lo:].abs().max() == 0
