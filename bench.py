@@ -1,0 +1,303 @@
+#!/usr/bin/env python
+"""Benchmark of the FLowHigh `generate` hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): midpoint ODE (2 NFE), batch of 64 x 10 s clips, 12 kHz -> 48 kHz,
+basic_cfm, transformer 2L x 16H x 64, BigVGAN 48 kHz / 256-band (ASSUMED vocoder config),
+random-init weights, synthetic speech-like audio, bf16 tensor-core path.  One "step" = one pass of the
+whole path (resample -> log-mel -> CFM -> vocoder -> post-processing) over one batch per GPU.
+
+  value : 48 kHz audio-seconds produced per wall second, whole job, inputs resident in HBM
+  e2e   : same through the public API (FlowHighSR.generate_batch) from pinned host buffers, H2D and
+          D2H copies inside the timed region
+  roofline : the dominant kernel (tcgen05 implicit-GEMM conv), algorithmic FLOPs / CUDA-event time
+  cpu_baseline : the oracle port of the reference (fp32 PyTorch-CPU restatement) on a bounded sample
+
+N > 1: launched by torchrun, one rank per GPU, each rank runs its own batch (weak scaling, clips are
+independent: no data-path collective); time = max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "48kHz audio-sec/sec (whole job)"
+UNIT = "audio-s/s"
+CLIP_SECONDS = 10.0
+SR_IN = 12000
+BATCH = 64
+STEPS_ODE = 1  # time_step = 1, midpoint -> 2 NFE
+
+
+def config_dict(n_gpus, batch):
+    return {
+        "workload": f"configs[1]: {batch} x 10 s clips/GPU, 12 kHz -> 48 kHz, basic_cfm, midpoint (2 NFE), "
+                    "transformer 2Lx16Hx64, BigVGAN 48k/256-band (assumed cfg: rates 5,4,3,2,2,2, C0 1536, "
+                    "AMPBlock1 k 3/7/11 d 1/3/5, snakebeta), random-init weights",
+        "clips_per_gpu": batch, "clip_seconds": CLIP_SECONDS, "sr_in": SR_IN, "sr_out": 48000, "nfe": 2,
+        "parallelism": f"clips sharded over {n_gpus} GPU(s), no data-path collective",
+        "l2_policy": "per-step working set (>= 40 GB of activations) far exceeds the 126 MB L2; no flush needed",
+    }
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower() == "active" for r in self.rows)]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------- CPU arm
+def cpu_reference_step(sample_seconds, vcfg, sd, seed):
+    """One pass of the ORACLE (CPU restatement of the reference, fp32) over a bounded sample."""
+    import torch
+    from flowhigh_b200.synth import synth_speech
+    from oracle import pipeline
+    wav = synth_speech(int(sample_seconds * SR_IN), SR_IN, seed)
+    N = int(sample_seconds * 48000) // 480
+    eps = torch.from_numpy(np.random.default_rng(seed).standard_normal((1, N, 256)).astype(np.float32))
+    o = pipeline.OracleFlowHigh(sd, vcfg, cfm_method="basic_cfm", ode_method="midpoint")
+    t0 = time.perf_counter()
+    o.generate(wav, SR_IN, eps, timestep=STEPS_ODE)
+    return time.perf_counter() - t0
+
+
+def cpu_weights():
+    from flowhigh_b200.config import BackboneConfig, VocoderConfig
+    from flowhigh_b200.weights import random_state_dict
+    vcfg = VocoderConfig.assumed_48k()
+    return vcfg, random_state_dict(BackboneConfig(), vcfg, seed=0, vocoder_gain=0.7)
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
+    pure Python and cannot travel to the GPU box), all host threads, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vcfg, sd = cpu_weights()
+    sample = 1.0
+    for i in range(args.warmup):
+        cpu_reference_step(sample, vcfg, sd, i)
+    t = [cpu_reference_step(sample, vcfg, sd, 100 + i) for i in range(args.steps)]
+    total = sum(t)
+    value = sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus, BATCH),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": f"1 clip x {sample:g} s per step (same model/config; the reference generate() is batch-1)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default=None, help="write the per-kernel CUDA-event breakdown to this JSON file")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from flowhigh_b200 import FlowHighSR, VocoderConfig, _lib
+    from flowhigh_b200.synth import synth_speech
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    W = max(args.warmup, 3)
+    B = args.batch
+
+    model = FlowHighSR.from_random(VocoderConfig.assumed_48k(), device=dev, seed=0, precision="bf16")
+    eng = model._engine()
+    n_in = int(CLIP_SECONDS * SR_IN)
+    host = np.stack([synth_speech(n_in, SR_IN, seed=rank * B + i) for i in range(min(B, 8))])
+    host = np.concatenate([host] * (-(-B // host.shape[0])))[:B]  # 8 distinct clips tiled (synthesis is slow)
+    host_t = torch.from_numpy(np.ascontiguousarray(host)).pin_memory()
+    x_dev = host_t.to(dev)
+    T = 48000 * int(CLIP_SECONDS)
+    N = T // 480
+    eps = torch.randn((B, N, 256), device=dev, generator=torch.Generator(dev).manual_seed(1234 + rank))
+
+    def step_resident():
+        cond = eng.resample_normalise(x_dev, SR_IN)
+        cond_mel = eng.encode(cond)
+        mel = eng.sample_mel(cond_mel, eps, steps=STEPS_ODE, ode_method="midpoint", cfm_method="basic_cfm", sigma=0.0)
+        wave = eng.vocoder(mel)
+        return eng.postprocess(wave, cond)
+
+    out_host = torch.empty((B, T), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        outs = model.generate_batch(list(host_t), SR_IN, 48000, timestep=STEPS_ODE, eps=list(eps), pinned=True)
+        for i, o in enumerate(outs):
+            out_host[i].copy_(o[0], non_blocking=True)
+        torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(W):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- e2e through the public API with host buffers
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+
+    # ---- roofline leg: per-kernel CUDA-event timing of one more step (rank 0)
+    breakdown = None
+    if rank == 0:
+        eng.start_profile()
+        step_resident()
+        breakdown = eng.stop_profile()
+    audio_s = B * CLIP_SECONDS * world
+    value = audio_s * args.steps / (ms / 1000.0)
+    e2e_value = audio_s * e2e_steps / e2e_s
+
+    if rank == 0:
+        hbm_peak, tf_peak, peak_src = peaks()
+        tc = {k: v for k, v in breakdown.items() if k.startswith("tc_conv")}
+        tc_ms = sum(v["ms"] for v in tc.values())
+        tc_fl = sum(v["flops"] for v in tc.values())
+        tc_n = sum(v["launches"] for v in tc.values())
+        tot_ms = sum(v["ms"] for v in breakdown.values())
+        achieved = tc_fl / (tc_ms / 1000.0) / 1e12 if tc_ms > 0 else 0.0
+        roofline = {"kernel": "tc_conv_kernel (tcgen05 implicit-GEMM conv, all launches of one step)", "bound": "tensor",
+                    "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
+                    "traffic": None, "peak_source": peak_src, "launches_per_step": tc_n,
+                    "avg_launch_ms": tc_ms / max(tc_n, 1), "share_of_step": tc_ms / tot_ms if tot_ms else None,
+                    "algorithmic_flops_per_step": tc_fl}
+        groups = {}
+        for k, v in breakdown.items():
+            gname = "tc_conv" if k.startswith("tc_conv") else k
+            g = groups.setdefault(gname, {"ms": 0.0, "launches": 0})
+            g["ms"] += v["ms"]
+            g["launches"] += v["launches"]
+        if args.breakdown:
+            os.makedirs(os.path.dirname(os.path.abspath(args.breakdown)), exist_ok=True)
+            json.dump({"per_kernel": breakdown, "groups": groups, "step_ms_profiled": tot_ms}, open(args.breakdown, "w"),
+                      indent=1)
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            vcfg, sd = cpu_weights()
+            cores = os.cpu_count() or 1
+            torch.set_num_threads(cores)
+            sample = 1.0
+            cpu_reference_step(sample, vcfg, sd, 0)  # warm-up
+            dt = cpu_reference_step(sample, vcfg, sd, 1)
+            cpu = {"value": sample / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"1 clip x {sample:g} s, oracle port of the reference (fp32 torch-CPU), 1 warm-up + 1 timed pass"}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic", "config": config_dict(world, B),
+            "per_gpu": value / world, "realtime_factor_per_gpu": value / world,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_t.numel() * 4),
+                    "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "stage_ms": {k: round(v["ms"], 3) for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(256) stft_logmel_kernel(const float* __restric
     int pos = n * 480 + i - 784;  // reflect pad 784 (melvoco.py:74)
     if (pos < 0) pos = -pos;
     if (pos >= Tlen) pos = 2 * (Tlen - 1) - pos;
-    const float v = __ldg(x + pos) * __ldg(window + i);  // fp32 product, as torch.stft
-    a[i] = {(T)v, (T)0};
+    const T v = (T)__ldg(x + pos) * (T)__ldg(window + i);  // fp32 product in the fp32 kernel, as torch.stft
+    a[i] = {v, (T)0};
   }
   __syncthreads();
   Cplx<T>* r = fft2048<T, false>(a, b, tw);

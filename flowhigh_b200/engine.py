@@ -54,6 +54,7 @@ class Engine:
         self.tc = precision == "bf16"
         self.precise_mel = (precision == "fp32") if precise_mel is None else precise_mel
         self._bufs: Dict[tuple, torch.Tensor] = {}
+        self.profile = None
         self._time_cache: Dict[float, dict] = {}
         dev = self.device
         with torch.cuda.device(dev):
@@ -83,8 +84,33 @@ class Engine:
             self._bufs[key] = t
         return t
 
-    def _call(self, name, *args):
+    def _call(self, name, *args, work=None):
+        if self.profile is None:
+            _lib.check(getattr(self.lib, name)(*args), name)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(self.device))
         _lib.check(getattr(self.lib, name)(*args), name)
+        e1.record(torch.cuda.current_stream(self.device))
+        self.profile.append((name, e0, e1, work or {}))
+
+    def start_profile(self):
+        """Brackets every kernel launch with CUDA events on the launching stream (bench.py roofline leg)."""
+        self.profile = []
+
+    def stop_profile(self):
+        """-> {kernel: {"ms": total, "launches": n, "flops": f, "bytes": b}}"""
+        torch.cuda.synchronize(self.device)
+        agg = {}
+        for name, e0, e1, work in self.profile or []:
+            key = work.get("tag", name)
+            d = agg.setdefault(key, {"ms": 0.0, "launches": 0, "flops": 0.0, "bytes": 0.0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["launches"] += 1
+            d["flops"] += work.get("flops", 0.0)
+            d["bytes"] += work.get("bytes", 0.0)
+        self.profile = None
+        return agg
 
     # ------------------------------------------------------------------ weight preparation
     def _mk_f32(self, tconv: packing.TappedConv) -> _F32Weight:
@@ -261,7 +287,21 @@ class Engine:
         args.alpha, args.beta_res, args.accumulate, args.geglu = alpha, beta, int(accumulate), int(geglu)
         args.B, args.L, args.Cin, args.Cout = B, L, rec.cin_pad, rec.cout_pad
         args.ntaps, args.P, args.tap_off, args.bn = rec.ntaps, rec.P, rec.off_c, rec.bn
+        if self.profile is None:
+            _lib.check(self.lib.fh_tc_conv_bf16(C.byref(args), self.stream), "fh_tc_conv_bf16")
+            return
+        flops = 2.0 * B * L * rec.P * rec.ntaps * rec.cin * rec.cout
+        esz_o = 2 if out_bf16 else 4
+        nbytes = B * L * rec.cin * 2 + B * L * rec.P * rec.cout * esz_o * (2 if accumulate else 1)
+        if res is not None:
+            nbytes += B * L * rec.P * rec.cout * (2 if res_bf16 else 4)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(self.device))
         _lib.check(self.lib.fh_tc_conv_bf16(C.byref(args), self.stream), "fh_tc_conv_bf16")
+        e1.record(torch.cuda.current_stream(self.device))
+        self.profile.append(("fh_tc_conv_bf16", e0, e1,
+                             {"flops": flops, "bytes": float(nbytes),
+                              "tag": f"tc_conv[Cin{rec.cin},Cout{rec.cout},k{rec.ntaps}x{rec.P}]"}))
 
     def _sgemm(self, A, lda, W, ldw, bias, res, ldr, beta, alpha, out, ldc, M, N, K):
         self._call("fh_sgemm_nt_f32", A.data_ptr(), lda, W.data_ptr() if isinstance(W, torch.Tensor) else W, ldw,

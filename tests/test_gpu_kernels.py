@@ -66,11 +66,11 @@ def test_logmel(cuda_device, sr, precise):
     l1_64 = float((a - ref64).abs().mean())
     print(f"logmel sr={sr} precise={precise}: L1 vs ref32 {l1_ref:.3g}, vs fp64 {l1_64:.3g}, ref floor {floor:.3g}")
     assert float((a[..., :128] - ref32[..., :128]).abs().max()) <= 1e-4  # occupied bands: tight
+    assert l1_ref <= 1e-4                    # north_star fp32 bar: mel L1 <= 1e-4 against the reference
     if precise:
-        assert l1_64 <= 2e-6                 # we are at the fp64 answer
-        assert l1_ref <= 1e-4 + floor        # so the distance to the reference is the reference's noise
+        assert l1_64 <= floor                # closer to the fp64 answer than the reference itself
     else:
-        assert l1_64 <= 3 * floor + 1e-5
+        assert l1_64 <= 2 * floor + 1e-5
 
 
 def test_postprocess(cuda_device):
@@ -98,8 +98,9 @@ def test_snake_f32(cuda_device):
         y = torch.empty_like(x).cuda()
         a = torch.exp(alpha).cuda()
         ib = (1.0 / (torch.exp(beta) + 1e-9)).cuda()
-        eng._call("fh_snake_aa_f32", x.cuda().data_ptr(), y.data_ptr(), a.data_ptr(), ib.data_ptr(),
-                  filt.flatten().cuda().data_ptr(), B, Cc, L, eng.stream)
+        xd, fd = x.cuda(), filt.flatten().cuda()  # keep the device tensors alive across the launch
+        eng._call("fh_snake_aa_f32", xd.data_ptr(), y.data_ptr(), a.data_ptr(), ib.data_ptr(), fd.data_ptr(), B, Cc, L,
+                  eng.stream)
         assert float((y.cpu() - ref).abs().max()) <= 5e-6
 
 
