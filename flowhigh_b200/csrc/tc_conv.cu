@@ -22,8 +22,7 @@
 namespace {
 
 constexpr int kMaxTapOff = 64;
-constexpr int kARowsPad = 192;                 // rows reserved per chunk window in an A slot
-constexpr int kASlotBytes = 2 * kARowsPad * 16;  // two 8-channel chunks
+constexpr int kMaxSpan = 64;                   // max (max_off - min_off) of the taps of one phase
 constexpr int kMaxStages = 8;
 constexpr int kThreads = 192;                  // 6 warps
 
@@ -43,7 +42,9 @@ struct TcParams {
   int m_tiles, n_tiles, total_tiles;
   int ci_pairs;        // Cin / 16
   int tg, n_groups;    // taps per smem stage, groups per ci-pair
-  int wrows;           // rows fetched per chunk window: 128 + (max_off - min_off)
+  int msub;            // 128-row sub-tiles per CTA tile (1, 2 or 4): B operand reuse + epilogue MLP
+  int wrows;           // rows fetched per chunk window: 128*msub + (max_off - min_off)
+  int arows_pad;       // rows reserved per chunk window in an A slot
   int stages, stage_bytes;
   int min_off[16];
   int tap_off[kMaxTapOff];
@@ -153,6 +154,35 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int id) {
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // ------------------------------------------------------------------------------ the kernel
+// residual rows for one 16-column group (two 8-channel chunks) of one output row
+__device__ __forceinline__ void load_res16(const TcParams& P, long long rbase, int n0, bool ok, float (&r)[16]) {
+#pragma unroll
+  for (int hh = 0; hh < 2; ++hh) {
+    const int n = n0 + hh * 8;
+    if (!ok || n >= P.Cout) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[hh * 8 + i] = 0.f;
+      continue;
+    }
+    const long long ridx = rbase + (long long)(n >> 3) * P.res_chunk;
+    if (P.res_is_bf16) {
+      const uint4 raw = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)P.res + ridx);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __bfloat1622float2(h[i]);
+        r[hh * 8 + 2 * i] = f.x;
+        r[hh * 8 + 2 * i + 1] = f.y;
+      }
+    } else {
+      const float4* rp = reinterpret_cast<const float4*>((const float*)P.res + ridx);
+      const float4 r0 = rp[0], r1 = rp[1];
+      r[hh * 8 + 0] = r0.x, r[hh * 8 + 1] = r0.y, r[hh * 8 + 2] = r0.z, r[hh * 8 + 3] = r0.w;
+      r[hh * 8 + 4] = r1.x, r[hh * 8 + 5] = r1.y, r[hh * 8 + 6] = r1.z, r[hh * 8 + 7] = r1.w;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // [0,256): barriers; [256,260): tmem base; stages from 1024
@@ -182,7 +212,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   const uint32_t tmem_base = *tmem_slot;
 
   const int steps_per_tile = P.ci_pairs * P.n_groups;
-  const uint32_t b_tap_bytes = (uint32_t)P.bn * 32u;  // one tap: 2 chunks x bn rows x 16 B
+  const uint32_t b_tap_bytes = (uint32_t)P.bn * 32u;     // one tap: 2 chunks x bn rows x 16 B
+  const uint32_t a_chunk_bytes = (uint32_t)P.arows_pad * 16u;  // one chunk window slot
+  const uint32_t a_slot_bytes = 2u * a_chunk_bytes;
+  const int tile_rows = 128 * P.msub;
+  const uint32_t acc_cols = (uint32_t)(P.msub * P.bn);   // TMEM columns of one accumulator stage
 
   if (warp == 0) {
     // ===================================================================== producer
@@ -190,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       int stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const TileCoord tc = decode_tile(P, tile);
-        const long long row = (long long)P.a_row0 + (long long)tc.mt * 128 + P.min_off[tc.p];
+        const long long row = (long long)P.a_row0 + (long long)tc.mt * tile_rows + P.min_off[tc.p];
         const __nv_bfloat16* a_base = P.a + (long long)tc.b * P.a_batch + row * 8;
         // packed weights: [p][nt][cp][tap][2][bn][8]
         const __nv_bfloat16* w_base =
@@ -205,8 +239,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             const uint32_t a_bytes = (uint32_t)P.wrows * 16u;
             mbar_expect_tx(fb, 2u * a_bytes + (uint32_t)nt_g * b_tap_bytes);
             bulk_g2s(sa, a_base + (long long)(2 * cp) * P.a_chunk, a_bytes, fb);
-            bulk_g2s(sa + kARowsPad * 16, a_base + (long long)(2 * cp + 1) * P.a_chunk, a_bytes, fb);
-            bulk_g2s(sa + kASlotBytes, w_base + ((long long)cp * P.ntaps + tap0) * ((long long)P.bn * 16),
+            bulk_g2s(sa + a_chunk_bytes, a_base + (long long)(2 * cp + 1) * P.a_chunk, a_bytes, fb);
+            bulk_g2s(sa + a_slot_bytes, w_base + ((long long)cp * P.ntaps + tap0) * ((long long)P.bn * 16),
                      (uint32_t)nt_g * b_tap_bytes, fb);
             if (++stage == S) {
               stage = 0;
@@ -225,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
         const TileCoord tc = decode_tile(P, tile);
         mbar_wait(tempty0 + 8 * as, aphase ^ 1, P.err_flag, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * P.bn);
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
         const int* offs = P.tap_off + tc.p * P.ntaps;
         const int mn = P.min_off[tc.p];
         uint32_t first = 1;
@@ -236,11 +270,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
           mbar_wait(full0 + 8 * stage, phase, P.err_flag, 3);
           tc_fence_after();
           const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
-          const uint32_t sb = sa + kASlotBytes;
+          const uint32_t sb = sa + a_slot_bytes;
           for (int j = 0; j < nt_g; ++j) {
-            const uint64_t adesc = make_desc(sa + (uint32_t)(offs[tap0 + j] - mn) * 16u, kARowsPad * 16, 128);
             const uint64_t bdesc = make_desc(sb + (uint32_t)j * b_tap_bytes, (uint32_t)P.bn * 16u, 128);
-            umma_bf16(d_tmem, adesc, bdesc, idesc, first ? 0u : 1u);
+            const uint32_t a0 = sa + (uint32_t)(offs[tap0 + j] - mn) * 16u;
+            for (int sub = 0; sub < P.msub; ++sub) {
+              // the tap shift and the 128-row sub-tile are both plain start-address offsets
+              const uint64_t adesc = make_desc(a0 + (uint32_t)sub * 2048u, a_chunk_bytes, 128);
+              umma_bf16(d_tmem + (uint32_t)(sub * P.bn), adesc, bdesc, idesc, first ? 0u : 1u);
+            }
             first = 0;
           }
           umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
@@ -261,100 +299,100 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     const int lane_grp = warp & 3;  // TMEM lanes 32*lane_grp .. +31 are accessible to this warp
     const int r = lane_grp * 32 + lane;
     int as = 0, aphase = 0;
+    const int groups_per_sub = P.bn >> 4;
+    const int n_groups_total = P.msub * groups_per_sub;
+    const bool use_res = P.res != nullptr && !P.geglu;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(P, tile);
+      const int n_base = tc.nt * P.bn;
+      const int t_base = tc.mt * tile_rows + r;
+      // residual of the first column group is fetched BEFORE waiting for the accumulator
+      float rcur[16], rnext[16];
+      if (use_res) {
+        const long long orow0 = (long long)t_base * P.P + tc.p;
+        load_res16(P, (long long)tc.b * P.res_batch + orow0 * P.res_row, n_base, t_base < P.L, rcur);
+      }
       mbar_wait(tfull0 + 8 * as, aphase, P.err_flag, 4);
       tc_fence_after();
-      const int t = tc.mt * 128 + r;
-      const bool row_ok = t < P.L;
-      const long long orow = (long long)t * P.P + tc.p;
-      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(as * P.bn);
-      const int n_base = tc.nt * P.bn;
-      for (int c0 = 0; c0 < P.bn; c0 += 16) {
-        if (n_base + c0 >= P.Cout) break;  // warp-uniform
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)as * acc_cols;
+      for (int gi = 0; gi < n_groups_total; ++gi) {
+        const int sub = gi / groups_per_sub, c0 = (gi - sub * groups_per_sub) << 4;
+        const int t = t_base + sub * 128;
+        const bool row_ok = t < P.L;
+        const long long orow = (long long)t * P.P + tc.p;
+        const bool col_ok = n_base + c0 < P.Cout;  // warp-uniform
         uint32_t v[16];
-        tmem_ld16(taddr + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (!row_ok) continue;
-        if (P.geglu) {
-          // columns (2i, 2i+1) = (x_i, gate_i) -> gelu(gate) * x ; 16 columns -> one 8-channel chunk
-          const int n_out = (n_base + c0) >> 1;
-          float o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int n = n_base + c0 + 2 * i;
-            float xv = __uint_as_float(v[2 * i]), gv = __uint_as_float(v[2 * i + 1]);
-            if (P.bias) {
-              xv += __ldg(P.bias + n);
-              gv += __ldg(P.bias + n + 1);
-            }
-            o[i] = gelu_f(gv) * xv;
-          }
-          const long long idx = (long long)tc.b * P.out_batch + (long long)(n_out >> 3) * P.out_chunk + orow * P.out_row;
-          if (P.out_is_bf16) {
-            __nv_bfloat162 h[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-            *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
-          } else {
-            float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
-            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-          }
-          continue;
+        if (col_ok) tmem_ld16(taddr + (uint32_t)(sub * P.bn + c0), v);
+        if (use_res && gi + 1 < n_groups_total) {
+          const int sub2 = (gi + 1) / groups_per_sub, c2 = ((gi + 1) - sub2 * groups_per_sub) << 4;
+          const int t2 = t_base + sub2 * 128;
+          load_res16(P, (long long)tc.b * P.res_batch + ((long long)t2 * P.P + tc.p) * P.res_row, n_base + c2,
+                     t2 < P.L, rnext);
         }
+        if (col_ok) tmem_ld_wait();
+        if (col_ok && row_ok) {
+          if (P.geglu) {
+            // columns (2i, 2i+1) = (x_i, gate_i) -> gelu(gate) * x ; 16 columns -> one 8-channel chunk
+            const int n_out = (n_base + c0) >> 1;
+            float o[8];
 #pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int n0 = n_base + c0 + hh * 8;
-          if (n0 >= P.Cout) break;
-          float o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float acc = __uint_as_float(v[hh * 8 + i]);
-            if (P.bias) acc += __ldg(P.bias + n0 + i);
-            o[i] = acc * P.alpha;
-          }
-          if (P.res) {
-            const long long ridx =
-                (long long)tc.b * P.res_batch + (long long)(n0 >> 3) * P.res_chunk + orow * P.res_row;
-            if (P.res_is_bf16) {
-              const uint4 raw = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)P.res + ridx);
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __bfloat1622float2(h[i]);
-                o[2 * i] = fmaf(P.beta_res, f.x, o[2 * i]);
-                o[2 * i + 1] = fmaf(P.beta_res, f.y, o[2 * i + 1]);
+            for (int i = 0; i < 8; ++i) {
+              const int n = n_base + c0 + 2 * i;
+              float xv = __uint_as_float(v[2 * i]), gv = __uint_as_float(v[2 * i + 1]);
+              if (P.bias) {
+                xv += __ldg(P.bias + n);
+                gv += __ldg(P.bias + n + 1);
               }
-            } else {
-              const float4* rp = reinterpret_cast<const float4*>((const float*)P.res + ridx);
-              const float4 r0 = rp[0], r1 = rp[1];
-              o[0] = fmaf(P.beta_res, r0.x, o[0]);
-              o[1] = fmaf(P.beta_res, r0.y, o[1]);
-              o[2] = fmaf(P.beta_res, r0.z, o[2]);
-              o[3] = fmaf(P.beta_res, r0.w, o[3]);
-              o[4] = fmaf(P.beta_res, r1.x, o[4]);
-              o[5] = fmaf(P.beta_res, r1.y, o[5]);
-              o[6] = fmaf(P.beta_res, r1.z, o[6]);
-              o[7] = fmaf(P.beta_res, r1.w, o[7]);
+              o[i] = gelu_f(gv) * xv;
             }
-          }
-          const long long idx = (long long)tc.b * P.out_batch + (long long)(n0 >> 3) * P.out_chunk + orow * P.out_row;
-          if (P.out_is_bf16) {
-            __nv_bfloat162 h[4];
+            const long long idx =
+                (long long)tc.b * P.out_batch + (long long)(n_out >> 3) * P.out_chunk + orow * P.out_row;
+            if (P.out_is_bf16) {
+              __nv_bfloat162 h[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-            *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
-          } else {
-            float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
-            if (P.accumulate) {
-              const float4 p0 = dst[0], p1 = dst[1];
-              o[0] += p0.x, o[1] += p0.y, o[2] += p0.z, o[3] += p0.w;
-              o[4] += p1.x, o[5] += p1.y, o[6] += p1.z, o[7] += p1.w;
+              for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+              *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
+            } else {
+              float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
+              dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+              dst[1] = make_float4(o[4], o[5], o[6], o[7]);
             }
-            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          } else {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              const int n0 = n_base + c0 + hh * 8;
+              if (n0 >= P.Cout) break;
+              float o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float acc = __uint_as_float(v[hh * 8 + i]);
+                if (P.bias) acc += __ldg(P.bias + n0 + i);
+                o[i] = acc * P.alpha;
+                if (use_res) o[i] = fmaf(P.beta_res, rcur[hh * 8 + i], o[i]);
+              }
+              const long long idx =
+                  (long long)tc.b * P.out_batch + (long long)(n0 >> 3) * P.out_chunk + orow * P.out_row;
+              if (P.out_is_bf16) {
+                __nv_bfloat162 h[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+                *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
+              } else {
+                float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
+                if (P.accumulate) {
+                  const float4 p0 = dst[0], p1 = dst[1];
+                  o[0] += p0.x, o[1] += p0.y, o[2] += p0.z, o[3] += p0.w;
+                  o[4] += p1.x, o[5] += p1.y, o[6] += p1.z, o[7] += p1.w;
+                }
+                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+              }
+            }
           }
+        }
+        if (use_res) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) rcur[i] = rnext[i];
         }
       }
       // all TMEM reads of this warp are complete (wait::ld above) -> release the accumulator
@@ -449,8 +487,13 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv_bf16(const fh_t
   p.accumulate = a->accumulate, p.geglu = a->geglu;
   p.alpha = a->alpha, p.beta_res = a->beta_res;
   p.B = a->B, p.L = a->L, p.Cin = a->Cin, p.Cout = a->Cout, p.ntaps = a->ntaps, p.P = a->P, p.bn = a->bn;
-  p.m_tiles = (a->L + 127) / 128;
   p.n_tiles = (a->Cout + a->bn - 1) / a->bn;
+  // sub-tiles: reuse each weight slot for up to 4 x 128 rows when the accumulators fit TMEM twice over
+  int msub = 256 / a->bn;
+  msub = msub >= 4 ? 4 : (msub >= 2 ? 2 : 1);
+  while (msub > 1 && (long long)a->B * a->P * ((a->L + 128 * msub - 1) / (128 * msub)) * p.n_tiles < 2 * 148) msub >>= 1;
+  p.msub = msub;
+  p.m_tiles = (a->L + 128 * msub - 1) / (128 * msub);
   const long long total = (long long)p.B * p.P * p.m_tiles * p.n_tiles;
   FH_REQUIRE(total < (1ll << 31), FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: too many tiles");
   p.total_tiles = (int)total;
@@ -469,16 +512,16 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv_bf16(const fh_t
     FH_REQUIRE(a->a_row0 + mn >= 0, FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: left halo %d too small for tap offset %d",
                a->a_row0, mn);
   }
-  p.wrows = 128 + span;
-  FH_REQUIRE(p.wrows <= kARowsPad, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv_bf16: tap span %d exceeds %d rows", span,
-             kARowsPad - 128);
+  FH_REQUIRE(span <= kMaxSpan, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv_bf16: tap span %d exceeds %d rows", span, kMaxSpan);
+  p.wrows = 128 * msub + span;
+  p.arows_pad = 128 * msub + kMaxSpan;
   // taps per stage: keep a B slot <= 32 KB
   int tg = 32768 / (a->bn * 32);
   if (tg < 1) tg = 1;
   if (tg > a->ntaps) tg = a->ntaps;
   p.tg = tg;
   p.n_groups = (a->ntaps + tg - 1) / tg;
-  p.stage_bytes = kASlotBytes + tg * a->bn * 32;
+  p.stage_bytes = 2 * p.arows_pad * 16 + tg * a->bn * 32;
   p.stage_bytes = (p.stage_bytes + 127) & ~127;
   const int budget = 200 * 1024;
   int stages = (budget - 1024) / p.stage_bytes;
