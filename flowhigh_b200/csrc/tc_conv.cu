@@ -93,6 +93,15 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
@@ -206,10 +215,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + P.P * P.ntaps) {
+    const int i = threadIdx.x - 64;
+    reinterpret_cast<int*>(smem + 512)[i] = P.tap_off[i] - P.min_off[i / P.ntaps];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  int* s_off = reinterpret_cast<int*>(smem + 512);  // [P][ntaps] tap offsets relative to the phase minimum
 
   const int steps_per_tile = P.ci_pairs * P.n_groups;
   const uint32_t b_tap_bytes = (uint32_t)P.bn * 32u;     // one tap: 2 chunks x bn rows x 16 B
@@ -252,46 +266,53 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      int stage = 0, phase = 0, as = 0, aphase = 0;
-      const uint32_t idesc = make_idesc(P.bn);
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(P, tile);
-        mbar_wait(tempty0 + 8 * as, aphase ^ 1, P.err_flag, 2);
+    // The whole warp walks the (warp-uniform) loops so that descriptors stay in uniform registers;
+    // only the tcgen05.mma / tcgen05.commit instructions are predicated on one elected lane.
+    const bool leader = elect_one();
+    int stage = 0, phase = 0, as = 0, aphase = 0;
+    const uint32_t idesc = make_idesc(P.bn);
+    const uint64_t adesc_c = make_desc(0, a_chunk_bytes, 128);
+    const uint64_t bdesc_c = make_desc(0, (uint32_t)P.bn * 16u, 128);
+    const uint32_t b_tap_u = b_tap_bytes >> 4;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(P, tile);
+      mbar_wait(tempty0 + 8 * as, aphase ^ 1, P.err_flag, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
+      const int* offs = s_off + tc.p * P.ntaps;  // (tap offset - min offset): rows == 16-byte descriptor units
+      uint32_t accum = 0;
+      for (int step = 0; step < steps_per_tile; ++step) {
+        const int g = step % P.n_groups;
+        const int tap0 = g * P.tg;
+        const int nt_g = min(P.tg, P.ntaps - tap0);
+        mbar_wait(full0 + 8 * stage, phase, P.err_flag, 3);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
-        const int* offs = P.tap_off + tc.p * P.ntaps;
-        const int mn = P.min_off[tc.p];
-        uint32_t first = 1;
-        for (int step = 0; step < steps_per_tile; ++step) {
-          const int g = step % P.n_groups;
-          const int tap0 = g * P.tg;
-          const int nt_g = min(P.tg, P.ntaps - tap0);
-          mbar_wait(full0 + 8 * stage, phase, P.err_flag, 3);
-          tc_fence_after();
-          const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
-          const uint32_t sb = sa + a_slot_bytes;
+        const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
+        const uint64_t ad0 = adesc_c + (uint64_t)(sa >> 4);
+        uint64_t bd = bdesc_c + (uint64_t)((sa + a_slot_bytes) >> 4);
+        if (leader) {
           for (int j = 0; j < nt_g; ++j) {
-            const uint64_t bdesc = make_desc(sb + (uint32_t)j * b_tap_bytes, (uint32_t)P.bn * 16u, 128);
-            const uint32_t a0 = sa + (uint32_t)(offs[tap0 + j] - mn) * 16u;
-            for (int sub = 0; sub < P.msub; ++sub) {
-              // the tap shift and the 128-row sub-tile are both plain start-address offsets
-              const uint64_t adesc = make_desc(a0 + (uint32_t)sub * 2048u, a_chunk_bytes, 128);
-              umma_bf16(d_tmem + (uint32_t)(sub * P.bn), adesc, bdesc, idesc, first ? 0u : 1u);
-            }
-            first = 0;
+            // the tap shift and the 128-row sub-tile are both plain start-address offsets
+            const uint64_t ad = ad0 + (uint64_t)(uint32_t)offs[tap0 + j];
+            for (int sub = 0; sub < P.msub; ++sub)
+              umma_bf16(d_tmem + (uint32_t)(sub * P.bn), ad + (uint64_t)(sub * 128), bd, idesc, accum);
+            accum = 1;
+            bd += b_tap_u;
           }
           umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(tfull0 + 8 * as);  // accumulator complete -> epilogue
-        if (++as == 2) {
-          as = 0;
-          aphase ^= 1;
+        accum = 1;
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
         }
+      }
+      if (leader) umma_commit(tfull0 + 8 * as);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++as == 2) {
+        as = 0;
+        aphase ^= 1;
       }
     }
   } else {
