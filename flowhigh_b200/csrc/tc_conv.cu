@@ -24,7 +24,7 @@ namespace {
 constexpr int kMaxTapOff = 64;
 constexpr int kMaxSpan = 64;                   // max (max_off - min_off) of the taps of one phase
 constexpr int kMaxStages = 8;
-constexpr int kThreads = 192;                  // 6 warps
+constexpr int kThreads = 320;                  // 10 warps: producer, MMA, 8 epilogue
 
 struct TcParams {
   const __nv_bfloat16* a;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, 4);
+      mbar_init(tempty0 + 8 * i, 8);
     }
     fence_barrier_init();
   }
@@ -316,8 +316,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
-    const int lane_grp = warp & 3;  // TMEM lanes 32*lane_grp .. +31 are accessible to this warp
+    // ===================================================================== epilogue (warps 2..9)
+    // Two warps per TMEM lane group (a warp may only touch lanes 32*(warp%4)..+31); the pair splits
+    // the 16-column groups of a tile even/odd.  Per warp the groups are software-pipelined:
+    // tcgen05.ld of group i+1 and the residual loads of group i+1 are in flight while group i is
+    // scaled, added and stored.
+    const int lane_grp = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = lane_grp * 32 + lane;
     int as = 0, aphase = 0;
     const int groups_per_sub = P.bn >> 4;
@@ -327,96 +332,109 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       const TileCoord tc = decode_tile(P, tile);
       const int n_base = tc.nt * P.bn;
       const int t_base = tc.mt * tile_rows + r;
-      // residual of the first column group is fetched BEFORE waiting for the accumulator
-      float rcur[16], rnext[16];
-      if (use_res) {
-        const long long orow0 = (long long)t_base * P.P + tc.p;
-        load_res16(P, (long long)tc.b * P.res_batch + orow0 * P.res_row, n_base, t_base < P.L, rcur);
-      }
-      mbar_wait(tfull0 + 8 * as, aphase, P.err_flag, 4);
-      tc_fence_after();
+      const long long res_b = (long long)tc.b * P.res_batch;
+      const long long out_b = (long long)tc.b * P.out_batch;
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)as * acc_cols;
-      for (int gi = 0; gi < n_groups_total; ++gi) {
-        const int sub = gi / groups_per_sub, c0 = (gi - sub * groups_per_sub) << 4;
-        const int t = t_base + sub * 128;
-        const bool row_ok = t < P.L;
+
+      auto group_coords = [&](int gi, int& sub, int& c0, int& t) {
+        sub = gi / groups_per_sub;
+        c0 = (gi - sub * groups_per_sub) << 4;
+        t = t_base + sub * 128;
+      };
+      auto fetch_res = [&](int gi, float (&rr)[16]) {
+        if (!use_res || gi >= n_groups_total) return;
+        int sub, c0, t;
+        group_coords(gi, sub, c0, t);
+        load_res16(P, res_b + ((long long)t * P.P + tc.p) * P.res_row, n_base + c0, t < P.L, rr);
+      };
+      auto issue_ld = [&](int gi, uint32_t (&v)[16]) {
+        if (gi >= n_groups_total) return;
+        int sub, c0, t;
+        group_coords(gi, sub, c0, t);
+        if (n_base + c0 < P.Cout) tmem_ld16(taddr + (uint32_t)(sub * P.bn + c0), v);  // warp-uniform
+      };
+      auto finish = [&](int gi, const uint32_t (&v)[16], const float (&rr)[16]) {
+        int sub, c0, t;
+        group_coords(gi, sub, c0, t);
+        if (n_base + c0 >= P.Cout || t >= P.L) return;
         const long long orow = (long long)t * P.P + tc.p;
-        const bool col_ok = n_base + c0 < P.Cout;  // warp-uniform
-        uint32_t v[16];
-        if (col_ok) tmem_ld16(taddr + (uint32_t)(sub * P.bn + c0), v);
-        if (use_res && gi + 1 < n_groups_total) {
-          const int sub2 = (gi + 1) / groups_per_sub, c2 = ((gi + 1) - sub2 * groups_per_sub) << 4;
-          const int t2 = t_base + sub2 * 128;
-          load_res16(P, (long long)tc.b * P.res_batch + ((long long)t2 * P.P + tc.p) * P.res_row, n_base + c2,
-                     t2 < P.L, rnext);
-        }
-        if (col_ok) tmem_ld_wait();
-        if (col_ok && row_ok) {
-          if (P.geglu) {
-            // columns (2i, 2i+1) = (x_i, gate_i) -> gelu(gate) * x ; 16 columns -> one 8-channel chunk
-            const int n_out = (n_base + c0) >> 1;
-            float o[8];
+        if (P.geglu) {
+          // columns (2i, 2i+1) = (x_i, gate_i) -> gelu(gate) * x ; 16 columns -> one 8-channel chunk
+          const int n_out = (n_base + c0) >> 1;
+          float o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int n = n_base + c0 + 2 * i;
-              float xv = __uint_as_float(v[2 * i]), gv = __uint_as_float(v[2 * i + 1]);
-              if (P.bias) {
-                xv += __ldg(P.bias + n);
-                gv += __ldg(P.bias + n + 1);
-              }
-              o[i] = gelu_f(gv) * xv;
+          for (int i = 0; i < 8; ++i) {
+            const int n = n_base + c0 + 2 * i;
+            float xv = __uint_as_float(v[2 * i]), gv = __uint_as_float(v[2 * i + 1]);
+            if (P.bias) {
+              xv += __ldg(P.bias + n);
+              gv += __ldg(P.bias + n + 1);
             }
-            const long long idx =
-                (long long)tc.b * P.out_batch + (long long)(n_out >> 3) * P.out_chunk + orow * P.out_row;
-            if (P.out_is_bf16) {
-              __nv_bfloat162 h[4];
+            o[i] = gelu_f(gv) * xv;
+          }
+          const long long idx = out_b + (long long)(n_out >> 3) * P.out_chunk + orow * P.out_row;
+          if (P.out_is_bf16) {
+            __nv_bfloat162 h[4];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-              *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
-            } else {
-              float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
-              dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-              dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-            }
+            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+            *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
           } else {
+            float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+          }
+          return;
+        }
 #pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const int n0 = n_base + c0 + hh * 8;
-              if (n0 >= P.Cout) break;
-              float o[8];
+        for (int hh = 0; hh < 2; ++hh) {
+          const int n0 = n_base + c0 + hh * 8;
+          if (n0 >= P.Cout) break;
+          float o[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                float acc = __uint_as_float(v[hh * 8 + i]);
-                if (P.bias) acc += __ldg(P.bias + n0 + i);
-                o[i] = acc * P.alpha;
-                if (use_res) o[i] = fmaf(P.beta_res, rcur[hh * 8 + i], o[i]);
-              }
-              const long long idx =
-                  (long long)tc.b * P.out_batch + (long long)(n0 >> 3) * P.out_chunk + orow * P.out_row;
-              if (P.out_is_bf16) {
-                __nv_bfloat162 h[4];
+          for (int i = 0; i < 8; ++i) {
+            float acc = __uint_as_float(v[hh * 8 + i]);
+            if (P.bias) acc += __ldg(P.bias + n0 + i);
+            o[i] = acc * P.alpha;
+            if (use_res) o[i] = fmaf(P.beta_res, rr[hh * 8 + i], o[i]);
+          }
+          const long long idx = out_b + (long long)(n0 >> 3) * P.out_chunk + orow * P.out_row;
+          if (P.out_is_bf16) {
+            __nv_bfloat162 h[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-                *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
-              } else {
-                float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
-                if (P.accumulate) {
-                  const float4 p0 = dst[0], p1 = dst[1];
-                  o[0] += p0.x, o[1] += p0.y, o[2] += p0.z, o[3] += p0.w;
-                  o[4] += p1.x, o[5] += p1.y, o[6] += p1.z, o[7] += p1.w;
-                }
-                dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-                dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-              }
+            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
+            *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
+          } else {
+            float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
+            if (P.accumulate) {
+              const float4 p0 = dst[0], p1 = dst[1];
+              o[0] += p0.x, o[1] += p0.y, o[2] += p0.z, o[3] += p0.w;
+              o[4] += p1.x, o[5] += p1.y, o[6] += p1.z, o[7] += p1.w;
             }
+            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
           }
         }
-        if (use_res) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) rcur[i] = rnext[i];
-        }
+      };
+
+      uint32_t va[16], vb[16];
+      float ra[16], rb[16];
+      fetch_res(half, ra);  // residual of the first group is requested BEFORE waiting for the accumulator
+      mbar_wait(tfull0 + 8 * as, aphase, P.err_flag, 4);
+      tc_fence_after();
+      issue_ld(half, va);
+      for (int gi = half; gi < n_groups_total; gi += 4) {
+        tmem_ld_wait();
+        issue_ld(gi + 2, vb);
+        fetch_res(gi + 2, rb);
+        finish(gi, va, ra);
+        if (gi + 2 >= n_groups_total) break;
+        tmem_ld_wait();
+        issue_ld(gi + 4, va);
+        fetch_res(gi + 4, ra);
+        finish(gi + 2, vb, rb);
       }
       // all TMEM reads of this warp are complete (wait::ld above) -> release the accumulator
+      tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * as);

@@ -10,21 +10,34 @@ namespace {
 // y[q] = sum_k f[k] s~[2q+k-5];  s[m] = u[m] + inv_b sin^2(a u[m]);  u[m] = 2 sum_i x~[i] f[m+5-2i]
 // (x~ / s~ = replicate-clamped; closed form of up2x -> snake -> down2x).
 //
-// Register-blocked: one thread owns one channel and R = 16 consecutive outputs; it keeps the
-// R + 10 inputs and the 2R + 11 intermediate 2x-rate samples in registers, so the 12 filter taps
-// are applied from registers (no shared-memory traffic in the inner loops).  A CTA covers
-// 512 time steps x 8 channels; the input tile is staged once through shared memory with a
-// 4-word pad every 8 rows, which makes the (8 channels x 4 time-groups) warp access pattern
-// bank-conflict free.  sin^2 uses the MUFU path: the argument is < ~1e2, where sin.approx's
-// absolute error (~1e-6) is far below the bf16 operand rounding that follows.
+// Register-blocked and 2-wide: one thread owns TWO adjacent channels and R = 16 consecutive
+// outputs; every filter tap is one packed FFMA2 (fma.rn.f32x2, sm_100) on a channel pair, applied
+// from registers.  sin^2(z) is evaluated as (1 - cos 2z)/2 so that
+//     s' = u - (inv_b/2) cos(2 a u),   y = sum_k f[k] s'~[.] + inv_b/2      (sum_k f[k] = 1)
+// costs one packed multiply, two MUFU.COS and one packed FMA per pair.  cos.approx's absolute
+// error (~1e-6 for |arg| < 1e2) is far below the bf16 operand rounding that follows.
+// A CTA covers 512 time steps x 8 channels; the input tile is staged once through shared memory
+// with a 4-word pad every 8 rows (conflict-free 64-bit reads for the 4 pairs x 8 groups of a warp).
 constexpr int SR = 16;                    // outputs per thread
 constexpr int SG = 32;                    // time-groups per CTA
 constexpr int STT = SR * SG;              // 512 time steps per CTA
 constexpr int SXR = STT + 10;             // staged input rows
 __host__ __device__ constexpr int sx_index(int row) { return row * 8 + (row >> 3) * 4; }
 
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 template <bool OUT_BF16>
-__global__ void __launch_bounds__(256) snake_aa_chunked_kernel(const float* __restrict__ x, void* __restrict__ y,
+__global__ void __launch_bounds__(128) snake_aa_chunked_kernel(const float* __restrict__ x, void* __restrict__ y,
                                                                const float* __restrict__ a,
                                                                const float* __restrict__ inv_b,
                                                                const float* __restrict__ filt, long long batch_stride,
@@ -38,47 +51,54 @@ __global__ void __launch_bounds__(256) snake_aa_chunked_kernel(const float* __re
   const int qt = tile * STT;
   const float* xb = x + (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)row0 * 8;
   // stage rows [qt-5, qt+STT+5), replicate-clamped, as float4 halves of each 8-channel row
-  for (int i = threadIdx.x; i < SXR * 2; i += 256) {
+  for (int i = threadIdx.x; i < SXR * 2; i += 128) {
     const int r = i >> 1, h = i & 1;
     const int t = min(max(qt - 5 + r, 0), L - 1);
     const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * 8 + h * 4));
     *reinterpret_cast<float4*>(&xs[sx_index(r) + h * 4]) = v;
   }
-  float f[12];
+  float2 fu[12], fd[12];  // up taps (x2 folded in) and down taps, broadcast to both channels
 #pragma unroll
-  for (int k = 0; k < 12; ++k) f[k] = __ldg(filt + k);
-  const int e = threadIdx.x & 7, g = threadIdx.x >> 3;
-  const float al = a[ch * 8 + e], ib = inv_b[ch * 8 + e];
+  for (int k = 0; k < 12; ++k) {
+    const float fk = __ldg(filt + k);
+    fu[k] = make_float2(2.0f * fk, 2.0f * fk);
+    fd[k] = make_float2(fk, fk);
+  }
+  const int e2 = threadIdx.x & 3, g = threadIdx.x >> 2;
+  const int c0 = ch * 8 + 2 * e2;
+  const float2 al2 = make_float2(2.0f * a[c0], 2.0f * a[c0 + 1]);
+  const float2 hib = make_float2(0.5f * inv_b[c0], 0.5f * inv_b[c0 + 1]);
+  const float2 nhib = make_float2(-hib.x, -hib.y);
   __syncthreads();
   const int q0 = qt + g * SR;  // first output of this thread
   if (q0 >= L) return;
   // inputs x~[q0-5 .. q0+SR+4]  (staged row r = q - (qt-5))
-  float xv[SR + 10];
-  const float* xp = xs + g * (SR * 8 + (SR >> 3) * 4) + e;  // sx_index(g*SR) + e; g*SR is a multiple of 8
+  float2 xv[SR + 10];
+  const float* xp = xs + g * (SR * 8 + (SR >> 3) * 4) + 2 * e2;  // sx_index(g*SR) + channel pair
 #pragma unroll
-  for (int j = 0; j < SR + 10; ++j) xv[j] = xp[j * 8 + (j >> 3) * 4];
-  // s values for m = 2*q0 - 5 + i, i in [0, 2SR+11)
-  float s[2 * SR + 10];
+  for (int j = 0; j < SR + 10; ++j) xv[j] = *reinterpret_cast<const float2*>(xp + j * 8 + (j >> 3) * 4);
+  // s' values for m = 2*q0 - 5 + i, i in [0, 2SR+10)
+  float2 s[2 * SR + 10];
 #pragma unroll
   for (int i = 0; i < 2 * SR + 10; ++i) {
-    // m = 2*q0 - 5 + i ; q = floor(m/2) = q0 + ((i - 5) >> 1) ; parity of m = parity of (i + 1)
-    const int qq = (i - 5) >> 1;  // arithmetic shift: i=0 -> -3
-    float u = 0.f;
+    // m = 2*q0 - 5 + i ; q = floor(m/2) = q0 + ((i - 5) >> 1) ; m is odd iff i is even
+    const int qq = (i - 5) >> 1;
+    float2 u = make_float2(0.f, 0.f);
     if ((i & 1) == 0) {  // m odd: inputs q+d, d = -2..3, taps 6-2d
 #pragma unroll
-      for (int d = -2; d <= 3; ++d) u = fmaf(xv[qq + d + 5], f[6 - 2 * d], u);
+      for (int d = -2; d <= 3; ++d) u = ffma2(xv[qq + d + 5], fu[6 - 2 * d], u);
     } else {  // m even: d = -3..2, taps 5-2d
 #pragma unroll
-      for (int d = -3; d <= 2; ++d) u = fmaf(xv[qq + d + 5], f[5 - 2 * d], u);
+      for (int d = -3; d <= 2; ++d) u = ffma2(xv[qq + d + 5], fu[5 - 2 * d], u);
     }
-    u *= 2.0f;
-    const float sn = __sinf(u * al);
-    s[i] = fmaf(ib, sn * sn, u);
+    const float2 z = fmul2(u, al2);
+    const float2 c = make_float2(__cosf(z.x), __cosf(z.y));
+    s[i] = ffma2(c, nhib, u);
   }
   // replicate-clamp of the 2x-rate signal at the sequence ends (only boundary threads)
   if (q0 == 0 || q0 + SR + 3 >= L) {
     const int ic = 2 * (L - q0) + 5;  // first i with m >= 2L
-    float prev = s[5];                // m = 0 when q0 == 0
+    float2 prev = s[5];               // m = 0 when q0 == 0
 #pragma unroll
     for (int i = 0; i < 2 * SR + 10; ++i) {
       if (q0 == 0 && i < 5) s[i] = prev;
@@ -86,17 +106,17 @@ __global__ void __launch_bounds__(256) snake_aa_chunked_kernel(const float* __re
       else s[i] = prev;
     }
   }
-  const long long obase = (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)(row0 + q0) * 8 + e;
+  const long long obase = (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)(row0 + q0) * 8 + 2 * e2;
 #pragma unroll
   for (int j = 0; j < SR; ++j) {
     if (q0 + j < L) {
-      float acc = 0.f;
+      float2 acc = hib;
 #pragma unroll
-      for (int k = 0; k < 12; ++k) acc = fmaf(f[k], s[2 * j + k], acc);
+      for (int k = 0; k < 12; ++k) acc = ffma2(fd[k], s[2 * j + k], acc);
       if (OUT_BF16)
-        ((__nv_bfloat16*)y)[obase + j * 8] = __float2bfloat16(acc);
+        *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)y + obase + j * 8) = __floats2bfloat162_rn(acc.x, acc.y);
       else
-        ((float*)y)[obase + j * 8] = acc;
+        *reinterpret_cast<float2*>((float*)y + obase + j * 8) = acc;
     }
   }
 }
@@ -142,10 +162,10 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
   const long long nblk = (long long)((L + STT - 1) / STT) * (C / 8) * B;
   FH_REQUIRE(nblk <= 2147483647LL, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: grid too large");
   if (out_is_bf16)
-    snake_aa_chunked_kernel<true><<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(x, y, a, inv_b, filt, batch_stride,
+    snake_aa_chunked_kernel<true><<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(x, y, a, inv_b, filt, batch_stride,
                                                                                  chunk_stride, row0, C / 8, L);
   else
-    snake_aa_chunked_kernel<false><<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(
+    snake_aa_chunked_kernel<false><<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(
         x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L);
   return fh::check_launch("fh_snake_aa_chunked");
 }
