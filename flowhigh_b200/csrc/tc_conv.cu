@@ -17,6 +17,7 @@
 // the epilogue (bias, alpha, residual, accumulate, GEGLU, bf16/fp32, chunked or row-major output)
 // reads them with tcgen05.ld.  Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer +
 // TMEM allocator, warps 2..5 = epilogue.  Persistent CTAs, static tile striding.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -562,7 +563,13 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv_bf16(const fh_t
   p.n_groups = (a->ntaps + tg - 1) / tg;
   p.stage_bytes = 2 * p.arows_pad * 16 + tg * a->bn * 32;
   p.stage_bytes = (p.stage_bytes + 127) & ~127;
-  const int budget = 200 * 1024;
+  static int budget_kb = 0;
+  if (!budget_kb) {
+    const char* e = getenv("FH_TC_SMEM_KB");
+    budget_kb = e ? atoi(e) : 200;
+    if (budget_kb < 64 || budget_kb > 220) budget_kb = 200;
+  }
+  const int budget = budget_kb * 1024;
   int stages = (budget - 1024) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   FH_REQUIRE(stages >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv_bf16: stage of %d bytes does not fit twice", p.stage_bytes);

@@ -2,6 +2,7 @@
 // fh_tc_conv_bf16 consumes: fused anti-aliased Snake/SnakeBeta (alias_free_torch/act.py:23-28,
 // resample.py:25-33, filter.py:86-94, activations.py:48-59,107-119) and conv_post + tanh
 // (bigvgan/models.py:189-192).  The residual stream stays fp32; only MMA operands are bf16.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace {
@@ -121,6 +122,87 @@ __global__ void __launch_bounds__(128) snake_aa_chunked_kernel(const float* __re
   }
 }
 
+// scalar variant (one channel per thread, 256 threads): kept selectable, see fh_snake_aa_chunked
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(256) snake_aa_chunked_scalar_kernel(const float* __restrict__ x, void* __restrict__ y,
+                                                               const float* __restrict__ a,
+                                                               const float* __restrict__ inv_b,
+                                                               const float* __restrict__ filt, long long batch_stride,
+                                                               long long chunk_stride, int row0, int nchunk, int L) {
+  __shared__ __align__(16) float xs[sx_index(SXR) + 8];
+  const int ntile = (L + STT - 1) / STT;
+  int id = blockIdx.x;
+  const int tile = id % ntile;
+  id /= ntile;
+  const int ch = id % nchunk, b = id / nchunk;
+  const int qt = tile * STT;
+  const float* xb = x + (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)row0 * 8;
+  // stage rows [qt-5, qt+STT+5), replicate-clamped, as float4 halves of each 8-channel row
+  for (int i = threadIdx.x; i < SXR * 2; i += 256) {
+    const int r = i >> 1, h = i & 1;
+    const int t = min(max(qt - 5 + r, 0), L - 1);
+    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * 8 + h * 4));
+    *reinterpret_cast<float4*>(&xs[sx_index(r) + h * 4]) = v;
+  }
+  float f[12], fu[12];  // down taps; up taps with the x2 gain folded in
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    f[k] = __ldg(filt + k);
+    fu[k] = 2.0f * f[k];
+  }
+  const int e = threadIdx.x & 7, g = threadIdx.x >> 3;
+  const float al2 = 2.0f * a[ch * 8 + e], hib = 0.5f * inv_b[ch * 8 + e];
+  __syncthreads();
+  const int q0 = qt + g * SR;  // first output of this thread
+  if (q0 >= L) return;
+  // inputs x~[q0-5 .. q0+SR+4]  (staged row r = q - (qt-5))
+  float xv[SR + 10];
+  const float* xp = xs + g * (SR * 8 + (SR >> 3) * 4) + e;  // sx_index(g*SR) + e; g*SR is a multiple of 8
+#pragma unroll
+  for (int j = 0; j < SR + 10; ++j) xv[j] = xp[j * 8 + (j >> 3) * 4];
+  // s values for m = 2*q0 - 5 + i, i in [0, 2SR+11)
+  float s[2 * SR + 10];
+#pragma unroll
+  for (int i = 0; i < 2 * SR + 10; ++i) {
+    // m = 2*q0 - 5 + i ; q = floor(m/2) = q0 + ((i - 5) >> 1) ; parity of m = parity of (i + 1)
+    const int qq = (i - 5) >> 1;  // arithmetic shift: i=0 -> -3
+    float u = 0.f;
+    if ((i & 1) == 0) {  // m odd: inputs q+d, d = -2..3, taps 6-2d
+#pragma unroll
+      for (int d = -2; d <= 3; ++d) u = fmaf(xv[qq + d + 5], fu[6 - 2 * d], u);
+    } else {  // m even: d = -3..2, taps 5-2d
+#pragma unroll
+      for (int d = -3; d <= 2; ++d) u = fmaf(xv[qq + d + 5], fu[5 - 2 * d], u);
+    }
+    s[i] = fmaf(-hib, __cosf(u * al2), u);  // s - inv_b/2, see the header comment
+  }
+  // replicate-clamp of the 2x-rate signal at the sequence ends (only boundary threads)
+  if (q0 == 0 || q0 + SR + 3 >= L) {
+    const int ic = 2 * (L - q0) + 5;  // first i with m >= 2L
+    float prev = s[5];                // m = 0 when q0 == 0
+#pragma unroll
+    for (int i = 0; i < 2 * SR + 10; ++i) {
+      if (q0 == 0 && i < 5) s[i] = prev;
+      if (i < ic) prev = s[i];
+      else s[i] = prev;
+    }
+  }
+  const long long obase = (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)(row0 + q0) * 8 + e;
+#pragma unroll
+  for (int j = 0; j < SR; ++j) {
+    if (q0 + j < L) {
+      float acc = hib;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) acc = fmaf(f[k], s[2 * j + k], acc);
+      if (OUT_BF16)
+        ((__nv_bfloat16*)y)[obase + j * 8] = __float2bfloat16(acc);
+      else
+        ((float*)y)[obase + j * 8] = acc;
+    }
+  }
+}
+
+
 __global__ void convpost_tanh_chunked_kernel(const float* __restrict__ x, long long batch_stride,
                                              long long chunk_stride, int row0, const float* __restrict__ w, float bias,
                                              float* __restrict__ y, int C, int L) {
@@ -161,12 +243,26 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
              "fh_snake_aa_chunked: x must be 16-byte aligned");
   const long long nblk = (long long)((L + STT - 1) / STT) * (C / 8) * B;
   FH_REQUIRE(nblk <= 2147483647LL, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: grid too large");
-  if (out_is_bf16)
-    snake_aa_chunked_kernel<true><<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(x, y, a, inv_b, filt, batch_stride,
-                                                                                 chunk_stride, row0, C / 8, L);
-  else
-    snake_aa_chunked_kernel<false><<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(
-        x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L);
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("FH_SNAKE_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+  if (variant == 1) {  // packed-FFMA2, two channels per thread
+    if (out_is_bf16)
+      snake_aa_chunked_kernel<true><<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(
+          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L);
+    else
+      snake_aa_chunked_kernel<false><<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(
+          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L);
+  } else {
+    if (out_is_bf16)
+      snake_aa_chunked_scalar_kernel<true><<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(
+          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L);
+    else
+      snake_aa_chunked_scalar_kernel<false><<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(
+          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L);
+  }
   return fh::check_launch("fh_snake_aa_chunked");
 }
 

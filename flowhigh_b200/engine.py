@@ -55,6 +55,9 @@ class Engine:
         self.precise_mel = (precision == "fp32") if precise_mel is None else precise_mel
         self._bufs: Dict[tuple, torch.Tensor] = {}
         self.profile = None
+        import os as _os
+        self.voc_streams = int(_os.environ.get("FH_VOC_STREAMS", "1"))
+        self._side_streams = []
         self._time_cache: Dict[float, dict] = {}
         dev = self.device
         with torch.cuda.device(dev):
@@ -425,7 +428,36 @@ class Engine:
     # ------------------------------------------------------------------ stage: vocoder
     def vocoder(self, mel: torch.Tensor) -> torch.Tensor:
         """MelVoco.decode (melvoco.py:114-121): mel [B,N,256] -> wave [B, 480 N]."""
-        return self._vocoder_tc(mel) if self.tc else self._vocoder_f32(mel)
+        if not self.tc:
+            return self._vocoder_f32(mel)
+        B, N, _ = mel.shape
+        ns = min(self.voc_streams, B)
+        wave = torch.empty((B, N * self.vcfg.total_upsample), dtype=torch.float32, device=self.device)
+        if ns <= 1:
+            self._vocoder_tc(mel, wave, "")
+            return wave
+        # Clips are independent: run halves of the batch on separate streams, staggered by one kernel,
+        # so that the FP32-pipe-bound snake kernel of one half overlaps the tensor/HBM-bound conv of the other.
+        main = torch.cuda.current_stream(self.device)
+        ev0 = torch.cuda.Event()
+        ev0.record(main)
+        while len(self._side_streams) < ns:
+            self._side_streams.append(torch.cuda.Stream(self.device))
+        bounds = [B * i // ns for i in range(ns + 1)]
+        prev_started = None
+        for i in range(ns):
+            st = self._side_streams[i]
+            st.wait_event(ev0)
+            if prev_started is not None:
+                st.wait_event(prev_started)
+            started = torch.cuda.Event()
+            with torch.cuda.stream(st):
+                self._vocoder_tc(mel[bounds[i]: bounds[i + 1]], wave[bounds[i]: bounds[i + 1]], f"s{i}", started)
+            prev_started = started
+            done = torch.cuda.Event()
+            done.record(st)
+            main.wait_event(done)
+        return wave
 
     def _conv_f32(self, rec: _F32Weight, x, out, B, L, res=None, beta=0.0, alpha=1.0, accumulate=0):
         self._call("fh_conv1d_taps_f32", x.data_ptr(), rec.w.data_ptr(), _ptr(rec.bias), rec.off.data_ptr(), _ptr(res),
@@ -491,14 +523,16 @@ class Engine:
         t = self.buf(name, (B * bs + 4096,), dtype)  # zero-initialised: halos stay zero forever
         return t, cs, bs
 
-    def _vocoder_tc(self, mel: torch.Tensor) -> torch.Tensor:
+    def _vocoder_tc(self, mel: torch.Tensor, wave: torch.Tensor, tag: str, started_event=None):
         v, V, st = self.vcfg, self.voc, self.stream
         B, N, nm = mel.shape
         bf, f32 = torch.bfloat16, torch.float32
-        melc, mcs, mbs = self._cbuf("vt_mel", B, nm, N, bf)
+        _cb = self._cbuf
+        self_cbuf = lambda name, *a: _cb(name + tag, *a)
+        melc, mcs, mbs = self_cbuf("vt_mel", B, nm, N, bf)
         self._call("fh_to_chunked_bf16", mel.data_ptr(), N * nm, 1, nm, melc.data_ptr(), mbs, mcs, HALO, B, nm, N, st)
         C0 = self.cpad(v.upsample_initial_channel)
-        xb, xcs, xbs = self._cbuf("vt_pre", B, C0, N, bf)
+        xb, xcs, xbs = self_cbuf("vt_pre", B, C0, N, bf)
         self._tc_conv(V["conv_pre"], melc, mbs, mcs, HALO, xb[HALO * 8:], (xbs, xcs, 8), 1, B, N)
         L = N
         nk = v.num_kernels
@@ -506,11 +540,11 @@ class Engine:
         for s, u in enumerate(v.upsample_rates):
             ch = self.cpad(v.stage_channels(s))
             Lo = L * u
-            X, cs, bs = self._cbuf(f"vt_X{s}", B, ch, Lo, f32)
-            XJ, _, _ = self._cbuf(f"vt_XJ{s}", B, ch, Lo, f32)
-            Y, _, _ = self._cbuf(f"vt_Y{s}", B, ch, Lo, f32)
-            XS, _, _ = self._cbuf(f"vt_XS{s}", B, ch, Lo, f32)
-            A, _, _ = self._cbuf(f"vt_A{s}", B, ch, Lo, bf)
+            X, cs, bs = self_cbuf(f"vt_X{s}", B, ch, Lo, f32)
+            XJ, _, _ = self_cbuf(f"vt_XJ{s}", B, ch, Lo, f32)
+            Y, _, _ = self_cbuf(f"vt_Y{s}", B, ch, Lo, f32)
+            XS, _, _ = self_cbuf(f"vt_XS{s}", B, ch, Lo, f32)
+            A, _, _ = self_cbuf(f"vt_A{s}", B, ch, Lo, bf)
             o = HALO * 8  # element offset of row t = 0
             strides = (bs, cs, 8)
             self._tc_conv(V[f"up{s}"], a_in, a_bs, a_cs, HALO, X[o:], strides, 0, B, L)
@@ -522,6 +556,9 @@ class Engine:
                     a1, ib1, f1 = V[f"r{s}.{j}.a1.{i}"]
                     self._call("fh_snake_aa_chunked", cur.data_ptr(), A.data_ptr(), a1.data_ptr(), ib1.data_ptr(),
                                f1.data_ptr(), bs, cs, HALO, B, ch, L, 1, st)
+                    if started_event is not None:
+                        started_event.record(torch.cuda.current_stream(self.device))
+                        started_event = None
                     if v.resblock == "1":
                         self._tc_conv(V[f"r{s}.{j}.c1.{i}"], A, bs, cs, HALO, Y[o:], strides, 0, B, L)
                         a2, ib2, f2 = V[f"r{s}.{j}.a2.{i}"]
@@ -538,17 +575,15 @@ class Engine:
                                       beta=1.0)
                         cur = XJ
             if s + 1 < v.num_stages:
-                XB, _, _ = self._cbuf(f"vt_XB{s}", B, ch, L, bf)
+                XB, _, _ = self_cbuf(f"vt_XB{s}", B, ch, L, bf)
                 self._call("fh_cast_f32_bf16", XS.data_ptr(), XB.data_ptr(), B * bs, st)
                 a_in, a_cs, a_bs = XB, cs, bs
         a, ib, f = V["post_act"]
-        AP, _, _ = self._cbuf("vt_AP", B, ch, L, f32)
+        AP, _, _ = self_cbuf("vt_AP", B, ch, L, f32)
         self._call("fh_snake_aa_chunked", XS.data_ptr(), AP.data_ptr(), a.data_ptr(), ib.data_ptr(), f.data_ptr(), bs, cs,
                    HALO, B, ch, L, 0, st)
-        wave = torch.empty((B, L), dtype=torch.float32, device=self.device)
         self._call("fh_convpost_tanh_chunked", AP.data_ptr(), bs, cs, HALO, V["post_w"].data_ptr(), V["post_b"],
                    wave.data_ptr(), B, ch, L, st)
-        return wave
 
     # ------------------------------------------------------------------ stage: post-processing
     def postprocess(self, pred: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
