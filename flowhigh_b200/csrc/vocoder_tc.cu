@@ -122,6 +122,164 @@ __global__ void __launch_bounds__(128) snake_aa_chunked_kernel(const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------ persistent, TMA-fed variant
+// Same arithmetic as above (packed FFMA2 pairs), but: persistent CTAs walk (batch, chunk, time-tile)
+// work items; the (17*32 + 10) x 8-channel fp32 input window of the NEXT item is fetched with one
+// cp.async.bulk (UBLKCP) into the other shared-memory buffer while the current item is computed;
+// 17 outputs per thread makes the un-padded 32-byte-row window bank-conflict free for the
+// (4 pairs x 8 groups) 64-bit reads of a warp; replicate clamps are patched in shared memory and
+// in registers on the first / last tile of a sequence only (block-uniform branch).
+constexpr int PR = 17;
+constexpr int PTT = PR * 32;   // 544 time steps per tile
+constexpr int PXR = PTT + 10;  // rows per staged window
+
+__device__ __forceinline__ uint32_t sm_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pmbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pmbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pmbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  const long long t0 = clock64();
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!ok && clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void pbulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <bool OUT_BF16>
+__global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(
+    const float* __restrict__ x, void* __restrict__ y, const float* __restrict__ a, const float* __restrict__ inv_b,
+    const float* __restrict__ filt, long long batch_stride, long long chunk_stride, int row0, int nchunk, int L,
+    int ntile, int total) {
+  __shared__ __align__(128) float xs[2][PXR * 8];
+  __shared__ __align__(8) unsigned long long bars[2];
+  const uint32_t bar0 = sm_u32(&bars[0]);
+  if (threadIdx.x == 0) {
+    pmbar_init(bar0, 1);
+    pmbar_init(bar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int rows_per_chunk = (int)(chunk_stride >> 3);
+  auto issue = [&](int item, int buf) {
+    const int tile = item % ntile;
+    const int rest = item / ntile;
+    const int ch = rest % nchunk, b = rest / nchunk;
+    const int r_first = row0 + tile * PTT - 5;  // >= row0 - 5 >= 0 (left halo)
+    int nrows = rows_per_chunk - r_first;       // stay inside this chunk's rows
+    nrows = nrows < PXR ? nrows : PXR;
+    const float* src = x + (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)r_first * 8;
+    pmbar_expect_tx(bar0 + 8 * buf, (uint32_t)nrows * 32u);
+    pbulk_g2s(sm_u32(&xs[buf][0]), src, (uint32_t)nrows * 32u, bar0 + 8 * buf);
+  };
+  float2 fu[12], fd[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const float fk = __ldg(filt + k);
+    fu[k] = make_float2(2.0f * fk, 2.0f * fk);
+    fd[k] = make_float2(fk, fk);
+  }
+  const int e2 = threadIdx.x & 3, g = threadIdx.x >> 2;
+  int item = blockIdx.x;
+  if (item < total && threadIdx.x == 0) issue(item, 0);
+  int buf = 0;
+  uint32_t ph0 = 0, ph1 = 0;
+  for (; item < total; item += gridDim.x) {
+    const int tile = item % ntile;
+    const int rest = item / ntile;
+    const int ch = rest % nchunk, b = rest / nchunk;
+    const int qt = tile * PTT;
+    const bool edge = (tile == 0) || (qt + PTT + 5 > L);
+    pmbar_wait(bar0 + 8 * buf, buf ? ph1 : ph0);
+    if (buf) ph1 ^= 1; else ph0 ^= 1;
+    float* xt = xs[buf];
+    if (edge) {  // replicate-pad the window in shared memory: rows t < 0 <- x[0], rows t >= L <- x[L-1]
+      for (int i = threadIdx.x; i < PXR * 2; i += 128) {
+        const int r = i >> 1, h = i & 1;
+        const int t = qt - 5 + r;
+        const int tc = min(max(t, 0), L - 1);
+        if (tc != t) {
+          const int rc = tc - (qt - 5);
+          if (rc >= 0 && rc < PXR)
+            *reinterpret_cast<float4*>(&xt[r * 8 + h * 4]) = *reinterpret_cast<const float4*>(&xt[rc * 8 + h * 4]);
+        }
+      }
+      __syncthreads();
+    }
+    const int c0 = ch * 8 + 2 * e2;
+    const float2 al2 = make_float2(2.0f * __ldg(a + c0), 2.0f * __ldg(a + c0 + 1));
+    const float2 hib = make_float2(0.5f * __ldg(inv_b + c0), 0.5f * __ldg(inv_b + c0 + 1));
+    const float2 nhib = make_float2(-hib.x, -hib.y);
+    const int q0 = qt + g * PR;
+    float2 xv[PR + 10];
+    const float* xp = xt + g * (PR * 8) + 2 * e2;
+#pragma unroll
+    for (int j = 0; j < PR + 10; ++j) xv[j] = *reinterpret_cast<const float2*>(xp + j * 8);
+    __syncthreads();  // every thread has read this buffer's window
+    if (threadIdx.x == 0 && item + (int)gridDim.x < total) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(item + gridDim.x, buf ^ 1);  // that buffer was fully read one iteration ago
+    }
+    if (q0 < L) {
+      float2 s[2 * PR + 10];
+#pragma unroll
+      for (int i = 0; i < 2 * PR + 10; ++i) {
+        const int qq = (i - 5) >> 1;
+        float2 u = make_float2(0.f, 0.f);
+        if ((i & 1) == 0) {
+#pragma unroll
+          for (int d = -2; d <= 3; ++d) u = ffma2(xv[qq + d + 5], fu[6 - 2 * d], u);
+        } else {
+#pragma unroll
+          for (int d = -3; d <= 2; ++d) u = ffma2(xv[qq + d + 5], fu[5 - 2 * d], u);
+        }
+        const float2 z = fmul2(u, al2);
+        const float2 c = make_float2(__cosf(z.x), __cosf(z.y));
+        s[i] = ffma2(c, nhib, u);
+      }
+      if (edge && (q0 == 0 || q0 + PR + 3 >= L)) {
+        const int ic = 2 * (L - q0) + 5;
+        float2 prev = s[5];
+#pragma unroll
+        for (int i = 0; i < 2 * PR + 10; ++i) {
+          if (q0 == 0 && i < 5) s[i] = prev;
+          if (i < ic) prev = s[i];
+          else s[i] = prev;
+        }
+      }
+      const long long obase =
+          (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)(row0 + q0) * 8 + 2 * e2;
+#pragma unroll
+      for (int j = 0; j < PR; ++j) {
+        if (!edge || q0 + j < L) {
+          float2 acc = hib;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) acc = ffma2(fd[k], s[2 * j + k], acc);
+          if (OUT_BF16)
+            *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)y + obase + j * 8) = __floats2bfloat162_rn(acc.x, acc.y);
+          else
+            *reinterpret_cast<float2*>((float*)y + obase + j * 8) = acc;
+        }
+      }
+    }
+    buf ^= 1;
+  }
+}
+
 // scalar variant (one channel per thread, 256 threads): kept selectable, see fh_snake_aa_chunked
 template <bool OUT_BF16>
 __global__ void __launch_bounds__(256) snake_aa_chunked_scalar_kernel(const float* __restrict__ x, void* __restrict__ y,
@@ -248,7 +406,26 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
     const char* e = getenv("FH_SNAKE_VARIANT");
     variant = e ? atoi(e) : 0;
   }
-  if (variant == 1) {  // packed-FFMA2, two channels per thread
+  if (variant == 2) {  // persistent, bulk-copy fed, packed FFMA2
+    const int ntile = (L + PTT - 1) / PTT;
+    const long long total = (long long)ntile * (C / 8) * B;
+    FH_REQUIRE(total <= 2147483647LL && row0 >= 5 && (chunk_stride % 8) == 0, FH_ERR_BAD_SHAPE,
+               "fh_snake_aa_chunked: needs a left halo of >= 5 rows");
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+    }
+    const int grid = (int)(total < (long long)sms * 4 ? total : (long long)sms * 4);
+    if (out_is_bf16)
+      snake_aa_chunked_tma_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(
+          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L, ntile, (int)total);
+    else
+      snake_aa_chunked_tma_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L, ntile, (int)total);
+  } else if (variant == 1) {  // packed-FFMA2, two channels per thread
     if (out_is_bf16)
       snake_aa_chunked_kernel<true><<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(
           x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L);
