@@ -46,6 +46,7 @@ SIGNATURES = {
     "fh_pp_cutoff": (_i, [_p, _p, _i, _f, _p]),
     "fh_pp_splice_istft_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "fh_pp_overlap_add_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
+    "fh_ola_crossfade_f32": (_i, [_p, _p, _i, _i, _i, _i64, _p]),
     "fh_sgemm_nt_f32": (_i, [_p, _i, _p, _i, _p, _p, _i, _f, _f, _p, _i, _i, _i, _i, _p]),
     "fh_gemv_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "fh_sincos_embed_f32": (_i, [_p, _f, _p, _i, _p]),

@@ -269,6 +269,24 @@ __global__ void pp_overlap_add_kernel(const float* __restrict__ frames, float* _
   if (absmax) block_absmax_atomic(fabsf(v), absmax + bi);
 }
 
+// long-form stitch: uniform chunks k = 0..K-1 spanning [k*step, k*step + clen); linear cross-fade in overlaps
+__global__ void ola_crossfade_kernel(const float* __restrict__ chunks, float* __restrict__ out, int K, int clen,
+                                     int step, long long total) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  const int ov = clen - step;
+  int k = (int)(t / step);
+  if (k > K - 1) k = K - 1;
+  const int o = (int)(t - (long long)k * step);  // offset inside chunk k
+  float v = chunks[(long long)k * clen + o];
+  if (k > 0 && o < ov) {  // also covered by the tail of chunk k-1
+    const float w = ((float)o + 0.5f) / (float)ov;
+    const float prev = chunks[(long long)(k - 1) * clen + (o + step)];
+    v = w * v + (1.0f - w) * prev;
+  }
+  out[t] = v;
+}
+
 }  // namespace
 
 // ================================================================================ C ABI
@@ -362,4 +380,15 @@ extern "C" __attribute__((visibility("default"))) int fh_pp_overlap_add_f32(cons
   pp_overlap_add_kernel<<<dim3((length + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(frames, y, window, absmax_bits,
                                                                                        NT, length);
   return fh::check_launch("fh_pp_overlap_add_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_ola_crossfade_f32(const float* chunks, float* out, int K,
+                                                                          int clen, int step, int64_t total,
+                                                                          void* stream) {
+  FH_REQUIRE(K > 0 && clen > 0 && step > 0 && step <= clen && 2 * step >= clen && total > 0 &&
+                 total <= (int64_t)(K - 1) * step + clen,
+             FH_ERR_BAD_SHAPE, "fh_ola_crossfade_f32: need clen/2 <= step <= clen and total within the chunks");
+  ola_crossfade_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(chunks, out, K, clen, step,
+                                                                                         total);
+  return fh::check_launch("fh_ola_crossfade_f32");
 }

@@ -404,7 +404,7 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("FH_SNAKE_VARIANT");
-    variant = e ? atoi(e) : 0;
+    variant = e ? atoi(e) : 2;
   }
   if (variant == 2) {  // persistent, bulk-copy fed, packed FFMA2
     const int ntile = (L + PTT - 1) / PTT;

@@ -281,6 +281,42 @@ class FlowHighSR(nn.Module):
                 results[i] = out[j: j + 1]
         return results  # type: ignore[return-value]
 
+    @torch.no_grad()
+    def generate_long(self, audio, sr: int, target_sampling_rate=48000, timestep=1, chunk_seconds: float = 10.0,
+                      overlap_seconds: float = 0.5, eps: Optional[torch.Tensor] = None, max_batch: int = 64):
+        """Long-form generation by overlapped chunking + overlap-add (not in the reference,
+        whose dense fp32 attention cannot hold a 10-minute clip).  The input is resampled and peak-normalised
+        ONCE (global scalar), cut into uniform chunks in the 48 kHz domain, every chunk runs log-mel -> CFM ->
+        vocoder as an independent clip, the vocoder outputs are cross-faded, and the STFT-domain
+        post-processing runs once over the stitched signal.  `eps` (optional) is [K, frames, 256]."""
+        eng = self._engine()
+        x = torch.from_numpy(self._prep_input(audio))[None].to(eng.device)
+        cond = eng.resample_normalise(x, int(sr), target_sampling_rate)  # [1, T]
+        T = cond.shape[1]
+        clen = int(round(chunk_seconds * 48000)) // 480 * 480
+        ov = int(round(overlap_seconds * 48000)) // 480 * 480
+        if T <= clen:
+            return self.generate(audio, sr, target_sampling_rate, timestep, eps=None if eps is None else eps[0])
+        step = clen - ov
+        K = -(-(T - clen) // step) + 1
+        Tpad = (K - 1) * step + clen
+        padded = torch.zeros((1, Tpad), dtype=torch.float32, device=eng.device)
+        padded[:, :T] = cond
+        chunks = padded.unfold(1, clen, step)[0].contiguous()  # [K, clen] (views of overlapped spans, copied once)
+        waves = torch.empty((K, clen), dtype=torch.float32, device=eng.device)
+        for b0 in range(0, K, max_batch):
+            c = chunks[b0: b0 + max_batch]
+            mel_c = eng.encode(c)
+            e = None if eps is None else eps[b0: b0 + max_batch]
+            mel = eng.sample_mel(mel_c, self._noise_like(mel_c, e), steps=int(timestep),
+                                 ode_method=self.odeint_kwargs["method"], cfm_method=self.cfm_method,
+                                 sigma=float(self.sigma))
+            waves[b0: b0 + max_batch] = eng.vocoder(mel)
+        Tv = T // 480 * 480  # the vocoder emits whole frames (pred is shorter than src when T % 480 != 0)
+        stitched = torch.empty((1, Tv), dtype=torch.float32, device=eng.device)
+        eng._call("fh_ola_crossfade_f32", waves.data_ptr(), stitched.data_ptr(), K, clen, step, Tv, eng.stream)
+        return eng.postprocess(stitched, cond)
+
     # ------------------------------------------------------------------ loaders
     @classmethod
     def from_local(cls, ckpt_dir, device="cuda", precision: str = "bf16") -> "FlowHighSR":

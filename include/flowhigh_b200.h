@@ -79,6 +79,11 @@ int fh_pp_splice_istft_f32(const float* spec_pred, const float* spec_src, const 
 int fh_pp_overlap_add_f32(const float* frames, float* y, const float* window, uint32_t* absmax_bits,
                           int B, int NT, int length, void* stream);
 
+/* long-form stitch (engine capability): K uniform chunks [K, clen] whose starts are
+ * `step` apart (clen/2 <= step <= clen) -> out[total]; overlaps are linearly cross-faded. */
+int fh_ola_crossfade_f32(const float* chunks, float* out, int K, int clen, int step, int64_t total,
+                         void* stream);
+
 /* ---------------------------------------------------------------- backbone, fp32 path
  * out[M,N] (ldc) = alpha * (A[M,K](lda) . W[N,K](ldw)^T + bias[N]) + beta_res * res[M,N](ldr)
  * replaces nn.Linear at flow.py:239,261; attend.py:176,189; transformer.py:100-103.
