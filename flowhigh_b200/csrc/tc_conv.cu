@@ -44,6 +44,7 @@ struct TcParams {
   int ci_pairs;        // Cin / 16
   int tg, n_groups;    // taps per smem stage, groups per ci-pair
   int msub;            // 128-row sub-tiles per CTA tile (1, 2 or 4): B operand reuse + epilogue MLP
+  int acc_stages;      // TMEM accumulator stages: 2 (epilogue overlaps the next tile) or 1 (msub*bn > 256)
   int wrows;           // rows fetched per chunk window: 128*msub + (max_off - min_off)
   int arows_pad;       // rows reserved per chunk window in an A slot
   int stages, stage_bytes;
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       }
       if (leader) umma_commit(tfull0 + 8 * as);  // accumulator complete -> epilogue
       __syncwarp();
-      if (++as == 2) {
+      if (++as == P.acc_stages) {
         as = 0;
         aphase ^= 1;
       }
@@ -439,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * as);
-      if (++as == 2) {
+      if (++as == P.acc_stages) {
         as = 0;
         aphase ^= 1;
       }
@@ -531,8 +532,20 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv_bf16(const fh_t
   // sub-tiles: reuse each weight slot for up to 4 x 128 rows when the accumulators fit TMEM twice over
   int msub = 256 / a->bn;
   msub = msub >= 4 ? 4 : (msub >= 2 ? 2 : 1);
+  // Wide tiles (bn > 128): the weight stream from L2 (bn*32 B per MMA) is the limiter, so two 128-row
+  // sub-tiles share every weight slot even though the accumulators (2*bn columns) then fill TMEM and
+  // the epilogue no longer overlaps the next tile -- worth it once a tile carries enough MMAs.
+  static int wide_msub = -1, wide_min = 96;
+  if (wide_msub < 0) {
+    const char* e = getenv("FH_TC_WIDE_MSUB");
+    wide_msub = e ? atoi(e) : 2;
+    const char* m = getenv("FH_TC_WIDE_MIN");
+    if (m) wide_min = atoi(m);
+  }
+  if (a->bn > 128 && wide_msub == 2 && (long long)a->ntaps * (a->Cin / 16) >= wide_min) msub = 2;
   while (msub > 1 && (long long)a->B * a->P * ((a->L + 128 * msub - 1) / (128 * msub)) * p.n_tiles < 2 * 148) msub >>= 1;
   p.msub = msub;
+  p.acc_stages = (2 * msub * a->bn <= 512) ? 2 : 1;
   p.m_tiles = (a->L + 128 * msub - 1) / (128 * msub);
   const long long total = (long long)p.B * p.P * p.m_tiles * p.n_tiles;
   FH_REQUIRE(total < (1ll << 31), FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: too many tiles");
