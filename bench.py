@@ -155,6 +155,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
+                    help="16-bit tensor-core operand format (same rate and bytes; fp16 meets the LSD bar, see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel CUDA-event breakdown to this JSON file")
     args = ap.parse_args()
@@ -177,7 +179,7 @@ def main():
     W = max(args.warmup, 3)
     B = args.batch
 
-    model = FlowHighSR.from_random(VocoderConfig.assumed_48k(), device=dev, seed=0, precision="bf16")
+    model = FlowHighSR.from_random(VocoderConfig.assumed_48k(), device=dev, seed=0, precision=args.precision)
     eng = model._engine()
     n_in = int(CLIP_SECONDS * SR_IN)
     host = np.stack([synth_speech(n_in, SR_IN, seed=rank * B + i) for i in range(min(B, 8))])
@@ -287,7 +289,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16", "data": "synthetic", "config": config_dict(world, B),
+            "dtype": args.precision, "data": "synthetic", "config": config_dict(world, B),
             "per_gpu": value / world, "realtime_factor_per_gpu": value / world,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_t.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps},

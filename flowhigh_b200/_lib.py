@@ -22,13 +22,14 @@ class TcConvArgs(C.Structure):
         ("w", _p), ("bias", _p), ("res", _p), ("out", _p),
         ("out_batch", _i64), ("out_chunk", _i64), ("out_row", _i64),
         ("res_batch", _i64), ("res_chunk", _i64), ("res_row", _i64),
-        ("out_is_bf16", _i), ("res_is_bf16", _i),
+        ("out_is_16", _i), ("res_is_16", _i),
         ("alpha", _f), ("beta_res", _f),
         ("accumulate", _i), ("geglu", _i),
         ("B", _i), ("L", _i), ("Cin", _i), ("Cout", _i),
         ("ntaps", _i), ("P", _i),
         ("tap_off", C.POINTER(_i)),
         ("bn", _i),
+        ("fp16", _i),
     ]
 
 
@@ -60,10 +61,10 @@ SIGNATURES = {
     "fh_snake_aa_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "fh_convpost_tanh_f32": (_i, [_p, _p, _f, _p, _i, _i, _i, _p]),
     "fh_transpose_f32": (_i, [_p, _p, _i, _i, _i, _p]),
-    "fh_cast_f32_bf16": (_i, [_p, _p, _i64, _p]),
-    "fh_tc_conv_bf16": (_i, [C.POINTER(TcConvArgs), _p]),
+    "fh_cast_f32_16": (_i, [_p, _p, _i64, _i, _p]),
+    "fh_tc_conv": (_i, [C.POINTER(TcConvArgs), _p]),
     "fh_tc_packed_weight_bytes": (_i64, [_i, _i, _i, _i, _i]),
-    "fh_to_chunked_bf16": (_i, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _i, _p]),
+    "fh_to_chunked_16": (_i, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _i, _i, _p]),
     "fh_snake_aa_chunked": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _p]),
     "fh_convpost_tanh_chunked": (_i, [_p, _i64, _i64, _i, _p, _f, _p, _i, _i, _i, _p]),
 }

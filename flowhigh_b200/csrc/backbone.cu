@@ -124,11 +124,11 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
       o[c] = v;
     }
   } else {
-    __nv_bfloat16* o = (__nv_bfloat16*)out;
+    unsigned short* o = (unsigned short*)out;
     for (int c = lane; c < C; c += 32) {
       float v = xr[c] * inv * gamma[c];
       if (beta) v += beta[c];
-      o[fh::chunked_index(out_rows * 8, row, c)] = __float2bfloat16(v);
+      o[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16(v, out_mode == 2);
     }
   }
 }
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
       if (out_mode == 0)
         ((float*)out)[row * (H * D) + c] = val;
       else
-        ((__nv_bfloat16*)out)[fh::chunked_index(out_rows * 8, row, c)] = __float2bfloat16(val);
+        ((unsigned short*)out)[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16(val, out_mode == 2);
     }
   }
 }
@@ -287,7 +287,7 @@ __global__ void geglu_kernel(const float* __restrict__ u, void* __restrict__ g, 
   if (out_mode == 0) {
     if (i < inner) ((float*)g)[(size_t)m * inner + i] = v;
   } else {
-    ((__nv_bfloat16*)g)[fh::chunked_index(out_rows * 8, m, i)] = __float2bfloat16(v);
+    ((unsigned short*)g)[fh::chunked_index(out_rows * 8, m, i)] = fh::cvt16(v, out_mode == 2);
   }
 }
 

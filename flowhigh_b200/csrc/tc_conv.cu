@@ -37,7 +37,7 @@ struct TcParams {
   long long out_batch, out_chunk, out_row;
   long long res_batch, res_chunk, res_row;
   int a_row0;
-  int out_is_bf16, res_is_bf16, accumulate, geglu;
+  int out_is_16, res_is_16, fp16, accumulate, geglu;
   float alpha, beta_res;
   int B, L, Cin, Cout, ntaps, P, bn;
   int m_tiles, n_tiles, total_tiles;
@@ -144,8 +144,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
 // K-major A/B, N>>3 [17,23), M>>4 [24,29)
-__device__ __forceinline__ uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(int n, int fp16) {
+  const uint32_t fmt = fp16 ? 0u : 1u;  // F16F32Format: F16 = 0, BF16 = 1
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 struct TileCoord {
@@ -176,12 +177,12 @@ __device__ __forceinline__ void load_res16(const TcParams& P, long long rbase, i
       continue;
     }
     const long long ridx = rbase + (long long)(n >> 3) * P.res_chunk;
-    if (P.res_is_bf16) {
-      const uint4 raw = *reinterpret_cast<const uint4*>((const __nv_bfloat16*)P.res + ridx);
-      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+    if (P.res_is_16) {
+      const uint4 raw = *reinterpret_cast<const uint4*>((const unsigned short*)P.res + ridx);
+      const uint32_t* h = reinterpret_cast<const uint32_t*>(&raw);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 f = __bfloat1622float2(h[i]);
+        const float2 f = fh::unpack16(h[i], P.fp16);
         r[hh * 8 + 2 * i] = f.x;
         r[hh * 8 + 2 * i + 1] = f.y;
       }
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     // only the tcgen05.mma / tcgen05.commit instructions are predicated on one elected lane.
     const bool leader = elect_one();
     int stage = 0, phase = 0, as = 0, aphase = 0;
-    const uint32_t idesc = make_idesc(P.bn);
+    const uint32_t idesc = make_idesc(P.bn, P.fp16);
     const uint64_t adesc_c = make_desc(0, a_chunk_bytes, 128);
     const uint64_t bdesc_c = make_desc(0, (uint32_t)P.bn * 16u, 128);
     const uint32_t b_tap_u = b_tap_bytes >> 4;
@@ -375,11 +376,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             o[i] = gelu_f(gv) * xv;
           }
           const long long idx = out_b + (long long)(n_out >> 3) * P.out_chunk + orow * P.out_row;
-          if (P.out_is_bf16) {
-            __nv_bfloat162 h[4];
+          if (P.out_is_16) {
+            uint32_t h[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-            *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
+            for (int i = 0; i < 4; ++i) h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
+            *reinterpret_cast<uint4*>((unsigned short*)P.out + idx) = *reinterpret_cast<uint4*>(h);
           } else {
             float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
             dst[0] = make_float4(o[0], o[1], o[2], o[3]);
@@ -400,11 +401,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             if (use_res) o[i] = fmaf(P.beta_res, rr[hh * 8 + i], o[i]);
           }
           const long long idx = out_b + (long long)(n0 >> 3) * P.out_chunk + orow * P.out_row;
-          if (P.out_is_bf16) {
-            __nv_bfloat162 h[4];
+          if (P.out_is_16) {
+            uint32_t h[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(o[2 * i], o[2 * i + 1]);
-            *reinterpret_cast<uint4*>((__nv_bfloat16*)P.out + idx) = *reinterpret_cast<uint4*>(h);
+            for (int i = 0; i < 4; ++i) h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
+            *reinterpret_cast<uint4*>((unsigned short*)P.out + idx) = *reinterpret_cast<uint4*>(h);
           } else {
             float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
             if (P.accumulate) {
@@ -457,7 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 // ------------------------------------------------------------------------------ layout helpers
 __global__ void to_chunked_bf16_kernel(const float* __restrict__ src, long long src_batch, long long src_c,
                                        long long src_t, __nv_bfloat16* __restrict__ dst, long long dst_batch,
-                                       long long dst_chunk, int dst_row0, int C, int L) {
+                                       long long dst_chunk, int dst_row0, int C, int L, int fp16) {
   // one thread per (t, chunk): gathers 8 channels, writes one 16-byte row
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nch = (C + 7) >> 3;
@@ -472,13 +473,13 @@ __global__ void to_chunked_bf16_kernel(const float* __restrict__ src, long long 
     t = (int)(i / nch);
   }
   const float* s = src + (long long)b * src_batch + (long long)t * src_t;
-  __nv_bfloat162 h[4];
+  uint32_t h[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int c0 = ch * 8 + 2 * k;
     const float f0 = c0 < C ? s[(long long)c0 * src_c] : 0.f;
     const float f1 = c0 + 1 < C ? s[(long long)(c0 + 1) * src_c] : 0.f;
-    h[k] = __floats2bfloat162_rn(f0, f1);
+    h[k] = fh::pack16(f0, f1, fp16);
   }
   *reinterpret_cast<uint4*>(dst + (long long)b * dst_batch + (long long)ch * dst_chunk + (long long)(dst_row0 + t) * 8) =
       *reinterpret_cast<uint4*>(h);
@@ -493,26 +494,26 @@ extern "C" __attribute__((visibility("default"))) int64_t fh_tc_packed_weight_by
   return (int64_t)P * n_tiles * (Cin / 16) * ntaps * bn * 32;
 }
 
-extern "C" __attribute__((visibility("default"))) int fh_tc_conv_bf16(const fh_tc_conv_args* a, void* stream) {
-  FH_REQUIRE(a != nullptr, FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: null args");
-  FH_REQUIRE(a->B > 0 && a->L > 0 && a->Cin > 0 && a->Cout > 0, FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: bad shape");
-  FH_REQUIRE(a->Cin % 16 == 0, FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: Cin=%d must be a multiple of 16", a->Cin);
-  FH_REQUIRE(a->Cout % 8 == 0, FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: Cout=%d must be a multiple of 8", a->Cout);
+extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_conv_args* a, void* stream) {
+  FH_REQUIRE(a != nullptr, FH_ERR_BAD_SHAPE, "fh_tc_conv: null args");
+  FH_REQUIRE(a->B > 0 && a->L > 0 && a->Cin > 0 && a->Cout > 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: bad shape");
+  FH_REQUIRE(a->Cin % 16 == 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: Cin=%d must be a multiple of 16", a->Cin);
+  FH_REQUIRE(a->Cout % 8 == 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: Cout=%d must be a multiple of 8", a->Cout);
   FH_REQUIRE(a->bn % 16 == 0 && a->bn >= 16 && a->bn <= 256, FH_ERR_UNSUPPORTED_CFG,
-             "fh_tc_conv_bf16: bn=%d must be a multiple of 16 in [16,256]", a->bn);
+             "fh_tc_conv: bn=%d must be a multiple of 16 in [16,256]", a->bn);
   FH_REQUIRE(a->P >= 1 && a->P <= 16 && a->ntaps >= 1 && a->P * a->ntaps <= kMaxTapOff, FH_ERR_UNSUPPORTED_CFG,
-             "fh_tc_conv_bf16: P=%d ntaps=%d unsupported", a->P, a->ntaps);
+             "fh_tc_conv: P=%d ntaps=%d unsupported", a->P, a->ntaps);
   FH_REQUIRE(!(a->geglu && (a->res || a->accumulate || (a->Cout % 16))), FH_ERR_UNSUPPORTED_CFG,
-             "fh_tc_conv_bf16: geglu epilogue excludes residual/accumulate and needs Cout %% 16 == 0");
-  FH_REQUIRE(!(a->accumulate && a->out_is_bf16), FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv_bf16: accumulate needs fp32 out");
+             "fh_tc_conv: geglu epilogue excludes residual/accumulate and needs Cout %% 16 == 0");
+  FH_REQUIRE(!(a->accumulate && a->out_is_16), FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: accumulate needs fp32 out");
   FH_REQUIRE(((uintptr_t)a->a % 16) == 0 && ((uintptr_t)a->w % 16) == 0 && ((uintptr_t)a->out % 16) == 0 &&
                  ((uintptr_t)a->res % 16) == 0,
-             FH_ERR_BAD_ALIGN, "fh_tc_conv_bf16: pointers must be 16-byte aligned");
-  FH_REQUIRE(a->a_chunk % 8 == 0 && a->a_batch % 8 == 0, FH_ERR_BAD_ALIGN, "fh_tc_conv_bf16: A strides must be x8");
-  const int esz_shift = a->out_is_bf16 ? 3 : 2;  // 16-byte alignment in elements
+             FH_ERR_BAD_ALIGN, "fh_tc_conv: pointers must be 16-byte aligned");
+  FH_REQUIRE(a->a_chunk % 8 == 0 && a->a_batch % 8 == 0, FH_ERR_BAD_ALIGN, "fh_tc_conv: A strides must be x8");
+  const int esz_shift = a->out_is_16 ? 3 : 2;  // 16-byte alignment in elements
   FH_REQUIRE((a->out_batch % (1 << esz_shift)) == 0 && (a->out_chunk % (1 << esz_shift)) == 0 &&
                  (a->out_row % (1 << esz_shift)) == 0,
-             FH_ERR_BAD_ALIGN, "fh_tc_conv_bf16: output strides break 16-byte alignment");
+             FH_ERR_BAD_ALIGN, "fh_tc_conv: output strides break 16-byte alignment");
 
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -524,7 +525,7 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv_bf16(const fh_t
   p.a_batch = a->a_batch, p.a_chunk = a->a_chunk, p.a_row0 = a->a_row0;
   p.out_batch = a->out_batch, p.out_chunk = a->out_chunk, p.out_row = a->out_row;
   p.res_batch = a->res_batch, p.res_chunk = a->res_chunk, p.res_row = a->res_row;
-  p.out_is_bf16 = a->out_is_bf16, p.res_is_bf16 = a->res_is_bf16;
+  p.out_is_16 = a->out_is_16, p.res_is_16 = a->res_is_16, p.fp16 = a->fp16;
   p.accumulate = a->accumulate, p.geglu = a->geglu;
   p.alpha = a->alpha, p.beta_res = a->beta_res;
   p.B = a->B, p.L = a->L, p.Cin = a->Cin, p.Cout = a->Cout, p.ntaps = a->ntaps, p.P = a->P, p.bn = a->bn;
@@ -548,7 +549,7 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv_bf16(const fh_t
   p.acc_stages = (2 * msub * a->bn <= 512) ? 2 : 1;
   p.m_tiles = (a->L + 128 * msub - 1) / (128 * msub);
   const long long total = (long long)p.B * p.P * p.m_tiles * p.n_tiles;
-  FH_REQUIRE(total < (1ll << 31), FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: too many tiles");
+  FH_REQUIRE(total < (1ll << 31), FH_ERR_BAD_SHAPE, "fh_tc_conv: too many tiles");
   p.total_tiles = (int)total;
   p.ci_pairs = a->Cin / 16;
   int span = 0;
@@ -562,10 +563,10 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv_bf16(const fh_t
     }
     p.min_off[ph] = mn;
     span = (mx - mn) > span ? (mx - mn) : span;
-    FH_REQUIRE(a->a_row0 + mn >= 0, FH_ERR_BAD_SHAPE, "fh_tc_conv_bf16: left halo %d too small for tap offset %d",
+    FH_REQUIRE(a->a_row0 + mn >= 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: left halo %d too small for tap offset %d",
                a->a_row0, mn);
   }
-  FH_REQUIRE(span <= kMaxSpan, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv_bf16: tap span %d exceeds %d rows", span, kMaxSpan);
+  FH_REQUIRE(span <= kMaxSpan, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: tap span %d exceeds %d rows", span, kMaxSpan);
   p.wrows = 128 * msub + span;
   p.arows_pad = 128 * msub + kMaxSpan;
   // taps per stage: keep a B slot <= 32 KB
@@ -585,7 +586,7 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv_bf16(const fh_t
   const int budget = budget_kb * 1024;
   int stages = (budget - 1024) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
-  FH_REQUIRE(stages >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv_bf16: stage of %d bytes does not fit twice", p.stage_bytes);
+  FH_REQUIRE(stages >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: stage of %d bytes does not fit twice", p.stage_bytes);
   p.stages = stages;
   p.err_flag = nullptr;
   const int smem = 1024 + stages * p.stage_bytes;
@@ -600,21 +601,21 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv_bf16(const fh_t
   }
   if (smem > smem_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv_bf16: cannot opt in to %d bytes of smem: %s", smem,
+    FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", smem,
                cudaGetErrorString(e));
     smem_set = smem;
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   tc_conv_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
-  return fh::check_launch("fh_tc_conv_bf16");
+  return fh::check_launch("fh_tc_conv");
 }
 
-extern "C" __attribute__((visibility("default"))) int fh_to_chunked_bf16(const float* src, int64_t src_batch, int64_t src_c, int64_t src_t, void* dst,
+extern "C" __attribute__((visibility("default"))) int fh_to_chunked_16(const float* src, int64_t src_batch, int64_t src_c, int64_t src_t, void* dst,
                                   int64_t dst_batch, int64_t dst_chunk, int dst_row0, int B, int C, int L,
-                                  void* stream) {
-  FH_REQUIRE(B > 0 && C > 0 && L > 0 && B <= 65535, FH_ERR_BAD_SHAPE, "fh_to_chunked_bf16: bad shape");
+                                  int fp16, void* stream) {
+  FH_REQUIRE(B > 0 && C > 0 && L > 0 && B <= 65535, FH_ERR_BAD_SHAPE, "fh_to_chunked_16: bad shape");
   const long long n = (long long)((C + 7) / 8) * L;
   to_chunked_bf16_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(
-      src, src_batch, src_c, src_t, (__nv_bfloat16*)dst, dst_batch, dst_chunk, dst_row0, C, L);
-  return fh::check_launch("fh_to_chunked_bf16");
+      src, src_batch, src_c, src_t, (__nv_bfloat16*)dst, dst_batch, dst_chunk, dst_row0, C, L, fp16);
+  return fh::check_launch("fh_to_chunked_16");
 }

@@ -174,14 +174,15 @@ __global__ void transpose_f32_kernel(const float* __restrict__ src, float* __res
   }
 }
 
-__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+__global__ void cast_f32_16_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, long long n,
+                                   int fp16) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(src + i);
-    __nv_bfloat162 h[2] = {__floats2bfloat162_rn(v.x, v.y), __floats2bfloat162_rn(v.z, v.w)};
+    uint32_t h[2] = {fh::pack16(v.x, v.y, fp16), fh::pack16(v.z, v.w, fp16)};
     *reinterpret_cast<uint2*>(dst + i) = *reinterpret_cast<uint2*>(h);
   } else {
-    for (long long k = i; k < n; ++k) dst[k] = __float2bfloat16(src[k]);
+    for (long long k = i; k < n; ++k) dst[k] = fh::cvt16(src[k], fp16);
   }
 }
 
@@ -231,10 +232,11 @@ extern "C" __attribute__((visibility("default"))) int fh_transpose_f32(const flo
   return fh::check_launch("fh_transpose_f32");
 }
 
-extern "C" __attribute__((visibility("default"))) int fh_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream) {
+extern "C" __attribute__((visibility("default"))) int fh_cast_f32_16(const float* src, void* dst, int64_t n, int fp16, void* stream) {
   if (n <= 0) return FH_OK;
-  FH_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, FH_ERR_BAD_ALIGN, "fh_cast_f32_bf16: alignment");
+  FH_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, FH_ERR_BAD_ALIGN, "fh_cast_f32_16: alignment");
   const long long nthreads = (n + 3) / 4;
-  cast_f32_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
-  return fh::check_launch("fh_cast_f32_bf16");
+  cast_f32_16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned short*)dst, n,
+                                                                                      fp16);
+  return fh::check_launch("fh_cast_f32_16");
 }

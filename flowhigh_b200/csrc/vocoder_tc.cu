@@ -1,7 +1,7 @@
 // Memory-bound vocoder kernels of the tensor-core path, on the chunked [C/8][Lp][8] layout that
-// fh_tc_conv_bf16 consumes: fused anti-aliased Snake/SnakeBeta (alias_free_torch/act.py:23-28,
+// fh_tc_conv consumes: fused anti-aliased Snake/SnakeBeta (alias_free_torch/act.py:23-28,
 // resample.py:25-33, filter.py:86-94, activations.py:48-59,107-119) and conv_post + tanh
-// (bigvgan/models.py:189-192).  The residual stream stays fp32; only MMA operands are bf16.
+// (bigvgan/models.py:189-192).  The residual stream stays fp32; only MMA operands are 16-bit.
 #include <stdlib.h>
 #include "common.cuh"
 
@@ -11,20 +11,13 @@ namespace {
 // y[q] = sum_k f[k] s~[2q+k-5];  s[m] = u[m] + inv_b sin^2(a u[m]);  u[m] = 2 sum_i x~[i] f[m+5-2i]
 // (x~ / s~ = replicate-clamped; closed form of up2x -> snake -> down2x).
 //
-// Register-blocked and 2-wide: one thread owns TWO adjacent channels and R = 16 consecutive
-// outputs; every filter tap is one packed FFMA2 (fma.rn.f32x2, sm_100) on a channel pair, applied
-// from registers.  sin^2(z) is evaluated as (1 - cos 2z)/2 so that
+// Register-blocked and 2-wide: one thread owns TWO adjacent channels and 17 consecutive outputs;
+// every filter tap is one packed FFMA2 (fma.rn.f32x2, sm_100; measured 1.55x the scalar FFMA rate,
+// tools/ffma2_bench.cu) on a channel pair, applied from registers.  sin^2(z) is evaluated as
+// (1 - cos 2z)/2 so that
 //     s' = u - (inv_b/2) cos(2 a u),   y = sum_k f[k] s'~[.] + inv_b/2      (sum_k f[k] = 1)
 // costs one packed multiply, two MUFU.COS and one packed FMA per pair.  cos.approx's absolute
-// error (~1e-6 for |arg| < 1e2) is far below the bf16 operand rounding that follows.
-// A CTA covers 512 time steps x 8 channels; the input tile is staged once through shared memory
-// with a 4-word pad every 8 rows (conflict-free 64-bit reads for the 4 pairs x 8 groups of a warp).
-constexpr int SR = 16;                    // outputs per thread
-constexpr int SG = 32;                    // time-groups per CTA
-constexpr int STT = SR * SG;              // 512 time steps per CTA
-constexpr int SXR = STT + 10;             // staged input rows
-__host__ __device__ constexpr int sx_index(int row) { return row * 8 + (row >> 3) * 4; }
-
+// error (~1e-6 for |arg| < 1e2) is far below the 16-bit operand rounding that follows.
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
                      rc = *reinterpret_cast<unsigned long long*>(&c), rd;
@@ -37,94 +30,7 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
-template <bool OUT_BF16>
-__global__ void __launch_bounds__(128) snake_aa_chunked_kernel(const float* __restrict__ x, void* __restrict__ y,
-                                                               const float* __restrict__ a,
-                                                               const float* __restrict__ inv_b,
-                                                               const float* __restrict__ filt, long long batch_stride,
-                                                               long long chunk_stride, int row0, int nchunk, int L) {
-  __shared__ __align__(16) float xs[sx_index(SXR) + 8];
-  const int ntile = (L + STT - 1) / STT;
-  int id = blockIdx.x;
-  const int tile = id % ntile;
-  id /= ntile;
-  const int ch = id % nchunk, b = id / nchunk;
-  const int qt = tile * STT;
-  const float* xb = x + (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)row0 * 8;
-  // stage rows [qt-5, qt+STT+5), replicate-clamped, as float4 halves of each 8-channel row
-  for (int i = threadIdx.x; i < SXR * 2; i += 128) {
-    const int r = i >> 1, h = i & 1;
-    const int t = min(max(qt - 5 + r, 0), L - 1);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * 8 + h * 4));
-    *reinterpret_cast<float4*>(&xs[sx_index(r) + h * 4]) = v;
-  }
-  float2 fu[12], fd[12];  // up taps (x2 folded in) and down taps, broadcast to both channels
-#pragma unroll
-  for (int k = 0; k < 12; ++k) {
-    const float fk = __ldg(filt + k);
-    fu[k] = make_float2(2.0f * fk, 2.0f * fk);
-    fd[k] = make_float2(fk, fk);
-  }
-  const int e2 = threadIdx.x & 3, g = threadIdx.x >> 2;
-  const int c0 = ch * 8 + 2 * e2;
-  const float2 al2 = make_float2(2.0f * a[c0], 2.0f * a[c0 + 1]);
-  const float2 hib = make_float2(0.5f * inv_b[c0], 0.5f * inv_b[c0 + 1]);
-  const float2 nhib = make_float2(-hib.x, -hib.y);
-  __syncthreads();
-  const int q0 = qt + g * SR;  // first output of this thread
-  if (q0 >= L) return;
-  // inputs x~[q0-5 .. q0+SR+4]  (staged row r = q - (qt-5))
-  float2 xv[SR + 10];
-  const float* xp = xs + g * (SR * 8 + (SR >> 3) * 4) + 2 * e2;  // sx_index(g*SR) + channel pair
-#pragma unroll
-  for (int j = 0; j < SR + 10; ++j) xv[j] = *reinterpret_cast<const float2*>(xp + j * 8 + (j >> 3) * 4);
-  // s' values for m = 2*q0 - 5 + i, i in [0, 2SR+10)
-  float2 s[2 * SR + 10];
-#pragma unroll
-  for (int i = 0; i < 2 * SR + 10; ++i) {
-    // m = 2*q0 - 5 + i ; q = floor(m/2) = q0 + ((i - 5) >> 1) ; m is odd iff i is even
-    const int qq = (i - 5) >> 1;
-    float2 u = make_float2(0.f, 0.f);
-    if ((i & 1) == 0) {  // m odd: inputs q+d, d = -2..3, taps 6-2d
-#pragma unroll
-      for (int d = -2; d <= 3; ++d) u = ffma2(xv[qq + d + 5], fu[6 - 2 * d], u);
-    } else {  // m even: d = -3..2, taps 5-2d
-#pragma unroll
-      for (int d = -3; d <= 2; ++d) u = ffma2(xv[qq + d + 5], fu[5 - 2 * d], u);
-    }
-    const float2 z = fmul2(u, al2);
-    const float2 c = make_float2(__cosf(z.x), __cosf(z.y));
-    s[i] = ffma2(c, nhib, u);
-  }
-  // replicate-clamp of the 2x-rate signal at the sequence ends (only boundary threads)
-  if (q0 == 0 || q0 + SR + 3 >= L) {
-    const int ic = 2 * (L - q0) + 5;  // first i with m >= 2L
-    float2 prev = s[5];               // m = 0 when q0 == 0
-#pragma unroll
-    for (int i = 0; i < 2 * SR + 10; ++i) {
-      if (q0 == 0 && i < 5) s[i] = prev;
-      if (i < ic) prev = s[i];
-      else s[i] = prev;
-    }
-  }
-  const long long obase = (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)(row0 + q0) * 8 + 2 * e2;
-#pragma unroll
-  for (int j = 0; j < SR; ++j) {
-    if (q0 + j < L) {
-      float2 acc = hib;
-#pragma unroll
-      for (int k = 0; k < 12; ++k) acc = ffma2(fd[k], s[2 * j + k], acc);
-      if (OUT_BF16)
-        *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)y + obase + j * 8) = __floats2bfloat162_rn(acc.x, acc.y);
-      else
-        *reinterpret_cast<float2*>((float*)y + obase + j * 8) = acc;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------ persistent, TMA-fed variant
-// Same arithmetic as above (packed FFMA2 pairs), but: persistent CTAs walk (batch, chunk, time-tile)
-// work items; the (17*32 + 10) x 8-channel fp32 input window of the NEXT item is fetched with one
+// Persistent CTAs walk (batch, chunk, time-tile) work items; the (17*32 + 10) x 8-channel fp32 input window of the NEXT item is fetched with one
 // cp.async.bulk (UBLKCP) into the other shared-memory buffer while the current item is computed;
 // 17 outputs per thread makes the un-padded 32-byte-row window bank-conflict free for the
 // (4 pairs x 8 groups) 64-bit reads of a warp; replicate clamps are patched in shared memory and
@@ -160,7 +66,7 @@ __device__ __forceinline__ void pbulk_g2s(uint32_t dst, const void* src, uint32_
                : "memory");
 }
 
-template <bool OUT_BF16>
+template <int OUT_KIND>
 __global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(
     const float* __restrict__ x, void* __restrict__ y, const float* __restrict__ a, const float* __restrict__ inv_b,
     const float* __restrict__ filt, long long batch_stride, long long chunk_stride, int row0, int nchunk, int L,
@@ -269,8 +175,8 @@ __global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(
           float2 acc = hib;
 #pragma unroll
           for (int k = 0; k < 12; ++k) acc = ffma2(fd[k], s[2 * j + k], acc);
-          if (OUT_BF16)
-            *reinterpret_cast<__nv_bfloat162*>((__nv_bfloat16*)y + obase + j * 8) = __floats2bfloat162_rn(acc.x, acc.y);
+          if (OUT_KIND)
+            *reinterpret_cast<uint32_t*>((unsigned short*)y + obase + j * 8) = fh::pack16(acc.x, acc.y, OUT_KIND == 2);
           else
             *reinterpret_cast<float2*>((float*)y + obase + j * 8) = acc;
         }
@@ -279,87 +185,6 @@ __global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(
     buf ^= 1;
   }
 }
-
-// scalar variant (one channel per thread, 256 threads): kept selectable, see fh_snake_aa_chunked
-template <bool OUT_BF16>
-__global__ void __launch_bounds__(256) snake_aa_chunked_scalar_kernel(const float* __restrict__ x, void* __restrict__ y,
-                                                               const float* __restrict__ a,
-                                                               const float* __restrict__ inv_b,
-                                                               const float* __restrict__ filt, long long batch_stride,
-                                                               long long chunk_stride, int row0, int nchunk, int L) {
-  __shared__ __align__(16) float xs[sx_index(SXR) + 8];
-  const int ntile = (L + STT - 1) / STT;
-  int id = blockIdx.x;
-  const int tile = id % ntile;
-  id /= ntile;
-  const int ch = id % nchunk, b = id / nchunk;
-  const int qt = tile * STT;
-  const float* xb = x + (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)row0 * 8;
-  // stage rows [qt-5, qt+STT+5), replicate-clamped, as float4 halves of each 8-channel row
-  for (int i = threadIdx.x; i < SXR * 2; i += 256) {
-    const int r = i >> 1, h = i & 1;
-    const int t = min(max(qt - 5 + r, 0), L - 1);
-    const float4 v = __ldg(reinterpret_cast<const float4*>(xb + (long long)t * 8 + h * 4));
-    *reinterpret_cast<float4*>(&xs[sx_index(r) + h * 4]) = v;
-  }
-  float f[12], fu[12];  // down taps; up taps with the x2 gain folded in
-#pragma unroll
-  for (int k = 0; k < 12; ++k) {
-    f[k] = __ldg(filt + k);
-    fu[k] = 2.0f * f[k];
-  }
-  const int e = threadIdx.x & 7, g = threadIdx.x >> 3;
-  const float al2 = 2.0f * a[ch * 8 + e], hib = 0.5f * inv_b[ch * 8 + e];
-  __syncthreads();
-  const int q0 = qt + g * SR;  // first output of this thread
-  if (q0 >= L) return;
-  // inputs x~[q0-5 .. q0+SR+4]  (staged row r = q - (qt-5))
-  float xv[SR + 10];
-  const float* xp = xs + g * (SR * 8 + (SR >> 3) * 4) + e;  // sx_index(g*SR) + e; g*SR is a multiple of 8
-#pragma unroll
-  for (int j = 0; j < SR + 10; ++j) xv[j] = xp[j * 8 + (j >> 3) * 4];
-  // s values for m = 2*q0 - 5 + i, i in [0, 2SR+11)
-  float s[2 * SR + 10];
-#pragma unroll
-  for (int i = 0; i < 2 * SR + 10; ++i) {
-    // m = 2*q0 - 5 + i ; q = floor(m/2) = q0 + ((i - 5) >> 1) ; parity of m = parity of (i + 1)
-    const int qq = (i - 5) >> 1;  // arithmetic shift: i=0 -> -3
-    float u = 0.f;
-    if ((i & 1) == 0) {  // m odd: inputs q+d, d = -2..3, taps 6-2d
-#pragma unroll
-      for (int d = -2; d <= 3; ++d) u = fmaf(xv[qq + d + 5], fu[6 - 2 * d], u);
-    } else {  // m even: d = -3..2, taps 5-2d
-#pragma unroll
-      for (int d = -3; d <= 2; ++d) u = fmaf(xv[qq + d + 5], fu[5 - 2 * d], u);
-    }
-    s[i] = fmaf(-hib, __cosf(u * al2), u);  // s - inv_b/2, see the header comment
-  }
-  // replicate-clamp of the 2x-rate signal at the sequence ends (only boundary threads)
-  if (q0 == 0 || q0 + SR + 3 >= L) {
-    const int ic = 2 * (L - q0) + 5;  // first i with m >= 2L
-    float prev = s[5];                // m = 0 when q0 == 0
-#pragma unroll
-    for (int i = 0; i < 2 * SR + 10; ++i) {
-      if (q0 == 0 && i < 5) s[i] = prev;
-      if (i < ic) prev = s[i];
-      else s[i] = prev;
-    }
-  }
-  const long long obase = (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)(row0 + q0) * 8 + e;
-#pragma unroll
-  for (int j = 0; j < SR; ++j) {
-    if (q0 + j < L) {
-      float acc = hib;
-#pragma unroll
-      for (int k = 0; k < 12; ++k) acc = fmaf(f[k], s[2 * j + k], acc);
-      if (OUT_BF16)
-        ((__nv_bfloat16*)y)[obase + j * 8] = __float2bfloat16(acc);
-      else
-        ((float*)y)[obase + j * 8] = acc;
-    }
-  }
-}
-
 
 __global__ void convpost_tanh_chunked_kernel(const float* __restrict__ x, long long batch_stride,
                                              long long chunk_stride, int row0, const float* __restrict__ w, float bias,
@@ -395,51 +220,29 @@ __global__ void convpost_tanh_chunked_kernel(const float* __restrict__ x, long l
 
 extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
     const float* x, void* y, const float* a, const float* inv_b, const float* filt, int64_t batch_stride,
-    int64_t chunk_stride, int row0, int B, int C, int L, int out_is_bf16, void* stream) {
+    int64_t chunk_stride, int row0, int B, int C, int L, int out_kind, void* stream) {
   FH_REQUIRE(B > 0 && C > 0 && (C % 8) == 0 && L > 0, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: C must be a multiple of 8");
-  FH_REQUIRE(((uintptr_t)x % 16) == 0 && (batch_stride % 4) == 0 && (chunk_stride % 4) == 0, FH_ERR_BAD_ALIGN,
-             "fh_snake_aa_chunked: x must be 16-byte aligned");
-  const long long nblk = (long long)((L + STT - 1) / STT) * (C / 8) * B;
-  FH_REQUIRE(nblk <= 2147483647LL, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: grid too large");
-  static int variant = -1;
-  if (variant < 0) {
-    const char* e = getenv("FH_SNAKE_VARIANT");
-    variant = e ? atoi(e) : 2;
+  FH_REQUIRE(out_kind >= 0 && out_kind <= 2, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: out_kind must be 0 (fp32), 1 (bf16), 2 (fp16)");
+  FH_REQUIRE(((uintptr_t)x % 16) == 0 && (batch_stride % 8) == 0 && (chunk_stride % 8) == 0, FH_ERR_BAD_ALIGN,
+             "fh_snake_aa_chunked: x must be 16-byte aligned and strides multiples of 8");
+  const int ntile = (L + PTT - 1) / PTT;
+  const long long total = (long long)ntile * (C / 8) * B;
+  FH_REQUIRE(total <= 2147483647LL && row0 >= 5, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: needs a left halo of >= 5 rows");
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
   }
-  if (variant == 2) {  // persistent, bulk-copy fed, packed FFMA2
-    const int ntile = (L + PTT - 1) / PTT;
-    const long long total = (long long)ntile * (C / 8) * B;
-    FH_REQUIRE(total <= 2147483647LL && row0 >= 5 && (chunk_stride % 8) == 0, FH_ERR_BAD_SHAPE,
-               "fh_snake_aa_chunked: needs a left halo of >= 5 rows");
-    static int sms = 0;
-    if (!sms) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      if (sms <= 0) sms = 148;
-    }
-    const int grid = (int)(total < (long long)sms * 4 ? total : (long long)sms * 4);
-    if (out_is_bf16)
-      snake_aa_chunked_tma_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(
-          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L, ntile, (int)total);
-    else
-      snake_aa_chunked_tma_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
-          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L, ntile, (int)total);
-  } else if (variant == 1) {  // packed-FFMA2, two channels per thread
-    if (out_is_bf16)
-      snake_aa_chunked_kernel<true><<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(
-          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L);
-    else
-      snake_aa_chunked_kernel<false><<<(unsigned)nblk, 128, 0, (cudaStream_t)stream>>>(
-          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L);
-  } else {
-    if (out_is_bf16)
-      snake_aa_chunked_scalar_kernel<true><<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(
-          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L);
-    else
-      snake_aa_chunked_scalar_kernel<false><<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(
-          x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, C / 8, L);
-  }
+  const int grid = (int)(total < (long long)sms * 4 ? total : (long long)sms * 4);
+#define FH_SNAKE_LAUNCH(KIND)                                                                                \
+  snake_aa_chunked_tma_kernel<KIND><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, a, inv_b, filt, batch_stride, \
+                                                                           chunk_stride, row0, C / 8, L, ntile, (int)total)
+  if (out_kind == 0) FH_SNAKE_LAUNCH(0);
+  else if (out_kind == 1) FH_SNAKE_LAUNCH(1);
+  else FH_SNAKE_LAUNCH(2);
+#undef FH_SNAKE_LAUNCH
   return fh::check_launch("fh_snake_aa_chunked");
 }
 

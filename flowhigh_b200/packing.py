@@ -3,7 +3,7 @@
 `tapped_conv_weights` turns Conv1d / ConvTranspose1d / Linear weights into the generic
 "tapped convolution" form both conv kernels consume:
     out[b, co, P*t + p] = sum_m sum_ci W[p][m][co][ci] * x[b, ci, t + off[p][m]]
-`pack_tc` lays W out as the shared-memory image of fh_tc_conv_bf16
+`pack_tc` lays W out as the shared-memory image of fh_tc_conv
 ([p][n_tile][ci_pair][tap][2 chunks][bn rows][8 ci] bf16, K-major no-swizzle core matrices).
 """
 from __future__ import annotations
@@ -89,8 +89,8 @@ def round_up(x: int, m: int) -> int:
 
 
 def pack_tc(tc: TappedConv, device, cin_pad: Optional[int] = None, cout_pad: Optional[int] = None,
-            bn: Optional[int] = None) -> Tuple[torch.Tensor, int, int, int]:
-    """-> (packed bf16 tensor, cin_pad, cout_pad, bn)."""
+            bn: Optional[int] = None, dtype=torch.bfloat16) -> Tuple[torch.Tensor, int, int, int]:
+    """-> (packed 16-bit tensor (bf16 or fp16), cin_pad, cout_pad, bn)."""
     P, ntaps, cout, cin = tc.w.shape
     cin_pad = cin_pad or round_up(cin, 16)
     cout_pad = cout_pad or round_up(cout, 16)
@@ -100,7 +100,7 @@ def pack_tc(tc: TappedConv, device, cin_pad: Optional[int] = None, cout_pad: Opt
     w[:, :, :cout, :cin] = tc.w
     # [P][tap][nt][bn][cp][2][8] -> [P][nt][cp][tap][2][bn][8]
     w = w.reshape(P, ntaps, n_tiles, bn, cin_pad // 16, 2, 8).permute(0, 2, 4, 1, 5, 3, 6).contiguous()
-    return w.to(torch.bfloat16).to(device), cin_pad, cout_pad, bn
+    return w.to(dtype).to(device), cin_pad, cout_pad, bn
 
 
 def pad_vec(v: Optional[torch.Tensor], n: int, fill: float = 0.0) -> Optional[torch.Tensor]:

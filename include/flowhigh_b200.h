@@ -101,7 +101,7 @@ int fh_sincos_embed_f32(const float* w, float t, float* out, int half, void* str
 int fh_dwconv_gelu_res_f32(const float* E, const float* w, const float* b, float* out,
                            int B, int N, int C, int k, void* stream);
 /* out = x / max(||x||,1e-12) * sqrt(C) * gamma + beta (beta may be NULL)   transformer.py:49-59,82-88
- * out_mode 0: fp32 row-major [M,C];  1: bf16 chunked [C/8][Mp][8] (row pitch out_rows). */
+ * out_mode 0: fp32 row-major [M,C];  1: bf16 chunked [C/8][Mp][8] (row pitch out_rows);  2: fp16 chunked. */
 int fh_rmsnorm_f32(const float* x, const float* gamma, const float* beta, void* out, int out_mode,
                    int64_t out_rows, int M, int C, void* stream);
 /* qkv [B*N, 3*H*D] -> q,k,v [B,H,N,D]; q,k: l2norm * gamma[h,d] * sqrt(D), rotary (halves)
@@ -136,27 +136,27 @@ int fh_convpost_tanh_f32(const float* x, const float* w, float bias, float* y, i
                          void* stream);
 /* [B,R,C] -> [B,C,R]  (the `b n d -> b d n` rearrange at melvoco.py:115) */
 int fh_transpose_f32(const float* src, float* dst, int B, int R, int C, void* stream);
-/* elementwise fp32 -> bf16 (whole chunked buffers, halos included) */
-int fh_cast_f32_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* elementwise fp32 -> bf16 / fp16 (whole chunked buffers, halos included) */
+int fh_cast_f32_16(const float* src, void* dst, int64_t n, int fp16, void* stream);
 
 /* ---------------------------------------------------------------- tensor-core path (tcgen05)
- * Implicit-GEMM tapped convolution on chunked operands, bf16 x bf16 -> fp32 in TMEM.
- *   A: activations, chunked bf16 [B][Cin/8][Lp_a][8] with >= halo zero rows each side of [0,L)
+ * Implicit-GEMM tapped convolution on chunked 16-bit operands (bf16 or fp16) -> fp32 in TMEM.
+ *   A: activations, chunked 16-bit [B][Cin/8][Lp_a][8] with >= halo zero rows each side of [0,L)
  *   W: packed by fh_tc_pack_* (host side, flowhigh_b200/packing.py) into the smem image
- *   out(t, n) at out + b*out_batch + (n/8)*out_chunk + (P*t+p)*out_row + n%8, fp32 or bf16
+ *   out(t, n) at out + b*out_batch + (n/8)*out_chunk + (P*t+p)*out_row + n%8, fp32 or 16-bit
  * A Linear layer is the k = 1 case with L = number of tokens. */
 typedef struct {
-  const void* a;          /* chunked bf16 activations */
+  const void* a;          /* chunked 16-bit activations */
   int64_t a_batch;        /* elements between batches */
   int64_t a_chunk;        /* elements between 8-channel chunks (= Lp_a * 8) */
   int a_row0;             /* row index of t = 0 inside a chunk (left halo) */
   const void* w;          /* packed weights */
   const float* bias;      /* [Cout] or NULL */
-  const void* res;        /* residual, addressed like out (res_is_bf16 selects type) or NULL */
+  const void* res;        /* residual, addressed like out (res_is_16 selects the width) or NULL */
   void* out;
   int64_t out_batch, out_chunk, out_row;
   int64_t res_batch, res_chunk, res_row;
-  int out_is_bf16, res_is_bf16;
+  int out_is_16, res_is_16; /* output / residual stored as 16-bit (type given by `fp16`) instead of fp32 */
   float alpha, beta_res;
   int accumulate;         /* out += ... (fp32 out only) */
   int geglu;              /* epilogue pairs columns (2i, 2i+1) -> gelu(col 2i+1) * col 2i */
@@ -164,19 +164,20 @@ typedef struct {
   int ntaps, P;           /* taps per phase, phases (output stride) */
   const int* tap_off;     /* HOST pointer [P][ntaps] row offsets */
   int bn;                 /* N tile, multiple of 16, <= 256 */
+  int fp16;               /* 16-bit operand format: 0 = bfloat16, 1 = IEEE half (same rate, 3 more mantissa bits) */
 } fh_tc_conv_args;
-int fh_tc_conv_bf16(const fh_tc_conv_args* args, void* stream);
+int fh_tc_conv(const fh_tc_conv_args* args, void* stream);
 /* bytes of the packed weight image for given shape (host helper, no GPU work) */
 int64_t fh_tc_packed_weight_bytes(int Cin, int Cout, int ntaps, int P, int bn);
 
-/* fp32 [B,C,L] planar or [M,C] row-major -> chunked bf16; src strides in elements */
-int fh_to_chunked_bf16(const float* src, int64_t src_batch, int64_t src_c, int64_t src_t,
-                       void* dst, int64_t dst_batch, int64_t dst_chunk, int dst_row0,
-                       int B, int C, int L, void* stream);
-/* chunked anti-aliased snake: x chunked fp32 -> y chunked bf16 (same geometry) */
+/* fp32 [B,C,L] planar or [M,C] row-major -> chunked 16-bit (bf16, or half when fp16 != 0); src strides in elements */
+int fh_to_chunked_16(const float* src, int64_t src_batch, int64_t src_c, int64_t src_t,
+                     void* dst, int64_t dst_batch, int64_t dst_chunk, int dst_row0,
+                     int B, int C, int L, int fp16, void* stream);
+/* chunked anti-aliased snake: x chunked fp32 -> y chunked (same geometry); out_kind 0 fp32, 1 bf16, 2 fp16 */
 int fh_snake_aa_chunked(const float* x, void* y, const float* a, const float* inv_b, const float* filt,
                         int64_t batch_stride, int64_t chunk_stride, int row0, int B, int C, int L,
-                        int out_is_bf16, void* stream);
+                        int out_kind, void* stream);
 int fh_convpost_tanh_chunked(const float* x, int64_t batch_stride, int64_t chunk_stride, int row0,
                              const float* w, float bias, float* y, int B, int C, int L, void* stream);
 

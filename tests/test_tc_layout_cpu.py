@@ -1,4 +1,4 @@
-"""CPU emulation of fh_tc_conv_bf16's addressing (tile decode, chunk windows, packed weight image,
+"""CPU emulation of fh_tc_conv's addressing (tile decode, chunk windows, packed weight image,
 tap-shifted descriptors, epilogue indexing) against the plain tapped convolution.  This pins the
 host-side packing (flowhigh_b200/packing.py) and the index arithmetic of csrc/tc_conv.cu; the
 tensor-core semantics themselves are checked on the GPU (tests/test_gpu_kernels.py)."""
