@@ -5,7 +5,8 @@
 
 Workload (BASELINE.json configs[1]): midpoint ODE (2 NFE), batch of 64 x 10 s clips, 12 kHz -> 48 kHz,
 basic_cfm, transformer 2L x 16H x 64, BigVGAN 48 kHz / 256-band (ASSUMED vocoder config),
-random-init weights, synthetic speech-like audio, bf16 tensor-core path.  One "step" = one pass of the
+random-init weights, synthetic speech-like audio, 16-bit tensor-core path (fp16 operands by default,
+--precision bf16 selects bfloat16: same MMA rate and bytes).  One "step" = one pass of the
 whole path (resample -> log-mel -> CFM -> vocoder -> post-processing) over one batch per GPU.
 
   value : 48 kHz audio-seconds produced per wall second, whole job, inputs resident in HBM

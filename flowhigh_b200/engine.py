@@ -43,7 +43,7 @@ class _F32Weight:
 
 class Engine:
     def __init__(self, sd: Dict[str, torch.Tensor], vcfg: VocoderConfig, bcfg: BackboneConfig = BackboneConfig(),
-                 device="cuda:0", precision: str = "bf16", precise_mel: Optional[bool] = None):
+                 device="cuda:0", precision: str = "fp16", precise_mel: Optional[bool] = None):
         if precision not in ("fp32", "bf16", "fp16"):
             raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
         self.device = torch.device(device)

@@ -142,7 +142,7 @@ class PostProcessing:
 class FlowHighSR(nn.Module):
     def __init__(self, flowhigh: FLowHigh, sigma=0.0, ode_atol=1e-5, ode_rtol=1e-5, use_torchode=False,
                  cfm_method="basic_cfm", torchdiffeq_ode_method="midpoint", torchode_method_klass=None,
-                 cond_drop_prob=0.0, upsampling_method="scipy", precision: str = "bf16"):
+                 cond_drop_prob=0.0, upsampling_method="scipy", precision: str = "fp16"):
         super().__init__()
         if use_torchode:
             raise NotImplementedError("adaptive-step torchode sampling is a SURVEY 8f 'next' row")
@@ -319,7 +319,7 @@ class FlowHighSR(nn.Module):
 
     # ------------------------------------------------------------------ loaders
     @classmethod
-    def from_local(cls, ckpt_dir, device="cuda", precision: str = "bf16") -> "FlowHighSR":
+    def from_local(cls, ckpt_dir, device="cuda", precision: str = "fp16") -> "FlowHighSR":
         """flowhighsr.py:109-137: expects bigvgan_48khz_256band.{json,pt} and FLowHigh_basic_400k.pt."""
         ckpt_dir = Path(ckpt_dir)
         voc = MelVoco(vocoder_config=ckpt_dir / "bigvgan_48khz_256band.json",
@@ -331,7 +331,7 @@ class FlowHighSR(nn.Module):
         return model.to(device).eval()
 
     @classmethod
-    def from_pretrained(cls, device="cuda", precision: str = "bf16") -> "FlowHighSR":
+    def from_pretrained(cls, device="cuda", precision: str = "fp16") -> "FlowHighSR":
         """flowhighsr.py:139-149 (needs network access to the HF hub)."""
         from huggingface_hub import hf_hub_download
         local_path = None
@@ -341,7 +341,7 @@ class FlowHighSR(nn.Module):
         return cls.from_local(Path(local_path).parent, device, precision=precision)
 
     @classmethod
-    def from_random(cls, vcfg: Optional[VocoderConfig] = None, device="cuda", seed: int = 0, precision: str = "bf16",
+    def from_random(cls, vcfg: Optional[VocoderConfig] = None, device="cuda", seed: int = 0, precision: str = "fp16",
                     vocoder_gain: float = 0.7, depth: int = 2, **kw) -> "FlowHighSR":
         """Random-init weights of the named architecture (no checkpoints offline)."""
         vcfg = vcfg or VocoderConfig.assumed_48k()
