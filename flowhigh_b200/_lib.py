@@ -57,6 +57,9 @@ SIGNATURES = {
     "fh_attention_f32": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _f, _p]),
     "fh_geglu_f32": (_i, [_p, _p, _i, _i64, _i, _i, _i, _p]),
     "fh_axpby_f32": (_i, [_p, _p, _f, _f, _p, _i64, _p]),
+    "fh_broadcast_row_f32": (_i, [_p, _p, _i64, _i, _p]),
+    "fh_mel_cutoff_f32": (_i, [_p, _p, _i, _i, _i, _f, _p]),
+    "fh_mel_splice_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "fh_conv1d_taps_f32": (_i, [_p, _p, _p, _p, _p, _f, _f, _i, _p, _i, _i, _i, _i, _i, _i, _p]),
     "fh_snake_aa_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "fh_convpost_tanh_f32": (_i, [_p, _p, _f, _p, _i, _i, _i, _p]),

@@ -297,6 +297,50 @@ __global__ void axpby_kernel(const float* __restrict__ x, const float* __restric
   if (i < n) y[i] = z ? a * x[i] + b * z[i] : a * x[i];
 }
 
+__global__ void broadcast_row_kernel(const float* __restrict__ row, float* __restrict__ out, int64_t M, int C) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M * C) out[i] = row[i % C];
+}
+
+// cfm_superresolution.py:134-144 on exp(mel) of one clip [N, F]: e[f] = sum_n exp(mel[n,f]); cumsum;
+// scan from the top for the first bin whose cumulative energy is below percentile * total (bin 0 never tested)
+__global__ void mel_cutoff_kernel(const float* __restrict__ mel, int* __restrict__ cutoff, int N, int F,
+                                  float percentile) {
+  extern __shared__ float e_sm[];
+  const int b = blockIdx.x;
+  const float* m = mel + (size_t)b * N * F;
+  for (int f = threadIdx.x; f < F; f += blockDim.x) {
+    float acc = 0.f;
+    for (int n = 0; n < N; ++n) acc += fabsf(expf(m[(size_t)n * F + f]));
+    e_sm[f] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int f = 0; f < F; ++f) {
+      acc += e_sm[f];
+      e_sm[f] = acc;
+    }
+    const float thr = e_sm[F - 1] * percentile;
+    int c = 0;
+    for (int idx = F - 1; idx >= 1; --idx)
+      if (e_sm[idx] < thr) {
+        c = idx;
+        break;
+      }
+    cutoff[b] = c;
+  }
+}
+
+__global__ void mel_splice_kernel(const float* __restrict__ lo, const float* __restrict__ hi,
+                                  const int* __restrict__ cutoff, float* __restrict__ out, int64_t per_clip, int F,
+                                  int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = (int)(i / per_clip), f = (int)(i % F);
+  out[i] = f < cutoff[b] ? lo[i] : hi[i];
+}
+
 }  // namespace
 
 // ================================================================================ C ABI
@@ -394,4 +438,27 @@ extern "C" __attribute__((visibility("default"))) int fh_axpby_f32(const float* 
   if (n <= 0) return FH_OK;
   axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, z, a, b, y, n);
   return fh::check_launch("fh_axpby_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_broadcast_row_f32(const float* row, float* out, int64_t M, int C,
+                                                                          void* stream) {
+  FH_REQUIRE(M > 0 && C > 0, FH_ERR_BAD_SHAPE, "fh_broadcast_row_f32: bad shape");
+  broadcast_row_kernel<<<(unsigned)((M * C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(row, out, M, C);
+  return fh::check_launch("fh_broadcast_row_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_mel_cutoff_f32(const float* mel, int* cutoff, int B, int N, int F,
+                                                                       float percentile, void* stream) {
+  FH_REQUIRE(B > 0 && N > 0 && F > 0 && F <= 4096, FH_ERR_BAD_SHAPE, "fh_mel_cutoff_f32: bad shape");
+  mel_cutoff_kernel<<<B, 256, F * sizeof(float), (cudaStream_t)stream>>>(mel, cutoff, N, F, percentile);
+  return fh::check_launch("fh_mel_cutoff_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_mel_splice_f32(const float* lo, const float* hi, const int* cutoff,
+                                                                       float* out, int B, int N, int F, void* stream) {
+  FH_REQUIRE(B > 0 && N > 0 && F > 0, FH_ERR_BAD_SHAPE, "fh_mel_splice_f32: bad shape");
+  const int64_t n = (int64_t)B * N * F;
+  mel_splice_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(lo, hi, cutoff, out, (int64_t)N * F, F,
+                                                                                 n);
+  return fh::check_launch("fh_mel_splice_f32");
 }

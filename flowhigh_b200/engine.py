@@ -397,23 +397,59 @@ class Engine:
             self._call("fh_rmsnorm_f32", h.data_ptr(), gam.data_ptr(), None, a.data_ptr(), 0, 0, M, D, st)
             self._sgemm(a, D, sd[FH + "to_pred.weight"], D, None, base, Din, 1.0, coef, out, Din, M, Din, D)
 
+    def mel_cutoff_bins(self, cond_mel: torch.Tensor) -> torch.Tensor:
+        """mel_cutoff_bins (cfm_superresolution.py:154-159): per-clip 99.95 % energy bin of exp(mel)."""
+        B, N, Fm = cond_mel.shape
+        cut = torch.empty((B,), dtype=torch.int32, device=self.device)
+        self._call("fh_mel_cutoff_f32", cond_mel.data_ptr(), cut.data_ptr(), B, N, Fm, 0.9995, self.stream)
+        return cut
+
+    def mel_splice(self, lo: torch.Tensor, hi: torch.Tensor, cut: torch.Tensor) -> torch.Tensor:
+        """mel_replace_ops (cfm_superresolution.py:146-152): bins below the cutoff from `lo`, the rest from `hi`."""
+        B, N, Fm = lo.shape
+        out = torch.empty_like(lo)
+        self._call("fh_mel_splice_f32", lo.data_ptr(), hi.data_ptr(), cut.data_ptr(), out.data_ptr(), B, N, Fm, self.stream)
+        return out
+
+    def _field_update(self, x, cond, null, t, base, coef, out, cond_scale, packed):
+        """out = base + coef * v(t, x), with classifier-free guidance when cond_scale != 1 (flow.py:165-178)."""
+        if cond_scale == 1.0:
+            self.vector_field_step(x, cond, t, base, coef, out, cond_packed=packed)
+            return self.tc
+        n = x.numel()
+        zero = self.buf("cfg_zero", x.shape)
+        vc = self.buf("cfg_vc", x.shape, zero=False)
+        vn = self.buf("cfg_vn", x.shape, zero=False)
+        self.vector_field_step(x, cond, t, zero, 1.0, vc, cond_packed=False)
+        self.vector_field_step(x, null, t, zero, 1.0, vn, cond_packed=False)
+        # null + (logits - null) * s
+        self._call("fh_axpby_f32", vn.data_ptr(), vc.data_ptr(), 1.0 - cond_scale, cond_scale, vc.data_ptr(), n, self.stream)
+        self._call("fh_axpby_f32", base.data_ptr(), vc.data_ptr(), 1.0, coef, out.data_ptr(), n, self.stream)
+        return False
+
     def sample_mel(self, cond_mel: torch.Tensor, eps: torch.Tensor, *, steps: int, ode_method: str, cfm_method: str,
-                   sigma: float, cond_scale: float = 1.0) -> torch.Tensor:
-        """CFM sampler (cfm_superresolution.py:162-284 up to `sampled`): prior + fixed-grid ODE."""
-        if cond_scale != 1.0:
-            raise NotImplementedError("classifier-free guidance (cond_scale != 1) is a SURVEY 8f 'next' row")
+                   sigma: float, cond_scale: float = 1.0, mel_pp: bool = False) -> torch.Tensor:
+        """CFM sampler (cfm_superresolution.py:162-284 up to `sampled`): prior + fixed-grid ODE (+ mel_pp)."""
         if ode_method not in ("euler", "midpoint"):
             raise ValueError(f"unsupported ODE method {ode_method!r} (euler|midpoint)")
         B, N, Din = cond_mel.shape
         n = cond_mel.numel()
         y = torch.empty_like(cond_mel)
+        cut = None
         if cfm_method == "basic_cfm":
             self._call("fh_axpby_f32", eps.data_ptr(), None, 1.0, 0.0, y.data_ptr(), n, self.stream)
-        elif cfm_method in ("independent_cfm_adaptive", "independent_cfm_constant"):
+        elif cfm_method in ("independent_cfm_adaptive", "independent_cfm_constant", "independent_cfm_mix"):
             # std_1 / std_2 quirk (cfm_superresolution.py:180-183): y0 = cond * 1 + eps * sigma
             self._call("fh_axpby_f32", cond_mel.data_ptr(), eps.data_ptr(), 1.0, float(sigma), y.data_ptr(), n, self.stream)
+            if cfm_method == "independent_cfm_mix":  # low bins from the adaptive prior, high bins pure noise (:232-237)
+                cut = self.mel_cutoff_bins(cond_mel)
+                y = self.mel_splice(y, eps, cut)
         else:
-            raise NotImplementedError(f"cfm_method {cfm_method!r}: the mel-cutoff splice is a SURVEY 8f 'next' row")
+            raise ValueError(f"unknown cfm_method {cfm_method!r}")
+        null = None
+        if cond_scale != 1.0:
+            null = torch.empty_like(cond_mel)
+            self._call("fh_broadcast_row_f32", self.sd[FH + "null_cond"].data_ptr(), null.data_ptr(), B * N, Din, self.stream)
         tgrid = np.linspace(0.0, 1.0, steps + 1, dtype=np.float32)  # torch.linspace(0,1,steps+1) fp32
         ymid = torch.empty_like(y) if ode_method == "midpoint" else None
         packed = False
@@ -421,13 +457,16 @@ class Engine:
             t0, t1 = tgrid[i], tgrid[i + 1]
             dt = np.float32(t1 - t0)
             if ode_method == "euler":
-                self.vector_field_step(y, cond_mel, float(t0), y, float(dt), y, cond_packed=packed)
+                packed = self._field_update(y, cond_mel, null, float(t0), y, float(dt), y, cond_scale, packed)
             else:
                 half = np.float32(0.5) * dt
-                self.vector_field_step(y, cond_mel, float(t0), y, float(half), ymid, cond_packed=packed)
-                packed = self.tc
-                self.vector_field_step(ymid, cond_mel, float(np.float32(t0 + half)), y, float(dt), y, cond_packed=packed)
-            packed = self.tc
+                packed = self._field_update(y, cond_mel, null, float(t0), y, float(half), ymid, cond_scale, packed)
+                packed = self._field_update(ymid, cond_mel, null, float(np.float32(t0 + half)), y, float(dt), y,
+                                            cond_scale, packed)
+        if mel_pp:  # cfm_superresolution.py:278-279
+            if cut is None:
+                cut = self.mel_cutoff_bins(cond_mel)
+            y = self.mel_splice(cond_mel, y, cut)
         return y
 
     # ------------------------------------------------------------------ stage: vocoder

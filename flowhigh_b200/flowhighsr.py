@@ -112,14 +112,15 @@ class FLowHigh(_Tree):
 
     def forward_with_cond_scale(self, x, *, times, cond, cond_scale=1.0, cond_mask=None, self_attn_mask=None):
         """flow.py:165-178: returns the vector field v(times, x | cond)."""
-        if cond_scale != 1.0:
-            raise NotImplementedError("cond_scale != 1 (classifier-free guidance) is a SURVEY 8f 'next' row")
         eng = self._owner()._engine()
         x = x.to(eng.device, torch.float32).contiguous()
         cond = cond.to(eng.device, torch.float32).contiguous()
         zero = torch.zeros_like(x)
         out = torch.empty_like(x)
-        eng.vector_field_step(x, cond, float(times), zero, 1.0, out)
+        null = None
+        if cond_scale != 1.0:
+            null = eng.sd["flowhigh.null_cond"].expand_as(cond).contiguous()
+        eng._field_update(x, cond, null, float(times), zero, 1.0, out, float(cond_scale), False)
         return out
 
     forward = forward_with_cond_scale
@@ -219,8 +220,6 @@ class FlowHighSR(nn.Module):
                std_2=None, mel_pp=False, cfm_method=None, eps: Optional[torch.Tensor] = None):
         if cfm_method not in CFM_METHODS:
             cfm_method = self.cfm_method
-        if mel_pp:
-            raise NotImplementedError("mel_pp (mel-domain low-band replacement) is a SURVEY 8f 'next' row")
         eng = self._engine()
         cond = cond.to(eng.device, torch.float32).contiguous()
         is_audio = cond.dim() == 2 or (cond.dim() == 3 and cond.shape[1] == 1)
@@ -228,7 +227,7 @@ class FlowHighSR(nn.Module):
             cond = eng.encode(cond.reshape(cond.shape[0], -1))
         mel = eng.sample_mel(cond, self._noise_like(cond, eps), steps=int(time_steps),
                              ode_method=self.odeint_kwargs["method"], cfm_method=cfm_method, sigma=float(self.sigma),
-                             cond_scale=float(cond_scale))
+                             cond_scale=float(cond_scale), mel_pp=bool(mel_pp))
         if not decode_to_audio:
             return mel
         return eng.vocoder(mel).unsqueeze(1)

@@ -76,6 +76,13 @@ def f32_conv_buffers(tc: TappedConv, device):
 
 
 def pick_bn(cout_pad: int) -> int:
+    import os
+    ov = os.environ.get("FH_BN_OVERRIDE")  # e.g. "192:96,384:128" (tuning experiments)
+    if ov:
+        for item in ov.split(","):
+            k, v = item.split(":")
+            if int(k) == cout_pad:
+                return int(v)
     if cout_pad <= 256:
         return cout_pad
     for bn in range(256, 127, -16):

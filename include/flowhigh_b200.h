@@ -118,6 +118,14 @@ int fh_geglu_f32(const float* u, void* g, int out_mode, int64_t out_rows, int M,
 /* y = a*x + b*z  elementwise (prior: y0 = cond + sigma*eps, cfm_superresolution.py:222-230) */
 int fh_axpby_f32(const float* x, const float* z, float a, float b, float* y, int64_t n, void* stream);
 
+/* out[m, :] = row[:]  (null_cond broadcast for classifier-free guidance, flow.py:224-230) */
+int fh_broadcast_row_f32(const float* row, float* out, int64_t M, int C, void* stream);
+/* cutoff[b] = locate_cutoff_freq(exp(mel[b]))  cfm_superresolution.py:134-144,154-159 (percentile 0.9995) */
+int fh_mel_cutoff_f32(const float* mel, int* cutoff, int B, int N, int F, float percentile, void* stream);
+/* out[b,n,f] = f < cutoff[b] ? lo : hi   (mel_replace_ops, cfm_superresolution.py:146-152) */
+int fh_mel_splice_f32(const float* lo, const float* hi, const int* cutoff, float* out, int B, int N, int F,
+                      void* stream);
+
 /* ---------------------------------------------------------------- vocoder, fp32 path  [B,C,L]
  * Generic tapped convolution: for phase p in [0,P):
  *   out[b, co, P*t + p] = alpha * ( bias[co] + sum_m sum_ci w[p][co][ci][m] * x[b, ci, t + off[p][m]] )

@@ -371,3 +371,41 @@ def test_generate_long_chunked_matches_oracle_per_chunk(cuda_device):
     err = float((out - ref).abs().max())
     print(f"generate_long fp32: K={K} chunks, max-abs vs oracle {err:.3g}")
     assert err <= 5e-4
+
+
+# ------------------------------------------------------------------ CFG, mel_pp, independent_cfm_mix
+def test_mel_cutoff_and_splice(cuda_device):
+    eng, sd, vcfg, g = engine("gen_basic_midpoint", "fp32")
+    mel = torch.from_numpy(g["ref_cond_mel"])
+    mel2 = torch.cat([mel, mel.flip(-1) * 0.5 - 3.0])
+    cut = eng.mel_cutoff_bins(mel2.cuda()).cpu().tolist()
+    ref = [model.mel_cutoff_bin(mel2[i]) for i in range(2)]
+    assert cut == ref, (cut, ref)
+    lo, hi = torch.randn_like(mel2), torch.randn_like(mel2)
+    out = eng.mel_splice(lo.cuda(), hi.cuda(), torch.tensor(cut, dtype=torch.int32).cuda()).cpu()
+    for i in range(2):
+        assert torch.equal(out[i][:, :cut[i]], lo[i][:, :cut[i]]) and torch.equal(out[i][:, cut[i]:], hi[i][:, cut[i]:])
+
+
+@pytest.mark.parametrize("variant", ["cfg", "mix", "mel_pp"])
+def test_sample_variants_f32(cuda_device, variant):
+    g = load_golden("gen_basic_euler4")
+    sd, vcfg = golden_weights(g)
+    cond_mel, eps = torch.from_numpy(g["ref_cond_mel"]), torch.from_numpy(g["eps"])
+    kw = dict(steps=2, ode_method="midpoint", cfm_method="basic_cfm", sigma=0.0)
+    extra = {}
+    if variant == "cfg":
+        extra = dict(cond_scale=1.7)
+    elif variant == "mix":
+        kw.update(cfm_method="independent_cfm_mix", sigma=1e-2)
+    else:
+        extra = dict(mel_pp=True)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    ref64 = model.cfm_sample_mel(sd64, cond_mel.double(), eps.double(), **kw, **extra).float()
+    ref32 = model.cfm_sample_mel(sd, cond_mel, eps, **kw, **extra)
+    eng, *_ = engine("gen_basic_euler4", "fp32")
+    out = eng.sample_mel(cond_mel.cuda(), eps.cuda(), **kw, **extra).cpu()
+    floor = float((ref32 - ref64).abs().max())
+    err = float((out - ref64).abs().max())
+    print(f"sample[{variant}] fp32: max-abs vs fp64 {err:.3g} (oracle fp32's own {floor:.3g})")
+    assert err <= 3 * floor + 1e-4
