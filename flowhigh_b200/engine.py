@@ -92,6 +92,15 @@ class Engine:
             self._bufs[key] = t
         return t
 
+    def _chk(self, *tensors):
+        """Kernels take raw pointers: every tensor handed to the engine must be dense fp32 on this device."""
+        for t in tensors:
+            if t is None:
+                continue
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise ValueError(f"engine tensors must be contiguous fp32 on {self.device} "
+                                 f"(got {t.dtype}, {t.device}, contiguous={t.is_contiguous()})")
+
     def _call(self, name, *args, work=None):
         if self.profile is None:
             _lib.check(getattr(self.lib, name)(*args), name)
@@ -221,6 +230,7 @@ class Engine:
     # ------------------------------------------------------------------ stage: resample + normalise
     def resample_normalise(self, x: torch.Tensor, sr_in: int, sr_out: int = 48000) -> torch.Tensor:
         """x [B, T_in] fp32 on device -> cond [B, T] = resample_poly(x) / max|.|  (flowhighsr.py:68-69)."""
+        self._chk(x)
         B, T_in = x.shape
         plan = tables.resample_plan(sr_in, sr_out)
         absmax = self.buf("rs_absmax", (B,), torch.int32)
@@ -245,6 +255,7 @@ class Engine:
     # ------------------------------------------------------------------ stage: log-mel
     def encode(self, audio: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """MelVoco.encode (melvoco.py:56-86): audio [B,T] -> log-mel [B,N,256]."""
+        self._chk(audio, out)
         B, T = audio.shape
         if T < 785:
             raise ValueError("audio shorter than 785 samples cannot be reflect-padded by 784 (melvoco.py:74)")
@@ -319,6 +330,7 @@ class Engine:
                           out: torch.Tensor, cond_packed: bool = False):
         """out = base + coef * v(t, x | cond)   -- one NFE with the CFM update folded into the
         to_pred GEMM epilogue (flow.py:180-274 + torchdiffeq euler/midpoint step)."""
+        self._chk(x, cond, base, out)
         sd, b = self.sd, self.bcfg
         B, N, Din = x.shape
         M, D, H, Dh = B * N, b.dim, b.heads, b.dim_head
@@ -399,6 +411,7 @@ class Engine:
 
     def mel_cutoff_bins(self, cond_mel: torch.Tensor) -> torch.Tensor:
         """mel_cutoff_bins (cfm_superresolution.py:154-159): per-clip 99.95 % energy bin of exp(mel)."""
+        self._chk(cond_mel)
         B, N, Fm = cond_mel.shape
         cut = torch.empty((B,), dtype=torch.int32, device=self.device)
         self._call("fh_mel_cutoff_f32", cond_mel.data_ptr(), cut.data_ptr(), B, N, Fm, 0.9995, self.stream)
@@ -406,6 +419,7 @@ class Engine:
 
     def mel_splice(self, lo: torch.Tensor, hi: torch.Tensor, cut: torch.Tensor) -> torch.Tensor:
         """mel_replace_ops (cfm_superresolution.py:146-152): bins below the cutoff from `lo`, the rest from `hi`."""
+        self._chk(lo, hi)
         B, N, Fm = lo.shape
         out = torch.empty_like(lo)
         self._call("fh_mel_splice_f32", lo.data_ptr(), hi.data_ptr(), cut.data_ptr(), out.data_ptr(), B, N, Fm, self.stream)
@@ -432,6 +446,7 @@ class Engine:
         """CFM sampler (cfm_superresolution.py:162-284 up to `sampled`): prior + fixed-grid ODE (+ mel_pp)."""
         if ode_method not in ("euler", "midpoint"):
             raise ValueError(f"unsupported ODE method {ode_method!r} (euler|midpoint)")
+        self._chk(cond_mel, eps)
         B, N, Din = cond_mel.shape
         n = cond_mel.numel()
         y = torch.empty_like(cond_mel)
@@ -472,6 +487,7 @@ class Engine:
     # ------------------------------------------------------------------ stage: vocoder
     def vocoder(self, mel: torch.Tensor) -> torch.Tensor:
         """MelVoco.decode (melvoco.py:114-121): mel [B,N,256] -> wave [B, 480 N]."""
+        self._chk(mel)
         if not self.tc:
             return self._vocoder_f32(mel)
         B, N, _ = mel.shape
@@ -632,6 +648,7 @@ class Engine:
     # ------------------------------------------------------------------ stage: post-processing
     def postprocess(self, pred: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
         """PostProcessing.post_processing (postprocessing.py:18-41) per clip: pred [B,Tp], src [B,T] -> [B,T]."""
+        self._chk(pred, src)
         B, T = src.shape
         Tp = pred.shape[1]
         NT, NTp = 1 + T // 480, 1 + Tp // 480

@@ -326,6 +326,16 @@ def test_generate_16bit_golden(cuda_device, name, precision):
         assert lsd_db(refv, voc) <= (0.05 if name != "gen_c1_adaptive_euler" else 0.10)
 
 
+def test_engine_rejects_non_contiguous_inputs(cuda_device):
+    eng, sd, vcfg, g = engine("gen_basic_midpoint", "fp32")
+    mel = torch.from_numpy(g["ref_cond_mel"]).cuda()  # Fortran-ordered in the fixture -> non-contiguous on device
+    if not mel.is_contiguous():
+        with pytest.raises(ValueError):
+            eng.vocoder(mel)
+    with pytest.raises(ValueError):
+        eng.encode(torch.zeros(2, 4800, device="cuda:0")[:, ::2])
+
+
 def test_no_cpu_fallback_and_launch_counter(cuda_device):
     from flowhigh_b200 import _lib
     eng, *_ = engine("gen_basic_midpoint", "fp32")
@@ -376,8 +386,8 @@ def test_generate_long_chunked_matches_oracle_per_chunk(cuda_device):
 # ------------------------------------------------------------------ CFG, mel_pp, independent_cfm_mix
 def test_mel_cutoff_and_splice(cuda_device):
     eng, sd, vcfg, g = engine("gen_basic_midpoint", "fp32")
-    mel = torch.from_numpy(g["ref_cond_mel"])
-    mel2 = torch.cat([mel, mel.flip(-1) * 0.5 - 3.0])
+    mel = torch.from_numpy(np.ascontiguousarray(g["ref_cond_mel"]))
+    mel2 = torch.cat([mel, mel.flip(-1) * 0.5 - 3.0]).contiguous()
     cut = eng.mel_cutoff_bins(mel2.cuda()).cpu().tolist()
     ref = [model.mel_cutoff_bin(mel2[i]) for i in range(2)]
     assert cut == ref, (cut, ref)
@@ -391,7 +401,8 @@ def test_mel_cutoff_and_splice(cuda_device):
 def test_sample_variants_f32(cuda_device, variant):
     g = load_golden("gen_basic_euler4")
     sd, vcfg = golden_weights(g)
-    cond_mel, eps = torch.from_numpy(g["ref_cond_mel"]), torch.from_numpy(g["eps"])
+    cond_mel = torch.from_numpy(np.ascontiguousarray(g["ref_cond_mel"]))  # stored Fortran-ordered (a permuted view)
+    eps = torch.from_numpy(np.ascontiguousarray(g["eps"]))
     kw = dict(steps=2, ode_method="midpoint", cfm_method="basic_cfm", sigma=0.0)
     extra = {}
     if variant == "cfg":
