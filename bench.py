@@ -262,9 +262,17 @@ def main():
         tc_n = sum(v["launches"] for v in tc.values())
         tot_ms = sum(v["ms"] for v in breakdown.values())
         achieved = tc_fl / (tc_ms / 1000.0) / 1e12 if tc_ms > 0 else 0.0
+        traffic = None  # DRAM bytes per launch from the committed ncu capture of this same workload (B = 64)
+        tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic_b64.json")
+        if B == BATCH and os.path.exists(tpath):
+            tj = json.load(open(tpath))["tc_conv"]
+            traffic = (tj["dram_read_bytes"] + tj["dram_write_bytes"]) / tj["launches"]
+        tc_by = sum(v["bytes"] for v in tc.values())
         roofline = {"kernel": "tc_conv_kernel (tcgen05 implicit-GEMM conv, all launches of one step)", "bound": "tensor",
                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
-                    "traffic": None, "peak_source": peak_src, "launches_per_step": tc_n,
+                    "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, B=64 capture)",
+                    "algorithmic_bytes_per_launch": tc_by / max(tc_n, 1),
+                    "peak_source": peak_src, "launches_per_step": tc_n,
                     "avg_launch_ms": tc_ms / max(tc_n, 1), "share_of_step": tc_ms / tot_ms if tot_ms else None,
                     "algorithmic_flops_per_step": tc_fl}
         groups = {}
