@@ -1,0 +1,258 @@
+// Tensor-core attention for the 16-bit path: softmax(10 * q k^T) v, no mask (attend.py:123-137), head dim 64.
+//
+// The logits reach +-640 (|q^| = |k^| = 8, scale 10; attend.py:147-160), so single-pass 16-bit operands are not
+// enough for q k^T (a 2^-11 operand rounding is a 0.05 logit error).  q (pre-scaled) and k are therefore
+// stored as hi + lo 16-bit pairs by the q/k-norm + rotary kernel and S = qh.kh + ql.kh + qh.kl runs as three
+// mma.sync.m16n8k16 passes with fp32 accumulation (error ~2^-21); P.V uses plain 16-bit operands (P in [0,1]).
+// Flash-style: one CTA = 64 queries x one (batch, head); 4 warps x 16 query rows; keys streamed in blocks of 64
+// through shared memory (rows padded to 72 halves: conflict-free 32-bit fragment loads; V is stored
+// transposed so the P.V B-fragments are also plain 32-bit loads); online softmax on the C fragments; the
+// S -> P register re-use of the m16n8k16 layouts avoids any shared-memory round trip for P.
+#include "common.cuh"
+
+namespace {
+
+constexpr int AD = 64, ABQ = 64, ABK = 64, APAD = 72;
+
+template <bool FP16>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  if (FP16)
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  else
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <bool FP16>
+__global__ void __launch_bounds__(128) attention_tc_kernel(const unsigned short* __restrict__ qh,
+                                                           const unsigned short* __restrict__ ql,
+                                                           const unsigned short* __restrict__ kh,
+                                                           const unsigned short* __restrict__ kl,
+                                                           const unsigned short* __restrict__ v16, void* __restrict__ out,
+                                                           int out_mode, long long out_rows, int H, int N) {
+  __shared__ __align__(16) unsigned short Kh[ABK][APAD];
+  __shared__ __align__(16) unsigned short Kl[ABK][APAD];
+  __shared__ __align__(16) unsigned short Vt[AD][APAD];  // [d][key]
+  const int bh = blockIdx.y, q0 = blockIdx.x * ABQ;
+  const int bi = bh / H, h = bh % H;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t base = (size_t)bh * N * AD;
+  // ---- Q fragments (hi, lo) for this warp's 16 rows
+  uint32_t Qh[4][4], Ql[4][4];
+  {
+    const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int d0 = kk * 16 + 2 * t;
+      Qh[kk][0] = r0 < N ? *reinterpret_cast<const uint32_t*>(qh + base + (size_t)r0 * AD + d0) : 0u;
+      Qh[kk][1] = r1 < N ? *reinterpret_cast<const uint32_t*>(qh + base + (size_t)r1 * AD + d0) : 0u;
+      Qh[kk][2] = r0 < N ? *reinterpret_cast<const uint32_t*>(qh + base + (size_t)r0 * AD + d0 + 8) : 0u;
+      Qh[kk][3] = r1 < N ? *reinterpret_cast<const uint32_t*>(qh + base + (size_t)r1 * AD + d0 + 8) : 0u;
+      Ql[kk][0] = r0 < N ? *reinterpret_cast<const uint32_t*>(ql + base + (size_t)r0 * AD + d0) : 0u;
+      Ql[kk][1] = r1 < N ? *reinterpret_cast<const uint32_t*>(ql + base + (size_t)r1 * AD + d0) : 0u;
+      Ql[kk][2] = r0 < N ? *reinterpret_cast<const uint32_t*>(ql + base + (size_t)r0 * AD + d0 + 8) : 0u;
+      Ql[kk][3] = r1 < N ? *reinterpret_cast<const uint32_t*>(ql + base + (size_t)r1 * AD + d0 + 8) : 0u;
+    }
+  }
+  float O[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) O[i][j] = 0.f;
+  float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
+
+  for (int k0 = 0; k0 < N; k0 += ABK) {
+    __syncthreads();
+    // ---- cooperative load of the key block: 64 rows x 8 chunks of 16 B for Kh, Kl, V
+    for (int i = threadIdx.x; i < ABK * 8; i += 128) {
+      const int r = i >> 3, c = i & 7;
+      const bool ok = k0 + r < N;
+      const size_t off = base + (size_t)(k0 + r) * AD + c * 8;
+      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+      const uint4 a = ok ? *reinterpret_cast<const uint4*>(kh + off) : z;
+      const uint4 b = ok ? *reinterpret_cast<const uint4*>(kl + off) : z;
+      *reinterpret_cast<uint4*>(&Kh[r][c * 8]) = a;
+      *reinterpret_cast<uint4*>(&Kl[r][c * 8]) = b;
+    }
+    // V is stored transposed ([d][key]); lanes walk along keys so the 2-byte stores are conflict-free
+    for (int i = threadIdx.x; i < ABK * 8; i += 128) {
+      const int r = i & 63, c = i >> 6;
+      const uint4 vv = (k0 + r < N) ? *reinterpret_cast<const uint4*>(v16 + base + (size_t)(k0 + r) * AD + c * 8)
+                                    : make_uint4(0u, 0u, 0u, 0u);
+      const unsigned short* vs = reinterpret_cast<const unsigned short*>(&vv);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) Vt[c * 8 + e][r] = vs[e];
+    }
+    __syncthreads();
+    // ---- S = Qh Kh^T + Ql Kh^T + Qh Kl^T
+    float S[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) S[i][j] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Kh[nt * 8 + g][kk * 16 + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Kh[nt * 8 + g][kk * 16 + 8 + 2 * t]);
+        mma16816<FP16>(S[nt], Qh[kk], b0, b1);
+        mma16816<FP16>(S[nt], Ql[kk], b0, b1);
+        const uint32_t l0 = *reinterpret_cast<const uint32_t*>(&Kl[nt * 8 + g][kk * 16 + 2 * t]);
+        const uint32_t l1 = *reinterpret_cast<const uint32_t*>(&Kl[nt * 8 + g][kk * 16 + 8 + 2 * t]);
+        mma16816<FP16>(S[nt], Qh[kk], l0, l1);
+      }
+    }
+    // ---- online softmax (rows g and g+8 of this warp's tile)
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = k0 + nt * 8 + 2 * t;
+      if (key >= N) S[nt][0] = -INFINITY, S[nt][2] = -INFINITY;
+      if (key + 1 >= N) S[nt][1] = -INFINITY, S[nt][3] = -INFINITY;
+      mx[0] = fmaxf(mx[0], fmaxf(S[nt][0], S[nt][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(S[nt][2], S[nt][3]));
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+    }
+    float corr[2], mnew[2], psum[2] = {0.f, 0.f};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mnew[r] = fmaxf(mrow[r], mx[r]);
+      corr[r] = __expf(mrow[r] - mnew[r]);
+      mrow[r] = mnew[r];
+    }
+    uint32_t P[8][2];  // [n-tile][row half] packed pairs
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float p0 = __expf(S[nt][0] - mnew[0]), p1 = __expf(S[nt][1] - mnew[0]);
+      const float p2 = __expf(S[nt][2] - mnew[1]), p3 = __expf(S[nt][3] - mnew[1]);
+      psum[0] += p0 + p1;
+      psum[1] += p2 + p3;
+      P[nt][0] = fh::pack16(p0, p1, FP16 ? 1 : 0);
+      P[nt][1] = fh::pack16(p2, p3, FP16 ? 1 : 0);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      psum[r] += __shfl_xor_sync(0xffffffffu, psum[r], 1);
+      psum[r] += __shfl_xor_sync(0xffffffffu, psum[r], 2);
+      lrow[r] = lrow[r] * corr[r] + psum[r];
+    }
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      O[nd][0] *= corr[0];
+      O[nd][1] *= corr[0];
+      O[nd][2] *= corr[1];
+      O[nd][3] *= corr[1];
+    }
+    // ---- O += P V   (A fragment of 16 keys = C fragments of two adjacent 8-key n-tiles)
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+      const uint32_t a[4] = {P[2 * kt][0], P[2 * kt][1], P[2 * kt + 1][0], P[2 * kt + 1][1]};
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Vt[nd * 8 + g][kt * 16 + 2 * t]);
+        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Vt[nd * 8 + g][kt * 16 + 8 + 2 * t]);
+        mma16816<FP16>(O[nd], a, b0, b1);
+      }
+    }
+  }
+  // ---- normalise and store
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int qi = q0 + warp * 16 + g + 8 * r;
+    if (qi >= N) continue;
+    const float inv = 1.0f / lrow[r];
+    const long long row = (long long)bi * N + qi;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+      const int c = h * AD + nd * 8 + 2 * t;
+      const float x0 = O[nd][2 * r] * inv, x1 = O[nd][2 * r + 1] * inv;
+      if (out_mode == 0)
+        *reinterpret_cast<float2*>((float*)out + row * (H * AD) + c) = make_float2(x0, x1);
+      else
+        *reinterpret_cast<uint32_t*>((unsigned short*)out + fh::chunked_index(out_rows * 8, row, c)) =
+            fh::pack16(x0, x1, out_mode == 2);
+    }
+  }
+}
+
+// q/k-norm + rotary (attend.py:144-151,179-184; pos_emb.py:45-60) emitting 16-bit hi/lo splits:
+// qh + ql = scale * rope(qhat), kh + kl = rope(khat), v16 = v.   One warp per (token, head), D = 64.
+__global__ void qknorm_rope_split_kernel(const float* __restrict__ qkv, const float* __restrict__ qg,
+                                         const float* __restrict__ kg, const float* __restrict__ inv_freq,
+                                         unsigned short* __restrict__ qh, unsigned short* __restrict__ ql,
+                                         unsigned short* __restrict__ kh, unsigned short* __restrict__ kl,
+                                         unsigned short* __restrict__ v16, int B, int N, int H, float scale, int fp16) {
+  constexpr int D = 64;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gw >= B * N * H) return;
+  const int h = gw % H, tok = gw / H, n = tok % N, bi = tok / N;
+  const float* src = qkv + (size_t)tok * 3 * H * D + h * D;
+  const size_t dst = (((size_t)bi * H + h) * N + n) * D;
+  const float fr = (float)n * inv_freq[lane];
+  const float cs = cosf(fr), sn = sinf(fr);
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    const float* s = src + which * H * D;
+    const float* gm = (which == 0 ? qg : kg) + h * D;
+    float x1 = s[lane], x2 = s[lane + 32];
+    const float ss = fh::warp_sum(x1 * x1 + x2 * x2);
+    const float inv = 8.0f / fmaxf(sqrtf(ss), 1e-12f);
+    x1 = x1 * inv * gm[lane];
+    x2 = x2 * inv * gm[lane + 32];
+    float y1 = x1 * cs - x2 * sn, y2 = x2 * cs + x1 * sn;
+    if (which == 0) y1 *= scale, y2 *= scale;
+    unsigned short* oh = (which == 0 ? qh : kh) + dst;
+    unsigned short* ol = (which == 0 ? ql : kl) + dst;
+    const unsigned short h1 = fh::cvt16(y1, fp16), h2 = fh::cvt16(y2, fp16);
+    const float f1 = fp16 ? __half2float(*reinterpret_cast<const __half*>(&h1)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h1));
+    const float f2 = fp16 ? __half2float(*reinterpret_cast<const __half*>(&h2)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h2));
+    oh[lane] = h1;
+    oh[lane + 32] = h2;
+    ol[lane] = fh::cvt16(y1 - f1, fp16);
+    ol[lane + 32] = fh::cvt16(y2 - f2, fp16);
+  }
+  const float* s = src + 2 * H * D;
+  v16[dst + lane] = fh::cvt16(s[lane], fp16);
+  v16[dst + lane + 32] = fh::cvt16(s[lane + 32], fp16);
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int fh_qknorm_rope_split(
+    const float* qkv, const float* qg, const float* kg, const float* inv_freq, void* qh, void* ql, void* kh, void* kl,
+    void* v16, int B, int N, int H, int D, float scale, int fp16, void* stream) {
+  FH_REQUIRE(D == 64, FH_ERR_UNSUPPORTED_CFG, "fh_qknorm_rope_split: dim_head must be 64 (got %d)", D);
+  const int64_t warps = (int64_t)B * N * H;
+  qknorm_rope_split_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      qkv, qg, kg, inv_freq, (unsigned short*)qh, (unsigned short*)ql, (unsigned short*)kh, (unsigned short*)kl,
+      (unsigned short*)v16, B, N, H, scale, fp16);
+  return fh::check_launch("fh_qknorm_rope_split");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_attention_tc(const void* qh, const void* ql, const void* kh,
+                                                                     const void* kl, const void* v16, void* out,
+                                                                     int out_mode, int64_t out_rows, int B, int H, int N,
+                                                                     int D, int fp16, void* stream) {
+  FH_REQUIRE(D == 64, FH_ERR_UNSUPPORTED_CFG, "fh_attention_tc: dim_head must be 64 (got %d)", D);
+  FH_REQUIRE(B * H <= 65535 && N > 0, FH_ERR_BAD_SHAPE, "fh_attention_tc: B*H must be <= 65535");
+  dim3 grid((N + ABQ - 1) / ABQ, B * H);
+  if (fp16)
+    attention_tc_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(
+        (const unsigned short*)qh, (const unsigned short*)ql, (const unsigned short*)kh, (const unsigned short*)kl,
+        (const unsigned short*)v16, out, out_mode, out_rows, H, N);
+  else
+    attention_tc_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+        (const unsigned short*)qh, (const unsigned short*)ql, (const unsigned short*)kh, (const unsigned short*)kl,
+        (const unsigned short*)v16, out, out_mode, out_rows, H, N);
+  return fh::check_launch("fh_attention_tc");
+}

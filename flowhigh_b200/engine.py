@@ -62,6 +62,7 @@ class Engine:
         self.profile = None
         import os as _os
         self.voc_streams = int(_os.environ.get("FH_VOC_STREAMS", "1"))
+        self.tc_attention = _os.environ.get("FH_TC_ATTENTION", "1") != "0"  # mma.sync split-operand attention
         self._side_streams = []
         self._time_cache: Dict[float, dict] = {}
         dev = self.device
@@ -373,12 +374,21 @@ class Engine:
                 self._call("fh_rmsnorm_f32", h.data_ptr(), tcnd[(l, 2, "gamma")].data_ptr(), tcnd[(l, 2, "beta")].data_ptr(),
                            a.data_ptr(), 0, 0, M, D, st)
                 self._sgemm(a, D, sd[p + "3.to_qkv.weight"], D, None, None, 0, 0.0, 1.0, qkv, 3 * D, M, 3 * D, D)
-            self._call("fh_qknorm_rope_f32", qkv.data_ptr(), sd[p + "3.q_norm.gamma"].data_ptr(),
-                       sd[p + "3.k_norm.gamma"].data_ptr(), sd[FH + "transformer.rotary_emb.inv_freq"].data_ptr(),
-                       q.data_ptr(), k.data_ptr(), v.data_ptr(), B, N, H, Dh, st)
+            if self.tc and self.tc_attention:
+                s16 = [self.buf(f"bb_{nm}16", (B, H, N, Dh), self.h16, zero=False) for nm in ("qh", "ql", "kh", "kl", "v")]
+                self._call("fh_qknorm_rope_split", qkv.data_ptr(), sd[p + "3.q_norm.gamma"].data_ptr(),
+                           sd[p + "3.k_norm.gamma"].data_ptr(), sd[FH + "transformer.rotary_emb.inv_freq"].data_ptr(),
+                           *[t_.data_ptr() for t_ in s16], B, N, H, Dh, float(b.qk_norm_scale), self.fp16, st)
+                self._call("fh_attention_tc", *[t_.data_ptr() for t_ in s16], act.data_ptr(), self.k16, Mp, B, H, N, Dh,
+                           self.fp16, st)
+            else:
+                self._call("fh_qknorm_rope_f32", qkv.data_ptr(), sd[p + "3.q_norm.gamma"].data_ptr(),
+                           sd[p + "3.k_norm.gamma"].data_ptr(), sd[FH + "transformer.rotary_emb.inv_freq"].data_ptr(),
+                           q.data_ptr(), k.data_ptr(), v.data_ptr(), B, N, H, Dh, st)
+                if self.tc:
+                    self._call("fh_attention_f32", q.data_ptr(), k.data_ptr(), v.data_ptr(), act.data_ptr(), self.k16, Mp, B, H,
+                               N, Dh, float(b.qk_norm_scale), st)
             if self.tc:
-                self._call("fh_attention_f32", q.data_ptr(), k.data_ptr(), v.data_ptr(), act.data_ptr(), self.k16, Mp, B, H, N, Dh,
-                           float(b.qk_norm_scale), st)
                 self._tc_conv(L[f"out{l}"], act, 0, cs, 0, h, rm(D), 0, 1, M, res=h, res_strides=rm(D), beta=1.0)
                 self._call("fh_rmsnorm_f32", h.data_ptr(), tcnd[(l, 4, "gamma")].data_ptr(), tcnd[(l, 4, "beta")].data_ptr(),
                            act.data_ptr(), self.k16, Mp, M, D, st)

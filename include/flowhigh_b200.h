@@ -112,6 +112,14 @@ int fh_qknorm_rope_f32(const float* qkv, const float* qg, const float* kg, const
  * out_mode as in fh_rmsnorm_f32. */
 int fh_attention_f32(const float* q, const float* k, const float* v, void* out, int out_mode,
                      int64_t out_rows, int B, int H, int N, int D, float scale, void* stream);
+/* 16-bit tensor path of the two calls above.  fh_qknorm_rope_split writes q (pre-multiplied by `scale`) and
+ * k as hi + lo 16-bit pairs and v as 16-bit, all [B,H,N,D]; fh_attention_tc computes
+ * softmax(qh.kh + ql.kh + qh.kl) v with mma.sync tensor-core tiles (logits reach +-640, see attention_tc.cu). */
+int fh_qknorm_rope_split(const float* qkv, const float* qg, const float* kg, const float* inv_freq,
+                         void* qh, void* ql, void* kh, void* kl, void* v16,
+                         int B, int N, int H, int D, float scale, int fp16, void* stream);
+int fh_attention_tc(const void* qh, const void* ql, const void* kh, const void* kl, const void* v16, void* out,
+                    int out_mode, int64_t out_rows, int B, int H, int N, int D, int fp16, void* stream);
 /* g[M,inner] = gelu(u[M, inner + i]) * u[M, i]    transformer.py:92-95 */
 int fh_geglu_f32(const float* u, void* g, int out_mode, int64_t out_rows, int M, int inner, int inner_pad,
                  void* stream);

@@ -420,3 +420,33 @@ def test_sample_variants_f32(cuda_device, variant):
     err = float((out - ref64).abs().max())
     print(f"sample[{variant}] fp32: max-abs vs fp64 {err:.3g} (oracle fp32's own {floor:.3g})")
     assert err <= 3 * floor + 1e-4
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("N", [51, 128, 333])
+def test_attention_tc_matches_fp32_attention(cuda_device, precision, N):
+    """mma.sync split-operand attention against the fp32 CUDA-core attention on the same q/k/v."""
+    eng, sd, vcfg, g = engine("gen_basic_midpoint", precision)
+    torch.manual_seed(N)
+    B, H, D = 2, 16, 64
+    qkv = torch.randn(B * N, 3 * H * D, device="cuda:0")
+    qg = (1 + 0.1 * torch.randn(H, 1, D, device="cuda:0")).contiguous()
+    kg = (1 + 0.1 * torch.randn(H, 1, D, device="cuda:0")).contiguous()
+    inv_freq = eng.sd["flowhigh.transformer.rotary_emb.inv_freq"]
+    q, k, v = (torch.empty(B, H, N, D, device="cuda:0") for _ in range(3))
+    ref = torch.empty(B * N, H * D, device="cuda:0")
+    eng._call("fh_qknorm_rope_f32", qkv.data_ptr(), qg.data_ptr(), kg.data_ptr(), inv_freq.data_ptr(), q.data_ptr(),
+              k.data_ptr(), v.data_ptr(), B, N, H, D, eng.stream)
+    eng._call("fh_attention_f32", q.data_ptr(), k.data_ptr(), v.data_ptr(), ref.data_ptr(), 0, 0, B, H, N, D, 10.0, eng.stream)
+    s16 = [torch.empty(B, H, N, D, device="cuda:0", dtype=eng.h16) for _ in range(5)]
+    out = torch.empty(B * N, H * D, device="cuda:0")
+    eng._call("fh_qknorm_rope_split", qkv.data_ptr(), qg.data_ptr(), kg.data_ptr(), inv_freq.data_ptr(),
+              *[t.data_ptr() for t in s16], B, N, H, D, 10.0, eng.fp16, eng.stream)
+    eng._call("fh_attention_tc", *[t.data_ptr() for t in s16], out.data_ptr(), 0, 0, B, H, N, D, eng.fp16, eng.stream)
+    torch.cuda.synchronize()
+    # the split reproduces q, k to ~2^-21 (fp16) / 2^-16 (bf16): logits agree to 1e-3; the remaining error is the
+    # 16-bit rounding of P and V in the P.V product
+    err = float((out - ref).abs().max())
+    rel = float((out - ref).norm() / ref.norm())
+    print(f"attention_tc {precision} N={N}: max-abs {err:.3g}, rel-L2 {rel:.3g}")
+    assert rel <= (2e-3 if precision == "fp16" else 1e-2)
