@@ -569,12 +569,21 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
   FH_REQUIRE(span <= kMaxSpan, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: tap span %d exceeds %d rows", span, kMaxSpan);
   p.wrows = 128 * msub + span;
   p.arows_pad = 128 * msub + kMaxSpan;
-  // taps per stage: keep a B slot <= 32 KB
-  int tg = 32768 / (a->bn * 32);
+  // taps per stage: a weight slot of <= 32 KB (<= 48 KB for narrow tiles, so that all taps of a ci-pair share
+  // one activation window fetch), with the taps spread evenly over the groups (11 taps -> 6+5, not 10+1)
+  static int slot_small_kb = 0, slot_wide_kb = 0;
+  if (!slot_small_kb) {
+    const char* e1 = getenv("FH_TC_SLOT_SMALL_KB");
+    const char* e2 = getenv("FH_TC_SLOT_WIDE_KB");
+    slot_small_kb = e1 ? atoi(e1) : 48;
+    slot_wide_kb = e2 ? atoi(e2) : 32;
+  }
+  int tg = ((a->bn <= 128 ? slot_small_kb : slot_wide_kb) * 1024) / (a->bn * 32);
   if (tg < 1) tg = 1;
   if (tg > a->ntaps) tg = a->ntaps;
-  p.tg = tg;
   p.n_groups = (a->ntaps + tg - 1) / tg;
+  tg = (a->ntaps + p.n_groups - 1) / p.n_groups;
+  p.tg = tg;
   p.stage_bytes = 2 * p.arows_pad * 16 + tg * a->bn * 32;
   p.stage_bytes = (p.stage_bytes + 127) & ~127;
   static int budget_kb = 0;
