@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit tensor-core operand format (same rate and bytes; fp16 meets the LSD bar, see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--breakdown", default=None, help="write the per-kernel CUDA-event breakdown to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -244,6 +245,35 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, e2e_s = float(t[0]), float(t[1])
 
+    # ---- latency leg (BASELINE metric, second half): p50 of one 10 s clip and of 1 s streaming chunks, B = 1,
+    #      through the public generate() call from a host array to a synchronised device result
+    latency = None
+    if rank == 0 and not args.no_latency:
+        def p50_p99(fn, n):
+            ts = []
+            for _ in range(n):
+                t0 = time.perf_counter()
+                fn()
+                torch.cuda.synchronize(dev)
+                ts.append(1000 * (time.perf_counter() - t0))
+            ts.sort()
+            return ts[len(ts) // 2], ts[min(len(ts) - 1, int(0.99 * len(ts)))]
+        clip = host[0]
+        for _ in range(3):
+            model.generate(clip, SR_IN, 48000, timestep=STEPS_ODE)
+        l50, l99 = p50_p99(lambda: model.generate(clip, SR_IN, 48000, timestep=STEPS_ODE), 30)
+        # config 5: basic_cfm, euler, time_step 4, 1 s chunks at 16 kHz
+        m5 = FlowHighSR.from_random(VocoderConfig.assumed_48k(), device=dev, seed=0, precision=args.precision,
+                                    torchdiffeq_ode_method="euler")
+        chunk = synth_speech(16000, 16000, seed=7)
+        for _ in range(3):
+            m5.generate(chunk, 16000, 48000, timestep=4)
+        c50, c99 = p50_p99(lambda: m5.generate(chunk, 16000, 48000, timestep=4), 50)
+        latency = {"clip_10s_midpoint_p50_ms": l50, "clip_10s_midpoint_p99_ms": l99,
+                   "chunk_1s_euler4_p50_ms": c50, "chunk_1s_euler4_p99_ms": c99,
+                   "note": "B=1, host numpy in -> device tensor out, stream-synchronised, no CUDA graph"}
+        del m5
+
     # ---- roofline leg: per-kernel CUDA-event timing of one more step (rank 0)
     breakdown = None
     if rank == 0:
@@ -303,6 +333,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_t.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "latency": latency,
             "stage_ms": {k: round(v["ms"], 3) for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])},
         }
         print(json.dumps(line), flush=True)

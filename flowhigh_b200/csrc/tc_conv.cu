@@ -576,7 +576,7 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
     const char* e1 = getenv("FH_TC_SLOT_SMALL_KB");
     const char* e2 = getenv("FH_TC_SLOT_WIDE_KB");
     slot_small_kb = e1 ? atoi(e1) : 48;
-    slot_wide_kb = e2 ? atoi(e2) : 32;
+    slot_wide_kb = e2 ? atoi(e2) : 48;
   }
   int tg = ((a->bn <= 128 ? slot_small_kb : slot_wide_kb) * 1024) / (a->bn * 32);
   if (tg < 1) tg = 1;
