@@ -155,6 +155,9 @@ class FlowHighSR(nn.Module):
         self.odeint_kwargs = dict(atol=ode_atol, rtol=ode_rtol, method=torchdiffeq_ode_method)
         self.upsampling_method = upsampling_method
         self.precision = precision
+        self.cuda_graphs = True          # capture small-batch generate() pipelines into CUDA graphs
+        self.cuda_graph_max_batch = 8
+        self._graphs: Dict[tuple, tuple] = {}
         self._eng: Optional[Engine] = None
         import weakref
         ref = weakref.ref(self)
@@ -180,10 +183,12 @@ class FlowHighSR(nn.Module):
 
     def _apply(self, fn, *a, **k):
         self._eng = None
+        self._graphs = {}
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
         self._eng = None
+        self._graphs = {}
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def load(self, path, strict=True):
@@ -205,6 +210,7 @@ class FlowHighSR(nn.Module):
     def set_precision(self, precision: str):
         self.precision = precision
         self._eng = None
+        self._graphs = {}
 
     # ------------------------------------------------------------------ reference API
     def set_cfm_method(self, cfm_method):
@@ -267,18 +273,55 @@ class FlowHighSR(nn.Module):
             host = torch.from_numpy(np.stack([prepped[i] for i in idxs]))
             if pinned:
                 host = host.pin_memory()
-            x = host.to(eng.device, non_blocking=True)
-            cond = eng.resample_normalise(x, s, target_sampling_rate)
-            cond_mel = eng.encode(cond)
-            e = None if eps is None else torch.cat([eps[i].reshape(1, *cond_mel.shape[1:]) for i in idxs]).to(eng.device)
-            mel = eng.sample_mel(cond_mel, self._noise_like(cond_mel, e), steps=int(timestep),
-                                 ode_method=self.odeint_kwargs["method"], cfm_method=self.cfm_method,
-                                 sigma=float(self.sigma))
-            wave = eng.vocoder(mel)
-            out = eng.postprocess(wave, cond)
+            e = None if eps is None else torch.cat([eps[i].reshape(1, -1, 256) for i in idxs])
+            if self.cuda_graphs and len(idxs) <= self.cuda_graph_max_batch:
+                out = self._run_group_graphed(eng, host, s, int(target_sampling_rate), int(timestep), e)
+            else:
+                x = host.to(eng.device, non_blocking=True)
+                out = self._run_group(eng, x, s, int(target_sampling_rate), int(timestep),
+                                      None if e is None else e.to(eng.device))
             for j, i in enumerate(idxs):
                 results[i] = out[j: j + 1]
         return results  # type: ignore[return-value]
+
+    def _run_group(self, eng, x, sr, target_sr, timestep, eps_dev):
+        """resample -> log-mel -> CFM -> vocoder -> post-processing for one batch of equal-length clips."""
+        cond = eng.resample_normalise(x, sr, target_sr)
+        cond_mel = eng.encode(cond)
+        mel = eng.sample_mel(cond_mel, self._noise_like(cond_mel, eps_dev), steps=timestep,
+                             ode_method=self.odeint_kwargs["method"], cfm_method=self.cfm_method, sigma=float(self.sigma))
+        return eng.postprocess(eng.vocoder(mel), cond)
+
+    def _run_group_graphed(self, eng, host, sr, target_sr, timestep, eps_host):
+        """Small batches are launch-bound (~300 kernel launches per clip): the whole per-shape pipeline is captured
+        once into a CUDA graph (static input / noise / output buffers) and replayed."""
+        B, n = host.shape
+        key = (B, n, sr, target_sr, timestep, self.odeint_kwargs["method"], self.cfm_method, float(self.sigma))
+        ent = self._graphs.get(key)
+        if ent is None:
+            x_static = torch.zeros((B, n), dtype=torch.float32, device=eng.device)
+            x_static.copy_(host)
+            T = -(-n * (target_sr // np.gcd(target_sr, sr)) // (sr // np.gcd(target_sr, sr)))
+            eps_static = torch.randn((B, T // 480, 256), dtype=torch.float32, device=eng.device)
+            side = torch.cuda.Stream(eng.device)
+            side.wait_stream(torch.cuda.current_stream(eng.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):  # allocate persistent buffers, time-conditioning cache, function attributes
+                    self._run_group(eng, x_static, sr, target_sr, timestep, eps_static)
+            torch.cuda.current_stream(eng.device).wait_stream(side)
+            torch.cuda.synchronize(eng.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out_static = self._run_group(eng, x_static, sr, target_sr, timestep, eps_static)
+            ent = self._graphs[key] = (graph, x_static, eps_static, out_static)
+        graph, x_static, eps_static, out_static = ent
+        x_static.copy_(host, non_blocking=True)
+        if eps_host is not None:
+            eps_static.copy_(eps_host.reshape(eps_static.shape), non_blocking=True)
+        else:
+            eps_static.normal_()
+        graph.replay()
+        return out_static.clone()
 
     @torch.no_grad()
     def generate_long(self, audio, sr: int, target_sampling_rate=48000, timestep=1, chunk_seconds: float = 10.0,

@@ -450,3 +450,24 @@ def test_attention_tc_matches_fp32_attention(cuda_device, precision, N):
     rel = float((out - ref).norm() / ref.norm())
     print(f"attention_tc {precision} N={N}: max-abs {err:.3g}, rel-L2 {rel:.3g}")
     assert rel <= (2e-3 if precision == "fp16" else 1e-2)
+
+
+def test_cuda_graph_generate_matches_eager(cuda_device):
+    g = load_golden("gen_basic_midpoint")
+    sd, vcfg = golden_weights(g)
+    m = FlowHighSR.from_random(vcfg, device="cuda:0", precision="fp16")
+    m.load_state_dict(sd)
+    m = m.cuda()
+    eps = torch.from_numpy(g["eps"])
+    wav, sr = g["wav"], int(g["sr"])
+    m.cuda_graphs = False
+    ref = m.generate(wav, sr, 48000, timestep=1, eps=eps).cpu()
+    m.cuda_graphs = True
+    a = m.generate(wav, sr, 48000, timestep=1, eps=eps).cpu()       # capture + first replay
+    b = m.generate(wav * 0.5, sr, 48000, timestep=1, eps=eps).cpu()  # replay with new input (peak-normalised -> same result)
+    c = m.generate(wav, sr, 48000, timestep=1, eps=eps).cpu()
+    assert len(m._graphs) == 1
+    assert torch.equal(a, ref) and torch.equal(c, ref)
+    assert float((b - ref).abs().max()) <= 1e-3
+    d = m.generate(wav[: len(wav) // 2], sr, 48000, timestep=1)       # new shape -> second graph, random noise
+    assert len(m._graphs) == 2 and torch.isfinite(d).all()
