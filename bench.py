@@ -271,7 +271,7 @@ def main():
         c50, c99 = p50_p99(lambda: m5.generate(chunk, 16000, 48000, timestep=4), 50)
         latency = {"clip_10s_midpoint_p50_ms": l50, "clip_10s_midpoint_p99_ms": l99,
                    "chunk_1s_euler4_p50_ms": c50, "chunk_1s_euler4_p99_ms": c99,
-                   "note": "B=1, host numpy in -> device tensor out, stream-synchronised, no CUDA graph"}
+                   "note": "B=1, host numpy in -> device tensor out, stream-synchronised, CUDA-graph replay of the whole pipeline"}
         del m5
 
     # ---- roofline leg: per-kernel CUDA-event timing of one more step (rank 0)

@@ -471,3 +471,66 @@ def test_cuda_graph_generate_matches_eager(cuda_device):
     assert float((b - ref).abs().max()) <= 1e-3
     d = m.generate(wav[: len(wav) // 2], sr, 48000, timestep=1)       # new shape -> second graph, random noise
     assert len(m._graphs) == 2 and torch.isfinite(d).all()
+
+
+# ------------------------------------------------------------------ edge cases of generate()
+@pytest.fixture(scope="module")
+def f32_model():
+    g = load_golden("gen_basic_midpoint")
+    sd, vcfg = golden_weights(g)
+    m = FlowHighSR.from_random(vcfg, device="cuda:0", precision="fp32")
+    m.load_state_dict(sd)
+    return m.cuda(), pipeline.OracleFlowHigh(sd, vcfg, cfm_method="basic_cfm", ode_method="midpoint")
+
+
+def _eps_for(n_in, sr, seed=0):
+    T = -(-n_in * (48000 // np.gcd(48000, sr)) // (sr // np.gcd(48000, sr)))
+    return torch.from_numpy(np.random.default_rng(seed).standard_normal((1, T // 480, 256)).astype(np.float32))
+
+
+@pytest.mark.parametrize("sr,n_in", [(16000, 5403), (22050, 7000), (48000, 9700), (8000, 2999), (24000, 393)])
+def test_generate_edge_lengths_and_rates(cuda_device, f32_model, sr, n_in):
+    """T % 480 != 0, non-integer ratio (320/147), no-op resampling (48 k in), and the shortest clip the
+    reflect pad allows (393 samples @ 24 k -> 786 @ 48 k)."""
+    m, o = f32_model
+    wav = synth_speech(n_in, sr, seed=n_in)
+    eps = _eps_for(n_in, sr)
+    out = m.generate(wav, sr, 48000, timestep=1, eps=eps).cpu()
+    ref = o.generate(wav, sr, eps, timestep=1)
+    assert out.shape == ref.shape
+    err = float((out - ref).abs().max())
+    print(f"generate edge sr={sr} n_in={n_in}: T={out.shape[-1]} max-abs vs oracle {err:.3g}")
+    assert err <= 1e-3
+
+
+def test_generate_int16_and_2d_input(cuda_device, f32_model):
+    m, o = f32_model
+    wav = (synth_speech(4000, 16000, seed=2) * 20000).astype(np.int16)[None]  # [1, T] int16: squeeze + /32768
+    eps = _eps_for(4000, 16000)
+    out = m.generate(wav, 16000, 48000, timestep=1, eps=eps).cpu()
+    ref = o.generate(wav, 16000, eps, timestep=1)
+    assert float((out - ref).abs().max()) <= 1e-3
+    out_t = m.generate(torch.from_numpy(wav.astype(np.float32) / 32768.0), 16000, 48000, timestep=1, eps=eps).cpu()
+    assert float((out_t - out).abs().max()) <= 1e-4  # torch.Tensor input, already in [-1, 1]
+
+
+def test_generate_batch_mixed_rates_equals_per_clip(cuda_device, f32_model):
+    """BASELINE config 3 in miniature: mixed 8/12/16/24 kHz clips in one call; every clip must come out as if
+    generated alone (per-clip normalisation, attention and cutoff)."""
+    m, o = f32_model
+    rates = [8000, 12000, 16000, 24000, 8000, 12000]
+    wavs = [synth_speech(r // 2, r, seed=i) * (0.3 + 0.1 * i) for i, r in enumerate(rates)]
+    eps = [_eps_for(len(w), r, seed=i) for i, (w, r) in enumerate(zip(wavs, rates))]
+    outs = m.generate_batch(wavs, rates, 48000, timestep=1, eps=eps)
+    for i, (w, r) in enumerate(zip(wavs, rates)):
+        single = m.generate(w, r, 48000, timestep=1, eps=eps[i])
+        assert outs[i].shape == single.shape == (1, 24000)
+        assert float((outs[i] - single).abs().max()) <= 2e-5
+    ref = o.generate(wavs[3], rates[3], eps[3], timestep=1)
+    assert float((outs[3].cpu() - ref).abs().max()) <= 1e-3
+
+
+def test_generate_rejects_too_short_clip(cuda_device, f32_model):
+    m, _ = f32_model
+    with pytest.raises(ValueError):
+        m.generate(np.zeros(100, np.float32) + 0.1, 16000, 48000)  # 300 samples @ 48 k < 785
