@@ -30,6 +30,7 @@ class TcConvArgs(C.Structure):
         ("tap_off", C.POINTER(_i)),
         ("bn", _i),
         ("fp16", _i),
+        ("x_f32", _p), ("sn_a", _p), ("sn_inv_b", _p), ("sn_filt", _p),
     ]
 
 

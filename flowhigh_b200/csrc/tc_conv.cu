@@ -51,6 +51,12 @@ struct TcParams {
   int min_off[16];
   int tap_off[kMaxTapOff];
   unsigned int* err_flag;
+  // fused anti-aliased snake A-producer (tc_conv_snake_kernel): raw fp32 activations + per-channel parameters
+  const float* xf;
+  const float* sn_a;
+  const float* sn_ib;
+  const float* sn_filt;
+  int xrows, x_stages, xs_bytes, rows_per_chunk;
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -195,6 +201,135 @@ __device__ __forceinline__ void load_res16(const TcParams& P, long long rbase, i
   }
 }
 
+// Epilogue role, shared by both kernels.  `gstep` warps share one TMEM lane group (a warp may only touch lanes
+// 32*(warp%4)..+31) and split the 16-column groups of a tile round-robin (`half` = index within the share).
+// Per warp the groups are software-pipelined: tcgen05.ld and the residual loads of the next group are in flight
+// while the current group is scaled, added and stored.
+__device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                              int lane_grp, int half, int gstep, int lane, int tile_rows,
+                                              uint32_t acc_cols) {
+  const int r = lane_grp * 32 + lane;
+  int as = 0, aphase = 0;
+  const int groups_per_sub = P.bn >> 4;
+  const int n_groups_total = P.msub * groups_per_sub;
+  const bool use_res = P.res != nullptr && !P.geglu;
+  for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    const TileCoord tc = decode_tile(P, tile);
+    const int n_base = tc.nt * P.bn;
+    const int t_base = tc.mt * tile_rows + r;
+    const long long res_b = (long long)tc.b * P.res_batch;
+    const long long out_b = (long long)tc.b * P.out_batch;
+    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)as * acc_cols;
+
+    auto group_coords = [&](int gi, int& sub, int& c0, int& t) {
+      sub = gi / groups_per_sub;
+      c0 = (gi - sub * groups_per_sub) << 4;
+      t = t_base + sub * 128;
+    };
+    auto fetch_res = [&](int gi, float (&rr)[16]) {
+      if (!use_res || gi >= n_groups_total) return;
+      int sub, c0, t;
+      group_coords(gi, sub, c0, t);
+      load_res16(P, res_b + ((long long)t * P.P + tc.p) * P.res_row, n_base + c0, t < P.L, rr);
+    };
+    auto issue_ld = [&](int gi, uint32_t (&v)[16]) {
+      if (gi >= n_groups_total) return;
+      int sub, c0, t;
+      group_coords(gi, sub, c0, t);
+      if (n_base + c0 < P.Cout) tmem_ld16(taddr + (uint32_t)(sub * P.bn + c0), v);  // warp-uniform
+    };
+    auto finish = [&](int gi, const uint32_t (&v)[16], const float (&rr)[16]) {
+      int sub, c0, t;
+      group_coords(gi, sub, c0, t);
+      if (n_base + c0 >= P.Cout || t >= P.L) return;
+      const long long orow = (long long)t * P.P + tc.p;
+      if (P.geglu) {
+        // columns (2i, 2i+1) = (x_i, gate_i) -> gelu(gate) * x ; 16 columns -> one 8-channel chunk
+        const int n_out = (n_base + c0) >> 1;
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int n = n_base + c0 + 2 * i;
+          float xv = __uint_as_float(v[2 * i]), gv = __uint_as_float(v[2 * i + 1]);
+          if (P.bias) {
+            xv += __ldg(P.bias + n);
+            gv += __ldg(P.bias + n + 1);
+          }
+          o[i] = gelu_f(gv) * xv;
+        }
+        const long long idx = out_b + (long long)(n_out >> 3) * P.out_chunk + orow * P.out_row;
+        if (P.out_is_16) {
+          uint32_t h[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
+          *reinterpret_cast<uint4*>((unsigned short*)P.out + idx) = *reinterpret_cast<uint4*>(h);
+        } else {
+          float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
+          dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+          dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        return;
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int n0 = n_base + c0 + hh * 8;
+        if (n0 >= P.Cout) break;
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float acc = __uint_as_float(v[hh * 8 + i]);
+          if (P.bias) acc += __ldg(P.bias + n0 + i);
+          o[i] = acc * P.alpha;
+          if (use_res) o[i] = fmaf(P.beta_res, rr[hh * 8 + i], o[i]);
+        }
+        const long long idx = out_b + (long long)(n0 >> 3) * P.out_chunk + orow * P.out_row;
+        if (P.out_is_16) {
+          uint32_t h[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
+          *reinterpret_cast<uint4*>((unsigned short*)P.out + idx) = *reinterpret_cast<uint4*>(h);
+        } else {
+          float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
+          if (P.accumulate) {
+            const float4 p0 = dst[0], p1 = dst[1];
+            o[0] += p0.x, o[1] += p0.y, o[2] += p0.z, o[3] += p0.w;
+            o[4] += p1.x, o[5] += p1.y, o[6] += p1.z, o[7] += p1.w;
+          }
+          dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+          dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    };
+
+    uint32_t va[16], vb[16];
+    float ra[16], rb[16];
+    fetch_res(half, ra);  // residual of the first group is requested BEFORE waiting for the accumulator
+    mbar_wait(tfull0 + 8 * as, aphase, P.err_flag, 4);
+    tc_fence_after();
+    issue_ld(half, va);
+    for (int gi = half; gi < n_groups_total; gi += 2 * gstep) {
+      tmem_ld_wait();
+      issue_ld(gi + gstep, vb);
+      fetch_res(gi + gstep, rb);
+      finish(gi, va, ra);
+      if (gi + gstep >= n_groups_total) break;
+      tmem_ld_wait();
+      issue_ld(gi + 2 * gstep, va);
+      fetch_res(gi + 2 * gstep, ra);
+      finish(gi + gstep, vb, rb);
+    }
+    // all TMEM reads of this warp are complete (wait::ld above) -> release the accumulator
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+    if (++as == P.acc_stages) {
+      as = 0;
+      aphase ^= 1;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // [0,256): barriers; [256,260): tmem base; stages from 1024
@@ -320,130 +455,274 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     }
   } else {
     // ===================================================================== epilogue (warps 2..9)
-    // Two warps per TMEM lane group (a warp may only touch lanes 32*(warp%4)..+31); the pair splits
-    // the 16-column groups of a tile even/odd.  Per warp the groups are software-pipelined:
-    // tcgen05.ld of group i+1 and the residual loads of group i+1 are in flight while group i is
-    // scaled, added and stored.
-    const int lane_grp = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int r = lane_grp * 32 + lane;
-    int as = 0, aphase = 0;
-    const int groups_per_sub = P.bn >> 4;
-    const int n_groups_total = P.msub * groups_per_sub;
-    const bool use_res = P.res != nullptr && !P.geglu;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(P, tile);
-      const int n_base = tc.nt * P.bn;
-      const int t_base = tc.mt * tile_rows + r;
-      const long long res_b = (long long)tc.b * P.res_batch;
-      const long long out_b = (long long)tc.b * P.out_batch;
-      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)as * acc_cols;
+    epilogue_role(P, tmem_base, tfull0, tempty0, warp & 3, (warp - 2) >> 2, 2, lane, tile_rows, acc_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
 
-      auto group_coords = [&](int gi, int& sub, int& c0, int& t) {
-        sub = gi / groups_per_sub;
-        c0 = (gi - sub * groups_per_sub) << 4;
-        t = t_base + sub * 128;
-      };
-      auto fetch_res = [&](int gi, float (&rr)[16]) {
-        if (!use_res || gi >= n_groups_total) return;
-        int sub, c0, t;
-        group_coords(gi, sub, c0, t);
-        load_res16(P, res_b + ((long long)t * P.P + tc.p) * P.res_row, n_base + c0, t < P.L, rr);
-      };
-      auto issue_ld = [&](int gi, uint32_t (&v)[16]) {
-        if (gi >= n_groups_total) return;
-        int sub, c0, t;
-        group_coords(gi, sub, c0, t);
-        if (n_base + c0 < P.Cout) tmem_ld16(taddr + (uint32_t)(sub * P.bn + c0), v);  // warp-uniform
-      };
-      auto finish = [&](int gi, const uint32_t (&v)[16], const float (&rr)[16]) {
-        int sub, c0, t;
-        group_coords(gi, sub, c0, t);
-        if (n_base + c0 >= P.Cout || t >= P.L) return;
-        const long long orow = (long long)t * P.P + tc.p;
-        if (P.geglu) {
-          // columns (2i, 2i+1) = (x_i, gate_i) -> gelu(gate) * x ; 16 columns -> one 8-channel chunk
-          const int n_out = (n_base + c0) >> 1;
-          float o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int n = n_base + c0 + 2 * i;
-            float xv = __uint_as_float(v[2 * i]), gv = __uint_as_float(v[2 * i + 1]);
-            if (P.bias) {
-              xv += __ldg(P.bias + n);
-              gv += __ldg(P.bias + n + 1);
-            }
-            o[i] = gelu_f(gv) * xv;
-          }
-          const long long idx = out_b + (long long)(n_out >> 3) * P.out_chunk + orow * P.out_row;
-          if (P.out_is_16) {
-            uint32_t h[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
-            *reinterpret_cast<uint4*>((unsigned short*)P.out + idx) = *reinterpret_cast<uint4*>(h);
-          } else {
-            float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
-            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-          }
-          return;
-        }
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int n0 = n_base + c0 + hh * 8;
-          if (n0 >= P.Cout) break;
-          float o[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float acc = __uint_as_float(v[hh * 8 + i]);
-            if (P.bias) acc += __ldg(P.bias + n0 + i);
-            o[i] = acc * P.alpha;
-            if (use_res) o[i] = fmaf(P.beta_res, rr[hh * 8 + i], o[i]);
-          }
-          const long long idx = out_b + (long long)(n0 >> 3) * P.out_chunk + orow * P.out_row;
-          if (P.out_is_16) {
-            uint32_t h[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
-            *reinterpret_cast<uint4*>((unsigned short*)P.out + idx) = *reinterpret_cast<uint4*>(h);
-          } else {
-            float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
-            if (P.accumulate) {
-              const float4 p0 = dst[0], p1 = dst[1];
-              o[0] += p0.x, o[1] += p0.y, o[2] += p0.z, o[3] += p0.w;
-              o[4] += p1.x, o[5] += p1.y, o[6] += p1.z, o[7] += p1.w;
-            }
-            dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-            dst[1] = make_float4(o[4], o[5], o[6], o[7]);
-          }
-        }
-      };
+// ------------------------------------------------------------------------------ fused snake + conv
+// Same implicit GEMM, but the A operand is produced IN the kernel: conv(Activation1d(x)) without the 16-bit
+// activation ever touching HBM (the HBM-bound C <= 128 stages drop from 28 to 20 bytes per element-pair).
+// Warp roles (16 warps): 0 = bulk-copy producer of raw fp32 activation windows (own ring of x_stages slots),
+// 1 = MMA issuer, 2 = bulk-copy producer of weight slots, 4..7 = epilogue, 8..15 = snake warps that turn a raw
+// window into the 16-bit K-major chunk image of the A slot (packed-FFMA2 taps from registers, as in
+// vocoder_tc.cu), fence.proxy.async, and arrive on the stage's full barrier next to the weight bytes.
+// One smem stage = one ci-pair (16 channels) with all taps; R outputs per snake thread (R odd: the 8 pairs x 4
+// groups of a warp then hit 32 distinct banks both when reading the window and when writing the A slot).
+__device__ __forceinline__ float2 tc_ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 tc_fmul2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
 
-      uint32_t va[16], vb[16];
-      float ra[16], rb[16];
-      fetch_res(half, ra);  // residual of the first group is requested BEFORE waiting for the accumulator
-      mbar_wait(tfull0 + 8 * as, aphase, P.err_flag, 4);
-      tc_fence_after();
-      issue_ld(half, va);
-      for (int gi = half; gi < n_groups_total; gi += 4) {
-        tmem_ld_wait();
-        issue_ld(gi + 2, vb);
-        fetch_res(gi + 2, rb);
-        finish(gi, va, ra);
-        if (gi + 2 >= n_groups_total) break;
-        tmem_ld_wait();
-        issue_ld(gi + 4, va);
-        fetch_res(gi + 4, ra);
-        finish(gi + 2, vb, rb);
+constexpr int kFusedThreads = 512;
+
+template <int R>
+__global__ void __launch_bounds__(kFusedThreads, 1) tc_conv_snake_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
+  const uint32_t tfull0 = empty0 + 8 * kMaxStages, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxStages + 4));
+  const uint32_t xfull0 = full0 + 192, xempty0 = full0 + 224;
+  int* s_off = reinterpret_cast<int*>(smem + 512);
+  const uint32_t xs0 = smem_u32(smem + 1024);
+  const uint32_t stage0 = xs0 + (uint32_t)(P.x_stages * P.xs_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int S = P.stages, XS = P.x_stages;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) {
+      mbar_init(full0 + 8 * i, 1 + 8);  // weight producer (expect_tx) + 8 snake warps
+      mbar_init(empty0 + 8 * i, 1);
+    }
+    for (int i = 0; i < XS; ++i) {
+      mbar_init(xfull0 + 8 * i, 1);
+      mbar_init(xempty0 + 8 * i, 8);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tfull0 + 8 * i, 1);
+      mbar_init(tempty0 + 8 * i, 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + P.ntaps) s_off[threadIdx.x - 64] = P.tap_off[threadIdx.x - 64] - P.min_off[0];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t b_tap_bytes = (uint32_t)P.bn * 32u;
+  const uint32_t a_chunk_bytes = (uint32_t)P.arows_pad * 16u;
+  const uint32_t a_slot_bytes = 2u * a_chunk_bytes;
+  const uint32_t x_chunk_bytes = (uint32_t)P.xrows * 32u;  // one 8-channel fp32 window
+  const int tile_rows = 128 * P.msub;
+  const uint32_t acc_cols = (uint32_t)(P.msub * P.bn);
+  const int mn = P.min_off[0];
+
+  if (warp == 0) {
+    // ===================================================================== raw-activation producer
+    if (lane == 0) {
+      int xs = 0, xph = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(P, tile);
+        const long long row = (long long)P.a_row0 + (long long)tc.mt * tile_rows + mn - 5;  // >= 0 (host check)
+        long long nrows = (long long)P.rows_per_chunk - row;  // stay inside this chunk's rows
+        if (nrows > P.xrows) nrows = P.xrows;
+        const float* x_base = P.xf + (long long)tc.b * P.a_batch + row * 8;
+        for (int cp = 0; cp < P.ci_pairs; ++cp) {
+          mbar_wait(xempty0 + 8 * xs, xph ^ 1, P.err_flag, 5);
+          const uint32_t dst = xs0 + (uint32_t)xs * (uint32_t)P.xs_bytes;
+          const uint32_t fb = xfull0 + 8 * xs;
+          mbar_expect_tx(fb, 2u * (uint32_t)nrows * 32u);
+          bulk_g2s(dst, x_base + (long long)(2 * cp) * P.a_chunk, (uint32_t)nrows * 32u, fb);
+          bulk_g2s(dst + x_chunk_bytes, x_base + (long long)(2 * cp + 1) * P.a_chunk, (uint32_t)nrows * 32u, fb);
+          if (++xs == XS) {
+            xs = 0;
+            xph ^= 1;
+          }
+        }
       }
-      // all TMEM reads of this warp are complete (wait::ld above) -> release the accumulator
-      tmem_ld_wait();
-      tc_fence_before();
+    }
+  } else if (warp == 2) {
+    // ===================================================================== weight producer
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(P, tile);
+        const __nv_bfloat16* w_base = P.w + ((long long)tc.nt * P.ci_pairs) * ((long long)P.ntaps * P.bn * 16);
+        for (int cp = 0; cp < P.ci_pairs; ++cp) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 1);
+          const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
+          const uint32_t fb = full0 + 8 * stage;
+          mbar_expect_tx(fb, (uint32_t)P.ntaps * b_tap_bytes);
+          bulk_g2s(sa + a_slot_bytes, w_base + (long long)cp * P.ntaps * ((long long)P.bn * 16),
+                   (uint32_t)P.ntaps * b_tap_bytes, fb);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one stage = one ci-pair)
+    const bool leader = elect_one();
+    int stage = 0, phase = 0, as = 0, aphase = 0;
+    const uint32_t idesc = make_idesc(P.bn, P.fp16);
+    const uint64_t adesc_c = make_desc(0, a_chunk_bytes, 128);
+    const uint64_t bdesc_c = make_desc(0, (uint32_t)P.bn * 16u, 128);
+    const uint32_t b_tap_u = b_tap_bytes >> 4;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      mbar_wait(tempty0 + 8 * as, aphase ^ 1, P.err_flag, 2);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
+      uint32_t accum = 0;
+      for (int cp = 0; cp < P.ci_pairs; ++cp) {
+        mbar_wait(full0 + 8 * stage, phase, P.err_flag, 3);
+        tc_fence_after();
+        const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
+        const uint64_t ad0 = adesc_c + (uint64_t)(sa >> 4);
+        uint64_t bd = bdesc_c + (uint64_t)((sa + a_slot_bytes) >> 4);
+        if (leader) {
+          for (int j = 0; j < P.ntaps; ++j) {
+            const uint64_t ad = ad0 + (uint64_t)(uint32_t)s_off[j];
+            for (int sub = 0; sub < P.msub; ++sub)
+              umma_bf16(d_tmem + (uint32_t)(sub * P.bn), ad + (uint64_t)(sub * 128), bd, idesc, accum);
+            accum = 1;
+            bd += b_tap_u;
+          }
+          umma_commit(empty0 + 8 * stage);
+        }
+        accum = 1;
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (leader) umma_commit(tfull0 + 8 * as);
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * as);
       if (++as == P.acc_stages) {
         as = 0;
         aphase ^= 1;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================================== epilogue (4 warps, one per lane group)
+    epilogue_role(P, tmem_base, tfull0, tempty0, warp & 3, 0, 1, lane, tile_rows, acc_cols);
+  } else if (warp >= 8) {
+    // ===================================================================== snake warps
+    const int stid = threadIdx.x - 256;
+    const int e2 = stid & 7, g = stid >> 3;       // channel pair (0..7 over the two chunks), row group (0..31)
+    const int csel = e2 >> 2, pc = e2 & 3;
+    float2 fu[12], fd[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) {
+      const float fk = __ldg(P.sn_filt + k);
+      fu[k] = make_float2(2.0f * fk, 2.0f * fk);
+      fd[k] = make_float2(fk, fk);
+    }
+    int stage = 0, phase = 0, xs = 0, xph = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const TileCoord tc = decode_tile(P, tile);
+      const int t_slot0 = tc.mt * tile_rows + mn;  // time of A-slot row 0; raw window row 0 is t_slot0 - 5
+      const bool edge = (t_slot0 - 5 < 0) || (t_slot0 + 32 * R + 5 > P.L);
+      const int q0 = t_slot0 + g * R;              // time of this thread's first output row
+      for (int cp = 0; cp < P.ci_pairs; ++cp) {
+        const int c0 = cp * 16 + csel * 8 + 2 * pc;
+        const float2 al2 = make_float2(2.0f * __ldg(P.sn_a + c0), 2.0f * __ldg(P.sn_a + c0 + 1));
+        const float2 hib = make_float2(0.5f * __ldg(P.sn_ib + c0), 0.5f * __ldg(P.sn_ib + c0 + 1));
+        const float2 nhib = make_float2(-hib.x, -hib.y);
+        mbar_wait(xfull0 + 8 * xs, xph, P.err_flag, 6);
+        const float* xw = reinterpret_cast<const float*>(smem + 1024 + (size_t)xs * P.xs_bytes + (size_t)csel * x_chunk_bytes) +
+                          2 * pc;
+        float2 xv[R + 10];
+        if (!edge) {
+#pragma unroll
+          for (int j = 0; j < R + 10; ++j) xv[j] = *reinterpret_cast<const float2*>(xw + (g * R + j) * 8);
+        } else {  // replicate pad: rows t < 0 read x[0], rows t >= L read x[L-1]
+#pragma unroll
+          for (int j = 0; j < R + 10; ++j) {
+            int t = q0 - 5 + j;
+            t = min(max(t, 0), P.L - 1);
+            int i = t - (t_slot0 - 5);
+            i = min(max(i, 0), P.xrows - 1);
+            xv[j] = *reinterpret_cast<const float2*>(xw + i * 8);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xempty0 + 8 * xs);  // the raw window of this stage has been consumed
+        if (++xs == XS) {
+          xs = 0;
+          xph ^= 1;
+        }
+        float2 sv[2 * R + 10];
+#pragma unroll
+        for (int i = 0; i < 2 * R + 10; ++i) {
+          const int qq = (i - 5) >> 1;
+          float2 u = make_float2(0.f, 0.f);
+          if ((i & 1) == 0) {
+#pragma unroll
+            for (int d = -2; d <= 3; ++d) u = tc_ffma2(xv[qq + d + 5], fu[6 - 2 * d], u);
+          } else {
+#pragma unroll
+            for (int d = -3; d <= 2; ++d) u = tc_ffma2(xv[qq + d + 5], fu[5 - 2 * d], u);
+          }
+          const float2 z = tc_fmul2(u, al2);
+          const float2 c = make_float2(__cosf(z.x), __cosf(z.y));
+          sv[i] = tc_ffma2(c, nhib, u);
+        }
+        if (edge) {  // replicate clamp of the 2x-rate signal: s[m < 0] = s[0], s[m > 2L-1] = s[2L-1]
+          const int i_lo = 5 - 2 * q0, i_hi = 2 * (P.L - q0) + 4;
+          if (i_hi >= 0 && i_hi < 2 * R + 10 - 1) {
+            float2 prev = sv[0];
+#pragma unroll
+            for (int i = 0; i < 2 * R + 10; ++i) {
+              if (i <= i_hi) prev = sv[i];
+              else sv[i] = prev;
+            }
+          }
+          if (i_lo > 0 && i_lo <= 2 * R + 10 - 1) {
+            float2 nxt = sv[2 * R + 9];
+#pragma unroll
+            for (int i = 2 * R + 9; i >= 0; --i) {
+              if (i >= i_lo) nxt = sv[i];
+              else sv[i] = nxt;
+            }
+          }
+        }
+        mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 7);  // the MMAs that last read this A slot retired
+        const uint32_t a_dst = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes + (uint32_t)csel * a_chunk_bytes +
+                               (uint32_t)(g * R) * 16u + (uint32_t)pc * 4u;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+          float2 acc = hib;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) acc = tc_ffma2(fd[k], sv[2 * j + k], acc);
+          const int t = q0 + j;
+          const uint32_t v = (t >= 0 && t < P.L) ? fh::pack16(acc.x, acc.y, P.fp16) : 0u;  // conv zero padding
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_dst + (uint32_t)j * 16u), "r"(v) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + 8 * stage);
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   }
@@ -530,6 +809,14 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
   p.alpha = a->alpha, p.beta_res = a->beta_res;
   p.B = a->B, p.L = a->L, p.Cin = a->Cin, p.Cout = a->Cout, p.ntaps = a->ntaps, p.P = a->P, p.bn = a->bn;
   p.n_tiles = (a->Cout + a->bn - 1) / a->bn;
+  const bool fused = a->x_f32 != nullptr;
+  if (fused) {
+    FH_REQUIRE(a->P == 1 && p.n_tiles == 1 && a->bn <= 128 && a->ntaps * a->bn * 32 <= 48 * 1024 && a->sn_a &&
+                   a->sn_inv_b && a->sn_filt && !a->geglu,
+               FH_ERR_UNSUPPORTED_CFG,
+               "fh_tc_conv: fused snake needs P == 1, one N tile of <= 128 columns and ntaps*bn*32 <= 48 KB");
+    FH_REQUIRE(((uintptr_t)a->x_f32 % 16) == 0, FH_ERR_BAD_ALIGN, "fh_tc_conv: x_f32 must be 16-byte aligned");
+  }
   // sub-tiles: reuse each weight slot for up to 4 x 128 rows when the accumulators fit TMEM twice over
   int msub = 256 / a->bn;
   msub = msub >= 4 ? 4 : (msub >= 2 ? 2 : 1);
@@ -544,7 +831,9 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
     if (m) wide_min = atoi(m);
   }
   if (a->bn > 128 && wide_msub == 2 && (long long)a->ntaps * (a->Cin / 16) >= wide_min) msub = 2;
-  while (msub > 1 && (long long)a->B * a->P * ((a->L + 128 * msub - 1) / (128 * msub)) * p.n_tiles < 2 * 148) msub >>= 1;
+  while (!fused && msub > 1 &&
+         (long long)a->B * a->P * ((a->L + 128 * msub - 1) / (128 * msub)) * p.n_tiles < 2 * 148)
+    msub >>= 1;
   p.msub = msub;
   p.acc_stages = (2 * msub * a->bn <= 512) ? 2 : 1;
   p.m_tiles = (a->L + 128 * msub - 1) / (128 * msub);
@@ -569,6 +858,17 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
   FH_REQUIRE(span <= kMaxSpan, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: tap span %d exceeds %d rows", span, kMaxSpan);
   p.wrows = 128 * msub + span;
   p.arows_pad = 128 * msub + kMaxSpan;
+  const int snake_R = msub == 4 ? 19 : 11;  // outputs per snake thread: 32*R rows cover 128*msub + span
+  if (fused) {
+    FH_REQUIRE(msub == 2 || msub == 4, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake needs bn <= 128");
+    FH_REQUIRE(p.wrows <= 32 * snake_R, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake window too small");
+    FH_REQUIRE(a->a_row0 + p.min_off[0] - 5 >= 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: fused snake needs 5 more halo rows");
+    p.arows_pad = 32 * snake_R + 4;   // (rows*4 words) = 16 mod 32: the two chunks of a slot use disjoint banks
+    p.xrows = 32 * snake_R + 10;      // raw window rows (= 2 mod 4: same bank property for 32-byte rows)
+    p.xs_bytes = 2 * p.xrows * 32;
+    p.rows_per_chunk = (int)(a->a_chunk / 8);
+    p.xf = a->x_f32, p.sn_a = a->sn_a, p.sn_ib = a->sn_inv_b, p.sn_filt = a->sn_filt;
+  }
   // taps per stage: a weight slot of <= 32 KB (<= 48 KB for narrow tiles, so that all taps of a ci-pair share
   // one activation window fetch), with the taps spread evenly over the groups (11 taps -> 6+5, not 10+1)
   static int slot_small_kb = 0, slot_wide_kb = 0;
@@ -579,6 +879,7 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
     slot_wide_kb = e2 ? atoi(e2) : 48;
   }
   int tg = ((a->bn <= 128 ? slot_small_kb : slot_wide_kb) * 1024) / (a->bn * 32);
+  if (fused) tg = a->ntaps;  // one stage = one ci-pair with all its taps
   if (tg < 1) tg = 1;
   if (tg > a->ntaps) tg = a->ntaps;
   p.n_groups = (a->ntaps + tg - 1) / tg;
@@ -593,6 +894,40 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
     if (budget_kb < 64 || budget_kb > 220) budget_kb = 200;
   }
   const int budget = budget_kb * 1024;
+  if (fused) {
+    p.x_stages = 3;
+    int st = (budget - 1024 - p.x_stages * p.xs_bytes) / p.stage_bytes;
+    if (st < 2) {
+      p.x_stages = 2;
+      st = (budget - 1024 - p.x_stages * p.xs_bytes) / p.stage_bytes;
+    }
+    FH_REQUIRE(st >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake stages do not fit shared memory");
+    p.stages = st > 3 ? 3 : st;
+    p.err_flag = nullptr;
+    const int fsmem = 1024 + p.x_stages * p.xs_bytes + p.stages * p.stage_bytes;
+    static int fsmem_set[2] = {0, 0};
+    static int fsms = 0;
+    if (!fsms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&fsms, cudaDevAttrMultiProcessorCount, dev);
+      if (fsms <= 0) fsms = 148;
+    }
+    const int which = msub == 4 ? 1 : 0;
+    if (fsmem > fsmem_set[which]) {
+      cudaError_t e = which ? cudaFuncSetAttribute(tc_conv_snake_kernel<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem)
+                            : cudaFuncSetAttribute(tc_conv_snake_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem);
+      FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", fsmem,
+                 cudaGetErrorString(e));
+      fsmem_set[which] = fsmem;
+    }
+    const int fgrid = p.total_tiles < fsms ? p.total_tiles : fsms;
+    if (which)
+      tc_conv_snake_kernel<19><<<fgrid, kFusedThreads, fsmem, (cudaStream_t)stream>>>(p);
+    else
+      tc_conv_snake_kernel<11><<<fgrid, kFusedThreads, fsmem, (cudaStream_t)stream>>>(p);
+    return fh::check_launch("fh_tc_conv(fused snake)");
+  }
   int stages = (budget - 1024) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   FH_REQUIRE(stages >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: stage of %d bytes does not fit twice", p.stage_bytes);

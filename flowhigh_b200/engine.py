@@ -63,6 +63,7 @@ class Engine:
         import os as _os
         self.voc_streams = int(_os.environ.get("FH_VOC_STREAMS", "1"))
         self.tc_attention = _os.environ.get("FH_TC_ATTENTION", "1") != "0"  # mma.sync split-operand attention
+        self.fuse_snake = _os.environ.get("FH_FUSE_SNAKE", "0") != "0"      # snake as the conv kernel's A-producer
         self._side_streams = []
         self._time_cache: Dict[float, dict] = {}
         dev = self.device
@@ -296,9 +297,12 @@ class Engine:
         return out
 
     def _tc_conv(self, rec: _TcWeight, a, a_batch, a_chunk, a_row0, out, out_strides, out_bf16, B, L, res=None,
-                 res_strides=(0, 0, 0), res_bf16=0, alpha=1.0, beta=0.0, accumulate=0, geglu=0):
+                 res_strides=(0, 0, 0), res_bf16=0, alpha=1.0, beta=0.0, accumulate=0, geglu=0, xf=None, snake=None):
         args = _lib.TcConvArgs()
-        args.a, args.a_batch, args.a_chunk, args.a_row0 = a.data_ptr(), a_batch, a_chunk, a_row0
+        args.a, args.a_batch, args.a_chunk, args.a_row0 = _ptr(a), a_batch, a_chunk, a_row0
+        if xf is not None:  # fused anti-aliased snake prologue: A = Activation1d(xf), computed in the kernel
+            args.x_f32 = xf.data_ptr()
+            args.sn_a, args.sn_inv_b, args.sn_filt = snake[0].data_ptr(), snake[1].data_ptr(), snake[2].data_ptr()
         args.w, args.bias = rec.packed.data_ptr(), _ptr(rec.bias)
         args.res, args.out = _ptr(res), out.data_ptr()
         args.out_batch, args.out_chunk, args.out_row = out_strides
@@ -312,7 +316,7 @@ class Engine:
             return
         flops = 2.0 * B * L * rec.P * rec.ntaps * rec.cin * rec.cout
         esz_o = 2 if out_bf16 else 4
-        nbytes = B * L * rec.cin * 2 + B * L * rec.P * rec.cout * esz_o * (2 if accumulate else 1)
+        nbytes = B * L * rec.cin * (4 if xf is not None else 2) + B * L * rec.P * rec.cout * esz_o * (2 if accumulate else 1)
         if res is not None:
             nbytes += B * L * rec.P * rec.cout * (2 if res_bf16 else 4)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -321,7 +325,7 @@ class Engine:
         e1.record(torch.cuda.current_stream(self.device))
         self.profile.append(("fh_tc_conv", e0, e1,
                              {"flops": flops, "bytes": float(nbytes),
-                              "tag": f"tc_conv[Cin{rec.cin},Cout{rec.cout},k{rec.ntaps}x{rec.P}]"}))
+                              "tag": f"tc_conv{'+snake' if xf is not None else ''}[Cin{rec.cin},Cout{rec.cout},k{rec.ntaps}x{rec.P}]"}))
 
     def _sgemm(self, A, lda, W, ldw, bias, res, ldr, beta, alpha, out, ldc, M, N, K):
         self._call("fh_sgemm_nt_f32", A.data_ptr(), lda, W.data_ptr() if isinstance(W, torch.Tensor) else W, ldw,
@@ -619,30 +623,36 @@ class Engine:
             strides = (bs, cs, 8)
             self._tc_conv(V[f"up{s}"], a_in, a_bs, a_cs, HALO, X[o:], strides, 0, B, L)
             L = Lo
+            fuse = self.fuse_snake and ch <= 128  # HBM-bound stages: snake runs inside the conv kernel
             for j, dil in enumerate(v.resblock_dilation_sizes):
                 cur = X
                 for i in range(len(dil)):
                     last = i == len(dil) - 1
-                    a1, ib1, f1 = V[f"r{s}.{j}.a1.{i}"]
-                    self._call("fh_snake_aa_chunked", cur.data_ptr(), A.data_ptr(), a1.data_ptr(), ib1.data_ptr(),
-                               f1.data_ptr(), bs, cs, HALO, B, ch, L, self.k16, st)
+                    sn1 = V[f"r{s}.{j}.a1.{i}"]
+                    if not fuse:
+                        self._call("fh_snake_aa_chunked", cur.data_ptr(), A.data_ptr(), sn1[0].data_ptr(), sn1[1].data_ptr(),
+                                   sn1[2].data_ptr(), bs, cs, HALO, B, ch, L, self.k16, st)
                     if started_event is not None:
                         started_event.record(torch.cuda.current_stream(self.device))
                         started_event = None
+                    fa = dict(xf=cur, snake=sn1) if fuse else {}
                     if v.resblock == "1":
-                        self._tc_conv(V[f"r{s}.{j}.c1.{i}"], A, bs, cs, HALO, Y[o:], strides, 0, B, L)
-                        a2, ib2, f2 = V[f"r{s}.{j}.a2.{i}"]
-                        self._call("fh_snake_aa_chunked", Y.data_ptr(), A.data_ptr(), a2.data_ptr(), ib2.data_ptr(),
-                                   f2.data_ptr(), bs, cs, HALO, B, ch, L, self.k16, st)
+                        self._tc_conv(V[f"r{s}.{j}.c1.{i}"], None if fuse else A, bs, cs, HALO, Y[o:], strides, 0, B, L, **fa)
+                        sn2 = V[f"r{s}.{j}.a2.{i}"]
+                        if not fuse:
+                            self._call("fh_snake_aa_chunked", Y.data_ptr(), A.data_ptr(), sn2[0].data_ptr(), sn2[1].data_ptr(),
+                                       sn2[2].data_ptr(), bs, cs, HALO, B, ch, L, self.k16, st)
+                        fa = dict(xf=Y, snake=sn2) if fuse else {}
                         conv = V[f"r{s}.{j}.c2.{i}"]
                     else:
                         conv = V[f"r{s}.{j}.c1.{i}"]
+                    src = None if fuse else A
                     if last:
-                        self._tc_conv(conv, A, bs, cs, HALO, XS[o:], strides, 0, B, L, res=cur[o:], res_strides=strides,
-                                      alpha=1.0 / nk, beta=1.0 / nk, accumulate=j > 0)
+                        self._tc_conv(conv, src, bs, cs, HALO, XS[o:], strides, 0, B, L, res=cur[o:], res_strides=strides,
+                                      alpha=1.0 / nk, beta=1.0 / nk, accumulate=j > 0, **fa)
                     else:
-                        self._tc_conv(conv, A, bs, cs, HALO, XJ[o:], strides, 0, B, L, res=cur[o:], res_strides=strides,
-                                      beta=1.0)
+                        self._tc_conv(conv, src, bs, cs, HALO, XJ[o:], strides, 0, B, L, res=cur[o:], res_strides=strides,
+                                      beta=1.0, **fa)
                         cur = XJ
             if s + 1 < v.num_stages:
                 XB, _, _ = self_cbuf(f"vt_XB{s}", B, ch, L, bf)

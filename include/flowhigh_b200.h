@@ -181,6 +181,13 @@ typedef struct {
   const int* tap_off;     /* HOST pointer [P][ntaps] row offsets */
   int bn;                 /* N tile, multiple of 16, <= 256 */
   int fp16;               /* 16-bit operand format: 0 = bfloat16, 1 = IEEE half (same rate, 3 more mantissa bits) */
+  /* fused anti-aliased Snake prologue (optional): when x_f32 != NULL the A operand is Activation1d(x_f32)
+   * computed inside the kernel (alias_free_torch/act.py:23-28); x_f32 is chunked fp32 with the geometry
+   * a_batch / a_chunk / a_row0 describe; `a` is ignored.  Needs P == 1, Cout <= bn <= 128 and a_row0 >= 5 - min tap. */
+  const float* x_f32;
+  const float* sn_a;      /* [Cin] alpha (already exp'd when logscale) */
+  const float* sn_inv_b;  /* [Cin] 1 / (beta + 1e-9) */
+  const float* sn_filt;   /* [12] Kaiser-sinc taps */
 } fh_tc_conv_args;
 int fh_tc_conv(const fh_tc_conv_args* args, void* stream);
 /* bytes of the packed weight image for given shape (host helper, no GPU work) */

@@ -534,3 +534,21 @@ def test_generate_rejects_too_short_clip(cuda_device, f32_model):
     m, _ = f32_model
     with pytest.raises(ValueError):
         m.generate(np.zeros(100, np.float32) + 0.1, 16000, 48000)  # 300 samples @ 48 k < 785
+
+
+@pytest.mark.parametrize("name", ["voc_resblock2_snake", "voc_resblock1_snakebeta"])
+def test_fused_snake_conv_matches_unfused(cuda_device, name):
+    """tc_conv_snake_kernel (snake computed by producer warps inside the conv kernel) against the two-kernel path."""
+    eng, sd, vcfg, g = engine(name, "fp16")
+    mel = dev(g["mel"])
+    prev = eng.fuse_snake
+    try:
+        eng.fuse_snake = False
+        a = eng.vocoder(mel).cpu()
+        eng.fuse_snake = True
+        b = eng.vocoder(mel).cpu()
+    finally:
+        eng.fuse_snake = prev
+    err = float((a - b).abs().max())
+    print(f"fused snake+conv vs unfused {name}: max-abs {err:.3g}")
+    assert err <= 2e-4
