@@ -67,7 +67,7 @@ __device__ __forceinline__ void pbulk_g2s(uint32_t dst, const void* src, uint32_
 }
 
 template <int OUT_KIND>
-__global__ void __launch_bounds__(128, 6) snake_aa_chunked_tma_kernel(
+__global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(
     const float* __restrict__ x, void* __restrict__ y, const float* __restrict__ a, const float* __restrict__ inv_b,
     const float* __restrict__ filt, long long batch_stride, long long chunk_stride, int row0, int nchunk, int L,
     int ntile, int total) {
@@ -131,70 +131,50 @@ __global__ void __launch_bounds__(128, 6) snake_aa_chunked_tma_kernel(
     const float2 hib = make_float2(0.5f * __ldg(inv_b + c0), 0.5f * __ldg(inv_b + c0 + 1));
     const float2 nhib = make_float2(-hib.x, -hib.y);
     const int q0 = qt + g * PR;
-    const float* xp = xt + g * (PR * 8) + 2 * e2;  // staged row of x~[q0 - 5], this thread's channel pair
+    float2 xv[PR + 10];
+    const float* xp = xt + g * (PR * 8) + 2 * e2;
+#pragma unroll
+    for (int j = 0; j < PR + 10; ++j) xv[j] = *reinterpret_cast<const float2*>(xp + j * 8);
+    __syncthreads();  // every thread has read this buffer's window
     if (threadIdx.x == 0 && item + (int)gridDim.x < total) {
-      // the other buffer was fully read one iteration ago (every iteration ends with __syncthreads)
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(item + gridDim.x, buf ^ 1);
+      issue(item + gridDim.x, buf ^ 1);  // that buffer was fully read one iteration ago
     }
     if (q0 < L) {
+      float2 s[2 * PR + 10];
+#pragma unroll
+      for (int i = 0; i < 2 * PR + 10; ++i) {
+        const int qq = (i - 5) >> 1;
+        float2 u = make_float2(0.f, 0.f);
+        if ((i & 1) == 0) {
+#pragma unroll
+          for (int d = -2; d <= 3; ++d) u = ffma2(xv[qq + d + 5], fu[6 - 2 * d], u);
+        } else {
+#pragma unroll
+          for (int d = -3; d <= 2; ++d) u = ffma2(xv[qq + d + 5], fu[5 - 2 * d], u);
+        }
+        const float2 z = fmul2(u, al2);
+        const float2 c = make_float2(__cosf(z.x), __cosf(z.y));
+        s[i] = ffma2(c, nhib, u);
+      }
+      if (edge && (q0 == 0 || q0 + PR + 3 >= L)) {
+        const int ic = 2 * (L - q0) + 5;
+        float2 prev = s[5];
+#pragma unroll
+        for (int i = 0; i < 2 * PR + 10; ++i) {
+          if (q0 == 0 && i < 5) s[i] = prev;
+          if (i < ic) prev = s[i];
+          else s[i] = prev;
+        }
+      }
       const long long obase =
           (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)(row0 + q0) * 8 + 2 * e2;
-      if (!edge) {
-        // Interior tiles: sliding windows.  The 2x-rate samples 2a and 2a+1 (relative to 2*q0 - 5) both read
-        // x~[a .. a+5]:  s[2a] = S(sum_w x[a+w] f2[10-2w]),  s[2a+1] = S(sum_w x[a+w] f2[11-2w]),  and output j
-        // needs the pairs a = j .. j+5, so only 6 inputs and 6 sample pairs are live at any time.
-        float2 xw[PR + 10], se[PR + 5], so[PR + 5];
 #pragma unroll
-        for (int w = 0; w < 5; ++w) xw[w] = *reinterpret_cast<const float2*>(xp + w * 8);
-#pragma unroll
-        for (int a_ = 0; a_ < PR + 5; ++a_) {
-          xw[a_ + 5] = *reinterpret_cast<const float2*>(xp + (a_ + 5) * 8);
-          float2 ue = make_float2(0.f, 0.f), uo = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int w = 0; w < 6; ++w) {
-            ue = ffma2(xw[a_ + w], fu[10 - 2 * w], ue);
-            uo = ffma2(xw[a_ + w], fu[11 - 2 * w], uo);
-          }
-          const float2 ze = fmul2(ue, al2), zo = fmul2(uo, al2);
-          se[a_] = ffma2(make_float2(__cosf(ze.x), __cosf(ze.y)), nhib, ue);
-          so[a_] = ffma2(make_float2(__cosf(zo.x), __cosf(zo.y)), nhib, uo);
-          if (a_ >= 5) {
-            const int j = a_ - 5;
-            float2 acc = hib;
-#pragma unroll
-            for (int p_ = 0; p_ < 6; ++p_) {
-              acc = ffma2(fd[2 * p_], se[j + p_], acc);
-              acc = ffma2(fd[2 * p_ + 1], so[j + p_], acc);
-            }
-            if (OUT_KIND)
-              *reinterpret_cast<uint32_t*>((unsigned short*)y + obase + j * 8) = fh::pack16(acc.x, acc.y, OUT_KIND == 2);
-            else
-              *reinterpret_cast<float2*>((float*)y + obase + j * 8) = acc;
-          }
-        }
-      } else {
-        // First / last tile of a sequence: generic form with the replicate clamp of the 2x-rate signal
-        // (s~[m] = s[clamp(m, 0, 2L-1)]); the staged window already holds the replicate-padded input.
-        for (int j = 0; j < PR; ++j) {
-          const int q = q0 + j;
-          if (q >= L) break;
+      for (int j = 0; j < PR; ++j) {
+        if (!edge || q0 + j < L) {
           float2 acc = hib;
 #pragma unroll
-          for (int k = 0; k < 12; ++k) {
-            const int m = min(max(2 * q + k - 5, 0), 2 * L - 1);
-            const float* xr = xt + ((m >> 1) - (qt - 5)) * 8 + 2 * e2;  // staged row of x~[m >> 1]
-            float2 u = make_float2(0.f, 0.f);
-            if (m & 1) {
-#pragma unroll
-              for (int d = -2; d <= 3; ++d) u = ffma2(*reinterpret_cast<const float2*>(xr + d * 8), fu[6 - 2 * d], u);
-            } else {
-#pragma unroll
-              for (int d = -3; d <= 2; ++d) u = ffma2(*reinterpret_cast<const float2*>(xr + d * 8), fu[5 - 2 * d], u);
-            }
-            const float2 z = fmul2(u, al2);
-            acc = ffma2(fd[k], ffma2(make_float2(__cosf(z.x), __cosf(z.y)), nhib, u), acc);
-          }
+          for (int k = 0; k < 12; ++k) acc = ffma2(fd[k], s[2 * j + k], acc);
           if (OUT_KIND)
             *reinterpret_cast<uint32_t*>((unsigned short*)y + obase + j * 8) = fh::pack16(acc.x, acc.y, OUT_KIND == 2);
           else
@@ -202,7 +182,6 @@ __global__ void __launch_bounds__(128, 6) snake_aa_chunked_tma_kernel(
         }
       }
     }
-    __syncthreads();  // every thread is done with this buffer's window
     buf ^= 1;
   }
 }
@@ -256,7 +235,7 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  const int grid = (int)(total < (long long)sms * 6 ? total : (long long)sms * 6);
+  const int grid = (int)(total < (long long)sms * 4 ? total : (long long)sms * 4);
 #define FH_SNAKE_LAUNCH(KIND)                                                                                \
   snake_aa_chunked_tma_kernel<KIND><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, a, inv_b, filt, batch_stride, \
                                                                            chunk_stride, row0, C / 8, L, ntile, (int)total)
