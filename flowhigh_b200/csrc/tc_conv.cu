@@ -41,7 +41,8 @@ struct TcParams {
   float alpha, beta_res;
   int B, L, Cin, Cout, ntaps, P, bn;
   int m_tiles, n_tiles, total_tiles;
-  int ci_pairs;        // Cin / 16
+  int ci_pairs;        // ceil(Cin / 16)
+  int ci_odd;          // Cin % 16 == 8: the last pair has one real 8-channel chunk; its partner is a zeroed smem window
   int tg, n_groups;    // taps per smem stage, groups per ci-pair
   int msub;            // 128-row sub-tiles per CTA tile (1, 2 or 4): B operand reuse + epilogue MLP
   int acc_stages;      // TMEM accumulator stages: 2 (epilogue overlaps the next tile) or 1 (msub*bn > 256)
@@ -330,7 +331,11 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
+// MINB = 2 caps the kernel at 96 registers per thread (a few spilled words in the epilogue) so that the 320-thread CTA
+// leaves half of the register file free: CTAs of the FP32-pipe-bound snake kernel of another stream can then be
+// co-resident on the same SM and run under the tensor-pipe-bound convolution (engine.voc_streams > 1).
+template <int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // [0,256): barriers; [256,260): tmem base; stages from 1024
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -356,6 +361,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   if (threadIdx.x >= 64 && threadIdx.x < 64 + P.P * P.ntaps) {
     const int i = threadIdx.x - 64;
     reinterpret_cast<int*>(smem + 512)[i] = P.tap_off[i] - P.min_off[i / P.ntaps];
+  }
+  if (P.ci_odd) {
+    // Odd chunk count (e.g. 24 channels): the partner window of the last chunk is never fetched.  Its weights are
+    // zero, so it only has to hold finite values: zero every stage's second window once (stale activations of other
+    // pairs that land there later are finite as well).
+    const uint32_t cb = (uint32_t)P.arows_pad * 16u;
+    for (int st = 0; st < S; ++st) {
+      uint4* z = reinterpret_cast<uint4*>(smem + 1024 + (size_t)st * P.stage_bytes + cb);
+      for (uint32_t i = threadIdx.x; i < cb / 16u; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   tc_fence_before();
   __syncthreads();
@@ -389,9 +405,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
             const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
             const uint32_t fb = full0 + 8 * stage;
             const uint32_t a_bytes = (uint32_t)P.wrows * 16u;
-            mbar_expect_tx(fb, 2u * a_bytes + (uint32_t)nt_g * b_tap_bytes);
+            const bool pair = !(P.ci_odd && cp == P.ci_pairs - 1);
+            mbar_expect_tx(fb, (pair ? 2u : 1u) * a_bytes + (uint32_t)nt_g * b_tap_bytes);
             bulk_g2s(sa, a_base + (long long)(2 * cp) * P.a_chunk, a_bytes, fb);
-            bulk_g2s(sa + a_chunk_bytes, a_base + (long long)(2 * cp + 1) * P.a_chunk, a_bytes, fb);
+            if (pair) bulk_g2s(sa + a_chunk_bytes, a_base + (long long)(2 * cp + 1) * P.a_chunk, a_bytes, fb);
             bulk_g2s(sa + a_slot_bytes, w_base + ((long long)cp * P.ntaps + tap0) * ((long long)P.bn * 16),
                      (uint32_t)nt_g * b_tap_bytes, fb);
             if (++stage == S) {
@@ -468,12 +485,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
 // ------------------------------------------------------------------------------ fused snake + conv
 // Same implicit GEMM, but the A operand is produced IN the kernel: conv(Activation1d(x)) without the 16-bit
 // activation ever touching HBM (the HBM-bound C <= 128 stages drop from 28 to 20 bytes per element-pair).
-// Warp roles (16 warps): 0 = bulk-copy producer of raw fp32 activation windows (own ring of x_stages slots),
-// 1 = MMA issuer, 2 = bulk-copy producer of weight slots, 4..7 = epilogue, 8..15 = snake warps that turn a raw
-// window into the 16-bit K-major chunk image of the A slot (packed-FFMA2 taps from registers, as in
-// vocoder_tc.cu), fence.proxy.async, and arrive on the stage's full barrier next to the weight bytes.
-// One smem stage = one ci-pair (16 channels) with all taps; R outputs per snake thread (R odd: the 8 pairs x 4
-// groups of a warp then hit 32 distinct banks both when reading the window and when writing the A slot).
+// Warp roles (20 warps): 0 = bulk-copy producer of raw fp32 activation windows (own ring of x_stages slots),
+// 1 = MMA issuer, 2 = bulk-copy producer of weight slots, 3 = idle, 4..7 = epilogue, 8..19 = snake warps.
+// One smem stage = one ci-pair (16 channels) x all taps x (256 + span) rows.  The snake warps turn the raw window
+// into the 16-bit K-major chunk image of the A slot in TWO phases with the 2x-rate signal staged in shared memory,
+// so that nothing is computed twice (the register-blocked standalone kernel recomputes a 10-sample halo per thread):
+//   phase 1: position q -> s[2q], s[2q+1] = snake(up-filter(x))      (12 packed FFMA2 + 2 x (mul, 2 cos, fma) per pair)
+//   phase 2: row t      -> y[t] = sum_k f[k] s[2t-5+k]  -> 16-bit    (12 packed FFMA2 per channel pair)
+// A thread owns a channel PAIR and kSR consecutive positions / rows in both phases (sliding register window);
+// kSR odd and the plane paddings below make every 64-bit shared-memory access of a half-warp conflict free.
+// Register budget (setmaxnreg): producers 24, epilogue 168, snake 96 per thread.
 __device__ __forceinline__ float2 tc_ffma2(float2 a, float2 b, float2 c) {
   unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
                      rc = *reinterpret_cast<unsigned long long*>(&c), rd;
@@ -486,9 +507,17 @@ __device__ __forceinline__ float2 tc_fmul2(float2 a, float2 b) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
-constexpr int kFusedThreads = 512;
+constexpr int kFusedThreads = 640;
+constexpr int kSnakeWarps = 12;
+constexpr int kSnakeThreads = kSnakeWarps * 32;
+constexpr int kSnakeGroups = kSnakeThreads / 8;   // 48 row groups x 8 channel pairs
+constexpr int kSR = 7;                            // positions / rows per snake thread (odd)
+constexpr int kSnakeCap = kSnakeGroups * kSR;     // 336 >= (256 + span) + 6
+constexpr int kXrPad = kSnakeCap + 6;             // raw window rows per chunk plane  (== 2 mod 4)
+constexpr int kSrPad = 2 * kSnakeCap + 13;        // 2x-rate rows per chunk plane      (== 1 mod 4)
+constexpr int kArPad = kSnakeCap + 4;             // A-slot rows per chunk plane       (== 4 mod 8)
+static_assert(kXrPad % 4 == 2 && kSrPad % 4 == 1 && kArPad % 8 == 4 && (kSR & 1), "bank-conflict-free paddings");
 
-template <int R>
 __global__ void __launch_bounds__(kFusedThreads, 1) tc_conv_snake_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -497,19 +526,26 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tc_conv_snake_kernel(const _
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxStages + 4));
   const uint32_t xfull0 = full0 + 192, xempty0 = full0 + 224;
   int* s_off = reinterpret_cast<int*>(smem + 512);
-  const uint32_t xs0 = smem_u32(smem + 1024);
-  const uint32_t stage0 = xs0 + (uint32_t)(P.x_stages * P.xs_bytes);
+  float* s_filt = reinterpret_cast<float*>(smem + 768);
+  float2* s_par = reinterpret_cast<float2*>(smem + 1024);  // [Cin <= 128] (2 alpha, 1/(2 beta)) per channel
+  // [2048 ..): x ring | 2x-rate buffer | A/W stages
+  const uint32_t xs_bytes = 2u * kXrPad * 32u;
+  const uint32_t sbuf_bytes = 2u * kSrPad * 32u;
+  unsigned char* xs_ptr = smem + 2048;
+  unsigned char* sbuf_ptr = xs_ptr + (size_t)P.x_stages * xs_bytes;
+  const uint32_t xs0 = smem_u32(xs_ptr);
+  const uint32_t stage0 = smem_u32(sbuf_ptr + sbuf_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = P.stages, XS = P.x_stages;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
-      mbar_init(full0 + 8 * i, 1 + 8);  // weight producer (expect_tx) + 8 snake warps
+      mbar_init(full0 + 8 * i, 1 + kSnakeWarps);  // weight producer (expect_tx) + snake warps
       mbar_init(empty0 + 8 * i, 1);
     }
     for (int i = 0; i < XS; ++i) {
       mbar_init(xfull0 + 8 * i, 1);
-      mbar_init(xempty0 + 8 * i, 8);
+      mbar_init(xempty0 + 8 * i, kSnakeWarps);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
@@ -519,148 +555,162 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tc_conv_snake_kernel(const _
   }
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   if (threadIdx.x >= 64 && threadIdx.x < 64 + P.ntaps) s_off[threadIdx.x - 64] = P.tap_off[threadIdx.x - 64] - P.min_off[0];
+  if (threadIdx.x >= 128 && threadIdx.x < 140) s_filt[threadIdx.x - 128] = __ldg(P.sn_filt + threadIdx.x - 128);
+  if (threadIdx.x >= 256 && threadIdx.x < 256 + 128) {
+    const int c = threadIdx.x - 256;
+    s_par[c] = c < P.Cin ? make_float2(2.0f * __ldg(P.sn_a + c), 0.5f * __ldg(P.sn_ib + c)) : make_float2(0.f, 0.f);
+  }
+  if (P.ci_odd) {  // the partner window of the last (single) chunk only has to be finite: zero it once
+    const uint32_t cb = (uint32_t)kArPad * 16u;
+    for (int st = 0; st < S; ++st) {
+      uint4* z = reinterpret_cast<uint4*>(sbuf_ptr + sbuf_bytes + (size_t)st * P.stage_bytes + cb);
+      for (uint32_t i = threadIdx.x; i < cb / 16u; i += kFusedThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const uint32_t b_tap_bytes = (uint32_t)P.bn * 32u;
-  const uint32_t a_chunk_bytes = (uint32_t)P.arows_pad * 16u;
+  const uint32_t a_chunk_bytes = (uint32_t)kArPad * 16u;
   const uint32_t a_slot_bytes = 2u * a_chunk_bytes;
-  const uint32_t x_chunk_bytes = (uint32_t)P.xrows * 32u;  // one 8-channel fp32 window
+  const uint32_t x_chunk_bytes = (uint32_t)kXrPad * 32u;  // one 8-channel fp32 window
   const int tile_rows = 128 * P.msub;
   const uint32_t acc_cols = (uint32_t)(P.msub * P.bn);
   const int mn = P.min_off[0];
 
-  if (warp == 0) {
-    // ===================================================================== raw-activation producer
-    if (lane == 0) {
-      int xs = 0, xph = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(P, tile);
-        const long long row = (long long)P.a_row0 + (long long)tc.mt * tile_rows + mn - 5;  // >= 0 (host check)
-        long long nrows = (long long)P.rows_per_chunk - row;  // stay inside this chunk's rows
-        if (nrows > P.xrows) nrows = P.xrows;
-        const float* x_base = P.xf + (long long)tc.b * P.a_batch + row * 8;
-        for (int cp = 0; cp < P.ci_pairs; ++cp) {
-          mbar_wait(xempty0 + 8 * xs, xph ^ 1, P.err_flag, 5);
-          const uint32_t dst = xs0 + (uint32_t)xs * (uint32_t)P.xs_bytes;
-          const uint32_t fb = xfull0 + 8 * xs;
-          mbar_expect_tx(fb, 2u * (uint32_t)nrows * 32u);
-          bulk_g2s(dst, x_base + (long long)(2 * cp) * P.a_chunk, (uint32_t)nrows * 32u, fb);
-          bulk_g2s(dst + x_chunk_bytes, x_base + (long long)(2 * cp + 1) * P.a_chunk, (uint32_t)nrows * 32u, fb);
-          if (++xs == XS) {
-            xs = 0;
-            xph ^= 1;
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == 0) {
+      // ===================================================================== raw-activation producer
+      if (lane == 0) {
+        int xs = 0, xph = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+          const TileCoord tc = decode_tile(P, tile);
+          const long long row = (long long)P.a_row0 + (long long)tc.mt * tile_rows + mn - 6;  // >= 0 (host check)
+          long long nrows = (long long)P.rows_per_chunk - row;  // stay inside this chunk's rows
+          if (nrows > P.xrows) nrows = P.xrows;
+          const float* x_base = P.xf + (long long)tc.b * P.a_batch + row * 8;
+          for (int cp = 0; cp < P.ci_pairs; ++cp) {
+            const bool pair = !(P.ci_odd && cp == P.ci_pairs - 1);
+            mbar_wait(xempty0 + 8 * xs, xph ^ 1, P.err_flag, 5);
+            const uint32_t dst = xs0 + (uint32_t)xs * xs_bytes;
+            const uint32_t fb = xfull0 + 8 * xs;
+            mbar_expect_tx(fb, (pair ? 2u : 1u) * (uint32_t)nrows * 32u);
+            bulk_g2s(dst, x_base + (long long)(2 * cp) * P.a_chunk, (uint32_t)nrows * 32u, fb);
+            if (pair) bulk_g2s(dst + x_chunk_bytes, x_base + (long long)(2 * cp + 1) * P.a_chunk, (uint32_t)nrows * 32u, fb);
+            if (++xs == XS) {
+              xs = 0;
+              xph ^= 1;
+            }
           }
         }
       }
-    }
-  } else if (warp == 2) {
-    // ===================================================================== weight producer
-    if (lane == 0) {
-      int stage = 0, phase = 0;
+    } else if (warp == 2) {
+      // ===================================================================== weight producer
+      if (lane == 0) {
+        int stage = 0, phase = 0;
+        for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+          const TileCoord tc = decode_tile(P, tile);
+          const __nv_bfloat16* w_base = P.w + ((long long)tc.nt * P.ci_pairs) * ((long long)P.ntaps * P.bn * 16);
+          for (int cp = 0; cp < P.ci_pairs; ++cp) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 1);
+            const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_expect_tx(fb, (uint32_t)P.ntaps * b_tap_bytes);
+            bulk_g2s(sa + a_slot_bytes, w_base + (long long)cp * P.ntaps * ((long long)P.bn * 16),
+                     (uint32_t)P.ntaps * b_tap_bytes, fb);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================================================================== MMA issuer (one stage = one ci-pair)
+      const bool leader = elect_one();
+      int stage = 0, phase = 0, as = 0, aphase = 0;
+      const uint32_t idesc = make_idesc(P.bn, P.fp16);
+      const uint64_t adesc_c = make_desc(0, a_chunk_bytes, 128);
+      const uint64_t bdesc_c = make_desc(0, (uint32_t)P.bn * 16u, 128);
+      const uint32_t b_tap_u = b_tap_bytes >> 4;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(P, tile);
-        const __nv_bfloat16* w_base = P.w + ((long long)tc.nt * P.ci_pairs) * ((long long)P.ntaps * P.bn * 16);
+        mbar_wait(tempty0 + 8 * as, aphase ^ 1, P.err_flag, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
+        uint32_t accum = 0;
         for (int cp = 0; cp < P.ci_pairs; ++cp) {
-          mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 1);
+          mbar_wait(full0 + 8 * stage, phase, P.err_flag, 3);
+          tc_fence_after();
           const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
-          const uint32_t fb = full0 + 8 * stage;
-          mbar_expect_tx(fb, (uint32_t)P.ntaps * b_tap_bytes);
-          bulk_g2s(sa + a_slot_bytes, w_base + (long long)cp * P.ntaps * ((long long)P.bn * 16),
-                   (uint32_t)P.ntaps * b_tap_bytes, fb);
+          const uint64_t ad0 = adesc_c + (uint64_t)(sa >> 4);
+          uint64_t bd = bdesc_c + (uint64_t)((sa + a_slot_bytes) >> 4);
+          if (leader) {
+            for (int j = 0; j < P.ntaps; ++j) {
+              const uint64_t ad = ad0 + (uint64_t)(uint32_t)s_off[j];
+              for (int sub = 0; sub < P.msub; ++sub)
+                umma_bf16(d_tmem + (uint32_t)(sub * P.bn), ad + (uint64_t)(sub * 128), bd, idesc, accum);
+              accum = 1;
+              bd += b_tap_u;
+            }
+            umma_commit(empty0 + 8 * stage);
+          }
+          accum = 1;
+          __syncwarp();
           if (++stage == S) {
             stage = 0;
             phase ^= 1;
           }
         }
-      }
-    }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (one stage = one ci-pair)
-    const bool leader = elect_one();
-    int stage = 0, phase = 0, as = 0, aphase = 0;
-    const uint32_t idesc = make_idesc(P.bn, P.fp16);
-    const uint64_t adesc_c = make_desc(0, a_chunk_bytes, 128);
-    const uint64_t bdesc_c = make_desc(0, (uint32_t)P.bn * 16u, 128);
-    const uint32_t b_tap_u = b_tap_bytes >> 4;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      mbar_wait(tempty0 + 8 * as, aphase ^ 1, P.err_flag, 2);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
-      uint32_t accum = 0;
-      for (int cp = 0; cp < P.ci_pairs; ++cp) {
-        mbar_wait(full0 + 8 * stage, phase, P.err_flag, 3);
-        tc_fence_after();
-        const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
-        const uint64_t ad0 = adesc_c + (uint64_t)(sa >> 4);
-        uint64_t bd = bdesc_c + (uint64_t)((sa + a_slot_bytes) >> 4);
-        if (leader) {
-          for (int j = 0; j < P.ntaps; ++j) {
-            const uint64_t ad = ad0 + (uint64_t)(uint32_t)s_off[j];
-            for (int sub = 0; sub < P.msub; ++sub)
-              umma_bf16(d_tmem + (uint32_t)(sub * P.bn), ad + (uint64_t)(sub * 128), bd, idesc, accum);
-            accum = 1;
-            bd += b_tap_u;
-          }
-          umma_commit(empty0 + 8 * stage);
-        }
-        accum = 1;
+        if (leader) umma_commit(tfull0 + 8 * as);
         __syncwarp();
-        if (++stage == S) {
-          stage = 0;
-          phase ^= 1;
+        if (++as == P.acc_stages) {
+          as = 0;
+          aphase ^= 1;
         }
       }
-      if (leader) umma_commit(tfull0 + 8 * as);
-      __syncwarp();
-      if (++as == P.acc_stages) {
-        as = 0;
-        aphase ^= 1;
-      }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp < 8) {
     // ===================================================================== epilogue (4 warps, one per lane group)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     epilogue_role(P, tmem_base, tfull0, tempty0, warp & 3, 0, 1, lane, tile_rows, acc_cols);
-  } else if (warp >= 8) {
+  } else {
     // ===================================================================== snake warps
     const int stid = threadIdx.x - 256;
-    const int e2 = stid & 7, g = stid >> 3;       // channel pair (0..7 over the two chunks), row group (0..31)
-    const int csel = e2 >> 2, pc = e2 & 3;
-    float2 fu[12], fd[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) {
-      const float fk = __ldg(P.sn_filt + k);
-      fu[k] = make_float2(2.0f * fk, 2.0f * fk);
-      fd[k] = make_float2(fk, fk);
-    }
+    const int pc = stid & 7, g = stid >> 3;       // channel pair (0..7 over the two chunks), row group (0..47)
+    const int csel = pc >> 2, pcl = pc & 3;
+    const int np = P.wrows + 6;                   // 2x-rate positions needed per window
     int stage = 0, phase = 0, xs = 0, xph = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const TileCoord tc = decode_tile(P, tile);
-      const int t_slot0 = tc.mt * tile_rows + mn;  // time of A-slot row 0; raw window row 0 is t_slot0 - 5
-      const bool edge = (t_slot0 - 5 < 0) || (t_slot0 + 32 * R + 5 > P.L);
-      const int q0 = t_slot0 + g * R;              // time of this thread's first output row
+      const int t_slot0 = tc.mt * tile_rows + mn;  // time of A-slot row 0; position 0 is t_slot0 - 3, raw row 0 is t_slot0 - 6
+      const bool edge = (t_slot0 - 6 < 0) || (t_slot0 + P.wrows + 6 > P.L);
       for (int cp = 0; cp < P.ci_pairs; ++cp) {
-        const int c0 = cp * 16 + csel * 8 + 2 * pc;
-        const float2 al2 = make_float2(2.0f * __ldg(P.sn_a + c0), 2.0f * __ldg(P.sn_a + c0 + 1));
-        const float2 hib = make_float2(0.5f * __ldg(P.sn_ib + c0), 0.5f * __ldg(P.sn_ib + c0 + 1));
+        const bool active = !(P.ci_odd && cp == P.ci_pairs - 1 && csel == 1);
+        const int c0 = cp * 16 + csel * 8 + 2 * pcl;
+        const float2 par0 = s_par[c0], par1 = s_par[c0 + 1];
+        const float2 al2 = make_float2(par0.x, par1.x), hib = make_float2(par0.y, par1.y);
         const float2 nhib = make_float2(-hib.x, -hib.y);
+        // ---------------- phase 1: raw window -> 2x-rate snake samples in shared memory
+        // Straight-line code, no per-position guards: positions / rows beyond the window compute on stale (finite or
+        // not, never consumed) shared memory and land in padding rows that nothing reads.
         mbar_wait(xfull0 + 8 * xs, xph, P.err_flag, 6);
-        const float* xw = reinterpret_cast<const float*>(smem + 1024 + (size_t)xs * P.xs_bytes + (size_t)csel * x_chunk_bytes) +
-                          2 * pc;
-        float2 xv[R + 10];
-        if (!edge) {
+        float2 xv[kSR + 6];
+        {
+          const float* xw = reinterpret_cast<const float*>(xs_ptr + (size_t)xs * xs_bytes + (size_t)csel * x_chunk_bytes) + 2 * pcl;
+          if (!edge) {
 #pragma unroll
-          for (int j = 0; j < R + 10; ++j) xv[j] = *reinterpret_cast<const float2*>(xw + (g * R + j) * 8);
-        } else {  // replicate pad: rows t < 0 read x[0], rows t >= L read x[L-1]
+            for (int j = 0; j < kSR + 6; ++j) xv[j] = *reinterpret_cast<const float2*>(xw + (g * kSR + j) * 8);
+          } else {  // replicate pad: rows t < 0 read x[0], rows t >= L read x[L-1]
 #pragma unroll
-          for (int j = 0; j < R + 10; ++j) {
-            int t = q0 - 5 + j;
-            t = min(max(t, 0), P.L - 1);
-            int i = t - (t_slot0 - 5);
-            i = min(max(i, 0), P.xrows - 1);
-            xv[j] = *reinterpret_cast<const float2*>(xw + i * 8);
+            for (int j = 0; j < kSR + 6; ++j) {
+              int t = t_slot0 - 6 + g * kSR + j;
+              t = min(max(t, 0), P.L - 1);
+              xv[j] = *reinterpret_cast<const float2*>(xw + (t - (t_slot0 - 6)) * 8);
+            }
           }
         }
         __syncwarp();
@@ -669,52 +719,83 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tc_conv_snake_kernel(const _
           xs = 0;
           xph ^= 1;
         }
-        float2 sv[2 * R + 10];
+        asm volatile("bar.sync 1, %0;" ::"n"(kSnakeThreads) : "memory");  // phase 2 of the previous stage has read the 2x buffer
+        if (active) {
+          float fu[12];
 #pragma unroll
-        for (int i = 0; i < 2 * R + 10; ++i) {
-          const int qq = (i - 5) >> 1;
-          float2 u = make_float2(0.f, 0.f);
-          if ((i & 1) == 0) {
+          for (int k = 0; k < 12; ++k) fu[k] = 2.0f * s_filt[k];
+          float2 ue[kSR], uo[kSR];
 #pragma unroll
-            for (int d = -2; d <= 3; ++d) u = tc_ffma2(xv[qq + d + 5], fu[6 - 2 * d], u);
+          for (int j = 0; j < kSR; ++j) {
+            ue[j] = tc_fmul2(xv[j], make_float2(fu[11], fu[11]));       // d = -3
+            uo[j] = tc_fmul2(xv[j + 1], make_float2(fu[10], fu[10]));   // d = -2
+          }
+#pragma unroll
+          for (int d = -2; d <= 2; ++d) {
+#pragma unroll
+            for (int j = 0; j < kSR; ++j) ue[j] = tc_ffma2(xv[j + 3 + d], make_float2(fu[5 - 2 * d], fu[5 - 2 * d]), ue[j]);
+          }
+#pragma unroll
+          for (int d = -1; d <= 3; ++d) {
+#pragma unroll
+            for (int j = 0; j < kSR; ++j) uo[j] = tc_ffma2(xv[j + 3 + d], make_float2(fu[6 - 2 * d], fu[6 - 2 * d]), uo[j]);
+          }
+          float* sw = reinterpret_cast<float*>(sbuf_ptr + (size_t)csel * (kSrPad * 32)) + 2 * pcl + (2 * g * kSR) * 8;
+#pragma unroll
+          for (int j = 0; j < kSR; ++j) {
+            const float2 ze = tc_fmul2(ue[j], al2), zo = tc_fmul2(uo[j], al2);
+            const float2 ce = make_float2(__cosf(ze.x), __cosf(ze.y)), co = make_float2(__cosf(zo.x), __cosf(zo.y));
+            *reinterpret_cast<float2*>(sw + (2 * j) * 8) = tc_ffma2(ce, nhib, ue[j]);
+            *reinterpret_cast<float2*>(sw + (2 * j + 1) * 8) = tc_ffma2(co, nhib, uo[j]);
+          }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kSnakeThreads) : "memory");  // the 2x-rate buffer is complete
+        // ---------------- phase 2: down-filter -> 16-bit rows of the A slot
+        mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 7);  // the MMAs that last read this A slot retired
+        if (active) {
+          const float* sw = reinterpret_cast<const float*>(sbuf_ptr + (size_t)csel * (kSrPad * 32)) + 2 * pcl;
+          const int i0 = 2 * g * kSR + 1;  // buffer row i holds s[2 (t_slot0 - 3) + i]; row r needs i = 2r + 1 .. 2r + 12
+          float2 sv[2 * kSR + 10];
+          if (!edge) {
+#pragma unroll
+            for (int ii = 0; ii < 2 * kSR + 10; ++ii) sv[ii] = *reinterpret_cast<const float2*>(sw + (i0 + ii) * 8);
+          } else {  // replicate clamp of the 2x-rate signal: s[m < 0] = s[0], s[m > 2L-1] = s[2L-1]
+            const int mb = 2 * (t_slot0 - 3);
+#pragma unroll
+            for (int ii = 0; ii < 2 * kSR + 10; ++ii) {
+              int m = mb + i0 + ii;
+              m = min(max(m, 0), 2 * P.L - 1);
+              int i = m - mb;
+              i = min(max(i, 0), kSrPad - 1);
+              sv[ii] = *reinterpret_cast<const float2*>(sw + i * 8);
+            }
+          }
+          float2 acc[kSR];
+#pragma unroll
+          for (int j = 0; j < kSR; ++j) acc[j] = hib;
+#pragma unroll
+          for (int k = 0; k < 12; ++k) {
+            const float fk = s_filt[k];
+#pragma unroll
+            for (int j = 0; j < kSR; ++j) acc[j] = tc_ffma2(make_float2(fk, fk), sv[2 * j + k], acc[j]);
+          }
+          const uint32_t a_dst = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes + (uint32_t)csel * a_chunk_bytes +
+                                 (uint32_t)(g * kSR) * 16u + (uint32_t)pcl * 4u;
+          const int t0 = t_slot0 + g * kSR;
+          uint32_t hv[kSR];
+          if (P.fp16) {  // block-uniform
+#pragma unroll
+            for (int j = 0; j < kSR; ++j) hv[j] = fh::pack16(acc[j].x, acc[j].y, 1);
           } else {
 #pragma unroll
-            for (int d = -3; d <= 2; ++d) u = tc_ffma2(xv[qq + d + 5], fu[5 - 2 * d], u);
+            for (int j = 0; j < kSR; ++j) hv[j] = fh::pack16(acc[j].x, acc[j].y, 0);
           }
-          const float2 z = tc_fmul2(u, al2);
-          const float2 c = make_float2(__cosf(z.x), __cosf(z.y));
-          sv[i] = tc_ffma2(c, nhib, u);
-        }
-        if (edge) {  // replicate clamp of the 2x-rate signal: s[m < 0] = s[0], s[m > 2L-1] = s[2L-1]
-          const int i_lo = 5 - 2 * q0, i_hi = 2 * (P.L - q0) + 4;
-          if (i_hi >= 0 && i_hi < 2 * R + 10 - 1) {
-            float2 prev = sv[0];
 #pragma unroll
-            for (int i = 0; i < 2 * R + 10; ++i) {
-              if (i <= i_hi) prev = sv[i];
-              else sv[i] = prev;
-            }
+          for (int j = 0; j < kSR; ++j) {
+            const unsigned tt = (unsigned)(t0 + j);
+            const uint32_t v = tt < (unsigned)P.L ? hv[j] : 0u;  // conv zero padding outside [0, L)
+            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_dst + (uint32_t)j * 16u), "r"(v) : "memory");
           }
-          if (i_lo > 0 && i_lo <= 2 * R + 10 - 1) {
-            float2 nxt = sv[2 * R + 9];
-#pragma unroll
-            for (int i = 2 * R + 9; i >= 0; --i) {
-              if (i >= i_lo) nxt = sv[i];
-              else sv[i] = nxt;
-            }
-          }
-        }
-        mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 7);  // the MMAs that last read this A slot retired
-        const uint32_t a_dst = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes + (uint32_t)csel * a_chunk_bytes +
-                               (uint32_t)(g * R) * 16u + (uint32_t)pc * 4u;
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-          float2 acc = hib;
-#pragma unroll
-          for (int k = 0; k < 12; ++k) acc = tc_ffma2(fd[k], sv[2 * j + k], acc);
-          const int t = q0 + j;
-          const uint32_t v = (t >= 0 && t < P.L) ? fh::pack16(acc.x, acc.y, P.fp16) : 0u;  // conv zero padding
-          asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_dst + (uint32_t)j * 16u), "r"(v) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
@@ -768,15 +849,15 @@ __global__ void to_chunked_bf16_kernel(const float* __restrict__ src, long long 
 
 // ================================================================================ C ABI
 extern "C" __attribute__((visibility("default"))) int64_t fh_tc_packed_weight_bytes(int Cin, int Cout, int ntaps, int P, int bn) {
-  if (Cin <= 0 || Cout <= 0 || ntaps <= 0 || P <= 0 || bn <= 0 || (Cin % 16) || (bn % 16)) return -1;
+  if (Cin <= 0 || Cout <= 0 || ntaps <= 0 || P <= 0 || bn <= 0 || (Cin % 8) || (bn % 16)) return -1;
   const int64_t n_tiles = (Cout + bn - 1) / bn;
-  return (int64_t)P * n_tiles * (Cin / 16) * ntaps * bn * 32;
+  return (int64_t)P * n_tiles * ((Cin + 15) / 16) * ntaps * bn * 32;
 }
 
 extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_conv_args* a, void* stream) {
   FH_REQUIRE(a != nullptr, FH_ERR_BAD_SHAPE, "fh_tc_conv: null args");
   FH_REQUIRE(a->B > 0 && a->L > 0 && a->Cin > 0 && a->Cout > 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: bad shape");
-  FH_REQUIRE(a->Cin % 16 == 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: Cin=%d must be a multiple of 16", a->Cin);
+  FH_REQUIRE(a->Cin % 8 == 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: Cin=%d must be a multiple of 8", a->Cin);
   FH_REQUIRE(a->Cout % 8 == 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: Cout=%d must be a multiple of 8", a->Cout);
   FH_REQUIRE(a->bn % 16 == 0 && a->bn >= 16 && a->bn <= 256, FH_ERR_UNSUPPORTED_CFG,
              "fh_tc_conv: bn=%d must be a multiple of 16 in [16,256]", a->bn);
@@ -811,10 +892,8 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
   p.n_tiles = (a->Cout + a->bn - 1) / a->bn;
   const bool fused = a->x_f32 != nullptr;
   if (fused) {
-    FH_REQUIRE(a->P == 1 && p.n_tiles == 1 && a->bn <= 128 && a->ntaps * a->bn * 32 <= 48 * 1024 && a->sn_a &&
-                   a->sn_inv_b && a->sn_filt && !a->geglu,
-               FH_ERR_UNSUPPORTED_CFG,
-               "fh_tc_conv: fused snake needs P == 1, one N tile of <= 128 columns and ntaps*bn*32 <= 48 KB");
+    FH_REQUIRE(a->P == 1 && p.n_tiles == 1 && a->bn <= 128 && a->Cin <= 128 && a->sn_a && a->sn_inv_b && a->sn_filt && !a->geglu,
+               FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake needs P == 1 and one N tile of <= 128 columns");
     FH_REQUIRE(((uintptr_t)a->x_f32 % 16) == 0, FH_ERR_BAD_ALIGN, "fh_tc_conv: x_f32 must be 16-byte aligned");
   }
   // sub-tiles: reuse each weight slot for up to 4 x 128 rows when the accumulators fit TMEM twice over
@@ -830,17 +909,19 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
     const char* m = getenv("FH_TC_WIDE_MIN");
     if (m) wide_min = atoi(m);
   }
-  if (a->bn > 128 && wide_msub == 2 && (long long)a->ntaps * (a->Cin / 16) >= wide_min) msub = 2;
+  if (a->bn > 128 && wide_msub == 2 && (long long)a->ntaps * ((a->Cin + 15) / 16) >= wide_min) msub = 2;
   while (!fused && msub > 1 &&
          (long long)a->B * a->P * ((a->L + 128 * msub - 1) / (128 * msub)) * p.n_tiles < 2 * 148)
     msub >>= 1;
+  if (fused) msub = 2;  // 256-row tiles: the snake warps' two-phase window (tc_conv_snake_kernel) is sized for them
   p.msub = msub;
   p.acc_stages = (2 * msub * a->bn <= 512) ? 2 : 1;
   p.m_tiles = (a->L + 128 * msub - 1) / (128 * msub);
   const long long total = (long long)p.B * p.P * p.m_tiles * p.n_tiles;
   FH_REQUIRE(total < (1ll << 31), FH_ERR_BAD_SHAPE, "fh_tc_conv: too many tiles");
   p.total_tiles = (int)total;
-  p.ci_pairs = a->Cin / 16;
+  p.ci_pairs = (a->Cin + 15) / 16;
+  p.ci_odd = (a->Cin % 16) != 0;
   int span = 0;
   for (int ph = 0; ph < a->P; ++ph) {
     int mn = a->tap_off[ph * a->ntaps], mx = mn;
@@ -858,14 +939,12 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
   FH_REQUIRE(span <= kMaxSpan, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: tap span %d exceeds %d rows", span, kMaxSpan);
   p.wrows = 128 * msub + span;
   p.arows_pad = 128 * msub + kMaxSpan;
-  const int snake_R = msub == 4 ? 19 : 11;  // outputs per snake thread: 32*R rows cover 128*msub + span
   if (fused) {
-    FH_REQUIRE(msub == 2 || msub == 4, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake needs bn <= 128");
-    FH_REQUIRE(p.wrows <= 32 * snake_R, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake window too small");
-    FH_REQUIRE(a->a_row0 + p.min_off[0] - 5 >= 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: fused snake needs 5 more halo rows");
-    p.arows_pad = 32 * snake_R + 4;   // (rows*4 words) = 16 mod 32: the two chunks of a slot use disjoint banks
-    p.xrows = 32 * snake_R + 10;      // raw window rows (= 2 mod 4: same bank property for 32-byte rows)
-    p.xs_bytes = 2 * p.xrows * 32;
+    FH_REQUIRE(p.wrows + 6 <= kSnakeCap, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake window too small for this tap span");
+    FH_REQUIRE(a->a_row0 + p.min_off[0] - 6 >= 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: fused snake needs 6 more halo rows");
+    p.arows_pad = kArPad;
+    p.xrows = p.wrows + 12;  // raw rows needed: positions t_slot0 - 3 .. t_slot0 + wrows + 2, +-3 each
+    p.xs_bytes = 2 * kXrPad * 32;
     p.rows_per_chunk = (int)(a->a_chunk / 8);
     p.xf = a->x_f32, p.sn_a = a->sn_a, p.sn_ib = a->sn_inv_b, p.sn_filt = a->sn_filt;
   }
@@ -895,17 +974,19 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
   }
   const int budget = budget_kb * 1024;
   if (fused) {
+    const int fbudget = 220 * 1024;  // this kernel owns the SM
+    const int sbuf = 2 * kSrPad * 32;
     p.x_stages = 3;
-    int st = (budget - 1024 - p.x_stages * p.xs_bytes) / p.stage_bytes;
-    if (st < 2) {
+    int st = (fbudget - 2048 - sbuf - p.x_stages * p.xs_bytes) / p.stage_bytes;
+    if (st < 3) {
       p.x_stages = 2;
-      st = (budget - 1024 - p.x_stages * p.xs_bytes) / p.stage_bytes;
+      st = (fbudget - 2048 - sbuf - p.x_stages * p.xs_bytes) / p.stage_bytes;
     }
     FH_REQUIRE(st >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake stages do not fit shared memory");
-    p.stages = st > 3 ? 3 : st;
+    p.stages = st > 4 ? 4 : st;
     p.err_flag = nullptr;
-    const int fsmem = 1024 + p.x_stages * p.xs_bytes + p.stages * p.stage_bytes;
-    static int fsmem_set[2] = {0, 0};
+    const int fsmem = 2048 + sbuf + p.x_stages * p.xs_bytes + p.stages * p.stage_bytes;
+    static int fsmem_set = 0;
     static int fsms = 0;
     if (!fsms) {
       int dev = 0;
@@ -913,19 +994,14 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
       cudaDeviceGetAttribute(&fsms, cudaDevAttrMultiProcessorCount, dev);
       if (fsms <= 0) fsms = 148;
     }
-    const int which = msub == 4 ? 1 : 0;
-    if (fsmem > fsmem_set[which]) {
-      cudaError_t e = which ? cudaFuncSetAttribute(tc_conv_snake_kernel<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem)
-                            : cudaFuncSetAttribute(tc_conv_snake_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem);
+    if (fsmem > fsmem_set) {
+      cudaError_t e = cudaFuncSetAttribute(tc_conv_snake_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem);
       FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", fsmem,
                  cudaGetErrorString(e));
-      fsmem_set[which] = fsmem;
+      fsmem_set = fsmem;
     }
     const int fgrid = p.total_tiles < fsms ? p.total_tiles : fsms;
-    if (which)
-      tc_conv_snake_kernel<19><<<fgrid, kFusedThreads, fsmem, (cudaStream_t)stream>>>(p);
-    else
-      tc_conv_snake_kernel<11><<<fgrid, kFusedThreads, fsmem, (cudaStream_t)stream>>>(p);
+    tc_conv_snake_kernel<<<fgrid, kFusedThreads, fsmem, (cudaStream_t)stream>>>(p);
     return fh::check_launch("fh_tc_conv(fused snake)");
   }
   int stages = (budget - 1024) / p.stage_bytes;
@@ -943,14 +1019,23 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
+  static int lowreg = -1;
+  if (lowreg < 0) {
+    const char* e = getenv("FH_TC_LOWREG");
+    lowreg = e ? atoi(e) : 0;
+  }
   if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = lowreg ? cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                           : cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", smem,
                cudaGetErrorString(e));
     smem_set = smem;
   }
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  tc_conv_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  if (lowreg)
+    tc_conv_kernel<2><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  else
+    tc_conv_kernel<1><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
   return fh::check_launch("fh_tc_conv");
 }
 

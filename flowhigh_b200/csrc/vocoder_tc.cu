@@ -235,7 +235,13 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  const int grid = (int)(total < (long long)sms * 4 ? total : (long long)sms * 4);
+  static int per_sm = 0;  // persistent CTAs per SM (4 fill the SM; 2 leave room for a co-resident conv CTA)
+  if (!per_sm) {
+    const char* e = getenv("FH_SNAKE_CTAS_PER_SM");
+    per_sm = e ? atoi(e) : 4;
+    if (per_sm < 1 || per_sm > 4) per_sm = 4;
+  }
+  const int grid = (int)(total < (long long)sms * per_sm ? total : (long long)sms * per_sm);
 #define FH_SNAKE_LAUNCH(KIND)                                                                                \
   snake_aa_chunked_tma_kernel<KIND><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, a, inv_b, filt, batch_stride, \
                                                                            chunk_stride, row0, C / 8, L, ntile, (int)total)

@@ -194,7 +194,7 @@ class Engine:
     def _prep_vocoder(self):
         sd, v = self.sd, self.vcfg
         mk = self._mk_tc if self.tc else self._mk_f32
-        pad = (lambda c: packing.round_up(c, 16)) if self.tc else (lambda c: c)
+        pad = (lambda c: packing.round_up(c, 8)) if self.tc else (lambda c: c)  # whole 8-channel chunks
         self.cpad = pad
         V = {}
         C0 = v.upsample_initial_channel

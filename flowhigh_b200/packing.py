@@ -84,7 +84,7 @@ def pick_bn(cout_pad: int) -> int:
             if int(k) == cout_pad:
                 return int(v)
     if cout_pad <= 256:
-        return cout_pad
+        return round_up(cout_pad, 16)  # MMA N granularity at M = 128; surplus columns carry zero weights
     for bn in range(256, 127, -16):
         if cout_pad % bn == 0:
             return bn
@@ -99,14 +99,15 @@ def pack_tc(tc: TappedConv, device, cin_pad: Optional[int] = None, cout_pad: Opt
             bn: Optional[int] = None, dtype=torch.bfloat16) -> Tuple[torch.Tensor, int, int, int]:
     """-> (packed 16-bit tensor (bf16 or fp16), cin_pad, cout_pad, bn)."""
     P, ntaps, cout, cin = tc.w.shape
-    cin_pad = cin_pad or round_up(cin, 16)
-    cout_pad = cout_pad or round_up(cout, 16)
+    cin_pad = cin_pad or round_up(cin, 8)     # channel counts of the activation buffers: whole 8-channel chunks
+    cout_pad = cout_pad or round_up(cout, 8)
     bn = bn or pick_bn(cout_pad)
     n_tiles = -(-cout_pad // bn)
-    w = torch.zeros(P, ntaps, n_tiles * bn, cin_pad, dtype=torch.float32, device=tc.w.device)
+    cin16 = round_up(cin_pad, 16)             # the weight image always carries whole ci-pairs (K = 16 per MMA)
+    w = torch.zeros(P, ntaps, n_tiles * bn, cin16, dtype=torch.float32, device=tc.w.device)
     w[:, :, :cout, :cin] = tc.w
     # [P][tap][nt][bn][cp][2][8] -> [P][nt][cp][tap][2][bn][8]
-    w = w.reshape(P, ntaps, n_tiles, bn, cin_pad // 16, 2, 8).permute(0, 2, 4, 1, 5, 3, 6).contiguous()
+    w = w.reshape(P, ntaps, n_tiles, bn, cin16 // 16, 2, 8).permute(0, 2, 4, 1, 5, 3, 6).contiguous()
     return w.to(dtype).to(device), cin_pad, cout_pad, bn
 
 

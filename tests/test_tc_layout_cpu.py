@@ -15,7 +15,8 @@ HALO = 32
 def emulate_tc_conv(a_chunked, a_bs, a_cs, a_row0, packed, rec_off, P, ntaps, cin_pad, cout_pad, bn, B, L,
                     out, o_bs, o_cs, o_row, bias=None):
     """Follows tc_conv_kernel step by step (fp32 arithmetic on the bf16-rounded operands)."""
-    m_tiles, n_tiles, ci_pairs = -(-L // 128), -(-cout_pad // bn), cin_pad // 16
+    m_tiles, n_tiles, ci_pairs = -(-L // 128), -(-cout_pad // bn), -(-cin_pad // 16)
+    n_chunks = cin_pad // 8  # odd chunk count: the partner window of the last chunk is a zeroed smem region (ci_odd)
     a = a_chunked.float().numpy()
     w = packed.float().numpy().reshape(P, n_tiles, ci_pairs, ntaps, 2, bn, 8)
     for b in range(B):
@@ -30,6 +31,8 @@ def emulate_tc_conv(a_chunked, a_bs, a_cs, a_row0, packed, rec_off, P, ntaps, ci
                     for cp in range(ci_pairs):
                         slot = np.zeros((2, wrows, 8), np.float32)
                         for c in range(2):
+                            if 2 * cp + c >= n_chunks:
+                                continue
                             base = b * a_bs + (2 * cp + c) * a_cs + row * 8
                             slot[c] = a[base: base + wrows * 8].reshape(wrows, 8)
                         for j in range(ntaps):
@@ -86,7 +89,8 @@ def test_tc_addressing_matches_conv(kind):
         tc = packing.linear_taps(w, bias)
         ref = F.conv1d(x.bfloat16().float(), w.bfloat16().float()[:, :, None], bias)
     packed, cin_pad, cout_pad, bn = packing.pack_tc(tc, "cpu", bn=32)
-    assert packed.numel() * 2 == tc.P * (-(-cout_pad // bn)) * (cin_pad // 16) * tc.ntaps * bn * 32
+    assert cin_pad == 24 and cout_pad == 40  # whole 8-channel chunks; the weight image pads Cin to whole ci-pairs
+    assert packed.numel() * 2 == tc.P * (-(-cout_pad // bn)) * (-(-cin_pad // 16)) * tc.ntaps * bn * 32
     Lp_in = HALO + packing.round_up(L, 128) + 64
     Lo = L * tc.P
     Lp_out = HALO + packing.round_up(Lo, 128) + 64
