@@ -50,6 +50,10 @@ struct TcParams {
   int arows_pad;       // rows reserved per chunk window in an A slot
   int stages, stage_bytes;
   int min_off[16];
+  int tap_rel0[16];     // (offset of tap 0) - min_off of the phase
+  int tap_step[16];     // offset(tap j+1) - offset(tap j) when the taps of a phase form an arithmetic sequence
+  int v8;               // fp32 output / residual rows are 32-byte aligned: 256-bit epilogue accesses
+  int tap_arith;        // all phases arithmetic: the MMA issuer strides descriptors instead of reading the offset table
   int tap_off[kMaxTapOff];
   unsigned int* err_flag;
   // fused anti-aliased snake A-producer (tc_conv_snake_kernel): raw fp32 activations + per-channel parameters
@@ -156,6 +160,33 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int fp16) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// tcgen05.mma with the two shared-memory descriptors passed as (lo, hi) words: only the 14-bit start-address field of
+// the low word changes between taps / sub-tiles / stages, so the issue loop advances plain 32-bit values.
+__device__ __forceinline__ void umma_f16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 256-bit global accesses (sm_100: LDG/STG.256): one 8-channel fp32 row of a chunk is one full 32-byte sector per
+// lane instead of two half-sector requests
+__device__ __forceinline__ void ldg_v8(const float* p, float (&r)[8]) {
+  asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void stg_v8(float* p, const float (&r)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(r[0]), "f"(r[1]), "f"(r[2]), "f"(r[3]),
+               "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
+               : "memory");
+}
+
 struct TileCoord {
   int b, p, mt, nt;
 };
@@ -193,6 +224,11 @@ __device__ __forceinline__ void load_res16(const TcParams& P, long long rbase, i
         r[hh * 8 + 2 * i] = f.x;
         r[hh * 8 + 2 * i + 1] = f.y;
       }
+    } else if (P.v8) {
+      float t[8];
+      ldg_v8((const float*)P.res + ridx, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[hh * 8 + i] = t[i];
     } else {
       const float4* rp = reinterpret_cast<const float4*>((const float*)P.res + ridx);
       const float4 r0 = rp[0], r1 = rp[1];
@@ -289,6 +325,15 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
 #pragma unroll
           for (int i = 0; i < 4; ++i) h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
           *reinterpret_cast<uint4*>((unsigned short*)P.out + idx) = *reinterpret_cast<uint4*>(h);
+        } else if (P.v8) {
+          float* dst = (float*)P.out + idx;
+          if (P.accumulate) {
+            float t[8];
+            ldg_v8(dst, t);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] += t[i];
+          }
+          stg_v8(dst, o);
         } else {
           float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
           if (P.accumulate) {
@@ -324,6 +369,97 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+    if (++as == P.acc_stages) {
+      as = 0;
+      aphase ^= 1;
+    }
+  }
+}
+
+// MMA issuer role, shared by both kernels.  The ncu source page of the first version showed this warp, not the tensor
+// pipe, pacing every shape but the widest (~300 cycles of uniform-datapath work per MMA: an integer modulo per stage,
+// a shared-memory load + R2UR per tap, 64-bit descriptor arithmetic per MMA).  Here every per-stage and per-tap
+// quantity is a running 32-bit value: stage base, tap stride (taps of a phase are an arithmetic sequence for Conv1d,
+// dilated Conv1d and polyphase ConvTranspose1d), weight stride; the sub-tile loop is specialised outside the tap loop.
+template <int MSUB>
+__device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t bn, uint32_t a_lo, uint32_t a_step, uint32_t b_lo,
+                                           uint32_t b_step, uint32_t hi, uint32_t idesc, uint32_t accum, int ntap) {
+#pragma unroll 1
+  for (int j = 0; j < ntap; ++j) {
+#pragma unroll
+    for (int sub = 0; sub < MSUB; ++sub)
+      umma_f16_split(d_tmem + (uint32_t)sub * bn, a_lo + (uint32_t)sub * 128u, hi, b_lo, hi, idesc, accum);
+    accum = 1;
+    a_lo += a_step;
+    b_lo += b_step;
+  }
+}
+
+__device__ __forceinline__ void mma_role(const TcParams& P, uint32_t tmem_base, uint32_t full0, uint32_t empty0,
+                                         uint32_t tfull0, uint32_t tempty0, uint32_t stage0, uint32_t a_chunk_bytes,
+                                         const int* s_off) {
+  const bool leader = elect_one();
+  int stage = 0, phase = 0, as = 0, aphase = 0;
+  const int S = P.stages, msub = P.msub, ntaps = P.ntaps, tg = P.tg, n_groups = P.n_groups, ci_pairs = P.ci_pairs;
+  const uint32_t bn = (uint32_t)P.bn;
+  const uint32_t idesc = make_idesc(P.bn, P.fp16);
+  const uint32_t hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1 (bit 46)
+  const uint32_t a_lbo = (a_chunk_bytes >> 4) << 16;            // LBO fields (bits 16..29 of the low word)
+  const uint32_t b_lbo = ((bn * 16u) >> 4) << 16;
+  const uint32_t b_step = (bn * 32u) >> 4;                      // one tap of weights
+  const uint32_t a_slot_u = (2u * a_chunk_bytes) >> 4;
+  const uint32_t stage_u = (uint32_t)P.stage_bytes >> 4, stage0_u = stage0 >> 4;
+  const uint32_t acc_cols = (uint32_t)(P.msub * P.bn);
+  const bool one_phase = P.P == 1;
+  uint32_t rel0 = (uint32_t)P.tap_rel0[0], a_step = (uint32_t)P.tap_step[0];
+  for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    int ph = 0;
+    if (!one_phase) {
+      ph = decode_tile(P, tile).p;
+      rel0 = (uint32_t)P.tap_rel0[ph];
+      a_step = (uint32_t)P.tap_step[ph];
+    }
+    mbar_wait(tempty0 + 8 * as, aphase ^ 1, P.err_flag, 2);
+    tc_fence_after();
+    const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
+    uint32_t accum = 0;
+    for (int cp = 0; cp < ci_pairs; ++cp) {
+      int tap0 = 0;
+      for (int g = 0; g < n_groups; ++g, tap0 += tg) {
+        const int nt_g = min(tg, ntaps - tap0);
+        mbar_wait(full0 + 8 * stage, phase, P.err_flag, 3);
+        tc_fence_after();
+        const uint32_t sa_u = stage0_u + (uint32_t)stage * stage_u;
+        if (leader) {
+          const uint32_t b_lo = b_lbo | (sa_u + a_slot_u);
+          if (P.tap_arith) {
+            const uint32_t a_lo = a_lbo | (sa_u + rel0 + (uint32_t)tap0 * a_step);
+            if (msub == 2) issue_taps<2>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
+            else if (msub == 4) issue_taps<4>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
+            else issue_taps<1>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
+          } else {  // irregular tap offsets: table in shared memory
+            const int* offs = s_off + ph * ntaps + tap0;
+            uint32_t bl = b_lo, acc = accum;
+            for (int j = 0; j < nt_g; ++j) {
+              const uint32_t a_lo = a_lbo | (sa_u + (uint32_t)offs[j]);
+              for (int sub = 0; sub < msub; ++sub)
+                umma_f16_split(d_tmem + (uint32_t)sub * bn, a_lo + (uint32_t)sub * 128u, hi, bl, hi, idesc, acc);
+              acc = 1;
+              bl += b_step;
+            }
+          }
+          umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
+        }
+        accum = 1;
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    if (leader) umma_commit(tfull0 + 8 * as);  // accumulator complete -> epilogue
+    __syncwarp();
     if (++as == P.acc_stages) {
       as = 0;
       aphase ^= 1;
@@ -421,55 +557,7 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    // The whole warp walks the (warp-uniform) loops so that descriptors stay in uniform registers;
-    // only the tcgen05.mma / tcgen05.commit instructions are predicated on one elected lane.
-    const bool leader = elect_one();
-    int stage = 0, phase = 0, as = 0, aphase = 0;
-    const uint32_t idesc = make_idesc(P.bn, P.fp16);
-    const uint64_t adesc_c = make_desc(0, a_chunk_bytes, 128);
-    const uint64_t bdesc_c = make_desc(0, (uint32_t)P.bn * 16u, 128);
-    const uint32_t b_tap_u = b_tap_bytes >> 4;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(P, tile);
-      mbar_wait(tempty0 + 8 * as, aphase ^ 1, P.err_flag, 2);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
-      const int* offs = s_off + tc.p * P.ntaps;  // (tap offset - min offset): rows == 16-byte descriptor units
-      uint32_t accum = 0;
-      for (int step = 0; step < steps_per_tile; ++step) {
-        const int g = step % P.n_groups;
-        const int tap0 = g * P.tg;
-        const int nt_g = min(P.tg, P.ntaps - tap0);
-        mbar_wait(full0 + 8 * stage, phase, P.err_flag, 3);
-        tc_fence_after();
-        const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
-        const uint64_t ad0 = adesc_c + (uint64_t)(sa >> 4);
-        uint64_t bd = bdesc_c + (uint64_t)((sa + a_slot_bytes) >> 4);
-        if (leader) {
-          for (int j = 0; j < nt_g; ++j) {
-            // the tap shift and the 128-row sub-tile are both plain start-address offsets
-            const uint64_t ad = ad0 + (uint64_t)(uint32_t)offs[tap0 + j];
-            for (int sub = 0; sub < P.msub; ++sub)
-              umma_bf16(d_tmem + (uint32_t)(sub * P.bn), ad + (uint64_t)(sub * 128), bd, idesc, accum);
-            accum = 1;
-            bd += b_tap_u;
-          }
-          umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
-        }
-        accum = 1;
-        __syncwarp();
-        if (++stage == S) {
-          stage = 0;
-          phase ^= 1;
-        }
-      }
-      if (leader) umma_commit(tfull0 + 8 * as);  // accumulator complete -> epilogue
-      __syncwarp();
-      if (++as == P.acc_stages) {
-        as = 0;
-        aphase ^= 1;
-      }
-    }
+    mma_role(P, tmem_base, full0, empty0, tfull0, tempty0, stage0, a_chunk_bytes, s_off);
   } else {
     // ===================================================================== epilogue (warps 2..9)
     epilogue_role(P, tmem_base, tfull0, tempty0, warp & 3, (warp - 2) >> 2, 2, lane, tile_rows, acc_cols);
@@ -631,47 +719,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tc_conv_snake_kernel(const _
       }
     } else if (warp == 1) {
       // ===================================================================== MMA issuer (one stage = one ci-pair)
-      const bool leader = elect_one();
-      int stage = 0, phase = 0, as = 0, aphase = 0;
-      const uint32_t idesc = make_idesc(P.bn, P.fp16);
-      const uint64_t adesc_c = make_desc(0, a_chunk_bytes, 128);
-      const uint64_t bdesc_c = make_desc(0, (uint32_t)P.bn * 16u, 128);
-      const uint32_t b_tap_u = b_tap_bytes >> 4;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        mbar_wait(tempty0 + 8 * as, aphase ^ 1, P.err_flag, 2);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
-        uint32_t accum = 0;
-        for (int cp = 0; cp < P.ci_pairs; ++cp) {
-          mbar_wait(full0 + 8 * stage, phase, P.err_flag, 3);
-          tc_fence_after();
-          const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
-          const uint64_t ad0 = adesc_c + (uint64_t)(sa >> 4);
-          uint64_t bd = bdesc_c + (uint64_t)((sa + a_slot_bytes) >> 4);
-          if (leader) {
-            for (int j = 0; j < P.ntaps; ++j) {
-              const uint64_t ad = ad0 + (uint64_t)(uint32_t)s_off[j];
-              for (int sub = 0; sub < P.msub; ++sub)
-                umma_bf16(d_tmem + (uint32_t)(sub * P.bn), ad + (uint64_t)(sub * 128), bd, idesc, accum);
-              accum = 1;
-              bd += b_tap_u;
-            }
-            umma_commit(empty0 + 8 * stage);
-          }
-          accum = 1;
-          __syncwarp();
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1;
-          }
-        }
-        if (leader) umma_commit(tfull0 + 8 * as);
-        __syncwarp();
-        if (++as == P.acc_stages) {
-          as = 0;
-          aphase ^= 1;
-        }
-      }
+      mma_role(P, tmem_base, full0, empty0, tfull0, tempty0, stage0, a_chunk_bytes, s_off);
     }
   } else if (warp < 8) {
     // ===================================================================== epilogue (4 warps, one per lane group)
@@ -922,7 +970,7 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
   p.total_tiles = (int)total;
   p.ci_pairs = (a->Cin + 15) / 16;
   p.ci_odd = (a->Cin % 16) != 0;
-  int span = 0;
+  int span = 0, arith = 1;
   for (int ph = 0; ph < a->P; ++ph) {
     int mn = a->tap_off[ph * a->ntaps], mx = mn;
     for (int m = 0; m < a->ntaps; ++m) {
@@ -932,11 +980,28 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
       mx = o > mx ? o : mx;
     }
     p.min_off[ph] = mn;
+    p.tap_rel0[ph] = a->tap_off[ph * a->ntaps] - mn;
+    p.tap_step[ph] = a->ntaps > 1 ? a->tap_off[ph * a->ntaps + 1] - a->tap_off[ph * a->ntaps] : 0;
+    for (int m = 1; m < a->ntaps; ++m)
+      if (a->tap_off[ph * a->ntaps + m] - a->tap_off[ph * a->ntaps + m - 1] != p.tap_step[ph]) arith = 0;
     span = (mx - mn) > span ? (mx - mn) : span;
     FH_REQUIRE(a->a_row0 + mn >= 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: left halo %d too small for tap offset %d",
                a->a_row0, mn);
   }
   FH_REQUIRE(span <= kMaxSpan, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: tap span %d exceeds %d rows", span, kMaxSpan);
+  p.tap_arith = arith;
+  {
+    static int use_v8 = -1;
+    if (use_v8 < 0) {
+      const char* e = getenv("FH_TC_V8");
+      use_v8 = e ? atoi(e) : 1;
+    }
+    const bool out_ok = a->out_is_16 || (((uintptr_t)a->out % 32) == 0 && a->out_batch % 8 == 0 && a->out_chunk % 8 == 0 &&
+                                         a->out_row % 8 == 0);
+    const bool res_ok = a->res == nullptr || a->res_is_16 ||
+                        (((uintptr_t)a->res % 32) == 0 && a->res_batch % 8 == 0 && a->res_chunk % 8 == 0 && a->res_row % 8 == 0);
+    p.v8 = (use_v8 && out_ok && res_ok) ? 1 : 0;
+  }
   p.wrows = 128 * msub + span;
   p.arows_pad = 128 * msub + kMaxSpan;
   if (fused) {

@@ -66,12 +66,16 @@ __device__ __forceinline__ void pbulk_g2s(uint32_t dst, const void* src, uint32_
                : "memory");
 }
 
-template <int OUT_KIND>
+// BULK_OUT (16-bit outputs): the 17 x 4-byte pieces a thread produces go to a shared-memory image of the output tile
+// (544 rows x 16 B, contiguous in HBM) which one cp.async.bulk store writes as whole lines, instead of 17 scattered
+// half-sector global stores per thread.
+template <int OUT_KIND, bool BULK_OUT>
 __global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(
     const float* __restrict__ x, void* __restrict__ y, const float* __restrict__ a, const float* __restrict__ inv_b,
     const float* __restrict__ filt, long long batch_stride, long long chunk_stride, int row0, int nchunk, int L,
     int ntile, int total) {
   __shared__ __align__(128) float xs[2][PXR * 8];
+  __shared__ __align__(128) unsigned char ys[BULK_OUT ? PTT * 16 : 16];
   __shared__ __align__(8) unsigned long long bars[2];
   const uint32_t bar0 = sm_u32(&bars[0]);
   if (threadIdx.x == 0) {
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(
     const float* xp = xt + g * (PR * 8) + 2 * e2;
 #pragma unroll
     for (int j = 0; j < PR + 10; ++j) xv[j] = *reinterpret_cast<const float2*>(xp + j * 8);
+    if (BULK_OUT && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // ys is free again
     __syncthreads();  // every thread has read this buffer's window
     if (threadIdx.x == 0 && item + (int)gridDim.x < total) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -175,15 +180,31 @@ __global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(
           float2 acc = hib;
 #pragma unroll
           for (int k = 0; k < 12; ++k) acc = ffma2(fd[k], s[2 * j + k], acc);
-          if (OUT_KIND)
+          if (BULK_OUT)
+            *reinterpret_cast<uint32_t*>(ys + (size_t)(g * PR + j) * 16 + 4 * e2) = fh::pack16(acc.x, acc.y, OUT_KIND == 2);
+          else if (OUT_KIND)
             *reinterpret_cast<uint32_t*>((unsigned short*)y + obase + j * 8) = fh::pack16(acc.x, acc.y, OUT_KIND == 2);
           else
             *reinterpret_cast<float2*>((float*)y + obase + j * 8) = acc;
         }
       }
     }
+    if (BULK_OUT) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int nrows = min(PTT, L - qt);
+        const unsigned short* dst =
+            (const unsigned short*)y + (long long)b * batch_stride + (long long)ch * chunk_stride + (long long)(row0 + qt) * 8;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sm_u32(ys)),
+                     "r"((uint32_t)nrows * 16u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
     buf ^= 1;
   }
+  if (BULK_OUT && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 __global__ void convpost_tanh_chunked_kernel(const float* __restrict__ x, long long batch_stride,
@@ -242,12 +263,19 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
     if (per_sm < 1 || per_sm > 4) per_sm = 4;
   }
   const int grid = (int)(total < (long long)sms * per_sm ? total : (long long)sms * per_sm);
-#define FH_SNAKE_LAUNCH(KIND)                                                                                \
-  snake_aa_chunked_tma_kernel<KIND><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, a, inv_b, filt, batch_stride, \
-                                                                           chunk_stride, row0, C / 8, L, ntile, (int)total)
-  if (out_kind == 0) FH_SNAKE_LAUNCH(0);
-  else if (out_kind == 1) FH_SNAKE_LAUNCH(1);
-  else FH_SNAKE_LAUNCH(2);
+  static int bulk = -1;
+  if (bulk < 0) {
+    const char* e = getenv("FH_SNAKE_BULK");
+    bulk = e ? atoi(e) : 1;
+  }
+#define FH_SNAKE_LAUNCH(KIND, BULK)                                                                                \
+  snake_aa_chunked_tma_kernel<KIND, BULK><<<grid, 128, 0, (cudaStream_t)stream>>>(x, y, a, inv_b, filt, batch_stride, \
+                                                                                 chunk_stride, row0, C / 8, L, ntile, (int)total)
+  if (out_kind == 0) FH_SNAKE_LAUNCH(0, false);
+  else if (out_kind == 1 && bulk) FH_SNAKE_LAUNCH(1, true);
+  else if (out_kind == 1) FH_SNAKE_LAUNCH(1, false);
+  else if (bulk) FH_SNAKE_LAUNCH(2, true);
+  else FH_SNAKE_LAUNCH(2, false);
 #undef FH_SNAKE_LAUNCH
   return fh::check_launch("fh_snake_aa_chunked");
 }

@@ -325,7 +325,8 @@ class Engine:
         e1.record(torch.cuda.current_stream(self.device))
         self.profile.append(("fh_tc_conv", e0, e1,
                              {"flops": flops, "bytes": float(nbytes),
-                              "tag": f"tc_conv{'+snake' if xf is not None else ''}[Cin{rec.cin},Cout{rec.cout},k{rec.ntaps}x{rec.P}]"}))
+                              "tag": f"tc_conv{'+snake' if xf is not None else ''}[Cin{rec.cin},Cout{rec.cout},k{rec.ntaps}x{rec.P}"
+                                     f"{',res' if res is not None else ''}]"}))
 
     def _sgemm(self, A, lda, W, ldw, bias, res, ldr, beta, alpha, out, ldc, M, N, K):
         self._call("fh_sgemm_nt_f32", A.data_ptr(), lda, W.data_ptr() if isinstance(W, torch.Tensor) else W, ldw,

@@ -83,9 +83,17 @@ def pick_bn(cout_pad: int) -> int:
             k, v = item.split(":")
             if int(k) == cout_pad:
                 return int(v)
-    if cout_pad <= 256:
+    # Measured on B200 once the MMA issue loop stopped pacing the kernel (gpurun_out/bd5_*.json): accumulators that fit
+    # TMEM twice (2 sub-tiles x bn <= 256 columns) so the epilogue overlaps the next tile beat the wider single-buffered
+    # tiles for 192 and 384 output channels (-12 % / -21 %); 768 keeps 3 x 256.
+    if cout_pad <= 128:
         return round_up(cout_pad, 16)  # MMA N granularity at M = 128; surplus columns carry zero weights
-    for bn in range(256, 127, -16):
+    if cout_pad <= 256:
+        half = cout_pad // 2
+        return half if cout_pad % 32 == 0 else round_up(cout_pad, 16)
+    if cout_pad % 256 == 0:
+        return 256
+    for bn in (128, 192, 160, 176, 144, 224, 208, 240):
         if cout_pad % bn == 0:
             return bn
     return 256
