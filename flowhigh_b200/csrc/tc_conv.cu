@@ -52,6 +52,7 @@ struct TcParams {
   int min_off[16];
   int tap_rel0[16];     // (offset of tap 0) - min_off of the phase
   int tap_step[16];     // offset(tap j+1) - offset(tap j) when the taps of a phase form an arithmetic sequence
+  int fast_epi;         // epilogue_fast applies (bias table in shared memory behind the stages)
   int v8;               // fp32 output / residual rows are 32-byte aligned: 256-bit epilogue accesses
   int tap_arith;        // all phases arithmetic: the MMA issuer strides descriptors instead of reading the offset table
   int tap_off[kMaxTapOff];
@@ -376,6 +377,112 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
   }
 }
 
+// Specialised epilogue for the hot vocoder / backbone shapes: fp32 output and residual in 32-byte-aligned rows, no GEGLU.
+// The generic role above spends ~210 instructions per 16-column group (per-element __ldg of the bias, runtime flag tests);
+// ncu showed the eight epilogue warps -- not HBM -- pacing the HBM-bound C <= 96 stages.  Here the bias (pre-multiplied by
+// alpha) comes from a shared-memory table with broadcast 128-bit loads, the flags are template parameters, and a group
+// costs ~45 instructions:  o = fma(acc, alpha, alpha * bias) [+ beta * residual] [+ previous output].
+template <bool HAS_RES, bool ACCUM>
+__device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                              int lane_grp, int half, int gstep, int lane, int tile_rows, uint32_t acc_cols,
+                                              const float* s_bias) {
+  const int r = lane_grp * 32 + lane;
+  int as = 0, aphase = 0;
+  const int groups_per_sub = P.bn >> 4;
+  const int n_groups_total = P.msub * groups_per_sub;
+  const float alpha = P.alpha, beta = P.beta_res;
+  const float* resp = (const float*)P.res;
+  float* outp = (float*)P.out;
+  for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    const TileCoord tc = decode_tile(P, tile);
+    const int n_base = tc.nt * P.bn;
+    const int t_base = tc.mt * tile_rows + r;
+    const long long res_b = (long long)tc.b * P.res_batch + (long long)tc.p * P.res_row;
+    const long long out_b = (long long)tc.b * P.out_batch + (long long)tc.p * P.out_row;
+    const long long res_rs = (long long)P.P * P.res_row, out_rs = (long long)P.P * P.out_row;
+    const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)as * acc_cols;
+
+    auto coords = [&](int gi, int& c0, int& t) {
+      const int sub = gi / groups_per_sub;
+      c0 = (gi - sub * groups_per_sub) << 4;
+      t = t_base + sub * 128;
+      return (uint32_t)(sub * P.bn + c0);
+    };
+    auto prefetch = [&](int gi, float (&rr)[16], float (&pp)[16]) {
+      if (gi >= n_groups_total) return;
+      int c0, t;
+      coords(gi, c0, t);
+      const int n0 = n_base + c0;
+      if (n0 >= P.Cout || t >= P.L) return;
+      const bool two = n0 + 8 < P.Cout;
+      if (HAS_RES) {
+        const float* q = resp + res_b + (long long)t * res_rs + (long long)(n0 >> 3) * P.res_chunk;
+        ldg_v8(q, *reinterpret_cast<float(*)[8]>(&rr[0]));
+        if (two) ldg_v8(q + P.res_chunk, *reinterpret_cast<float(*)[8]>(&rr[8]));
+      }
+      if (ACCUM) {
+        const float* q = outp + out_b + (long long)t * out_rs + (long long)(n0 >> 3) * P.out_chunk;
+        ldg_v8(q, *reinterpret_cast<float(*)[8]>(&pp[0]));
+        if (two) ldg_v8(q + P.out_chunk, *reinterpret_cast<float(*)[8]>(&pp[8]));
+      }
+    };
+    auto issue_ld = [&](int gi, uint32_t (&v)[16]) {
+      if (gi >= n_groups_total) return;
+      int c0, t;
+      const uint32_t col = coords(gi, c0, t);
+      if (n_base + c0 < P.Cout) tmem_ld16(taddr + col, v);  // warp-uniform
+    };
+    auto finish = [&](int gi, const uint32_t (&v)[16], const float (&rr)[16], const float (&pp)[16]) {
+      int c0, t;
+      coords(gi, c0, t);
+      const int n0 = n_base + c0;
+      if (n0 >= P.Cout || t >= P.L) return;
+      float* dst = outp + out_b + (long long)t * out_rs + (long long)(n0 >> 3) * P.out_chunk;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        if (hh == 1 && n0 + 8 >= P.Cout) break;
+        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n0 + hh * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n0 + hh * 8 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          o[i] = fmaf(__uint_as_float(v[hh * 8 + i]), alpha, bb[i]);
+          if (HAS_RES) o[i] = fmaf(beta, rr[hh * 8 + i], o[i]);
+          if (ACCUM) o[i] += pp[hh * 8 + i];
+        }
+        stg_v8(dst + (long long)hh * P.out_chunk, o);
+      }
+    };
+
+    uint32_t va[16], vb[16];
+    float ra[16], rb[16], pa[16], pb[16];
+    prefetch(half, ra, pa);  // requested BEFORE waiting for the accumulator
+    mbar_wait(tfull0 + 8 * as, aphase, P.err_flag, 4);
+    tc_fence_after();
+    issue_ld(half, va);
+    for (int gi = half; gi < n_groups_total; gi += 2 * gstep) {
+      tmem_ld_wait();
+      issue_ld(gi + gstep, vb);
+      prefetch(gi + gstep, rb, pb);
+      finish(gi, va, ra, pa);
+      if (gi + gstep >= n_groups_total) break;
+      tmem_ld_wait();
+      issue_ld(gi + 2 * gstep, va);
+      prefetch(gi + 2 * gstep, ra, pa);
+      finish(gi + gstep, vb, rb, pb);
+    }
+    tmem_ld_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+    if (++as == P.acc_stages) {
+      as = 0;
+      aphase ^= 1;
+    }
+  }
+}
+
 // MMA issuer role, shared by both kernels.  The ncu source page of the first version showed this warp, not the tensor
 // pipe, pacing every shape but the widest (~300 cycles of uniform-datapath work per MMA: an integer modulo per stage,
 // a shared-memory load + R2UR per tap, 64-bit descriptor arithmetic per MMA).  Here every per-stage and per-tap
@@ -498,6 +605,11 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
     const int i = threadIdx.x - 64;
     reinterpret_cast<int*>(smem + 512)[i] = P.tap_off[i] - P.min_off[i / P.ntaps];
   }
+  if (P.fast_epi) {  // alpha * bias for every output channel of this launch (zeros when there is no bias)
+    float* sb = reinterpret_cast<float*>(smem + 1024 + (size_t)S * P.stage_bytes);
+    const int n = (P.n_tiles * P.bn + 15) & ~15;
+    for (int i = threadIdx.x; i < n; i += kThreads) sb[i] = (P.bias && i < P.Cout) ? P.alpha * __ldg(P.bias + i) : 0.f;
+  }
   if (P.ci_odd) {
     // Odd chunk count (e.g. 24 channels): the partner window of the last chunk is never fetched.  Its weights are
     // zero, so it only has to hold finite values: zero every stage's second window once (stale activations of other
@@ -560,7 +672,20 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
     mma_role(P, tmem_base, full0, empty0, tfull0, tempty0, stage0, a_chunk_bytes, s_off);
   } else {
     // ===================================================================== epilogue (warps 2..9)
-    epilogue_role(P, tmem_base, tfull0, tempty0, warp & 3, (warp - 2) >> 2, 2, lane, tile_rows, acc_cols);
+    if (P.fast_epi) {
+      const float* s_bias = reinterpret_cast<const float*>(smem + 1024 + (size_t)S * P.stage_bytes);
+      const int lg = warp & 3, hf = (warp - 2) >> 2;
+      if (P.res != nullptr && P.accumulate)
+        epilogue_fast<true, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+      else if (P.res != nullptr)
+        epilogue_fast<true, false>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+      else if (P.accumulate)
+        epilogue_fast<false, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+      else
+        epilogue_fast<false, false>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+    } else {
+      epilogue_role(P, tmem_base, tfull0, tempty0, warp & 3, (warp - 2) >> 2, 2, lane, tile_rows, acc_cols);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -1069,12 +1194,20 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
     tc_conv_snake_kernel<<<fgrid, kFusedThreads, fsmem, (cudaStream_t)stream>>>(p);
     return fh::check_launch("fh_tc_conv(fused snake)");
   }
-  int stages = (budget - 1024) / p.stage_bytes;
+  static int fast_on = -1;
+  if (fast_on < 0) {
+    const char* e = getenv("FH_TC_FAST_EPI");
+    fast_on = e ? atoi(e) : 1;
+  }
+  const int bias_tab = ((p.n_tiles * a->bn + 15) & ~15) * 4;
+  p.fast_epi = (fast_on && p.v8 && !a->geglu && !a->out_is_16 && !(a->res && a->res_is_16) && bias_tab <= 8192) ? 1 : 0;
+  const int tail = p.fast_epi ? bias_tab : 0;
+  int stages = (budget - 1024 - tail) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   FH_REQUIRE(stages >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: stage of %d bytes does not fit twice", p.stage_bytes);
   p.stages = stages;
   p.err_flag = nullptr;
-  const int smem = 1024 + stages * p.stage_bytes;
+  const int smem = 1024 + stages * p.stage_bytes + tail;
 
   static int num_sms = 0;
   static int smem_set = 0;

@@ -549,6 +549,11 @@ def test_fused_snake_conv_matches_unfused(cuda_device, name):
         b = eng.vocoder(mel).cpu()
     finally:
         eng.fuse_snake = prev
+    # The two paths round differently (snake FMA order, bias folded into an FMA in the specialised epilogue); a
+    # rounding-level change upstream flips 16-bit operand roundings downstream, so they agree only to the 16-bit
+    # operand error itself (max-abs ~2e-3 vs fp64 for either path).  Both must sit at the same distance from fp64.
+    ref = torch.from_numpy(g["f64_vocoder"]).reshape(a.shape).float()
     err = float((a - b).abs().max())
-    print(f"fused snake+conv vs unfused {name}: max-abs {err:.3g}")
-    assert err <= 2e-4
+    sa, sb = snr_db(ref, a), snr_db(ref, b)
+    print(f"fused snake+conv vs unfused {name}: max-abs {err:.3g}, SNR vs fp64 {sa:.2f} / {sb:.2f} dB")
+    assert err <= 3e-3 and sa >= 55.0 and sb >= 55.0 and abs(sa - sb) <= 0.5
