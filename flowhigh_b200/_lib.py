@@ -57,6 +57,7 @@ SIGNATURES = {
     "fh_qknorm_rope_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "fh_attention_f32": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _f, _p]),
     "fh_qknorm_rope_split": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
+    "fh_tc_conv_snake_dual": (_i, [C.POINTER(TcConvArgs), _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _p]),
     "fh_attention_tc": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i, _p]),
     "fh_geglu_f32": (_i, [_p, _p, _i, _i64, _i, _i, _i, _p]),
     "fh_axpby_f32": (_i, [_p, _p, _f, _f, _p, _i64, _p]),

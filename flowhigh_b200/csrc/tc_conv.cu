@@ -19,6 +19,7 @@
 // TMEM allocator, warps 2..5 = epilogue.  Persistent CTAs, static tile striding.
 #include <stdlib.h>
 #include "common.cuh"
+#include "snake_worker.cuh"
 
 namespace {
 
@@ -44,6 +45,7 @@ struct TcParams {
   int ci_pairs;        // ceil(Cin / 16)
   int ci_odd;          // Cin % 16 == 8: the last pair has one real 8-channel chunk; its partner is a zeroed smem window
   int tg, n_groups;    // taps per smem stage, groups per ci-pair
+  int kc;              // ci-pairs per smem stage (> 1 only when a stage holds all taps: few-tap convs, Linear)
   int msub;            // 128-row sub-tiles per CTA tile (1, 2 or 4): B operand reuse + epilogue MLP
   int acc_stages;      // TMEM accumulator stages: 2 (epilogue overlaps the next tile) or 1 (msub*bn > 256)
   int wrows;           // rows fetched per chunk window: 128*msub + (max_off - min_off)
@@ -391,6 +393,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
   const int groups_per_sub = P.bn >> 4;
   const int n_groups_total = P.msub * groups_per_sub;
   const float alpha = P.alpha, beta = P.beta_res;
+  const int bmask = P.bias ? ~0 : 0;  // no bias: every group reads the 16 zeros at the head of the table
   const float* resp = (const float*)P.res;
   float* outp = (float*)P.out;
   for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -441,8 +444,8 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         if (hh == 1 && n0 + 8 >= P.Cout) break;
-        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n0 + hh * 8);
-        const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n0 + hh * 8 + 4);
+        const float4 b0 = *reinterpret_cast<const float4*>(s_bias + ((n0 + hh * 8) & bmask));
+        const float4 b1 = *reinterpret_cast<const float4*>(s_bias + ((n0 + hh * 8) & bmask) + 4);
         const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
         float o[8];
 #pragma unroll
@@ -508,6 +511,7 @@ __device__ __forceinline__ void mma_role(const TcParams& P, uint32_t tmem_base, 
   const bool leader = elect_one();
   int stage = 0, phase = 0, as = 0, aphase = 0;
   const int S = P.stages, msub = P.msub, ntaps = P.ntaps, tg = P.tg, n_groups = P.n_groups, ci_pairs = P.ci_pairs;
+  const int kc = P.kc;
   const uint32_t bn = (uint32_t)P.bn;
   const uint32_t idesc = make_idesc(P.bn, P.fp16);
   const uint32_t hi = (128u >> 4) | (1u << 14);                 // SBO = 128 B, descriptor version 1 (bit 46)
@@ -530,7 +534,8 @@ __device__ __forceinline__ void mma_role(const TcParams& P, uint32_t tmem_base, 
     tc_fence_after();
     const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
     uint32_t accum = 0;
-    for (int cp = 0; cp < ci_pairs; ++cp) {
+    for (int cp = 0; cp < ci_pairs; cp += kc) {
+      const int nkc = min(kc, ci_pairs - cp);
       int tap0 = 0;
       for (int g = 0; g < n_groups; ++g, tap0 += tg) {
         const int nt_g = min(tg, ntaps - tap0);
@@ -538,22 +543,28 @@ __device__ __forceinline__ void mma_role(const TcParams& P, uint32_t tmem_base, 
         tc_fence_after();
         const uint32_t sa_u = stage0_u + (uint32_t)stage * stage_u;
         if (leader) {
-          const uint32_t b_lo = b_lbo | (sa_u + a_slot_u);
-          if (P.tap_arith) {
-            const uint32_t a_lo = a_lbo | (sa_u + rel0 + (uint32_t)tap0 * a_step);
-            if (msub == 2) issue_taps<2>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
-            else if (msub == 4) issue_taps<4>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
-            else issue_taps<1>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
-          } else {  // irregular tap offsets: table in shared memory
-            const int* offs = s_off + ph * ntaps + tap0;
-            uint32_t bl = b_lo, acc = accum;
-            for (int j = 0; j < nt_g; ++j) {
-              const uint32_t a_lo = a_lbo | (sa_u + (uint32_t)offs[j]);
-              for (int sub = 0; sub < msub; ++sub)
-                umma_f16_split(d_tmem + (uint32_t)sub * bn, a_lo + (uint32_t)sub * 128u, hi, bl, hi, idesc, acc);
-              acc = 1;
-              bl += b_step;
+          uint32_t b_lo = b_lbo | (sa_u + (uint32_t)kc * a_slot_u);  // weights sit behind the kc activation slots
+          uint32_t a_base_lo = a_lbo | sa_u;
+          for (int c = 0; c < nkc; ++c) {
+            if (P.tap_arith) {
+              const uint32_t a_lo = a_base_lo + rel0 + (uint32_t)tap0 * a_step;
+              if (msub == 2) issue_taps<2>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
+              else if (msub == 4) issue_taps<4>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
+              else issue_taps<1>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
+            } else {  // irregular tap offsets: table in shared memory
+              const int* offs = s_off + ph * ntaps + tap0;
+              uint32_t bl = b_lo, acc = accum;
+              for (int j = 0; j < nt_g; ++j) {
+                const uint32_t a_lo = a_base_lo + (uint32_t)offs[j];
+                for (int sub = 0; sub < msub; ++sub)
+                  umma_f16_split(d_tmem + (uint32_t)sub * bn, a_lo + (uint32_t)sub * 128u, hi, bl, hi, idesc, acc);
+                acc = 1;
+                bl += b_step;
+              }
             }
+            accum = 1;
+            a_base_lo += a_slot_u;
+            b_lo += (uint32_t)nt_g * b_step;
           }
           umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
         }
@@ -574,21 +585,70 @@ __device__ __forceinline__ void mma_role(const TcParams& P, uint32_t tmem_base, 
   }
 }
 
-// MINB = 2 caps the kernel at 96 registers per thread (a few spilled words in the epilogue) so that the 320-thread CTA
-// leaves half of the register file free: CTAs of the FP32-pipe-bound snake kernel of another stream can then be
-// co-resident on the same SM and run under the tensor-pipe-bound convolution (engine.voc_streams > 1).
-template <int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_constant__ TcParams P) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  // [0,256): barriers; [256,260): tmem base; stages from 1024
+// Bulk-copy producer role (one elected lane): per stage, the (rows + span)-row window of each 8-channel chunk and the
+// packed weights of the stage's taps, all signalled on the stage's full barrier.
+__device__ __forceinline__ void producer_role(const TcParams& P, uint32_t full0, uint32_t empty0, uint32_t stage0,
+                                              uint32_t a_chunk_bytes, int tile_rows) {
+  const int S = P.stages;
+  const uint32_t b_tap_bytes = (uint32_t)P.bn * 32u;
+  const uint32_t a_slot_bytes = 2u * a_chunk_bytes;
+  int stage = 0, phase = 0;
+  for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    const TileCoord tc = decode_tile(P, tile);
+    const long long row = (long long)P.a_row0 + (long long)tc.mt * tile_rows + P.min_off[tc.p];
+    const __nv_bfloat16* a_base = P.a + (long long)tc.b * P.a_batch + row * 8;
+    // packed weights: [p][nt][cp][tap][2][bn][8]
+    const __nv_bfloat16* w_base =
+        P.w + ((long long)(tc.p * P.n_tiles + tc.nt) * P.ci_pairs) * ((long long)P.ntaps * P.bn * 16);
+    for (int cp = 0; cp < P.ci_pairs; cp += P.kc) {
+      const int nkc = min(P.kc, P.ci_pairs - cp);
+      for (int g = 0; g < P.n_groups; ++g) {
+        const int tap0 = g * P.tg;
+        const int nt_g = min(P.tg, P.ntaps - tap0);
+        mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 1);
+        const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
+        const uint32_t fb = full0 + 8 * stage;
+        const uint32_t a_bytes = (uint32_t)P.wrows * 16u;
+        const int nchunk = 2 * nkc - ((P.ci_odd && cp + nkc == P.ci_pairs) ? 1 : 0);
+        const uint32_t w_bytes = (uint32_t)(nkc * nt_g) * b_tap_bytes;  // kc > 1 only with n_groups == 1: contiguous
+        mbar_expect_tx(fb, (uint32_t)nchunk * a_bytes + w_bytes);
+        for (int c = 0; c < nchunk; ++c)
+          bulk_g2s(sa + (uint32_t)c * a_chunk_bytes, a_base + (long long)(2 * cp + c) * P.a_chunk, a_bytes, fb);
+        bulk_g2s(sa + (uint32_t)P.kc * a_slot_bytes, w_base + ((long long)cp * P.ntaps + tap0) * ((long long)P.bn * 16),
+                 w_bytes, fb);
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_dispatch(const TcParams& P, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
+                                                  int lg, int hf, int lane, int tile_rows, uint32_t acc_cols,
+                                                  const float* s_bias) {
+  if (P.fast_epi) {
+    if (P.res != nullptr && P.accumulate)
+      epilogue_fast<true, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+    else if (P.res != nullptr)
+      epilogue_fast<true, false>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+    else if (P.accumulate)
+      epilogue_fast<false, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+    else
+      epilogue_fast<false, false>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+  } else {
+    epilogue_role(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols);
+  }
+}
+
+// Per-CTA setup shared by the conv kernels: mbarriers, tap-offset table, alpha * bias table, zeroed partner windows.
+// The caller allocates TMEM and issues the __syncthreads that publishes all of it.
+__device__ __forceinline__ void conv_cta_setup(const TcParams& P, unsigned char* smem, int nthreads, int epi_warps) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
   const uint32_t tfull0 = empty0 + 8 * kMaxStages, tempty0 = tfull0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxStages + 4));
-  const uint32_t stage0 = smem_u32(smem + 1024);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int S = P.stages;
-
   if (threadIdx.x == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(full0 + 8 * i, 1);
@@ -596,96 +656,64 @@ __global__ void __launch_bounds__(kThreads, MINB) tc_conv_kernel(const __grid_co
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, 8);
+      mbar_init(tempty0 + 8 * i, epi_warps);
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   if (threadIdx.x >= 64 && threadIdx.x < 64 + P.P * P.ntaps) {
     const int i = threadIdx.x - 64;
     reinterpret_cast<int*>(smem + 512)[i] = P.tap_off[i] - P.min_off[i / P.ntaps];
   }
-  if (P.fast_epi) {  // alpha * bias for every output channel of this launch (zeros when there is no bias)
+  if (P.fast_epi) {  // alpha * bias for every output channel of this launch (16 zeros when there is no bias)
     float* sb = reinterpret_cast<float*>(smem + 1024 + (size_t)S * P.stage_bytes);
-    const int n = (P.n_tiles * P.bn + 15) & ~15;
-    for (int i = threadIdx.x; i < n; i += kThreads) sb[i] = (P.bias && i < P.Cout) ? P.alpha * __ldg(P.bias + i) : 0.f;
+    const int n = P.bias ? ((P.n_tiles * P.bn + 15) & ~15) : 16;
+    for (int i = threadIdx.x; i < n; i += nthreads) sb[i] = (P.bias && i < P.Cout) ? P.alpha * __ldg(P.bias + i) : 0.f;
   }
   if (P.ci_odd) {
     // Odd chunk count (e.g. 24 channels): the partner window of the last chunk is never fetched.  Its weights are
-    // zero, so it only has to hold finite values: zero every stage's second window once (stale activations of other
+    // zero, so it only has to hold finite values: zero every stage's second windows once (stale activations of other
     // pairs that land there later are finite as well).
     const uint32_t cb = (uint32_t)P.arows_pad * 16u;
-    for (int st = 0; st < S; ++st) {
-      uint4* z = reinterpret_cast<uint4*>(smem + 1024 + (size_t)st * P.stage_bytes + cb);
-      for (uint32_t i = threadIdx.x; i < cb / 16u; i += kThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int st = 0; st < S * P.kc; ++st) {
+      uint4* z = reinterpret_cast<uint4*>(smem + 1024 + (size_t)(st / P.kc) * P.stage_bytes + (size_t)(2 * (st % P.kc) + 1) * cb);
+      for (uint32_t i = threadIdx.x; i < cb / 16u; i += nthreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  // [0,256): barriers; [256,260): tmem base; [512,768): tap offsets; stages from 1024; bias table behind the stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
+  const uint32_t tfull0 = empty0 + 8 * kMaxStages, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxStages + 4));
+  const uint32_t stage0 = smem_u32(smem + 1024);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  conv_cta_setup(P, smem, kThreads, 8);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   int* s_off = reinterpret_cast<int*>(smem + 512);  // [P][ntaps] tap offsets relative to the phase minimum
 
-  const int steps_per_tile = P.ci_pairs * P.n_groups;
-  const uint32_t b_tap_bytes = (uint32_t)P.bn * 32u;     // one tap: 2 chunks x bn rows x 16 B
   const uint32_t a_chunk_bytes = (uint32_t)P.arows_pad * 16u;  // one chunk window slot
-  const uint32_t a_slot_bytes = 2u * a_chunk_bytes;
   const int tile_rows = 128 * P.msub;
   const uint32_t acc_cols = (uint32_t)(P.msub * P.bn);   // TMEM columns of one accumulator stage
 
   if (warp == 0) {
     // ===================================================================== producer
-    if (lane == 0) {
-      int stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(P, tile);
-        const long long row = (long long)P.a_row0 + (long long)tc.mt * tile_rows + P.min_off[tc.p];
-        const __nv_bfloat16* a_base = P.a + (long long)tc.b * P.a_batch + row * 8;
-        // packed weights: [p][nt][cp][tap][2][bn][8]
-        const __nv_bfloat16* w_base =
-            P.w + ((long long)(tc.p * P.n_tiles + tc.nt) * P.ci_pairs) * ((long long)P.ntaps * P.bn * 16);
-        for (int cp = 0; cp < P.ci_pairs; ++cp) {
-          for (int g = 0; g < P.n_groups; ++g) {
-            const int tap0 = g * P.tg;
-            const int nt_g = min(P.tg, P.ntaps - tap0);
-            mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 1);
-            const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
-            const uint32_t fb = full0 + 8 * stage;
-            const uint32_t a_bytes = (uint32_t)P.wrows * 16u;
-            const bool pair = !(P.ci_odd && cp == P.ci_pairs - 1);
-            mbar_expect_tx(fb, (pair ? 2u : 1u) * a_bytes + (uint32_t)nt_g * b_tap_bytes);
-            bulk_g2s(sa, a_base + (long long)(2 * cp) * P.a_chunk, a_bytes, fb);
-            if (pair) bulk_g2s(sa + a_chunk_bytes, a_base + (long long)(2 * cp + 1) * P.a_chunk, a_bytes, fb);
-            bulk_g2s(sa + a_slot_bytes, w_base + ((long long)cp * P.ntaps + tap0) * ((long long)P.bn * 16),
-                     (uint32_t)nt_g * b_tap_bytes, fb);
-            if (++stage == S) {
-              stage = 0;
-              phase ^= 1;
-            }
-          }
-        }
-      }
-    }
+    if (lane == 0) producer_role(P, full0, empty0, stage0, a_chunk_bytes, tile_rows);
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     mma_role(P, tmem_base, full0, empty0, tfull0, tempty0, stage0, a_chunk_bytes, s_off);
   } else {
     // ===================================================================== epilogue (warps 2..9)
-    if (P.fast_epi) {
-      const float* s_bias = reinterpret_cast<const float*>(smem + 1024 + (size_t)S * P.stage_bytes);
-      const int lg = warp & 3, hf = (warp - 2) >> 2;
-      if (P.res != nullptr && P.accumulate)
-        epilogue_fast<true, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
-      else if (P.res != nullptr)
-        epilogue_fast<true, false>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
-      else if (P.accumulate)
-        epilogue_fast<false, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
-      else
-        epilogue_fast<false, false>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
-    } else {
-      epilogue_role(P, tmem_base, tfull0, tempty0, warp & 3, (warp - 2) >> 2, 2, lane, tile_rows, acc_cols);
-    }
+    epilogue_dispatch(P, tmem_base, tfull0, tempty0, warp & 3, (warp - 2) >> 2, lane, tile_rows, acc_cols,
+                      reinterpret_cast<const float*>(smem + 1024 + (size_t)P.stages * P.stage_bytes));
   }
   tc_fence_before();
   __syncthreads();
@@ -988,6 +1016,72 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tc_conv_snake_kernel(const _
   }
 }
 
+// ------------------------------------------------------------------------------ dual kernel: conv || snake
+// The vocoder alternates a tensor-pipe / HBM-bound convolution with an FP32-pipe-bound anti-aliased snake; run back to
+// back, each leaves the other pipe of the SM idle (and streams could not make them co-resident: the conv CTA holds
+// most of the register file and shared memory).  This kernel is both at once, for two independent half-batches: the
+// ten conv warps of tc_conv_kernel (producer, MMA issuer, eight epilogue warps) work on half-batch A while two
+// 128-thread snake workers (snake_worker.cuh) walk the tiles of half-batch B.  Register budget via setmaxnreg:
+// producers 24, epilogue 128, snake 96.  The engine staggers the two half-batches by one operator so that every
+// launch pairs a conv with a snake.
+constexpr int kDualThreads = 640;  // warps 0..3 producer / MMA / 2 idle, 4..11 epilogue, 12..19 snake (2 workers)
+constexpr int kDualWorkers = 2;
+constexpr int kDualR = 11;         // snake outputs per thread (96-register budget)
+
+struct DualParams {
+  TcParams c;
+  fh::SnakeParams s;
+  int snake_off;   // byte offset of the snake workers' shared memory
+  int s_out_kind;  // 1 bf16, 2 fp16
+};
+
+__global__ void __launch_bounds__(kDualThreads, 1) tc_conv_snake_dual_kernel(const __grid_constant__ DualParams D) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const TcParams& P = D.c;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
+  const uint32_t tfull0 = empty0 + 8 * kMaxStages, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxStages + 4));
+  const uint32_t stage0 = smem_u32(smem + 1024);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  conv_cta_setup(P, smem, kDualThreads, 8);
+  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  int* s_off = reinterpret_cast<int*>(smem + 512);
+  const uint32_t a_chunk_bytes = (uint32_t)P.arows_pad * 16u;
+  const int tile_rows = 128 * P.msub;
+  const uint32_t acc_cols = (uint32_t)(P.msub * P.bn);
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == 0) {
+      if (lane == 0) producer_role(P, full0, empty0, stage0, a_chunk_bytes, tile_rows);
+    } else if (warp == 1) {
+      mma_role(P, tmem_base, full0, empty0, tfull0, tempty0, stage0, a_chunk_bytes, s_off);
+    }
+  } else if (warp < 12) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
+    epilogue_dispatch(P, tmem_base, tfull0, tempty0, warp & 3, (warp - 4) >> 2, lane, tile_rows, acc_cols,
+                      reinterpret_cast<const float*>(smem + 1024 + (size_t)P.stages * P.stage_bytes));
+  } else {
+    const int grp = (warp - 12) >> 2;
+    const int tid = threadIdx.x - 384 - grp * 128;
+    unsigned char* sm = smem + D.snake_off + (size_t)grp * fh::SnakeGeom<kDualR>::kSmemBytes;
+    const int worker = blockIdx.x * kDualWorkers + grp, nworkers = gridDim.x * kDualWorkers;
+    fh::snake_worker<3, true, kDualR>(D.s, sm, tid, worker, nworkers, 1 + grp);  // one instantiation: small I-cache footprint
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------ layout helpers
 __global__ void to_chunked_bf16_kernel(const float* __restrict__ src, long long src_batch, long long src_c,
                                        long long src_t, __nv_bfloat16* __restrict__ dst, long long dst_batch,
@@ -1027,7 +1121,9 @@ extern "C" __attribute__((visibility("default"))) int64_t fh_tc_packed_weight_by
   return (int64_t)P * n_tiles * ((Cin + 15) / 16) * ntaps * bn * 32;
 }
 
-extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_conv_args* a, void* stream) {
+// Validates the arguments and derives the launch plan (tile shape, stages, shared-memory carve-up).  `budget_bytes` is
+// the shared memory the conv roles may use (0 = default); the fused-snake variant launches from here (returns 1).
+static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcParams& p, int* smem_out) {
   FH_REQUIRE(a != nullptr, FH_ERR_BAD_SHAPE, "fh_tc_conv: null args");
   FH_REQUIRE(a->B > 0 && a->L > 0 && a->Cin > 0 && a->Cout > 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: bad shape");
   FH_REQUIRE(a->Cin % 8 == 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: Cin=%d must be a multiple of 8", a->Cin);
@@ -1048,7 +1144,6 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
                  (a->out_row % (1 << esz_shift)) == 0,
              FH_ERR_BAD_ALIGN, "fh_tc_conv: output strides break 16-byte alignment");
 
-  TcParams p;
   memset(&p, 0, sizeof(p));
   p.a = (const __nv_bfloat16*)a->a;
   p.w = (const __nv_bfloat16*)a->w;
@@ -1154,7 +1249,23 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
   p.n_groups = (a->ntaps + tg - 1) / tg;
   tg = (a->ntaps + p.n_groups - 1) / p.n_groups;
   p.tg = tg;
-  p.stage_bytes = 2 * p.arows_pad * 16 + tg * a->bn * 32;
+  // ci-pairs per stage: a stage should carry >= ~12 MMAs so that its barrier round trip is amortised (Linear layers are
+  // one tap per ci-pair, k = 3 convs three), as long as at least 3-4 stages still fit
+  static int kc_target = -1;
+  if (kc_target < 0) {
+    const char* e = getenv("FH_TC_KC_MMAS");
+    kc_target = e ? atoi(e) : 12;
+  }
+  int kc = 1;
+  if (!fused && p.n_groups == 1 && kc_target > 0) {
+    const int pair_bytes = 2 * p.arows_pad * 16 + a->ntaps * a->bn * 32;
+    kc = (kc_target + a->ntaps * msub - 1) / (a->ntaps * msub);
+    if (kc > 4) kc = 4;
+    if (kc > p.ci_pairs) kc = p.ci_pairs;
+    while (kc > 1 && (200 * 1024 - 1024 - 8192) / (kc * pair_bytes) < 4) --kc;
+  }
+  p.kc = kc;
+  p.stage_bytes = kc * (2 * p.arows_pad * 16 + tg * a->bn * 32);
   p.stage_bytes = (p.stage_bytes + 127) & ~127;
   static int budget_kb = 0;
   if (!budget_kb) {
@@ -1162,8 +1273,9 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
     budget_kb = e ? atoi(e) : 200;
     if (budget_kb < 64 || budget_kb > 220) budget_kb = 200;
   }
-  const int budget = budget_kb * 1024;
+  const int budget = budget_bytes > 0 ? budget_bytes : budget_kb * 1024;
   if (fused) {
+    FH_REQUIRE(budget_bytes == 0, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: the fused snake prologue cannot run in the dual kernel");
     const int fbudget = 220 * 1024;  // this kernel owns the SM
     const int sbuf = 2 * kSrPad * 32;
     p.x_stages = 3;
@@ -1192,14 +1304,15 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
     }
     const int fgrid = p.total_tiles < fsms ? p.total_tiles : fsms;
     tc_conv_snake_kernel<<<fgrid, kFusedThreads, fsmem, (cudaStream_t)stream>>>(p);
-    return fh::check_launch("fh_tc_conv(fused snake)");
+    const int rc = fh::check_launch("fh_tc_conv(fused snake)");
+    return rc == FH_OK ? 1 : rc;
   }
   static int fast_on = -1;
   if (fast_on < 0) {
     const char* e = getenv("FH_TC_FAST_EPI");
     fast_on = e ? atoi(e) : 1;
   }
-  const int bias_tab = ((p.n_tiles * a->bn + 15) & ~15) * 4;
+  const int bias_tab = a->bias ? ((p.n_tiles * a->bn + 15) & ~15) * 4 : 64;
   p.fast_epi = (fast_on && p.v8 && !a->geglu && !a->out_is_16 && !(a->res && a->res_is_16) && bias_tab <= 8192) ? 1 : 0;
   const int tail = p.fast_epi ? bias_tab : 0;
   int stages = (budget - 1024 - tail) / p.stage_bytes;
@@ -1207,34 +1320,75 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
   FH_REQUIRE(stages >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: stage of %d bytes does not fit twice", p.stage_bytes);
   p.stages = stages;
   p.err_flag = nullptr;
-  const int smem = 1024 + stages * p.stage_bytes + tail;
+  *smem_out = 1024 + stages * p.stage_bytes + tail;
+  return FH_OK;
+}
 
+static int device_sms() {
   static int num_sms = 0;
-  static int smem_set = 0;
   if (!num_sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (num_sms <= 0) num_sms = 148;
   }
-  static int lowreg = -1;
-  if (lowreg < 0) {
-    const char* e = getenv("FH_TC_LOWREG");
-    lowreg = e ? atoi(e) : 0;
-  }
+  return num_sms;
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_conv_args* a, void* stream) {
+  TcParams p;
+  int smem = 0;
+  const int rc = tc_plan(a, stream, 0, p, &smem);
+  if (rc != FH_OK) return rc == 1 ? FH_OK : rc;  // 1: the fused-snake variant was launched by the planner
+  static int smem_set = 0;
   if (smem > smem_set) {
-    cudaError_t e = lowreg ? cudaFuncSetAttribute(tc_conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                           : cudaFuncSetAttribute(tc_conv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", smem,
                cudaGetErrorString(e));
     smem_set = smem;
   }
+  const int num_sms = device_sms();
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  if (lowreg)
-    tc_conv_kernel<2><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
-  else
-    tc_conv_kernel<1><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  tc_conv_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
   return fh::check_launch("fh_tc_conv");
+}
+
+// One launch = the convolution of one half-batch (tensor pipe, HBM) + the anti-aliased snake of the other half-batch
+// (FP32 pipe) on the same SMs: see tc_conv_snake_dual_kernel.
+extern "C" __attribute__((visibility("default"))) int fh_tc_conv_snake_dual(
+    const fh_tc_conv_args* a, const float* sx, void* sy, const float* sa, const float* sinv_b, const float* sfilt,
+    int64_t s_batch_stride, int64_t s_chunk_stride, int s_row0, int sB, int sC, int sL, int s_out_kind, void* stream) {
+  FH_REQUIRE(a != nullptr && a->x_f32 == nullptr, FH_ERR_BAD_SHAPE, "fh_tc_conv_snake_dual: needs a plain conv");
+  FH_REQUIRE(sB > 0 && sC > 0 && (sC % 8) == 0 && sL > 0 && (s_out_kind == 1 || s_out_kind == 2), FH_ERR_BAD_SHAPE,
+             "fh_tc_conv_snake_dual: snake needs C %% 8 == 0 and a 16-bit output");
+  FH_REQUIRE(((uintptr_t)sx % 16) == 0 && ((uintptr_t)sy % 16) == 0 && (s_batch_stride % 8) == 0 &&
+                 (s_chunk_stride % 8) == 0 && s_row0 >= 5,
+             FH_ERR_BAD_ALIGN, "fh_tc_conv_snake_dual: snake buffers must be 16-byte aligned with a left halo of >= 5 rows");
+  using G = fh::SnakeGeom<kDualR>;
+  constexpr int kSnakeSmem = kDualWorkers * G::kSmemBytes;
+  DualParams d;
+  int csmem = 0;
+  const int rc = tc_plan(a, stream, 226 * 1024 - kSnakeSmem, d.c, &csmem);
+  if (rc != FH_OK) return rc;
+  d.snake_off = (csmem + 127) & ~127;
+  const int ntile = (sL + G::kRows - 1) / G::kRows;
+  const long long total = (long long)ntile * (sC / 8) * sB;
+  FH_REQUIRE(total <= 2147483647LL, FH_ERR_BAD_SHAPE, "fh_tc_conv_snake_dual: too many snake tiles");
+  d.s.x = sx, d.s.y = sy, d.s.a = sa, d.s.inv_b = sinv_b, d.s.filt = sfilt;
+  d.s.batch_stride = s_batch_stride, d.s.chunk_stride = s_chunk_stride;
+  d.s.row0 = s_row0, d.s.nchunk = sC / 8, d.s.L = sL, d.s.ntile = ntile, d.s.total = (int)total;
+  d.s_out_kind = s_out_kind;
+  d.s.fp16 = s_out_kind == 2;
+  const int smem = d.snake_off + kSnakeSmem;
+  static int smem_set = 0;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_conv_snake_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv_snake_dual: cannot opt in to %d bytes of smem: %s", smem,
+               cudaGetErrorString(e));
+    smem_set = smem;
+  }
+  tc_conv_snake_dual_kernel<<<device_sms(), kDualThreads, smem, (cudaStream_t)stream>>>(d);
+  return fh::check_launch("fh_tc_conv_snake_dual");
 }
 
 extern "C" __attribute__((visibility("default"))) int fh_to_chunked_16(const float* src, int64_t src_batch, int64_t src_c, int64_t src_t, void* dst,

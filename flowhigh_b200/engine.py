@@ -64,6 +64,11 @@ class Engine:
         self.voc_streams = int(_os.environ.get("FH_VOC_STREAMS", "1"))
         self.tc_attention = _os.environ.get("FH_TC_ATTENTION", "1") != "0"  # mma.sync split-operand attention
         self.fuse_snake = _os.environ.get("FH_FUSE_SNAKE", "0") != "0"      # snake as the conv kernel's A-producer
+        # dual launches: conv of one half-batch + snake of the other half-batch in one kernel (fh_tc_conv_snake_dual).
+        # Correct and tested, but measured slower than back-to-back launches on B200 (389 vs 375 ms per step: the two
+        # instruction streams thrash the 32 KB L1.5 I-cache and the snake workers get 8 warps instead of 16): off.
+        self.dual = _os.environ.get("FH_DUAL", "0") != "0"
+        self._tape = None
         self._side_streams = []
         self._time_cache: Dict[float, dict] = {}
         dev = self.device
@@ -104,6 +109,10 @@ class Engine:
                                  f"(got {t.dtype}, {t.device}, contiguous={t.is_contiguous()})")
 
     def _call(self, name, *args, work=None):
+        if self._tape is not None:
+            kind = "snake" if (name == "fh_snake_aa_chunked" and args[11] in (1, 2)) else "other"
+            self._tape.append((kind, name, args, work))
+            return
         if self.profile is None:
             _lib.check(getattr(self.lib, name)(*args), name)
             return
@@ -311,22 +320,73 @@ class Engine:
         args.alpha, args.beta_res, args.accumulate, args.geglu = alpha, beta, int(accumulate), int(geglu)
         args.B, args.L, args.Cin, args.Cout = B, L, rec.cin_pad, rec.cout_pad
         args.ntaps, args.P, args.tap_off, args.bn = rec.ntaps, rec.P, rec.off_c, rec.bn
-        if self.profile is None:
-            _lib.check(self.lib.fh_tc_conv(C.byref(args), self.stream), "fh_tc_conv")
-            return
         flops = 2.0 * B * L * rec.P * rec.ntaps * rec.cin * rec.cout
         esz_o = 2 if out_bf16 else 4
         nbytes = B * L * rec.cin * (4 if xf is not None else 2) + B * L * rec.P * rec.cout * esz_o * (2 if accumulate else 1)
         if res is not None:
             nbytes += B * L * rec.P * rec.cout * (2 if res_bf16 else 4)
+        work = {"flops": flops, "bytes": float(nbytes),
+                "tag": f"tc_conv{'+snake' if xf is not None else ''}[Cin{rec.cin},Cout{rec.cout},k{rec.ntaps}x{rec.P}"
+                       f"{',res' if res is not None else ''}]"}
+        if self._tape is not None:
+            self._tape.append(("conv" if xf is None else "other", "fh_tc_conv", (args,), work))
+            return
+        self._launch_conv(args, work)
+
+    def _launch_conv(self, args, work):
+        if self.profile is None:
+            _lib.check(self.lib.fh_tc_conv(C.byref(args), self.stream), "fh_tc_conv")
+            return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(self.device))
         _lib.check(self.lib.fh_tc_conv(C.byref(args), self.stream), "fh_tc_conv")
         e1.record(torch.cuda.current_stream(self.device))
-        self.profile.append(("fh_tc_conv", e0, e1,
-                             {"flops": flops, "bytes": float(nbytes),
-                              "tag": f"tc_conv{'+snake' if xf is not None else ''}[Cin{rec.cin},Cout{rec.cout},k{rec.ntaps}x{rec.P}"
-                                     f"{',res' if res is not None else ''}]"}))
+        self.profile.append(("fh_tc_conv", e0, e1, work))
+
+    def _launch_dual(self, conv, snake):
+        """conv = tape entry of a fh_tc_conv, snake = tape entry of a 16-bit fh_snake_aa_chunked (other half-batch)."""
+        args, cwork = conv[2][0], conv[3]
+        sa = snake[2]  # (x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, B, C, L, out_kind, stream)
+        call = lambda: _lib.check(self.lib.fh_tc_conv_snake_dual(C.byref(args), *sa[:12], self.stream), "fh_tc_conv_snake_dual")
+        if self.profile is None:
+            call()
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(torch.cuda.current_stream(self.device))
+        call()
+        e1.record(torch.cuda.current_stream(self.device))
+        sbytes = 6.0 * sa[8] * sa[9] * sa[10]
+        self.profile.append(("fh_tc_conv_snake_dual", e0, e1,
+                             {"flops": cwork["flops"], "bytes": cwork["bytes"] + sbytes, "tag": "dual:" + cwork["tag"]}))
+
+    def _replay(self, entry):
+        kind, name, args, work = entry
+        if name == "fh_tc_conv":
+            self._launch_conv(args[0], work)
+        else:
+            tape, self._tape = self._tape, None
+            try:
+                self._call(name, *args[:-1], self.stream, work=work)
+            finally:
+                self._tape = tape
+
+    def _run_dual(self, A, B):
+        """Merges the operator tapes of two half-batches: half A runs one operator ahead, so its convolution meets the
+        snake of half B (and vice versa) in one dual launch; everything else is launched on its own, in tape order."""
+        i = j = 0
+        while i < len(A) or j < len(B):
+            a = A[i] if i < len(A) else None
+            b = B[j] if j < len(B) else None
+            if a is not None and b is not None and {a[0], b[0]} == {"conv", "snake"}:
+                conv, snake = (a, b) if a[0] == "conv" else (b, a)
+                self._launch_dual(conv, snake)
+                i, j = i + 1, j + 1
+            elif b is None or (a is not None and i <= j):
+                self._replay(a)
+                i += 1
+            else:
+                self._replay(b)
+                j += 1
 
     def _sgemm(self, A, lda, W, ldw, bias, res, ldr, beta, alpha, out, ldc, M, N, K):
         self._call("fh_sgemm_nt_f32", A.data_ptr(), lda, W.data_ptr() if isinstance(W, torch.Tensor) else W, ldw,
@@ -508,6 +568,18 @@ class Engine:
         B, N, _ = mel.shape
         ns = min(self.voc_streams, B)
         wave = torch.empty((B, N * self.vcfg.total_upsample), dtype=torch.float32, device=self.device)
+        if self.dual and not self.fuse_snake and ns <= 1 and B >= 2:
+            h = (B + 1) // 2
+            tapes = []
+            for tag, sl in (("d0", slice(0, h)), ("d1", slice(h, B))):
+                self._tape = []
+                try:
+                    self._vocoder_tc(mel[sl], wave[sl], tag)
+                    tapes.append(self._tape)
+                finally:
+                    self._tape = None
+            self._run_dual(tapes[0], tapes[1])
+            return wave
         if ns <= 1:
             self._vocoder_tc(mel, wave, "")
             return wave

@@ -176,7 +176,7 @@ typedef struct {
   float alpha, beta_res;
   int accumulate;         /* out += ... (fp32 out only) */
   int geglu;              /* epilogue pairs columns (2i, 2i+1) -> gelu(col 2i+1) * col 2i */
-  int B, L, Cin, Cout;    /* Cin multiple of 16, Cout multiple of 8 */
+  int B, L, Cin, Cout;    /* Cin and Cout multiples of 8 (whole 8-channel chunks) */
   int ntaps, P;           /* taps per phase, phases (output stride) */
   const int* tap_off;     /* HOST pointer [P][ntaps] row offsets */
   int bn;                 /* N tile, multiple of 16, <= 256 */
@@ -190,6 +190,13 @@ typedef struct {
   const float* sn_filt;   /* [12] Kaiser-sinc taps */
 } fh_tc_conv_args;
 int fh_tc_conv(const fh_tc_conv_args* args, void* stream);
+/* One launch = fh_tc_conv(args) for one half-batch + fh_snake_aa_chunked(sx -> sy, 16-bit out) for an independent
+ * half-batch on the same SMs (tensor pipe and FP32 pipe busy together; replaces the back-to-back launches of
+ * bigvgan/models.py:63-72 `conv(act(x))` chains when two half-batches are staggered by one operator).
+ * args->x_f32 must be NULL; s_out_kind 1 = bf16, 2 = fp16. */
+int fh_tc_conv_snake_dual(const fh_tc_conv_args* args, const float* sx, void* sy, const float* sa,
+                          const float* sinv_b, const float* sfilt, int64_t s_batch_stride, int64_t s_chunk_stride,
+                          int s_row0, int sB, int sC, int sL, int s_out_kind, void* stream);
 /* bytes of the packed weight image for given shape (host helper, no GPU work) */
 int64_t fh_tc_packed_weight_bytes(int Cin, int Cout, int ntaps, int P, int bn);
 

@@ -557,3 +557,22 @@ def test_fused_snake_conv_matches_unfused(cuda_device, name):
     sa, sb = snr_db(ref, a), snr_db(ref, b)
     print(f"fused snake+conv vs unfused {name}: max-abs {err:.3g}, SNR vs fp64 {sa:.2f} / {sb:.2f} dB")
     assert err <= 3e-3 and sa >= 55.0 and sb >= 55.0 and abs(sa - sb) <= 0.5
+
+
+def test_dual_conv_snake_launches_match_separate(cuda_device):
+    """fh_tc_conv_snake_dual (conv of one half-batch + snake of the other in one kernel, engine tapes staggered by one
+    operator) must reproduce the back-to-back launches: same kernels' arithmetic, only the schedule differs."""
+    eng, sd, vcfg, g = engine("voc_resblock1_snakebeta", "fp16")
+    mel = dev(g["mel"])
+    mel = torch.cat([mel, mel.flip(1) * 0.9, mel * 0.8], 0).contiguous()  # B = 3: unequal halves
+    prev = eng.dual
+    try:
+        eng.dual = False
+        a = eng.vocoder(mel).cpu()
+        eng.dual = True
+        b = eng.vocoder(mel).cpu()
+    finally:
+        eng.dual = prev
+    err = float((a - b).abs().max())
+    print(f"dual conv||snake launches vs separate: max-abs {err:.3g}")
+    assert err <= 3e-3 and snr_db(a, b) >= 55.0
