@@ -45,3 +45,35 @@ def lsd_db(ref, x):
     B = torch.stft(x.double().flatten(), 2048, 480, window=w, return_complex=True).abs() ** 2
     d = 10 * torch.log10(A.clamp_min(1e-10)) - 10 * torch.log10(B.clamp_min(1e-10))
     return float(d.pow(2).mean(0).sqrt().mean())
+
+
+def _unfold(w):
+    """weight -> (weight_g, weight_v) of torch.nn.utils.weight_norm (dim 0), with v deliberately not unit-norm."""
+    scale = torch.linspace(0.5, 2.0, w.shape[0]).reshape(-1, *([1] * (w.dim() - 1)))
+    v = w * scale
+    g = w.reshape(w.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (w.dim() - 1)))
+    return g, v
+
+
+def write_hub_dir(path, vcfg, sd):
+    """Lays out `path` like the ResembleAI/FlowHigh hub repo (flowhighsr.py:109-149): BigVGAN JSON (the AttrDict fields
+    bigvgan/models.py reads), bigvgan .pt = {'generator': weight_g / weight_v pairs} as upstream BigVGAN ships it,
+    FLowHigh_basic_400k.pt = {'model': full state dict, vocoder folded}, and the unused FLowHigh json.
+    Returns the raw generator dict."""
+    import json
+    VOC = "flowhigh.audio_enc_dec.vocoder."
+    (path / "bigvgan_48khz_256band.json").write_text(json.dumps(vcfg.to_attr_json()))
+    gen = {}
+    for k, t in sd.items():
+        if not k.startswith(VOC):
+            continue
+        name = k[len(VOC):]
+        if name.endswith(".weight") and t.dim() == 3 and ("conv" in name or name.startswith("ups.")):
+            g, v = _unfold(t)
+            gen[name + "_g"], gen[name + "_v"] = g, v
+        else:
+            gen[name] = t.clone()
+    torch.save({"generator": gen}, path / "bigvgan_48khz_256band.pt")
+    torch.save({"model": sd}, path / "FLowHigh_basic_400k.pt")
+    (path / "FLowHigh_basic_400k.json").write_text("{}")
+    return gen
