@@ -85,8 +85,45 @@ __global__ void sincos_embed_kernel(const float* __restrict__ w, float t, float*
 }
 
 // ------------------------------------------------------------------------------ conv pos embed
-__global__ void dwconv_gelu_res_kernel(const float* __restrict__ E, const float* __restrict__ w,
-                                       const float* __restrict__ b, float* __restrict__ out, int N, int C, int k) {
+// out[n, c] = E[n, c] + gelu(b[c] + sum_j w[c, j] E[n + j - k/2, c])   (transformer.py:28-46, flow.py:240)
+// HBM-bound (one fp32 read + one write per element).  A thread owns one channel and kDwT consecutive time steps:
+// the kDwT + K - 1 inputs it needs are loaded once into registers (coalesced over the 128 channels of the block,
+// halo re-reads between neighbouring tiles are L2 hits) and all K taps run from registers, fully unrolled.
+constexpr int kDwT = 32;
+template <int K>
+__global__ void __launch_bounds__(128) dwconv_gelu_res_kernel(const float* __restrict__ E, const float* __restrict__ w,
+                                                              const float* __restrict__ b, float* __restrict__ out, int N,
+                                                              int C) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int n0 = blockIdx.y * kDwT, bi = blockIdx.z;
+  if (c >= C) return;
+  const float* e = E + (size_t)bi * N * C + c;
+  constexpr int half = K >> 1;
+  float wr[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) wr[j] = __ldg(w + (size_t)c * K + j);
+  float x[kDwT + K - 1];
+#pragma unroll
+  for (int i = 0; i < kDwT + K - 1; ++i) {
+    const int nn = n0 + i - half;
+    x[i] = (nn >= 0 && nn < N) ? __ldg(e + (size_t)nn * C) : 0.f;  // Conv1d zero padding
+  }
+  const float bias = __ldg(b + c);
+  float* o = out + ((size_t)bi * N + n0) * C + c;
+#pragma unroll
+  for (int t = 0; t < kDwT; ++t) {
+    if (n0 + t < N) {
+      float acc = bias;
+#pragma unroll
+      for (int j = 0; j < K; ++j) acc = fmaf(wr[j], x[t + j], acc);
+      o[(size_t)t * C] = x[t + half] + fh::gelu_erf(acc);
+    }
+  }
+}
+
+// any odd kernel size (the checkpoint uses 31)
+__global__ void dwconv_gelu_res_generic_kernel(const float* __restrict__ E, const float* __restrict__ w,
+                                               const float* __restrict__ b, float* __restrict__ out, int N, int C, int k) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y, bi = blockIdx.z;
   if (c >= C) return;
@@ -372,7 +409,10 @@ extern "C" __attribute__((visibility("default"))) int fh_dwconv_gelu_res_f32(con
                                       int k, void* stream) {
   FH_REQUIRE(B > 0 && N > 0 && C > 0 && (k & 1), FH_ERR_BAD_SHAPE, "fh_dwconv_gelu_res_f32: kernel size must be odd");
   FH_REQUIRE(N <= 65535 && B <= 65535, FH_ERR_BAD_SHAPE, "fh_dwconv_gelu_res_f32: N, B must be <= 65535");
-  dwconv_gelu_res_kernel<<<dim3((C + 255) / 256, N, B), 256, 0, (cudaStream_t)stream>>>(E, w, b, out, N, C, k);
+  if (k == 31)
+    dwconv_gelu_res_kernel<31><<<dim3((C + 127) / 128, (N + kDwT - 1) / kDwT, B), 128, 0, (cudaStream_t)stream>>>(E, w, b, out, N, C);
+  else
+    dwconv_gelu_res_generic_kernel<<<dim3((C + 255) / 256, N, B), 256, 0, (cudaStream_t)stream>>>(E, w, b, out, N, C, k);
   return fh::check_launch("fh_dwconv_gelu_res_f32");
 }
 
