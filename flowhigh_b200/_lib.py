@@ -46,6 +46,9 @@ SIGNATURES = {
     "fh_stft_logmel_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "fh_stft_center_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "fh_pp_cutoff": (_i, [_p, _p, _i, _f, _p]),
+    "fh_pp_energy_ws_bytes": (_i, [_i, _i]),
+    "fh_pp_src_energy_f32": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p]),
+    "fh_pp_fused_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "fh_pp_splice_istft_f32": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _p]),
     "fh_pp_overlap_add_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "fh_ola_crossfade_f32": (_i, [_p, _p, _i, _i, _i, _i64, _p]),

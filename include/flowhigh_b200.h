@@ -71,6 +71,15 @@ int fh_stft_center_f32(const float* x, float* spec, float* energy, const float* 
                        const float* twiddle, int B, int T, int NT, void* stream);
 /* cutoff[b] = postprocessing.py:10-16 applied to energy[b,:] (cumsum, 0.99 threshold) */
 int fh_pp_cutoff(const float* energy, int* cutoff, int B, float threshold, void* stream);
+/* Fused form of the same post-processing (no spectrogram in HBM; two real frames per complex FFT):
+ * fh_pp_src_energy: energy[B,1025] = sum_t |STFT(src)| (workspace of fh_pp_energy_ws_bytes(B, NT) bytes, 8-byte aligned);
+ * fh_pp_fused: per frame STFT(pred), STFT(src) -> splice at cutoff[b] -> inverse FFT -> windowed frames [B,NT,2048]
+ * for fh_pp_overlap_add_f32.  pred [B,Tp] and src [B,T] must span the same NT = 1 + T/480 frames. */
+int fh_pp_energy_ws_bytes(int B, int NT);
+int fh_pp_src_energy_f32(const float* src, float* energy, void* workspace, const float* window, const float* twiddle,
+                         int B, int T, int NT, void* stream);
+int fh_pp_fused_f32(const float* pred, const float* src, const int* cutoff, float* frames, const float* window,
+                    const float* twiddle, int B, int Tp, int T, int NT, void* stream);
 /* frames [B,NT,2048] = window * irfft(f < cutoff[b] ? spec_src : spec_pred) */
 int fh_pp_splice_istft_f32(const float* spec_pred, const float* spec_src, const int* cutoff,
                            float* frames, const float* window, const float* twiddle,

@@ -73,17 +73,26 @@ def test_logmel(cuda_device, sr, precise):
         assert l1_64 <= 2 * floor + 1e-5
 
 
-def test_postprocess(cuda_device):
+@pytest.mark.parametrize("fused", [True, False])
+def test_postprocess(cuda_device, fused):
+    """fused: spectrogram-free path (two real frames per complex FFT, splice + inverse FFT per frame);
+    unfused: STFT(pred), STFT(src) to HBM, energy, splice + iSTFT -- both against the oracle."""
     eng, *_ = engine("gen_basic_midpoint", "fp32")
     torch.manual_seed(0)
-    for T in (480 * 30, 480 * 30 + 123):
-        src = torch.from_numpy(np.stack([synth_speech(T, 48000, 3), synth_speech(T, 48000, 4) * 0.5]))
-        pred = torch.randn(2, 480 * 30) * 0.1
-        out = eng.postprocess(pred.cuda(), src.cuda()).cpu()
-        for i in range(2):
-            ref = dsp.postprocess(pred[i:i + 1], src[i:i + 1], T)
-            assert float((out[i:i + 1] - ref).abs().max()) <= 2e-5
-            assert abs(float(out[i].abs().max()) - 0.99) < 1e-6
+    prev = eng.pp_fused
+    eng.pp_fused = fused
+    try:
+        for T in (480 * 30, 480 * 30 + 123, 480 * 37 + 1):  # odd and even frame counts, pred shorter than src
+            Tp = T // 480 * 480
+            src = torch.from_numpy(np.stack([synth_speech(T, 48000, 3), synth_speech(T, 48000, 4) * 0.5]))
+            pred = torch.randn(2, Tp) * 0.1
+            out = eng.postprocess(pred.cuda(), src.cuda()).cpu()
+            for i in range(2):
+                ref = dsp.postprocess(pred[i:i + 1], src[i:i + 1], T)
+                assert float((out[i:i + 1] - ref).abs().max()) <= 2e-5
+                assert abs(float(out[i].abs().max()) - 0.99) < 1e-6
+    finally:
+        eng.pp_fused = prev
 
 
 # ------------------------------------------------------------------ fp32 kernels
