@@ -49,6 +49,10 @@ class BackboneConfig:
     conv_pos_kernel: int = 31
     qk_norm_scale: float = 10.0   # attend.py:155
     rotary_theta: float = 50000.0  # pos_emb.py:34
+    # transformer.py:123-124,150-153: U-Net style skip connections (OFF in the shipped model): layers of the
+    # second half combine [x, skip * scale] with a Linear(2 dim -> dim) before the attention block
+    use_unet_skip_connection: bool = False
+    skip_connect_scale: float = 2 ** -0.5
 
     @property
     def ff_inner(self) -> int:

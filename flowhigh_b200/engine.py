@@ -184,6 +184,10 @@ class Engine:
             w2 = torch.zeros(b.dim, ip, device=w1.device)
             w2[:, : self.inner] = sd[p + "5.3.weight"]
             L[f"ff2{l}"] = self._mk_tc(packing.linear_taps(w2, sd[p + "5.3.bias"]))
+            if p + "0.weight" in sd:  # U-Net skip combiner Linear(2 dim -> dim) as two accumulating GEMMs (no concat)
+                ws = sd[p + "0.weight"]
+                L[f"skipA{l}"] = self._mk_tc(packing.linear_taps(ws[:, : b.dim].contiguous(), sd[p + "0.bias"]))
+                L[f"skipB{l}"] = self._mk_tc(packing.linear_taps((ws[:, b.dim:] * b.skip_connect_scale).contiguous(), None))
         self.bb_tc = L
 
     def _snake_params(self, prefix: str, cpad: int):
@@ -429,8 +433,30 @@ class Engine:
         wc = sd[FH + "conv_embed.dw_conv1d.0.weight"]
         self._call("fh_dwconv_gelu_res_f32", E.data_ptr(), wc.data_ptr(), sd[FH + "conv_embed.dw_conv1d.0.bias"].data_ptr(),
                    h.data_ptr(), B, N, D, wc.shape[-1], st)
+        skips = []
         for l in range(b.depth):
             p = FH + f"transformer.layers.{l}."
+            if p + "0.weight" in sd:
+                # transformer.py:213-218: x = Linear(cat(x, skip * scale)) = W[:, :D] x + b + (scale W[:, D:]) skip
+                sk = skips.pop()
+                h2 = self.buf("bb_h2", (M, D), zero=False)
+                if self.tc:
+                    self._call("fh_to_chunked_16", h.data_ptr(), 0, 1, D, act.data_ptr(), 0, cs, 0, 1, D, M, self.fp16, st)
+                    self._tc_conv(L[f"skipA{l}"], act, 0, cs, 0, h2, rm(D), 0, 1, M)
+                    self._tc_conv(L[f"skipB{l}"], sk, 0, cs, 0, h, rm(D), 0, 1, M, res=h2, res_strides=rm(D), beta=1.0)
+                else:
+                    ws = sd[p + "0.weight"]
+                    self._sgemm(h, D, ws, 2 * D, sd[p + "0.bias"], None, 0, 0.0, 1.0, h2, D, M, D, D)
+                    self._sgemm(sk, D, ws.data_ptr() + D * 4, 2 * D, None, h2, D, 1.0, float(b.skip_connect_scale), h, D,
+                                M, D, D)
+            elif b.use_unet_skip_connection:
+                if self.tc:
+                    sk = self.buf(f"bb_skip{l}", (D // 8, Mp, 8), self.h16)
+                    self._call("fh_to_chunked_16", h.data_ptr(), 0, 1, D, sk.data_ptr(), 0, cs, 0, 1, D, M, self.fp16, st)
+                else:
+                    sk = self.buf(f"bb_skip{l}", (M, D), zero=False)
+                    self._call("fh_axpby_f32", h.data_ptr(), None, 1.0, 0.0, sk.data_ptr(), M * D, st)
+                skips.append(sk)
             if self.tc:
                 self._call("fh_rmsnorm_f32", h.data_ptr(), tcnd[(l, 2, "gamma")].data_ptr(), tcnd[(l, 2, "beta")].data_ptr(),
                            act.data_ptr(), self.k16, Mp, M, D, st)

@@ -94,7 +94,7 @@ class FLowHigh(_Tree):
 
     def __init__(self, *, audio_enc_dec: Optional[MelVoco] = None, dim_in=None, dim=1024, depth=24, dim_head=64,
                  heads=16, ff_mult=4, conv_pos_embed_kernel_size=31, attn_qk_norm=True, architecture="transformer",
-                 **unused):
+                 use_unet_skip_connection=False, skip_connect_scale=None, **unused):
         super().__init__()
         if architecture != "transformer":
             raise NotImplementedError("architecture='convnext' is not part of the accelerated path")
@@ -103,8 +103,14 @@ class FLowHigh(_Tree):
         if audio_enc_dec is None:
             raise ValueError("audio_enc_dec (MelVoco) is required")
         dim_in = dim if dim_in is None else dim_in
+        # use_unet_skip_connection: the reference's Transformer option (transformer.py:123,150-153); the reference FLowHigh
+        # never forwards it, so it is an extension of this constructor, OFF by default like the checkpoint.
+        if depth % 2:
+            raise ValueError("depth must be even (transformer.py:130)")
         self.bcfg = BackboneConfig(dim_in=dim_in, dim=dim, depth=depth, heads=heads, dim_head=dim_head,
-                                   ff_mult=ff_mult, conv_pos_kernel=conv_pos_embed_kernel_size)
+                                   ff_mult=ff_mult, conv_pos_kernel=conv_pos_embed_kernel_size,
+                                   use_unet_skip_connection=bool(use_unet_skip_connection),
+                                   skip_connect_scale=2 ** -0.5 if skip_connect_scale is None else float(skip_connect_scale))
         if (dim_in, dim, heads, dim_head) != (256, 1024, 16, 64):
             raise ValueError("kernels are specialised for dim_in 256, dim 1024, 16 heads x 64")
         self.audio_enc_dec = audio_enc_dec
@@ -384,11 +390,12 @@ class FlowHighSR(nn.Module):
 
     @classmethod
     def from_random(cls, vcfg: Optional[VocoderConfig] = None, device="cuda", seed: int = 0, precision: str = "fp16",
-                    vocoder_gain: float = 0.7, depth: int = 2, **kw) -> "FlowHighSR":
+                    vocoder_gain: float = 0.7, depth: int = 2, use_unet_skip_connection: bool = False,
+                    **kw) -> "FlowHighSR":
         """Random-init weights of the named architecture (no checkpoints offline)."""
         vcfg = vcfg or VocoderConfig.assumed_48k()
         voc = MelVoco(vocoder_config=vcfg)
-        net = FLowHigh(dim_in=voc.n_mels, audio_enc_dec=voc, depth=depth)
+        net = FLowHigh(dim_in=voc.n_mels, audio_enc_dec=voc, depth=depth, use_unet_skip_connection=use_unet_skip_connection)
         model = cls(flowhigh=net, precision=precision, **kw)
         model.load_state_dict(random_state_dict(net.bcfg, vcfg, seed=seed, vocoder_gain=vocoder_gain))
         return model.to(device).eval()

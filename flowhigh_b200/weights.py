@@ -113,6 +113,9 @@ def state_dict_spec(bcfg: BackboneConfig, vcfg: VocoderConfig) -> List[Tuple[str
     add((FH + "conv_embed.dw_conv1d.0.bias", (D,), "bias"))
     for l in range(bcfg.depth):
         p = FH + f"transformer.layers.{l}."
+        if bcfg.use_unet_skip_connection and l + 1 > bcfg.depth // 2:  # transformer.py:148-151: registered first
+            add((p + "0.weight", (D, 2 * D), "linear"))
+            add((p + "0.bias", (D,), "bias"))
         for idx in (2, 4):
             if idx == 4:
                 # attention (index 3) is registered between the two norms

@@ -69,7 +69,8 @@ def _attention(sd, prefix, x, heads, rot, scale=10.0):
 
 
 def vector_field(sd: Dict[str, torch.Tensor], x: torch.Tensor, cond: torch.Tensor, t: torch.Tensor,
-                 depth: int = 2, heads: int = 16, null_cond: bool = False) -> torch.Tensor:
+                 depth: int = 2, heads: int = 16, null_cond: bool = False,
+                 skip_connect_scale: float = 2 ** -0.5) -> torch.Tensor:
     """FLowHigh.forward (inference branch).  x, cond [B,N,256]; t 0-dim or [B]."""
     B, N, _ = x.shape
     if t.ndim == 0:
@@ -86,8 +87,13 @@ def vector_field(sd: Dict[str, torch.Tensor], x: torch.Tensor, cond: torch.Tenso
     pos_idx = torch.arange(N, dtype=inv_freq.dtype)
     fr = torch.einsum("i,j->ij", pos_idx, inv_freq)
     rot = torch.cat((fr, fr), dim=-1)
+    skips = []
     for l in range(depth):
         p = FH + f"transformer.layers.{l}."
+        if p + "0.weight" in sd:  # transformer.py:213-218 (use_unet_skip_connection): second-half layers pop a skip
+            h = F.linear(torch.cat((h, skips.pop() * skip_connect_scale), dim=-1), sd[p + "0.weight"], sd[p + "0.bias"])
+        else:
+            skips.append(h)
         a = _ada_rmsnorm(sd, p + "2.", h, temb)
         h = _attention(sd, p + "3.", a, heads, rot) + h
         f = _ada_rmsnorm(sd, p + "4.", h, temb)

@@ -91,8 +91,13 @@ def load_reference():
     return _loaded["pkg"]
 
 
-def build_reference_model(sd, vcfg, *, cfm_method="basic_cfm", ode_method="midpoint", sigma=0.0, depth=2):
-    """Reference FlowHighSR with `sd` loaded (strict), bypassing the checkpoint-file loaders."""
+def build_reference_model(sd, vcfg, *, cfm_method="basic_cfm", ode_method="midpoint", sigma=0.0, depth=2,
+                          use_unet_skip_connection=False):
+    """Reference FlowHighSR with `sd` loaded (strict), bypassing the checkpoint-file loaders.
+
+    use_unet_skip_connection: the reference's FLowHigh never forwards that flag to its Transformer, so the
+    unmodified reference `Transformer(..., use_unet_skip_connection=True)` (transformer.py:108-165) is constructed with
+    the arguments of flow.py:109-122 and swapped in before the weights are loaded."""
     pkg = load_reference()
     from flowhigh.models import melvoco as ref_melvoco
     from flowhigh.models.bigvgan.models import BigVGAN
@@ -109,6 +114,12 @@ def build_reference_model(sd, vcfg, *, cfm_method="basic_cfm", ode_method="midpo
     ref_melvoco.init_bigvgan = init_bigvgan
     voc = pkg.models.MelVoco(vocoder_config=None, vocoder_path=None)
     net = pkg.models.FLowHigh(dim_in=voc.n_mels, audio_enc_dec=voc, depth=depth).eval()
+    if use_unet_skip_connection:
+        from flowhigh.models.transformer import Transformer
+        net.transformer = Transformer(dim=1024, depth=depth, dim_head=64, heads=16, ff_mult=4, ff_dropout=0.0,
+                                      attn_dropout=0.0, attn_flash=False, attn_qk_norm=True, adaptive_rmsnorm=True,
+                                      adaptive_rmsnorm_cond_dim_in=1024, use_gateloop_layers=False,
+                                      use_unet_skip_connection=True).eval()
     m = pkg.FlowHighSR(flowhigh=net, cfm_method=cfm_method, torchdiffeq_ode_method=ode_method, sigma=sigma)
     m.load_state_dict(sd, strict=True)
     return m.eval()

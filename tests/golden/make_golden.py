@@ -94,6 +94,31 @@ def vocoder_case(name, vcfg, n_frames, seed):
     print(name, out.shape, "absmax", float(out.abs().max()), "ref-vs-f64 %.3g" % (out - out64).abs().max())
 
 
+def skip_case(name, seed):
+    """Vector field and CFM mel of the U-Net-skip transformer variant from the unmodified reference
+    Transformer(use_unet_skip_connection=True) swapped into FLowHigh (oracle/ref_harness.py)."""
+    vcfg = VocoderConfig.tiny()
+    bcfg = BackboneConfig(use_unet_skip_connection=True)
+    sd = random_state_dict(bcfg, vcfg, seed=seed, vocoder_gain=GAIN)
+    ref = ref_harness.build_reference_model(sd, vcfg, cfm_method="basic_cfm", ode_method="midpoint", sigma=0.0,
+                                            use_unet_skip_connection=True)
+    rng = np.random.default_rng(seed)
+    B, N = 2, 37
+    x = torch.from_numpy(rng.standard_normal((B, N, 256)).astype(np.float32))
+    cond = torch.from_numpy((rng.standard_normal((B, N, 256)) * 2.0 - 5.0).astype(np.float32))
+    v = ref.flowhigh.forward_with_cond_scale(x, times=torch.tensor(0.25), cond=cond)
+    v64 = model.vector_field(sd64(sd), x.double(), cond.double(), torch.tensor(0.25, dtype=torch.float64))
+    mel64 = model.cfm_sample_mel(sd64(sd), cond.double(), x.double(), steps=2, ode_method="midpoint",
+                                 cfm_method="basic_cfm", sigma=0.0)
+    fn = lambda tt, yy: ref.flowhigh.forward_with_cond_scale(yy, times=tt, cond=cond)
+    mel = model.odeint_fixed(fn, x, torch.linspace(0, 1, 3), "midpoint")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x.numpy(), cond=cond.numpy(), ref_vfield_t025=v.detach().numpy(),
+                        f64_vfield_t025=v64.float().numpy(), ref_mel=mel.detach().numpy(), f64_mel=mel64.float().numpy(),
+                        seed=seed, gain=GAIN, vcfg=str(vcfg.to_attr_json()), weight_checksum=checksum(sd))
+    print(name, "vfield absmax", float(v.abs().max()), "ref-vs-f64 vfield %.3g mel %.3g" % ((v - v64).abs().max(),
+                                                                                          (mel - mel64).abs().max()))
+
+
 def frontend_case(name):
     import scipy.signal
     d = {}
@@ -128,3 +153,4 @@ if __name__ == "__main__":
     generate_case("gen_basic_euler4", VocoderConfig.tiny(), 24000, 12240, 4, "basic_cfm", "euler", 0.0, seed=3)
     vocoder_case("voc_resblock2_snake", VocoderConfig.tiny(resblock="2", activation="snake", logscale=False), 24, seed=4)
     vocoder_case("voc_resblock1_snakebeta", VocoderConfig.tiny(), 30, seed=5)
+    skip_case("vf_unet_skip", seed=6)

@@ -12,7 +12,7 @@ from flowhigh_b200.engine import Engine, HALO
 from flowhigh_b200.synth import synth_speech
 from flowhigh_b200.weights import random_state_dict
 from oracle import dsp, model, pipeline
-from util import golden_weights, load_golden, lsd_db, snr_db
+from util import golden_weights, load_golden, lsd_db, snr_db, vcfg_from_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -610,3 +610,31 @@ def test_from_local_wav_in_wav_out(cuda_device, tmp_path):
     save_wav(tmp_path / "out.wav", out.cpu(), 48000)
     back, sr_out = load_wav(tmp_path / "out.wav")
     assert sr_out == 48000 and float((back - out.cpu()).abs().max()) <= 1.0 / 32768
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_unet_skip_variant(cuda_device, precision):
+    """Transformer(use_unet_skip_connection=True) on the engine (two accumulating GEMMs instead of cat + Linear)
+    against the golden of the reference Transformer (tests/golden/vf_unet_skip.npz)."""
+    g = load_golden("vf_unet_skip")
+    vcfg = vcfg_from_golden(g)
+    bcfg = BackboneConfig(use_unet_skip_connection=True)
+    sd = random_state_dict(bcfg, vcfg, seed=int(g["seed"]), vocoder_gain=float(g["gain"]))
+    m = FlowHighSR.from_random(vcfg, device="cuda:0", precision=precision, use_unet_skip_connection=True)
+    m.load_state_dict(sd)
+    x, cond = dev(g["x"]), dev(g["cond"])
+    v = m.flowhigh.forward_with_cond_scale(x, times=torch.tensor(0.25), cond=cond).cpu()
+    ref, f64 = torch.from_numpy(g["ref_vfield_t025"]), torch.from_numpy(g["f64_vfield_t025"])
+    err = float((v - f64).abs().max())
+    print(f"unet-skip vector field {precision}: max-abs vs fp64 {err:.3g} (reference fp32: {float((ref - f64).abs().max()):.3g})")
+    if precision == "fp32":
+        assert err <= 1e-4
+    else:
+        assert snr_db(f64, v) >= 40.0
+    eng = m._engine()
+    mel = eng.sample_mel(cond, x, steps=2, ode_method="midpoint", cfm_method="basic_cfm", sigma=0.0).cpu()
+    mref = torch.from_numpy(g["f64_mel"])
+    if precision == "fp32":
+        assert float((mel - mref).abs().mean()) <= 1e-4
+    else:
+        assert snr_db(mref, mel) >= 40.0

@@ -14,7 +14,7 @@ from flowhigh_b200.config import BackboneConfig, VocoderConfig
 from flowhigh_b200.synth import synth_speech
 from flowhigh_b200.weights import kaiser_sinc_filter12, random_state_dict, state_dict_spec, fold_weight_norm
 from oracle import dsp, model, pipeline
-from util import golden_weights, load_golden
+from util import golden_weights, load_golden, vcfg_from_golden
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -190,3 +190,28 @@ def test_c_abi_exports_every_declared_symbol():
     assert lib.fh_version() == 1
     lib.fh_tc_packed_weight_bytes.restype = ctypes.c_int64
     assert lib.fh_tc_packed_weight_bytes(32, 48, 3, 1, 48) == 1 * 1 * 2 * 3 * 48 * 32
+
+
+def test_unet_skip_variant_pinned_against_reference_transformer():
+    """Transformer(use_unet_skip_connection=True).  The golden was produced by the unmodified
+    reference Transformer swapped into the reference FLowHigh (oracle/ref_harness.py); the oracle must reproduce it and
+    the state_dict must carry the combiner keys at the reference's position (first in the layer)."""
+    from flowhigh_b200.config import BackboneConfig
+    g = load_golden("vf_unet_skip")
+    vcfg = vcfg_from_golden(g)
+    bcfg = BackboneConfig(use_unet_skip_connection=True)
+    sd = random_state_dict(bcfg, vcfg, seed=int(g["seed"]), vocoder_gain=float(g["gain"]))
+    cs = float(sum(v.double().abs().sum().item() for k, v in sd.items() if k.endswith("weight")))
+    assert abs(cs - float(g["weight_checksum"])) <= 1e-6 * abs(cs)
+    keys = [k for k in sd if ".transformer.layers.1." in k]
+    assert keys[0].endswith("layers.1.0.weight") and keys[1].endswith("layers.1.0.bias")
+    assert sd[keys[0]].shape == (1024, 2048) and not any(".layers.0.0." in k for k in sd)
+    x, cond = torch.from_numpy(g["x"]), torch.from_numpy(g["cond"])
+    sd64 = {k: v.double() for k, v in sd.items()}
+    v64 = model.vector_field(sd64, x.double(), cond.double(), torch.tensor(0.25, dtype=torch.float64))
+    assert float((v64.float() - torch.from_numpy(g["f64_vfield_t025"])).abs().max()) <= 1e-6
+    assert float((v64.float() - torch.from_numpy(g["ref_vfield_t025"])).abs().max()) <= 1e-4   # reference fp32 noise
+    v32 = model.vector_field(sd, x, cond, torch.tensor(0.25))
+    assert float((v32 - torch.from_numpy(g["ref_vfield_t025"])).abs().max()) <= 1e-4
+    # without the flag the keys are absent and the default layout is unchanged (711 keys for the assumed config)
+    assert not any(".layers.1.0." in k for k in random_state_dict(BackboneConfig(), vcfg, seed=0))
