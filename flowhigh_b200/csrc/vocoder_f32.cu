@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(SN_T) snake_aa_kernel(const float* __restrict_
   }
   __syncthreads();
   const float al = a[c], ib = inv_b[c];
-  // s window: m in [2*q0-5, 2*q0 + 2*SN_T + 6]; clamped to [0, 2L-1] (replicate pad of the 2x signal)
-  for (int i = threadIdx.x; i < 2 * SN_T + 11; i += SN_T) {
+  // s window: m in [2*q0-5, 2*q0 + 2*SN_T + 4]; clamped to [0, 2L-1] (replicate pad of the 2x signal)
+  for (int i = threadIdx.x; i < 2 * SN_T + 10; i += SN_T) {  // outputs read ss[2 t + k], k < 12: indices 0 .. 2 SN_T + 9
     int m = 2 * q0 - 5 + i;
     m = min(max(m, 0), 2 * L - 1);
     const int q = m >> 1;
