@@ -31,6 +31,7 @@ class TcConvArgs(C.Structure):
         ("bn", _i),
         ("fp16", _i),
         ("x_f32", _p), ("sn_a", _p), ("sn_inv_b", _p), ("sn_filt", _p),
+        ("act", _i),
     ]
 
 
@@ -56,6 +57,9 @@ SIGNATURES = {
     "fh_gemv_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),
     "fh_sincos_embed_f32": (_i, [_p, _f, _p, _i, _p]),
     "fh_dwconv_gelu_res_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "fh_dwconv_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "fh_layernorm_f32": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _f, _p]),
+    "fh_gelu_f32": (_i, [_p, _p, _i, _i64, _i, _i, _p]),
     "fh_rmsnorm_f32": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _p]),
     "fh_qknorm_rope_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "fh_attention_f32": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _f, _p]),

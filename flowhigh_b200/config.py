@@ -52,6 +52,11 @@ class BackboneConfig:
     # transformer.py:123-124,150-153: U-Net style skip connections (OFF in the shipped model): layers of the
     # second half combine [x, skip * scale] with a Linear(2 dim -> dim) before the attention block
     use_unet_skip_connection: bool = False
+    # flow.py:124-139: alternative vector-field network, 8 ConvNeXt blocks (dwconv7 -> AdaLayerNorm -> Linear 3x -> GELU ->
+    # Linear -> layer scale -> residual) + final LayerNorm instead of the transformer (not used by the shipped checkpoint)
+    architecture: str = "transformer"
+    convnext_layers: int = 8
+    convnext_mult: int = 3
     skip_connect_scale: float = 2 ** -0.5
 
     @property

@@ -89,8 +89,9 @@ __global__ void sincos_embed_kernel(const float* __restrict__ w, float t, float*
 // HBM-bound (one fp32 read + one write per element).  A thread owns one channel and kDwT consecutive time steps:
 // the kDwT + K - 1 inputs it needs are loaded once into registers (coalesced over the 128 channels of the block,
 // halo re-reads between neighbouring tiles are L2 hits) and all K taps run from registers, fully unrolled.
+// GELU_RES = false: plain depthwise Conv1d + bias (ConvNeXtBlock.dwconv, convnext.py:29,47).
 constexpr int kDwT = 32;
-template <int K>
+template <int K, bool GELU_RES>
 __global__ void __launch_bounds__(128) dwconv_gelu_res_kernel(const float* __restrict__ E, const float* __restrict__ w,
                                                               const float* __restrict__ b, float* __restrict__ out, int N,
                                                               int C) {
@@ -116,14 +117,15 @@ __global__ void __launch_bounds__(128) dwconv_gelu_res_kernel(const float* __res
       float acc = bias;
 #pragma unroll
       for (int j = 0; j < K; ++j) acc = fmaf(wr[j], x[t + j], acc);
-      o[(size_t)t * C] = x[t + half] + fh::gelu_erf(acc);
+      o[(size_t)t * C] = GELU_RES ? x[t + half] + fh::gelu_erf(acc) : acc;
     }
   }
 }
 
 // any odd kernel size (the checkpoint uses 31)
 __global__ void dwconv_gelu_res_generic_kernel(const float* __restrict__ E, const float* __restrict__ w,
-                                               const float* __restrict__ b, float* __restrict__ out, int N, int C, int k) {
+                                               const float* __restrict__ b, float* __restrict__ out, int N, int C, int k,
+                                               int gelu_res) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = blockIdx.y, bi = blockIdx.z;
   if (c >= C) return;
@@ -134,7 +136,55 @@ __global__ void dwconv_gelu_res_generic_kernel(const float* __restrict__ E, cons
     const int nn = n + j - half;
     if (nn >= 0 && nn < N) acc = fmaf(__ldg(w + (size_t)c * k + j), __ldg(e + (size_t)nn * C + c), acc);
   }
-  out[((size_t)bi * N + n) * C + c] = e[(size_t)n * C + c] + fh::gelu_erf(acc);
+  out[((size_t)bi * N + n) * C + c] = gelu_res ? e[(size_t)n * C + c] + fh::gelu_erf(acc) : acc;
+}
+
+// ------------------------------------------------------------------------------ LayerNorm / AdaLayerNorm
+// y = (x - mean) / sqrt(var + eps) * w + b  (F.layer_norm, biased variance).  AdaLayerNorm (convnext.py:86-93) is the
+// same kernel with w = scale(t), b = shift(t).  One warp per row, the row lives in registers (C <= 1024);
+// out_mode 0 -> fp32 row-major, 1 / 2 -> bf16 / fp16 chunked [C/8][rows][8].
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                 void* __restrict__ out, int out_mode, int64_t out_rows, int M, int C, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + (size_t)row * C;
+  float v[32];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = c < C ? xr[c] : 0.f;
+    s += v[i];
+  }
+  const float mean = fh::warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    const float d = c < C ? v[i] - mean : 0.f;
+    q = fmaf(d, d, q);
+  }
+  const float inv = rsqrtf(fh::warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    const int c = lane + 32 * i;
+    if (c >= C) break;
+    float y = (v[i] - mean) * inv * w[c];
+    if (b) y += b[c];
+    if (out_mode == 0) ((float*)out)[(size_t)row * C + c] = y;
+    else ((unsigned short*)out)[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16(y, out_mode == 2);
+  }
+}
+
+// exact-erf GELU, fp32 row-major in -> fp32 row-major (out_mode 0) or 16-bit chunked (nn.GELU, convnext.py:36)
+__global__ void gelu_kernel(const float* __restrict__ x, void* __restrict__ out, int out_mode, int64_t out_rows, int M, int C) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * C) return;
+  const int row = (int)(i / C), c = (int)(i % C);
+  const float y = fh::gelu_erf(x[i]);
+  if (out_mode == 0) ((float*)out)[i] = y;
+  else ((unsigned short*)out)[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16(y, out_mode == 2);
 }
 
 // ------------------------------------------------------------------------------ (adaptive) RMS norm
@@ -410,10 +460,37 @@ extern "C" __attribute__((visibility("default"))) int fh_dwconv_gelu_res_f32(con
   FH_REQUIRE(B > 0 && N > 0 && C > 0 && (k & 1), FH_ERR_BAD_SHAPE, "fh_dwconv_gelu_res_f32: kernel size must be odd");
   FH_REQUIRE(N <= 65535 && B <= 65535, FH_ERR_BAD_SHAPE, "fh_dwconv_gelu_res_f32: N, B must be <= 65535");
   if (k == 31)
-    dwconv_gelu_res_kernel<31><<<dim3((C + 127) / 128, (N + kDwT - 1) / kDwT, B), 128, 0, (cudaStream_t)stream>>>(E, w, b, out, N, C);
+    dwconv_gelu_res_kernel<31, true><<<dim3((C + 127) / 128, (N + kDwT - 1) / kDwT, B), 128, 0, (cudaStream_t)stream>>>(E, w, b, out, N, C);
   else
-    dwconv_gelu_res_generic_kernel<<<dim3((C + 255) / 256, N, B), 256, 0, (cudaStream_t)stream>>>(E, w, b, out, N, C, k);
+    dwconv_gelu_res_generic_kernel<<<dim3((C + 255) / 256, N, B), 256, 0, (cudaStream_t)stream>>>(E, w, b, out, N, C, k, 1);
   return fh::check_launch("fh_dwconv_gelu_res_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_dwconv_f32(const float* x, const float* w, const float* b, float* out, int B, int N, int C,
+                             int k, void* stream) {
+  FH_REQUIRE(B > 0 && N > 0 && C > 0 && (k & 1), FH_ERR_BAD_SHAPE, "fh_dwconv_f32: kernel size must be odd");
+  FH_REQUIRE(N <= 65535 && B <= 65535 && x != out, FH_ERR_BAD_SHAPE, "fh_dwconv_f32: N, B must be <= 65535, out of place");
+  if (k == 7)
+    dwconv_gelu_res_kernel<7, false><<<dim3((C + 127) / 128, (N + kDwT - 1) / kDwT, B), 128, 0, (cudaStream_t)stream>>>(x, w, b, out, N, C);
+  else
+    dwconv_gelu_res_generic_kernel<<<dim3((C + 255) / 256, N, B), 256, 0, (cudaStream_t)stream>>>(x, w, b, out, N, C, k, 0);
+  return fh::check_launch("fh_dwconv_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_layernorm_f32(const float* x, const float* w, const float* b, void* out, int out_mode,
+                                int64_t out_rows, int M, int C, float eps, void* stream) {
+  FH_REQUIRE(M > 0 && C > 0 && C <= 1024 && w != nullptr && (out_mode == 0 || (C % 8 == 0 && out_rows >= M)), FH_ERR_BAD_SHAPE,
+             "fh_layernorm_f32: bad shape (C <= 1024)");
+  layernorm_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, w, b, out, out_mode, out_rows, M, C, eps);
+  return fh::check_launch("fh_layernorm_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_gelu_f32(const float* x, void* out, int out_mode, int64_t out_rows, int M, int C,
+                           void* stream) {
+  FH_REQUIRE(M > 0 && C > 0 && (out_mode == 0 || (C % 8 == 0 && out_rows >= M)), FH_ERR_BAD_SHAPE, "fh_gelu_f32: bad shape");
+  const long long n = (long long)M * C;
+  gelu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, out_mode, out_rows, M, C);
+  return fh::check_launch("fh_gelu_f32");
 }
 
 extern "C" __attribute__((visibility("default"))) int fh_rmsnorm_f32(const float* x, const float* gamma, const float* beta, void* out, int out_mode,

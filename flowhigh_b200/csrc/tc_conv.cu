@@ -39,6 +39,7 @@ struct TcParams {
   long long res_batch, res_chunk, res_row;
   int a_row0;
   int out_is_16, res_is_16, fp16, accumulate, geglu;
+  int act_gelu;        // exact-erf GELU on (acc + bias) * alpha before the residual (ConvNeXt pwconv1)
   float alpha, beta_res;
   int B, L, Cin, Cout, ntaps, P, bn;
   int m_tiles, n_tiles, total_tiles;
@@ -320,6 +321,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
           float acc = __uint_as_float(v[hh * 8 + i]);
           if (P.bias) acc += __ldg(P.bias + n0 + i);
           o[i] = acc * P.alpha;
+          if (P.act_gelu) o[i] = gelu_f(o[i]);
           if (use_res) o[i] = fmaf(P.beta_res, rr[hh * 8 + i], o[i]);
         }
         const long long idx = out_b + (long long)(n0 >> 3) * P.out_chunk + orow * P.out_row;
@@ -1155,6 +1157,8 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   p.res_batch = a->res_batch, p.res_chunk = a->res_chunk, p.res_row = a->res_row;
   p.out_is_16 = a->out_is_16, p.res_is_16 = a->res_is_16, p.fp16 = a->fp16;
   p.accumulate = a->accumulate, p.geglu = a->geglu;
+  p.act_gelu = a->act == 1;
+  FH_REQUIRE(a->act == 0 || (a->act == 1 && !a->geglu), FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: act must be 0 (none) or 1 (GELU, not with geglu)");
   p.alpha = a->alpha, p.beta_res = a->beta_res;
   p.B = a->B, p.L = a->L, p.Cin = a->Cin, p.Cout = a->Cout, p.ntaps = a->ntaps, p.P = a->P, p.bn = a->bn;
   p.n_tiles = (a->Cout + a->bn - 1) / a->bn;
@@ -1313,7 +1317,7 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
     fast_on = e ? atoi(e) : 1;
   }
   const int bias_tab = a->bias ? ((p.n_tiles * a->bn + 15) & ~15) * 4 : 64;
-  p.fast_epi = (fast_on && p.v8 && !a->geglu && !a->out_is_16 && !(a->res && a->res_is_16) && bias_tab <= 8192) ? 1 : 0;
+  p.fast_epi = (fast_on && p.v8 && !a->geglu && !p.act_gelu && !a->out_is_16 && !(a->res && a->res_is_16) && bias_tab <= 8192) ? 1 : 0;
   const int tail = p.fast_epi ? bias_tab : 0;
   int stages = (budget - 1024 - tail) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;

@@ -163,10 +163,22 @@ class Engine:
         self.inner = b.ff_inner
         self.inner_pad = packing.round_up(self.inner, 16)
         if not self.tc:
+            if b.architecture == "convnext":  # fp32 path: gamma * (W2 x + b2) folded once
+                self.cn_f32 = [((sd[FH + f"convnext.{i}.pwconv2.weight"] * sd[FH + f"convnext.{i}.gamma"][:, None]).contiguous(),
+                                (sd[FH + f"convnext.{i}.pwconv2.bias"] * sd[FH + f"convnext.{i}.gamma"]).contiguous())
+                               for i in range(b.convnext_layers)]
             return
         L = {}
         L["to_embed"] = self._mk_tc(packing.linear_taps(sd[FH + "to_embed.weight"], sd[FH + "to_embed.bias"]))
         L["to_pred"] = self._mk_tc(packing.linear_taps(sd[FH + "to_pred.weight"], None))
+        if b.architecture == "convnext":
+            for i in range(b.convnext_layers):
+                p = FH + f"convnext.{i}."
+                L[f"pw1{i}"] = self._mk_tc(packing.linear_taps(sd[p + "pwconv1.weight"], sd[p + "pwconv1.bias"]))
+                gm = sd[p + "gamma"]  # layer scale folded into the second pointwise conv: gamma * (W x + b)
+                L[f"pw2{i}"] = self._mk_tc(packing.linear_taps(sd[p + "pwconv2.weight"] * gm[:, None], sd[p + "pwconv2.bias"] * gm))
+            self.bb_tc = L
+            return
         for l in range(b.depth):
             p = FH + f"transformer.layers.{l}."
             L[f"qkv{l}"] = self._mk_tc(packing.linear_taps(sd[p + "3.to_qkv.weight"], None))
@@ -299,6 +311,15 @@ class Engine:
         self._call("fh_gemv_f32", sd[FH + "sinu_pos_emb.1.weight"].data_ptr(), four.data_ptr(),
                    sd[FH + "sinu_pos_emb.1.bias"].data_ptr(), temb.data_ptr(), D, D, 1, self.stream)
         out = {}
+        if b.architecture == "convnext":  # AdaLayerNorm scale(t), shift(t) of every block (convnext.py:86-88)
+            for i in range(b.convnext_layers):
+                for nm in ("scale", "shift"):
+                    v = torch.empty(D, device=self.device)
+                    self._call("fh_gemv_f32", sd[FH + f"convnext.{i}.norm.{nm}.weight"].data_ptr(), temb.data_ptr(),
+                               sd[FH + f"convnext.{i}.norm.{nm}.bias"].data_ptr(), v.data_ptr(), D, D, 0, self.stream)
+                    out[(i, nm)] = v
+            self._time_cache[key] = out
+            return out
         for l in range(b.depth):
             for idx in (2, 4):
                 p = FH + f"transformer.layers.{l}.{idx}."
@@ -311,7 +332,7 @@ class Engine:
         return out
 
     def _tc_conv(self, rec: _TcWeight, a, a_batch, a_chunk, a_row0, out, out_strides, out_bf16, B, L, res=None,
-                 res_strides=(0, 0, 0), res_bf16=0, alpha=1.0, beta=0.0, accumulate=0, geglu=0, xf=None, snake=None):
+                 res_strides=(0, 0, 0), res_bf16=0, alpha=1.0, beta=0.0, accumulate=0, geglu=0, xf=None, snake=None, act=0):
         args = _lib.TcConvArgs()
         args.a, args.a_batch, args.a_chunk, args.a_row0 = _ptr(a), a_batch, a_chunk, a_row0
         if xf is not None:  # fused anti-aliased snake prologue: A = Activation1d(xf), computed in the kernel
@@ -323,6 +344,7 @@ class Engine:
         args.res_batch, args.res_chunk, args.res_row = res_strides
         args.out_is_16, args.res_is_16, args.fp16 = int(out_bf16), int(res_bf16), self.fp16
         args.alpha, args.beta_res, args.accumulate, args.geglu = alpha, beta, int(accumulate), int(geglu)
+        args.act = int(act)
         args.B, args.L, args.Cin, args.Cout = B, L, rec.cin_pad, rec.cout_pad
         args.ntaps, args.P, args.tap_off, args.bn = rec.ntaps, rec.P, rec.off_c, rec.bn
         flops = 2.0 * B * L * rec.P * rec.ntaps * rec.cin * rec.cout
@@ -433,6 +455,19 @@ class Engine:
         wc = sd[FH + "conv_embed.dw_conv1d.0.weight"]
         self._call("fh_dwconv_gelu_res_f32", E.data_ptr(), wc.data_ptr(), sd[FH + "conv_embed.dw_conv1d.0.bias"].data_ptr(),
                    h.data_ptr(), B, N, D, wc.shape[-1], st)
+        if b.architecture == "convnext":
+            self._convnext_blocks(h, tcnd, B, N, M, D, act if self.tc else None, cs if self.tc else 0, Mp if self.tc else 0)
+            fw, fb = sd[FH + "final_layer_norm.weight"], sd[FH + "final_layer_norm.bias"]
+            if self.tc:
+                self._call("fh_layernorm_f32", h.data_ptr(), fw.data_ptr(), fb.data_ptr(), act.data_ptr(), self.k16, Mp, M, D,
+                           1e-6, st)
+                self._tc_conv(L["to_pred"], act, 0, cs, 0, out, rm(Din), 0, 1, M, res=base, res_strides=rm(Din), alpha=coef,
+                              beta=1.0)
+            else:
+                a = self.buf("bb_a", (M, D), zero=False)
+                self._call("fh_layernorm_f32", h.data_ptr(), fw.data_ptr(), fb.data_ptr(), a.data_ptr(), 0, 0, M, D, 1e-6, st)
+                self._sgemm(a, D, sd[FH + "to_pred.weight"], D, None, base, Din, 1.0, coef, out, Din, M, Din, D)
+            return
         skips = []
         for l in range(b.depth):
             p = FH + f"transformer.layers.{l}."
@@ -510,6 +545,33 @@ class Engine:
             a = self.buf("bb_a", (M, D), zero=False)
             self._call("fh_rmsnorm_f32", h.data_ptr(), gam.data_ptr(), None, a.data_ptr(), 0, 0, M, D, st)
             self._sgemm(a, D, sd[FH + "to_pred.weight"], D, None, base, Din, 1.0, coef, out, Din, M, Din, D)
+
+    def _convnext_blocks(self, h, tcnd, B, N, M, D, act, cs, Mp):
+        """8 x ConvNeXtBlock (convnext.py:46-63): h += gamma * pwconv2(gelu(pwconv1(AdaLN(dwconv7(h); t)))), in place."""
+        sd, b, st = self.sd, self.bcfg, self.stream
+        I = D * b.convnext_mult
+        y = self.buf("bb_cn_y", (M, D), zero=False)
+        rm = lambda ld: (0, 8, ld)
+        for i in range(b.convnext_layers):
+            p = FH + f"convnext.{i}."
+            self._call("fh_dwconv_f32", h.data_ptr(), sd[p + "dwconv.weight"].data_ptr(), sd[p + "dwconv.bias"].data_ptr(),
+                       y.data_ptr(), B, N, D, 7, st)
+            if self.tc:
+                L = self.bb_tc
+                g = self.buf("bb_cn_g", (I // 8, Mp, 8), self.h16)
+                self._call("fh_layernorm_f32", y.data_ptr(), tcnd[(i, "scale")].data_ptr(), tcnd[(i, "shift")].data_ptr(),
+                           act.data_ptr(), self.k16, Mp, M, D, 1e-6, st)
+                self._tc_conv(L[f"pw1{i}"], act, 0, cs, 0, g, (0, cs, 8), 1, 1, M, act=1)
+                self._tc_conv(L[f"pw2{i}"], g, 0, cs, 0, h, rm(D), 0, 1, M, res=h, res_strides=rm(D), beta=1.0)
+            else:
+                a = self.buf("bb_a", (M, D), zero=False)
+                u = self.buf("bb_cn_u", (M, I), zero=False)
+                self._call("fh_layernorm_f32", y.data_ptr(), tcnd[(i, "scale")].data_ptr(), tcnd[(i, "shift")].data_ptr(),
+                           a.data_ptr(), 0, 0, M, D, 1e-6, st)
+                self._sgemm(a, D, sd[p + "pwconv1.weight"], D, sd[p + "pwconv1.bias"], None, 0, 0.0, 1.0, u, I, M, I, D)
+                self._call("fh_gelu_f32", u.data_ptr(), u.data_ptr(), 0, 0, M, I, st)
+                w2, b2 = self.cn_f32[i]  # layer scale folded into pwconv2 at load time
+                self._sgemm(u, I, w2, I, b2, h, D, 1.0, 1.0, h, D, M, D, I)
 
     def mel_cutoff_bins(self, cond_mel: torch.Tensor) -> torch.Tensor:
         """mel_cutoff_bins (cfm_superresolution.py:154-159): per-clip 99.95 % energy bin of exp(mel)."""

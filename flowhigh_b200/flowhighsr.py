@@ -90,14 +90,14 @@ class MelVoco(_Tree):
 
 
 class FLowHigh(_Tree):
-    """models/flow.py:55-142 (transformer architecture only; convnext is a SURVEY 8f row)."""
+    """models/flow.py:55-142: vector-field network, `architecture` = 'transformer' (the checkpoint) or 'convnext'."""
 
     def __init__(self, *, audio_enc_dec: Optional[MelVoco] = None, dim_in=None, dim=1024, depth=24, dim_head=64,
                  heads=16, ff_mult=4, conv_pos_embed_kernel_size=31, attn_qk_norm=True, architecture="transformer",
                  use_unet_skip_connection=False, skip_connect_scale=None, **unused):
         super().__init__()
-        if architecture != "transformer":
-            raise NotImplementedError("architecture='convnext' is not part of the accelerated path")
+        if architecture not in ("transformer", "convnext"):
+            raise ValueError("Choose approriate architecture")  # flow.py:84-85
         if not attn_qk_norm:
             raise NotImplementedError("the attention kernels implement the qk-norm variant the checkpoint uses")
         if audio_enc_dec is None:
@@ -109,6 +109,7 @@ class FLowHigh(_Tree):
             raise ValueError("depth must be even (transformer.py:130)")
         self.bcfg = BackboneConfig(dim_in=dim_in, dim=dim, depth=depth, heads=heads, dim_head=dim_head,
                                    ff_mult=ff_mult, conv_pos_kernel=conv_pos_embed_kernel_size,
+                                   architecture=architecture,
                                    use_unet_skip_connection=bool(use_unet_skip_connection),
                                    skip_connect_scale=2 ** -0.5 if skip_connect_scale is None else float(skip_connect_scale))
         if (dim_in, dim, heads, dim_head) != (256, 1024, 16, 64):
@@ -391,11 +392,12 @@ class FlowHighSR(nn.Module):
     @classmethod
     def from_random(cls, vcfg: Optional[VocoderConfig] = None, device="cuda", seed: int = 0, precision: str = "fp16",
                     vocoder_gain: float = 0.7, depth: int = 2, use_unet_skip_connection: bool = False,
-                    **kw) -> "FlowHighSR":
+                    architecture: str = "transformer", **kw) -> "FlowHighSR":
         """Random-init weights of the named architecture (no checkpoints offline)."""
         vcfg = vcfg or VocoderConfig.assumed_48k()
         voc = MelVoco(vocoder_config=vcfg)
-        net = FLowHigh(dim_in=voc.n_mels, audio_enc_dec=voc, depth=depth, use_unet_skip_connection=use_unet_skip_connection)
+        net = FLowHigh(dim_in=voc.n_mels, audio_enc_dec=voc, depth=depth, use_unet_skip_connection=use_unet_skip_connection,
+                       architecture=architecture)
         model = cls(flowhigh=net, precision=precision, **kw)
         model.load_state_dict(random_state_dict(net.bcfg, vcfg, seed=seed, vocoder_gain=vocoder_gain))
         return model.to(device).eval()

@@ -111,6 +111,25 @@ def state_dict_spec(bcfg: BackboneConfig, vcfg: VocoderConfig) -> List[Tuple[str
     add((FH + "to_embed.bias", (D,), "bias"))
     add((FH + "conv_embed.dw_conv1d.0.weight", (D, 1, bcfg.conv_pos_kernel), "dwconv"))
     add((FH + "conv_embed.dw_conv1d.0.bias", (D,), "bias"))
+    if bcfg.architecture == "convnext":  # flow.py:124-139, convnext.py:9-93; a module's own parameter (gamma) comes first
+        I = D * bcfg.convnext_mult
+        for i in range(bcfg.convnext_layers):
+            p = FH + f"convnext.{i}."
+            add((p + "gamma", (D,), "gamma1"))
+            add((p + "dwconv.weight", (D, 1, 7), "dwconv"))
+            add((p + "dwconv.bias", (D,), "bias"))
+            add((p + "norm.scale.weight", (D, D), "adaw"))   # zero / one initialised in the reference (convnext.py:79-82):
+            add((p + "norm.scale.bias", (D,), "gamma1"))     # perturbed here so that the time conditioning is exercised
+            add((p + "norm.shift.weight", (D, D), "adaw"))
+            add((p + "norm.shift.bias", (D,), "small"))
+            add((p + "pwconv1.weight", (I, D), "linear"))
+            add((p + "pwconv1.bias", (I,), "bias"))
+            add((p + "pwconv2.weight", (D, I), "linear"))
+            add((p + "pwconv2.bias", (D,), "bias"))
+        add((FH + "final_layer_norm.weight", (D,), "gamma1"))
+        add((FH + "final_layer_norm.bias", (D,), "small"))
+        add((FH + "to_pred.weight", (Din, D), "linear"))
+        return spec
     for l in range(bcfg.depth):
         p = FH + f"transformer.layers.{l}."
         if bcfg.use_unet_skip_connection and l + 1 > bcfg.depth // 2:  # transformer.py:148-151: registered first

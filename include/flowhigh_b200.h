@@ -109,6 +109,16 @@ int fh_sincos_embed_f32(const float* w, float t, float* out, int half, void* str
 /* out = E + gelu(dwconv_k(E) + b) over time, E [B,N,C], w [C,k]   transformer.py:33-46, flow.py:240 */
 int fh_dwconv_gelu_res_f32(const float* E, const float* w, const float* b, float* out,
                            int B, int N, int C, int k, void* stream);
+/* ConvNeXt variant of the vector field (models/convnext.py:9-93, flow.py:124-139,247-253):
+ * fh_dwconv_f32: depthwise Conv1d over time, odd k (7 in ConvNeXtBlock), zero padding, + bias; [B,N,C] fp32, out of place.
+ * fh_layernorm_f32: F.layer_norm(x, eps) * w + b per row (AdaLayerNorm with w = scale(t), b = shift(t); b may be NULL);
+ *   out_mode as in fh_rmsnorm_f32.
+ * fh_gelu_f32: exact-erf GELU, fp32 row-major in, out_mode as in fh_rmsnorm_f32. */
+int fh_dwconv_f32(const float* x, const float* w, const float* b, float* out, int B, int N, int C, int k, void* stream);
+int fh_layernorm_f32(const float* x, const float* w, const float* b, void* out, int out_mode, int64_t out_rows,
+                     int M, int C, float eps, void* stream);
+int fh_gelu_f32(const float* x, void* out, int out_mode, int64_t out_rows, int M, int C, void* stream);
+
 /* out = x / max(||x||,1e-12) * sqrt(C) * gamma + beta (beta may be NULL)   transformer.py:49-59,82-88
  * out_mode 0: fp32 row-major [M,C];  1: bf16 chunked [C/8][Mp][8] (row pitch out_rows);  2: fp16 chunked. */
 int fh_rmsnorm_f32(const float* x, const float* gamma, const float* beta, void* out, int out_mode,
@@ -197,6 +207,7 @@ typedef struct {
   const float* sn_a;      /* [Cin] alpha (already exp'd when logscale) */
   const float* sn_inv_b;  /* [Cin] 1 / (beta + 1e-9) */
   const float* sn_filt;   /* [12] Kaiser-sinc taps */
+  int act;                /* 0 none, 1 exact-erf GELU on (acc + bias) * alpha, before the residual (convnext.py:56-57) */
 } fh_tc_conv_args;
 int fh_tc_conv(const fh_tc_conv_args* args, void* stream);
 /* One launch = fh_tc_conv(args) for one half-batch + fh_snake_aa_chunked(sx -> sy, 16-bit out) for an independent

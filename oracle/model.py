@@ -83,6 +83,21 @@ def vector_field(sd: Dict[str, torch.Tensor], x: torch.Tensor, cond: torch.Tenso
                    padding=wc.shape[-1] // 2, groups=wc.shape[0])
     h = F.gelu(pos).transpose(1, 2) + emb
     temb = time_embedding(sd, t)
+    if FH + "convnext.0.gamma" in sd:  # architecture == 'convnext' (flow.py:247-253, convnext.py:46-63,86-93)
+        i = 0
+        while FH + f"convnext.{i}.gamma" in sd:
+            p = FH + f"convnext.{i}."
+            y = F.conv1d(h.transpose(1, 2), sd[p + "dwconv.weight"], sd[p + "dwconv.bias"], padding=3,
+                         groups=h.shape[-1]).transpose(1, 2)
+            scale = F.linear(temb, sd[p + "norm.scale.weight"], sd[p + "norm.scale.bias"])[:, None, :]
+            shift = F.linear(temb, sd[p + "norm.shift.weight"], sd[p + "norm.shift.bias"])[:, None, :]
+            y = F.layer_norm(y, (y.shape[-1],), eps=1e-6) * scale + shift
+            y = F.linear(F.gelu(F.linear(y, sd[p + "pwconv1.weight"], sd[p + "pwconv1.bias"])), sd[p + "pwconv2.weight"],
+                         sd[p + "pwconv2.bias"])
+            h = h + sd[p + "gamma"] * y
+            i += 1
+        h = F.layer_norm(h, (h.shape[-1],), sd[FH + "final_layer_norm.weight"], sd[FH + "final_layer_norm.bias"], eps=1e-6)
+        return F.linear(h, sd[FH + "to_pred.weight"])
     inv_freq = sd[FH + "transformer.rotary_emb.inv_freq"]
     pos_idx = torch.arange(N, dtype=inv_freq.dtype)
     fr = torch.einsum("i,j->ij", pos_idx, inv_freq)

@@ -92,7 +92,7 @@ def load_reference():
 
 
 def build_reference_model(sd, vcfg, *, cfm_method="basic_cfm", ode_method="midpoint", sigma=0.0, depth=2,
-                          use_unet_skip_connection=False):
+                          use_unet_skip_connection=False, architecture="transformer"):
     """Reference FlowHighSR with `sd` loaded (strict), bypassing the checkpoint-file loaders.
 
     use_unet_skip_connection: the reference's FLowHigh never forwards that flag to its Transformer, so the
@@ -113,7 +113,7 @@ def build_reference_model(sd, vcfg, *, cfm_method="basic_cfm", ode_method="midpo
 
     ref_melvoco.init_bigvgan = init_bigvgan
     voc = pkg.models.MelVoco(vocoder_config=None, vocoder_path=None)
-    net = pkg.models.FLowHigh(dim_in=voc.n_mels, audio_enc_dec=voc, depth=depth).eval()
+    net = pkg.models.FLowHigh(dim_in=voc.n_mels, audio_enc_dec=voc, depth=depth, architecture=architecture).eval()
     if use_unet_skip_connection:
         from flowhigh.models.transformer import Transformer
         net.transformer = Transformer(dim=1024, depth=depth, dim_head=64, heads=16, ff_mult=4, ff_dropout=0.0,

@@ -119,6 +119,31 @@ def skip_case(name, seed):
                                                                                           (mel - mel64).abs().max()))
 
 
+def convnext_case(name, seed):
+    """architecture='convnext' (SURVEY 8f row 4): the reference FLowHigh builds it natively (flow.py:124-139)."""
+    vcfg = VocoderConfig.tiny()
+    bcfg = BackboneConfig(architecture="convnext")
+    sd = random_state_dict(bcfg, vcfg, seed=seed, vocoder_gain=GAIN)
+    ref = ref_harness.build_reference_model(sd, vcfg, cfm_method="basic_cfm", ode_method="euler", sigma=0.0,
+                                            architecture="convnext")
+    assert list(ref.state_dict().keys()) == list(sd.keys()), "convnext key order differs from the reference"
+    rng = np.random.default_rng(seed)
+    B, N = 2, 41
+    x = torch.from_numpy(rng.standard_normal((B, N, 256)).astype(np.float32))
+    cond = torch.from_numpy((rng.standard_normal((B, N, 256)) * 2.0 - 5.0).astype(np.float32))
+    v = ref.flowhigh.forward_with_cond_scale(x, times=torch.tensor(0.25), cond=cond)
+    v64 = model.vector_field(sd64(sd), x.double(), cond.double(), torch.tensor(0.25, dtype=torch.float64))
+    mel64 = model.cfm_sample_mel(sd64(sd), cond.double(), x.double(), steps=2, ode_method="euler", cfm_method="basic_cfm",
+                                 sigma=0.0)
+    fn = lambda tt, yy: ref.flowhigh.forward_with_cond_scale(yy, times=tt, cond=cond)
+    mel = model.odeint_fixed(fn, x, torch.linspace(0, 1, 3), "euler")
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), x=x.numpy(), cond=cond.numpy(), ref_vfield_t025=v.detach().numpy(),
+                        f64_vfield_t025=v64.float().numpy(), ref_mel=mel.detach().numpy(), f64_mel=mel64.float().numpy(),
+                        seed=seed, gain=GAIN, vcfg=str(vcfg.to_attr_json()), weight_checksum=checksum(sd))
+    print(name, "vfield absmax", float(v.abs().max()), "ref-vs-f64 vfield %.3g mel %.3g" % ((v - v64).abs().max(),
+                                                                                          (mel - mel64).abs().max()))
+
+
 def frontend_case(name):
     import scipy.signal
     d = {}
@@ -154,3 +179,4 @@ if __name__ == "__main__":
     vocoder_case("voc_resblock2_snake", VocoderConfig.tiny(resblock="2", activation="snake", logscale=False), 24, seed=4)
     vocoder_case("voc_resblock1_snakebeta", VocoderConfig.tiny(), 30, seed=5)
     skip_case("vf_unet_skip", seed=6)
+    convnext_case("vf_convnext", seed=7)

@@ -638,3 +638,29 @@ def test_unet_skip_variant(cuda_device, precision):
         assert float((mel - mref).abs().mean()) <= 1e-4
     else:
         assert snr_db(mref, mel) >= 40.0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_convnext_variant(cuda_device, precision):
+    """architecture='convnext' on the engine (dwconv7, AdaLayerNorm, pointwise GEMMs with a GELU epilogue, layer scale
+    folded into pwconv2) against the golden of the reference FLowHigh(architecture='convnext')."""
+    g = load_golden("vf_convnext")
+    vcfg = vcfg_from_golden(g)
+    sd = random_state_dict(BackboneConfig(architecture="convnext"), vcfg, seed=int(g["seed"]), vocoder_gain=float(g["gain"]))
+    m = FlowHighSR.from_random(vcfg, device="cuda:0", precision=precision, architecture="convnext")
+    m.load_state_dict(sd)
+    x, cond = dev(g["x"]), dev(g["cond"])
+    v = m.flowhigh.forward_with_cond_scale(x, times=torch.tensor(0.25), cond=cond).cpu()
+    ref, f64 = torch.from_numpy(g["ref_vfield_t025"]), torch.from_numpy(g["f64_vfield_t025"])
+    err = float((v - f64).abs().max())
+    print(f"convnext vector field {precision}: max-abs vs fp64 {err:.3g} (reference fp32: {float((ref - f64).abs().max()):.3g})")
+    if precision == "fp32":
+        assert err <= 1e-4
+    else:
+        assert snr_db(f64, v) >= 40.0
+    mel = m._engine().sample_mel(cond, x, steps=2, ode_method="euler", cfm_method="basic_cfm", sigma=0.0).cpu()
+    mref = torch.from_numpy(g["f64_mel"])
+    if precision == "fp32":
+        assert float((mel - mref).abs().mean()) <= 1e-4
+    else:
+        assert snr_db(mref, mel) >= 40.0

@@ -215,3 +215,22 @@ def test_unet_skip_variant_pinned_against_reference_transformer():
     assert float((v32 - torch.from_numpy(g["ref_vfield_t025"])).abs().max()) <= 1e-4
     # without the flag the keys are absent and the default layout is unchanged (711 keys for the assumed config)
     assert not any(".layers.1.0." in k for k in random_state_dict(BackboneConfig(), vcfg, seed=0))
+
+
+def test_convnext_variant_pinned_against_reference():
+    """architecture='convnext' (flow.py:124-139).  Golden from the unmodified reference FLowHigh; the key
+    order of the spec was asserted equal to the reference's state_dict() when the fixture was generated."""
+    g = load_golden("vf_convnext")
+    vcfg = vcfg_from_golden(g)
+    bcfg = BackboneConfig(architecture="convnext")
+    sd = random_state_dict(bcfg, vcfg, seed=int(g["seed"]), vocoder_gain=float(g["gain"]))
+    cs = float(sum(v.double().abs().sum().item() for k, v in sd.items() if k.endswith("weight")))
+    assert abs(cs - float(g["weight_checksum"])) <= 1e-6 * abs(cs)
+    assert not any(".transformer." in k for k in sd) and sum(".convnext." in k for k in sd) == 8 * 11
+    x, cond = torch.from_numpy(g["x"]), torch.from_numpy(g["cond"])
+    sd64 = {k: v.double() for k, v in sd.items()}
+    v64 = model.vector_field(sd64, x.double(), cond.double(), torch.tensor(0.25, dtype=torch.float64))
+    assert float((v64.float() - torch.from_numpy(g["f64_vfield_t025"])).abs().max()) <= 1e-6
+    assert float((v64.float() - torch.from_numpy(g["ref_vfield_t025"])).abs().max()) <= 1e-4
+    mel = model.cfm_sample_mel(sd, cond, x, steps=2, ode_method="euler", cfm_method="basic_cfm", sigma=0.0)
+    assert float((mel - torch.from_numpy(g["ref_mel"])).abs().max()) <= 1e-4
