@@ -47,7 +47,7 @@ struct TcParams {
   int ci_odd;          // Cin % 16 == 8: the last pair has one real 8-channel chunk; its partner is a zeroed smem window
   int tg, n_groups;    // taps per smem stage, groups per ci-pair
   int kc;              // ci-pairs per smem stage (> 1 only when a stage holds all taps: few-tap convs, Linear)
-  int msub;            // 128-row sub-tiles per CTA tile (1, 2 or 4): B operand reuse + epilogue MLP
+  int msub;            // 128-row sub-tiles per CTA tile (1, 2, 4 or 8): B operand reuse + epilogue MLP
   int acc_stages;      // TMEM accumulator stages: 2 (epilogue overlaps the next tile) or 1 (msub*bn > 256)
   int wrows;           // rows fetched per chunk window: 128*msub + (max_off - min_off)
   int arows_pad;       // rows reserved per chunk window in an A slot
@@ -552,6 +552,7 @@ __device__ __forceinline__ void mma_role(const TcParams& P, uint32_t tmem_base, 
               const uint32_t a_lo = a_base_lo + rel0 + (uint32_t)tap0 * a_step;
               if (msub == 2) issue_taps<2>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
               else if (msub == 4) issue_taps<4>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
+              else if (msub == 8) issue_taps<8>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
               else issue_taps<1>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
             } else {  // irregular tap offsets: table in shared memory
               const int* offs = s_off + ph * ntaps + tap0;
@@ -1170,7 +1171,7 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   }
   // sub-tiles: reuse each weight slot for up to 4 x 128 rows when the accumulators fit TMEM twice over
   int msub = 256 / a->bn;
-  msub = msub >= 4 ? 4 : (msub >= 2 ? 2 : 1);
+  msub = msub >= 8 ? 8 : (msub >= 4 ? 4 : (msub >= 2 ? 2 : 1));  // 8 x 128 rows for bn <= 32 (24-channel last stage)
   // Wide tiles (bn > 128): the weight stream from L2 (bn*32 B per MMA) is the limiter, so two 128-row
   // sub-tiles share every weight slot even though the accumulators (2*bn columns) then fill TMEM and
   // the epilogue no longer overlaps the next tile -- worth it once a tile carries enough MMAs.
