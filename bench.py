@@ -305,6 +305,20 @@ def main():
                     "peak_source": peak_src, "launches_per_step": tc_n,
                     "avg_launch_ms": tc_ms / max(tc_n, 1), "share_of_step": tc_ms / tot_ms if tot_ms else None,
                     "algorithmic_flops_per_step": tc_fl}
+        # second roofline: the HBM / FP32-issue-bound anti-aliased snake (all launches of one step)
+        sn = breakdown.get("fh_snake_aa_chunked")
+        roofline_snake = None
+        if sn and sn["ms"] > 0:
+            gbs = sn["bytes"] / (sn["ms"] / 1000.0) / 1e9
+            straffic = None
+            if B == BATCH and os.path.exists(tpath) and "snake" in json.load(open(tpath)):
+                tj = json.load(open(tpath))["snake"]
+                straffic = (tj["dram_read_bytes"] + tj["dram_write_bytes"]) / tj["launches"]
+            roofline_snake = {"kernel": "snake_aa_chunked_tma_kernel (fused up2x -> Snake -> down2x)", "bound": "hbm",
+                              "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": straffic,
+                              "algorithmic_bytes_per_launch": sn["bytes"] / sn["launches"], "launches_per_step": sn["launches"],
+                              "avg_launch_ms": sn["ms"] / sn["launches"], "share_of_step": sn["ms"] / tot_ms if tot_ms else None,
+                              "note": "FP32-issue-bound: ncu fma pipe 60 % active, DRAM 38 % (profiles/r1_ncu_snake.txt)"}
         groups = {}
         for k, v in breakdown.items():
             gname = "tc_conv" if k.startswith("tc_conv") else k
@@ -332,7 +346,7 @@ def main():
             "per_gpu": value / world, "realtime_factor_per_gpu": value / world,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_t.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_snake": roofline_snake, "cpu_baseline": cpu,
             "latency": latency,
             "stage_ms": {k: round(v["ms"], 3) for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])},
         }

@@ -117,6 +117,8 @@ class Engine:
         if self.profile is None:
             _lib.check(getattr(self.lib, name)(*args), name)
             return
+        if work is None and name == "fh_snake_aa_chunked":  # algorithmic bytes: fp32 in + fp32 / 16-bit out per element
+            work = {"bytes": float(args[8] * args[9] * args[10]) * (8.0 if args[11] == 0 else 6.0)}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(self.device))
         _lib.check(getattr(self.lib, name)(*args), name)
