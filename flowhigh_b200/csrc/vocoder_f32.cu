@@ -186,7 +186,58 @@ __global__ void cast_f32_16_kernel(const float* __restrict__ src, unsigned short
   }
 }
 
+// out = a + b (+ c) (+ d): the mean over the AMP branches of a stage (bigvgan/models.py:181-187; each branch already
+// carries the 1/num_kernels factor), written as fp32 and / or as the 16-bit operand of the next upsampler.  HBM-bound.
+__global__ void sum_cast_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
+                                const float* __restrict__ d, float* __restrict__ out32, unsigned short* __restrict__ out16,
+                                long long n, int fp16) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    float4 v = *reinterpret_cast<const float4*>(a + i);
+    if (b) {
+      const float4 w = *reinterpret_cast<const float4*>(b + i);
+      v.x += w.x, v.y += w.y, v.z += w.z, v.w += w.w;
+    }
+    if (c) {
+      const float4 w = *reinterpret_cast<const float4*>(c + i);
+      v.x += w.x, v.y += w.y, v.z += w.z, v.w += w.w;
+    }
+    if (d) {
+      const float4 w = *reinterpret_cast<const float4*>(d + i);
+      v.x += w.x, v.y += w.y, v.z += w.z, v.w += w.w;
+    }
+    if (out32) *reinterpret_cast<float4*>(out32 + i) = v;
+    if (out16) {
+      uint32_t h[2] = {fh::pack16(v.x, v.y, fp16), fh::pack16(v.z, v.w, fp16)};
+      *reinterpret_cast<uint2*>(out16 + i) = *reinterpret_cast<uint2*>(h);
+    }
+  } else {
+    for (long long k = i; k < n; ++k) {
+      float v = a[k];
+      if (b) v += b[k];
+      if (c) v += c[k];
+      if (d) v += d[k];
+      if (out32) out32[k] = v;
+      if (out16) out16[k] = fh::cvt16(v, fp16);
+    }
+  }
+}
+
 }  // namespace
+
+extern "C" __attribute__((visibility("default"))) int fh_sum_cast_f32(const float* a, const float* b, const float* c, const float* d,
+                                                                      float* out32, void* out16, int64_t n, int fp16,
+                                                                      void* stream) {
+  if (n <= 0) return FH_OK;
+  FH_REQUIRE(a != nullptr && (out32 != nullptr || out16 != nullptr), FH_ERR_BAD_SHAPE, "fh_sum_cast_f32: needs a source and an output");
+  FH_REQUIRE(((uintptr_t)a % 16) == 0 && ((uintptr_t)b % 16) == 0 && ((uintptr_t)c % 16) == 0 && ((uintptr_t)d % 16) == 0 &&
+                 ((uintptr_t)out32 % 16) == 0 && ((uintptr_t)out16 % 8) == 0,
+             FH_ERR_BAD_ALIGN, "fh_sum_cast_f32: alignment");
+  const long long nthreads = (n + 3) / 4;
+  sum_cast_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, c, d, out32, (unsigned short*)out16, n,
+                                                                                   fp16);
+  return fh::check_launch("fh_sum_cast_f32");
+}
 
 extern "C" __attribute__((visibility("default"))) int fh_conv1d_taps_f32(const float* x, const float* w, const float* bias, const int* off, const float* res,
                                   float beta_res, float alpha, int accumulate, float* out, int B, int Cin, int Cout,

@@ -15,6 +15,7 @@ Two numeric modes:
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import math
 from typing import Dict, Optional
@@ -69,6 +70,10 @@ class Engine:
         # instruction streams thrash the 32 KB L1.5 I-cache and the snake workers get 8 warps instead of 16): off.
         self.dual = _os.environ.get("FH_DUAL", "0") != "0"
         self._tape = None
+        # AMP branches of a stage on parallel streams for small batches (B = 1 latency path)
+        self.branch_streams = _os.environ.get("FH_BRANCH_STREAMS", "1") != "0"
+        self.branch_streams_max_batch = 4
+        self._branch_streams = []
         self.pp_fused = _os.environ.get("FH_PP_FUSED", "1") != "0"  # spectrogram-free post-processing
         self._side_streams = []
         self._time_cache: Dict[float, dict] = {}
@@ -775,53 +780,85 @@ class Engine:
         L = N
         nk = v.num_kernels
         a_in, a_cs, a_bs = xb, xcs, xbs
+        # The AMP branches of a stage (one per resblock kernel size) are independent until their mean
+        # (bigvgan/models.py:181-187): each writes its own pre-scaled output and fh_sum_cast_f32 adds them (same HBM
+        # bytes as accumulating in place, without the read-modify-write epilogue).  For small batches the branches run
+        # on parallel streams (parallel CUDA-graph branches when captured): a single clip does not fill 148 SMs.
+        par = (self.branch_streams and B <= self.branch_streams_max_batch and self._tape is None and not self.fuse_snake
+               and started_event is None and nk > 1)
+        main = torch.cuda.current_stream(self.device)
+        if par:
+            while len(self._branch_streams) < nk:
+                self._branch_streams.append(torch.cuda.Stream(self.device))
         for s, u in enumerate(v.upsample_rates):
             ch = self.cpad(v.stage_channels(s))
             Lo = L * u
             X, cs, bs = self_cbuf(f"vt_X{s}", B, ch, Lo, f32)
-            XJ, _, _ = self_cbuf(f"vt_XJ{s}", B, ch, Lo, f32)
-            Y, _, _ = self_cbuf(f"vt_Y{s}", B, ch, Lo, f32)
-            XS, _, _ = self_cbuf(f"vt_XS{s}", B, ch, Lo, f32)
-            A, _, _ = self_cbuf(f"vt_A{s}", B, ch, Lo, bf)
             o = HALO * 8  # element offset of row t = 0
             strides = (bs, cs, 8)
             self._tc_conv(V[f"up{s}"], a_in, a_bs, a_cs, HALO, X[o:], strides, 0, B, L)
             L = Lo
             fuse = self.fuse_snake and ch <= 128  # HBM-bound stages: snake runs inside the conv kernel
+            if par:
+                ev_up = torch.cuda.Event()
+                ev_up.record(main)
+            outs = []
             for j, dil in enumerate(v.resblock_dilation_sizes):
-                cur = X
-                for i in range(len(dil)):
-                    last = i == len(dil) - 1
-                    sn1 = V[f"r{s}.{j}.a1.{i}"]
-                    if not fuse:
-                        self._call("fh_snake_aa_chunked", cur.data_ptr(), A.data_ptr(), sn1[0].data_ptr(), sn1[1].data_ptr(),
-                                   sn1[2].data_ptr(), bs, cs, HALO, B, ch, L, self.k16, st)
-                    if started_event is not None:
-                        started_event.record(torch.cuda.current_stream(self.device))
-                        started_event = None
-                    fa = dict(xf=cur, snake=sn1) if fuse else {}
-                    if v.resblock == "1":
-                        self._tc_conv(V[f"r{s}.{j}.c1.{i}"], None if fuse else A, bs, cs, HALO, Y[o:], strides, 0, B, L, **fa)
-                        sn2 = V[f"r{s}.{j}.a2.{i}"]
+                bt = f"_{j}" if par else ""  # parallel branches need their own scratch
+                XJ, _, _ = self_cbuf(f"vt_XJ{s}{bt}", B, ch, Lo, f32)
+                Y, _, _ = self_cbuf(f"vt_Y{s}{bt}", B, ch, Lo, f32)
+                A, _, _ = self_cbuf(f"vt_A{s}{bt}", B, ch, Lo, bf)
+                XSj, _, _ = self_cbuf(f"vt_XS{s}_{j}", B, ch, Lo, f32)
+                outs.append(XSj)
+                ctx = torch.cuda.stream(self._branch_streams[j]) if par else contextlib.nullcontext()
+                if par:
+                    self._branch_streams[j].wait_event(ev_up)
+                with ctx:
+                    st = self.stream
+                    cur = X
+                    for i in range(len(dil)):
+                        last = i == len(dil) - 1
+                        sn1 = V[f"r{s}.{j}.a1.{i}"]
                         if not fuse:
-                            self._call("fh_snake_aa_chunked", Y.data_ptr(), A.data_ptr(), sn2[0].data_ptr(), sn2[1].data_ptr(),
-                                       sn2[2].data_ptr(), bs, cs, HALO, B, ch, L, self.k16, st)
-                        fa = dict(xf=Y, snake=sn2) if fuse else {}
-                        conv = V[f"r{s}.{j}.c2.{i}"]
-                    else:
-                        conv = V[f"r{s}.{j}.c1.{i}"]
-                    src = None if fuse else A
-                    if last:
-                        self._tc_conv(conv, src, bs, cs, HALO, XS[o:], strides, 0, B, L, res=cur[o:], res_strides=strides,
-                                      alpha=1.0 / nk, beta=1.0 / nk, accumulate=j > 0, **fa)
-                    else:
-                        self._tc_conv(conv, src, bs, cs, HALO, XJ[o:], strides, 0, B, L, res=cur[o:], res_strides=strides,
-                                      beta=1.0, **fa)
-                        cur = XJ
+                            self._call("fh_snake_aa_chunked", cur.data_ptr(), A.data_ptr(), sn1[0].data_ptr(), sn1[1].data_ptr(),
+                                       sn1[2].data_ptr(), bs, cs, HALO, B, ch, L, self.k16, st)
+                        if started_event is not None:
+                            started_event.record(torch.cuda.current_stream(self.device))
+                            started_event = None
+                        fa = dict(xf=cur, snake=sn1) if fuse else {}
+                        if v.resblock == "1":
+                            self._tc_conv(V[f"r{s}.{j}.c1.{i}"], None if fuse else A, bs, cs, HALO, Y[o:], strides, 0, B, L, **fa)
+                            sn2 = V[f"r{s}.{j}.a2.{i}"]
+                            if not fuse:
+                                self._call("fh_snake_aa_chunked", Y.data_ptr(), A.data_ptr(), sn2[0].data_ptr(),
+                                           sn2[1].data_ptr(), sn2[2].data_ptr(), bs, cs, HALO, B, ch, L, self.k16, st)
+                            fa = dict(xf=Y, snake=sn2) if fuse else {}
+                            conv = V[f"r{s}.{j}.c2.{i}"]
+                        else:
+                            conv = V[f"r{s}.{j}.c1.{i}"]
+                        src = None if fuse else A
+                        if last:
+                            self._tc_conv(conv, src, bs, cs, HALO, XSj[o:], strides, 0, B, L, res=cur[o:], res_strides=strides,
+                                          alpha=1.0 / nk, beta=1.0 / nk, **fa)
+                        else:
+                            self._tc_conv(conv, src, bs, cs, HALO, XJ[o:], strides, 0, B, L, res=cur[o:], res_strides=strides,
+                                          beta=1.0, **fa)
+                            cur = XJ
+                    if par:
+                        done = torch.cuda.Event()
+                        done.record(self._branch_streams[j])
+                        main.wait_event(done)
+            st = self.stream
+            ptrs = [t_.data_ptr() for t_ in outs] + [None] * (4 - len(outs))
+            if len(outs) > 4:
+                raise ValueError("at most 4 resblock kernel sizes per stage")
             if s + 1 < v.num_stages:
                 XB, _, _ = self_cbuf(f"vt_XB{s}", B, ch, L, bf)
-                self._call("fh_cast_f32_16", XS.data_ptr(), XB.data_ptr(), B * bs, self.fp16, st)
+                self._call("fh_sum_cast_f32", *ptrs, None, XB.data_ptr(), B * bs, self.fp16, st)
                 a_in, a_cs, a_bs = XB, cs, bs
+            else:
+                XS, _, _ = self_cbuf(f"vt_XS{s}", B, ch, Lo, f32)
+                self._call("fh_sum_cast_f32", *ptrs, XS.data_ptr(), None, B * bs, self.fp16, st)
         a, ib, f = V["post_act"]
         AP, _, _ = self_cbuf("vt_AP", B, ch, L, f32)
         self._call("fh_snake_aa_chunked", XS.data_ptr(), AP.data_ptr(), a.data_ptr(), ib.data_ptr(), f.data_ptr(), bs, cs,

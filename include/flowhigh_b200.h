@@ -173,6 +173,10 @@ int fh_convpost_tanh_f32(const float* x, const float* w, float bias, float* y, i
 int fh_transpose_f32(const float* src, float* dst, int B, int R, int C, void* stream);
 /* elementwise fp32 -> bf16 / fp16 (whole chunked buffers, halos included) */
 int fh_cast_f32_16(const float* src, void* dst, int64_t n, int fp16, void* stream);
+/* out = a + b + c + d (b, c, d optional): the mean over the AMP branches of a BigVGAN stage (bigvgan/models.py:181-187, each
+ * branch pre-scaled by 1/num_kernels), as fp32 (out32) and / or 16-bit (out16); same flat geometry for all buffers. */
+int fh_sum_cast_f32(const float* a, const float* b, const float* c, const float* d, float* out32, void* out16,
+                    int64_t n, int fp16, void* stream);
 
 /* ---------------------------------------------------------------- tensor-core path (tcgen05)
  * Implicit-GEMM tapped convolution on chunked 16-bit operands (bf16 or fp16) -> fp32 in TMEM.
