@@ -5,9 +5,10 @@
 // stored as hi + lo 16-bit pairs by the q/k-norm + rotary kernel and S = qh.kh + ql.kh + qh.kl runs as three
 // mma.sync.m16n8k16 passes with fp32 accumulation (error ~2^-21); P.V uses plain 16-bit operands (P in [0,1]).
 // Flash-style: one CTA = 64 queries x one (batch, head); 4 warps x 16 query rows; keys streamed in blocks of 64
-// through shared memory (rows padded to 72 halves: conflict-free 32-bit fragment loads; V is stored
-// transposed so the P.V B-fragments are also plain 32-bit loads); online softmax on the C fragments; the
-// S -> P register re-use of the m16n8k16 layouts avoids any shared-memory round trip for P.
+// through shared memory (rows padded to 72 halves = 144 B: the 8 row addresses of an ldmatrix tile hit 32 distinct
+// banks); every B fragment comes from ldmatrix.x4 (two n-tiles x two k-halves per instruction; .trans for V, which
+// stays row-major [key][d]); online softmax on the C fragments; the S -> P register re-use of the m16n8k16 layouts
+// avoids any shared-memory round trip for P.
 #include "common.cuh"
 
 namespace {
@@ -26,6 +27,19 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                  : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void ldmatrix_x4(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(a));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem_row) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(smem_row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(a));
+}
+
 template <bool FP16>
 __global__ void __launch_bounds__(128) attention_tc_kernel(const unsigned short* __restrict__ qh,
                                                            const unsigned short* __restrict__ ql,
@@ -35,11 +49,12 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const unsigned short*
                                                            int out_mode, long long out_rows, int H, int N) {
   __shared__ __align__(16) unsigned short Kh[ABK][APAD];
   __shared__ __align__(16) unsigned short Kl[ABK][APAD];
-  __shared__ __align__(16) unsigned short Vt[AD][APAD];  // [d][key]
+  __shared__ __align__(16) unsigned short Vs[ABK][APAD];  // [key][d]
   const int bh = blockIdx.y, q0 = blockIdx.x * ABQ;
   const int bi = bh / H, h = bh % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
+  const int lm = lane >> 3, lr = lane & 7;  // ldmatrix: this lane addresses row lr of 8x8 tile lm
   const size_t base = (size_t)bh * N * AD;
   // ---- Q fragments (hi, lo) for this warp's 16 rows
   uint32_t Qh[4][4], Ql[4][4];
@@ -75,17 +90,10 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const unsigned short*
       const uint4 z = make_uint4(0u, 0u, 0u, 0u);
       const uint4 a = ok ? *reinterpret_cast<const uint4*>(kh + off) : z;
       const uint4 b = ok ? *reinterpret_cast<const uint4*>(kl + off) : z;
+      const uint4 vv = ok ? *reinterpret_cast<const uint4*>(v16 + off) : z;
       *reinterpret_cast<uint4*>(&Kh[r][c * 8]) = a;
       *reinterpret_cast<uint4*>(&Kl[r][c * 8]) = b;
-    }
-    // V is stored transposed ([d][key]); lanes walk along keys so the 2-byte stores are conflict-free
-    for (int i = threadIdx.x; i < ABK * 8; i += 128) {
-      const int r = i & 63, c = i >> 6;
-      const uint4 vv = (k0 + r < N) ? *reinterpret_cast<const uint4*>(v16 + base + (size_t)(k0 + r) * AD + c * 8)
-                                    : make_uint4(0u, 0u, 0u, 0u);
-      const unsigned short* vs = reinterpret_cast<const unsigned short*>(&vv);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) Vt[c * 8 + e][r] = vs[e];
+      *reinterpret_cast<uint4*>(&Vs[r][c * 8]) = vv;
     }
     __syncthreads();
     // ---- S = Qh Kh^T + Ql Kh^T + Qh Kl^T
@@ -97,14 +105,17 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const unsigned short*
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Kh[nt * 8 + g][kk * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Kh[nt * 8 + g][kk * 16 + 8 + 2 * t]);
-        mma16816<FP16>(S[nt], Qh[kk], b0, b1);
-        mma16816<FP16>(S[nt], Ql[kk], b0, b1);
-        const uint32_t l0 = *reinterpret_cast<const uint32_t*>(&Kl[nt * 8 + g][kk * 16 + 2 * t]);
-        const uint32_t l1 = *reinterpret_cast<const uint32_t*>(&Kl[nt * 8 + g][kk * 16 + 8 + 2 * t]);
-        mma16816<FP16>(S[nt], Qh[kk], l0, l1);
+      for (int nt = 0; nt < 8; nt += 2) {
+        // tiles: (keys nt*8.., d kk*16..), (same keys, d +8), (keys (nt+1)*8.., d kk*16..), (.., d +8)
+        uint32_t bh[4], bl[4];
+        ldmatrix_x4(bh, &Kh[(nt + (lm >> 1)) * 8 + lr][kk * 16 + (lm & 1) * 8]);
+        ldmatrix_x4(bl, &Kl[(nt + (lm >> 1)) * 8 + lr][kk * 16 + (lm & 1) * 8]);
+        mma16816<FP16>(S[nt], Qh[kk], bh[0], bh[1]);
+        mma16816<FP16>(S[nt], Ql[kk], bh[0], bh[1]);
+        mma16816<FP16>(S[nt], Qh[kk], bl[0], bl[1]);
+        mma16816<FP16>(S[nt + 1], Qh[kk], bh[2], bh[3]);
+        mma16816<FP16>(S[nt + 1], Ql[kk], bh[2], bh[3]);
+        mma16816<FP16>(S[nt + 1], Qh[kk], bl[2], bl[3]);
       }
     }
     // ---- online softmax (rows g and g+8 of this warp's tile)
@@ -157,10 +168,12 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const unsigned short*
     for (int kt = 0; kt < 4; ++kt) {
       const uint32_t a[4] = {P[2 * kt][0], P[2 * kt][1], P[2 * kt + 1][0], P[2 * kt + 1][1]};
 #pragma unroll
-      for (int nd = 0; nd < 8; ++nd) {
-        const uint32_t b0 = *reinterpret_cast<const uint32_t*>(&Vt[nd * 8 + g][kt * 16 + 2 * t]);
-        const uint32_t b1 = *reinterpret_cast<const uint32_t*>(&Vt[nd * 8 + g][kt * 16 + 8 + 2 * t]);
-        mma16816<FP16>(O[nd], a, b0, b1);
+      for (int nd = 0; nd < 8; nd += 2) {
+        // transposed tiles: (keys kt*16.., d nd*8..), (keys +8, same d), (keys kt*16.., d (nd+1)*8..), (keys +8, ..)
+        uint32_t bv[4];
+        ldmatrix_x4_trans(bv, &Vs[kt * 16 + (lm & 1) * 8 + lr][(nd + (lm >> 1)) * 8]);
+        mma16816<FP16>(O[nd], a, bv[0], bv[1]);
+        mma16816<FP16>(O[nd + 1], a, bv[2], bv[3]);
       }
     }
   }
