@@ -47,9 +47,9 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const unsigned short*
                                                            const unsigned short* __restrict__ kl,
                                                            const unsigned short* __restrict__ v16, void* __restrict__ out,
                                                            int out_mode, long long out_rows, int H, int N) {
-  __shared__ __align__(16) unsigned short Kh[ABK][APAD];
-  __shared__ __align__(16) unsigned short Kl[ABK][APAD];
-  __shared__ __align__(16) unsigned short Vs[ABK][APAD];  // [key][d]
+  // two stages of (Kh, Kl, V) key blocks: the next block streams in with cp.async while this one is multiplied
+  extern __shared__ __align__(16) unsigned short att_smem[];
+  typedef unsigned short (*Tile)[APAD];
   const int bh = blockIdx.y, q0 = blockIdx.x * ABQ;
   const int bi = bh / H, h = bh % H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,22 +80,29 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const unsigned short*
     for (int j = 0; j < 4; ++j) O[i][j] = 0.f;
   float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
 
-  for (int k0 = 0; k0 < N; k0 += ABK) {
-    __syncthreads();
-    // ---- cooperative load of the key block: 64 rows x 8 chunks of 16 B for Kh, Kl, V
+  auto stage_ptr = [&](int st, int which) { return reinterpret_cast<Tile>(att_smem + (size_t)(st * 3 + which) * ABK * APAD); };
+  auto prefetch = [&](int k0, int st) {  // 64 rows x 8 chunks of 16 B for Kh, Kl, V; rows past N are zero-filled
+    Tile sKh = stage_ptr(st, 0), sKl = stage_ptr(st, 1), sV = stage_ptr(st, 2);
     for (int i = threadIdx.x; i < ABK * 8; i += 128) {
       const int r = i >> 3, c = i & 7;
-      const bool ok = k0 + r < N;
-      const size_t off = base + (size_t)(k0 + r) * AD + c * 8;
-      const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-      const uint4 a = ok ? *reinterpret_cast<const uint4*>(kh + off) : z;
-      const uint4 b = ok ? *reinterpret_cast<const uint4*>(kl + off) : z;
-      const uint4 vv = ok ? *reinterpret_cast<const uint4*>(v16 + off) : z;
-      *reinterpret_cast<uint4*>(&Kh[r][c * 8]) = a;
-      *reinterpret_cast<uint4*>(&Kl[r][c * 8]) = b;
-      *reinterpret_cast<uint4*>(&Vs[r][c * 8]) = vv;
+      const uint32_t nbytes = (k0 + r < N) ? 16u : 0u;
+      const size_t off = base + (size_t)min(k0 + r, N - 1) * AD + c * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(&sKh[r][c * 8])),
+                   "l"(kh + off), "r"(nbytes) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(&sKl[r][c * 8])),
+                   "l"(kl + off), "r"(nbytes) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(&sV[r][c * 8])),
+                   "l"(v16 + off), "r"(nbytes) : "memory");
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(0, 0);
+  int stg = 0;
+  for (int k0 = 0; k0 < N; k0 += ABK, stg ^= 1) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // block k0 has landed for every thread, and everyone is done reading the other stage
+    if (k0 + ABK < N) prefetch(k0 + ABK, stg ^ 1);
+    Tile Kh = stage_ptr(stg, 0), Kl = stage_ptr(stg, 1), Vs = stage_ptr(stg, 2);
     // ---- S = Qh Kh^T + Ql Kh^T + Qh Kl^T
     float S[8][4];
 #pragma unroll
@@ -259,12 +266,19 @@ extern "C" __attribute__((visibility("default"))) int fh_attention_tc(const void
   FH_REQUIRE(D == 64, FH_ERR_UNSUPPORTED_CFG, "fh_attention_tc: dim_head must be 64 (got %d)", D);
   FH_REQUIRE(B * H <= 65535 && N > 0, FH_ERR_BAD_SHAPE, "fh_attention_tc: B*H must be <= 65535");
   dim3 grid((N + ABQ - 1) / ABQ, B * H);
+  constexpr int kSmem = 2 * 3 * ABK * APAD * (int)sizeof(unsigned short);  // 55 296 B: two stages of Kh, Kl, V
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    attr_set = true;
+  }
   if (fp16)
-    attention_tc_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(
+    attention_tc_kernel<true><<<grid, 128, kSmem, (cudaStream_t)stream>>>(
         (const unsigned short*)qh, (const unsigned short*)ql, (const unsigned short*)kh, (const unsigned short*)kl,
         (const unsigned short*)v16, out, out_mode, out_rows, H, N);
   else
-    attention_tc_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(
+    attention_tc_kernel<false><<<grid, 128, kSmem, (cudaStream_t)stream>>>(
         (const unsigned short*)qh, (const unsigned short*)ql, (const unsigned short*)kh, (const unsigned short*)kl,
         (const unsigned short*)v16, out, out_mode, out_rows, H, N);
   return fh::check_launch("fh_attention_tc");
