@@ -1,0 +1,279 @@
+// Anti-aliased Snake / SnakeBeta with both FIR filters on the tensor pipe (fp16 output mode of the chunked layout).
+//
+// Same closed form as snake_worker.cuh (reference alias_free_torch/act.py:23-28, resample.py:25-33,
+// filter.py:86-94, activations.py:48-59,107-119):
+//   u[m] = 2 sum_i x~[i] f[m+5-2i]      s'[m] = u[m] - (inv_b/2) cos(2 a u[m])      y[q] = inv_b/2 + sum_k f[k] s'~[2q+k-5]
+// The scalar kernel spends 24 of its ~34 issue slots per element on the 6 + 6 + 12 filter taps.  Here the two filters
+// are banded Toeplitz matrices applied with mma.sync.m16n8k16 (fp16 operands, fp32 accumulate):
+//   * M = 16 independent sequences = 8 channels of one chunk x 2 time segments ("halves") of the tile, so a thread
+//     (g = lane / 4, q = lane % 4) only ever needs the snake parameters of channel g;
+//   * up stage:  D[seq][8 up-samples] = X[seq][16 input steps] . Tup[16][8]; the fp32 input is split x = hi + lo
+//     (two MMAs) so that no input precision is lost; the k-slot -> time map inside an 8-step block is permuted
+//     (slot 2q -> row q, slot 2q+1 -> row q+4) so that the fragment loads from the [time][8 ch] fp32 window are
+//     bank-conflict free; the Toeplitz fragment is built with the same permutation;
+//   * snake on the accumulator registers (packed FMUL2 / FFMA2, MUFU.COS);
+//   * two adjacent accumulator tiles of the up stage ARE the A fragment of the down stage (16 up-samples), so
+//     nothing is shuffled or staged:  Y[seq][8 outputs] = sum_{d=-1,0,1} S_{i+d}[seq][16] . Tdn_d[16][8];
+//   * the filter taps are rounded to fp16 (relative 2^-12, below the fp16 rounding of the output); SPLIT_F adds the
+//     tap residual as extra MMAs.
+// Replicate clamps: x~ is patched in the shared-memory window (first / last segments); the s~ clamp only changes the
+// first and last three outputs of a sequence, which the warp recomputes in scalar fp32 on those segments.
+// Pipeline: one shared double-buffered input window per CTA tile (cp.async.bulk against an mbarrier), everything
+// else per warp -- see snake_mma_cta below.
+#pragma once
+#include <cuda_fp16.h>
+#include "snake_worker.cuh"
+
+namespace fh {
+
+template <int NB>  // 8-output blocks per half-segment
+struct SnakeMmaGeom {
+  static constexpr int kWarps = 4;
+  static constexpr int kSeg = 8 * NB;           // outputs per half-segment
+  static constexpr int kWarpRows = 2 * kSeg;    // outputs per warp and tile (two halves, adjacent in time)
+  static constexpr int kRows = kWarps * kWarpRows;
+  static constexpr int kHalo = 8;               // window rows before / after the tile
+  static constexpr int kXRows = kRows + 2 * kHalo;
+  static constexpr int kXBytes = kXRows * 32;
+  static constexpr int kWarpYBytes = kWarpRows * 16;
+  // two input windows, per warp two output images, two mbarriers + two release counters
+  static constexpr int kSmemBytes = 2 * kXBytes + 2 * kWarps * kWarpYBytes + 32;
+};
+
+__device__ __forceinline__ uint32_t sm_pack(float lo, float hi) {
+  __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void sm_split(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  __half2 h = __floats2half2_rn(x0, x1);
+  const float2 hf = __half22float2(h);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = sm_pack(x0 - hf.x, x1 - hf.y);
+}
+__device__ __forceinline__ void sm_mma(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                       uint32_t b1, float c0, float c1, float c2, float c3) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
+      : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+}
+
+// One CTA of 4 warps walks tiles (batch, chunk, kRows outputs) cta, cta + nctas, ...  The input window of a tile is
+// shared (one cp.async.bulk against a "full" mbarrier); everything else is per warp: each warp computes its own
+// 2 x kSeg rows, stores them with its own bulk store and releases the window through a shared-memory counter -- the
+// last warp to release a window refills it with the tile after next.  There is no CTA-wide barrier in the loop (ncu
+// on a bar.sync version: 16 % of the warp stalls).
+template <bool SPLIT_X, bool SPLIT_F, int NB>
+__device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned char* smem, int tid, int cta, int nctas) {
+  using G = SnakeMmaGeom<NB>;
+  const int lane = tid & 31, warp = tid >> 5;
+  float* xs0 = reinterpret_cast<float*>(smem);
+  float* xs1 = reinterpret_cast<float*>(smem + G::kXBytes);
+  unsigned char* ys0 = smem + 2 * G::kXBytes + warp * 2 * G::kWarpYBytes;  // this warp's two output images
+  unsigned char* ctl = smem + 2 * G::kXBytes + 2 * G::kWarps * G::kWarpYBytes;
+  const uint32_t bar0 = sw_u32(ctl);
+  int* released = reinterpret_cast<int*>(ctl + 16);  // warps done with window 0 / 1
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    released[0] = released[1] = 0;
+  }
+  // rows a clipped copy does not fill must hold finite values (they only ever meet zero filter weights)
+  for (int i = tid; i < 2 * G::kXBytes / 16; i += 32 * G::kWarps) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const int rows_per_chunk = (int)(S.chunk_stride >> 3);
+  auto issue = [&](int item, int buf) {
+    const int tile = item % S.ntile;
+    const int rest = item / S.ntile;
+    const int ch = rest % S.nchunk, b = rest / S.nchunk;
+    const int r_first = S.row0 + tile * G::kRows - G::kHalo;  // >= 0: the launcher requires row0 >= kHalo
+    int nrows = rows_per_chunk - r_first;                     // stay inside this chunk's rows
+    nrows = nrows < G::kXRows ? nrows : G::kXRows;
+    const float* src = S.x + (long long)b * S.batch_stride + (long long)ch * S.chunk_stride + (long long)r_first * 8;
+    const uint32_t bar = bar0 + 8 * buf;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)nrows * 32u) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     sw_u32(buf ? xs1 : xs0)),
+                 "l"(src), "r"((uint32_t)nrows * 32u), "r"(bar)
+                 : "memory");
+  };
+
+  const int g = lane >> 2, q = lane & 3;
+  // ---- Toeplitz B fragments (k16 x n8, "col"): reg r holds k-slots 2q + 8r, 2q + 8r + 1 of column n = g
+  auto tap = [&](int idx, float scale) -> float { return (idx >= 0 && idx < 12) ? scale * __ldg(S.filt + idx) : 0.f; };
+  uint32_t bu[2][2], bul[2][2], bd[3][2], bdl[3][2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    // up n-block e of a 16-up-sample block starting at input step T: up-sample m = 2T + 8e + n from the input steps
+    // T - 8 + ko (e = 0) or T + ko (e = 1), ko = q + 8r (slot 2q + 8r) and q + 4 + 8r (slot 2q + 8r + 1)
+    const int base = e ? 13 : 21;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const float v0 = tap(g + base - 2 * (q + 8 * r), 2.0f), v1 = tap(g + base - 2 * (q + 4 + 8 * r), 2.0f);
+      sm_split(v0, v1, bu[e][r], bul[e][r]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    // down block: output Q + n from the up-samples 2Q + 16 (d - 1) + c, c = k-slot (identity map)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int c0 = 2 * q + 8 * r;
+      const float v0 = tap(16 * (d - 1) + c0 - 2 * g + 5, 1.0f), v1 = tap(16 * (d - 1) + c0 + 1 - 2 * g + 5, 1.0f);
+      sm_split(v0, v1, bd[d][r], bdl[d][r]);
+    }
+  }
+
+  int item = cta;
+  if (tid == 0) {
+    if (item < S.total) issue(item, 0);
+    if (item + nctas < S.total) issue(item + nctas, 1);
+  }
+  int buf = 0;
+  uint32_t ph0 = 0, ph1 = 0;
+  const int ssA = warp * G::kWarpRows;  // first tile row of this warp's half A; half B starts kSeg rows later
+  for (; item < S.total; item += nctas) {
+    const int tile = item % S.ntile;
+    const int rest = item / S.ntile;
+    const int ch = rest % S.nchunk, b = rest / S.nchunk;
+    const int qt = tile * G::kRows;
+    const bool edge = (tile == 0) || (qt + G::kRows + G::kHalo > S.L);
+    const bool active = qt + ssA < S.L;  // warp-uniform
+    sw_mbar_wait(bar0 + 8 * buf, buf ? ph1 : ph0);
+    if (buf) ph1 ^= 1; else ph0 ^= 1;
+    float* xt = buf ? xs1 : xs0;
+    unsigned char* yt = ys0 + (size_t)buf * G::kWarpYBytes;
+    if (edge && active) {
+      // replicate-pad the rows this warp reads: t < 0 <- x[0], t >= L <- x[L-1] (a neighbour warp may write the same
+      // values into the shared halo rows)
+      for (int i = lane; i < (G::kWarpRows + 2 * G::kHalo) * 2; i += 32) {
+        const int r = ssA + (i >> 1), h = i & 1;
+        const int t = qt - G::kHalo + r;
+        const int tc = min(max(t, 0), S.L - 1);
+        if (tc != t) {
+          const int rc = tc - (qt - G::kHalo);
+          if (rc >= 0 && rc < G::kXRows)
+            *reinterpret_cast<float4*>(&xt[r * 8 + h * 4]) = *reinterpret_cast<const float4*>(&xt[rc * 8 + h * 4]);
+        }
+      }
+      __syncwarp();
+    }
+    if (active) {
+      const int cg = ch * 8 + g;
+      const float alv = 2.0f * __ldg(S.a + cg), hib = 0.5f * __ldg(S.inv_b + cg);
+      const float2 al2 = make_float2(alv, alv), nhib2 = make_float2(-hib, -hib);
+      // window row of item row r is r + kHalo; input block jx of half h covers window rows h kSeg + 8 jx + 8 ...
+      const float* xp = xt + (ssA + q) * 8 + g;
+      unsigned char* yp = yt + (size_t)(2 * q) * 16 + 2 * g;
+      uint32_t xh[NB + 2][2], xl[NB + 2][2];  // input blocks jx = -1 .. NB at index jx + 1
+      uint32_t U[NB + 2][4];                  // snake output blocks j = -1 .. NB at index j + 1 (A fragments)
+      auto load_x = [&](int jx) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float x0 = xp[(8 * jx + 8) * 8 + h * G::kSeg * 8], x1 = xp[(8 * jx + 12) * 8 + h * G::kSeg * 8];
+          if (SPLIT_X) sm_split(x0, x1, xh[jx + 1][h], xl[jx + 1][h]);
+          else xh[jx + 1][h] = sm_pack(x0, x1);
+        }
+      };
+      auto up_block = [&](int j, int e) {  // 8 up-samples 2 (q0 + 8 j) + 8 e + n -> U[j + 1][2 e + h]
+        const int p = (e ? j : j - 1) + 1, n = p + 1;
+        float dd[4];
+        sm_mma(dd, xh[p][0], xh[p][1], xh[n][0], xh[n][1], bu[e][0], bu[e][1], 0.f, 0.f, 0.f, 0.f);
+        if (SPLIT_X) sm_mma(dd, xl[p][0], xl[p][1], xl[n][0], xl[n][1], bu[e][0], bu[e][1], dd[0], dd[1], dd[2], dd[3]);
+        if (SPLIT_F) sm_mma(dd, xh[p][0], xh[p][1], xh[n][0], xh[n][1], bul[e][0], bul[e][1], dd[0], dd[1], dd[2], dd[3]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 u = make_float2(dd[2 * h], dd[2 * h + 1]);
+          const float2 z = sw_fmul2(u, al2);
+          const float2 c = make_float2(__cosf(z.x), __cosf(z.y));
+          const float2 s = sw_ffma2(c, nhib2, u);
+          U[j + 1][2 * e + h] = sm_pack(s.x, s.y);
+        }
+      };
+      load_x(-1);
+      load_x(0);
+#pragma unroll
+      for (int j = -1; j <= NB; ++j) {
+        if (j >= 0 && j < NB) load_x(j + 1);
+        if (j >= 0) up_block(j, 0);
+        else U[j + 1][0] = U[j + 1][1] = 0u;  // up-samples below 2 q0 - 8 only meet zero weights
+        if (j < NB) up_block(j, 1);
+        else U[j + 1][2] = U[j + 1][3] = 0u;
+        if (j >= 1) {
+          const int i = j - 1;  // outputs q0 + 8 i + n from blocks i - 1, i, i + 1 (indices i, i + 1, i + 2)
+          float y[4];
+          sm_mma(y, U[i][0], U[i][1], U[i][2], U[i][3], bd[0][0], bd[0][1], hib, hib, hib, hib);
+          sm_mma(y, U[i + 1][0], U[i + 1][1], U[i + 1][2], U[i + 1][3], bd[1][0], bd[1][1], y[0], y[1], y[2], y[3]);
+          sm_mma(y, U[i + 2][0], U[i + 2][1], U[i + 2][2], U[i + 2][3], bd[2][0], bd[2][1], y[0], y[1], y[2], y[3]);
+          if (SPLIT_F) {
+            sm_mma(y, U[i][0], U[i][1], U[i][2], U[i][3], bdl[0][0], bdl[0][1], y[0], y[1], y[2], y[3]);
+            sm_mma(y, U[i + 1][0], U[i + 1][1], U[i + 1][2], U[i + 1][3], bdl[1][0], bdl[1][1], y[0], y[1], y[2], y[3]);
+            sm_mma(y, U[i + 2][0], U[i + 2][1], U[i + 2][2], U[i + 2][3], bdl[2][0], bdl[2][1], y[0], y[1], y[2], y[3]);
+          }
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            unsigned char* o = yp + (size_t)(8 * i + h * G::kSeg) * 16;
+            *reinterpret_cast<__half*>(o) = __float2half_rn(y[2 * h]);
+            *reinterpret_cast<__half*>(o + 16) = __float2half_rn(y[2 * h + 1]);
+          }
+        }
+      }
+    }
+    if (edge && active) {  // the s~ clamp changes outputs 0..2 and L-3..L-1 only: recompute those in scalar fp32
+      __syncwarp();
+      for (int w = lane; w < 48; w += 32) {
+        const int c = w & 7, o = w >> 3;
+        const int qq = o < 3 ? o : S.L - 6 + o;
+        if (qq >= qt + ssA && qq < qt + ssA + G::kWarpRows && qq < S.L && (o < 3 || qq >= 3)) {
+          const int cc = ch * 8 + c;
+          const float alv = 2.0f * __ldg(S.a + cc), hib = 0.5f * __ldg(S.inv_b + cc);
+          float acc = hib;
+          for (int k = 0; k < 12; ++k) {
+            const int m = min(max(2 * qq + k - 5, 0), 2 * S.L - 1);
+            const int ihi = (m + 5) >> 1;
+            float u = 0.f;
+            for (int t6 = 0; t6 < 6; ++t6) {
+              const int i = ihi - t6;
+              const int ic = min(max(i, 0), S.L - 1);
+              u = fmaf(2.0f * __ldg(S.filt + (m + 5 - 2 * i)), xt[(ic - qt + G::kHalo) * 8 + c], u);
+            }
+            acc = fmaf(__ldg(S.filt + k), u - hib * __cosf(alv * u), acc);
+          }
+          *reinterpret_cast<__half*>(yt + (size_t)(qq - qt - ssA) * 16 + 2 * c) = __float2half_rn(acc);
+        }
+      }
+    }
+    // generic-proxy accesses of this warp (window reads / patches, output image writes) before the async proxy's
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    // the bulk store of the previous tile reads this warp's other image, which the next tile rewrites
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) {
+      if (active) {
+        const int nrows = min(G::kWarpRows, S.L - qt - ssA);
+        const unsigned short* dst = (const unsigned short*)S.y + (long long)b * S.batch_stride +
+                                    (long long)ch * S.chunk_stride + (long long)(S.row0 + qt + ssA) * 8;
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sw_u32(yt)),
+                     "r"((uint32_t)nrows * 16u)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      // release the window; the last of the four warps refills it with the tile after next
+      __threadfence_block();
+      if (atomicAdd(&released[buf], 1) == G::kWarps - 1) {
+        released[buf] = 0;  // next touched after the refill below has landed and been consumed
+        __threadfence_block();
+        if (item + 2 * nctas < S.total) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue(item + 2 * nctas, buf);
+        }
+      }
+    }
+    buf ^= 1;
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+}  // namespace fh

@@ -189,7 +189,9 @@ __device__ __forceinline__ void snake_worker(const SnakeParams& S, unsigned char
           (long long)b * S.batch_stride + (long long)ch * S.chunk_stride + (long long)(S.row0 + q0) * 8 + 2 * e2;
 #pragma unroll
       for (int j = 0; j < R; ++j) {
-        if (!edge || q0 + j < S.L) {
+        // the bulk-store path writes into the shared-memory image (rows past L are never stored to HBM): no
+        // per-output predicate there, so the 17 tap chains are one basic block and get interleaved by the scheduler
+        if (BULK_OUT || !edge || q0 + j < S.L) {
           float2 acc = hib;
 #pragma unroll
           for (int k = 0; k < 12; ++k) acc = sw_ffma2(fd[k], s[2 * j + k], acc);

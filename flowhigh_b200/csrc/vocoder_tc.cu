@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "snake_worker.cuh"
+#include "snake_mma.cuh"
 
 namespace {
 
@@ -17,6 +18,29 @@ template <int OUT_KIND, bool BULK_OUT>
 __global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(const __grid_constant__ fh::SnakeParams S) {
   extern __shared__ __align__(128) unsigned char snake_smem[];
   fh::snake_worker<OUT_KIND, BULK_OUT, PR>(S, snake_smem, threadIdx.x, blockIdx.x, gridDim.x, 0);
+}
+
+// fp16 output mode: both FIR filters as Toeplitz MMAs (snake_mma.cuh).  MODE bit 0: hi/lo split of the input,
+// bit 1: hi/lo split of the filter taps.
+template <int MODE, int NB, int MINB>
+__global__ void __launch_bounds__(128, MINB) snake_aa_mma_kernel(const __grid_constant__ fh::SnakeParams S) {
+  extern __shared__ __align__(128) unsigned char snake_smem[];
+  fh::snake_mma_cta<(MODE & 1) != 0, (MODE & 2) != 0, NB>(S, snake_smem, threadIdx.x, blockIdx.x, gridDim.x);
+}
+
+template <int MODE, int NB, int MINB>
+void launch_snake_mma(fh::SnakeParams sp, int B, int C, int L, int sms, cudaStream_t stream) {
+  using G = fh::SnakeMmaGeom<NB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(snake_aa_mma_kernel<MODE, NB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
+    attr_set = true;
+  }
+  sp.ntile = (L + G::kRows - 1) / G::kRows;
+  const long long total = (long long)sp.ntile * (C / 8) * B;
+  sp.total = (int)total;
+  const int grid = (int)(total < (long long)sms * MINB ? total : (long long)sms * MINB);
+  snake_aa_mma_kernel<MODE, NB, MINB><<<grid, 128, G::kSmemBytes, stream>>>(sp);
 }
 
 __global__ void convpost_tanh_chunked_kernel(const float* __restrict__ x, long long batch_stride,
@@ -58,6 +82,19 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
   FH_REQUIRE(out_kind >= 0 && out_kind <= 2, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: out_kind must be 0 (fp32), 1 (bf16), 2 (fp16)");
   FH_REQUIRE(((uintptr_t)x % 16) == 0 && (batch_stride % 8) == 0 && (chunk_stride % 8) == 0, FH_ERR_BAD_ALIGN,
              "fh_snake_aa_chunked: x must be 16-byte aligned and strides multiples of 8");
+  static int mma_mode = -2;  // FH_SNAKE_MMA: -1 = scalar kernel, 0..3 = Toeplitz-MMA kernel (bit 0 split x, bit 1 split taps)
+  if (mma_mode == -2) {
+    const char* e = getenv("FH_SNAKE_MMA");
+    mma_mode = e ? atoi(e) : 0;  // the input split buys < 0.3 dB of end-to-end SNR for 15 % more kernel time
+    if (mma_mode < -1 || mma_mode > 3) mma_mode = 0;
+  }
+  static int mma_nb = 0;  // FH_SNAKE_NB: 8-output blocks per half-segment of the MMA kernel (8 or 4)
+  if (!mma_nb) {
+    const char* e = getenv("FH_SNAKE_NB");
+    mma_nb = e ? atoi(e) : 8;
+    if (mma_nb != 4 && mma_nb != 8) mma_nb = 8;
+  }
+  const bool use_mma = out_kind == 2 && mma_mode >= 0 && row0 >= fh::SnakeMmaGeom<8>::kHalo;
   constexpr int kTileRows = fh::SnakeGeom<PR>::kRows;
   const int ntile = (L + kTileRows - 1) / kTileRows;
   const long long total = (long long)ntile * (C / 8) * B;
@@ -85,6 +122,19 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
   sp.x = x, sp.y = y, sp.a = a, sp.inv_b = inv_b, sp.filt = filt;
   sp.batch_stride = batch_stride, sp.chunk_stride = chunk_stride;
   sp.row0 = row0, sp.nchunk = C / 8, sp.L = L, sp.ntile = ntile, sp.total = (int)total, sp.fp16 = out_kind == 2;
+  if (use_mma) {
+    FH_REQUIRE((long long)((L + 63) / 64) * (C / 8) * B <= 2147483647LL, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: too many work items");
+    cudaStream_t cs = (cudaStream_t)stream;
+    if (mma_nb == 4) {
+      if (mma_mode == 0) launch_snake_mma<0, 4, 6>(sp, B, C, L, sms, cs);
+      else launch_snake_mma<1, 4, 6>(sp, B, C, L, sms, cs);
+    } else {
+      if (mma_mode == 0) launch_snake_mma<0, 8, 4>(sp, B, C, L, sms, cs);
+      else if (mma_mode == 3) launch_snake_mma<3, 8, 4>(sp, B, C, L, sms, cs);
+      else launch_snake_mma<1, 8, 4>(sp, B, C, L, sms, cs);
+    }
+    return fh::check_launch("fh_snake_aa_chunked");
+  }
   constexpr int kSmem = fh::SnakeGeom<PR>::kSmemBytes;
 #define FH_SNAKE_LAUNCH(KIND, BULK) snake_aa_chunked_tma_kernel<KIND, BULK><<<grid, 128, kSmem, (cudaStream_t)stream>>>(sp)
   if (out_kind == 0) FH_SNAKE_LAUNCH(0, false);
