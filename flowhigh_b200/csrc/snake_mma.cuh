@@ -168,7 +168,6 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
       const float* xp = xt + (ssA + q) * 8 + g;
       unsigned char* yp = yt + (size_t)(2 * q) * 16 + 2 * g;
       uint32_t xh[NB + 2][2], xl[NB + 2][2];  // input blocks jx = -1 .. NB at index jx + 1
-      uint32_t U[NB + 2][4];                  // snake output blocks j = -1 .. NB at index j + 1 (A fragments)
       auto load_x = [&](int jx) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -177,46 +176,67 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
           else xh[jx + 1][h] = sm_pack(x0, x1);
         }
       };
-      auto up_block = [&](int j, int e) {  // 8 up-samples 2 (q0 + 8 j) + 8 e + n -> U[j + 1][2 e + h]
+      // up n-block (j, e): the 8 up-samples 2 (q0 + 8 j) + 8 e + n, both halves, into dd
+      auto up_mma = [&](int j, int e, float (&dd)[4]) {
         const int p = (e ? j : j - 1) + 1, n = p + 1;
-        float dd[4];
         sm_mma(dd, xh[p][0], xh[p][1], xh[n][0], xh[n][1], bu[e][0], bu[e][1], 0.f, 0.f, 0.f, 0.f);
         if (SPLIT_X) sm_mma(dd, xl[p][0], xl[p][1], xl[n][0], xl[n][1], bu[e][0], bu[e][1], dd[0], dd[1], dd[2], dd[3]);
         if (SPLIT_F) sm_mma(dd, xh[p][0], xh[p][1], xh[n][0], xh[n][1], bul[e][0], bul[e][1], dd[0], dd[1], dd[2], dd[3]);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float2 u = make_float2(dd[2 * h], dd[2 * h + 1]);
-          const float2 z = sw_fmul2(u, al2);
-          const float2 c = make_float2(__cosf(z.x), __cosf(z.y));
-          const float2 s = sw_ffma2(c, nhib2, u);
-          U[j + 1][2 * e + h] = sm_pack(s.x, s.y);
-        }
       };
+      auto snake2 = [&](float u0, float u1) -> uint32_t {
+        const float2 u = make_float2(u0, u1);
+        const float2 z = sw_fmul2(u, al2);
+        const float2 c = make_float2(__cosf(z.x), __cosf(z.y));
+        const float2 s = sw_ffma2(c, nhib2, u);
+        return sm_pack(s.x, s.y);
+      };
+      // Software pipeline, in-order issue in mind (mma.sync are volatile asm, i.e. issued in source order): in step j
+      //   1. the up-stage MMAs of step j + 1 are issued,
+      //   2. the snake of step j runs on accumulators issued one step earlier        -> A fragment U_j,
+      //   3. U_j is scattered into the three down blocks it touches (j - 1: last term, j: middle, j + 1: first), three
+      //      independent MMAs; every down accumulator is next touched one whole step later.
+      float dd[2][2][4];  // [step parity][e][acc]
+      float y[3][4];      // down accumulators of blocks i, at index i % 3
       load_x(-1);
       load_x(0);
+      if (NB >= 1) load_x(1);
+      up_mma(-1, 1, dd[0][1]);
 #pragma unroll
       for (int j = -1; j <= NB; ++j) {
-        if (j >= 0 && j < NB) load_x(j + 1);
-        if (j >= 0) up_block(j, 0);
-        else U[j + 1][0] = U[j + 1][1] = 0u;  // up-samples below 2 q0 - 8 only meet zero weights
-        if (j < NB) up_block(j, 1);
-        else U[j + 1][2] = U[j + 1][3] = 0u;
+        const int cur = (j + 1) & 1, nxt = cur ^ 1;
+        if (j + 3 <= NB) load_x(j + 3);  // consumed by the MMAs issued in the next step
+        if (j + 1 <= NB) {
+          up_mma(j + 1, 0, dd[nxt][0]);
+          if (j + 1 < NB) up_mma(j + 1, 1, dd[nxt][1]);
+        }
+        uint32_t U[4];  // A fragment of the 16 up-samples of step j
+        if (j >= 0) U[0] = snake2(dd[cur][0][0], dd[cur][0][1]), U[1] = snake2(dd[cur][0][2], dd[cur][0][3]);
+        else U[0] = U[1] = 0u;  // up-samples below 2 q0 - 8 only meet zero weights
+        if (j < NB) U[2] = snake2(dd[cur][1][0], dd[cur][1][1]), U[3] = snake2(dd[cur][1][2], dd[cur][1][3]);
+        else U[2] = U[3] = 0u;
+        if (j >= 1) {  // last term of down block j - 1, then store it
+          float (&yy)[4] = y[(j - 1) % 3];
+          sm_mma(yy, U[0], U[1], U[2], U[3], bd[2][0], bd[2][1], yy[0], yy[1], yy[2], yy[3]);
+          if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], bdl[2][0], bdl[2][1], yy[0], yy[1], yy[2], yy[3]);
+        }
+        if (j >= 0 && j < NB) {
+          float (&yy)[4] = y[j % 3];
+          sm_mma(yy, U[0], U[1], U[2], U[3], bd[1][0], bd[1][1], yy[0], yy[1], yy[2], yy[3]);
+          if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], bdl[1][0], bdl[1][1], yy[0], yy[1], yy[2], yy[3]);
+        }
+        if (j + 1 < NB) {
+          float (&yy)[4] = y[(j + 1) % 3];
+          sm_mma(yy, U[0], U[1], U[2], U[3], bd[0][0], bd[0][1], hib, hib, hib, hib);
+          if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], bdl[0][0], bdl[0][1], yy[0], yy[1], yy[2], yy[3]);
+        }
         if (j >= 1) {
-          const int i = j - 1;  // outputs q0 + 8 i + n from blocks i - 1, i, i + 1 (indices i, i + 1, i + 2)
-          float y[4];
-          sm_mma(y, U[i][0], U[i][1], U[i][2], U[i][3], bd[0][0], bd[0][1], hib, hib, hib, hib);
-          sm_mma(y, U[i + 1][0], U[i + 1][1], U[i + 1][2], U[i + 1][3], bd[1][0], bd[1][1], y[0], y[1], y[2], y[3]);
-          sm_mma(y, U[i + 2][0], U[i + 2][1], U[i + 2][2], U[i + 2][3], bd[2][0], bd[2][1], y[0], y[1], y[2], y[3]);
-          if (SPLIT_F) {
-            sm_mma(y, U[i][0], U[i][1], U[i][2], U[i][3], bdl[0][0], bdl[0][1], y[0], y[1], y[2], y[3]);
-            sm_mma(y, U[i + 1][0], U[i + 1][1], U[i + 1][2], U[i + 1][3], bdl[1][0], bdl[1][1], y[0], y[1], y[2], y[3]);
-            sm_mma(y, U[i + 2][0], U[i + 2][1], U[i + 2][2], U[i + 2][3], bdl[2][0], bdl[2][1], y[0], y[1], y[2], y[3]);
-          }
+          const int i = j - 1;  // outputs q0 + 8 i + 2 q, + 1 of channel g, both halves
+          const float (&yy)[4] = y[i % 3];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             unsigned char* o = yp + (size_t)(8 * i + h * G::kSeg) * 16;
-            *reinterpret_cast<__half*>(o) = __float2half_rn(y[2 * h]);
-            *reinterpret_cast<__half*>(o + 16) = __float2half_rn(y[2 * h + 1]);
+            *reinterpret_cast<__half*>(o) = __float2half_rn(yy[2 * h]);
+            *reinterpret_cast<__half*>(o + 16) = __float2half_rn(yy[2 * h + 1]);
           }
         }
       }

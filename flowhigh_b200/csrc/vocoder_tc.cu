@@ -88,12 +88,6 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
     mma_mode = e ? atoi(e) : 0;  // the input split buys < 0.3 dB of end-to-end SNR for 15 % more kernel time
     if (mma_mode < -1 || mma_mode > 3) mma_mode = 0;
   }
-  static int mma_nb = 0;  // FH_SNAKE_NB: 8-output blocks per half-segment of the MMA kernel (8 or 4)
-  if (!mma_nb) {
-    const char* e = getenv("FH_SNAKE_NB");
-    mma_nb = e ? atoi(e) : 8;
-    if (mma_nb != 4 && mma_nb != 8) mma_nb = 8;
-  }
   const bool use_mma = out_kind == 2 && mma_mode >= 0 && row0 >= fh::SnakeMmaGeom<8>::kHalo;
   constexpr int kTileRows = fh::SnakeGeom<PR>::kRows;
   const int ntile = (L + kTileRows - 1) / kTileRows;
@@ -123,16 +117,12 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
   sp.batch_stride = batch_stride, sp.chunk_stride = chunk_stride;
   sp.row0 = row0, sp.nchunk = C / 8, sp.L = L, sp.ntile = ntile, sp.total = (int)total, sp.fp16 = out_kind == 2;
   if (use_mma) {
-    FH_REQUIRE((long long)((L + 63) / 64) * (C / 8) * B <= 2147483647LL, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: too many work items");
+    FH_REQUIRE((long long)((L + 511) / 512) * (C / 8) * B <= 2147483647LL, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: too many work items");
     cudaStream_t cs = (cudaStream_t)stream;
-    if (mma_nb == 4) {
-      if (mma_mode == 0) launch_snake_mma<0, 4, 6>(sp, B, C, L, sms, cs);
-      else launch_snake_mma<1, 4, 6>(sp, B, C, L, sms, cs);
-    } else {
-      if (mma_mode == 0) launch_snake_mma<0, 8, 4>(sp, B, C, L, sms, cs);
-      else if (mma_mode == 3) launch_snake_mma<3, 8, 4>(sp, B, C, L, sms, cs);
-      else launch_snake_mma<1, 8, 4>(sp, B, C, L, sms, cs);
-    }
+    // 8 blocks of 8 outputs per half-segment, 4 CTAs per SM (4-block segments at 6 CTAs per SM: 142 vs 118 ms per step)
+    if (mma_mode == 0) launch_snake_mma<0, 8, 4>(sp, B, C, L, sms, cs);
+    else if (mma_mode == 3) launch_snake_mma<3, 8, 4>(sp, B, C, L, sms, cs);
+    else launch_snake_mma<1, 8, 4>(sp, B, C, L, sms, cs);
     return fh::check_launch("fh_snake_aa_chunked");
   }
   constexpr int kSmem = fh::SnakeGeom<PR>::kSmemBytes;
