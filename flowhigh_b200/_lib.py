@@ -81,6 +81,7 @@ SIGNATURES = {
     "fh_tc_packed_weight_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "fh_to_chunked_16": (_i, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _i, _i, _p]),
     "fh_snake_aa_chunked": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _p]),
+    "fh_snake_aa_chunked_h": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _p]),
     "fh_convpost_tanh_chunked": (_i, [_p, _i64, _i64, _i, _p, _f, _p, _i, _i, _i, _p]),
 }
 

@@ -63,7 +63,10 @@ __device__ __forceinline__ void sm_mma(float (&d)[4], uint32_t a0, uint32_t a1, 
 // 2 x kSeg rows, stores them with its own bulk store and releases the window through a shared-memory counter -- the
 // last warp to release a window refills it with the tile after next.  There is no CTA-wide barrier in the loop (ncu
 // on a bar.sync version: 16 % of the warp stalls).
-template <bool SPLIT_X, bool SPLIT_F, int NB>
+// IN16: the input is already fp16 on the same chunked layout (16-byte rows, written by the 16-bit epilogue of the
+// preceding convolution): the A fragments of the up stage come straight from the window with one ldmatrix.x4.trans
+// per 8 up-samples (identity k-slot -> time map), no conversion instructions at all.
+template <bool SPLIT_X, bool SPLIT_F, int NB, bool IN16 = false>
 __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned char* smem, int tid, int cta, int nctas) {
   using G = SnakeMmaGeom<NB>;
   const int lane = tid & 31, warp = tid >> 5;
@@ -91,12 +94,14 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
     const int r_first = S.row0 + tile * G::kRows - G::kHalo;  // >= 0: the launcher requires row0 >= kHalo
     int nrows = rows_per_chunk - r_first;                     // stay inside this chunk's rows
     nrows = nrows < G::kXRows ? nrows : G::kXRows;
-    const float* src = S.x + (long long)b * S.batch_stride + (long long)ch * S.chunk_stride + (long long)r_first * 8;
+    const long long eoff = (long long)b * S.batch_stride + (long long)ch * S.chunk_stride + (long long)r_first * 8;
+    const void* src = IN16 ? (const void*)((const unsigned short*)S.x + eoff) : (const void*)(S.x + eoff);
+    const uint32_t bytes = (uint32_t)nrows * (IN16 ? 16u : 32u);
     const uint32_t bar = bar0 + 8 * buf;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)nrows * 32u) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      sw_u32(buf ? xs1 : xs0)),
-                 "l"(src), "r"((uint32_t)nrows * 32u), "r"(bar)
+                 "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
   };
 
@@ -107,11 +112,13 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
 #pragma unroll
   for (int e = 0; e < 2; ++e) {
     // up n-block e of a 16-up-sample block starting at input step T: up-sample m = 2T + 8e + n from the input steps
-    // T - 8 + ko (e = 0) or T + ko (e = 1), ko = q + 8r (slot 2q + 8r) and q + 4 + 8r (slot 2q + 8r + 1)
+    // T - 8 + ko (e = 0) or T + ko (e = 1), ko = q + 8r (slot 2q + 8r) and q + 4 + 8r (slot 2q + 8r + 1); ko = slot
+    // for the ldmatrix-fed fp16 input
     const int base = e ? 13 : 21;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      const float v0 = tap(g + base - 2 * (q + 8 * r), 2.0f), v1 = tap(g + base - 2 * (q + 4 + 8 * r), 2.0f);
+      const int ko0 = IN16 ? 2 * q + 8 * r : q + 8 * r, ko1 = IN16 ? ko0 + 1 : ko0 + 4;
+      const float v0 = tap(g + base - 2 * ko0, 2.0f), v1 = tap(g + base - 2 * ko1, 2.0f);
       sm_split(v0, v1, bu[e][r], bul[e][r]);
     }
   }
@@ -154,8 +161,14 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
         const int tc = min(max(t, 0), S.L - 1);
         if (tc != t) {
           const int rc = tc - (qt - G::kHalo);
-          if (rc >= 0 && rc < G::kXRows)
-            *reinterpret_cast<float4*>(&xt[r * 8 + h * 4]) = *reinterpret_cast<const float4*>(&xt[rc * 8 + h * 4]);
+          if (rc >= 0 && rc < G::kXRows) {
+            if (IN16) {  // 16-byte rows: two 8-byte halves
+              const uint2* w16 = reinterpret_cast<const uint2*>(xt);
+              reinterpret_cast<uint2*>(xt)[r * 2 + h] = w16[rc * 2 + h];
+            } else {
+              *reinterpret_cast<float4*>(&xt[r * 8 + h * 4]) = *reinterpret_cast<const float4*>(&xt[rc * 8 + h * 4]);
+            }
+          }
         }
       }
       __syncwarp();
@@ -177,7 +190,19 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
         }
       };
       // up n-block (j, e): the 8 up-samples 2 (q0 + 8 j) + 8 e + n, both halves, into dd
+      // fp16 input: lane l addresses row (l & 7) of matrix l >> 3: {half A, half B} x {first, second 8 input steps}
+      const uint32_t lm_base = sw_u32(xt) + (uint32_t)(ssA + (lane & 7) + ((lane >> 3) & 1) * G::kSeg + (lane >> 4) * 8) * 16u;
       auto up_mma = [&](int j, int e, float (&dd)[4]) {
+        if (IN16) {
+          const int k0 = (e ? 8 * j : 8 * j - 8) + G::kHalo;  // first window row (relative to this warp's half A)
+          uint32_t a0, a1, a2, a3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                       : "r"(lm_base + (uint32_t)(k0 * 16)));
+          sm_mma(dd, a0, a1, a2, a3, bu[e][0], bu[e][1], 0.f, 0.f, 0.f, 0.f);
+          if (SPLIT_F) sm_mma(dd, a0, a1, a2, a3, bul[e][0], bul[e][1], dd[0], dd[1], dd[2], dd[3]);
+          return;
+        }
         const int p = (e ? j : j - 1) + 1, n = p + 1;
         sm_mma(dd, xh[p][0], xh[p][1], xh[n][0], xh[n][1], bu[e][0], bu[e][1], 0.f, 0.f, 0.f, 0.f);
         if (SPLIT_X) sm_mma(dd, xl[p][0], xl[p][1], xl[n][0], xl[n][1], bu[e][0], bu[e][1], dd[0], dd[1], dd[2], dd[3]);
@@ -197,14 +222,16 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
       //      independent MMAs; every down accumulator is next touched one whole step later.
       float dd[2][2][4];  // [step parity][e][acc]
       float y[3][4];      // down accumulators of blocks i, at index i % 3
-      load_x(-1);
-      load_x(0);
-      if (NB >= 1) load_x(1);
+      if (!IN16) {
+        load_x(-1);
+        load_x(0);
+        if (NB >= 1) load_x(1);
+      }
       up_mma(-1, 1, dd[0][1]);
 #pragma unroll
       for (int j = -1; j <= NB; ++j) {
         const int cur = (j + 1) & 1, nxt = cur ^ 1;
-        if (j + 3 <= NB) load_x(j + 3);  // consumed by the MMAs issued in the next step
+        if (!IN16 && j + 3 <= NB) load_x(j + 3);  // consumed by the MMAs issued in the next step
         if (j + 1 <= NB) {
           up_mma(j + 1, 0, dd[nxt][0]);
           if (j + 1 < NB) up_mma(j + 1, 1, dd[nxt][1]);
@@ -257,7 +284,9 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
             for (int t6 = 0; t6 < 6; ++t6) {
               const int i = ihi - t6;
               const int ic = min(max(i, 0), S.L - 1);
-              u = fmaf(2.0f * __ldg(S.filt + (m + 5 - 2 * i)), xt[(ic - qt + G::kHalo) * 8 + c], u);
+              const int xi = (ic - qt + G::kHalo) * 8 + c;
+              const float xv = IN16 ? __half2float(reinterpret_cast<const __half*>(xt)[xi]) : xt[xi];
+              u = fmaf(2.0f * __ldg(S.filt + (m + 5 - 2 * i)), xv, u);
             }
             acc = fmaf(__ldg(S.filt + k), u - hib * __cosf(alv * u), acc);
           }

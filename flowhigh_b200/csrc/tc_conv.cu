@@ -386,7 +386,9 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
 // ncu showed the eight epilogue warps -- not HBM -- pacing the HBM-bound C <= 96 stages.  Here the bias (pre-multiplied by
 // alpha) comes from a shared-memory table with broadcast 128-bit loads, the flags are template parameters, and a group
 // costs ~45 instructions:  o = fma(acc, alpha, alpha * bias) [+ beta * residual] [+ previous output].
-template <bool HAS_RES, bool ACCUM>
+// OUT16: 16-bit output rows (16 bytes per chunk row, no residual / accumulate) -- the snake that follows a first AMP
+// convolution reads them as MMA operands directly.
+template <bool HAS_RES, bool ACCUM, bool OUT16 = false>
 __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                               int lane_grp, int half, int gstep, int lane, int tile_rows, uint32_t acc_cols,
                                               const float* s_bias) {
@@ -442,7 +444,8 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
       coords(gi, c0, t);
       const int n0 = n_base + c0;
       if (n0 >= P.Cout || t >= P.L) return;
-      float* dst = outp + out_b + (long long)t * out_rs + (long long)(n0 >> 3) * P.out_chunk;
+      const long long oidx = out_b + (long long)t * out_rs + (long long)(n0 >> 3) * P.out_chunk;
+      float* dst = outp + oidx;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
         if (hh == 1 && n0 + 8 >= P.Cout) break;
@@ -456,7 +459,14 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
           if (HAS_RES) o[i] = fmaf(beta, rr[hh * 8 + i], o[i]);
           if (ACCUM) o[i] += pp[hh * 8 + i];
         }
-        stg_v8(dst + (long long)hh * P.out_chunk, o);
+        if (OUT16) {
+          uint32_t h[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
+          *reinterpret_cast<uint4*>((unsigned short*)P.out + oidx + (long long)hh * P.out_chunk) = *reinterpret_cast<uint4*>(h);
+        } else {
+          stg_v8(dst + (long long)hh * P.out_chunk, o);
+        }
       }
     };
 
@@ -632,7 +642,9 @@ __device__ __forceinline__ void epilogue_dispatch(const TcParams& P, uint32_t tm
                                                   int lg, int hf, int lane, int tile_rows, uint32_t acc_cols,
                                                   const float* s_bias) {
   if (P.fast_epi) {
-    if (P.res != nullptr && P.accumulate)
+    if (P.out_is_16)
+      epilogue_fast<false, false, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+    else if (P.res != nullptr && P.accumulate)
       epilogue_fast<true, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
     else if (P.res != nullptr)
       epilogue_fast<true, false>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
@@ -1318,7 +1330,8 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
     fast_on = e ? atoi(e) : 1;
   }
   const int bias_tab = a->bias ? ((p.n_tiles * a->bn + 15) & ~15) * 4 : 64;
-  p.fast_epi = (fast_on && p.v8 && !a->geglu && !p.act_gelu && !a->out_is_16 && !(a->res && a->res_is_16) && bias_tab <= 8192) ? 1 : 0;
+  p.fast_epi = (fast_on && p.v8 && !a->geglu && !p.act_gelu && !(a->res && a->res_is_16) && bias_tab <= 8192 &&
+                (!a->out_is_16 || (a->res == nullptr && !a->accumulate))) ? 1 : 0;
   const int tail = p.fast_epi ? bias_tab : 0;
   int stages = (budget - 1024 - tail) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;

@@ -22,25 +22,26 @@ __global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(const __gr
 
 // fp16 output mode: both FIR filters as Toeplitz MMAs (snake_mma.cuh).  MODE bit 0: hi/lo split of the input,
 // bit 1: hi/lo split of the filter taps.
-template <int MODE, int NB, int MINB>
+template <int MODE, int NB, int MINB, bool IN16>
 __global__ void __launch_bounds__(128, MINB) snake_aa_mma_kernel(const __grid_constant__ fh::SnakeParams S) {
   extern __shared__ __align__(128) unsigned char snake_smem[];
-  fh::snake_mma_cta<(MODE & 1) != 0, (MODE & 2) != 0, NB>(S, snake_smem, threadIdx.x, blockIdx.x, gridDim.x);
+  fh::snake_mma_cta<(MODE & 1) != 0, (MODE & 2) != 0, NB, IN16>(S, snake_smem, threadIdx.x, blockIdx.x, gridDim.x);
 }
 
-template <int MODE, int NB, int MINB>
+template <int MODE, int NB, int MINB, bool IN16 = false>
 void launch_snake_mma(fh::SnakeParams sp, int B, int C, int L, int sms, cudaStream_t stream) {
   using G = fh::SnakeMmaGeom<NB>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(snake_aa_mma_kernel<MODE, NB, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::kSmemBytes);
+    cudaFuncSetAttribute(snake_aa_mma_kernel<MODE, NB, MINB, IN16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         G::kSmemBytes);
     attr_set = true;
   }
   sp.ntile = (L + G::kRows - 1) / G::kRows;
   const long long total = (long long)sp.ntile * (C / 8) * B;
   sp.total = (int)total;
   const int grid = (int)(total < (long long)sms * MINB ? total : (long long)sms * MINB);
-  snake_aa_mma_kernel<MODE, NB, MINB><<<grid, 128, G::kSmemBytes, stream>>>(sp);
+  snake_aa_mma_kernel<MODE, NB, MINB, IN16><<<grid, 128, G::kSmemBytes, stream>>>(sp);
 }
 
 __global__ void convpost_tanh_chunked_kernel(const float* __restrict__ x, long long batch_stride,
@@ -134,6 +135,32 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
   else FH_SNAKE_LAUNCH(2, false);
 #undef FH_SNAKE_LAUNCH
   return fh::check_launch("fh_snake_aa_chunked");
+}
+
+// fp16 in -> fp16 out on the same chunked geometry: the input was written by the 16-bit epilogue of the first
+// convolution of an AMP unit (fh_tc_conv with out_is_16), so the fp32 round trip of that tensor disappears.
+extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked_h(
+    const void* x16, void* y, const float* a, const float* inv_b, const float* filt, int64_t batch_stride,
+    int64_t chunk_stride, int row0, int B, int C, int L, void* stream) {
+  FH_REQUIRE(B > 0 && C > 0 && (C % 8) == 0 && L > 0, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked_h: C must be a multiple of 8");
+  FH_REQUIRE(((uintptr_t)x16 % 16) == 0 && ((uintptr_t)y % 16) == 0 && (batch_stride % 8) == 0 && (chunk_stride % 8) == 0,
+             FH_ERR_BAD_ALIGN, "fh_snake_aa_chunked_h: buffers must be 16-byte aligned and strides multiples of 8");
+  FH_REQUIRE(row0 >= fh::SnakeMmaGeom<8>::kHalo, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked_h: needs a left halo of >= 8 rows");
+  FH_REQUIRE((long long)((L + 511) / 512) * (C / 8) * B <= 2147483647LL, FH_ERR_BAD_SHAPE,
+             "fh_snake_aa_chunked_h: too many work items");
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  fh::SnakeParams sp;
+  sp.x = (const float*)x16, sp.y = y, sp.a = a, sp.inv_b = inv_b, sp.filt = filt;
+  sp.batch_stride = batch_stride, sp.chunk_stride = chunk_stride;
+  sp.row0 = row0, sp.nchunk = C / 8, sp.L = L, sp.ntile = 0, sp.total = 0, sp.fp16 = 1;
+  launch_snake_mma<0, 8, 4, true>(sp, B, C, L, sms, (cudaStream_t)stream);
+  return fh::check_launch("fh_snake_aa_chunked_h");
 }
 
 extern "C" __attribute__((visibility("default"))) int fh_convpost_tanh_chunked(

@@ -232,6 +232,10 @@ int fh_to_chunked_16(const float* src, int64_t src_batch, int64_t src_c, int64_t
 int fh_snake_aa_chunked(const float* x, void* y, const float* a, const float* inv_b, const float* filt,
                         int64_t batch_stride, int64_t chunk_stride, int row0, int B, int C, int L,
                         int out_kind, void* stream);
+/* same op with an fp16 chunked input (written by fh_tc_conv with out_is_16) and fp16 output: Activation1d.forward
+ * (alias_free_torch/act.py:23-28) between the two convolutions of an AMPBlock1 unit (bigvgan/models.py:63-72) */
+int fh_snake_aa_chunked_h(const void* x16, void* y, const float* a, const float* inv_b, const float* filt,
+                          int64_t batch_stride, int64_t chunk_stride, int row0, int B, int C, int L, void* stream);
 int fh_convpost_tanh_chunked(const float* x, int64_t batch_stride, int64_t chunk_stride, int row0,
                              const float* w, float bias, float* y, int B, int C, int L, void* stream);
 

@@ -113,44 +113,51 @@ def test_snake_f32(cuda_device):
         assert float((y.cpu() - ref).abs().max()) <= 5e-6
 
 
-@pytest.mark.parametrize("out_kind", [2, 1, 0])
+@pytest.mark.parametrize("out_kind", [2, 3, 1, 0])
 def test_snake_chunked(cuda_device, out_kind):
     """fh_snake_aa_chunked on the chunked [C/8][Lp][8] layout against the oracle closed form: fp16 output (Toeplitz-MMA
-    kernel), bf16 and fp32 output (scalar kernel).  Lengths cover one-tile, multi-tile, tile-boundary (512 / 544 rows)
+    kernel; out_kind 3 = fh_snake_aa_chunked_h, the same kernel fed with fp16 rows through ldmatrix), bf16 and fp32
+    output (scalar kernel).  Lengths cover one-tile, multi-tile, tile-boundary (512 / 544 rows)
     and shorter-than-the-filter sequences; the rows after L must stay untouched (they are the next conv's zero padding)."""
     eng, sd, vcfg, _ = engine("gen_basic_midpoint", "fp32")
     torch.manual_seed(5)
     filt = torch.from_numpy(np.ascontiguousarray(eng.sd["flowhigh.audio_enc_dec.vocoder.activation_post.upsample.filter"].cpu().numpy()))
     fd = filt.flatten().cuda()
-    odt = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16}[out_kind]
-    tol = {0: 5e-6, 1: 2.0 ** -8, 2: 2.0 ** -11}[out_kind]
+    odt = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16, 3: torch.float16}[out_kind]
+    tol = {0: 5e-6, 1: 2.0 ** -8, 2: 2.0 ** -11, 3: 2.0 ** -11}[out_kind]
     for (B, Cc, L) in [(2, 16, 700), (1, 8, 3), (1, 8, 13), (1, 8, 512), (2, 8, 513), (1, 16, 544), (1, 8, 1021),
                        (1, 8, 1024), (1, 8, 1030), (3, 24, 2500)]:
         x = torch.randn(B, Cc, L) * 2
+        if out_kind == 3:
+            x = x.half().float()  # the fp16-input entry point is exact in its input
         alpha, beta = torch.randn(Cc) * 0.3, torch.randn(Cc) * 0.3
         ref = model.aa_activation(x.double(), alpha.double(), beta.double(), filt.double(), filt.double(), True)
         Lp = HALO + packing.round_up(L, 128) + 64
         cs, bs = Lp * 8, (Cc // 8) * Lp * 8
         xc = torch.zeros(B, Cc // 8, Lp, 8)
         xc[:, :, HALO:HALO + L] = x.reshape(B, Cc // 8, 8, L).permute(0, 1, 3, 2)
-        xd = xc.cuda()
+        xd = xc.cuda().half() if out_kind == 3 else xc.cuda()
         y = torch.full((B, Cc // 8, Lp, 8), 7.0, dtype=odt, device="cuda:0")
         a = torch.exp(alpha).cuda()
         ib = (1.0 / (torch.exp(beta) + 1e-9)).cuda()
-        eng._call("fh_snake_aa_chunked", xd.data_ptr(), y.data_ptr(), a.data_ptr(), ib.data_ptr(), fd.data_ptr(), bs, cs,
-                  HALO, B, Cc, L, out_kind, eng.stream)
+        if out_kind == 3:
+            eng._call("fh_snake_aa_chunked_h", xd.data_ptr(), y.data_ptr(), a.data_ptr(), ib.data_ptr(), fd.data_ptr(), bs,
+                      cs, HALO, B, Cc, L, eng.stream)
+        else:
+            eng._call("fh_snake_aa_chunked", xd.data_ptr(), y.data_ptr(), a.data_ptr(), ib.data_ptr(), fd.data_ptr(), bs,
+                      cs, HALO, B, Cc, L, out_kind, eng.stream)
         torch.cuda.synchronize()
         yc = y.cpu().double()
         out = yc[:, :, HALO:HALO + L].permute(0, 1, 3, 2).reshape(B, Cc, L)
         err = (out - ref).abs()
         # fp16 kind (Toeplitz-MMA kernel): input, snake output and filter taps are rounded to fp16 on the way, i.e.
         # 2^-11 relative to the INPUT scale (|x| up to ~8 here), not to y
-        bound = tol * ref.abs() + {0: 1e-5, 1: 3e-4, 2: 1e-2}[out_kind]
+        bound = tol * ref.abs() + {0: 1e-5, 1: 3e-4, 2: 1e-2, 3: 1e-2}[out_kind]
         worst = float((err - bound).max())
         snr = snr_db(ref.float(), out.float())
         print(f"snake chunked kind={out_kind} {(B, Cc, L)}: max-abs {float(err.max()):.3g}, SNR {snr:.1f} dB")
         assert worst <= 0, (B, Cc, L, np.unravel_index(int((err - bound).argmax()), err.shape))
-        assert snr >= {0: 120.0, 1: 50.0, 2: 60.0}[out_kind]
+        assert snr >= {0: 120.0, 1: 50.0, 2: 60.0, 3: 60.0}[out_kind]
         assert bool((yc[:, :, :HALO] == 7.0).all()) and bool((yc[:, :, HALO + L:] == 7.0).all())
 
 
