@@ -314,11 +314,11 @@ def main():
             if B == BATCH and os.path.exists(tpath) and "snake" in json.load(open(tpath)):
                 tj = json.load(open(tpath))["snake"]
                 straffic = (tj["dram_read_bytes"] + tj["dram_write_bytes"]) / tj["launches"]
-            roofline_snake = {"kernel": "snake_aa_chunked_tma_kernel (fused up2x -> Snake -> down2x)", "bound": "hbm",
+            roofline_snake = {"kernel": "snake_aa_mma_kernel (fused up2x -> Snake -> down2x, both FIR filters as Toeplitz MMAs)", "bound": "hbm",
                               "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": straffic,
                               "algorithmic_bytes_per_launch": sn["bytes"] / sn["launches"], "launches_per_step": sn["launches"],
                               "avg_launch_ms": sn["ms"] / sn["launches"], "share_of_step": sn["ms"] / tot_ms if tot_ms else None,
-                              "note": "FP32-issue-bound: ncu fma pipe 60 % active, DRAM 38 % (profiles/r1_ncu_snake.txt)"}
+                              "note": "fp32 rows in (fp16 rows behind the first conv of an AMP unit), fp16 rows out; ncu: profiles/r1_ncu_snake.txt"}
         groups = {}
         for k, v in breakdown.items():
             gname = "tc_conv" if k.startswith("tc_conv") else k

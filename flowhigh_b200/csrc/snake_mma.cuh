@@ -34,10 +34,10 @@ struct SnakeMmaGeom {
   static constexpr int kRows = kWarps * kWarpRows;
   static constexpr int kHalo = 8;               // window rows before / after the tile
   static constexpr int kXRows = kRows + 2 * kHalo;
-  static constexpr int kXBytes = kXRows * 32;
+  static constexpr int kXBytes = kXRows * 32;  // fp32 rows; fp16 input rows take half of it
   static constexpr int kWarpYBytes = kWarpRows * 16;
   // two input windows, per warp two output images, two mbarriers + two release counters
-  static constexpr int kSmemBytes = 2 * kXBytes + 2 * kWarps * kWarpYBytes + 32;
+  static constexpr int smem_bytes(bool in16) { return 2 * (in16 ? kXBytes / 2 : kXBytes) + 2 * kWarps * kWarpYBytes + 32; }
 };
 
 __device__ __forceinline__ uint32_t sm_pack(float lo, float hi) {
@@ -70,10 +70,11 @@ template <bool SPLIT_X, bool SPLIT_F, int NB, bool IN16 = false>
 __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned char* smem, int tid, int cta, int nctas) {
   using G = SnakeMmaGeom<NB>;
   const int lane = tid & 31, warp = tid >> 5;
+  constexpr int kXB = IN16 ? G::kXBytes / 2 : G::kXBytes;  // bytes of one input window
   float* xs0 = reinterpret_cast<float*>(smem);
-  float* xs1 = reinterpret_cast<float*>(smem + G::kXBytes);
-  unsigned char* ys0 = smem + 2 * G::kXBytes + warp * 2 * G::kWarpYBytes;  // this warp's two output images
-  unsigned char* ctl = smem + 2 * G::kXBytes + 2 * G::kWarps * G::kWarpYBytes;
+  float* xs1 = reinterpret_cast<float*>(smem + kXB);
+  unsigned char* ys0 = smem + 2 * kXB + warp * 2 * G::kWarpYBytes;  // this warp's two output images
+  unsigned char* ctl = smem + 2 * kXB + 2 * G::kWarps * G::kWarpYBytes;
   const uint32_t bar0 = sw_u32(ctl);
   int* released = reinterpret_cast<int*>(ctl + 16);  // warps done with window 0 / 1
   if (tid == 0) {
@@ -83,7 +84,7 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
     released[0] = released[1] = 0;
   }
   // rows a clipped copy does not fill must hold finite values (they only ever meet zero filter weights)
-  for (int i = tid; i < 2 * G::kXBytes / 16; i += 32 * G::kWarps) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < 2 * kXB / 16; i += 32 * G::kWarps) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   const int rows_per_chunk = (int)(S.chunk_stride >> 3);

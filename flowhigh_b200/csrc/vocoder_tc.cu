@@ -34,14 +34,14 @@ void launch_snake_mma(fh::SnakeParams sp, int B, int C, int L, int sms, cudaStre
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(snake_aa_mma_kernel<MODE, NB, MINB, IN16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         G::kSmemBytes);
+                         G::smem_bytes(IN16));
     attr_set = true;
   }
   sp.ntile = (L + G::kRows - 1) / G::kRows;
   const long long total = (long long)sp.ntile * (C / 8) * B;
   sp.total = (int)total;
   const int grid = (int)(total < (long long)sms * MINB ? total : (long long)sms * MINB);
-  snake_aa_mma_kernel<MODE, NB, MINB, IN16><<<grid, 128, G::kSmemBytes, stream>>>(sp);
+  snake_aa_mma_kernel<MODE, NB, MINB, IN16><<<grid, 128, G::smem_bytes(IN16), stream>>>(sp);
 }
 
 __global__ void convpost_tanh_chunked_kernel(const float* __restrict__ x, long long batch_stride,
@@ -159,7 +159,15 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked_h(
   sp.x = (const float*)x16, sp.y = y, sp.a = a, sp.inv_b = inv_b, sp.filt = filt;
   sp.batch_stride = batch_stride, sp.chunk_stride = chunk_stride;
   sp.row0 = row0, sp.nchunk = C / 8, sp.L = L, sp.ntile = 0, sp.total = 0, sp.fp16 = 1;
-  launch_snake_mma<0, 8, 4, true>(sp, B, C, L, sms, (cudaStream_t)stream);
+  // FH_SNAKE_H_CTAS=5: five CTAs per SM fit with the half-size fp16 windows (33 KB, 90 registers) -- measured SLOWER
+  // (101.5 vs 98.3 ms per step, like every other occupancy increase of this kernel: it is not latency-bound)
+  static int per_sm = 0;
+  if (!per_sm) {
+    const char* e = getenv("FH_SNAKE_H_CTAS");
+    per_sm = e ? atoi(e) : 4;
+  }
+  if (per_sm == 5) launch_snake_mma<0, 8, 5, true>(sp, B, C, L, sms, (cudaStream_t)stream);
+  else launch_snake_mma<0, 8, 4, true>(sp, B, C, L, sms, (cudaStream_t)stream);
   return fh::check_launch("fh_snake_aa_chunked_h");
 }
 

@@ -10,6 +10,6 @@ F="ncu --profile-from-start off --set full --clock-control none --import-source 
 $F -k regex:tc_conv_kernel -s 34 -c 2 -o gpurun_out/${R}_prof_tc768 $P --batch 8 > /dev/null 2>&1
 $F -k regex:tc_conv_kernel -s 47 -c 2 -o gpurun_out/${R}_prof_tc384 $P --batch 8 > /dev/null 2>&1
 $F -k regex:tc_conv_kernel -s 98 -c 2 -o gpurun_out/${R}_prof_tc48 $P --batch 8 > /dev/null 2>&1
-$F -k regex:snake_aa -s 54 -c 1 -o gpurun_out/${R}_prof_snake $P --batch 8 > /dev/null 2>&1
+$F -k regex:snake_aa_mma -s 54 -c 2 -o gpurun_out/${R}_prof_snake $P --batch 8 > /dev/null 2>&1
 ncu --profile-from-start off --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${R}_traffic_b64.csv $P --batch 64 > /dev/null 2>&1
 ls -la gpurun_out/${R}_*
