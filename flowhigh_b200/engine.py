@@ -106,6 +106,11 @@ class Engine:
         if t is None:
             t = (torch.zeros if zero else torch.empty)(key[1], dtype=dtype, device=self.device)
             self._bufs[key] = t
+            # The zero-fill runs on the stream that is current NOW, but the buffer may first be used on another one
+            # (the AMP branch streams wait on an event recorded before their scratch buffers are created): without
+            # this, the fill can land after a branch kernel has written the buffer.  First use of a shape only.
+            if not torch.cuda.is_current_stream_capturing():
+                torch.cuda.current_stream(self.device).synchronize()
         return t
 
     def _chk(self, *tensors):

@@ -617,6 +617,22 @@ def test_fused_snake_conv_matches_unfused(cuda_device, name):
     assert err <= 3e-3 and sa >= 55.0 and sb >= 55.0 and abs(sa - sb) <= 2.0
 
 
+def test_first_call_with_parallel_branches_is_clean(cuda_device):
+    """The per-branch scratch buffers of the small-batch path are created (zero-filled) on first use; that fill must be
+    ordered before the branch streams touch them (found by compute-sanitizer timing: the very first call of a fresh
+    engine returned garbage).  First call == later calls, bit for bit."""
+    g = load_golden("voc_resblock1_snakebeta")
+    sd, vcfg = golden_weights(g)
+    eng = Engine(sd, vcfg, device="cuda:0", precision="fp16")
+    assert eng.branch_streams
+    mel = dev(g["mel"])
+    first = eng.vocoder(mel).cpu()
+    again = eng.vocoder(mel).cpu()
+    assert torch.equal(first, again)
+    ref = torch.from_numpy(g["f64_vocoder"]).reshape(first.shape).float()
+    assert snr_db(ref, first) >= 55.0
+
+
 def test_dual_conv_snake_launches_match_separate(cuda_device):
     """fh_tc_conv_snake_dual (conv of one half-batch + snake of the other in one kernel, engine tapes staggered by one
     operator) must reproduce the back-to-back launches: same kernels' arithmetic, only the schedule differs."""
