@@ -36,8 +36,8 @@ struct SnakeMmaGeom {
   static constexpr int kXRows = kRows + 2 * kHalo;
   static constexpr int kXBytes = kXRows * 32;  // fp32 rows; fp16 input rows take half of it
   static constexpr int kWarpYBytes = kWarpRows * 16;
-  // two input windows, per warp two output images, two mbarriers + two release counters
-  static constexpr int smem_bytes(bool in16) { return 2 * (in16 ? kXBytes / 2 : kXBytes) + 2 * kWarps * kWarpYBytes + 32; }
+  // two input windows, per warp two output images, 128 control bytes: two mbarriers, two release counters, 2 x 12 taps
+  static constexpr int smem_bytes(bool in16) { return 2 * (in16 ? kXBytes / 2 : kXBytes) + 2 * kWarps * kWarpYBytes + 128; }
 };
 
 __device__ __forceinline__ uint32_t sm_pack(float lo, float hi) {
@@ -77,11 +77,36 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
   unsigned char* ctl = smem + 2 * kXB + 2 * G::kWarps * G::kWarpYBytes;
   const uint32_t bar0 = sw_u32(ctl);
   int* released = reinterpret_cast<int*>(ctl + 16);  // warps done with window 0 / 1
+  float* s_taps = reinterpret_cast<float*>(ctl + 32);  // [0, 12): up-filter taps (2 f), [12, 24): down-filter taps (f)
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0) : "memory");
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     released[0] = released[1] = 0;
+    // fp16 taps by ERROR FEEDBACK instead of round-to-nearest: within each polyphase branch (even / odd taps) the
+    // taps are rounded in order of decreasing magnitude and every rounding error is carried into the next, finer-grained
+    // tap, so the branch sums (the DC gains) stay exact to ~2^-20.  On low-pass signals the response error of the
+    // rounded filters drops from -66 dB (round-to-nearest) to -83 dB (CPU experiment).
+    for (int w = 0; w < 2; ++w) {
+      const float scale = w ? 1.0f : 2.0f;
+      for (int ph = 0; ph < 2; ++ph) {
+        unsigned done = 0;
+        float carry = 0.f;
+        for (int n = 0; n < 6; ++n) {
+          int best = -1;
+          float bm = -1.f;
+          for (int c = 0; c < 6; ++c) {
+            const float m = fabsf(__ldg(S.filt + 2 * c + ph));
+            if (!((done >> c) & 1u) && m > bm) bm = m, best = c;
+          }
+          done |= 1u << best;
+          const float v = scale * __ldg(S.filt + 2 * best + ph) + carry;
+          const float h = SPLIT_F ? v : __half2float(__float2half_rn(v));  // the tap-split mode keeps exact taps
+          carry = v - h;
+          s_taps[12 * w + 2 * best + ph] = h;
+        }
+      }
+    }
   }
   // rows a clipped copy does not fill must hold finite values (they only ever meet zero filter weights)
   for (int i = tid; i < 2 * kXB / 16; i += 32 * G::kWarps) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -108,7 +133,9 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
 
   const int g = lane >> 2, q = lane & 3;
   // ---- Toeplitz B fragments (k16 x n8, "col"): reg r holds k-slots 2q + 8r, 2q + 8r + 1 of column n = g
-  auto tap = [&](int idx, float scale) -> float { return (idx >= 0 && idx < 12) ? scale * __ldg(S.filt + idx) : 0.f; };
+  auto tap = [&](int idx, float scale) -> float {  // scale 2 = up filter, 1 = down filter
+    return (idx >= 0 && idx < 12) ? s_taps[(scale == 2.0f ? 0 : 12) + idx] : 0.f;
+  };
   uint32_t bu[2][2], bul[2][2], bd[3][2], bdl[3][2];
 #pragma unroll
   for (int e = 0; e < 2; ++e) {

@@ -118,7 +118,7 @@ def test_snake_chunked(cuda_device, out_kind):
     """fh_snake_aa_chunked on the chunked [C/8][Lp][8] layout against the oracle closed form: fp16 output (Toeplitz-MMA
     kernel; out_kind 3 = fh_snake_aa_chunked_h, the same kernel fed with fp16 rows through ldmatrix), bf16 and fp32
     output (scalar kernel).  Lengths cover one-tile, multi-tile, tile-boundary (512 / 544 rows)
-    and shorter-than-the-filter sequences; the rows after L must stay untouched (they are the next conv's zero padding)."""
+    and shorter-than-the-filter sequences (tile = 1024 rows by default, 512 with FH_SNAKE_NB=8, 544 for the scalar kernel); the rows after L must stay untouched (they are the next conv's zero padding)."""
     eng, sd, vcfg, _ = engine("gen_basic_midpoint", "fp32")
     torch.manual_seed(5)
     filt = torch.from_numpy(np.ascontiguousarray(eng.sd["flowhigh.audio_enc_dec.vocoder.activation_post.upsample.filter"].cpu().numpy()))
@@ -126,7 +126,7 @@ def test_snake_chunked(cuda_device, out_kind):
     odt = {0: torch.float32, 1: torch.bfloat16, 2: torch.float16, 3: torch.float16}[out_kind]
     tol = {0: 5e-6, 1: 2.0 ** -8, 2: 2.0 ** -11, 3: 2.0 ** -11}[out_kind]
     for (B, Cc, L) in [(2, 16, 700), (1, 8, 3), (1, 8, 13), (1, 8, 512), (2, 8, 513), (1, 16, 544), (1, 8, 1021),
-                       (1, 8, 1024), (1, 8, 1030), (3, 24, 2500)]:
+                       (1, 8, 1024), (1, 8, 1030), (1, 8, 2047), (1, 8, 2051), (3, 24, 2500)]:
         x = torch.randn(B, Cc, L) * 2
         if out_kind == 3:
             x = x.half().float()  # the fp16-input entry point is exact in its input
