@@ -207,7 +207,8 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
       const float2 al2 = make_float2(alv, alv), nhib2 = make_float2(-hib, -hib);
       // window row of item row r is r + kHalo; input block jx of half h covers window rows h kSeg + 8 jx + 8 ...
       const float* xp = xt + (ssA + q) * 8 + g;
-      unsigned char* yp = yt + (size_t)(2 * q) * 16 + 2 * g;
+      // stmatrix row addresses: lanes 0-7 = rows of half A, lanes 8-15 = rows of half B (others ignored by .x2)
+      const uint32_t st_base = sw_u32(yt) + (uint32_t)((lane & 7) + ((lane >> 3) & 1) * G::kSeg) * 16u;
       uint32_t xh[NB + 2][2], xl[NB + 2][2];  // input blocks jx = -1 .. NB at index jx + 1
       auto load_x = [&](int jx) {
 #pragma unroll
@@ -285,14 +286,14 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
           if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], bdl[0][0], bdl[0][1], yy[0], yy[1], yy[2], yy[3]);
         }
         if (j >= 1) {
-          const int i = j - 1;  // outputs q0 + 8 i + 2 q, + 1 of channel g, both halves
+          // outputs q0 + 8 i + {2 q, 2 q + 1} of channel g, both halves: the accumulator tile is an 8 x 8 [seq][time]
+          // fragment per half, stored TRANSPOSED ([time][8 ch] rows of 16 bytes) by one stmatrix
+          const int i = j - 1;
           const float (&yy)[4] = y[i % 3];
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            unsigned char* o = yp + (size_t)(8 * i + h * G::kSeg) * 16;
-            *reinterpret_cast<__half*>(o) = __float2half_rn(yy[2 * h]);
-            *reinterpret_cast<__half*>(o + 16) = __float2half_rn(yy[2 * h + 1]);
-          }
+          const uint32_t r0 = sm_pack(yy[0], yy[1]), r1 = sm_pack(yy[2], yy[3]);
+          asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(st_base + (uint32_t)(8 * i * 16)),
+                       "r"(r0), "r"(r1)
+                       : "memory");
         }
       }
     }
