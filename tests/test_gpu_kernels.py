@@ -617,6 +617,26 @@ def test_fused_snake_conv_matches_unfused(cuda_device, name):
     assert err <= 3e-3 and sa >= 55.0 and sb >= 55.0 and abs(sa - sb) <= 2.0
 
 
+@pytest.mark.parametrize("name", ["voc_resblock1_snakebeta", "voc_resblock2_snake"])
+def test_vocoder_large_batch_path(cuda_device, name):
+    """Batches above 4 clips run the AMP branches back to back and accumulate their mean in place (accumulate epilogue of
+    fh_tc_conv, fh_cast_f32_16 between stages) -- the path bench.py measures at B = 64.  The golden clips against the
+    reference, every clip against its own B = 1 run (parallel-branch path: separate outputs + fh_sum_cast_f32)."""
+    eng, sd, vcfg, g = engine(name, "fp16")
+    mel = dev(g["mel"])
+    batch = torch.cat([mel, mel.flip(1) * 0.9, mel * 0.8, mel.roll(3, 1), mel * 1.1 - 0.2, mel.flip(1)], 0).contiguous()
+    assert batch.shape[0] > eng.branch_streams_max_batch
+    out = eng.vocoder(batch).cpu()
+    nb = mel.shape[0]  # the golden mel is itself a small batch: its clips come first
+    ref = torch.from_numpy(g["f64_vocoder"]).reshape(out[:nb].shape).float()
+    s0 = snr_db(ref, out[:nb])
+    print(f"large-batch vocoder {name}: golden clips SNR vs reference {s0:.1f} dB")
+    assert s0 >= 55.0 and torch.isfinite(out).all()
+    for i in range(batch.shape[0]):
+        single = eng.vocoder(batch[i:i + 1].contiguous()).cpu()
+        assert snr_db(single, out[i:i + 1]) >= 55.0, i
+
+
 def test_first_call_with_parallel_branches_is_clean(cuda_device):
     """The per-branch scratch buffers of the small-batch path are created (zero-filled) on first use; that fill must be
     ordered before the branch streams touch them (found by compute-sanitizer timing: the very first call of a fresh
