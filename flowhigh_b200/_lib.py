@@ -32,6 +32,7 @@ class TcConvArgs(C.Structure):
         ("fp16", _i),
         ("x_f32", _p), ("sn_a", _p), ("sn_inv_b", _p), ("sn_filt", _p),
         ("act", _i),
+        ("acc_src", _p),
     ]
 
 

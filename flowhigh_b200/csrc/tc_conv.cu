@@ -39,6 +39,7 @@ struct TcParams {
   long long res_batch, res_chunk, res_row;
   int a_row0;
   int out_is_16, res_is_16, fp16, accumulate, geglu;
+  const float* acc_src;  // accumulate source when it is not the output itself (fp32, output geometry); else nullptr
   int act_gelu;        // exact-erf GELU on (acc + bias) * alpha before the residual (ConvNeXt pwconv1)
   float alpha, beta_res;
   int B, L, Cin, Cout, ntaps, P, bn;
@@ -400,6 +401,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
   const int bmask = P.bias ? ~0 : 0;  // no bias: every group reads the 16 zeros at the head of the table
   const float* resp = (const float*)P.res;
   float* outp = (float*)P.out;
+  const float* accp = P.acc_src ? P.acc_src : (const float*)P.out;  // "previous output" rows of the accumulate form
   for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
     const TileCoord tc = decode_tile(P, tile);
     const int n_base = tc.nt * P.bn;
@@ -428,7 +430,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
         if (two) ldg_v8(q + P.res_chunk, *reinterpret_cast<float(*)[8]>(&rr[8]));
       }
       if (ACCUM) {
-        const float* q = outp + out_b + (long long)t * out_rs + (long long)(n0 >> 3) * P.out_chunk;
+        const float* q = accp + out_b + (long long)t * out_rs + (long long)(n0 >> 3) * P.out_chunk;
         ldg_v8(q, *reinterpret_cast<float(*)[8]>(&pp[0]));
         if (two) ldg_v8(q + P.out_chunk, *reinterpret_cast<float(*)[8]>(&pp[8]));
       }
@@ -642,7 +644,9 @@ __device__ __forceinline__ void epilogue_dispatch(const TcParams& P, uint32_t tm
                                                   int lg, int hf, int lane, int tile_rows, uint32_t acc_cols,
                                                   const float* s_bias) {
   if (P.fast_epi) {
-    if (P.out_is_16)
+    if (P.out_is_16 && P.accumulate)  // last AMP branch of a stage: mean of the branches written as the next stage's operand
+      epilogue_fast<true, true, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+    else if (P.out_is_16)
       epilogue_fast<false, false, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
     else if (P.res != nullptr && P.accumulate)
       epilogue_fast<true, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
@@ -1149,7 +1153,8 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
              "fh_tc_conv: P=%d ntaps=%d unsupported", a->P, a->ntaps);
   FH_REQUIRE(!(a->geglu && (a->res || a->accumulate || (a->Cout % 16))), FH_ERR_UNSUPPORTED_CFG,
              "fh_tc_conv: geglu epilogue excludes residual/accumulate and needs Cout %% 16 == 0");
-  FH_REQUIRE(!(a->accumulate && a->out_is_16), FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: accumulate needs fp32 out");
+  FH_REQUIRE(!(a->accumulate && a->out_is_16) || (a->acc_src && a->res && !a->res_is_16), FH_ERR_UNSUPPORTED_CFG,
+             "fh_tc_conv: accumulate into a 16-bit output needs acc_src (fp32) and an fp32 residual");
   FH_REQUIRE(((uintptr_t)a->a % 16) == 0 && ((uintptr_t)a->w % 16) == 0 && ((uintptr_t)a->out % 16) == 0 &&
                  ((uintptr_t)a->res % 16) == 0,
              FH_ERR_BAD_ALIGN, "fh_tc_conv: pointers must be 16-byte aligned");
@@ -1170,6 +1175,7 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   p.res_batch = a->res_batch, p.res_chunk = a->res_chunk, p.res_row = a->res_row;
   p.out_is_16 = a->out_is_16, p.res_is_16 = a->res_is_16, p.fp16 = a->fp16;
   p.accumulate = a->accumulate, p.geglu = a->geglu;
+  p.acc_src = a->accumulate ? a->acc_src : nullptr;
   p.act_gelu = a->act == 1;
   FH_REQUIRE(a->act == 0 || (a->act == 1 && !a->geglu), FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: act must be 0 (none) or 1 (GELU, not with geglu)");
   p.alpha = a->alpha, p.beta_res = a->beta_res;
@@ -1237,7 +1243,9 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
                                          a->out_row % 8 == 0);
     const bool res_ok = a->res == nullptr || a->res_is_16 ||
                         (((uintptr_t)a->res % 32) == 0 && a->res_batch % 8 == 0 && a->res_chunk % 8 == 0 && a->res_row % 8 == 0);
-    p.v8 = (use_v8 && out_ok && res_ok) ? 1 : 0;
+    const bool acc_ok = !(a->accumulate && a->acc_src) ||
+                        (((uintptr_t)a->acc_src % 32) == 0 && a->out_batch % 8 == 0 && a->out_chunk % 8 == 0 && a->out_row % 8 == 0);
+    p.v8 = (use_v8 && out_ok && res_ok && acc_ok) ? 1 : 0;
   }
   p.wrows = 128 * msub + span;
   p.arows_pad = 128 * msub + kMaxSpan;
@@ -1331,7 +1339,9 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   }
   const int bias_tab = a->bias ? ((p.n_tiles * a->bn + 15) & ~15) * 4 : 64;
   p.fast_epi = (fast_on && p.v8 && !a->geglu && !p.act_gelu && !(a->res && a->res_is_16) && bias_tab <= 8192 &&
-                (!a->out_is_16 || (a->res == nullptr && !a->accumulate))) ? 1 : 0;
+                (!a->out_is_16 || (a->res == nullptr && !a->accumulate) || (a->accumulate && a->acc_src && a->res))) ? 1 : 0;
+  FH_REQUIRE(p.fast_epi || !(a->accumulate && a->out_is_16), FH_ERR_UNSUPPORTED_CFG,
+             "fh_tc_conv: accumulate into a 16-bit output is only implemented by the specialised epilogue");
   const int tail = p.fast_epi ? bias_tab : 0;
   int stages = (budget - 1024 - tail) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;

@@ -16,6 +16,8 @@ Two numeric modes:
 from __future__ import annotations
 
 import contextlib
+from os import environ as _environ
+_os_environ_get = _environ.get
 import ctypes as C
 import math
 from typing import Dict, Optional
@@ -349,7 +351,8 @@ class Engine:
         return out
 
     def _tc_conv(self, rec: _TcWeight, a, a_batch, a_chunk, a_row0, out, out_strides, out_bf16, B, L, res=None,
-                 res_strides=(0, 0, 0), res_bf16=0, alpha=1.0, beta=0.0, accumulate=0, geglu=0, xf=None, snake=None, act=0):
+                 res_strides=(0, 0, 0), res_bf16=0, alpha=1.0, beta=0.0, accumulate=0, geglu=0, xf=None, snake=None, act=0,
+                 acc_src=None):
         args = _lib.TcConvArgs()
         args.a, args.a_batch, args.a_chunk, args.a_row0 = _ptr(a), a_batch, a_chunk, a_row0
         if xf is not None:  # fused anti-aliased snake prologue: A = Activation1d(xf), computed in the kernel
@@ -362,11 +365,12 @@ class Engine:
         args.out_is_16, args.res_is_16, args.fp16 = int(out_bf16), int(res_bf16), self.fp16
         args.alpha, args.beta_res, args.accumulate, args.geglu = alpha, beta, int(accumulate), int(geglu)
         args.act = int(act)
+        args.acc_src = _ptr(acc_src)
         args.B, args.L, args.Cin, args.Cout = B, L, rec.cin_pad, rec.cout_pad
         args.ntaps, args.P, args.tap_off, args.bn = rec.ntaps, rec.P, rec.off_c, rec.bn
         flops = 2.0 * B * L * rec.P * rec.ntaps * rec.cin * rec.cout
         esz_o = 2 if out_bf16 else 4
-        nbytes = B * L * rec.cin * (4 if xf is not None else 2) + B * L * rec.P * rec.cout * esz_o * (2 if accumulate else 1)
+        nbytes = B * L * rec.cin * (4 if xf is not None else 2) + B * L * rec.P * rec.cout * (esz_o + ((4 if acc_src is not None else esz_o) if accumulate else 0))
         if res is not None:
             nbytes += B * L * rec.P * rec.cout * (2 if res_bf16 else 4)
         work = {"flops": flops, "bytes": float(nbytes),
@@ -814,6 +818,12 @@ class Engine:
                 ev_up = torch.cuda.Event()
                 ev_up.record(main)
             outs = []
+            # sequential branches: the last one adds the running mean (XS, fp32) and writes the stage output directly as
+            # the 16-bit operand of the next upsampler -- no fp32 store of the mean, no separate cast pass
+            fuse_cast = (not par and nk > 1 and s + 1 < v.num_stages and self._tape is None and not fuse
+                         and _os_environ_get("FH_FUSE_CAST", "1") != "0")
+            if fuse_cast:
+                XBf, _, _ = self_cbuf(f"vt_XB{s}", B, ch, Lo, bf)
             for j, dil in enumerate(v.resblock_dilation_sizes):
                 bt = f"_{j}" if par else ""  # parallel branches need their own scratch
                 XJ, _, _ = self_cbuf(f"vt_XJ{s}{bt}", B, ch, Lo, f32)
@@ -854,7 +864,10 @@ class Engine:
                         else:
                             conv = V[f"r{s}.{j}.c1.{i}"]
                         src = None if fuse else A
-                        if last:
+                        if last and fuse_cast and j == nk - 1:
+                            self._tc_conv(conv, src, bs, cs, HALO, XBf[o:], strides, 1, B, L, res=cur[o:], res_strides=strides,
+                                          alpha=1.0 / nk, beta=1.0 / nk, accumulate=True, acc_src=XSj[o:], **fa)
+                        elif last:
                             self._tc_conv(conv, src, bs, cs, HALO, XSj[o:], strides, 0, B, L, res=cur[o:], res_strides=strides,
                                           alpha=1.0 / nk, beta=1.0 / nk, accumulate=(j > 0 and not par), **fa)
                         else:
@@ -875,7 +888,7 @@ class Engine:
                 XB, _, _ = self_cbuf(f"vt_XB{s}", B, ch, L, bf)
                 if par:
                     self._call("fh_sum_cast_f32", *ptrs, None, XB.data_ptr(), B * bs, self.fp16, st)
-                else:
+                elif not fuse_cast:
                     self._call("fh_cast_f32_16", XS.data_ptr(), XB.data_ptr(), B * bs, self.fp16, st)
                 a_in, a_cs, a_bs = XB, cs, bs
             elif par:

@@ -212,6 +212,9 @@ typedef struct {
   const float* sn_inv_b;  /* [Cin] 1 / (beta + 1e-9) */
   const float* sn_filt;   /* [12] Kaiser-sinc taps */
   int act;                /* 0 none, 1 exact-erf GELU on (acc + bias) * alpha, before the residual (convnext.py:56-57) */
+  const float* acc_src;   /* accumulate != 0: rows to add, fp32 with the output geometry; NULL = the output itself.
+                           * Lets the last AMP branch of a stage (bigvgan/models.py:181-187, xs / num_kernels) write the
+                           * mean directly as the 16-bit operand of the next upsampler (out_is_16 = 1). */
 } fh_tc_conv_args;
 int fh_tc_conv(const fh_tc_conv_args* args, void* stream);
 /* One launch = fh_tc_conv(args) for one half-batch + fh_snake_aa_chunked(sx -> sy, 16-bit out) for an independent
