@@ -99,20 +99,6 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------- CPU arm
-def cpu_reference_step(sample_seconds, vcfg, sd, seed):
-    """One pass of the ORACLE (CPU restatement of the reference, fp32) over a bounded sample."""
-    import torch
-    from flowhigh_b200.synth import synth_speech
-    from oracle import pipeline
-    wav = synth_speech(int(sample_seconds * SR_IN), SR_IN, seed)
-    N = int(sample_seconds * 48000) // 480
-    eps = torch.from_numpy(np.random.default_rng(seed).standard_normal((1, N, 256)).astype(np.float32))
-    o = pipeline.OracleFlowHigh(sd, vcfg, cfm_method="basic_cfm", ode_method="midpoint")
-    t0 = time.perf_counter()
-    o.generate(wav, SR_IN, eps, timestep=STEPS_ODE)
-    return time.perf_counter() - t0
-
-
 def cpu_weights():
     from flowhigh_b200.config import BackboneConfig, VocoderConfig
     from flowhigh_b200.weights import random_state_dict
@@ -120,32 +106,95 @@ def cpu_weights():
     return vcfg, random_state_dict(BackboneConfig(), vcfg, seed=0, vocoder_gain=0.7)
 
 
+class CpuReference:
+    """The reference's CPU implementation of the path, one clip per step (its generate() is batch-1).
+    kind "reference": the UNMODIFIED reference package (baseline/_ref, or /root/reference in the build container),
+    imported through oracle/ref_harness.py (stubs for the four packages missing offline, `.cuda()` neutralised --
+    the caller hides the GPU); kind "port": the oracle restatement, only when no reference tree is present."""
+
+    def __init__(self):
+        import torch
+        from oracle import ref_harness
+        self.vcfg, self.sd = cpu_weights()
+        self.kind = "reference" if ref_harness.available() and not torch.cuda.is_available() else "port"
+        if self.kind == "reference":
+            self.model = ref_harness.build_reference_model(self.sd, self.vcfg, cfm_method="basic_cfm",
+                                                           ode_method="midpoint", sigma=0.0)
+        else:
+            from oracle import pipeline
+            self.model = pipeline.OracleFlowHigh(self.sd, self.vcfg, cfm_method="basic_cfm", ode_method="midpoint")
+
+    def step(self, sample_seconds, seed):
+        import torch
+        from flowhigh_b200.synth import synth_speech
+        wav = synth_speech(int(sample_seconds * SR_IN), SR_IN, seed)
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            with torch.no_grad():
+                out = self.model.generate(wav, SR_IN, 48000, timestep=STEPS_ODE)
+        else:
+            N = int(sample_seconds * 48000) // 480
+            eps = torch.from_numpy(np.random.default_rng(seed).standard_normal((1, N, 256)).astype(np.float32))
+            out = self.model.generate(wav, SR_IN, eps, timestep=STEPS_ODE)
+        dt = time.perf_counter() - t0
+        assert out.shape[-1] == int(sample_seconds * 48000) and bool(torch.isfinite(out).all())
+        return dt
+
+
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
-    pure Python and cannot travel to the GPU box), all host threads, bounded sample per step."""
+    """--impl reference: the reference's own CPU implementation on the box's host cores, all threads, one 10 s clip of
+    the configs[1] workload per step.  The run is bounded to a few minutes: when K + W steps of
+    the measured step time would not fit, fewer steps are executed and the line says so."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""  # the reference hard-codes .cuda() (SURVEY F7): this arm is its CPU path
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    vcfg, sd = cpu_weights()
-    sample = 1.0
-    for i in range(args.warmup):
-        cpu_reference_step(sample, vcfg, sd, i)
-    t = [cpu_reference_step(sample, vcfg, sd, 100 + i) for i in range(args.steps)]
+    ref = CpuReference()
+    sample = float(args.ref_clip_seconds)
+    budget = float(args.ref_budget_seconds)
+    t_first = ref.step(sample, 0)  # warm-up 1 (also sizes the run)
+    n_warm = 1
+    steps = args.steps
+    if t_first * (args.steps + args.warmup) > budget:
+        steps = max(3, min(args.steps, int(budget / t_first) - 1))
+    else:
+        for i in range(1, args.warmup):
+            ref.step(sample, i)
+            n_warm += 1
+    t = [ref.step(sample, 100 + i) for i in range(steps)]
     total = sum(t)
-    value = sample * args.steps / total
+    value = sample * steps / total
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1000 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": n_warm, "requested": {"steps": args.steps, "warmup": args.warmup},
+        "ms_per_step": 1000 * total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args.gpus, BATCH),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"1 clip x {sample:g} s per step (same model/config; the reference generate() is batch-1)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": ref.kind,
+                         "sample": f"1 clip x {sample:g} s per step ({'unmodified reference package, generate()' if ref.kind == 'reference' else 'oracle port'}; "
+                                   f"the reference generate() is batch-1), median step {1000 * statistics.median(t):.0f} ms"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(clip_seconds=10.0, steps=2, timeout=600):
+    """cpu_baseline leg of the GPU arm: the reference arm in a child process with the GPU hidden (the reference would
+    otherwise run on CUDA), bounded to ~10-30 s of CPU work."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", "1",
+           "--ref-clip-seconds", str(clip_seconds), "--ref-budget-seconds", "60"]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+        for ln in reversed(r.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)["cpu_baseline"]
+        return {"error": (r.stderr or r.stdout)[-300:]}
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)}
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
@@ -159,7 +208,10 @@ def main():
     ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
                     help="16-bit tensor-core operand format (same rate and bytes; fp16 meets the LSD bar, see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-clip-seconds", type=float, default=CLIP_SECONDS, help="reference arm: clip length per step")
+    ap.add_argument("--ref-budget-seconds", type=float, default=240.0, help="reference arm: bound on the whole run")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--latency-samples", type=int, default=200)
     ap.add_argument("--breakdown", default=None, help="write the per-kernel CUDA-event breakdown to this JSON file")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -204,11 +256,15 @@ def main():
     eps = torch.randn((B, N, 256), device=dev, generator=torch.Generator(dev).manual_seed(1234 + rank))
 
     def step_resident():
+        eng.new_call()
+        eng.status_begin()  # overflow / NaN guard of the 16-bit path: reset here, read once after the timed loop
         cond = eng.resample_normalise(x_dev, SR_IN)
         cond_mel = eng.encode(cond)
         mel = eng.sample_mel(cond_mel, eps, steps=STEPS_ODE, ode_method="midpoint", cfm_method="basic_cfm", sigma=0.0)
         wave = eng.vocoder(mel)
-        return eng.postprocess(wave, cond)
+        out = eng.postprocess(wave, cond)
+        eng.status_end()
+        return out
 
     out_host = torch.empty((B, T), dtype=torch.float32).pin_memory()
 
@@ -241,6 +297,25 @@ def main():
     launches = _lib.launch_count() - n0
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- the timed output is checked, not just produced: finite, guard clean, and clip 0 of the batch against its own
+    #      B = 1 run through the public API (different tile shapes, parallel AMP branches, CUDA-graph-free)
+    status = eng.status_read()
+    finite = bool(torch.isfinite(out).all())
+    if not finite or status:
+        raise RuntimeError(f"bench: the timed step produced a non-finite output (finite={finite}) or tripped the 16-bit "
+                           f"overflow guard (status {status:#x})")
+    self_check = None
+    if rank == 0:
+        model.cuda_graphs = False
+        single = model.generate(host[0], SR_IN, 48000, timestep=STEPS_ODE, eps=eps[0:1])[0].double()
+        model.cuda_graphs = True
+        b0 = out[0].double()
+        snr = float(10 * torch.log10((single ** 2).sum() / ((single - b0) ** 2).sum().clamp_min(1e-300)))
+        self_check = {"finite": finite, "overflow_status": status, "clip0_snr_vs_b1_generate_db": round(snr, 1),
+                      "out_absmax": float(out.abs().max())}
+        if snr < 50.0:
+            raise RuntimeError(f"bench: clip 0 of the timed batch differs from its own B=1 generate(): SNR {snr:.1f} dB")
+
     # ---- e2e through the public API with host buffers
     step_e2e()
     barrier()
@@ -267,22 +342,29 @@ def main():
                 fn()
                 torch.cuda.synchronize(dev)
                 ts.append(1000 * (time.perf_counter() - t0))
+            raw = list(ts)
             ts.sort()
-            return ts[len(ts) // 2], ts[min(len(ts) - 1, int(0.99 * len(ts)))]
+            p50 = ts[len(ts) // 2]
+            slow = [i for i, v in enumerate(raw) if v > 2 * p50]
+            return p50, ts[min(len(ts) - 1, int(0.99 * len(ts)))], {"n": n, "max_ms": ts[-1], "p90_ms": ts[int(0.9 * n)],
+                                                                    "samples_over_2x_p50": len(slow), "their_index": slow[:8]}
+        NL = args.latency_samples
         clip = host[0]
-        for _ in range(3):
+        for _ in range(5):
             model.generate(clip, SR_IN, 48000, timestep=STEPS_ODE)
-        l50, l99 = p50_p99(lambda: model.generate(clip, SR_IN, 48000, timestep=STEPS_ODE), 30)
+        l50, l99, ltail = p50_p99(lambda: model.generate(clip, SR_IN, 48000, timestep=STEPS_ODE), NL)
         # config 5: basic_cfm, euler, time_step 4, 1 s chunks at 16 kHz
         m5 = FlowHighSR.from_random(VocoderConfig.assumed_48k(), device=dev, seed=0, precision=args.precision,
                                     torchdiffeq_ode_method="euler")
         chunk = synth_speech(16000, 16000, seed=7)
-        for _ in range(3):
+        for _ in range(5):
             m5.generate(chunk, 16000, 48000, timestep=4)
-        c50, c99 = p50_p99(lambda: m5.generate(chunk, 16000, 48000, timestep=4), 50)
+        c50, c99, ctail = p50_p99(lambda: m5.generate(chunk, 16000, 48000, timestep=4), NL)
         latency = {"clip_10s_midpoint_p50_ms": l50, "clip_10s_midpoint_p99_ms": l99,
                    "chunk_1s_euler4_p50_ms": c50, "chunk_1s_euler4_p99_ms": c99,
-                   "note": "B=1, host numpy in -> device tensor out, stream-synchronised, CUDA-graph replay of the whole pipeline"}
+                   "samples": NL, "clip_10s_tail": ltail, "chunk_1s_tail": ctail,
+                   "note": "B=1, host numpy in -> device tensor out, stream-synchronised (overflow-guard read included), "
+                           "CUDA-graph replay of the whole pipeline"}
         del m5
 
     # ---- roofline leg: per-kernel CUDA-event timing of one more step (rank 0)
@@ -342,14 +424,7 @@ def main():
                       indent=1)
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            vcfg, sd = cpu_weights()
-            cores = os.cpu_count() or 1
-            torch.set_num_threads(cores)
-            sample = 1.0
-            cpu_reference_step(sample, vcfg, sd, 0)  # warm-up
-            dt = cpu_reference_step(sample, vcfg, sd, 1)
-            cpu = {"value": sample / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": f"1 clip x {sample:g} s, oracle port of the reference (fp32 torch-CPU), 1 warm-up + 1 timed pass"}
+            cpu = cpu_baseline_subprocess()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -358,7 +433,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_t.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_snake": roofline_snake, "cpu_baseline": cpu,
-            "latency": latency,
+            "latency": latency, "self_check": self_check,
             "stage_ms": {k: round(v["ms"], 3) for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])},
         }
         print(json.dumps(line), flush=True)

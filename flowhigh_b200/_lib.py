@@ -41,6 +41,7 @@ SIGNATURES = {
     "fh_version": (_i, []),
     "fh_last_error_string": (C.c_char_p, []),
     "fh_launch_count": (_i64, []),
+    "fh_set_status_word": (_i, [_p]),
     "fh_resample_poly_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "fh_scale_by_absmax_f32": (_i, [_p, _p, _p, _f, _i, _i, _p]),
     "fh_absmax_f32": (_i, [_p, _p, _i, _i, _p]),

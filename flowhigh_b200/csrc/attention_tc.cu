@@ -46,7 +46,8 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const unsigned short*
                                                            const unsigned short* __restrict__ kh,
                                                            const unsigned short* __restrict__ kl,
                                                            const unsigned short* __restrict__ v16, void* __restrict__ out,
-                                                           int out_mode, long long out_rows, int H, int N) {
+                                                           int out_mode, long long out_rows, int H, int N,
+                                                           unsigned int* status) {
   // two stages of (Kh, Kl, V) key blocks: the next block streams in with cp.async while this one is multiplied
   extern __shared__ __align__(16) unsigned short att_smem[];
   typedef unsigned short (*Tile)[APAD];
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(128) attention_tc_kernel(const unsigned short*
         *reinterpret_cast<float2*>((float*)out + row * (H * AD) + c) = make_float2(x0, x1);
       else
         *reinterpret_cast<uint32_t*>((unsigned short*)out + fh::chunked_index(out_rows * 8, row, c)) =
-            fh::pack16(x0, x1, out_mode == 2);
+            fh::pack16_guard(x0, x1, out_mode == 2, status);
     }
   }
 }
@@ -210,7 +211,8 @@ __global__ void qknorm_rope_split_kernel(const float* __restrict__ qkv, const fl
                                          const float* __restrict__ kg, const float* __restrict__ inv_freq,
                                          unsigned short* __restrict__ qh, unsigned short* __restrict__ ql,
                                          unsigned short* __restrict__ kh, unsigned short* __restrict__ kl,
-                                         unsigned short* __restrict__ v16, int B, int N, int H, float scale, int fp16) {
+                                         unsigned short* __restrict__ v16, int B, int N, int H, float scale, int fp16,
+                                         unsigned int* status) {
   constexpr int D = 64;
   const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -233,7 +235,7 @@ __global__ void qknorm_rope_split_kernel(const float* __restrict__ qkv, const fl
     if (which == 0) y1 *= scale, y2 *= scale;
     unsigned short* oh = (which == 0 ? qh : kh) + dst;
     unsigned short* ol = (which == 0 ? ql : kl) + dst;
-    const unsigned short h1 = fh::cvt16(y1, fp16), h2 = fh::cvt16(y2, fp16);
+    const unsigned short h1 = fh::cvt16_guard(y1, fp16, status), h2 = fh::cvt16_guard(y2, fp16, status);
     const float f1 = fp16 ? __half2float(*reinterpret_cast<const __half*>(&h1)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h1));
     const float f2 = fp16 ? __half2float(*reinterpret_cast<const __half*>(&h2)) : __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(&h2));
     oh[lane] = h1;
@@ -242,8 +244,8 @@ __global__ void qknorm_rope_split_kernel(const float* __restrict__ qkv, const fl
     ol[lane + 32] = fh::cvt16(y2 - f2, fp16);
   }
   const float* s = src + 2 * H * D;
-  v16[dst + lane] = fh::cvt16(s[lane], fp16);
-  v16[dst + lane + 32] = fh::cvt16(s[lane + 32], fp16);
+  v16[dst + lane] = fh::cvt16_guard(s[lane], fp16, status);
+  v16[dst + lane + 32] = fh::cvt16_guard(s[lane + 32], fp16, status);
 }
 
 }  // namespace
@@ -255,7 +257,7 @@ extern "C" __attribute__((visibility("default"))) int fh_qknorm_rope_split(
   const int64_t warps = (int64_t)B * N * H;
   qknorm_rope_split_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
       qkv, qg, kg, inv_freq, (unsigned short*)qh, (unsigned short*)ql, (unsigned short*)kh, (unsigned short*)kl,
-      (unsigned short*)v16, B, N, H, scale, fp16);
+      (unsigned short*)v16, B, N, H, scale, fp16, fh::status_word());
   return fh::check_launch("fh_qknorm_rope_split");
 }
 
@@ -267,19 +269,16 @@ extern "C" __attribute__((visibility("default"))) int fh_attention_tc(const void
   FH_REQUIRE(B * H <= 65535 && N > 0, FH_ERR_BAD_SHAPE, "fh_attention_tc: B*H must be <= 65535");
   dim3 grid((N + ABQ - 1) / ABQ, B * H);
   constexpr int kSmem = 2 * 3 * ABK * APAD * (int)sizeof(unsigned short);  // 55 296 B: two stages of Kh, Kl, V
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(attention_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    cudaFuncSetAttribute(attention_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    attr_set = true;
-  }
+  static int set_t[64] = {0}, set_f[64] = {0};
+  fh::ensure_dyn_smem(attention_tc_kernel<true>, kSmem, set_t);
+  fh::ensure_dyn_smem(attention_tc_kernel<false>, kSmem, set_f);
   if (fp16)
     attention_tc_kernel<true><<<grid, 128, kSmem, (cudaStream_t)stream>>>(
         (const unsigned short*)qh, (const unsigned short*)ql, (const unsigned short*)kh, (const unsigned short*)kl,
-        (const unsigned short*)v16, out, out_mode, out_rows, H, N);
+        (const unsigned short*)v16, out, out_mode, out_rows, H, N, fh::status_word());
   else
     attention_tc_kernel<false><<<grid, 128, kSmem, (cudaStream_t)stream>>>(
         (const unsigned short*)qh, (const unsigned short*)ql, (const unsigned short*)kh, (const unsigned short*)kl,
-        (const unsigned short*)v16, out, out_mode, out_rows, H, N);
+        (const unsigned short*)v16, out, out_mode, out_rows, H, N, fh::status_word());
   return fh::check_launch("fh_attention_tc");
 }

@@ -144,7 +144,8 @@ __global__ void dwconv_gelu_res_generic_kernel(const float* __restrict__ E, cons
 // same kernel with w = scale(t), b = shift(t).  One warp per row, the row lives in registers (C <= 1024);
 // out_mode 0 -> fp32 row-major, 1 / 2 -> bf16 / fp16 chunked [C/8][rows][8].
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                                 void* __restrict__ out, int out_mode, int64_t out_rows, int M, int C, float eps) {
+                                 void* __restrict__ out, int out_mode, int64_t out_rows, int M, int C, float eps,
+                                 unsigned int* status) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -173,25 +174,26 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     float y = (v[i] - mean) * inv * w[c];
     if (b) y += b[c];
     if (out_mode == 0) ((float*)out)[(size_t)row * C + c] = y;
-    else ((unsigned short*)out)[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16(y, out_mode == 2);
+    else ((unsigned short*)out)[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16_guard(y, out_mode == 2, status);
   }
 }
 
 // exact-erf GELU, fp32 row-major in -> fp32 row-major (out_mode 0) or 16-bit chunked (nn.GELU, convnext.py:36)
-__global__ void gelu_kernel(const float* __restrict__ x, void* __restrict__ out, int out_mode, int64_t out_rows, int M, int C) {
+__global__ void gelu_kernel(const float* __restrict__ x, void* __restrict__ out, int out_mode, int64_t out_rows, int M, int C,
+                            unsigned int* status) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)M * C) return;
   const int row = (int)(i / C), c = (int)(i % C);
   const float y = fh::gelu_erf(x[i]);
   if (out_mode == 0) ((float*)out)[i] = y;
-  else ((unsigned short*)out)[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16(y, out_mode == 2);
+  else ((unsigned short*)out)[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16_guard(y, out_mode == 2, status);
 }
 
 // ------------------------------------------------------------------------------ (adaptive) RMS norm
 // one warp per row; out_mode 0 -> fp32 row-major, 1 -> bf16 chunked [C/8][rows][8]
 __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                const float* __restrict__ beta, void* __restrict__ out, int out_mode, int64_t out_rows,
-                               int M, int C) {
+                               int M, int C, unsigned int* status) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -215,7 +217,7 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
     for (int c = lane; c < C; c += 32) {
       float v = xr[c] * inv * gamma[c];
       if (beta) v += beta[c];
-      o[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16(v, out_mode == 2);
+      o[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16_guard(v, out_mode == 2, status);
     }
   }
 }
@@ -258,7 +260,8 @@ __global__ void qknorm_rope_kernel(const float* __restrict__ qkv, const float* _
 // online softmax.  256 threads: thread (ty, tx) owns S/O rows 4*ty..+3, cols 4*tx..+3.
 __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restrict__ Q, const float* __restrict__ Kt,
                                                             const float* __restrict__ V, void* __restrict__ out,
-                                                            int out_mode, int64_t out_rows, int H, int N, float scale) {
+                                                            int out_mode, int64_t out_rows, int H, int N, float scale,
+                                                            unsigned int* status) {
   constexpr int D = 64, BQ = 64, BK = 64;
   extern __shared__ __align__(16) float att_smem[];
   float (*Qs)[BQ + 1] = reinterpret_cast<float (*)[BQ + 1]>(att_smem);                      // [d][q]
@@ -355,14 +358,14 @@ __global__ void __launch_bounds__(256) attention_f32_kernel(const float* __restr
       if (out_mode == 0)
         ((float*)out)[row * (H * D) + c] = val;
       else
-        ((unsigned short*)out)[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16(val, out_mode == 2);
+        ((unsigned short*)out)[fh::chunked_index(out_rows * 8, row, c)] = fh::cvt16_guard(val, out_mode == 2, status);
     }
   }
 }
 
 // ------------------------------------------------------------------------------ GEGLU / axpby
 __global__ void geglu_kernel(const float* __restrict__ u, void* __restrict__ g, int out_mode, int64_t out_rows, int M,
-                             int inner, int inner_pad) {
+                             int inner, int inner_pad, unsigned int* status) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (i >= inner_pad) return;
@@ -374,7 +377,7 @@ __global__ void geglu_kernel(const float* __restrict__ u, void* __restrict__ g, 
   if (out_mode == 0) {
     if (i < inner) ((float*)g)[(size_t)m * inner + i] = v;
   } else {
-    ((unsigned short*)g)[fh::chunked_index(out_rows * 8, m, i)] = fh::cvt16(v, out_mode == 2);
+    ((unsigned short*)g)[fh::chunked_index(out_rows * 8, m, i)] = fh::cvt16_guard(v, out_mode == 2, status);
   }
 }
 
@@ -481,7 +484,8 @@ extern "C" __attribute__((visibility("default"))) int fh_layernorm_f32(const flo
                                 int64_t out_rows, int M, int C, float eps, void* stream) {
   FH_REQUIRE(M > 0 && C > 0 && C <= 1024 && w != nullptr && (out_mode == 0 || (C % 8 == 0 && out_rows >= M)), FH_ERR_BAD_SHAPE,
              "fh_layernorm_f32: bad shape (C <= 1024)");
-  layernorm_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, w, b, out, out_mode, out_rows, M, C, eps);
+  layernorm_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, w, b, out, out_mode, out_rows, M, C, eps,
+                                                                  fh::status_word());
   return fh::check_launch("fh_layernorm_f32");
 }
 
@@ -489,7 +493,8 @@ extern "C" __attribute__((visibility("default"))) int fh_gelu_f32(const float* x
                            void* stream) {
   FH_REQUIRE(M > 0 && C > 0 && (out_mode == 0 || (C % 8 == 0 && out_rows >= M)), FH_ERR_BAD_SHAPE, "fh_gelu_f32: bad shape");
   const long long n = (long long)M * C;
-  gelu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, out_mode, out_rows, M, C);
+  gelu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, out, out_mode, out_rows, M, C,
+                                                                               fh::status_word());
   return fh::check_launch("fh_gelu_f32");
 }
 
@@ -497,7 +502,8 @@ extern "C" __attribute__((visibility("default"))) int fh_rmsnorm_f32(const float
                               int64_t out_rows, int M, int C, void* stream) {
   FH_REQUIRE(M > 0 && C > 0 && (out_mode == 0 || (C % 8 == 0 && out_rows >= M)), FH_ERR_BAD_SHAPE,
              "fh_rmsnorm_f32: bad shape");
-  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, out, out_mode, out_rows, M, C);
+  rmsnorm_kernel<<<(M + 7) / 8, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, out, out_mode, out_rows, M, C,
+                                                                fh::status_word());
   return fh::check_launch("fh_rmsnorm_f32");
 }
 
@@ -515,13 +521,10 @@ extern "C" __attribute__((visibility("default"))) int fh_attention_f32(const flo
   FH_REQUIRE(D == 64, FH_ERR_UNSUPPORTED_CFG, "fh_attention_f32: dim_head must be 64 (got %d)", D);
   FH_REQUIRE(B * H <= 65535, FH_ERR_BAD_SHAPE, "fh_attention_f32: B*H must be <= 65535");
   constexpr int kAttSmem = (3 * 64 * 65 + 64 * 68) * (int)sizeof(float);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(attention_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttSmem);
-    attr_set = true;
-  }
+  static int smem_set[64] = {0};
+  fh::ensure_dyn_smem(attention_f32_kernel, kAttSmem, smem_set);
   attention_f32_kernel<<<dim3((N + 63) / 64, B * H), 256, kAttSmem, (cudaStream_t)stream>>>(q, k, v, out, out_mode, out_rows, H,
-                                                                                   N, scale);
+                                                                                   N, scale, fh::status_word());
   return fh::check_launch("fh_attention_f32");
 }
 
@@ -540,14 +543,15 @@ extern "C" __attribute__((visibility("default"))) int fh_geglu_f32(const float* 
       void* gg = out_mode == 0 ? (void*)((float*)g + (size_t)done * inner)
                                : (void*)((__nv_bfloat16*)g + (size_t)done * 8);
       geglu_kernel<<<dim3(grid.x, cnt), 256, 0, (cudaStream_t)stream>>>(uu, gg, out_mode, out_rows, cnt, inner,
-                                                                        inner_pad);
+                                                                        inner_pad, fh::status_word());
       int rc = fh::check_launch("fh_geglu_f32");
       if (rc) return rc;
       done += cnt;
     }
     return FH_OK;
   }
-  geglu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(u, g, out_mode, out_rows, M, inner, inner_pad);
+  geglu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(u, g, out_mode, out_rows, M, inner, inner_pad,
+                                                       fh::status_word());
   return fh::check_launch("fh_geglu_f32");
 }
 

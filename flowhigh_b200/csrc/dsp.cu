@@ -16,11 +16,17 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+static thread_local unsigned int* g_status = nullptr;
+unsigned int* status_word() { return g_status; }
 }  // namespace fh
 
 extern "C" __attribute__((visibility("default"))) int fh_version(void) { return 1; }
 extern "C" __attribute__((visibility("default"))) const char* fh_last_error_string(void) { return fh::g_err; }
 extern "C" __attribute__((visibility("default"))) int64_t fh_launch_count(void) { return (int64_t)fh::g_launches.load(); }
+extern "C" __attribute__((visibility("default"))) int fh_set_status_word(uint32_t* status) {
+  fh::g_status = status;
+  return FH_OK;
+}
 
 namespace {
 
@@ -527,11 +533,8 @@ extern "C" __attribute__((visibility("default"))) int fh_stft_logmel_f32(const f
   dim3 grid(N, B);
   if (precise) {
     const int smem = 2 * kFftBuf * sizeof(double) * 2;
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(stft_logmel_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-      attr_set = true;
-    }
+    static int smem_set[64] = {0};
+    fh::ensure_dyn_smem(stft_logmel_kernel<double>, smem, smem_set);
     stft_logmel_kernel<double><<<grid, 128, smem, (cudaStream_t)stream>>>(
         audio, mel, window, (const float2*)twiddle, mel_start, mel_len, mel_w, mel_stride, T, N);
   } else {

@@ -162,6 +162,9 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
     }
   }
 
+  // Overflow guard: the fp16 roundings of the input and of the snake samples do NOT saturate, so an out-of-range value
+  // becomes inf, turns the outputs it reaches into inf / NaN, and is caught where the outputs are packed (saturating).
+  Guard16 guard;
   int item = cta;
   if (tid == 0) {
     if (item < S.total) issue(item, 0);
@@ -291,7 +294,9 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
           // fragment per half, stored TRANSPOSED ([time][8 ch] rows of 16 bytes) by one stmatrix
           const int i = j - 1;
           const float (&yy)[4] = y[i % 3];
-          const uint32_t r0 = sm_pack(yy[0], yy[1]), r1 = sm_pack(yy[2], yy[3]);
+          const uint32_t r0 = pack16(yy[0], yy[1], 1), r1 = pack16(yy[2], yy[3], 1);
+          guard.see(r0, 1);
+          guard.see(r1, 1);
           asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(st_base + (uint32_t)(8 * i * 16)),
                        "r"(r0), "r"(r1)
                        : "memory");
@@ -353,6 +358,7 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
     buf ^= 1;
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  guard.commit(S.status, 1);
 }
 
 }  // namespace fh

@@ -33,6 +33,7 @@ struct SnakeParams {
   long long batch_stride, chunk_stride;
   int row0, nchunk, L, ntile, total;
   int fp16;  // 16-bit output format when OUT_KIND == 3 (chosen at run time): 0 bfloat16, 1 IEEE half
+  unsigned int* status;  // overflow / NaN status word of the caller (common.cuh Guard16) or nullptr
 };
 
 template <int R>
@@ -117,6 +118,7 @@ __device__ __forceinline__ void snake_worker(const SnakeParams& S, unsigned char
     fd[k] = make_float2(fk, fk);
   }
   const int e2 = tid & 3, g = tid >> 2;
+  Guard16 guard;
   int item = worker;
   if (item < S.total && tid == 0) issue(item, 0);
   int buf = 0;
@@ -195,11 +197,12 @@ __device__ __forceinline__ void snake_worker(const SnakeParams& S, unsigned char
           float2 acc = hib;
 #pragma unroll
           for (int k = 0; k < 12; ++k) acc = sw_ffma2(fd[k], s[2 * j + k], acc);
-          if (BULK_OUT)
-            *reinterpret_cast<uint32_t*>(ys + (size_t)(g * R + j) * 16 + 4 * e2) = pack16(acc.x, acc.y, out_fp16);
-          else if (OUT_KIND)
-            *reinterpret_cast<uint32_t*>((unsigned short*)S.y + obase + j * 8) = pack16(acc.x, acc.y, out_fp16);
-          else
+          if (OUT_KIND) {
+            const uint32_t hv = pack16(acc.x, acc.y, out_fp16);
+            guard.see(hv, out_fp16);
+            if (BULK_OUT) *reinterpret_cast<uint32_t*>(ys + (size_t)(g * R + j) * 16 + 4 * e2) = hv;
+            else *reinterpret_cast<uint32_t*>((unsigned short*)S.y + obase + j * 8) = hv;
+          } else
             *reinterpret_cast<float2*>((float*)S.y + obase + j * 8) = acc;
         }
       }
@@ -220,6 +223,7 @@ __device__ __forceinline__ void snake_worker(const SnakeParams& S, unsigned char
     buf ^= 1;
   }
   if (BULK_OUT && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (OUT_KIND) guard.commit(S.status, out_fp16);
 }
 
 }  // namespace fh

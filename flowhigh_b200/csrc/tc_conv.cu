@@ -61,6 +61,7 @@ struct TcParams {
   int tap_arith;        // all phases arithmetic: the MMA issuer strides descriptors instead of reading the offset table
   int tap_off[kMaxTapOff];
   unsigned int* err_flag;
+  unsigned int* status;  // overflow / NaN status word of the caller (common.cuh Guard16) or nullptr
   // fused anti-aliased snake A-producer (tc_conv_snake_kernel): raw fp32 activations + per-channel parameters
   const float* xf;
   const float* sn_a;
@@ -255,6 +256,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
   const int groups_per_sub = P.bn >> 4;
   const int n_groups_total = P.msub * groups_per_sub;
   const bool use_res = P.res != nullptr && !P.geglu;
+  fh::Guard16 guard;
   for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
     const TileCoord tc = decode_tile(P, tile);
     const int n_base = tc.nt * P.bn;
@@ -303,7 +305,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
         if (P.out_is_16) {
           uint32_t h[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
+          for (int i = 0; i < 4; ++i) {
+            h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
+            guard.see(h[i], P.fp16);
+          }
           *reinterpret_cast<uint4*>((unsigned short*)P.out + idx) = *reinterpret_cast<uint4*>(h);
         } else {
           float4* dst = reinterpret_cast<float4*>((float*)P.out + idx);
@@ -329,7 +334,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
         if (P.out_is_16) {
           uint32_t h[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
+          for (int i = 0; i < 4; ++i) {
+            h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
+            guard.see(h[i], P.fp16);
+          }
           *reinterpret_cast<uint4*>((unsigned short*)P.out + idx) = *reinterpret_cast<uint4*>(h);
         } else if (P.v8) {
           float* dst = (float*)P.out + idx;
@@ -380,6 +388,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
       aphase ^= 1;
     }
   }
+  if (P.out_is_16) guard.commit(P.status, P.fp16);
 }
 
 // Specialised epilogue for the hot vocoder / backbone shapes: fp32 output and residual in 32-byte-aligned rows, no GEGLU.
@@ -402,6 +411,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
   const float* resp = (const float*)P.res;
   float* outp = (float*)P.out;
   const float* accp = P.acc_src ? P.acc_src : (const float*)P.out;  // "previous output" rows of the accumulate form
+  fh::Guard16 guard;
   for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
     const TileCoord tc = decode_tile(P, tile);
     const int n_base = tc.nt * P.bn;
@@ -464,7 +474,10 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
         if (OUT16) {
           uint32_t h[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
+          for (int i = 0; i < 4; ++i) {
+            h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
+            guard.see(h[i], P.fp16);
+          }
           *reinterpret_cast<uint4*>((unsigned short*)P.out + oidx + (long long)hh * P.out_chunk) = *reinterpret_cast<uint4*>(h);
         } else {
           stg_v8(dst + (long long)hh * P.out_chunk, o);
@@ -498,6 +511,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
       aphase ^= 1;
     }
   }
+  if (OUT16) guard.commit(P.status, P.fp16);
 }
 
 // MMA issuer role, shared by both kernels.  The ncu source page of the first version showed this warp, not the tensor
@@ -1104,7 +1118,7 @@ __global__ void __launch_bounds__(kDualThreads, 1) tc_conv_snake_dual_kernel(con
 // ------------------------------------------------------------------------------ layout helpers
 __global__ void to_chunked_bf16_kernel(const float* __restrict__ src, long long src_batch, long long src_c,
                                        long long src_t, __nv_bfloat16* __restrict__ dst, long long dst_batch,
-                                       long long dst_chunk, int dst_row0, int C, int L, int fp16) {
+                                       long long dst_chunk, int dst_row0, int C, int L, int fp16, unsigned int* status) {
   // one thread per (t, chunk): gathers 8 channels, writes one 16-byte row
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nch = (C + 7) >> 3;
@@ -1125,7 +1139,7 @@ __global__ void to_chunked_bf16_kernel(const float* __restrict__ src, long long 
     const int c0 = ch * 8 + 2 * k;
     const float f0 = c0 < C ? s[(long long)c0 * src_c] : 0.f;
     const float f1 = c0 + 1 < C ? s[(long long)(c0 + 1) * src_c] : 0.f;
-    h[k] = fh::pack16(f0, f1, fp16);
+    h[k] = fh::pack16_guard(f0, f1, fp16, status);
   }
   *reinterpret_cast<uint4*>(dst + (long long)b * dst_batch + (long long)ch * dst_chunk + (long long)(dst_row0 + t) * 8) =
       *reinterpret_cast<uint4*>(h);
@@ -1179,6 +1193,7 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   p.act_gelu = a->act == 1;
   FH_REQUIRE(a->act == 0 || (a->act == 1 && !a->geglu), FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: act must be 0 (none) or 1 (GELU, not with geglu)");
   p.alpha = a->alpha, p.beta_res = a->beta_res;
+  p.status = fh::status_word();
   p.B = a->B, p.L = a->L, p.Cin = a->Cin, p.Cout = a->Cout, p.ntaps = a->ntaps, p.P = a->P, p.bn = a->bn;
   p.n_tiles = (a->Cout + a->bn - 1) / a->bn;
   const bool fused = a->x_f32 != nullptr;
@@ -1313,19 +1328,12 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
     p.stages = st > 4 ? 4 : st;
     p.err_flag = nullptr;
     const int fsmem = 2048 + sbuf + p.x_stages * p.xs_bytes + p.stages * p.stage_bytes;
-    static int fsmem_set = 0;
-    static int fsms = 0;
-    if (!fsms) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&fsms, cudaDevAttrMultiProcessorCount, dev);
-      if (fsms <= 0) fsms = 148;
-    }
-    if (fsmem > fsmem_set) {
-      cudaError_t e = cudaFuncSetAttribute(tc_conv_snake_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fsmem);
+    static int fsmem_set[64] = {0};
+    const int fsms = fh::dev_sms();
+    {
+      cudaError_t e = fh::ensure_dyn_smem(tc_conv_snake_kernel, fsmem, fsmem_set);
       FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", fsmem,
                  cudaGetErrorString(e));
-      fsmem_set = fsmem;
     }
     const int fgrid = p.total_tiles < fsms ? p.total_tiles : fsms;
     tc_conv_snake_kernel<<<fgrid, kFusedThreads, fsmem, (cudaStream_t)stream>>>(p);
@@ -1352,28 +1360,18 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   return FH_OK;
 }
 
-static int device_sms() {
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    if (num_sms <= 0) num_sms = 148;
-  }
-  return num_sms;
-}
+static int device_sms() { return fh::dev_sms(); }
 
 extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_conv_args* a, void* stream) {
   TcParams p;
   int smem = 0;
   const int rc = tc_plan(a, stream, 0, p, &smem);
   if (rc != FH_OK) return rc == 1 ? FH_OK : rc;  // 1: the fused-snake variant was launched by the planner
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static int smem_set[64] = {0};
+  {
+    cudaError_t e = fh::ensure_dyn_smem(tc_conv_kernel, smem, smem_set);
     FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", smem,
                cudaGetErrorString(e));
-    smem_set = smem;
   }
   const int num_sms = device_sms();
   const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
@@ -1407,13 +1405,13 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv_snake_dual(
   d.s.row0 = s_row0, d.s.nchunk = sC / 8, d.s.L = sL, d.s.ntile = ntile, d.s.total = (int)total;
   d.s_out_kind = s_out_kind;
   d.s.fp16 = s_out_kind == 2;
+  d.s.status = fh::status_word();
   const int smem = d.snake_off + kSnakeSmem;
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_conv_snake_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  static int smem_set[64] = {0};
+  {
+    cudaError_t e = fh::ensure_dyn_smem(tc_conv_snake_dual_kernel, smem, smem_set);
     FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv_snake_dual: cannot opt in to %d bytes of smem: %s", smem,
                cudaGetErrorString(e));
-    smem_set = smem;
   }
   tc_conv_snake_dual_kernel<<<device_sms(), kDualThreads, smem, (cudaStream_t)stream>>>(d);
   return fh::check_launch("fh_tc_conv_snake_dual");
@@ -1425,6 +1423,6 @@ extern "C" __attribute__((visibility("default"))) int fh_to_chunked_16(const flo
   FH_REQUIRE(B > 0 && C > 0 && L > 0 && B <= 65535, FH_ERR_BAD_SHAPE, "fh_to_chunked_16: bad shape");
   const long long n = (long long)((C + 7) / 8) * L;
   to_chunked_bf16_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(
-      src, src_batch, src_c, src_t, (__nv_bfloat16*)dst, dst_batch, dst_chunk, dst_row0, C, L, fp16);
+      src, src_batch, src_c, src_t, (__nv_bfloat16*)dst, dst_batch, dst_chunk, dst_row0, C, L, fp16, fh::status_word());
   return fh::check_launch("fh_to_chunked_16");
 }

@@ -175,14 +175,14 @@ __global__ void transpose_f32_kernel(const float* __restrict__ src, float* __res
 }
 
 __global__ void cast_f32_16_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, long long n,
-                                   int fp16) {
+                                   int fp16, unsigned int* status) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(src + i);
-    uint32_t h[2] = {fh::pack16(v.x, v.y, fp16), fh::pack16(v.z, v.w, fp16)};
+    uint32_t h[2] = {fh::pack16_guard(v.x, v.y, fp16, status), fh::pack16_guard(v.z, v.w, fp16, status)};
     *reinterpret_cast<uint2*>(dst + i) = *reinterpret_cast<uint2*>(h);
   } else {
-    for (long long k = i; k < n; ++k) dst[k] = fh::cvt16(src[k], fp16);
+    for (long long k = i; k < n; ++k) dst[k] = fh::cvt16_guard(src[k], fp16, status);
   }
 }
 
@@ -190,7 +190,7 @@ __global__ void cast_f32_16_kernel(const float* __restrict__ src, unsigned short
 // carries the 1/num_kernels factor), written as fp32 and / or as the 16-bit operand of the next upsampler.  HBM-bound.
 __global__ void sum_cast_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
                                 const float* __restrict__ d, float* __restrict__ out32, unsigned short* __restrict__ out16,
-                                long long n, int fp16) {
+                                long long n, int fp16, unsigned int* status) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     float4 v = *reinterpret_cast<const float4*>(a + i);
@@ -208,7 +208,7 @@ __global__ void sum_cast_kernel(const float* __restrict__ a, const float* __rest
     }
     if (out32) *reinterpret_cast<float4*>(out32 + i) = v;
     if (out16) {
-      uint32_t h[2] = {fh::pack16(v.x, v.y, fp16), fh::pack16(v.z, v.w, fp16)};
+      uint32_t h[2] = {fh::pack16_guard(v.x, v.y, fp16, status), fh::pack16_guard(v.z, v.w, fp16, status)};
       *reinterpret_cast<uint2*>(out16 + i) = *reinterpret_cast<uint2*>(h);
     }
   } else {
@@ -218,7 +218,7 @@ __global__ void sum_cast_kernel(const float* __restrict__ a, const float* __rest
       if (c) v += c[k];
       if (d) v += d[k];
       if (out32) out32[k] = v;
-      if (out16) out16[k] = fh::cvt16(v, fp16);
+      if (out16) out16[k] = fh::cvt16_guard(v, fp16, status);
     }
   }
 }
@@ -235,7 +235,7 @@ extern "C" __attribute__((visibility("default"))) int fh_sum_cast_f32(const floa
              FH_ERR_BAD_ALIGN, "fh_sum_cast_f32: alignment");
   const long long nthreads = (n + 3) / 4;
   sum_cast_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, b, c, d, out32, (unsigned short*)out16, n,
-                                                                                   fp16);
+                                                                                   fp16, fh::status_word());
   return fh::check_launch("fh_sum_cast_f32");
 }
 
@@ -249,11 +249,8 @@ extern "C" __attribute__((visibility("default"))) int fh_conv1d_taps_f32(const f
   // worst-case window: offsets are bounded by the caller's halo; size smem for span <= CT_T + 512
   const int max_span = CT_T + 512;
   const int smem = (CT_CI * max_span + CT_CI * ntaps * CT_CO) * (int)sizeof(float);
-  static int smem_set = 0;
-  if (smem > smem_set) {
-    cudaFuncSetAttribute(conv1d_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    smem_set = smem;
-  }
+  static int smem_set[64] = {0};
+  fh::ensure_dyn_smem(conv1d_taps_kernel, smem, smem_set);
   dim3 grid((L + CT_T - 1) / CT_T, (Cout + CT_CO - 1) / CT_CO, B * P);
   conv1d_taps_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(x, w, bias, off, res, beta_res, alpha, accumulate, out,
                                                                 Cin, Cout, L, ntaps, P);
@@ -288,6 +285,6 @@ extern "C" __attribute__((visibility("default"))) int fh_cast_f32_16(const float
   FH_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0, FH_ERR_BAD_ALIGN, "fh_cast_f32_16: alignment");
   const long long nthreads = (n + 3) / 4;
   cast_f32_16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned short*)dst, n,
-                                                                                      fp16);
+                                                                                      fp16, fh::status_word());
   return fh::check_launch("fh_cast_f32_16");
 }

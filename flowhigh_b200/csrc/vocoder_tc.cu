@@ -31,12 +31,8 @@ __global__ void __launch_bounds__(128, MINB) snake_aa_mma_kernel(const __grid_co
 template <int MODE, int NB, int MINB, bool IN16 = false>
 void launch_snake_mma(fh::SnakeParams sp, int B, int C, int L, int sms, cudaStream_t stream) {
   using G = fh::SnakeMmaGeom<NB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(snake_aa_mma_kernel<MODE, NB, MINB, IN16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         G::smem_bytes(IN16));
-    attr_set = true;
-  }
+  static int smem_set[64] = {0};
+  fh::ensure_dyn_smem(snake_aa_mma_kernel<MODE, NB, MINB, IN16>, G::smem_bytes(IN16), smem_set);
   sp.ntile = (L + G::kRows - 1) / G::kRows;
   const long long total = (long long)sp.ntile * (C / 8) * B;
   sp.total = (int)total;
@@ -94,13 +90,7 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
   const int ntile = (L + kTileRows - 1) / kTileRows;
   const long long total = (long long)ntile * (C / 8) * B;
   FH_REQUIRE(total <= 2147483647LL && row0 >= 5, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: needs a left halo of >= 5 rows");
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = fh::dev_sms();
   static int per_sm = 0;  // persistent CTAs per SM (4 fill the SM)
   if (!per_sm) {
     const char* e = getenv("FH_SNAKE_CTAS_PER_SM");
@@ -117,6 +107,7 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
   sp.x = x, sp.y = y, sp.a = a, sp.inv_b = inv_b, sp.filt = filt;
   sp.batch_stride = batch_stride, sp.chunk_stride = chunk_stride;
   sp.row0 = row0, sp.nchunk = C / 8, sp.L = L, sp.ntile = ntile, sp.total = (int)total, sp.fp16 = out_kind == 2;
+  sp.status = fh::status_word();
   if (use_mma) {
     FH_REQUIRE((long long)((L + 511) / 512) * (C / 8) * B <= 2147483647LL, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked: too many work items");
     cudaStream_t cs = (cudaStream_t)stream;
@@ -156,17 +147,12 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked_h(
   FH_REQUIRE(row0 >= fh::SnakeMmaGeom<8>::kHalo, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked_h: needs a left halo of >= 8 rows");
   FH_REQUIRE((long long)((L + 511) / 512) * (C / 8) * B <= 2147483647LL, FH_ERR_BAD_SHAPE,
              "fh_snake_aa_chunked_h: too many work items");
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = fh::dev_sms();
   fh::SnakeParams sp;
   sp.x = (const float*)x16, sp.y = y, sp.a = a, sp.inv_b = inv_b, sp.filt = filt;
   sp.batch_stride = batch_stride, sp.chunk_stride = chunk_stride;
   sp.row0 = row0, sp.nchunk = C / 8, sp.L = L, sp.ntile = 0, sp.total = 0, sp.fp16 = 1;
+  sp.status = fh::status_word();
   // FH_SNAKE_H_CTAS=5: five CTAs per SM fit with the half-size fp16 windows (33 KB, 90 registers) -- measured SLOWER
   // (101.5 vs 98.3 ms per step, like every other occupancy increase of this kernel: it is not latency-bound)
   static int per_sm = 0;

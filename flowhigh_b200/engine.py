@@ -15,6 +15,7 @@ Two numeric modes:
 """
 from __future__ import annotations
 
+import collections
 import contextlib
 from os import environ as _environ
 _os_environ_get = _environ.get
@@ -61,7 +62,15 @@ class Engine:
         self.h16 = torch.float16 if self.fp16 else torch.bfloat16  # storage dtype of MMA operands
         self.k16 = 2 if self.fp16 else 1                          # out_mode / out_kind code of that dtype
         self.precise_mel = (precision == "fp32") if precise_mel is None else precise_mel
-        self._bufs: Dict[tuple, torch.Tensor] = {}
+        # persistent scratch buffers, keyed by (name, exact shape, dtype), least recently used first.  The cache is
+        # capped (FH_BUF_CAP_GB, default 120 of the 180 GB): a service that sees ever new clip lengths evicts the buffers
+        # of old shapes instead of growing without bound.  CUDA graphs keep their own references (touch log below).
+        self._bufs: "collections.OrderedDict[tuple, torch.Tensor]" = collections.OrderedDict()
+        self._buf_bytes = 0
+        self._buf_cap = int(float(_os_environ_get("FH_BUF_CAP_GB", "120")) * (1 << 30))
+        self._buf_epoch = 0            # bumped per top-level call: buffers touched in the current call are never evicted
+        self._buf_last: Dict[tuple, int] = {}
+        self._touch_log = None         # {id: object} while a CUDA graph is warmed up / captured: what the graph must keep alive
         self.profile = None
         import os as _os
         self.voc_streams = int(_os.environ.get("FH_VOC_STREAMS", "1"))
@@ -81,7 +90,7 @@ class Engine:
         self._branch_streams = []
         self.pp_fused = _os.environ.get("FH_PP_FUSED", "1") != "0"  # spectrogram-free post-processing
         self._side_streams = []
-        self._time_cache: Dict[float, dict] = {}
+        self._time_cache: "collections.OrderedDict[float, dict]" = collections.OrderedDict()  # LRU, <= 512 grid values
         dev = self.device
         with torch.cuda.device(dev):
             self.sd = {k: v.detach().to(dev, torch.float32).contiguous() for k, v in sd.items()}
@@ -93,6 +102,10 @@ class Engine:
             self.mel_len = torch.from_numpy(ml).to(dev)
             self.mel_w = torch.from_numpy(mw).to(dev)
             self._resample_taps: Dict[tuple, tuple] = {}
+            # overflow / NaN guard of the 16-bit path (include/flowhigh_b200.h fh_set_status_word): one device word,
+            # reset at the start of a pipeline, copied to pinned host memory at its end, read once per generate()
+            self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._status_host = torch.zeros(1, dtype=torch.int32).pin_memory()
             self._prep_backbone()
             self._prep_vocoder()
         torch.cuda.synchronize(dev)
@@ -102,17 +115,59 @@ class Engine:
     def stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    def new_call(self):
+        """Marks the start of a top-level call (generate_batch / bench step): buffers last used by earlier calls
+        become evictable when the cache cap is hit, and the calling thread's launches report to this engine's
+        status word."""
+        self._buf_epoch += 1
+        _lib.check(self.lib.fh_set_status_word(self.status.data_ptr()), "fh_set_status_word")
+
+    def status_begin(self):
+        """Zeroes the status word (stream-ordered; capturable)."""
+        self._call("fh_fill_u32", self.status.data_ptr(), 0, 1, self.stream)
+
+    def status_end(self):
+        """Stream-ordered copy of the status word to pinned host memory (capturable)."""
+        self._status_host.copy_(self.status, non_blocking=True)
+
+    def status_read(self) -> int:
+        """Synchronises the current stream and returns the status word of the last status_begin/status_end bracket:
+        bit 0 = a 16-bit operand saturated (fp16 |x| >= 65504) or was inf / NaN."""
+        torch.cuda.current_stream(self.device).synchronize()
+        return int(self._status_host[0])
+
+    def _evict_for(self, need: int):
+        if torch.cuda.is_current_stream_capturing():
+            return
+        for key in list(self._bufs.keys()):
+            if self._buf_bytes + need <= self._buf_cap:
+                break
+            if self._buf_last.get(key, -1) >= self._buf_epoch:
+                continue  # in use by the current call
+            t = self._bufs.pop(key)
+            self._buf_last.pop(key, None)
+            self._buf_bytes -= t.numel() * t.element_size()
+
     def buf(self, name: str, shape, dtype=torch.float32, zero: bool = True) -> torch.Tensor:
         key = (name, tuple(int(s) for s in shape), dtype)
         t = self._bufs.get(key)
+        self._buf_last[key] = self._buf_epoch
+        if t is not None:
+            self._bufs.move_to_end(key)
         if t is None:
+            need = int(np.prod(key[1], dtype=np.int64)) * torch.empty((), dtype=dtype).element_size()
+            if self._buf_bytes + need > self._buf_cap:
+                self._evict_for(need)
             t = (torch.zeros if zero else torch.empty)(key[1], dtype=dtype, device=self.device)
             self._bufs[key] = t
+            self._buf_bytes += need
             # The zero-fill runs on the stream that is current NOW, but the buffer may first be used on another one
             # (the AMP branch streams wait on an event recorded before their scratch buffers are created): without
             # this, the fill can land after a branch kernel has written the buffer.  First use of a shape only.
             if not torch.cuda.is_current_stream_capturing():
                 torch.cuda.current_stream(self.device).synchronize()
+        if self._touch_log is not None:
+            self._touch_log[id(t)] = t
         return t
 
     def _chk(self, *tensors):
@@ -320,6 +375,9 @@ class Engine:
         key = float(np.float32(t))
         hit = self._time_cache.get(key)
         if hit is not None:
+            self._time_cache.move_to_end(key)
+            if self._touch_log is not None:
+                self._touch_log[id(hit)] = hit
             return hit
         sd, b = self.sd, self.bcfg
         D = b.dim
@@ -338,6 +396,8 @@ class Engine:
                                sd[FH + f"convnext.{i}.norm.{nm}.bias"].data_ptr(), v.data_ptr(), D, D, 0, self.stream)
                     out[(i, nm)] = v
             self._time_cache[key] = out
+            if self._touch_log is not None:
+                self._touch_log[id(out)] = out
             return out
         for l in range(b.depth):
             for idx in (2, 4):
@@ -348,6 +408,10 @@ class Engine:
                                sd[p + f"to_{nm}.bias"].data_ptr(), v.data_ptr(), D, D, 0, self.stream)
                     out[(l, idx, nm)] = v
         self._time_cache[key] = out
+        if self._touch_log is not None:
+            self._touch_log[id(out)] = out
+        while len(self._time_cache) > 512:
+            self._time_cache.popitem(last=False)
         return out
 
     def _tc_conv(self, rec: _TcWeight, a, a_batch, a_chunk, a_row0, out, out_strides, out_bf16, B, L, res=None,
@@ -627,8 +691,12 @@ class Engine:
         return False
 
     def sample_mel(self, cond_mel: torch.Tensor, eps: torch.Tensor, *, steps: int, ode_method: str, cfm_method: str,
-                   sigma: float, cond_scale: float = 1.0, mel_pp: bool = False) -> torch.Tensor:
-        """CFM sampler (cfm_superresolution.py:162-284 up to `sampled`): prior + fixed-grid ODE (+ mel_pp)."""
+                   sigma: float, cond_scale: float = 1.0, mel_pp: bool = False, std_1: Optional[float] = None,
+                   std_2: Optional[float] = None) -> torch.Tensor:
+        """CFM sampler (cfm_superresolution.py:162-284 up to `sampled`): prior + fixed-grid ODE (+ mel_pp).
+        std_1 / std_2: the reference falls back to (1.0, sigma) unless BOTH are given (:180-183)."""
+        if std_1 is None or std_2 is None:
+            std_1, std_2 = 1.0, float(sigma)
         if ode_method not in ("euler", "midpoint"):
             raise ValueError(f"unsupported ODE method {ode_method!r} (euler|midpoint)")
         self._chk(cond_mel, eps)
@@ -639,8 +707,9 @@ class Engine:
         if cfm_method == "basic_cfm":
             self._call("fh_axpby_f32", eps.data_ptr(), None, 1.0, 0.0, y.data_ptr(), n, self.stream)
         elif cfm_method in ("independent_cfm_adaptive", "independent_cfm_constant", "independent_cfm_mix"):
-            # std_1 / std_2 quirk (cfm_superresolution.py:180-183): y0 = cond * 1 + eps * sigma
-            self._call("fh_axpby_f32", cond_mel.data_ptr(), eps.data_ptr(), 1.0, float(sigma), y.data_ptr(), n, self.stream)
+            # y0 = cond * std_1 + eps * std_2  (generate() always ends up with cond * 1 + eps * sigma: SURVEY F5)
+            self._call("fh_axpby_f32", cond_mel.data_ptr(), eps.data_ptr(), float(std_1), float(std_2), y.data_ptr(), n,
+                       self.stream)
             if cfm_method == "independent_cfm_mix":  # low bins from the adaptive prior, high bins pure noise (:232-237)
                 cut = self.mel_cutoff_bins(cond_mel)
                 y = self.mel_splice(y, eps, cut)
@@ -777,7 +846,10 @@ class Engine:
 
     def _cbuf(self, name, B, C, L, dtype):
         Lp, cs, bs = self._geom(C, L)
-        t = self.buf(name, (B * bs + 4096,), dtype)  # zero-initialised: halos stay zero forever
+        # Zero-initialised, and kernels only ever write rows [0, L): the halo AND the rows [L, Lp) stay zero forever --
+        # the conv windows read them as the Conv1d zero padding.  Lp rounds L up to 128 rows, so the key carries the
+        # EXACT L: a shorter clip that shares the 128-row bucket of a longer one must not see its stale tail rows.
+        t = self.buf(f"{name}@{L}", (B * bs + 4096,), dtype)
         return t, cs, bs
 
     def _vocoder_tc(self, mel: torch.Tensor, wave: torch.Tensor, tag: str, started_event=None):

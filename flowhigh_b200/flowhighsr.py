@@ -15,6 +15,7 @@ an unknown `cfm_method` passed to `sample` silently falls back to `self.cfm_meth
 """
 from __future__ import annotations
 
+import collections
 import json
 from pathlib import Path
 from typing import Dict, List, Optional, Sequence, Union
@@ -28,6 +29,23 @@ from .engine import Engine
 from .weights import FH, VOC, fold_weight_norm, random_state_dict, state_dict_spec
 
 REPO_ID = "ResembleAI/FlowHigh"
+
+
+def _on_model_device(fn):
+    """Runs a public entry point with the model's GPU as the current device: the kernels launch on
+    `torch.cuda.current_stream(device)` and set per-device function attributes, so a model on cuda:1 must not be
+    driven while cuda:0 is current."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        owner = self if isinstance(self, FlowHighSR) else self._owner()
+        dev = owner.device
+        if dev.type != "cuda":
+            return fn(self, *a, **k)  # _engine() raises the "no CPU path" error
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapper
 
 
 class _Tree(nn.Module):
@@ -81,11 +99,16 @@ class MelVoco(_Tree):
     def latent_dim(self):
         return self.n_mels
 
+    @_on_model_device
     def encode(self, audio: torch.Tensor) -> torch.Tensor:
-        return self._owner()._engine().encode(audio.to(self._owner().device, torch.float32).contiguous())
+        eng = self._owner()._engine()
+        eng.new_call()
+        return eng.encode(audio.to(self._owner().device, torch.float32).contiguous())
 
+    @_on_model_device
     def decode(self, mel: torch.Tensor) -> torch.Tensor:
         eng = self._owner()._engine()
+        eng.new_call()
         return eng.vocoder(mel.to(eng.device, torch.float32).contiguous()).unsqueeze(1)
 
 
@@ -117,9 +140,15 @@ class FLowHigh(_Tree):
         self.audio_enc_dec = audio_enc_dec
         self._owner = None
 
+    @_on_model_device
     def forward_with_cond_scale(self, x, *, times, cond, cond_scale=1.0, cond_mask=None, self_attn_mask=None):
         """flow.py:165-178: returns the vector field v(times, x | cond)."""
+        if cond_mask is not None or self_attn_mask is not None:
+            # generate() / sample() never pass them (cfm_superresolution.py:196,209-210: self_attn_mask = None,
+            # cond_mask = None); the attention kernels have no masked form, so a mask must not be silently dropped
+            raise NotImplementedError("cond_mask / self_attn_mask are not supported by the B200 attention kernels")
         eng = self._owner()._engine()
+        eng.new_call()
         x = x.to(eng.device, torch.float32).contiguous()
         cond = cond.to(eng.device, torch.float32).contiguous()
         zero = torch.zeros_like(x)
@@ -139,11 +168,13 @@ class PostProcessing:
     def __init__(self, owner):
         self._owner = owner
 
+    @_on_model_device
     def post_processing(self, pred: torch.Tensor, src: torch.Tensor, length: int) -> torch.Tensor:
         assert pred.dim() == 2 and src.dim() == 2
         if length != src.shape[-1]:
             raise ValueError("length must equal src.size(-1) (the only way the reference calls it)")
         eng = self._owner()._engine()
+        eng.new_call()
         return eng.postprocess(pred.to(eng.device, torch.float32).contiguous(), src.to(eng.device, torch.float32).contiguous())
 
 
@@ -164,7 +195,14 @@ class FlowHighSR(nn.Module):
         self.precision = precision
         self.cuda_graphs = True          # capture small-batch generate() pipelines into CUDA graphs
         self.cuda_graph_max_batch = 8
-        self._graphs: Dict[tuple, tuple] = {}
+        # Graphs are keyed by the exact input shape.  A service rarely sees a length twice, so a shape is captured only
+        # when it comes back (`cuda_graph_min_hits`-th sighting; the eager run costs a third of a capture), and at most
+        # `cuda_graph_cache_size` graphs (with their static buffers and private pools) are kept, least recently used out.
+        self.cuda_graph_min_hits = 2
+        self.cuda_graph_cache_size = 8
+        self._graphs: "collections.OrderedDict[tuple, tuple]" = collections.OrderedDict()
+        self._graph_seen: "collections.OrderedDict[tuple, int]" = collections.OrderedDict()
+        self.overflow_check = "raise"    # 16-bit paths: "raise" FloatingPointError on a saturated / non-finite operand, or "off"
         self._eng: Optional[Engine] = None
         import weakref
         ref = weakref.ref(self)
@@ -189,13 +227,11 @@ class FlowHighSR(nn.Module):
         return next(self.parameters()).device
 
     def _apply(self, fn, *a, **k):
-        self._eng = None
-        self._graphs = {}
+        self._drop_engine()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, state_dict, strict: bool = True, **kw):
-        self._eng = None
-        self._graphs = {}
+        self._drop_engine()
         return super().load_state_dict(state_dict, strict=strict, **kw)
 
     def load(self, path, strict=True):
@@ -216,8 +252,12 @@ class FlowHighSR(nn.Module):
 
     def set_precision(self, precision: str):
         self.precision = precision
+        self._drop_engine()
+
+    def _drop_engine(self):
         self._eng = None
-        self._graphs = {}
+        self._graphs = collections.OrderedDict()
+        self._graph_seen = collections.OrderedDict()
 
     # ------------------------------------------------------------------ reference API
     def set_cfm_method(self, cfm_method):
@@ -229,28 +269,42 @@ class FlowHighSR(nn.Module):
         return torch.randn_like(cond_mel)  # same draw the reference makes (cfm_superresolution.py:220)
 
     @torch.inference_mode()
+    @_on_model_device
     def sample(self, *, cond=None, cond_mask=None, time_steps=4, cond_scale=1.0, decode_to_audio=True, std_1=None,
                std_2=None, mel_pp=False, cfm_method=None, eps: Optional[torch.Tensor] = None):
         if cfm_method not in CFM_METHODS:
             cfm_method = self.cfm_method
+        if cond_mask is not None:
+            raise NotImplementedError("cond_mask is not supported (generate() never passes one)")
+        # cfm_superresolution.py:180-183: BOTH fall back to (1.0, sigma) unless both are given
+        if std_1 is None or std_2 is None:
+            std_1, std_2 = 1.0, float(self.sigma)
         eng = self._engine()
+        eng.new_call()
+        eng.status_begin()
         cond = cond.to(eng.device, torch.float32).contiguous()
         is_audio = cond.dim() == 2 or (cond.dim() == 3 and cond.shape[1] == 1)
         if is_audio:
             cond = eng.encode(cond.reshape(cond.shape[0], -1))
         mel = eng.sample_mel(cond, self._noise_like(cond, eps), steps=int(time_steps),
                              ode_method=self.odeint_kwargs["method"], cfm_method=cfm_method, sigma=float(self.sigma),
-                             cond_scale=float(cond_scale), mel_pp=bool(mel_pp))
+                             cond_scale=float(cond_scale), mel_pp=bool(mel_pp), std_1=float(std_1), std_2=float(std_2))
         if not decode_to_audio:
             return mel
-        return eng.vocoder(mel).unsqueeze(1)
+        out = eng.vocoder(mel).unsqueeze(1)
+        self._check_status(eng)
+        return out
 
     def _prep_input(self, audio) -> np.ndarray:
         if isinstance(audio, torch.Tensor):
             audio = audio.detach().cpu().numpy()
         audio = np.asarray(audio)
         if audio.ndim == 2:
-            audio = audio.squeeze(0)
+            if audio.shape[0] != 1:  # the reference's squeeze(0) would silently keep [C, T] and fail later
+                raise ValueError(f"generate() takes mono audio, [T] or [1, T]; got shape {tuple(audio.shape)}")
+            audio = audio[0]
+        elif audio.ndim != 1:
+            raise ValueError(f"generate() takes mono audio, [T] or [1, T]; got shape {tuple(audio.shape)}")
         if audio.max() > 1:  # flowhighsr.py:62-63 (any dtype)
             audio = audio / 32768.0
         return np.ascontiguousarray(audio, dtype=np.float32)
@@ -262,6 +316,7 @@ class FlowHighSR(nn.Module):
         return out[0]
 
     @torch.no_grad()
+    @_on_model_device
     def generate_batch(self, audios: Sequence, sr: Union[int, Sequence[int]], target_sampling_rate=48000, timestep=1,
                        eps: Optional[Sequence[torch.Tensor]] = None, pinned: bool = False) -> List[torch.Tensor]:
         """Batched `generate`: every clip is processed exactly as the reference processes it alone
@@ -270,13 +325,18 @@ class FlowHighSR(nn.Module):
         if self.upsampling_method != "scipy":
             raise NotImplementedError("upsampling_method='librosa' (soxr_hq) is a SURVEY 8f 'next' row")
         eng = self._engine()
+        eng.new_call()
         srs = [sr] * len(audios) if isinstance(sr, int) else list(sr)
         prepped = [self._prep_input(a) for a in audios]
         groups: Dict[tuple, List[int]] = {}
         for i, (a, s) in enumerate(zip(prepped, srs)):
             groups.setdefault((int(s), a.shape[0]), []).append(i)
         results: List[Optional[torch.Tensor]] = [None] * len(audios)
-        for (s, n), idxs in groups.items():
+        flags = 0
+        check = self.overflow_check != "off" and eng.tc
+        for gi, ((s, n), idxs) in enumerate(groups.items()):
+            if check and gi > 0:
+                flags |= eng.status_read()  # one status word per engine: collect the previous group's before the next resets it
             host = torch.from_numpy(np.stack([prepped[i] for i in idxs]))
             if pinned:
                 host = host.pin_memory()
@@ -289,39 +349,77 @@ class FlowHighSR(nn.Module):
                                       None if e is None else e.to(eng.device))
             for j, i in enumerate(idxs):
                 results[i] = out[j: j + 1]
+        if check:
+            self._check_status(eng, flags | eng.status_read())
         return results  # type: ignore[return-value]
 
     def _run_group(self, eng, x, sr, target_sr, timestep, eps_dev):
         """resample -> log-mel -> CFM -> vocoder -> post-processing for one batch of equal-length clips."""
+        eng.status_begin()
         cond = eng.resample_normalise(x, sr, target_sr)
         cond_mel = eng.encode(cond)
         mel = eng.sample_mel(cond_mel, self._noise_like(cond_mel, eps_dev), steps=timestep,
                              ode_method=self.odeint_kwargs["method"], cfm_method=self.cfm_method, sigma=float(self.sigma))
-        return eng.postprocess(eng.vocoder(mel), cond)
+        out = eng.postprocess(eng.vocoder(mel), cond)
+        eng.status_end()
+        return out
+
+    def _check_status(self, eng, flags: int = None):
+        """16-bit paths: raises when a tensor-core operand left the fp16 range (saturated at +-65504) or was inf / NaN --
+        the device-side replacement of the reference's per-NFE NaN prints (models/flow.py:256-267).  One stream
+        synchronisation per generate() call; `overflow_check = "off"` skips it."""
+        if self.overflow_check == "off" or not eng.tc:
+            return
+        if flags is None:
+            eng.status_end()
+            flags = eng.status_read()
+        if flags:
+            raise FloatingPointError(
+                f"flowhigh_b200: a {eng.precision} tensor-core operand overflowed or was not finite (status {flags:#x}); "
+                "the result is not trustworthy -- use precision='bf16' (fp32 range) or 'fp32' for these weights / inputs")
 
     def _run_group_graphed(self, eng, host, sr, target_sr, timestep, eps_host):
         """Small batches are launch-bound (~300 kernel launches per clip): the whole per-shape pipeline is captured
-        once into a CUDA graph (static input / noise / output buffers) and replayed."""
+        into a CUDA graph (static input / noise / output buffers) and replayed.  A shape is captured when it is seen
+        for the `cuda_graph_min_hits`-th time; the cache holds `cuda_graph_cache_size` graphs, least recently used out
+        (each entry owns its static buffers, its private pool and references to the engine buffers it replays into)."""
         B, n = host.shape
         key = (B, n, sr, target_sr, timestep, self.odeint_kwargs["method"], self.cfm_method, float(self.sigma))
         ent = self._graphs.get(key)
         if ent is None:
+            seen = self._graph_seen.get(key, 0) + 1
+            self._graph_seen[key] = seen
+            self._graph_seen.move_to_end(key)
+            while len(self._graph_seen) > 64 * max(1, self.cuda_graph_cache_size):
+                self._graph_seen.popitem(last=False)
+            if seen < self.cuda_graph_min_hits:
+                x = host.to(eng.device, non_blocking=True)
+                return self._run_group(eng, x, sr, target_sr, timestep, None if eps_host is None else eps_host.to(eng.device))
             x_static = torch.zeros((B, n), dtype=torch.float32, device=eng.device)
             x_static.copy_(host)
             T = -(-n * (target_sr // np.gcd(target_sr, sr)) // (sr // np.gcd(target_sr, sr)))
             eps_static = torch.randn((B, T // 480, 256), dtype=torch.float32, device=eng.device)
-            side = torch.cuda.Stream(eng.device)
-            side.wait_stream(torch.cuda.current_stream(eng.device))
-            with torch.cuda.stream(side):
-                for _ in range(2):  # allocate persistent buffers, time-conditioning cache, function attributes
-                    self._run_group(eng, x_static, sr, target_sr, timestep, eps_static)
-            torch.cuda.current_stream(eng.device).wait_stream(side)
-            torch.cuda.synchronize(eng.device)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out_static = self._run_group(eng, x_static, sr, target_sr, timestep, eps_static)
-            ent = self._graphs[key] = (graph, x_static, eps_static, out_static)
-        graph, x_static, eps_static, out_static = ent
+            eng._touch_log = {}
+            try:
+                side = torch.cuda.Stream(eng.device)
+                side.wait_stream(torch.cuda.current_stream(eng.device))
+                with torch.cuda.stream(side):
+                    for _ in range(2):  # allocate persistent buffers, time-conditioning cache, function attributes
+                        self._run_group(eng, x_static, sr, target_sr, timestep, eps_static)
+                torch.cuda.current_stream(eng.device).wait_stream(side)
+                torch.cuda.synchronize(eng.device)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out_static = self._run_group(eng, x_static, sr, target_sr, timestep, eps_static)
+                keep = list(eng._touch_log.values())
+            finally:
+                eng._touch_log = None
+            ent = self._graphs[key] = (graph, x_static, eps_static, out_static, keep)
+            while len(self._graphs) > max(1, self.cuda_graph_cache_size):
+                self._graphs.popitem(last=False)
+        else:
+            self._graphs.move_to_end(key)
+        graph, x_static, eps_static, out_static, _keep = ent
         x_static.copy_(host, non_blocking=True)
         if eps_host is not None:
             eps_static.copy_(eps_host.reshape(eps_static.shape), non_blocking=True)
@@ -331,6 +429,7 @@ class FlowHighSR(nn.Module):
         return out_static.clone()
 
     @torch.no_grad()
+    @_on_model_device
     def generate_long(self, audio, sr: int, target_sampling_rate=48000, timestep=1, chunk_seconds: float = 10.0,
                       overlap_seconds: float = 0.5, eps: Optional[torch.Tensor] = None, max_batch: int = 64):
         """Long-form generation by overlapped chunking + overlap-add (not in the reference,
@@ -339,6 +438,8 @@ class FlowHighSR(nn.Module):
         vocoder as an independent clip, the vocoder outputs are cross-faded, and the STFT-domain
         post-processing runs once over the stitched signal.  `eps` (optional) is [K, frames, 256]."""
         eng = self._engine()
+        eng.new_call()
+        eng.status_begin()
         x = torch.from_numpy(self._prep_input(audio))[None].to(eng.device)
         cond = eng.resample_normalise(x, int(sr), target_sampling_rate)  # [1, T]
         T = cond.shape[1]
@@ -364,7 +465,9 @@ class FlowHighSR(nn.Module):
         Tv = T // 480 * 480  # the vocoder emits whole frames (pred is shorter than src when T % 480 != 0)
         stitched = torch.empty((1, Tv), dtype=torch.float32, device=eng.device)
         eng._call("fh_ola_crossfade_f32", waves.data_ptr(), stitched.data_ptr(), K, clen, step, Tv, eng.stream)
-        return eng.postprocess(stitched, cond)
+        out = eng.postprocess(stitched, cond)
+        self._check_status(eng)
+        return out
 
     # ------------------------------------------------------------------ loaders
     @classmethod

@@ -36,6 +36,14 @@ int fh_version(void);
 const char* fh_last_error_string(void);
 /* number of kernel launches issued through this library by the calling process */
 int64_t fh_launch_count(void);
+/* Overflow / NaN guard of the 16-bit tensor path.  `status` is a DEVICE uint32 the caller owns and zeroes (NULL turns
+ * the guard off); it is remembered per host thread and handed to every later launch from that thread of a kernel that
+ * writes 16-bit operands (fh_tc_conv, fh_snake_aa_chunked[_h], fh_to_chunked_16, fh_rmsnorm_f32, fh_layernorm_f32,
+ * fh_gelu_f32, fh_geglu_f32, fh_attention_*, fh_qknorm_rope_split, fh_cast_f32_16, fh_sum_cast_f32).  fp16 conversions
+ * saturate at +-65504; a saturated, infinite or NaN operand ORs bit 0 into *status.  The host reads the word once per
+ * generate() -- the device-side replacement of the reference's per-NFE `torch.isnan(x).any()` prints
+ * (models/flow.py:256-267), without their four host syncs per NFE. */
+int fh_set_status_word(uint32_t* status);
 
 /* ---------------------------------------------------------------- resampler + peak normalise
  * replaces scipy.signal.resample_poly + `cond /= max|cond|`   flowhighsr.py:68-69

@@ -1,8 +1,8 @@
 """ORACLE tooling -- runs the UNMODIFIED reference from /root/reference on CPU.
 
-Only usable in the build container (the GPU box has no /root/reference); used by
-tests/golden/make_golden.py to pin oracle/ against the reference's own code, and by
-tests/test_reference_live.py (skipped when the reference tree is absent).
+Runs from /root/reference in the build container (tests/golden/make_golden.py pins oracle/ against the
+reference's own code there) or from baseline/_ref, the `pip install --target` copy of the unmodified reference
+that travels to the GPU box for `bench.py --impl reference` and the `cpu_baseline` leg.
 
 Four packages the reference imports are missing offline: `librosa`,
 `torchdiffeq`, `torchode`, `gateloop_transformer`.  They are replaced by stub modules:
@@ -21,11 +21,24 @@ import types
 
 import torch
 
-REF_SRC = "/root/reference/src"
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the reference tree of the build container, else the pip --target install that travels to the GPU box
+# (baseline/_ref: git-ignored, created by __graft_entry__.build(); unmodified reference package)
+_CANDIDATES = ("/root/reference/src", os.path.join(os.path.dirname(_HERE), "baseline", "_ref"))
+
+
+def ref_src():
+    for c in _CANDIDATES:
+        if os.path.isdir(os.path.join(c, "flowhigh")):
+            return c
+    return None
+
+
+REF_SRC = ref_src() or _CANDIDATES[0]
 
 
 def available() -> bool:
-    return os.path.isdir(os.path.join(REF_SRC, "flowhigh"))
+    return ref_src() is not None
 
 
 _loaded = {}
@@ -80,12 +93,13 @@ def load_reference():
     scratch = tempfile.mkdtemp(prefix="fh_ref_")
     os.chdir(scratch)
     try:
-        sys.path.insert(0, REF_SRC)
+        src = ref_src()
+        sys.path.insert(0, src)
         import flowhigh  # noqa: F401
         import logging
         logging.getLogger().setLevel(logging.ERROR)  # F9b: avoid tensor repr formatting cost
     finally:
-        sys.path.remove(REF_SRC)
+        sys.path.remove(src)
         os.chdir(cwd)
     _loaded["pkg"] = sys.modules["flowhigh"]
     return _loaded["pkg"]

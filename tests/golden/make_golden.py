@@ -168,15 +168,96 @@ def frontend_case(name):
     print(name, "ok")
 
 
+def big_case(name, sr, n_in, steps, cfm_method, ode_method, sigma, seed):
+    """The configuration bench.py times (VocoderConfig.assumed_48k(): C0 = 1536, stages 768 ... 24) at the BASELINE clip
+    sizes, from the unmodified reference.  Slim fixture: input, noise seed and the reference's mel / vocoder / final
+    outputs only (no fp64 restatement; that pins the oracle on the small fixtures above)."""
+    vcfg = VocoderConfig.assumed_48k()
+    sd = random_state_dict(BackboneConfig(), vcfg, seed=seed, vocoder_gain=GAIN)
+    ref = ref_harness.build_reference_model(sd, vcfg, cfm_method=cfm_method, ode_method=ode_method, sigma=sigma)
+    wav = synth_speech(n_in, sr, seed=seed + 100)
+    T = -(-n_in * 48000 // sr)
+    N = T // 480
+    eps = torch.from_numpy(np.random.default_rng(seed + 7).standard_normal((1, N, 256)).astype(np.float32))
+    import scipy.signal
+    cond_np = scipy.signal.resample_poly(wav, 48000, sr)
+    cond_np = cond_np / np.max(np.abs(cond_np))
+    cond = torch.tensor(cond_np).unsqueeze(0).float()
+    with ref_harness.patched_randn_like(eps):
+        mel = ref.sample(cond=cond, time_steps=steps, cfm_method=cfm_method, decode_to_audio=False)
+    voc = ref.flowhigh.audio_enc_dec.decode(mel).squeeze(1)
+    with ref_harness.patched_randn_like(eps):
+        final = ref.generate(wav, sr, 48000, timestep=steps)
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        wav=wav, sr=sr, steps=steps, cfm_method=cfm_method, ode_method=ode_method, sigma=sigma, seed=seed, gain=GAIN,
+        eps_seed=seed + 7, vcfg=str(vcfg.to_attr_json()), weight_checksum=checksum(sd),
+        ref_mel=mel.numpy(), ref_vocoder=voc.numpy(), ref_final=final.numpy())
+    print(name, "T", T, "N", N, "vocoder absmax", float(voc.abs().max()), "final absmax", float(final.abs().max()))
+
+
+def sample_variants_case(name, seed):
+    """`sample()` with cond_scale != 1 (classifier-free guidance, flow.py:165-178), cfm_method='independent_cfm_mix'
+    (cfm_superresolution.py:232-237) and mel_pp=True (:278-279) from the unmodified reference (mel output)."""
+    vcfg = VocoderConfig.tiny()
+    sd = random_state_dict(BackboneConfig(), vcfg, seed=seed, vocoder_gain=GAIN)
+    rng = np.random.default_rng(seed)
+    B, N = 2, 45
+    # band-limited log-mel-like conditioning: different cutoff bins per clip
+    cond = rng.standard_normal((B, N, 256)).astype(np.float32) * 1.5 - 4.0
+    cond[0, :, 90:] = -11.5129 + 0.01 * rng.standard_normal((N, 166)).astype(np.float32)
+    cond[1, :, 170:] = -11.5129 + 0.01 * rng.standard_normal((N, 86)).astype(np.float32)
+    cond = torch.from_numpy(cond)
+    eps = torch.from_numpy(rng.standard_normal((B, N, 256)).astype(np.float32))
+    d = dict(cond=cond.numpy(), eps=eps.numpy(), seed=seed, gain=GAIN, vcfg=str(vcfg.to_attr_json()),
+             weight_checksum=checksum(sd))
+    cases = {"cfg": dict(cfm_method="basic_cfm", ode="midpoint", sigma=0.0, kw=dict(cond_scale=1.7, time_steps=2)),
+             "mix": dict(cfm_method="independent_cfm_mix", ode="euler", sigma=1e-4, kw=dict(time_steps=2)),
+             "mel_pp": dict(cfm_method="independent_cfm_adaptive", ode="euler", sigma=1e-4, kw=dict(time_steps=1, mel_pp=True)),
+             "cfg_mix_pp": dict(cfm_method="independent_cfm_mix", ode="midpoint", sigma=1e-4,
+                                kw=dict(cond_scale=0.6, time_steps=1, mel_pp=True))}
+    for tag, c in cases.items():
+        ref = ref_harness.build_reference_model(sd, vcfg, cfm_method=c["cfm_method"], ode_method=c["ode"], sigma=c["sigma"])
+        with ref_harness.patched_randn_like(eps):
+            mel = ref.sample(cond=cond, decode_to_audio=False, cfm_method=c["cfm_method"], **c["kw"])
+        cuts = ref.mel_cutoff_bins(cond)
+        mel64 = model.cfm_sample_mel(sd64(sd), cond.double(), eps.double(), steps=c["kw"]["time_steps"], ode_method=c["ode"],
+                                     cfm_method=c["cfm_method"], sigma=c["sigma"], cond_scale=c["kw"].get("cond_scale", 1.0),
+                                     mel_pp=c["kw"].get("mel_pp", False))
+        d["ref_mel_" + tag] = mel.numpy()
+        d["f64_mel_" + tag] = mel64.float().numpy()
+        d["cuts"] = np.asarray(cuts, dtype=np.int32)
+        print(name, tag, "cut bins", cuts, "ref-vs-f64 %.3g" % (mel - mel64).abs().max())
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **d)
+
+
 if __name__ == "__main__":
     assert ref_harness.available(), "needs /root/reference"
     torch.manual_seed(0)
-    frontend_case("frontend")
-    generate_case("gen_c1_adaptive_euler", VocoderConfig.tiny(), 16000, 16000, 1, "independent_cfm_adaptive", "euler",
-                  1e-4, seed=1)
-    generate_case("gen_basic_midpoint", VocoderConfig.tiny(), 12000, 9000, 1, "basic_cfm", "midpoint", 0.0, seed=2)
-    generate_case("gen_basic_euler4", VocoderConfig.tiny(), 24000, 12240, 4, "basic_cfm", "euler", 0.0, seed=3)
-    vocoder_case("voc_resblock2_snake", VocoderConfig.tiny(resblock="2", activation="snake", logscale=False), 24, seed=4)
-    vocoder_case("voc_resblock1_snakebeta", VocoderConfig.tiny(), 30, seed=5)
-    skip_case("vf_unet_skip", seed=6)
-    convnext_case("vf_convnext", seed=7)
+    only = set(sys.argv[1:])
+    want = lambda n: not only or n in only
+    if want("frontend"):
+        frontend_case("frontend")
+    if want("gen_c1_adaptive_euler"):
+        generate_case("gen_c1_adaptive_euler", VocoderConfig.tiny(), 16000, 16000, 1, "independent_cfm_adaptive", "euler",
+                      1e-4, seed=1)
+    if want("gen_basic_midpoint"):
+        generate_case("gen_basic_midpoint", VocoderConfig.tiny(), 12000, 9000, 1, "basic_cfm", "midpoint", 0.0, seed=2)
+    if want("gen_basic_euler4"):
+        generate_case("gen_basic_euler4", VocoderConfig.tiny(), 24000, 12240, 4, "basic_cfm", "euler", 0.0, seed=3)
+    if want("voc_resblock2_snake"):
+        vocoder_case("voc_resblock2_snake", VocoderConfig.tiny(resblock="2", activation="snake", logscale=False), 24, seed=4)
+    if want("voc_resblock1_snakebeta"):
+        vocoder_case("voc_resblock1_snakebeta", VocoderConfig.tiny(), 30, seed=5)
+    if want("vf_unet_skip"):
+        skip_case("vf_unet_skip", seed=6)
+    if want("vf_convnext"):
+        convnext_case("vf_convnext", seed=7)
+    if want("sample_variants"):
+        sample_variants_case("sample_variants", seed=8)
+    # the configuration bench.py times: BASELINE configs[0] exactly (4 s, 16 kHz, adaptive, euler 1 step, N = 400) and one
+    # clip of configs[1] (10 s, 12 kHz, basic_cfm, midpoint, N = 1000)
+    if want("big_c0_4s_adaptive_euler"):
+        big_case("big_c0_4s_adaptive_euler", 16000, 64000, 1, "independent_cfm_adaptive", "euler", 1e-4, seed=21)
+    if want("big_c1_10s_basic_midpoint"):
+        big_case("big_c1_10s_basic_midpoint", 12000, 120000, 1, "basic_cfm", "midpoint", 0.0, seed=0)

@@ -519,7 +519,7 @@ def test_cuda_graph_generate_matches_eager(cuda_device):
     wav, sr = g["wav"], int(g["sr"])
     m.cuda_graphs = False
     ref = m.generate(wav, sr, 48000, timestep=1, eps=eps).cpu()
-    m.cuda_graphs = True
+    m.cuda_graphs, m.cuda_graph_min_hits = True, 1
     a = m.generate(wav, sr, 48000, timestep=1, eps=eps).cpu()       # capture + first replay
     b = m.generate(wav * 0.5, sr, 48000, timestep=1, eps=eps).cpu()  # replay with new input (peak-normalised -> same result)
     c = m.generate(wav, sr, 48000, timestep=1, eps=eps).cpu()
@@ -749,3 +749,235 @@ def test_convnext_variant(cuda_device, precision):
         assert float((mel - mref).abs().mean()) <= 1e-4
     else:
         assert snr_db(mref, mel) >= 40.0
+
+
+# ------------------------------------------------------------------ the configuration bench.py times
+BIG = ["big_c0_4s_adaptive_euler", "big_c1_10s_basic_midpoint"]
+_BIG_MODELS = {}
+
+
+def _big_model(name, precision):
+    """assumed_48k() vocoder (C0 = 1536, stages 768 ... 24) at the BASELINE clip sizes (N = 400 / N = 1000)."""
+    g = load_golden(name)
+    key = (int(g["seed"]), str(g["cfm_method"]), precision)
+    if key not in _BIG_MODELS:
+        _BIG_MODELS.clear()  # one 150 M-parameter model (+ its activation buffers) resident at a time
+        torch.cuda.empty_cache()
+        sd, vcfg = golden_weights(g)
+        m = FlowHighSR.from_random(vcfg, device="cuda:0", precision=precision, sigma=float(g["sigma"]),
+                                   cfm_method=str(g["cfm_method"]), torchdiffeq_ode_method=str(g["ode_method"]))
+        m.load_state_dict(sd)
+        _BIG_MODELS[key] = m.cuda()
+    return _BIG_MODELS[key], g
+
+
+def _big_eps(g):
+    N = g["ref_mel"].shape[1]
+    return torch.from_numpy(np.random.default_rng(int(g["eps_seed"])).standard_normal((1, N, 256)).astype(np.float32))
+
+
+@pytest.mark.parametrize("name", BIG)
+def test_big_config_f32_golden(cuda_device, name):
+    """fp32 path against the unmodified reference on BASELINE configs[0] (4 s, 16 kHz, adaptive, euler, N = 400) and one
+    clip of configs[1] (10 s, 12 kHz, basic_cfm, midpoint, N = 1000): waveform max-abs <= 1e-4 (north_star)."""
+    m, g = _big_model(name, "fp32")
+    eps = _big_eps(g)
+    out = m.generate(g["wav"], int(g["sr"]), 48000, timestep=int(g["steps"]), eps=eps).cpu()
+    ref = torch.from_numpy(g["ref_final"])
+    eng = m._engine()
+    voc = eng.vocoder(dev(g["ref_mel"])).cpu()
+    refv = torch.from_numpy(g["ref_vocoder"])
+    e_fin, e_voc = float((out - ref).abs().max()), float((voc - refv).abs().max())
+    print(f"big fp32 {name}: final max-abs {e_fin:.3g}, vocoder(ref mel) max-abs {e_voc:.3g} (|voc| max {float(refv.abs().max()):.3f})")
+    assert out.shape == ref.shape and torch.isfinite(out).all()
+    assert e_voc <= 1e-4
+    assert e_fin <= 1e-4
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("name", BIG)
+def test_big_config_16bit_golden(cuda_device, name, precision):
+    """16-bit tensor-core path on the timed configuration: SNR >= 40 dB and (fp16) LSD <= 0.05 dB against the
+    reference's fp32 output, before AND after the post-processing (which splices the exact low band)."""
+    m, g = _big_model(name, precision)
+    eps = _big_eps(g)
+    out = m.generate(g["wav"], int(g["sr"]), 48000, timestep=int(g["steps"]), eps=eps).cpu()
+    ref = torch.from_numpy(g["ref_final"])
+    eng = m._engine()
+    voc = eng.vocoder(dev(g["ref_mel"])).cpu()
+    refv = torch.from_numpy(g["ref_vocoder"])
+    s_f, l_f, s_v, l_v = snr_db(ref, out), lsd_db(ref, out), snr_db(refv, voc), lsd_db(refv, voc)
+    print(f"big {precision} {name}: final SNR {s_f:.1f} dB LSD {l_f:.3f} dB | vocoder(ref mel) SNR {s_v:.1f} dB LSD {l_v:.3f} dB")
+    assert torch.isfinite(out).all() and torch.isfinite(voc).all()
+    assert s_v >= 40.0 and s_f >= 40.0
+    if precision == "fp16":
+        assert l_v <= 0.05 and l_f <= 0.05
+
+
+def test_big_config_batch64_matches_single(cuda_device):
+    """The path bench.py times: B = 64 (sequential AMP branches, accumulate / acc_src / out16 epilogues, bn = 256 tiles,
+    8 x 128-row sub-tiles, > 2^31-byte buffers) -- clip i of the batch against its own B = 1 run, and clip 0 against the
+    reference golden."""
+    m, g = _big_model("big_c1_10s_basic_midpoint", "fp16")
+    eng = m._engine()
+    B, n_in, sr = 64, int(g["wav"].shape[0]), int(g["sr"])
+    N = g["ref_mel"].shape[1]
+    wavs = [g["wav"]] + [synth_speech(n_in, sr, seed=900 + i) for i in range(1, 4)]
+    wavs = [wavs[i % 4] for i in range(B)]
+    gen = torch.Generator().manual_seed(5)
+    eps = [_big_eps(g)[0]] + [torch.randn((N, 256), generator=gen) for _ in range(B - 1)]
+    outs = m.generate_batch(wavs, sr, 48000, timestep=int(g["steps"]), eps=eps)
+    outs = [o.cpu() for o in outs]
+    assert all(torch.isfinite(o).all() for o in outs)
+    ref = torch.from_numpy(g["ref_final"])
+    s0, l0 = snr_db(ref, outs[0]), lsd_db(ref, outs[0])
+    print(f"B=64 clip 0 vs reference golden: SNR {s0:.1f} dB LSD {l0:.3f} dB")
+    assert s0 >= 40.0 and l0 <= 0.05
+    worst = 1e9
+    for i in (0, 1, 31, 62, 63):
+        single = m.generate(wavs[i], sr, 48000, timestep=int(g["steps"]), eps=eps[i]).cpu()
+        worst = min(worst, snr_db(single, outs[i]))
+    print(f"B=64 clip i vs its own B=1 run: worst SNR {worst:.1f} dB")
+    assert worst >= 55.0
+    del eng
+
+
+# ------------------------------------------------------------------ ADVICE r1: stale rows of a longer clip
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_shorter_clip_after_longer_in_same_bucket(cuda_device, precision):
+    """N = 102 then N = 100 frames: stage-0 L = 510 then 500 share a 128-row bucket; the second run must not read the
+    first clip's rows [500, 510) as zero padding.  Compared with a fresh engine, eager and CUDA-graph paths."""
+    g = load_golden("gen_basic_midpoint")
+    sd, vcfg = golden_weights(g)
+
+    def fresh():
+        m = FlowHighSR.from_random(vcfg, device="cuda:0", precision=precision)
+        m.load_state_dict(sd)
+        return m.cuda()
+    long_wav, short_wav = synth_speech(102 * 160, 16000, seed=1), synth_speech(100 * 160, 16000, seed=2)
+    e_long = torch.randn((1, 102, 256), generator=torch.Generator().manual_seed(1))
+    e_short = torch.randn((1, 100, 256), generator=torch.Generator().manual_seed(2))
+    clean = fresh()
+    clean.cuda_graphs = False
+    want = clean.generate(short_wav, 16000, 48000, eps=e_short).cpu()
+    for graphs in (False, True):
+        m = fresh()
+        m.cuda_graphs, m.cuda_graph_min_hits = graphs, 1
+        m.generate(long_wav, 16000, 48000, eps=e_long)
+        got = m.generate(short_wav, 16000, 48000, eps=e_short).cpu()
+        assert torch.equal(got, want), (graphs, float((got - want).abs().max()))
+        m.generate(long_wav, 16000, 48000, eps=e_long)
+        got = m.generate(short_wav, 16000, 48000, eps=e_short).cpu()  # graph replays alternate between the two shapes
+        assert torch.equal(got, want), (graphs, float((got - want).abs().max()))
+
+
+def test_cuda_graph_cache_is_bounded(cuda_device):
+    g = load_golden("gen_basic_midpoint")
+    sd, vcfg = golden_weights(g)
+    m = FlowHighSR.from_random(vcfg, device="cuda:0", precision="fp16")
+    m.load_state_dict(sd)
+    m = m.cuda()
+    m.cuda_graph_cache_size, m.cuda_graph_min_hits = 2, 2
+    for rep in range(2):
+        for n in (8000, 8160, 8320, 8480):
+            out = m.generate(synth_speech(n, 16000, seed=n), 16000, 48000)
+            assert torch.isfinite(out).all()
+    assert len(m._graphs) <= 2
+    m.generate(synth_speech(8000, 16000, seed=1), 16000, 48000)  # first sighting of a shape runs eagerly: no capture
+    eng = m._engine()
+    eng._buf_cap = 1  # every buffer of an older call becomes evictable
+    before = len(eng._bufs)
+    m.generate(synth_speech(9000, 16000, seed=1), 16000, 48000)
+    assert len(eng._bufs) < 2 * before  # the 8000-sample shapes were evicted, not kept beside the new ones
+
+
+# ------------------------------------------------------------------ VERDICT r1 #2: fp16 range guard
+def test_fp16_overflow_is_reported_not_silent(cuda_device):
+    """Weights x30 and Snake beta -> small push tensor-core operands beyond 65504: the fp16 path must either stay finite
+    and correct or raise; bf16 (fp32 range) and fp32 must run.  The reference only prints on NaN (flow.py:256-267)."""
+    g = load_golden("voc_resblock1_snakebeta")
+    sd, vcfg = golden_weights(g)
+    hot = {k: v.clone() for k, v in sd.items()}
+    for k in hot:
+        if ".vocoder." in k and k.endswith(".weight") and ("resblocks" in k or "ups" in k):
+            hot[k] = hot[k] * 30.0
+        if k.endswith("act.beta") or k.endswith("activation_post.beta"):
+            hot[k] = hot[k] - 9.0  # logscale: beta = exp(.) -> 1/beta ~ 8000 x larger
+    mel = torch.from_numpy(g["mel"])
+    ref = model.vocoder_forward(hot, vcfg, mel).squeeze(1)
+    assert torch.isfinite(ref).all()
+    m16 = FlowHighSR.from_random(vcfg, device="cuda:0", precision="fp16")
+    m16.load_state_dict(hot)
+    m16 = m16.cuda()
+    with pytest.raises(FloatingPointError):
+        m16.sample(cond=mel, time_steps=1, decode_to_audio=True)
+    m16.overflow_check = "off"
+    out = m16.sample(cond=mel, time_steps=1, decode_to_audio=True)  # unchecked: still no exception, caller's risk
+    assert out.shape[-1] == mel.shape[1] * 480
+    # the same model with benign weights does not trip the guard
+    ok = FlowHighSR.from_random(vcfg, device="cuda:0", precision="fp16")
+    ok.load_state_dict(sd)
+    assert torch.isfinite(ok.cuda().sample(cond=mel, time_steps=1)).all()
+    # fp32 range formats run the hot weights: the vocoder alone against the oracle
+    e32 = Engine(hot, vcfg, device="cuda:0", precision="fp32")
+    out32 = e32.vocoder(mel.cuda()).cpu()
+    assert torch.isfinite(out32).all() and snr_db(ref, out32) >= 60.0
+
+
+# ------------------------------------------------------------------ SURVEY 8f row 1 pinned against the reference
+@pytest.mark.parametrize("variant", ["cfg", "mix", "mel_pp", "cfg_mix_pp"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_sample_variants_reference_golden(cuda_device, variant, precision):
+    """`sample()` with cond_scale != 1, independent_cfm_mix and mel_pp through the public API, against the mel the
+    unmodified reference produced (tests/golden/make_golden.py:sample_variants_case)."""
+    spec = {"cfg": dict(cfm_method="basic_cfm", ode="midpoint", sigma=0.0, kw=dict(cond_scale=1.7, time_steps=2)),
+            "mix": dict(cfm_method="independent_cfm_mix", ode="euler", sigma=1e-4, kw=dict(time_steps=2)),
+            "mel_pp": dict(cfm_method="independent_cfm_adaptive", ode="euler", sigma=1e-4, kw=dict(time_steps=1, mel_pp=True)),
+            "cfg_mix_pp": dict(cfm_method="independent_cfm_mix", ode="midpoint", sigma=1e-4,
+                               kw=dict(cond_scale=0.6, time_steps=1, mel_pp=True))}[variant]
+    g = load_golden("sample_variants")
+    sd, vcfg = golden_weights(g)
+    m = FlowHighSR.from_random(vcfg, device="cuda:0", precision=precision, sigma=spec["sigma"], cfm_method=spec["cfm_method"],
+                               torchdiffeq_ode_method=spec["ode"])
+    m.load_state_dict(sd)
+    m = m.cuda()
+    out = m.sample(cond=torch.from_numpy(g["cond"]), decode_to_audio=False, cfm_method=spec["cfm_method"],
+                   eps=torch.from_numpy(g["eps"]), **spec["kw"]).cpu()
+    ref, ref64 = torch.from_numpy(g["ref_mel_" + variant]), torch.from_numpy(g["f64_mel_" + variant])
+    floor = float((ref - ref64).abs().max())
+    e64 = float((out - ref64).abs().max())
+    print(f"sample[{variant}] {precision}: max-abs vs fp64 {e64:.3g} (reference's own fp32 {floor:.3g}), SNR vs reference "
+          f"{snr_db(ref, out):.1f} dB")
+    if precision == "fp32":
+        assert e64 <= 3 * floor + 1e-4
+    else:
+        assert snr_db(ref, out) >= 40.0
+
+
+def test_masks_and_stereo_are_rejected(cuda_device, f32_model):
+    f32_model, _ = f32_model
+    x = torch.zeros(1, 10, 256)
+    with pytest.raises(NotImplementedError):
+        f32_model.flowhigh.forward_with_cond_scale(x, times=0.5, cond=x, self_attn_mask=torch.ones(1, 10, dtype=torch.bool))
+    with pytest.raises(NotImplementedError):
+        f32_model.sample(cond=x, cond_mask=torch.ones(1, 10, dtype=torch.bool))
+    with pytest.raises(ValueError):
+        f32_model.generate(np.zeros((2, 8000), np.float32), 16000)
+
+
+def test_sample_passes_std_through(cuda_device, f32_model):
+    """cfm_superresolution.py:180-183: (std_1, std_2) are used when BOTH are given, else (1, sigma)."""
+    f32_model, _ = f32_model
+    g = load_golden("gen_c1_adaptive_euler")
+    cond, eps = torch.from_numpy(np.ascontiguousarray(g["ref_cond_mel"])), torch.from_numpy(g["eps"])
+    f32_model.set_cfm_method("independent_cfm_adaptive")
+    try:
+        eng = f32_model._engine()
+        a = f32_model.sample(cond=cond, time_steps=1, decode_to_audio=False, std_1=0.9, std_2=0.3, eps=eps).cpu()
+        b = eng.sample_mel(cond.cuda(), eps.cuda(), steps=1, ode_method=f32_model.odeint_kwargs["method"],
+                           cfm_method="independent_cfm_adaptive", sigma=0.0, std_1=0.9, std_2=0.3).cpu()
+        c = f32_model.sample(cond=cond, time_steps=1, decode_to_audio=False, std_2=0.3, eps=eps).cpu()  # one given: ignored
+        d = f32_model.sample(cond=cond, time_steps=1, decode_to_audio=False, eps=eps).cpu()
+        assert torch.equal(a, b) and torch.equal(c, d) and not torch.equal(a, c)
+    finally:
+        f32_model.set_cfm_method("basic_cfm")

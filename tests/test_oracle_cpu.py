@@ -68,6 +68,18 @@ def test_mel_filterbank_structure():
     assert np.array_equal(dense, b) and length.max() <= 33
 
 
+def test_mel_filterbank_pinned_against_torchaudio():
+    """librosa is not installable offline, so `librosa.filters.mel` (melvoco.py:64-70) is restated; torchaudio's
+    independent Slaney implementation pins the restatement and the engine's table (fp32 rounding apart)."""
+    import torchaudio
+    fb = torchaudio.functional.melscale_fbanks(1025, 20.0, 24000.0, 256, 48000, norm="slaney", mel_scale="slaney").T.numpy()
+    a = dsp.mel_filterbank()
+    b = tables.mel_filterbank_dense()
+    assert np.abs(a - fb).max() <= 1e-6 and np.abs(b - fb).max() <= 1e-6  # peak weight 6.2e-2
+    # same support: the only disagreement allowed is an edge tap below fp32 resolution of the bin frequencies
+    assert int(((a > 0) != (fb > 0)).sum()) <= 2 and a[(a > 0) != (fb > 0)].max(initial=0.0) <= 1e-6
+
+
 @pytest.mark.parametrize("sr", [8000, 24000])
 def test_logmel_golden(sr):
     g = load_golden("frontend")
@@ -234,3 +246,29 @@ def test_convnext_variant_pinned_against_reference():
     assert float((v64.float() - torch.from_numpy(g["ref_vfield_t025"])).abs().max()) <= 1e-4
     mel = model.cfm_sample_mel(sd, cond, x, steps=2, ode_method="euler", cfm_method="basic_cfm", sigma=0.0)
     assert float((mel - torch.from_numpy(g["ref_mel"])).abs().max()) <= 1e-4
+
+
+SAMPLE_VARIANTS = {  # tests/golden/make_golden.py:sample_variants_case
+    "cfg": dict(cfm_method="basic_cfm", ode_method="midpoint", sigma=0.0, steps=2, cond_scale=1.7),
+    "mix": dict(cfm_method="independent_cfm_mix", ode_method="euler", sigma=1e-4, steps=2),
+    "mel_pp": dict(cfm_method="independent_cfm_adaptive", ode_method="euler", sigma=1e-4, steps=1, mel_pp=True),
+    "cfg_mix_pp": dict(cfm_method="independent_cfm_mix", ode_method="midpoint", sigma=1e-4, steps=1, cond_scale=0.6,
+                       mel_pp=True),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(SAMPLE_VARIANTS))
+def test_sample_variants_pinned_against_reference(variant):
+    """CFG (flow.py:165-178), independent_cfm_mix (cfm_superresolution.py:232-237) and mel_pp (:278-279): the oracle's
+    fp64 result against the mel the unmodified reference's sample() produced (its fp32 rounding is the only gap)."""
+    g = load_golden("sample_variants")
+    sd, vcfg = golden_weights(g)
+    cond, eps = torch.from_numpy(g["cond"]), torch.from_numpy(g["eps"])
+    assert [model.mel_cutoff_bin(cond[i]) for i in range(cond.shape[0])] == g["cuts"].tolist()
+    sd64 = {k: v.double() for k, v in sd.items()}
+    out = model.cfm_sample_mel(sd64, cond.double(), eps.double(), **SAMPLE_VARIANTS[variant]).float()
+    ref = torch.from_numpy(g["ref_mel_" + variant])
+    d = (out - ref).abs()
+    # guided sampling from pure noise amplifies the reference's fp32 attention noise (logits reach +-640): mean 3e-4
+    tol_max, tol_mean = (2e-2, 1e-3) if variant == "cfg" else (1e-4, 5e-6)
+    assert float(d.max()) <= tol_max and float(d.mean()) <= tol_mean, (float(d.max()), float(d.mean()))
