@@ -59,6 +59,233 @@ __device__ __forceinline__ void sm_mma(float (&d)[4], uint32_t a0, uint32_t a1, 
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
 }
 
+// ---- pieces shared by the standalone kernel (snake_mma_cta) and the fused conv prologue (tc_conv.cu) ----------------
+
+// fp16 taps by ERROR FEEDBACK instead of round-to-nearest (one thread): within each polyphase branch (even / odd taps)
+// the taps are rounded in order of decreasing magnitude and every rounding error is carried into the next, finer-grained
+// tap, so the branch sums (the DC gains) stay exact to ~2^-20.  On low-pass signals the response error of the rounded
+// filters drops from -66 dB (round-to-nearest) to -83 dB (CPU experiment).
+// s_taps[0, 12): up-filter taps (2 f), [12, 24): down-filter taps (f).
+template <bool SPLIT_F>
+__device__ __forceinline__ void snake_mma_make_taps(const float* __restrict__ filt, float* s_taps) {
+  for (int w = 0; w < 2; ++w) {
+    const float scale = w ? 1.0f : 2.0f;
+    for (int ph = 0; ph < 2; ++ph) {
+      unsigned done = 0;
+      float carry = 0.f;
+      for (int n = 0; n < 6; ++n) {
+        int best = -1;
+        float bm = -1.f;
+        for (int c = 0; c < 6; ++c) {
+          const float m = fabsf(__ldg(filt + 2 * c + ph));
+          if (!((done >> c) & 1u) && m > bm) bm = m, best = c;
+        }
+        done |= 1u << best;
+        const float v = scale * __ldg(filt + 2 * best + ph) + carry;
+        const float h = SPLIT_F ? v : __half2float(__float2half_rn(v));  // the tap-split mode keeps exact taps
+        carry = v - h;
+        s_taps[12 * w + 2 * best + ph] = h;
+      }
+    }
+  }
+}
+
+// Toeplitz B fragments (k16 x n8, "col") of one thread: reg r holds k-slots 2q + 8r, 2q + 8r + 1 of column n = g
+struct SnakeFrags {
+  uint32_t bu[2][2], bul[2][2], bd[3][2], bdl[3][2];
+};
+template <bool IN16>
+__device__ __forceinline__ void snake_mma_frags(const float* s_taps, int lane, SnakeFrags& F) {
+  const int g = lane >> 2, q = lane & 3;
+  auto tap = [&](int idx, float scale) -> float {  // scale 2 = up filter, 1 = down filter
+    return (idx >= 0 && idx < 12) ? s_taps[(scale == 2.0f ? 0 : 12) + idx] : 0.f;
+  };
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    // up n-block e of a 16-up-sample block starting at input step T: up-sample m = 2T + 8e + n from the input steps
+    // T - 8 + ko (e = 0) or T + ko (e = 1), ko = q + 8r (slot 2q + 8r) and q + 4 + 8r (slot 2q + 8r + 1); ko = slot
+    // for the ldmatrix-fed fp16 input
+    const int base = e ? 13 : 21;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int ko0 = IN16 ? 2 * q + 8 * r : q + 8 * r, ko1 = IN16 ? ko0 + 1 : ko0 + 4;
+      const float v0 = tap(g + base - 2 * ko0, 2.0f), v1 = tap(g + base - 2 * ko1, 2.0f);
+      sm_split(v0, v1, F.bu[e][r], F.bul[e][r]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    // down block: output Q + n from the up-samples 2Q + 16 (d - 1) + c, c = k-slot (identity map)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int c0 = 2 * q + 8 * r;
+      const float v0 = tap(16 * (d - 1) + c0 - 2 * g + 5, 1.0f), v1 = tap(16 * (d - 1) + c0 + 1 - 2 * g + 5, 1.0f);
+      sm_split(v0, v1, F.bd[d][r], F.bdl[d][r]);
+    }
+  }
+}
+
+// One warp, one unit: the 2 x (8 NB) outputs q0 .. q0 + 16 NB - 1 of the 8 channels of chunk `ch`.
+//   xw : shared-memory window of the unit, row 0 = time q0 - kHalo, 16 NB + 2 kHalo rows of 8 channels
+//        (fp32 rows of 32 bytes, or fp16 rows of 16 bytes when IN16); rows [lo, hi) relative to xw exist (the replicate
+//        patch may read a clamped row from a neighbour's part of a shared window)
+//   yt : shared-memory output image, row 0 = time q0, 16-byte rows [time][8 ch] fp16
+// edge: the unit touches t < 0 or t >= L (replicate clamps apply).  Rows of the image with t >= L are computed from the
+// clamped signal (finite) and must be ignored / overwritten by the caller.
+template <bool SPLIT_X, bool SPLIT_F, int NB, bool IN16>
+__device__ __forceinline__ void snake_mma_unit(const SnakeFrags& F, float* xw, unsigned char* yt, int q0, int L, int ch,
+                                               const float* __restrict__ sn_a, const float* __restrict__ sn_inv_b,
+                                               const float* __restrict__ sn_filt, bool edge, int lo, int hi, int lane,
+                                               Guard16& guard) {
+  using G = SnakeMmaGeom<NB>;
+  const int g = lane >> 2, q = lane & 3;
+  if (edge) {
+    // replicate-pad the rows this warp reads: t < 0 <- x[0], t >= L <- x[L-1] (a neighbour warp may write the same
+    // values into the shared halo rows)
+    for (int i = lane; i < (G::kWarpRows + 2 * G::kHalo) * 2; i += 32) {
+      const int r = i >> 1, h = i & 1;
+      const int t = q0 - G::kHalo + r;
+      const int tc = min(max(t, 0), L - 1);
+      if (tc != t) {
+        const int rc = tc - (q0 - G::kHalo);
+        if (rc >= lo && rc < hi) {
+          if (IN16) {  // 16-byte rows: two 8-byte halves
+            const uint2* w16 = reinterpret_cast<const uint2*>(xw);
+            reinterpret_cast<uint2*>(xw)[r * 2 + h] = w16[rc * 2 + h];
+          } else {
+            *reinterpret_cast<float4*>(&xw[r * 8 + h * 4]) = *reinterpret_cast<const float4*>(&xw[rc * 8 + h * 4]);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  {
+    const int cg = ch * 8 + g;
+    const float alv = 2.0f * __ldg(sn_a + cg), hib = 0.5f * __ldg(sn_inv_b + cg);
+    const float2 al2 = make_float2(alv, alv), nhib2 = make_float2(-hib, -hib);
+    // window row of unit row r is r + kHalo; input block jx of half h covers window rows h kSeg + 8 jx + 8 ...
+    const float* xp = xw + q * 8 + g;
+    // stmatrix row addresses: lanes 0-7 = rows of half A, lanes 8-15 = rows of half B (others ignored by .x2)
+    const uint32_t st_base = sw_u32(yt) + (uint32_t)((lane & 7) + ((lane >> 3) & 1) * G::kSeg) * 16u;
+    uint32_t xh[NB + 2][2], xl[NB + 2][2];  // input blocks jx = -1 .. NB at index jx + 1
+    auto load_x = [&](int jx) {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float x0 = xp[(8 * jx + 8) * 8 + h * G::kSeg * 8], x1 = xp[(8 * jx + 12) * 8 + h * G::kSeg * 8];
+        if (SPLIT_X) sm_split(x0, x1, xh[jx + 1][h], xl[jx + 1][h]);
+        else xh[jx + 1][h] = sm_pack(x0, x1);
+      }
+    };
+    // up n-block (j, e): the 8 up-samples 2 (q0 + 8 j) + 8 e + n, both halves, into dd
+    // fp16 input: lane l addresses row (l & 7) of matrix l >> 3: {half A, half B} x {first, second 8 input steps}
+    const uint32_t lm_base = sw_u32(xw) + (uint32_t)((lane & 7) + ((lane >> 3) & 1) * G::kSeg + (lane >> 4) * 8) * 16u;
+    auto up_mma = [&](int j, int e, float (&dd)[4]) {
+      if (IN16) {
+        const int k0 = (e ? 8 * j : 8 * j - 8) + G::kHalo;  // first window row (relative to this unit's half A)
+        uint32_t a0, a1, a2, a3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
+                     : "r"(lm_base + (uint32_t)(k0 * 16)));
+        sm_mma(dd, a0, a1, a2, a3, F.bu[e][0], F.bu[e][1], 0.f, 0.f, 0.f, 0.f);
+        if (SPLIT_F) sm_mma(dd, a0, a1, a2, a3, F.bul[e][0], F.bul[e][1], dd[0], dd[1], dd[2], dd[3]);
+        return;
+      }
+      const int p = (e ? j : j - 1) + 1, n = p + 1;
+      sm_mma(dd, xh[p][0], xh[p][1], xh[n][0], xh[n][1], F.bu[e][0], F.bu[e][1], 0.f, 0.f, 0.f, 0.f);
+      if (SPLIT_X) sm_mma(dd, xl[p][0], xl[p][1], xl[n][0], xl[n][1], F.bu[e][0], F.bu[e][1], dd[0], dd[1], dd[2], dd[3]);
+      if (SPLIT_F) sm_mma(dd, xh[p][0], xh[p][1], xh[n][0], xh[n][1], F.bul[e][0], F.bul[e][1], dd[0], dd[1], dd[2], dd[3]);
+    };
+    auto snake2 = [&](float u0, float u1) -> uint32_t {
+      const float2 u = make_float2(u0, u1);
+      const float2 z = sw_fmul2(u, al2);
+      const float2 c = make_float2(__cosf(z.x), __cosf(z.y));
+      const float2 s = sw_ffma2(c, nhib2, u);
+      return sm_pack(s.x, s.y);
+    };
+    // Software pipeline, in-order issue in mind (mma.sync are volatile asm, i.e. issued in source order): in step j
+    //   1. the up-stage MMAs of step j + 1 are issued,
+    //   2. the snake of step j runs on accumulators issued one step earlier        -> A fragment U_j,
+    //   3. U_j is scattered into the three down blocks it touches (j - 1: last term, j: middle, j + 1: first), three
+    //      independent MMAs; every down accumulator is next touched one whole step later.
+    float dd[2][2][4];  // [step parity][e][acc]
+    float y[3][4];      // down accumulators of blocks i, at index i % 3
+    if (!IN16) {
+      load_x(-1);
+      load_x(0);
+      if (NB >= 1) load_x(1);
+    }
+    up_mma(-1, 1, dd[0][1]);
+#pragma unroll
+    for (int j = -1; j <= NB; ++j) {
+      const int cur = (j + 1) & 1, nxt = cur ^ 1;
+      if (!IN16 && j + 3 <= NB) load_x(j + 3);  // consumed by the MMAs issued in the next step
+      if (j + 1 <= NB) {
+        up_mma(j + 1, 0, dd[nxt][0]);
+        if (j + 1 < NB) up_mma(j + 1, 1, dd[nxt][1]);
+      }
+      uint32_t U[4];  // A fragment of the 16 up-samples of step j
+      if (j >= 0) U[0] = snake2(dd[cur][0][0], dd[cur][0][1]), U[1] = snake2(dd[cur][0][2], dd[cur][0][3]);
+      else U[0] = U[1] = 0u;  // up-samples below 2 q0 - 8 only meet zero weights
+      if (j < NB) U[2] = snake2(dd[cur][1][0], dd[cur][1][1]), U[3] = snake2(dd[cur][1][2], dd[cur][1][3]);
+      else U[2] = U[3] = 0u;
+      if (j >= 1) {  // last term of down block j - 1, then store it
+        float (&yy)[4] = y[(j - 1) % 3];
+        sm_mma(yy, U[0], U[1], U[2], U[3], F.bd[2][0], F.bd[2][1], yy[0], yy[1], yy[2], yy[3]);
+        if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], F.bdl[2][0], F.bdl[2][1], yy[0], yy[1], yy[2], yy[3]);
+      }
+      if (j >= 0 && j < NB) {
+        float (&yy)[4] = y[j % 3];
+        sm_mma(yy, U[0], U[1], U[2], U[3], F.bd[1][0], F.bd[1][1], yy[0], yy[1], yy[2], yy[3]);
+        if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], F.bdl[1][0], F.bdl[1][1], yy[0], yy[1], yy[2], yy[3]);
+      }
+      if (j + 1 < NB) {
+        float (&yy)[4] = y[(j + 1) % 3];
+        sm_mma(yy, U[0], U[1], U[2], U[3], F.bd[0][0], F.bd[0][1], hib, hib, hib, hib);
+        if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], F.bdl[0][0], F.bdl[0][1], yy[0], yy[1], yy[2], yy[3]);
+      }
+      if (j >= 1) {
+        // outputs q0 + 8 i + {2 q, 2 q + 1} of channel g, both halves: the accumulator tile is an 8 x 8 [seq][time]
+        // fragment per half, stored TRANSPOSED ([time][8 ch] rows of 16 bytes) by one stmatrix
+        const int i = j - 1;
+        const float (&yy)[4] = y[i % 3];
+        const uint32_t r0 = pack16(yy[0], yy[1], 1), r1 = pack16(yy[2], yy[3], 1);
+        guard.see(r0, 1);
+        guard.see(r1, 1);
+        asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(st_base + (uint32_t)(8 * i * 16)),
+                     "r"(r0), "r"(r1)
+                     : "memory");
+      }
+    }
+  }
+  if (edge) {  // the s~ clamp changes outputs 0..2 and L-3..L-1 only: recompute those in scalar fp32
+    __syncwarp();
+    for (int w = lane; w < 48; w += 32) {
+      const int c = w & 7, o = w >> 3;
+      const int qq = o < 3 ? o : L - 6 + o;
+      if (qq >= q0 && qq < q0 + G::kWarpRows && qq < L && (o < 3 || qq >= 3)) {
+        const int cc = ch * 8 + c;
+        const float alv = 2.0f * __ldg(sn_a + cc), hib = 0.5f * __ldg(sn_inv_b + cc);
+        float acc = hib;
+        for (int k = 0; k < 12; ++k) {
+          const int m = min(max(2 * qq + k - 5, 0), 2 * L - 1);
+          const int ihi = (m + 5) >> 1;
+          float u = 0.f;
+          for (int t6 = 0; t6 < 6; ++t6) {
+            const int i = ihi - t6;
+            const int ic = min(max(i, 0), L - 1);
+            const int xi = (ic - q0 + G::kHalo) * 8 + c;
+            const float xv = IN16 ? __half2float(reinterpret_cast<const __half*>(xw)[xi]) : xw[xi];
+            u = fmaf(2.0f * __ldg(sn_filt + (m + 5 - 2 * i)), xv, u);
+          }
+          acc = fmaf(__ldg(sn_filt + k), u - hib * __cosf(alv * u), acc);
+        }
+        *reinterpret_cast<__half*>(yt + (size_t)(qq - q0) * 16 + 2 * c) = __float2half_rn(acc);
+      }
+    }
+  }
+}
+
 // One CTA of 4 warps walks tiles (batch, chunk, kRows outputs) cta, cta + nctas, ...  The input window of a tile is
 // shared (one cp.async.bulk against a "full" mbarrier); everything else is per warp: each warp computes its own
 // 2 x kSeg rows, stores them with its own bulk store and releases the window through a shared-memory counter -- the
@@ -84,30 +311,7 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     released[0] = released[1] = 0;
-    // fp16 taps by ERROR FEEDBACK instead of round-to-nearest: within each polyphase branch (even / odd taps) the
-    // taps are rounded in order of decreasing magnitude and every rounding error is carried into the next, finer-grained
-    // tap, so the branch sums (the DC gains) stay exact to ~2^-20.  On low-pass signals the response error of the
-    // rounded filters drops from -66 dB (round-to-nearest) to -83 dB (CPU experiment).
-    for (int w = 0; w < 2; ++w) {
-      const float scale = w ? 1.0f : 2.0f;
-      for (int ph = 0; ph < 2; ++ph) {
-        unsigned done = 0;
-        float carry = 0.f;
-        for (int n = 0; n < 6; ++n) {
-          int best = -1;
-          float bm = -1.f;
-          for (int c = 0; c < 6; ++c) {
-            const float m = fabsf(__ldg(S.filt + 2 * c + ph));
-            if (!((done >> c) & 1u) && m > bm) bm = m, best = c;
-          }
-          done |= 1u << best;
-          const float v = scale * __ldg(S.filt + 2 * best + ph) + carry;
-          const float h = SPLIT_F ? v : __half2float(__float2half_rn(v));  // the tap-split mode keeps exact taps
-          carry = v - h;
-          s_taps[12 * w + 2 * best + ph] = h;
-        }
-      }
-    }
+    snake_mma_make_taps<SPLIT_F>(S.filt, s_taps);
   }
   // rows a clipped copy does not fill must hold finite values (they only ever meet zero filter weights)
   for (int i = tid; i < 2 * kXB / 16; i += 32 * G::kWarps) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -132,36 +336,8 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
                  : "memory");
   };
 
-  const int g = lane >> 2, q = lane & 3;
-  // ---- Toeplitz B fragments (k16 x n8, "col"): reg r holds k-slots 2q + 8r, 2q + 8r + 1 of column n = g
-  auto tap = [&](int idx, float scale) -> float {  // scale 2 = up filter, 1 = down filter
-    return (idx >= 0 && idx < 12) ? s_taps[(scale == 2.0f ? 0 : 12) + idx] : 0.f;
-  };
-  uint32_t bu[2][2], bul[2][2], bd[3][2], bdl[3][2];
-#pragma unroll
-  for (int e = 0; e < 2; ++e) {
-    // up n-block e of a 16-up-sample block starting at input step T: up-sample m = 2T + 8e + n from the input steps
-    // T - 8 + ko (e = 0) or T + ko (e = 1), ko = q + 8r (slot 2q + 8r) and q + 4 + 8r (slot 2q + 8r + 1); ko = slot
-    // for the ldmatrix-fed fp16 input
-    const int base = e ? 13 : 21;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int ko0 = IN16 ? 2 * q + 8 * r : q + 8 * r, ko1 = IN16 ? ko0 + 1 : ko0 + 4;
-      const float v0 = tap(g + base - 2 * ko0, 2.0f), v1 = tap(g + base - 2 * ko1, 2.0f);
-      sm_split(v0, v1, bu[e][r], bul[e][r]);
-    }
-  }
-#pragma unroll
-  for (int d = 0; d < 3; ++d) {
-    // down block: output Q + n from the up-samples 2Q + 16 (d - 1) + c, c = k-slot (identity map)
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int c0 = 2 * q + 8 * r;
-      const float v0 = tap(16 * (d - 1) + c0 - 2 * g + 5, 1.0f), v1 = tap(16 * (d - 1) + c0 + 1 - 2 * g + 5, 1.0f);
-      sm_split(v0, v1, bd[d][r], bdl[d][r]);
-    }
-  }
-
+  SnakeFrags F;
+  snake_mma_frags<IN16>(s_taps, lane, F);
   // Overflow guard: the fp16 roundings of the input and of the snake samples do NOT saturate, so an out-of-range value
   // becomes inf, turns the outputs it reaches into inf / NaN, and is caught where the outputs are packed (saturating).
   Guard16 guard;
@@ -184,150 +360,10 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
     if (buf) ph1 ^= 1; else ph0 ^= 1;
     float* xt = buf ? xs1 : xs0;
     unsigned char* yt = ys0 + (size_t)buf * G::kWarpYBytes;
-    if (edge && active) {
-      // replicate-pad the rows this warp reads: t < 0 <- x[0], t >= L <- x[L-1] (a neighbour warp may write the same
-      // values into the shared halo rows)
-      for (int i = lane; i < (G::kWarpRows + 2 * G::kHalo) * 2; i += 32) {
-        const int r = ssA + (i >> 1), h = i & 1;
-        const int t = qt - G::kHalo + r;
-        const int tc = min(max(t, 0), S.L - 1);
-        if (tc != t) {
-          const int rc = tc - (qt - G::kHalo);
-          if (rc >= 0 && rc < G::kXRows) {
-            if (IN16) {  // 16-byte rows: two 8-byte halves
-              const uint2* w16 = reinterpret_cast<const uint2*>(xt);
-              reinterpret_cast<uint2*>(xt)[r * 2 + h] = w16[rc * 2 + h];
-            } else {
-              *reinterpret_cast<float4*>(&xt[r * 8 + h * 4]) = *reinterpret_cast<const float4*>(&xt[rc * 8 + h * 4]);
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
     if (active) {
-      const int cg = ch * 8 + g;
-      const float alv = 2.0f * __ldg(S.a + cg), hib = 0.5f * __ldg(S.inv_b + cg);
-      const float2 al2 = make_float2(alv, alv), nhib2 = make_float2(-hib, -hib);
-      // window row of item row r is r + kHalo; input block jx of half h covers window rows h kSeg + 8 jx + 8 ...
-      const float* xp = xt + (ssA + q) * 8 + g;
-      // stmatrix row addresses: lanes 0-7 = rows of half A, lanes 8-15 = rows of half B (others ignored by .x2)
-      const uint32_t st_base = sw_u32(yt) + (uint32_t)((lane & 7) + ((lane >> 3) & 1) * G::kSeg) * 16u;
-      uint32_t xh[NB + 2][2], xl[NB + 2][2];  // input blocks jx = -1 .. NB at index jx + 1
-      auto load_x = [&](int jx) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const float x0 = xp[(8 * jx + 8) * 8 + h * G::kSeg * 8], x1 = xp[(8 * jx + 12) * 8 + h * G::kSeg * 8];
-          if (SPLIT_X) sm_split(x0, x1, xh[jx + 1][h], xl[jx + 1][h]);
-          else xh[jx + 1][h] = sm_pack(x0, x1);
-        }
-      };
-      // up n-block (j, e): the 8 up-samples 2 (q0 + 8 j) + 8 e + n, both halves, into dd
-      // fp16 input: lane l addresses row (l & 7) of matrix l >> 3: {half A, half B} x {first, second 8 input steps}
-      const uint32_t lm_base = sw_u32(xt) + (uint32_t)(ssA + (lane & 7) + ((lane >> 3) & 1) * G::kSeg + (lane >> 4) * 8) * 16u;
-      auto up_mma = [&](int j, int e, float (&dd)[4]) {
-        if (IN16) {
-          const int k0 = (e ? 8 * j : 8 * j - 8) + G::kHalo;  // first window row (relative to this warp's half A)
-          uint32_t a0, a1, a2, a3;
-          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3)
-                       : "r"(lm_base + (uint32_t)(k0 * 16)));
-          sm_mma(dd, a0, a1, a2, a3, bu[e][0], bu[e][1], 0.f, 0.f, 0.f, 0.f);
-          if (SPLIT_F) sm_mma(dd, a0, a1, a2, a3, bul[e][0], bul[e][1], dd[0], dd[1], dd[2], dd[3]);
-          return;
-        }
-        const int p = (e ? j : j - 1) + 1, n = p + 1;
-        sm_mma(dd, xh[p][0], xh[p][1], xh[n][0], xh[n][1], bu[e][0], bu[e][1], 0.f, 0.f, 0.f, 0.f);
-        if (SPLIT_X) sm_mma(dd, xl[p][0], xl[p][1], xl[n][0], xl[n][1], bu[e][0], bu[e][1], dd[0], dd[1], dd[2], dd[3]);
-        if (SPLIT_F) sm_mma(dd, xh[p][0], xh[p][1], xh[n][0], xh[n][1], bul[e][0], bul[e][1], dd[0], dd[1], dd[2], dd[3]);
-      };
-      auto snake2 = [&](float u0, float u1) -> uint32_t {
-        const float2 u = make_float2(u0, u1);
-        const float2 z = sw_fmul2(u, al2);
-        const float2 c = make_float2(__cosf(z.x), __cosf(z.y));
-        const float2 s = sw_ffma2(c, nhib2, u);
-        return sm_pack(s.x, s.y);
-      };
-      // Software pipeline, in-order issue in mind (mma.sync are volatile asm, i.e. issued in source order): in step j
-      //   1. the up-stage MMAs of step j + 1 are issued,
-      //   2. the snake of step j runs on accumulators issued one step earlier        -> A fragment U_j,
-      //   3. U_j is scattered into the three down blocks it touches (j - 1: last term, j: middle, j + 1: first), three
-      //      independent MMAs; every down accumulator is next touched one whole step later.
-      float dd[2][2][4];  // [step parity][e][acc]
-      float y[3][4];      // down accumulators of blocks i, at index i % 3
-      if (!IN16) {
-        load_x(-1);
-        load_x(0);
-        if (NB >= 1) load_x(1);
-      }
-      up_mma(-1, 1, dd[0][1]);
-#pragma unroll
-      for (int j = -1; j <= NB; ++j) {
-        const int cur = (j + 1) & 1, nxt = cur ^ 1;
-        if (!IN16 && j + 3 <= NB) load_x(j + 3);  // consumed by the MMAs issued in the next step
-        if (j + 1 <= NB) {
-          up_mma(j + 1, 0, dd[nxt][0]);
-          if (j + 1 < NB) up_mma(j + 1, 1, dd[nxt][1]);
-        }
-        uint32_t U[4];  // A fragment of the 16 up-samples of step j
-        if (j >= 0) U[0] = snake2(dd[cur][0][0], dd[cur][0][1]), U[1] = snake2(dd[cur][0][2], dd[cur][0][3]);
-        else U[0] = U[1] = 0u;  // up-samples below 2 q0 - 8 only meet zero weights
-        if (j < NB) U[2] = snake2(dd[cur][1][0], dd[cur][1][1]), U[3] = snake2(dd[cur][1][2], dd[cur][1][3]);
-        else U[2] = U[3] = 0u;
-        if (j >= 1) {  // last term of down block j - 1, then store it
-          float (&yy)[4] = y[(j - 1) % 3];
-          sm_mma(yy, U[0], U[1], U[2], U[3], bd[2][0], bd[2][1], yy[0], yy[1], yy[2], yy[3]);
-          if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], bdl[2][0], bdl[2][1], yy[0], yy[1], yy[2], yy[3]);
-        }
-        if (j >= 0 && j < NB) {
-          float (&yy)[4] = y[j % 3];
-          sm_mma(yy, U[0], U[1], U[2], U[3], bd[1][0], bd[1][1], yy[0], yy[1], yy[2], yy[3]);
-          if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], bdl[1][0], bdl[1][1], yy[0], yy[1], yy[2], yy[3]);
-        }
-        if (j + 1 < NB) {
-          float (&yy)[4] = y[(j + 1) % 3];
-          sm_mma(yy, U[0], U[1], U[2], U[3], bd[0][0], bd[0][1], hib, hib, hib, hib);
-          if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], bdl[0][0], bdl[0][1], yy[0], yy[1], yy[2], yy[3]);
-        }
-        if (j >= 1) {
-          // outputs q0 + 8 i + {2 q, 2 q + 1} of channel g, both halves: the accumulator tile is an 8 x 8 [seq][time]
-          // fragment per half, stored TRANSPOSED ([time][8 ch] rows of 16 bytes) by one stmatrix
-          const int i = j - 1;
-          const float (&yy)[4] = y[i % 3];
-          const uint32_t r0 = pack16(yy[0], yy[1], 1), r1 = pack16(yy[2], yy[3], 1);
-          guard.see(r0, 1);
-          guard.see(r1, 1);
-          asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(st_base + (uint32_t)(8 * i * 16)),
-                       "r"(r0), "r"(r1)
-                       : "memory");
-        }
-      }
-    }
-    if (edge && active) {  // the s~ clamp changes outputs 0..2 and L-3..L-1 only: recompute those in scalar fp32
-      __syncwarp();
-      for (int w = lane; w < 48; w += 32) {
-        const int c = w & 7, o = w >> 3;
-        const int qq = o < 3 ? o : S.L - 6 + o;
-        if (qq >= qt + ssA && qq < qt + ssA + G::kWarpRows && qq < S.L && (o < 3 || qq >= 3)) {
-          const int cc = ch * 8 + c;
-          const float alv = 2.0f * __ldg(S.a + cc), hib = 0.5f * __ldg(S.inv_b + cc);
-          float acc = hib;
-          for (int k = 0; k < 12; ++k) {
-            const int m = min(max(2 * qq + k - 5, 0), 2 * S.L - 1);
-            const int ihi = (m + 5) >> 1;
-            float u = 0.f;
-            for (int t6 = 0; t6 < 6; ++t6) {
-              const int i = ihi - t6;
-              const int ic = min(max(i, 0), S.L - 1);
-              const int xi = (ic - qt + G::kHalo) * 8 + c;
-              const float xv = IN16 ? __half2float(reinterpret_cast<const __half*>(xt)[xi]) : xt[xi];
-              u = fmaf(2.0f * __ldg(S.filt + (m + 5 - 2 * i)), xv, u);
-            }
-            acc = fmaf(__ldg(S.filt + k), u - hib * __cosf(alv * u), acc);
-          }
-          *reinterpret_cast<__half*>(yt + (size_t)(qq - qt - ssA) * 16 + 2 * c) = __float2half_rn(acc);
-        }
-      }
+      float* xw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(xt) + (size_t)ssA * (IN16 ? 16 : 32));
+      snake_mma_unit<SPLIT_X, SPLIT_F, NB, IN16>(F, xw, yt, qt + ssA, S.L, ch, S.a, S.inv_b, S.filt, edge, -ssA,
+                                                 G::kXRows - ssA, lane, guard);
     }
     // generic-proxy accesses of this warp (window reads / patches, output image writes) before the async proxy's
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -103,12 +103,14 @@ class MelVoco(_Tree):
     def encode(self, audio: torch.Tensor) -> torch.Tensor:
         eng = self._owner()._engine()
         eng.new_call()
+        eng.status_begin()
         return eng.encode(audio.to(self._owner().device, torch.float32).contiguous())
 
     @_on_model_device
     def decode(self, mel: torch.Tensor) -> torch.Tensor:
         eng = self._owner()._engine()
         eng.new_call()
+        eng.status_begin()  # sub-boundary calls leave the check to the caller: model._check_status(engine)
         return eng.vocoder(mel.to(eng.device, torch.float32).contiguous()).unsqueeze(1)
 
 
@@ -149,6 +151,7 @@ class FLowHigh(_Tree):
             raise NotImplementedError("cond_mask / self_attn_mask are not supported by the B200 attention kernels")
         eng = self._owner()._engine()
         eng.new_call()
+        eng.status_begin()
         x = x.to(eng.device, torch.float32).contiguous()
         cond = cond.to(eng.device, torch.float32).contiguous()
         zero = torch.zeros_like(x)

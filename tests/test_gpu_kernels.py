@@ -892,36 +892,48 @@ def test_cuda_graph_cache_is_bounded(cuda_device):
 
 
 # ------------------------------------------------------------------ fp16 range guard
-def test_fp16_overflow_is_reported_not_silent(cuda_device):
-    """Weights x30 and Snake beta -> small push tensor-core operands beyond 65504: the fp16 path must either stay finite
-    and correct or raise; bf16 (fp32 range) and fp32 must run.  The reference only prints on NaN (flow.py:256-267)."""
+@pytest.mark.parametrize("case", ["weights", "beta"])
+def test_fp16_overflow_is_reported_not_silent(cuda_device, case):
+    """conv_pre weights x 30000, or Snake beta -> e^-10.5 beta (1/beta 36000 x larger), push tensor-core operands beyond
+    65504 while the fp32 computation stays finite (oracle: conv inputs reach 3e5 / 1e5).  The fp16 path must raise
+    instead of returning a silently saturated result; bf16 (fp32 range) and fp32 must run it; conv_pre x 300 (operands
+    up to 3e3) must pass the guard.  The reference only prints on NaN (flow.py:256-267)."""
     g = load_golden("voc_resblock1_snakebeta")
     sd, vcfg = golden_weights(g)
-    hot = {k: v.clone() for k, v in sd.items()}
-    for k in hot:
-        if ".vocoder." in k and k.endswith(".weight") and ("resblocks" in k or "ups" in k):
-            hot[k] = hot[k] * 30.0
-        if k.endswith("act.beta") or k.endswith("activation_post.beta"):
-            hot[k] = hot[k] - 9.0  # logscale: beta = exp(.) -> 1/beta ~ 8000 x larger
+    pre = "flowhigh.audio_enc_dec.vocoder.conv_pre.weight"
+
+    def variant(scale, dbeta):
+        hot = {k: v.clone() for k, v in sd.items()}
+        hot[pre] = hot[pre] * scale
+        for k in hot:
+            if k.endswith("act.beta") or k.endswith("activation_post.beta"):
+                hot[k] = hot[k] + dbeta  # logscale parameters: beta = exp(.)
+        return hot
+    hot = variant(30000.0, 0.0) if case == "weights" else variant(1.0, -10.5)
     mel = torch.from_numpy(g["mel"])
-    ref = model.vocoder_forward(hot, vcfg, mel).squeeze(1)
+    ref = model.vocoder_forward(hot, vcfg, mel)
     assert torch.isfinite(ref).all()
-    m16 = FlowHighSR.from_random(vcfg, device="cuda:0", precision="fp16")
-    m16.load_state_dict(hot)
-    m16 = m16.cuda()
+
+    def build(weights, precision):
+        m = FlowHighSR.from_random(vcfg, device="cuda:0", precision=precision)
+        m.load_state_dict(weights)
+        return m.cuda()
+    m16 = build(hot, "fp16")
     with pytest.raises(FloatingPointError):
-        m16.sample(cond=mel, time_steps=1, decode_to_audio=True)
+        m16.flowhigh.audio_enc_dec.decode(mel)  # sub-boundary calls do not check ...
+        m16._check_status(m16._engine())        # ... until the caller asks
+    with pytest.raises(FloatingPointError):
+        m16.sample(cond=mel, time_steps=1, decode_to_audio=True)  # the public path checks by itself
     m16.overflow_check = "off"
-    out = m16.sample(cond=mel, time_steps=1, decode_to_audio=True)  # unchecked: still no exception, caller's risk
+    out = m16.sample(cond=mel, time_steps=1, decode_to_audio=True)  # unchecked: no exception, caller's risk
     assert out.shape[-1] == mel.shape[1] * 480
-    # the same model with benign weights does not trip the guard
-    ok = FlowHighSR.from_random(vcfg, device="cuda:0", precision="fp16")
-    ok.load_state_dict(sd)
-    assert torch.isfinite(ok.cuda().sample(cond=mel, time_steps=1)).all()
-    # fp32 range formats run the hot weights: the vocoder alone against the oracle
-    e32 = Engine(hot, vcfg, device="cuda:0", precision="fp32")
-    out32 = e32.vocoder(mel.cuda()).cpu()
-    assert torch.isfinite(out32).all() and snr_db(ref, out32) >= 60.0
+    for precision in ("bf16", "fp32"):
+        out = build(hot, precision).flowhigh.audio_enc_dec.decode(mel).cpu()
+        assert torch.isfinite(out).all()
+        if precision == "fp32":
+            assert snr_db(ref, out) >= 40.0
+    mild = build(variant(300.0, 0.0), "fp16")
+    assert torch.isfinite(mild.sample(cond=mel, time_steps=1, decode_to_audio=True)).all()  # in range: guard silent
 
 
 # ------------------------------------------------------------------ SURVEY 8f row 1 pinned against the reference
