@@ -33,6 +33,7 @@ class TcConvArgs(C.Structure):
         ("x_f32", _p), ("sn_a", _p), ("sn_inv_b", _p), ("sn_filt", _p),
         ("act", _i),
         ("acc_src", _p),
+        ("x_is_16", _i),
     ]
 
 
@@ -42,6 +43,7 @@ SIGNATURES = {
     "fh_last_error_string": (C.c_char_p, []),
     "fh_launch_count": (_i64, []),
     "fh_set_status_word": (_i, [_p]),
+    "fh_set_debug_word": (_i, [_p]),
     "fh_resample_poly_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "fh_scale_by_absmax_f32": (_i, [_p, _p, _p, _f, _i, _i, _p]),
     "fh_absmax_f32": (_i, [_p, _p, _i, _i, _p]),
@@ -66,7 +68,6 @@ SIGNATURES = {
     "fh_qknorm_rope_f32": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "fh_attention_f32": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _f, _p]),
     "fh_qknorm_rope_split": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
-    "fh_tc_conv_snake_dual": (_i, [C.POINTER(TcConvArgs), _p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _p]),
     "fh_attention_tc": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i, _p]),
     "fh_geglu_f32": (_i, [_p, _p, _i, _i64, _i, _i, _i, _p]),
     "fh_axpby_f32": (_i, [_p, _p, _f, _f, _p, _i64, _p]),

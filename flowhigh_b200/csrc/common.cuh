@@ -14,6 +14,9 @@ void count_launch(int n = 1);
 // device address of the caller's status word (fh_set_status_word, thread-local on the host; may be nullptr):
 // launchers of kernels that write 16-bit operands pass it on, see Guard16 below
 unsigned int* status_word();
+// debug word (fh_set_debug_word; pinned HOST memory survives a device trap): a bounded mbarrier wait that times out
+// writes (code | block << 8) there before trapping, so a protocol bug names the wait that hung
+unsigned int* err_word();
 
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();

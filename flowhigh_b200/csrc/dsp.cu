@@ -18,6 +18,8 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches += n; }
 static thread_local unsigned int* g_status = nullptr;
 unsigned int* status_word() { return g_status; }
+static thread_local unsigned int* g_errword = nullptr;
+unsigned int* err_word() { return g_errword; }
 }  // namespace fh
 
 extern "C" __attribute__((visibility("default"))) int fh_version(void) { return 1; }
@@ -25,6 +27,10 @@ extern "C" __attribute__((visibility("default"))) const char* fh_last_error_stri
 extern "C" __attribute__((visibility("default"))) int64_t fh_launch_count(void) { return (int64_t)fh::g_launches.load(); }
 extern "C" __attribute__((visibility("default"))) int fh_set_status_word(uint32_t* status) {
   fh::g_status = status;
+  return FH_OK;
+}
+extern "C" __attribute__((visibility("default"))) int fh_set_debug_word(uint32_t* word) {
+  fh::g_errword = word;
   return FH_OK;
 }
 

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include "common.cuh"
 #include "snake_worker.cuh"
+#include "snake_mma.cuh"
 
 namespace {
 
@@ -53,6 +54,7 @@ struct TcParams {
   int wrows;           // rows fetched per chunk window: 128*msub + (max_off - min_off)
   int arows_pad;       // rows reserved per chunk window in an A slot
   int stages, stage_bytes;
+  int empty_ring;       // number of "stage consumed" barriers the MMA issuer cycles through (= stages, or 8 in the fused kernel)
   int min_off[16];
   int tap_rel0[16];     // (offset of tap 0) - min_off of the phase
   int tap_step[16];     // offset(tap j+1) - offset(tap j) when the taps of a phase form an arithmetic sequence
@@ -62,12 +64,13 @@ struct TcParams {
   int tap_off[kMaxTapOff];
   unsigned int* err_flag;
   unsigned int* status;  // overflow / NaN status word of the caller (common.cuh Guard16) or nullptr
-  // fused anti-aliased snake A-producer (tc_conv_snake_kernel): raw fp32 activations + per-channel parameters
-  const float* xf;
+  int m_stride, m_valid;  // output rows a tile advances by / keeps (128 msub unless the A window is aligned: fused snake)
+  // fused anti-aliased snake prologue (tc_conv_snakepro_kernel): raw activations (fp32 or fp16 rows) + snake parameters
+  const void* xf;
   const float* sn_a;
   const float* sn_ib;
   const float* sn_filt;
-  int xrows, x_stages, xs_bytes, rows_per_chunk;
+  int x_stages, xs_bytes, xs_off, rows_per_chunk, pro_nb, snake_warps;
 };
 
 // ------------------------------------------------------------------------------ PTX wrappers
@@ -81,6 +84,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_n(uint32_t bar, uint32_t n) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(n) : "memory");
 }
 __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -99,7 +105,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigne
   const long long t0 = clock64();
   while (!mbar_try(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
-      if (err_flag) atomicExch(err_flag, (unsigned)code);
+      if (err_flag) {
+        atomicExch(err_flag, (unsigned)code | (blockIdx.x << 8) | ((threadIdx.x >> 5) << 24));
+        __threadfence_system();
+      }
       __trap();
     }
   }
@@ -261,6 +270,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
     const TileCoord tc = decode_tile(P, tile);
     const int n_base = tc.nt * P.bn;
     const int t_base = tc.mt * tile_rows + r;
+    const int t_lim = min(P.L, tc.mt * tile_rows + P.m_valid);  // rows this tile keeps
     const long long res_b = (long long)tc.b * P.res_batch;
     const long long out_b = (long long)tc.b * P.out_batch;
     const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)as * acc_cols;
@@ -274,7 +284,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
       if (!use_res || gi >= n_groups_total) return;
       int sub, c0, t;
       group_coords(gi, sub, c0, t);
-      load_res16(P, res_b + ((long long)t * P.P + tc.p) * P.res_row, n_base + c0, t < P.L, rr);
+      load_res16(P, res_b + ((long long)t * P.P + tc.p) * P.res_row, n_base + c0, t < t_lim, rr);
     };
     auto issue_ld = [&](int gi, uint32_t (&v)[16]) {
       if (gi >= n_groups_total) return;
@@ -285,7 +295,7 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
     auto finish = [&](int gi, const uint32_t (&v)[16], const float (&rr)[16]) {
       int sub, c0, t;
       group_coords(gi, sub, c0, t);
-      if (n_base + c0 >= P.Cout || t >= P.L) return;
+      if (n_base + c0 >= P.Cout || t >= t_lim) return;
       const long long orow = (long long)t * P.P + tc.p;
       if (P.geglu) {
         // columns (2i, 2i+1) = (x_i, gate_i) -> gelu(gate) * x ; 16 columns -> one 8-channel chunk
@@ -416,6 +426,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
     const TileCoord tc = decode_tile(P, tile);
     const int n_base = tc.nt * P.bn;
     const int t_base = tc.mt * tile_rows + r;
+    const int t_lim = min(P.L, tc.mt * tile_rows + P.m_valid);  // rows this tile keeps
     const long long res_b = (long long)tc.b * P.res_batch + (long long)tc.p * P.res_row;
     const long long out_b = (long long)tc.b * P.out_batch + (long long)tc.p * P.out_row;
     const long long res_rs = (long long)P.P * P.res_row, out_rs = (long long)P.P * P.out_row;
@@ -432,7 +443,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
       int c0, t;
       coords(gi, c0, t);
       const int n0 = n_base + c0;
-      if (n0 >= P.Cout || t >= P.L) return;
+      if (n0 >= P.Cout || t >= t_lim) return;
       const bool two = n0 + 8 < P.Cout;
       if (HAS_RES) {
         const float* q = resp + res_b + (long long)t * res_rs + (long long)(n0 >> 3) * P.res_chunk;
@@ -455,7 +466,7 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
       int c0, t;
       coords(gi, c0, t);
       const int n0 = n_base + c0;
-      if (n0 >= P.Cout || t >= P.L) return;
+      if (n0 >= P.Cout || t >= t_lim) return;
       const long long oidx = out_b + (long long)t * out_rs + (long long)(n0 >> 3) * P.out_chunk;
       float* dst = outp + oidx;
 #pragma unroll
@@ -537,7 +548,8 @@ __device__ __forceinline__ void mma_role(const TcParams& P, uint32_t tmem_base, 
                                          uint32_t tfull0, uint32_t tempty0, uint32_t stage0, uint32_t a_chunk_bytes,
                                          const int* s_off) {
   const bool leader = elect_one();
-  int stage = 0, phase = 0, as = 0, aphase = 0;
+  int stage = 0, phase = 0, as = 0, aphase = 0, estage = 0;
+  const int EB = P.empty_ring;
   const int S = P.stages, msub = P.msub, ntaps = P.ntaps, tg = P.tg, n_groups = P.n_groups, ci_pairs = P.ci_pairs;
   const int kc = P.kc;
   const uint32_t bn = (uint32_t)P.bn;
@@ -595,10 +607,11 @@ __device__ __forceinline__ void mma_role(const TcParams& P, uint32_t tmem_base, 
             a_base_lo += a_slot_u;
             b_lo += (uint32_t)nt_g * b_step;
           }
-          umma_commit(empty0 + 8 * stage);  // frees the smem stage when these MMAs retire
+          umma_commit(empty0 + 8 * estage);  // frees the smem stage when these MMAs retire
         }
         accum = 1;
         __syncwarp();
+        if (++estage == EB) estage = 0;
         if (++stage == S) {
           stage = 0;
           phase ^= 1;
@@ -656,37 +669,36 @@ __device__ __forceinline__ void producer_role(const TcParams& P, uint32_t full0,
 
 __device__ __forceinline__ void epilogue_dispatch(const TcParams& P, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                                   int lg, int hf, int lane, int tile_rows, uint32_t acc_cols,
-                                                  const float* s_bias) {
+                                                  const float* s_bias, int gstep = 2) {
   if (P.fast_epi) {
     if (P.out_is_16 && P.accumulate)  // last AMP branch of a stage: mean of the branches written as the next stage's operand
-      epilogue_fast<true, true, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+      epilogue_fast<true, true, true>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
     else if (P.out_is_16)
-      epilogue_fast<false, false, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+      epilogue_fast<false, false, true>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
     else if (P.res != nullptr && P.accumulate)
-      epilogue_fast<true, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+      epilogue_fast<true, true>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
     else if (P.res != nullptr)
-      epilogue_fast<true, false>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+      epilogue_fast<true, false>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
     else if (P.accumulate)
-      epilogue_fast<false, true>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+      epilogue_fast<false, true>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
     else
-      epilogue_fast<false, false>(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols, s_bias);
+      epilogue_fast<false, false>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
   } else {
-    epilogue_role(P, tmem_base, tfull0, tempty0, lg, hf, 2, lane, tile_rows, acc_cols);
+    epilogue_role(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols);
   }
 }
 
 // Per-CTA setup shared by the conv kernels: mbarriers, tap-offset table, alpha * bias table, zeroed partner windows.
 // The caller allocates TMEM and issues the __syncthreads that publishes all of it.
-__device__ __forceinline__ void conv_cta_setup(const TcParams& P, unsigned char* smem, int nthreads, int epi_warps) {
+__device__ __forceinline__ void conv_cta_setup(const TcParams& P, unsigned char* smem, int nthreads, int epi_warps,
+                                               int full_count = 1) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
   const uint32_t tfull0 = empty0 + 8 * kMaxStages, tempty0 = tfull0 + 16;
   const int S = P.stages;
   if (threadIdx.x == 0) {
-    for (int i = 0; i < S; ++i) {
-      mbar_init(full0 + 8 * i, 1);
-      mbar_init(empty0 + 8 * i, 1);
-    }
+    for (int i = 0; i < S; ++i) mbar_init(full0 + 8 * i, full_count);
+    for (int i = 0; i < P.empty_ring; ++i) mbar_init(empty0 + 8 * i, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(tfull0 + 8 * i, 1);
       mbar_init(tempty0 + 8 * i, epi_warps);
@@ -756,126 +768,114 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   }
 }
 
-// ------------------------------------------------------------------------------ fused snake + conv
-// Same implicit GEMM, but the A operand is produced IN the kernel: conv(Activation1d(x)) without the 16-bit
-// activation ever touching HBM (the HBM-bound C <= 128 stages drop from 28 to 20 bytes per element-pair).
-// Warp roles (20 warps): 0 = bulk-copy producer of raw fp32 activation windows (own ring of x_stages slots),
-// 1 = MMA issuer, 2 = bulk-copy producer of weight slots, 3 = idle, 4..7 = epilogue, 8..19 = snake warps.
-// One smem stage = one ci-pair (16 channels) x all taps x (256 + span) rows.  The snake warps turn the raw window
-// into the 16-bit K-major chunk image of the A slot in TWO phases with the 2x-rate signal staged in shared memory,
-// so that nothing is computed twice (the register-blocked standalone kernel recomputes a 10-sample halo per thread):
-//   phase 1: position q -> s[2q], s[2q+1] = snake(up-filter(x))      (12 packed FFMA2 + 2 x (mul, 2 cos, fma) per pair)
-//   phase 2: row t      -> y[t] = sum_k f[k] s[2t-5+k]  -> 16-bit    (12 packed FFMA2 per channel pair)
-// A thread owns a channel PAIR and kSR consecutive positions / rows in both phases (sliding register window);
-// kSR odd and the plane paddings below make every 64-bit shared-memory access of a half-warp conflict free.
-// Register budget (setmaxnreg): producers 24, epilogue 168, snake 96 per thread.
-__device__ __forceinline__ float2 tc_ffma2(float2 a, float2 b, float2 c) {
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
-                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-  return *reinterpret_cast<float2*>(&rd);
-}
-__device__ __forceinline__ float2 tc_fmul2(float2 a, float2 b) {
-  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
-  return *reinterpret_cast<float2*>(&rd);
-}
+// ------------------------------------------------------------------------------ fused snake prologue + conv
+// conv(Activation1d(x)) in ONE kernel for the HBM-bound stages (Cin <= 128, one N tile): the 16-bit activated operand
+// is produced in shared memory by eight "snake" warps running the Toeplitz-MMA snake (snake_mma.cuh) and consumed by
+// tcgen05.mma from there -- it never touches HBM (an AMPBlock1 unit drops from 24 to 16 bytes per element).
+//
+// Warp roles (20 warps): 0 = bulk-copy producer of raw activation windows (fp32 rows, or the fp16 rows the first
+// convolution of the unit wrote: IN16), 1 = MMA issuer + TMEM, 2 = bulk-copy producer of weight slots, 3 = idle,
+// 4..11 = epilogue (same specialised epilogues as tc_conv_kernel), 12..19 = snake warps.
+// One smem stage = one ci-pair (2 x 8 channels) x all taps; its A slot holds 128 msub window rows per chunk.
+// Work unit of a snake warp = 8 channels x 128 window rows (SnakeMmaGeom<8>): 2 chunks x msub units per stage.
+// Units are numbered globally (tile, chunk, sub); warp w takes units w, w + 8, ...; all synchronisation is by
+// mbarrier (x ring: one slot per unit window; stage full = weights landed + every unit of the stage written), so the
+// eight warps drift freely over several stages and never meet at a block barrier.
+// The A window is ALIGNED (exactly 128 msub rows starting at t0 + min_off): a tile therefore yields
+// m_valid = 128 msub - span output rows and tiles advance by m_valid rows; the discarded accumulator rows cost tensor
+// time these stages do not need, while the snake warps never compute a row twice within a tile.
+// Conv zero padding: image rows outside [0, L) are zeroed after the (replicate-clamped) snake wrote them.
+constexpr int kProThreads = 640;
+constexpr int kProSnakeWarps = 12;
+constexpr int kProEpiWarps = 4;
+constexpr int kProXMax = 24;  // x-ring slots
 
-constexpr int kFusedThreads = 640;
-constexpr int kSnakeWarps = 12;
-constexpr int kSnakeThreads = kSnakeWarps * 32;
-constexpr int kSnakeGroups = kSnakeThreads / 8;   // 48 row groups x 8 channel pairs
-constexpr int kSR = 7;                            // positions / rows per snake thread (odd)
-constexpr int kSnakeCap = kSnakeGroups * kSR;     // 336 >= (256 + span) + 6
-constexpr int kXrPad = kSnakeCap + 6;             // raw window rows per chunk plane  (== 2 mod 4)
-constexpr int kSrPad = 2 * kSnakeCap + 13;        // 2x-rate rows per chunk plane      (== 1 mod 4)
-constexpr int kArPad = kSnakeCap + 4;             // A-slot rows per chunk plane       (== 4 mod 8)
-static_assert(kXrPad % 4 == 2 && kSrPad % 4 == 1 && kArPad % 8 == 4 && (kSR & 1), "bank-conflict-free paddings");
-
-__global__ void __launch_bounds__(kFusedThreads, 1) tc_conv_snake_kernel(const __grid_constant__ TcParams P) {
+// kProNB: snake unit = 8 channels x 16 kProNB window rows (128 or 256)
+template <bool IN16, int kProNB>
+__global__ void __launch_bounds__(kProThreads, 1) tc_conv_snakepro_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  using G = fh::SnakeMmaGeom<kProNB>;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
   const uint32_t tfull0 = empty0 + 8 * kMaxStages, tempty0 = tfull0 + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxStages + 4));
-  const uint32_t xfull0 = full0 + 192, xempty0 = full0 + 224;
+  const uint32_t xfull0 = smem_u32(smem + P.xs_off + P.x_stages * P.xs_bytes), xempty0 = xfull0 + 8 * kProXMax;  // behind the x ring
   int* s_off = reinterpret_cast<int*>(smem + 512);
-  float* s_filt = reinterpret_cast<float*>(smem + 768);
-  float2* s_par = reinterpret_cast<float2*>(smem + 1024);  // [Cin <= 128] (2 alpha, 1/(2 beta)) per channel
-  // [2048 ..): x ring | 2x-rate buffer | A/W stages
-  const uint32_t xs_bytes = 2u * kXrPad * 32u;
-  const uint32_t sbuf_bytes = 2u * kSrPad * 32u;
-  unsigned char* xs_ptr = smem + 2048;
-  unsigned char* sbuf_ptr = xs_ptr + (size_t)P.x_stages * xs_bytes;
-  const uint32_t xs0 = smem_u32(xs_ptr);
-  const uint32_t stage0 = smem_u32(sbuf_ptr + sbuf_bytes);
+  float* s_taps = reinterpret_cast<float*>(smem + 768);
+  const uint32_t stage0 = smem_u32(smem + 1024);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int S = P.stages, XS = P.x_stages;
+  const int S = P.stages, XD = P.x_stages;
+  const int h = (128 * P.msub) / G::kWarpRows;     // units per chunk and tile
+  const int AU = P.ci_pairs * 2 * h;               // units per tile, dummies of an odd last pair included
+  const int nchunks = P.Cin >> 3;
+  const int RU = nchunks * h;                      // real units (= x windows) per tile
+  constexpr uint32_t kRowB = IN16 ? 16u : 32u;
+  constexpr int kWinRows = G::kWarpRows + 2 * G::kHalo;  // 144
+  unsigned char* xring = smem + P.xs_off;
+  const uint32_t xwin_bytes = (uint32_t)P.xs_bytes;
 
+  conv_cta_setup(P, smem, kProThreads, kProEpiWarps, 1 + 2 * h);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < S; ++i) {
-      mbar_init(full0 + 8 * i, 1 + kSnakeWarps);  // weight producer (expect_tx) + snake warps
-      mbar_init(empty0 + 8 * i, 1);
-    }
-    for (int i = 0; i < XS; ++i) {
+    for (int i = 0; i < XD; ++i) {
       mbar_init(xfull0 + 8 * i, 1);
-      mbar_init(xempty0 + 8 * i, kSnakeWarps);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(tfull0 + 8 * i, 1);
-      mbar_init(tempty0 + 8 * i, 4);
+      mbar_init(xempty0 + 8 * i, 1);
     }
     fence_barrier_init();
+    fh::snake_mma_make_taps<false>(P.sn_filt, s_taps);
   }
+  // window rows a clipped copy does not fill, and the 64 spare rows behind every A window, must hold finite values
+  for (uint32_t i = threadIdx.x; i < (uint32_t)XD * xwin_bytes / 16u; i += kProThreads)
+    reinterpret_cast<uint4*>(xring)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (uint32_t i = threadIdx.x; i < (uint32_t)S * (uint32_t)P.stage_bytes / 16u; i += kProThreads)
+    reinterpret_cast<uint4*>(smem + 1024)[i] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + P.ntaps) s_off[threadIdx.x - 64] = P.tap_off[threadIdx.x - 64] - P.min_off[0];
-  if (threadIdx.x >= 128 && threadIdx.x < 140) s_filt[threadIdx.x - 128] = __ldg(P.sn_filt + threadIdx.x - 128);
-  if (threadIdx.x >= 256 && threadIdx.x < 256 + 128) {
-    const int c = threadIdx.x - 256;
-    s_par[c] = c < P.Cin ? make_float2(2.0f * __ldg(P.sn_a + c), 0.5f * __ldg(P.sn_ib + c)) : make_float2(0.f, 0.f);
-  }
-  if (P.ci_odd) {  // the partner window of the last (single) chunk only has to be finite: zero it once
-    const uint32_t cb = (uint32_t)kArPad * 16u;
-    for (int st = 0; st < S; ++st) {
-      uint4* z = reinterpret_cast<uint4*>(sbuf_ptr + sbuf_bytes + (size_t)st * P.stage_bytes + cb);
-      for (uint32_t i = threadIdx.x; i < cb / 16u; i += kFusedThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   const uint32_t b_tap_bytes = (uint32_t)P.bn * 32u;
-  const uint32_t a_chunk_bytes = (uint32_t)kArPad * 16u;
+  const uint32_t a_chunk_bytes = (uint32_t)P.arows_pad * 16u;
   const uint32_t a_slot_bytes = 2u * a_chunk_bytes;
-  const uint32_t x_chunk_bytes = (uint32_t)kXrPad * 32u;  // one 8-channel fp32 window
-  const int tile_rows = 128 * P.msub;
   const uint32_t acc_cols = (uint32_t)(P.msub * P.bn);
   const int mn = P.min_off[0];
+  // Stage sseq reuses the slot of stage sseq - S: wait until the MMAs of THAT stage have retired.  The issuer commits
+  // stage k to barrier k % 8, so a waiter would have to run 8 stages (>= 16 units) ahead of the issuer to alias a
+  // parity -- the eight snake warps cannot (each finishes unit u - 8 before it starts unit u).
+  auto wait_stage_free = [&](int sseq) {
+    if (sseq < S) return;
+    const int d = sseq - S;  // empty_ring == 8
+    mbar_wait(empty0 + 8 * (uint32_t)(d & 7), (uint32_t)((d >> 3) & 1), P.err_flag, 7);
+  };
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (warp == 0) {
-      // ===================================================================== raw-activation producer
+      // ===================================================================== raw-activation window producer
       if (lane == 0) {
-        int xs = 0, xph = 0;
+        int xs = 0;
+        uint32_t xph = 0;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
           const TileCoord tc = decode_tile(P, tile);
-          const long long row = (long long)P.a_row0 + (long long)tc.mt * tile_rows + mn - 6;  // >= 0 (host check)
-          long long nrows = (long long)P.rows_per_chunk - row;  // stay inside this chunk's rows
-          if (nrows > P.xrows) nrows = P.xrows;
-          const float* x_base = P.xf + (long long)tc.b * P.a_batch + row * 8;
-          for (int cp = 0; cp < P.ci_pairs; ++cp) {
-            const bool pair = !(P.ci_odd && cp == P.ci_pairs - 1);
+          const int t_slot0 = tc.mt * P.m_stride + mn;
+          const unsigned char* xb = reinterpret_cast<const unsigned char*>(P.xf) + (long long)tc.b * P.a_batch * (kRowB / 8);
+          for (int rv = 0; rv < RU; ++rv) {
+            const int chunk = rv / h, sub = rv - chunk * h;
             mbar_wait(xempty0 + 8 * xs, xph ^ 1, P.err_flag, 5);
-            const uint32_t dst = xs0 + (uint32_t)xs * xs_bytes;
+            long long row = (long long)P.a_row0 + t_slot0 + sub * G::kWarpRows - G::kHalo;  // first window row in the chunk
+            int skip = row < 0 ? (int)(-row) : 0;                                          // rows before the buffer: replicate-patched
+            long long nrows = kWinRows - skip;
+            if (row + skip + nrows > P.rows_per_chunk) nrows = (long long)P.rows_per_chunk - row - skip;
             const uint32_t fb = xfull0 + 8 * xs;
-            mbar_expect_tx(fb, (pair ? 2u : 1u) * (uint32_t)nrows * 32u);
-            bulk_g2s(dst, x_base + (long long)(2 * cp) * P.a_chunk, (uint32_t)nrows * 32u, fb);
-            if (pair) bulk_g2s(dst + x_chunk_bytes, x_base + (long long)(2 * cp + 1) * P.a_chunk, (uint32_t)nrows * 32u, fb);
-            if (++xs == XS) {
+            if (nrows > 0) {
+              mbar_expect_tx(fb, (uint32_t)nrows * kRowB);
+              bulk_g2s(smem_u32(xring) + (uint32_t)xs * xwin_bytes + (uint32_t)skip * kRowB,
+                       xb + ((long long)chunk * P.a_chunk + (row + skip) * 8) * (kRowB / 8), (uint32_t)nrows * kRowB, fb);
+            } else {
+              mbar_arrive(fb);
+            }
+            if (++xs == XD) {
               xs = 0;
               xph ^= 1;
             }
@@ -885,21 +885,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tc_conv_snake_kernel(const _
     } else if (warp == 2) {
       // ===================================================================== weight producer
       if (lane == 0) {
-        int stage = 0, phase = 0;
+        int stage = 0, sseq = 0;
         for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-          const TileCoord tc = decode_tile(P, tile);
-          const __nv_bfloat16* w_base = P.w + ((long long)tc.nt * P.ci_pairs) * ((long long)P.ntaps * P.bn * 16);
-          for (int cp = 0; cp < P.ci_pairs; ++cp) {
-            mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 1);
+          for (int cp = 0; cp < P.ci_pairs; ++cp, ++sseq) {
+            wait_stage_free(sseq);
             const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
             const uint32_t fb = full0 + 8 * stage;
             mbar_expect_tx(fb, (uint32_t)P.ntaps * b_tap_bytes);
-            bulk_g2s(sa + a_slot_bytes, w_base + (long long)cp * P.ntaps * ((long long)P.bn * 16),
-                     (uint32_t)P.ntaps * b_tap_bytes, fb);
-            if (++stage == S) {
-              stage = 0;
-              phase ^= 1;
-            }
+            bulk_g2s(sa + a_slot_bytes, P.w + (long long)cp * P.ntaps * ((long long)P.bn * 16), (uint32_t)P.ntaps * b_tap_bytes, fb);
+            // odd last pair: its partner window (zeroed at setup, zero weights) has no snake units -- their arrivals are made here
+            if (P.ci_odd && cp == P.ci_pairs - 1) mbar_arrive_n(fb, (uint32_t)h);
+            if (++stage == S) stage = 0;
           }
         }
       }
@@ -907,206 +903,64 @@ __global__ void __launch_bounds__(kFusedThreads, 1) tc_conv_snake_kernel(const _
       // ===================================================================== MMA issuer (one stage = one ci-pair)
       mma_role(P, tmem_base, full0, empty0, tfull0, tempty0, stage0, a_chunk_bytes, s_off);
     }
-  } else if (warp < 8) {
-    // ===================================================================== epilogue (4 warps, one per lane group)
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
-    epilogue_role(P, tmem_base, tfull0, tempty0, warp & 3, 0, 1, lane, tile_rows, acc_cols);
+  } else if (warp < 4 + kProEpiWarps) {
+    // ===================================================================== epilogue (4 warps, one per lane group: in
+    // this kernel the snake warps, not the epilogue, set the pace -- ncu: the epilogue warps wait for accumulators)
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
+    epilogue_dispatch(P, tmem_base, tfull0, tempty0, warp & 3, 0, lane, P.m_stride, acc_cols,
+                      reinterpret_cast<const float*>(smem + 1024 + (size_t)P.stages * P.stage_bytes), 1);
   } else {
     // ===================================================================== snake warps
-    const int stid = threadIdx.x - 256;
-    const int pc = stid & 7, g = stid >> 3;       // channel pair (0..7 over the two chunks), row group (0..47)
-    const int csel = pc >> 2, pcl = pc & 3;
-    const int np = P.wrows + 6;                   // 2x-rate positions needed per window
-    int stage = 0, phase = 0, xs = 0, xph = 0;
-    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    const int sw = warp - 4 - kProEpiWarps;
+    if (sw >= P.snake_warps) goto done;  // (tiny shapes: fewer units per 8 stages than warps, see tc_plan)
+    fh::SnakeFrags F;
+    fh::snake_mma_frags<IN16>(s_taps, lane, F);
+    fh::Guard16 guard;
+    const int my_tiles = (P.total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int n_units = my_tiles * RU;  // < 2^31 (tc_plan)
+    // REAL units (= x windows) are dealt round-robin: warp w takes windows w, w + 8, ...  It has therefore consumed window
+    // n - 8 itself before it waits for window n, which keeps every parity wait below unambiguous (x ring of >= 8 slots
+    // filled in order; stage barriers cycling over 8 stages of >= 1 unit each).
+    for (int n = sw; n < n_units; n += P.snake_warps) {
+      const int tseq = n / RU, rv = n - tseq * RU;
+      const int chunk = rv / h, sub = rv - chunk * h;
+      const int pair = chunk >> 1, c = chunk & 1;
+      const int sseq = tseq * P.ci_pairs + pair;
+      const int slot = sseq % S;
+      const uint32_t fb = full0 + 8 * slot;
+      const int tile = (int)blockIdx.x + tseq * (int)gridDim.x;
       const TileCoord tc = decode_tile(P, tile);
-      const int t_slot0 = tc.mt * tile_rows + mn;  // time of A-slot row 0; position 0 is t_slot0 - 3, raw row 0 is t_slot0 - 6
-      const bool edge = (t_slot0 - 6 < 0) || (t_slot0 + P.wrows + 6 > P.L);
-      for (int cp = 0; cp < P.ci_pairs; ++cp) {
-        const bool active = !(P.ci_odd && cp == P.ci_pairs - 1 && csel == 1);
-        const int c0 = cp * 16 + csel * 8 + 2 * pcl;
-        const float2 par0 = s_par[c0], par1 = s_par[c0 + 1];
-        const float2 al2 = make_float2(par0.x, par1.x), hib = make_float2(par0.y, par1.y);
-        const float2 nhib = make_float2(-hib.x, -hib.y);
-        // ---------------- phase 1: raw window -> 2x-rate snake samples in shared memory
-        // Straight-line code, no per-position guards: positions / rows beyond the window compute on stale (finite or
-        // not, never consumed) shared memory and land in padding rows that nothing reads.
-        mbar_wait(xfull0 + 8 * xs, xph, P.err_flag, 6);
-        float2 xv[kSR + 6];
-        {
-          const float* xw = reinterpret_cast<const float*>(xs_ptr + (size_t)xs * xs_bytes + (size_t)csel * x_chunk_bytes) + 2 * pcl;
-          if (!edge) {
-#pragma unroll
-            for (int j = 0; j < kSR + 6; ++j) xv[j] = *reinterpret_cast<const float2*>(xw + (g * kSR + j) * 8);
-          } else {  // replicate pad: rows t < 0 read x[0], rows t >= L read x[L-1]
-#pragma unroll
-            for (int j = 0; j < kSR + 6; ++j) {
-              int t = t_slot0 - 6 + g * kSR + j;
-              t = min(max(t, 0), P.L - 1);
-              xv[j] = *reinterpret_cast<const float2*>(xw + (t - (t_slot0 - 6)) * 8);
-            }
-          }
-        }
+      const int q0 = tc.mt * P.m_stride + mn + sub * G::kWarpRows;  // time of the unit's first image row
+      const int xg = n / XD, xs = n - xg * XD;
+      const uint32_t xph = (uint32_t)(xg & 1);
+      unsigned char* yt = smem + 1024 + (size_t)slot * P.stage_bytes + (size_t)c * a_chunk_bytes + (size_t)sub * G::kWarpYBytes;
+      mbar_wait(xfull0 + 8 * xs, xph, P.err_flag, 6);          // the raw window has landed
+      wait_stage_free(sseq);                                   // the MMAs that last read this A slot have retired
+      const bool active = q0 < P.L && q0 + G::kWarpRows > 0;
+      const bool edge = (q0 - G::kHalo < 0) || (q0 + G::kWarpRows + G::kHalo > P.L);
+      if (active) {
+        float* xw = reinterpret_cast<float*>(xring + (size_t)xs * xwin_bytes);
+        fh::snake_mma_unit<false, false, kProNB, IN16>(F, xw, yt, q0, P.L, chunk, P.sn_a, P.sn_ib, P.sn_filt, edge, 0,
+                                                      kWinRows, lane, guard);
+      }
+      if (!active || edge) {  // conv zero padding: rows outside [0, L)
         __syncwarp();
-        if (lane == 0) mbar_arrive(xempty0 + 8 * xs);  // the raw window of this stage has been consumed
-        if (++xs == XS) {
-          xs = 0;
-          xph ^= 1;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kSnakeThreads) : "memory");  // phase 2 of the previous stage has read the 2x buffer
-        if (active) {
-          float fu[12];
-#pragma unroll
-          for (int k = 0; k < 12; ++k) fu[k] = 2.0f * s_filt[k];
-          float2 ue[kSR], uo[kSR];
-#pragma unroll
-          for (int j = 0; j < kSR; ++j) {
-            ue[j] = tc_fmul2(xv[j], make_float2(fu[11], fu[11]));       // d = -3
-            uo[j] = tc_fmul2(xv[j + 1], make_float2(fu[10], fu[10]));   // d = -2
-          }
-#pragma unroll
-          for (int d = -2; d <= 2; ++d) {
-#pragma unroll
-            for (int j = 0; j < kSR; ++j) ue[j] = tc_ffma2(xv[j + 3 + d], make_float2(fu[5 - 2 * d], fu[5 - 2 * d]), ue[j]);
-          }
-#pragma unroll
-          for (int d = -1; d <= 3; ++d) {
-#pragma unroll
-            for (int j = 0; j < kSR; ++j) uo[j] = tc_ffma2(xv[j + 3 + d], make_float2(fu[6 - 2 * d], fu[6 - 2 * d]), uo[j]);
-          }
-          float* sw = reinterpret_cast<float*>(sbuf_ptr + (size_t)csel * (kSrPad * 32)) + 2 * pcl + (2 * g * kSR) * 8;
-#pragma unroll
-          for (int j = 0; j < kSR; ++j) {
-            const float2 ze = tc_fmul2(ue[j], al2), zo = tc_fmul2(uo[j], al2);
-            const float2 ce = make_float2(__cosf(ze.x), __cosf(ze.y)), co = make_float2(__cosf(zo.x), __cosf(zo.y));
-            *reinterpret_cast<float2*>(sw + (2 * j) * 8) = tc_ffma2(ce, nhib, ue[j]);
-            *reinterpret_cast<float2*>(sw + (2 * j + 1) * 8) = tc_ffma2(co, nhib, uo[j]);
-          }
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(kSnakeThreads) : "memory");  // the 2x-rate buffer is complete
-        // ---------------- phase 2: down-filter -> 16-bit rows of the A slot
-        mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 7);  // the MMAs that last read this A slot retired
-        if (active) {
-          const float* sw = reinterpret_cast<const float*>(sbuf_ptr + (size_t)csel * (kSrPad * 32)) + 2 * pcl;
-          const int i0 = 2 * g * kSR + 1;  // buffer row i holds s[2 (t_slot0 - 3) + i]; row r needs i = 2r + 1 .. 2r + 12
-          float2 sv[2 * kSR + 10];
-          if (!edge) {
-#pragma unroll
-            for (int ii = 0; ii < 2 * kSR + 10; ++ii) sv[ii] = *reinterpret_cast<const float2*>(sw + (i0 + ii) * 8);
-          } else {  // replicate clamp of the 2x-rate signal: s[m < 0] = s[0], s[m > 2L-1] = s[2L-1]
-            const int mb = 2 * (t_slot0 - 3);
-#pragma unroll
-            for (int ii = 0; ii < 2 * kSR + 10; ++ii) {
-              int m = mb + i0 + ii;
-              m = min(max(m, 0), 2 * P.L - 1);
-              int i = m - mb;
-              i = min(max(i, 0), kSrPad - 1);
-              sv[ii] = *reinterpret_cast<const float2*>(sw + i * 8);
-            }
-          }
-          float2 acc[kSR];
-#pragma unroll
-          for (int j = 0; j < kSR; ++j) acc[j] = hib;
-#pragma unroll
-          for (int k = 0; k < 12; ++k) {
-            const float fk = s_filt[k];
-#pragma unroll
-            for (int j = 0; j < kSR; ++j) acc[j] = tc_ffma2(make_float2(fk, fk), sv[2 * j + k], acc[j]);
-          }
-          const uint32_t a_dst = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes + (uint32_t)csel * a_chunk_bytes +
-                                 (uint32_t)(g * kSR) * 16u + (uint32_t)pcl * 4u;
-          const int t0 = t_slot0 + g * kSR;
-          uint32_t hv[kSR];
-          if (P.fp16) {  // block-uniform
-#pragma unroll
-            for (int j = 0; j < kSR; ++j) hv[j] = fh::pack16(acc[j].x, acc[j].y, 1);
-          } else {
-#pragma unroll
-            for (int j = 0; j < kSR; ++j) hv[j] = fh::pack16(acc[j].x, acc[j].y, 0);
-          }
-#pragma unroll
-          for (int j = 0; j < kSR; ++j) {
-            const unsigned tt = (unsigned)(t0 + j);
-            const uint32_t v = tt < (unsigned)P.L ? hv[j] : 0u;  // conv zero padding outside [0, L)
-            asm volatile("st.shared.b32 [%0], %1;" ::"r"(a_dst + (uint32_t)j * 16u), "r"(v) : "memory");
-          }
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full0 + 8 * stage);
-        if (++stage == S) {
-          stage = 0;
-          phase ^= 1;
+        for (int r = lane; r < G::kWarpRows; r += 32) {
+          const int t = q0 + r;
+          if (t < 0 || t >= P.L) *reinterpret_cast<uint4*>(yt + (size_t)r * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // image writes (generic) before the MMA reads (async)
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(xempty0 + 8 * xs);
+        mbar_arrive(fb);
+      }
     }
+    guard.commit(P.status, 1);
   }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-// ------------------------------------------------------------------------------ dual kernel: conv || snake
-// The vocoder alternates a tensor-pipe / HBM-bound convolution with an FP32-pipe-bound anti-aliased snake; run back to
-// back, each leaves the other pipe of the SM idle (and streams could not make them co-resident: the conv CTA holds
-// most of the register file and shared memory).  This kernel is both at once, for two independent half-batches: the
-// ten conv warps of tc_conv_kernel (producer, MMA issuer, eight epilogue warps) work on half-batch A while two
-// 128-thread snake workers (snake_worker.cuh) walk the tiles of half-batch B.  Register budget via setmaxnreg:
-// producers 24, epilogue 128, snake 96.  The engine staggers the two half-batches by one operator so that every
-// launch pairs a conv with a snake.
-constexpr int kDualThreads = 640;  // warps 0..3 producer / MMA / 2 idle, 4..11 epilogue, 12..19 snake (2 workers)
-constexpr int kDualWorkers = 2;
-constexpr int kDualR = 11;         // snake outputs per thread (96-register budget)
-
-struct DualParams {
-  TcParams c;
-  fh::SnakeParams s;
-  int snake_off;   // byte offset of the snake workers' shared memory
-  int s_out_kind;  // 1 bf16, 2 fp16
-};
-
-__global__ void __launch_bounds__(kDualThreads, 1) tc_conv_snake_dual_kernel(const __grid_constant__ DualParams D) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  const TcParams& P = D.c;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
-  const uint32_t tfull0 = empty0 + 8 * kMaxStages, tempty0 = tfull0 + 16;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxStages + 4));
-  const uint32_t stage0 = smem_u32(smem + 1024);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  conv_cta_setup(P, smem, kDualThreads, 8);
-  if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  int* s_off = reinterpret_cast<int*>(smem + 512);
-  const uint32_t a_chunk_bytes = (uint32_t)P.arows_pad * 16u;
-  const int tile_rows = 128 * P.msub;
-  const uint32_t acc_cols = (uint32_t)(P.msub * P.bn);
-
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-    if (warp == 0) {
-      if (lane == 0) producer_role(P, full0, empty0, stage0, a_chunk_bytes, tile_rows);
-    } else if (warp == 1) {
-      mma_role(P, tmem_base, full0, empty0, tfull0, tempty0, stage0, a_chunk_bytes, s_off);
-    }
-  } else if (warp < 12) {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 128;");
-    epilogue_dispatch(P, tmem_base, tfull0, tempty0, warp & 3, (warp - 4) >> 2, lane, tile_rows, acc_cols,
-                      reinterpret_cast<const float*>(smem + 1024 + (size_t)P.stages * P.stage_bytes));
-  } else {
-    const int grp = (warp - 12) >> 2;
-    const int tid = threadIdx.x - 384 - grp * 128;
-    unsigned char* sm = smem + D.snake_off + (size_t)grp * fh::SnakeGeom<kDualR>::kSmemBytes;
-    const int worker = blockIdx.x * kDualWorkers + grp, nworkers = gridDim.x * kDualWorkers;
-    fh::snake_worker<3, true, kDualR>(D.s, sm, tid, worker, nworkers, 1 + grp);  // one instantiation: small I-cache footprint
-  }
+done:
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -1154,8 +1008,10 @@ extern "C" __attribute__((visibility("default"))) int64_t fh_tc_packed_weight_by
   return (int64_t)P * n_tiles * ((Cin + 15) / 16) * ntaps * bn * 32;
 }
 
+static int device_sms() { return fh::dev_sms(); }
+
 // Validates the arguments and derives the launch plan (tile shape, stages, shared-memory carve-up).  `budget_bytes` is
-// the shared memory the conv roles may use (0 = default); the fused-snake variant launches from here (returns 1).
+// the shared memory the conv roles may use (0 = default).  Returns FH_OK (plain kernel), 1 (fused snake prologue) or < 0.
 static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcParams& p, int* smem_out) {
   FH_REQUIRE(a != nullptr, FH_ERR_BAD_SHAPE, "fh_tc_conv: null args");
   FH_REQUIRE(a->B > 0 && a->L > 0 && a->Cin > 0 && a->Cout > 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: bad shape");
@@ -1201,6 +1057,8 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
     FH_REQUIRE(a->P == 1 && p.n_tiles == 1 && a->bn <= 128 && a->Cin <= 128 && a->sn_a && a->sn_inv_b && a->sn_filt && !a->geglu,
                FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake needs P == 1 and one N tile of <= 128 columns");
     FH_REQUIRE(((uintptr_t)a->x_f32 % 16) == 0, FH_ERR_BAD_ALIGN, "fh_tc_conv: x_f32 must be 16-byte aligned");
+    FH_REQUIRE(!a->x_is_16 || a->fp16, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: a 16-bit snake input must be fp16");
+    FH_REQUIRE(a->fp16, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: the fused snake prologue produces fp16 operands");
   }
   // sub-tiles: reuse each weight slot for up to 4 x 128 rows when the accumulators fit TMEM twice over
   int msub = 256 / a->bn;
@@ -1219,13 +1077,11 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   while (!fused && msub > 1 &&
          (long long)a->B * a->P * ((a->L + 128 * msub - 1) / (128 * msub)) * p.n_tiles < 2 * 148)
     msub >>= 1;
-  if (fused) msub = 2;  // 256-row tiles: the snake warps' two-phase window (tc_conv_snake_kernel) is sized for them
+  // (fused: snake work units are 128 window rows = one sub-tile, any msub works)
   p.msub = msub;
   p.acc_stages = (2 * msub * a->bn <= 512) ? 2 : 1;
+  p.m_stride = p.m_valid = 128 * msub;
   p.m_tiles = (a->L + 128 * msub - 1) / (128 * msub);
-  const long long total = (long long)p.B * p.P * p.m_tiles * p.n_tiles;
-  FH_REQUIRE(total < (1ll << 31), FH_ERR_BAD_SHAPE, "fh_tc_conv: too many tiles");
-  p.total_tiles = (int)total;
   p.ci_pairs = (a->Cin + 15) / 16;
   p.ci_odd = (a->Cin % 16) != 0;
   int span = 0, arith = 1;
@@ -1248,6 +1104,13 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   }
   FH_REQUIRE(span <= kMaxSpan, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: tap span %d exceeds %d rows", span, kMaxSpan);
   p.tap_arith = arith;
+  if (fused) {  // aligned A window of exactly 128 msub rows: a tile keeps 128 msub - span output rows
+    p.m_stride = p.m_valid = 128 * msub - span;
+    p.m_tiles = (a->L + p.m_stride - 1) / p.m_stride;
+  }
+  const long long total = (long long)p.B * p.P * p.m_tiles * p.n_tiles;
+  FH_REQUIRE(total < (1ll << 31), FH_ERR_BAD_SHAPE, "fh_tc_conv: too many tiles");
+  p.total_tiles = (int)total;
   {
     static int use_v8 = -1;
     if (use_v8 < 0) {
@@ -1265,11 +1128,6 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   p.wrows = 128 * msub + span;
   p.arows_pad = 128 * msub + kMaxSpan;
   if (fused) {
-    FH_REQUIRE(p.wrows + 6 <= kSnakeCap, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake window too small for this tap span");
-    FH_REQUIRE(a->a_row0 + p.min_off[0] - 6 >= 0, FH_ERR_BAD_SHAPE, "fh_tc_conv: fused snake needs 6 more halo rows");
-    p.arows_pad = kArPad;
-    p.xrows = p.wrows + 12;  // raw rows needed: positions t_slot0 - 3 .. t_slot0 + wrows + 2, +-3 each
-    p.xs_bytes = 2 * kXrPad * 32;
     p.rows_per_chunk = (int)(a->a_chunk / 8);
     p.xf = a->x_f32, p.sn_a = a->sn_a, p.sn_ib = a->sn_inv_b, p.sn_filt = a->sn_filt;
   }
@@ -1314,32 +1172,6 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
     if (budget_kb < 64 || budget_kb > 220) budget_kb = 200;
   }
   const int budget = budget_bytes > 0 ? budget_bytes : budget_kb * 1024;
-  if (fused) {
-    FH_REQUIRE(budget_bytes == 0, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: the fused snake prologue cannot run in the dual kernel");
-    const int fbudget = 220 * 1024;  // this kernel owns the SM
-    const int sbuf = 2 * kSrPad * 32;
-    p.x_stages = 3;
-    int st = (fbudget - 2048 - sbuf - p.x_stages * p.xs_bytes) / p.stage_bytes;
-    if (st < 3) {
-      p.x_stages = 2;
-      st = (fbudget - 2048 - sbuf - p.x_stages * p.xs_bytes) / p.stage_bytes;
-    }
-    FH_REQUIRE(st >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake stages do not fit shared memory");
-    p.stages = st > 4 ? 4 : st;
-    p.err_flag = nullptr;
-    const int fsmem = 2048 + sbuf + p.x_stages * p.xs_bytes + p.stages * p.stage_bytes;
-    static int fsmem_set[64] = {0};
-    const int fsms = fh::dev_sms();
-    {
-      cudaError_t e = fh::ensure_dyn_smem(tc_conv_snake_kernel, fsmem, fsmem_set);
-      FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", fsmem,
-                 cudaGetErrorString(e));
-    }
-    const int fgrid = p.total_tiles < fsms ? p.total_tiles : fsms;
-    tc_conv_snake_kernel<<<fgrid, kFusedThreads, fsmem, (cudaStream_t)stream>>>(p);
-    const int rc = fh::check_launch("fh_tc_conv(fused snake)");
-    return rc == FH_OK ? 1 : rc;
-  }
   static int fast_on = -1;
   if (fast_on < 0) {
     const char* e = getenv("FH_TC_FAST_EPI");
@@ -1351,70 +1183,94 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   FH_REQUIRE(p.fast_epi || !(a->accumulate && a->out_is_16), FH_ERR_UNSUPPORTED_CFG,
              "fh_tc_conv: accumulate into a 16-bit output is only implemented by the specialised epilogue");
   const int tail = p.fast_epi ? bias_tab : 0;
+  if (fused) {
+    // this kernel owns the SM: conv stages (3-4: the eight snake warps spread over up to four of them), then the x ring
+    // (one slot per 272-row unit window, at least one per snake warp)
+    const int fbudget = 222 * 1024;
+    const int grid_hint = p.total_tiles < device_sms() ? p.total_tiles : device_sms();
+    static int pro_nb = 0, pro_st = -1;
+    if (!pro_nb) {
+      const char* e = getenv("FH_PRO_NB");
+      pro_nb = (e && atoi(e) == 16) ? 16 : 8;
+      const char* e2 = getenv("FH_PRO_STAGES");
+      pro_st = e2 ? atoi(e2) : 0;
+    }
+    const int kProNB = (pro_nb == 16 && msub >= 2) ? 16 : 8;
+    p.pro_nb = kProNB;
+    p.xs_bytes = (16 * kProNB + 16) * (a->x_is_16 ? 16 : 32);
+    // ncu (profiles/r2_ncu_fused_*.txt): with one window slot per snake warp a third of the snake warps' samples sat on
+    // the window barrier -- the DRAM latency of every unit was exposed.  Two to three slots per warp hide it; the conv
+    // stages only need to hold the >= 8 units the eight warps work on, plus one stage for the MMAs in flight.
+    const int units_per_stage = 2 * (128 * msub) / (16 * kProNB);
+    int st = units_per_stage >= 8 ? 2 : 3;
+    if (pro_st >= 2 && pro_st <= 4) st = pro_st;
+    while (st > 2 && 1024 + st * p.stage_bytes + tail + 16 * p.xs_bytes + 16 * kProXMax > fbudget) --st;
+    const int room = fbudget - 1024 - st * p.stage_bytes - tail - 16 * kProXMax - 128;
+    int xd = room / p.xs_bytes;
+    if (xd > kProXMax) xd = kProXMax;
+    // >= 8 x slots: the consumer of window n has finished window n - 8 itself, so it can never be two fills ahead of the
+    // producer on a slot (mbarrier parity waits cannot tell generation g from g - 2)
+    // Active snake warps W: a warp has consumed window n - W itself before it waits for window n, so every parity wait is
+    // unambiguous as long as the x ring has >= W slots and the 8 stage barriers cover >= W units.
+    {
+      const int upc = (128 * msub) / (16 * kProNB);                // units per chunk and tile
+      const int min_units = p.ci_odd ? upc : 2 * upc;              // real units of the smallest stage
+      int w = kProSnakeWarps;
+      if (w > kMaxStages * min_units) w = kMaxStages * min_units;
+      if (w > xd) w = xd;
+      p.snake_warps = w;
+    }
+    FH_REQUIRE(xd >= 4 && p.snake_warps >= 1, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake stages (%d bytes each) do not fit shared memory",
+               p.stage_bytes);
+    FH_REQUIRE(((long long)p.total_tiles / grid_hint + 2) * p.ci_pairs * 16 < (1ll << 30), FH_ERR_BAD_SHAPE,
+               "fh_tc_conv: too many fused-snake units per CTA");
+    p.stages = st;
+    p.empty_ring = kMaxStages;
+    p.x_stages = xd;
+    p.xs_off = (1024 + st * p.stage_bytes + tail + 127) & ~127;
+    p.err_flag = fh::err_word();
+    *smem_out = p.xs_off + xd * p.xs_bytes + 16 * kProXMax;
+    return 1;
+  }
   int stages = (budget - 1024 - tail) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   FH_REQUIRE(stages >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: stage of %d bytes does not fit twice", p.stage_bytes);
   p.stages = stages;
-  p.err_flag = nullptr;
+  p.empty_ring = stages;
+  p.err_flag = fh::err_word();
   *smem_out = 1024 + stages * p.stage_bytes + tail;
   return FH_OK;
 }
-
-static int device_sms() { return fh::dev_sms(); }
 
 extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_conv_args* a, void* stream) {
   TcParams p;
   int smem = 0;
   const int rc = tc_plan(a, stream, 0, p, &smem);
-  if (rc != FH_OK) return rc == 1 ? FH_OK : rc;  // 1: the fused-snake variant was launched by the planner
+  if (rc != FH_OK && rc != 1) return rc;
+  const int num_sms = device_sms();
+  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  if (rc == 1) {  // fused snake prologue
+    static int set_a[64] = {0}, set_b[64] = {0}, set_c[64] = {0}, set_d[64] = {0};
+    cudaError_t e;
+#define FH_PRO_LAUNCH(IN16, NB, TAB)                                                              \
+  e = fh::ensure_dyn_smem(tc_conv_snakepro_kernel<IN16, NB>, smem, TAB);                          \
+  FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", smem, cudaGetErrorString(e)); \
+  tc_conv_snakepro_kernel<IN16, NB><<<grid, kProThreads, smem, (cudaStream_t)stream>>>(p)
+    if (a->x_is_16 && p.pro_nb == 16) { FH_PRO_LAUNCH(true, 16, set_a); }
+    else if (a->x_is_16) { FH_PRO_LAUNCH(true, 8, set_b); }
+    else if (p.pro_nb == 16) { FH_PRO_LAUNCH(false, 16, set_c); }
+    else { FH_PRO_LAUNCH(false, 8, set_d); }
+#undef FH_PRO_LAUNCH
+    return fh::check_launch("fh_tc_conv(fused snake)");
+  }
   static int smem_set[64] = {0};
   {
     cudaError_t e = fh::ensure_dyn_smem(tc_conv_kernel, smem, smem_set);
     FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", smem,
                cudaGetErrorString(e));
   }
-  const int num_sms = device_sms();
-  const int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   tc_conv_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
   return fh::check_launch("fh_tc_conv");
-}
-
-// One launch = the convolution of one half-batch (tensor pipe, HBM) + the anti-aliased snake of the other half-batch
-// (FP32 pipe) on the same SMs: see tc_conv_snake_dual_kernel.
-extern "C" __attribute__((visibility("default"))) int fh_tc_conv_snake_dual(
-    const fh_tc_conv_args* a, const float* sx, void* sy, const float* sa, const float* sinv_b, const float* sfilt,
-    int64_t s_batch_stride, int64_t s_chunk_stride, int s_row0, int sB, int sC, int sL, int s_out_kind, void* stream) {
-  FH_REQUIRE(a != nullptr && a->x_f32 == nullptr, FH_ERR_BAD_SHAPE, "fh_tc_conv_snake_dual: needs a plain conv");
-  FH_REQUIRE(sB > 0 && sC > 0 && (sC % 8) == 0 && sL > 0 && (s_out_kind == 1 || s_out_kind == 2), FH_ERR_BAD_SHAPE,
-             "fh_tc_conv_snake_dual: snake needs C %% 8 == 0 and a 16-bit output");
-  FH_REQUIRE(((uintptr_t)sx % 16) == 0 && ((uintptr_t)sy % 16) == 0 && (s_batch_stride % 8) == 0 &&
-                 (s_chunk_stride % 8) == 0 && s_row0 >= 5,
-             FH_ERR_BAD_ALIGN, "fh_tc_conv_snake_dual: snake buffers must be 16-byte aligned with a left halo of >= 5 rows");
-  using G = fh::SnakeGeom<kDualR>;
-  constexpr int kSnakeSmem = kDualWorkers * G::kSmemBytes;
-  DualParams d;
-  int csmem = 0;
-  const int rc = tc_plan(a, stream, 226 * 1024 - kSnakeSmem, d.c, &csmem);
-  if (rc != FH_OK) return rc;
-  d.snake_off = (csmem + 127) & ~127;
-  const int ntile = (sL + G::kRows - 1) / G::kRows;
-  const long long total = (long long)ntile * (sC / 8) * sB;
-  FH_REQUIRE(total <= 2147483647LL, FH_ERR_BAD_SHAPE, "fh_tc_conv_snake_dual: too many snake tiles");
-  d.s.x = sx, d.s.y = sy, d.s.a = sa, d.s.inv_b = sinv_b, d.s.filt = sfilt;
-  d.s.batch_stride = s_batch_stride, d.s.chunk_stride = s_chunk_stride;
-  d.s.row0 = s_row0, d.s.nchunk = sC / 8, d.s.L = sL, d.s.ntile = ntile, d.s.total = (int)total;
-  d.s_out_kind = s_out_kind;
-  d.s.fp16 = s_out_kind == 2;
-  d.s.status = fh::status_word();
-  const int smem = d.snake_off + kSnakeSmem;
-  static int smem_set[64] = {0};
-  {
-    cudaError_t e = fh::ensure_dyn_smem(tc_conv_snake_dual_kernel, smem, smem_set);
-    FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv_snake_dual: cannot opt in to %d bytes of smem: %s", smem,
-               cudaGetErrorString(e));
-  }
-  tc_conv_snake_dual_kernel<<<device_sms(), kDualThreads, smem, (cudaStream_t)stream>>>(d);
-  return fh::check_launch("fh_tc_conv_snake_dual");
 }
 
 extern "C" __attribute__((visibility("default"))) int fh_to_chunked_16(const float* src, int64_t src_batch, int64_t src_c, int64_t src_t, void* dst,

@@ -75,15 +75,15 @@ class Engine:
         import os as _os
         self.voc_streams = int(_os.environ.get("FH_VOC_STREAMS", "1"))
         self.tc_attention = _os.environ.get("FH_TC_ATTENTION", "1") != "0"  # mma.sync split-operand attention
-        self.fuse_snake = _os.environ.get("FH_FUSE_SNAKE", "0") != "0"      # snake as the conv kernel's A-producer
-        # dual launches: conv of one half-batch + snake of the other half-batch in one kernel (fh_tc_conv_snake_dual).
-        # Correct and tested, but measured slower than back-to-back launches on B200 (389 vs 375 ms per step: the two
-        # instruction streams thrash the 32 KB L1.5 I-cache and the snake workers get 8 warps instead of 16): off.
-        self.dual = _os.environ.get("FH_DUAL", "0") != "0"
+        # fp16 path, stages of <= 128 channels: FH_FUSE_SNAKE=1 runs the anti-aliased snake INSIDE the conv kernel as the
+        # producer of its A operand (tc_conv_snakepro_kernel: 16 instead of 24 HBM bytes per element of an AMP unit).
+        # Parity-tested, but measured at the same step time as the separate launches on B200 (311-319 vs 312 ms; ncu in
+        # profiles/r2_ncu_fused_snake_conv.txt: the snake warps, not HBM, pace the kernel), so the separate launches
+        # stay the default.
+        self.fuse_snake = self.fp16 == 1 and _os.environ.get("FH_FUSE_SNAKE", "0") != "0"
         # fp16 path: the first convolution of an AMP unit writes fp16 rows and the snake behind it reads them as MMA
         # operands (fh_snake_aa_chunked_h) -- the fp32 round trip of that tensor disappears
         self.y16 = self.fp16 and precision != "fp32" and _os.environ.get("FH_Y16", "1") != "0"
-        self._tape = None
         # AMP branches of a stage on parallel streams for small batches (B = 1 latency path)
         self.branch_streams = _os.environ.get("FH_BRANCH_STREAMS", "1") != "0"
         self.branch_streams_max_batch = 4
@@ -180,10 +180,6 @@ class Engine:
                                  f"(got {t.dtype}, {t.device}, contiguous={t.is_contiguous()})")
 
     def _call(self, name, *args, work=None):
-        if self._tape is not None:
-            kind = "snake" if (name == "fh_snake_aa_chunked" and args[11] in (1, 2)) else "other"
-            self._tape.append((kind, name, args, work))
-            return
         if self.profile is None:
             _lib.check(getattr(self.lib, name)(*args), name)
             return
@@ -416,11 +412,12 @@ class Engine:
 
     def _tc_conv(self, rec: _TcWeight, a, a_batch, a_chunk, a_row0, out, out_strides, out_bf16, B, L, res=None,
                  res_strides=(0, 0, 0), res_bf16=0, alpha=1.0, beta=0.0, accumulate=0, geglu=0, xf=None, snake=None, act=0,
-                 acc_src=None):
+                 acc_src=None, x16=False):
         args = _lib.TcConvArgs()
         args.a, args.a_batch, args.a_chunk, args.a_row0 = _ptr(a), a_batch, a_chunk, a_row0
         if xf is not None:  # fused anti-aliased snake prologue: A = Activation1d(xf), computed in the kernel
             args.x_f32 = xf.data_ptr()
+            args.x_is_16 = 1 if x16 else 0
             args.sn_a, args.sn_inv_b, args.sn_filt = snake[0].data_ptr(), snake[1].data_ptr(), snake[2].data_ptr()
         args.w, args.bias = rec.packed.data_ptr(), _ptr(rec.bias)
         args.res, args.out = _ptr(res), out.data_ptr()
@@ -434,15 +431,12 @@ class Engine:
         args.ntaps, args.P, args.tap_off, args.bn = rec.ntaps, rec.P, rec.off_c, rec.bn
         flops = 2.0 * B * L * rec.P * rec.ntaps * rec.cin * rec.cout
         esz_o = 2 if out_bf16 else 4
-        nbytes = B * L * rec.cin * (4 if xf is not None else 2) + B * L * rec.P * rec.cout * (esz_o + ((4 if acc_src is not None else esz_o) if accumulate else 0))
+        nbytes = B * L * rec.cin * (4 if (xf is not None and not x16) else 2) + B * L * rec.P * rec.cout * (esz_o + ((4 if acc_src is not None else esz_o) if accumulate else 0))
         if res is not None:
             nbytes += B * L * rec.P * rec.cout * (2 if res_bf16 else 4)
         work = {"flops": flops, "bytes": float(nbytes),
                 "tag": f"tc_conv{'+snake' if xf is not None else ''}[Cin{rec.cin},Cout{rec.cout},k{rec.ntaps}x{rec.P}"
                        f"{',res' if res is not None else ''}]"}
-        if self._tape is not None:
-            self._tape.append(("conv" if xf is None else "other", "fh_tc_conv", (args,), work))
-            return
         self._launch_conv(args, work)
 
     def _launch_conv(self, args, work):
@@ -454,51 +448,6 @@ class Engine:
         _lib.check(self.lib.fh_tc_conv(C.byref(args), self.stream), "fh_tc_conv")
         e1.record(torch.cuda.current_stream(self.device))
         self.profile.append(("fh_tc_conv", e0, e1, work))
-
-    def _launch_dual(self, conv, snake):
-        """conv = tape entry of a fh_tc_conv, snake = tape entry of a 16-bit fh_snake_aa_chunked (other half-batch)."""
-        args, cwork = conv[2][0], conv[3]
-        sa = snake[2]  # (x, y, a, inv_b, filt, batch_stride, chunk_stride, row0, B, C, L, out_kind, stream)
-        call = lambda: _lib.check(self.lib.fh_tc_conv_snake_dual(C.byref(args), *sa[:12], self.stream), "fh_tc_conv_snake_dual")
-        if self.profile is None:
-            call()
-            return
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(torch.cuda.current_stream(self.device))
-        call()
-        e1.record(torch.cuda.current_stream(self.device))
-        sbytes = 6.0 * sa[8] * sa[9] * sa[10]
-        self.profile.append(("fh_tc_conv_snake_dual", e0, e1,
-                             {"flops": cwork["flops"], "bytes": cwork["bytes"] + sbytes, "tag": "dual:" + cwork["tag"]}))
-
-    def _replay(self, entry):
-        kind, name, args, work = entry
-        if name == "fh_tc_conv":
-            self._launch_conv(args[0], work)
-        else:
-            tape, self._tape = self._tape, None
-            try:
-                self._call(name, *args[:-1], self.stream, work=work)
-            finally:
-                self._tape = tape
-
-    def _run_dual(self, A, B):
-        """Merges the operator tapes of two half-batches: half A runs one operator ahead, so its convolution meets the
-        snake of half B (and vice versa) in one dual launch; everything else is launched on its own, in tape order."""
-        i = j = 0
-        while i < len(A) or j < len(B):
-            a = A[i] if i < len(A) else None
-            b = B[j] if j < len(B) else None
-            if a is not None and b is not None and {a[0], b[0]} == {"conv", "snake"}:
-                conv, snake = (a, b) if a[0] == "conv" else (b, a)
-                self._launch_dual(conv, snake)
-                i, j = i + 1, j + 1
-            elif b is None or (a is not None and i <= j):
-                self._replay(a)
-                i += 1
-            else:
-                self._replay(b)
-                j += 1
 
     def _sgemm(self, A, lda, W, ldw, bias, res, ldr, beta, alpha, out, ldc, M, N, K):
         self._call("fh_sgemm_nt_f32", A.data_ptr(), lda, W.data_ptr() if isinstance(W, torch.Tensor) else W, ldw,
@@ -747,18 +696,6 @@ class Engine:
         B, N, _ = mel.shape
         ns = min(self.voc_streams, B)
         wave = torch.empty((B, N * self.vcfg.total_upsample), dtype=torch.float32, device=self.device)
-        if self.dual and not self.fuse_snake and ns <= 1 and B >= 2:
-            h = (B + 1) // 2
-            tapes = []
-            for tag, sl in (("d0", slice(0, h)), ("d1", slice(h, B))):
-                self._tape = []
-                try:
-                    self._vocoder_tc(mel[sl], wave[sl], tag)
-                    tapes.append(self._tape)
-                finally:
-                    self._tape = None
-            self._run_dual(tapes[0], tapes[1])
-            return wave
         if ns <= 1:
             self._vocoder_tc(mel, wave, "")
             return wave
@@ -871,8 +808,7 @@ class Engine:
         # 2 ms per step cheaper than separate outputs + a sum pass).  Small batches do not fill 148 SMs: there each
         # branch writes its own pre-scaled output on its own stream (parallel CUDA-graph branches when captured) and
         # fh_sum_cast_f32 adds them.
-        par = (self.branch_streams and B <= self.branch_streams_max_batch and self._tape is None and not self.fuse_snake
-               and started_event is None and nk > 1)
+        par = (self.branch_streams and B <= self.branch_streams_max_batch and started_event is None and nk > 1)
         main = torch.cuda.current_stream(self.device)
         if par:
             while len(self._branch_streams) < nk:
@@ -885,23 +821,23 @@ class Engine:
             strides = (bs, cs, 8)
             self._tc_conv(V[f"up{s}"], a_in, a_bs, a_cs, HALO, X[o:], strides, 0, B, L)
             L = Lo
-            fuse = self.fuse_snake and ch <= 128  # HBM-bound stages: snake runs inside the conv kernel
+            # HBM-bound stages (<= 128 channels, one N tile): the snake runs inside the conv kernel as its A-producer
+            fuse = self.fuse_snake and ch <= 128 and all(V[f"r{s}.{j}.c1.0"].bn >= ch for j in range(nk))
             if par:
                 ev_up = torch.cuda.Event()
                 ev_up.record(main)
             outs = []
             # sequential branches: the last one adds the running mean (XS, fp32) and writes the stage output directly as
             # the 16-bit operand of the next upsampler -- no fp32 store of the mean, no separate cast pass
-            fuse_cast = (not par and nk > 1 and s + 1 < v.num_stages and self._tape is None and not fuse
-                         and _os_environ_get("FH_FUSE_CAST", "1") != "0")
+            fuse_cast = (not par and nk > 1 and s + 1 < v.num_stages and _os_environ_get("FH_FUSE_CAST", "1") != "0")
             if fuse_cast:
                 XBf, _, _ = self_cbuf(f"vt_XB{s}", B, ch, Lo, bf)
             for j, dil in enumerate(v.resblock_dilation_sizes):
                 bt = f"_{j}" if par else ""  # parallel branches need their own scratch
                 XJ, _, _ = self_cbuf(f"vt_XJ{s}{bt}", B, ch, Lo, f32)
-                y16 = self.y16 and not fuse and not self.dual and self._tape is None and v.resblock == "1"
+                y16 = (self.y16 or fuse) and v.resblock == "1"  # the tensor between the two convs of a unit is fp16
                 Y, _, _ = self_cbuf(f"vt_Y{s}{bt}" + ("h" if y16 else ""), B, ch, Lo, bf if y16 else f32)
-                A, _, _ = self_cbuf(f"vt_A{s}{bt}", B, ch, Lo, bf)
+                A = None if fuse else self_cbuf(f"vt_A{s}{bt}", B, ch, Lo, bf)[0]
                 # parallel branches write their own output (summed below); sequential ones accumulate in place
                 XSj, _, _ = self_cbuf(f"vt_XS{s}_{j}" if par else f"vt_XS{s}", B, ch, Lo, f32)
                 outs.append(XSj)
@@ -925,13 +861,15 @@ class Engine:
                             self._tc_conv(V[f"r{s}.{j}.c1.{i}"], None if fuse else A, bs, cs, HALO, Y[o:], strides,
                                           1 if y16 else 0, B, L, **fa)
                             sn2 = V[f"r{s}.{j}.a2.{i}"]
-                            if y16:
+                            if fuse:
+                                pass  # the second snake is the prologue of the second conv (fp16 rows in)
+                            elif y16:
                                 self._call("fh_snake_aa_chunked_h", Y.data_ptr(), A.data_ptr(), sn2[0].data_ptr(),
                                            sn2[1].data_ptr(), sn2[2].data_ptr(), bs, cs, HALO, B, ch, L, st)
-                            elif not fuse:
+                            else:
                                 self._call("fh_snake_aa_chunked", Y.data_ptr(), A.data_ptr(), sn2[0].data_ptr(),
                                            sn2[1].data_ptr(), sn2[2].data_ptr(), bs, cs, HALO, B, ch, L, self.k16, st)
-                            fa = dict(xf=Y, snake=sn2) if fuse else {}
+                            fa = dict(xf=Y, snake=sn2, x16=True) if fuse else {}
                             conv = V[f"r{s}.{j}.c2.{i}"]
                         else:
                             conv = V[f"r{s}.{j}.c1.{i}"]

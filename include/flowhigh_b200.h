@@ -44,6 +44,10 @@ int64_t fh_launch_count(void);
  * generate() -- the device-side replacement of the reference's per-NFE `torch.isnan(x).any()` prints
  * (models/flow.py:256-267), without their four host syncs per NFE. */
 int fh_set_status_word(uint32_t* status);
+/* Debug aid: `word` is a uint32 in PINNED HOST memory (or NULL).  The tcgen05 kernels bound every mbarrier wait; a wait
+ * that times out (a protocol bug) writes (wait code | block << 8 | warp << 24) there before trapping -- host memory
+ * survives the resulting launch failure.  Thread-local like the status word. */
+int fh_set_debug_word(uint32_t* word);
 
 /* ---------------------------------------------------------------- resampler + peak normalise
  * replaces scipy.signal.resample_poly + `cond /= max|cond|`   flowhighsr.py:68-69
@@ -212,10 +216,12 @@ typedef struct {
   const int* tap_off;     /* HOST pointer [P][ntaps] row offsets */
   int bn;                 /* N tile, multiple of 16, <= 256 */
   int fp16;               /* 16-bit operand format: 0 = bfloat16, 1 = IEEE half (same rate, 3 more mantissa bits) */
-  /* fused anti-aliased Snake prologue (optional): when x_f32 != NULL the A operand is Activation1d(x_f32)
-   * computed inside the kernel (alias_free_torch/act.py:23-28); x_f32 is chunked fp32 with the geometry
-   * a_batch / a_chunk / a_row0 describe; `a` is ignored.  Needs P == 1, Cout <= bn <= 128 and a_row0 >= 5 - min tap. */
-  const float* x_f32;
+  /* fused anti-aliased Snake prologue (optional): when x_f32 != NULL the A operand is Activation1d(x) computed inside
+   * the kernel (alias_free_torch/act.py:23-28 + bigvgan/models.py:63-72 `conv(act(x))`) and never written to HBM;
+   * x is chunked fp32 -- or fp16 rows when x_is_16 != 0 -- with the geometry a_batch / a_chunk / a_row0 describe
+   * (>= 8 zero rows are NOT required: windows are clipped to the buffer and replicate-patched); `a` is ignored.
+   * Needs fp16 operands, P == 1, Cin <= 128 and Cout <= bn <= 128. */
+  const void* x_f32;
   const float* sn_a;      /* [Cin] alpha (already exp'd when logscale) */
   const float* sn_inv_b;  /* [Cin] 1 / (beta + 1e-9) */
   const float* sn_filt;   /* [12] Kaiser-sinc taps */
@@ -223,15 +229,9 @@ typedef struct {
   const float* acc_src;   /* accumulate != 0: rows to add, fp32 with the output geometry; NULL = the output itself.
                            * Lets the last AMP branch of a stage (bigvgan/models.py:181-187, xs / num_kernels) write the
                            * mean directly as the 16-bit operand of the next upsampler (out_is_16 = 1). */
+  int x_is_16;            /* fused prologue: x_f32 points to fp16 rows (the 16-bit output of the unit's first conv) */
 } fh_tc_conv_args;
 int fh_tc_conv(const fh_tc_conv_args* args, void* stream);
-/* One launch = fh_tc_conv(args) for one half-batch + fh_snake_aa_chunked(sx -> sy, 16-bit out) for an independent
- * half-batch on the same SMs (tensor pipe and FP32 pipe busy together; replaces the back-to-back launches of
- * bigvgan/models.py:63-72 `conv(act(x))` chains when two half-batches are staggered by one operator).
- * args->x_f32 must be NULL; s_out_kind 1 = bf16, 2 = fp16. */
-int fh_tc_conv_snake_dual(const fh_tc_conv_args* args, const float* sx, void* sy, const float* sa,
-                          const float* sinv_b, const float* sfilt, int64_t s_batch_stride, int64_t s_chunk_stride,
-                          int s_row0, int sB, int sC, int sL, int s_out_kind, void* stream);
 /* bytes of the packed weight image for given shape (host helper, no GPU work) */
 int64_t fh_tc_packed_weight_bytes(int Cin, int Cout, int ntaps, int P, int bn);
 

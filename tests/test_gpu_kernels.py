@@ -595,7 +595,8 @@ def test_generate_rejects_too_short_clip(cuda_device, f32_model):
 
 @pytest.mark.parametrize("name", ["voc_resblock2_snake", "voc_resblock1_snakebeta"])
 def test_fused_snake_conv_matches_unfused(cuda_device, name):
-    """tc_conv_snake_kernel (snake computed by producer warps inside the conv kernel) against the two-kernel path."""
+    """tc_conv_snakepro_kernel (the Toeplitz-MMA snake as the in-kernel producer of the conv's A operand, fp32 and fp16
+    row inputs, aligned windows with m_valid = 128 msub - span rows per tile) against the separate snake launches."""
     eng, sd, vcfg, g = engine(name, "fp16")
     mel = dev(g["mel"])
     prev = eng.fuse_snake
@@ -613,7 +614,6 @@ def test_fused_snake_conv_matches_unfused(cuda_device, name):
     err = float((a - b).abs().max())
     sa, sb = snr_db(ref, a), snr_db(ref, b)
     print(f"fused snake+conv vs unfused {name}: max-abs {err:.3g}, SNR vs fp64 {sa:.2f} / {sb:.2f} dB")
-    # the unfused path runs the Toeplitz-MMA snake (fp16 filter taps, ~1.3 dB below the scalar snake of the fused path)
     assert err <= 3e-3 and sa >= 55.0 and sb >= 55.0 and abs(sa - sb) <= 2.0
 
 
@@ -651,25 +651,6 @@ def test_first_call_with_parallel_branches_is_clean(cuda_device):
     assert torch.equal(first, again)
     ref = torch.from_numpy(g["f64_vocoder"]).reshape(first.shape).float()
     assert snr_db(ref, first) >= 55.0
-
-
-def test_dual_conv_snake_launches_match_separate(cuda_device):
-    """fh_tc_conv_snake_dual (conv of one half-batch + snake of the other in one kernel, engine tapes staggered by one
-    operator) must reproduce the back-to-back launches: same kernels' arithmetic, only the schedule differs."""
-    eng, sd, vcfg, g = engine("voc_resblock1_snakebeta", "fp16")
-    mel = dev(g["mel"])
-    mel = torch.cat([mel, mel.flip(1) * 0.9, mel * 0.8], 0).contiguous()  # B = 3: unequal halves
-    prev = eng.dual
-    try:
-        eng.dual = False
-        a = eng.vocoder(mel).cpu()
-        eng.dual = True
-        b = eng.vocoder(mel).cpu()
-    finally:
-        eng.dual = prev
-    err = float((a - b).abs().max())
-    print(f"dual conv||snake launches vs separate: max-abs {err:.3g}")
-    assert err <= 3e-3 and snr_db(a, b) >= 55.0
 
 
 def test_from_local_wav_in_wav_out(cuda_device, tmp_path):
