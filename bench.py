@@ -205,7 +205,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16"],
+    ap.add_argument("--precision", default="fp16", choices=["fp16", "bf16", "fp16x2"],
                     help="16-bit tensor-core operand format (same rate and bytes; fp16 meets the LSD bar, see DESIGN.md)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-clip-seconds", type=float, default=CLIP_SECONDS, help="reference arm: clip length per step")

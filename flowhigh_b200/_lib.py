@@ -79,10 +79,13 @@ SIGNATURES = {
     "fh_convpost_tanh_f32": (_i, [_p, _p, _f, _p, _i, _i, _i, _p]),
     "fh_transpose_f32": (_i, [_p, _p, _i, _i, _i, _p]),
     "fh_cast_f32_16": (_i, [_p, _p, _i64, _i, _p]),
+    "fh_cast_f32_16_split": (_i, [_p, _p, _i64, _i, _i64, _i64, _i, _i, _p]),
     "fh_sum_cast_f32": (_i, [_p, _p, _p, _p, _p, _p, _i64, _i, _p]),
     "fh_tc_conv": (_i, [C.POINTER(TcConvArgs), _p]),
     "fh_tc_packed_weight_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "fh_to_chunked_16": (_i, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _i, _i, _p]),
+    "fh_to_chunked_16_split": (_i, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i, _i, _i, _i, _i, _p]),
+    "fh_snake_aa_chunked_split": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _p]),
     "fh_snake_aa_chunked": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _p]),
     "fh_snake_aa_chunked_h": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _p]),
     "fh_convpost_tanh_chunked": (_i, [_p, _i64, _i64, _i, _p, _f, _p, _i, _i, _i, _p]),

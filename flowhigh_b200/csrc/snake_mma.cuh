@@ -38,7 +38,9 @@ struct SnakeMmaGeom {
   static constexpr int kXBytes = kXRows * 32;  // fp32 rows; fp16 input rows take half of it
   static constexpr int kWarpYBytes = kWarpRows * 16;
   // two input windows, per warp two output images, 128 control bytes: two mbarriers, two release counters, 2 x 12 taps
-  static constexpr int smem_bytes(bool in16) { return 2 * (in16 ? kXBytes / 2 : kXBytes) + 2 * kWarps * kWarpYBytes + 128; }
+  static constexpr int smem_bytes(bool in16, bool split_out = false) {
+    return 2 * (in16 ? kXBytes / 2 : kXBytes) + (split_out ? 4 : 2) * kWarps * kWarpYBytes + 128;
+  }
 };
 
 __device__ __forceinline__ uint32_t sm_pack(float lo, float hi) {
@@ -132,11 +134,13 @@ __device__ __forceinline__ void snake_mma_frags(const float* s_taps, int lane, S
 //   yt : shared-memory output image, row 0 = time q0, 16-byte rows [time][8 ch] fp16
 // edge: the unit touches t < 0 or t >= L (replicate clamps apply).  Rows of the image with t >= L are computed from the
 // clamped signal (finite) and must be ignored / overwritten by the caller.
-template <bool SPLIT_X, bool SPLIT_F, int NB, bool IN16>
+// SPLIT_OUT: the fp32 result is written as hi + lo fp16 pairs (yt_lo: second image, same geometry) -- the operand of a
+// convolution whose input channels are doubled [hi | lo] against duplicated weights keeps ~22 bits of the activation.
+template <bool SPLIT_X, bool SPLIT_F, int NB, bool IN16, bool SPLIT_OUT = false>
 __device__ __forceinline__ void snake_mma_unit(const SnakeFrags& F, float* xw, unsigned char* yt, int q0, int L, int ch,
                                                const float* __restrict__ sn_a, const float* __restrict__ sn_inv_b,
                                                const float* __restrict__ sn_filt, bool edge, int lo, int hi, int lane,
-                                               Guard16& guard) {
+                                               Guard16& guard, unsigned char* yt_lo = nullptr) {
   using G = SnakeMmaGeom<NB>;
   const int g = lane >> 2, q = lane & 3;
   if (edge) {
@@ -255,6 +259,15 @@ __device__ __forceinline__ void snake_mma_unit(const SnakeFrags& F, float* xw, u
         asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(st_base + (uint32_t)(8 * i * 16)),
                      "r"(r0), "r"(r1)
                      : "memory");
+        if (SPLIT_OUT) {
+          const float2 h0 = __half22float2(*reinterpret_cast<const __half2*>(&r0));
+          const float2 h1 = __half22float2(*reinterpret_cast<const __half2*>(&r1));
+          const uint32_t l0 = pack16(yy[0] - h0.x, yy[1] - h0.y, 1), l1 = pack16(yy[2] - h1.x, yy[3] - h1.y, 1);
+          asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(
+                           st_base + (uint32_t)(yt_lo - yt) + (uint32_t)(8 * i * 16)),
+                       "r"(l0), "r"(l1)
+                       : "memory");
+        }
       }
     }
   }
@@ -280,7 +293,9 @@ __device__ __forceinline__ void snake_mma_unit(const SnakeFrags& F, float* xw, u
           }
           acc = fmaf(__ldg(sn_filt + k), u - hib * __cosf(alv * u), acc);
         }
-        *reinterpret_cast<__half*>(yt + (size_t)(qq - q0) * 16 + 2 * c) = __float2half_rn(acc);
+        const __half hv = __float2half_rn(acc);
+        *reinterpret_cast<__half*>(yt + (size_t)(qq - q0) * 16 + 2 * c) = hv;
+        if (SPLIT_OUT) *reinterpret_cast<__half*>(yt_lo + (size_t)(qq - q0) * 16 + 2 * c) = __float2half_rn(acc - __half2float(hv));
       }
     }
   }
@@ -294,15 +309,16 @@ __device__ __forceinline__ void snake_mma_unit(const SnakeFrags& F, float* xw, u
 // IN16: the input is already fp16 on the same chunked layout (16-byte rows, written by the 16-bit epilogue of the
 // preceding convolution): the A fragments of the up stage come straight from the window with one ldmatrix.x4.trans
 // per 8 up-samples (identity k-slot -> time map), no conversion instructions at all.
-template <bool SPLIT_X, bool SPLIT_F, int NB, bool IN16 = false>
+template <bool SPLIT_X, bool SPLIT_F, int NB, bool IN16 = false, bool SPLIT_OUT = false>
 __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned char* smem, int tid, int cta, int nctas) {
   using G = SnakeMmaGeom<NB>;
   const int lane = tid & 31, warp = tid >> 5;
   constexpr int kXB = IN16 ? G::kXBytes / 2 : G::kXBytes;  // bytes of one input window
   float* xs0 = reinterpret_cast<float*>(smem);
   float* xs1 = reinterpret_cast<float*>(smem + kXB);
-  unsigned char* ys0 = smem + 2 * kXB + warp * 2 * G::kWarpYBytes;  // this warp's two output images
-  unsigned char* ctl = smem + 2 * kXB + 2 * G::kWarps * G::kWarpYBytes;
+  constexpr int kImg = SPLIT_OUT ? 2 : 1;  // images per buffer (hi, lo)
+  unsigned char* ys0 = smem + 2 * kXB + warp * 2 * kImg * G::kWarpYBytes;  // this warp's two output buffers
+  unsigned char* ctl = smem + 2 * kXB + 2 * kImg * G::kWarps * G::kWarpYBytes;
   const uint32_t bar0 = sw_u32(ctl);
   int* released = reinterpret_cast<int*>(ctl + 16);  // warps done with window 0 / 1
   float* s_taps = reinterpret_cast<float*>(ctl + 32);  // [0, 12): up-filter taps (2 f), [12, 24): down-filter taps (f)
@@ -359,11 +375,11 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
     sw_mbar_wait(bar0 + 8 * buf, buf ? ph1 : ph0);
     if (buf) ph1 ^= 1; else ph0 ^= 1;
     float* xt = buf ? xs1 : xs0;
-    unsigned char* yt = ys0 + (size_t)buf * G::kWarpYBytes;
+    unsigned char* yt = ys0 + (size_t)buf * kImg * G::kWarpYBytes;
     if (active) {
       float* xw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(xt) + (size_t)ssA * (IN16 ? 16 : 32));
-      snake_mma_unit<SPLIT_X, SPLIT_F, NB, IN16>(F, xw, yt, qt + ssA, S.L, ch, S.a, S.inv_b, S.filt, edge, -ssA,
-                                                 G::kXRows - ssA, lane, guard);
+      snake_mma_unit<SPLIT_X, SPLIT_F, NB, IN16, SPLIT_OUT>(F, xw, yt, qt + ssA, S.L, ch, S.a, S.inv_b, S.filt, edge, -ssA,
+                                                            G::kXRows - ssA, lane, guard, yt + G::kWarpYBytes);
     }
     // generic-proxy accesses of this warp (window reads / patches, output image writes) before the async proxy's
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -373,11 +389,15 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
     if (lane == 0) {
       if (active) {
         const int nrows = min(G::kWarpRows, S.L - qt - ssA);
-        const unsigned short* dst = (const unsigned short*)S.y + (long long)b * S.batch_stride +
+        const unsigned short* dst = (const unsigned short*)S.y + (long long)b * S.y_batch_stride +
                                     (long long)ch * S.chunk_stride + (long long)(S.row0 + qt + ssA) * 8;
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sw_u32(yt)),
                      "r"((uint32_t)nrows * 16u)
                      : "memory");
+        if (SPLIT_OUT)
+          asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst + S.lo_offset),
+                       "r"(sw_u32(yt + G::kWarpYBytes)), "r"((uint32_t)nrows * 16u)
+                       : "memory");
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       // release the window; the last of the four warps refills it with the tile after next

@@ -31,6 +31,8 @@ struct SnakeParams {
   const float* inv_b;
   const float* filt;
   long long batch_stride, chunk_stride;
+  long long y_batch_stride;  // batch stride of y (elements; the hi + lo output of the split mode has twice the chunks)
+  long long lo_offset;       // split mode: element offset of the "lo" chunks behind the "hi" chunks of y, else 0
   int row0, nchunk, L, ntile, total;
   int fp16;  // 16-bit output format when OUT_KIND == 3 (chosen at run time): 0 bfloat16, 1 IEEE half
   unsigned int* status;  // overflow / NaN status word of the caller (common.cuh Guard16) or nullptr
@@ -188,7 +190,7 @@ __device__ __forceinline__ void snake_worker(const SnakeParams& S, unsigned char
         }
       }
       const long long obase =
-          (long long)b * S.batch_stride + (long long)ch * S.chunk_stride + (long long)(S.row0 + q0) * 8 + 2 * e2;
+          (long long)b * S.y_batch_stride + (long long)ch * S.chunk_stride + (long long)(S.row0 + q0) * 8 + 2 * e2;
 #pragma unroll
       for (int j = 0; j < R; ++j) {
         // the bulk-store path writes into the shared-memory image (rows past L are never stored to HBM): no
@@ -212,7 +214,7 @@ __device__ __forceinline__ void snake_worker(const SnakeParams& S, unsigned char
       sw_group_sync(bar_id);
       if (tid == 0) {
         const int nrows = min(G::kRows, S.L - qt);
-        const unsigned short* dst = (const unsigned short*)S.y + (long long)b * S.batch_stride +
+        const unsigned short* dst = (const unsigned short*)S.y + (long long)b * S.y_batch_stride +
                                     (long long)ch * S.chunk_stride + (long long)(S.row0 + qt) * 8;
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(sw_u32(ys)),
                      "r"((uint32_t)nrows * 16u)

@@ -972,7 +972,8 @@ done:
 // ------------------------------------------------------------------------------ layout helpers
 __global__ void to_chunked_bf16_kernel(const float* __restrict__ src, long long src_batch, long long src_c,
                                        long long src_t, __nv_bfloat16* __restrict__ dst, long long dst_batch,
-                                       long long dst_chunk, int dst_row0, int C, int L, int fp16, unsigned int* status) {
+                                       long long dst_chunk, int dst_row0, int C, int L, int fp16, unsigned int* status,
+                                       long long lo_offset) {
   // one thread per (t, chunk): gathers 8 channels, writes one 16-byte row
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int nch = (C + 7) >> 3;
@@ -987,16 +988,19 @@ __global__ void to_chunked_bf16_kernel(const float* __restrict__ src, long long 
     t = (int)(i / nch);
   }
   const float* s = src + (long long)b * src_batch + (long long)t * src_t;
-  uint32_t h[4];
+  uint32_t h[4], l[4];
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     const int c0 = ch * 8 + 2 * k;
     const float f0 = c0 < C ? s[(long long)c0 * src_c] : 0.f;
     const float f1 = c0 + 1 < C ? s[(long long)(c0 + 1) * src_c] : 0.f;
     h[k] = fh::pack16_guard(f0, f1, fp16, status);
+    const float2 hf = fh::unpack16(h[k], fp16);
+    l[k] = fh::pack16(f0 - hf.x, f1 - hf.y, fp16);
   }
-  *reinterpret_cast<uint4*>(dst + (long long)b * dst_batch + (long long)ch * dst_chunk + (long long)(dst_row0 + t) * 8) =
-      *reinterpret_cast<uint4*>(h);
+  __nv_bfloat16* o = dst + (long long)b * dst_batch + (long long)ch * dst_chunk + (long long)(dst_row0 + t) * 8;
+  *reinterpret_cast<uint4*>(o) = *reinterpret_cast<uint4*>(h);
+  if (lo_offset) *reinterpret_cast<uint4*>(o + lo_offset) = *reinterpret_cast<uint4*>(l);  // hi + lo split (fp16x2)
 }
 
 }  // namespace
@@ -1279,6 +1283,19 @@ extern "C" __attribute__((visibility("default"))) int fh_to_chunked_16(const flo
   FH_REQUIRE(B > 0 && C > 0 && L > 0 && B <= 65535, FH_ERR_BAD_SHAPE, "fh_to_chunked_16: bad shape");
   const long long n = (long long)((C + 7) / 8) * L;
   to_chunked_bf16_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(
-      src, src_batch, src_c, src_t, (__nv_bfloat16*)dst, dst_batch, dst_chunk, dst_row0, C, L, fp16, fh::status_word());
+      src, src_batch, src_c, src_t, (__nv_bfloat16*)dst, dst_batch, dst_chunk, dst_row0, C, L, fp16, fh::status_word(), 0);
   return fh::check_launch("fh_to_chunked_16");
+}
+
+// same, written as hi + lo 16-bit pairs: channels [0, C) = round(x), channels [Cpad, Cpad + C) = round(x - hi)
+// (Cpad = C rounded up to 8); the operand of a convolution with duplicated weights (precision "fp16x2")
+extern "C" __attribute__((visibility("default"))) int fh_to_chunked_16_split(const float* src, int64_t src_batch, int64_t src_c, int64_t src_t,
+                                  void* dst, int64_t dst_batch, int64_t dst_chunk, int dst_row0, int B, int C, int L,
+                                  int fp16, void* stream) {
+  FH_REQUIRE(B > 0 && C > 0 && L > 0 && B <= 65535, FH_ERR_BAD_SHAPE, "fh_to_chunked_16_split: bad shape");
+  const long long n = (long long)((C + 7) / 8) * L;
+  to_chunked_bf16_kernel<<<dim3((unsigned)((n + 255) / 256), B), 256, 0, (cudaStream_t)stream>>>(
+      src, src_batch, src_c, src_t, (__nv_bfloat16*)dst, dst_batch, dst_chunk, dst_row0, C, L, fp16, fh::status_word(),
+      (long long)((C + 7) / 8) * dst_chunk);
+  return fh::check_launch("fh_to_chunked_16_split");
 }

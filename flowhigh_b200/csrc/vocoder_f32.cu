@@ -186,6 +186,22 @@ __global__ void cast_f32_16_kernel(const float* __restrict__ src, unsigned short
   }
 }
 
+// chunked fp32 [B][nchunk][rows][8] -> chunked fp16 hi + lo [B][2 nchunk][rows][8] (halos included): hi = round(x),
+// lo = round(x - hi).  The operand of a convolution with duplicated weights (precision "fp16x2").
+__global__ void cast_split_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, long long chunk_elems,
+                                  int nchunk, long long src_batch, long long dst_batch, int fp16, unsigned int* status) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const int ch = blockIdx.y, b = blockIdx.z;
+  if (i >= chunk_elems) return;
+  const float4 v = *reinterpret_cast<const float4*>(src + (long long)b * src_batch + (long long)ch * chunk_elems + i);
+  uint32_t h[2] = {fh::pack16_guard(v.x, v.y, fp16, status), fh::pack16_guard(v.z, v.w, fp16, status)};
+  const float2 h0 = fh::unpack16(h[0], fp16), h1 = fh::unpack16(h[1], fp16);
+  uint32_t l[2] = {fh::pack16(v.x - h0.x, v.y - h0.y, fp16), fh::pack16(v.z - h1.x, v.w - h1.y, fp16)};
+  unsigned short* o = dst + (long long)b * dst_batch + (long long)ch * chunk_elems + i;
+  *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(h);
+  *reinterpret_cast<uint2*>(o + (long long)nchunk * chunk_elems) = *reinterpret_cast<uint2*>(l);
+}
+
 // out = a + b (+ c) (+ d): the mean over the AMP branches of a stage (bigvgan/models.py:181-187; each branch already
 // carries the 1/num_kernels factor), written as fp32 and / or as the 16-bit operand of the next upsampler.  HBM-bound.
 __global__ void sum_cast_kernel(const float* __restrict__ a, const float* __restrict__ b, const float* __restrict__ c,
@@ -278,6 +294,19 @@ extern "C" __attribute__((visibility("default"))) int fh_transpose_f32(const flo
              "fh_transpose_f32: bad shape");
   transpose_f32_kernel<<<dim3((Cc + 31) / 32, (R + 31) / 32, B), dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, R, Cc);
   return fh::check_launch("fh_transpose_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_cast_f32_16_split(const float* src, void* dst, int64_t chunk_elems, int nchunk,
+                                                                           int64_t src_batch, int64_t dst_batch, int B, int fp16,
+                                                                           void* stream) {
+  FH_REQUIRE(B > 0 && nchunk > 0 && chunk_elems > 0 && (chunk_elems % 8) == 0 && B <= 65535 && nchunk <= 65535, FH_ERR_BAD_SHAPE,
+             "fh_cast_f32_16_split: bad shape");
+  FH_REQUIRE(((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 16) == 0 && (src_batch % 8) == 0 && (dst_batch % 8) == 0,
+             FH_ERR_BAD_ALIGN, "fh_cast_f32_16_split: alignment");
+  const long long nthreads = (chunk_elems + 3) / 4;
+  cast_split_kernel<<<dim3((unsigned)((nthreads + 255) / 256), nchunk, B), 256, 0, (cudaStream_t)stream>>>(
+      src, (unsigned short*)dst, chunk_elems, nchunk, src_batch, dst_batch, fp16, fh::status_word());
+  return fh::check_launch("fh_cast_f32_16_split");
 }
 
 extern "C" __attribute__((visibility("default"))) int fh_cast_f32_16(const float* src, void* dst, int64_t n, int fp16, void* stream) {

@@ -22,22 +22,22 @@ __global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(const __gr
 
 // fp16 output mode: both FIR filters as Toeplitz MMAs (snake_mma.cuh).  MODE bit 0: hi/lo split of the input,
 // bit 1: hi/lo split of the filter taps.
-template <int MODE, int NB, int MINB, bool IN16>
+template <int MODE, int NB, int MINB, bool IN16, bool SPLIT_OUT>
 __global__ void __launch_bounds__(128, MINB) snake_aa_mma_kernel(const __grid_constant__ fh::SnakeParams S) {
   extern __shared__ __align__(128) unsigned char snake_smem[];
-  fh::snake_mma_cta<(MODE & 1) != 0, (MODE & 2) != 0, NB, IN16>(S, snake_smem, threadIdx.x, blockIdx.x, gridDim.x);
+  fh::snake_mma_cta<(MODE & 1) != 0, (MODE & 2) != 0, NB, IN16, SPLIT_OUT>(S, snake_smem, threadIdx.x, blockIdx.x, gridDim.x);
 }
 
-template <int MODE, int NB, int MINB, bool IN16 = false>
+template <int MODE, int NB, int MINB, bool IN16 = false, bool SPLIT_OUT = false>
 void launch_snake_mma(fh::SnakeParams sp, int B, int C, int L, int sms, cudaStream_t stream) {
   using G = fh::SnakeMmaGeom<NB>;
   static int smem_set[64] = {0};
-  fh::ensure_dyn_smem(snake_aa_mma_kernel<MODE, NB, MINB, IN16>, G::smem_bytes(IN16), smem_set);
+  fh::ensure_dyn_smem(snake_aa_mma_kernel<MODE, NB, MINB, IN16, SPLIT_OUT>, G::smem_bytes(IN16, SPLIT_OUT), smem_set);
   sp.ntile = (L + G::kRows - 1) / G::kRows;
   const long long total = (long long)sp.ntile * (C / 8) * B;
   sp.total = (int)total;
   const int grid = (int)(total < (long long)sms * MINB ? total : (long long)sms * MINB);
-  snake_aa_mma_kernel<MODE, NB, MINB, IN16><<<grid, 128, G::smem_bytes(IN16), stream>>>(sp);
+  snake_aa_mma_kernel<MODE, NB, MINB, IN16, SPLIT_OUT><<<grid, 128, G::smem_bytes(IN16, SPLIT_OUT), stream>>>(sp);
 }
 
 __global__ void convpost_tanh_chunked_kernel(const float* __restrict__ x, long long batch_stride,
@@ -105,7 +105,7 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
   }
   fh::SnakeParams sp;
   sp.x = x, sp.y = y, sp.a = a, sp.inv_b = inv_b, sp.filt = filt;
-  sp.batch_stride = batch_stride, sp.chunk_stride = chunk_stride;
+  sp.batch_stride = batch_stride, sp.chunk_stride = chunk_stride, sp.y_batch_stride = batch_stride, sp.lo_offset = 0;
   sp.row0 = row0, sp.nchunk = C / 8, sp.L = L, sp.ntile = ntile, sp.total = (int)total, sp.fp16 = out_kind == 2;
   sp.status = fh::status_word();
   if (use_mma) {
@@ -136,6 +136,29 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
   return fh::check_launch("fh_snake_aa_chunked");
 }
 
+// fp32 in -> fp16 hi + lo out (precision "fp16x2"): y holds 2 C channels per batch, [hi chunks | lo chunks]; the input is
+// split hi + lo as well (two MMAs per up-filter block), so the activation keeps ~22 bits into the following convolution,
+// whose weights are duplicated over the doubled input channels.
+extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked_split(
+    const float* x, void* y, const float* a, const float* inv_b, const float* filt, int64_t x_batch_stride,
+    int64_t y_batch_stride, int64_t chunk_stride, int row0, int B, int C, int L, void* stream) {
+  FH_REQUIRE(B > 0 && C > 0 && (C % 8) == 0 && L > 0, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked_split: C must be a multiple of 8");
+  FH_REQUIRE(((uintptr_t)x % 16) == 0 && ((uintptr_t)y % 16) == 0 && (x_batch_stride % 8) == 0 && (y_batch_stride % 8) == 0 &&
+                 (chunk_stride % 8) == 0,
+             FH_ERR_BAD_ALIGN, "fh_snake_aa_chunked_split: buffers must be 16-byte aligned and strides multiples of 8");
+  FH_REQUIRE(row0 >= fh::SnakeMmaGeom<8>::kHalo, FH_ERR_BAD_SHAPE, "fh_snake_aa_chunked_split: needs a left halo of >= 8 rows");
+  FH_REQUIRE((long long)((L + 511) / 512) * (C / 8) * B <= 2147483647LL, FH_ERR_BAD_SHAPE,
+             "fh_snake_aa_chunked_split: too many work items");
+  fh::SnakeParams sp;
+  sp.x = x, sp.y = y, sp.a = a, sp.inv_b = inv_b, sp.filt = filt;
+  sp.batch_stride = x_batch_stride, sp.chunk_stride = chunk_stride, sp.y_batch_stride = y_batch_stride;
+  sp.lo_offset = (int64_t)(C / 8) * chunk_stride;
+  sp.row0 = row0, sp.nchunk = C / 8, sp.L = L, sp.ntile = 0, sp.total = 0, sp.fp16 = 1;
+  sp.status = fh::status_word();
+  launch_snake_mma<1, 8, 3, false, true>(sp, B, C, L, fh::dev_sms(), (cudaStream_t)stream);
+  return fh::check_launch("fh_snake_aa_chunked_split");
+}
+
 // fp16 in -> fp16 out on the same chunked geometry: the input was written by the 16-bit epilogue of the first
 // convolution of an AMP unit (fh_tc_conv with out_is_16), so the fp32 round trip of that tensor disappears.
 extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked_h(
@@ -150,7 +173,7 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked_h(
   const int sms = fh::dev_sms();
   fh::SnakeParams sp;
   sp.x = (const float*)x16, sp.y = y, sp.a = a, sp.inv_b = inv_b, sp.filt = filt;
-  sp.batch_stride = batch_stride, sp.chunk_stride = chunk_stride;
+  sp.batch_stride = batch_stride, sp.chunk_stride = chunk_stride, sp.y_batch_stride = batch_stride, sp.lo_offset = 0;
   sp.row0 = row0, sp.nchunk = C / 8, sp.L = L, sp.ntile = 0, sp.total = 0, sp.fp16 = 1;
   sp.status = fh::status_word();
   // FH_SNAKE_H_CTAS=5: five CTAs per SM fit with the half-size fp16 windows (33 KB, 90 registers) -- measured SLOWER

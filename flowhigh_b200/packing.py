@@ -68,6 +68,17 @@ def conv_transpose1d_taps(weight: torch.Tensor, bias, stride: int) -> TappedConv
     return TappedConv(w, off, bias, u, ntaps)
 
 
+def split_input(tc: TappedConv, cin_pad: int) -> TappedConv:
+    """Weights for a hi + lo split activation operand (precision "fp16x2"): the input channels are doubled,
+    [0, cin) multiply the hi halves and [cin_pad, cin_pad + cin) the lo halves, with the SAME weights, so
+    W . (hi + lo) is accumulated in fp32 by the ordinary kernel over 2 * cin_pad input channels."""
+    P, ntaps, cout, cin = tc.w.shape
+    w = torch.zeros(P, ntaps, cout, 2 * cin_pad, dtype=tc.w.dtype, device=tc.w.device)
+    w[..., :cin] = tc.w
+    w[..., cin_pad:cin_pad + cin] = tc.w
+    return TappedConv(w, tc.off, tc.bias, tc.P, tc.ntaps)
+
+
 def f32_conv_buffers(tc: TappedConv, device):
     """fh_conv1d_taps_f32 operands: w [P][Cout][Cin][ntaps] fp32, off [P][ntaps] int32."""
     w = tc.w.permute(0, 2, 3, 1).contiguous().to(device)

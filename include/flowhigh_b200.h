@@ -185,6 +185,11 @@ int fh_convpost_tanh_f32(const float* x, const float* w, float bias, float* y, i
 int fh_transpose_f32(const float* src, float* dst, int B, int R, int C, void* stream);
 /* elementwise fp32 -> bf16 / fp16 (whole chunked buffers, halos included) */
 int fh_cast_f32_16(const float* src, void* dst, int64_t n, int fp16, void* stream);
+/* precision "fp16x2" (activation operands kept as hi + lo fp16 pairs against duplicated weights: ~22-bit activations at
+ * twice the MMAs; meets the LSD <= 0.05 dB bar on high-dynamic-range clips where 11-bit operands leave 0.08 dB):
+ * chunked fp32 [B][nchunk][rows][8] -> chunked 16-bit [B][2 nchunk][rows][8] = [round(x) | round(x - hi)], halos included. */
+int fh_cast_f32_16_split(const float* src, void* dst, int64_t chunk_elems, int nchunk, int64_t src_batch,
+                         int64_t dst_batch, int B, int fp16, void* stream);
 /* out = a + b + c + d (b, c, d optional): the mean over the AMP branches of a BigVGAN stage (bigvgan/models.py:181-187, each
  * branch pre-scaled by 1/num_kernels), as fp32 (out32) and / or 16-bit (out16); same flat geometry for all buffers. */
 int fh_sum_cast_f32(const float* a, const float* b, const float* c, const float* d, float* out32, void* out16,
@@ -239,6 +244,10 @@ int64_t fh_tc_packed_weight_bytes(int Cin, int Cout, int ntaps, int P, int bn);
 int fh_to_chunked_16(const float* src, int64_t src_batch, int64_t src_c, int64_t src_t,
                      void* dst, int64_t dst_batch, int64_t dst_chunk, int dst_row0,
                      int B, int C, int L, int fp16, void* stream);
+/* fh_to_chunked_16 with the hi + lo split: channels [0, C) = round(x), [Cpad, Cpad + C) = round(x - hi), Cpad = 8 ceil(C / 8) */
+int fh_to_chunked_16_split(const float* src, int64_t src_batch, int64_t src_c, int64_t src_t,
+                           void* dst, int64_t dst_batch, int64_t dst_chunk, int dst_row0,
+                           int B, int C, int L, int fp16, void* stream);
 /* chunked anti-aliased snake: x chunked fp32 -> y chunked (same geometry); out_kind 0 fp32, 1 bf16, 2 fp16 */
 int fh_snake_aa_chunked(const float* x, void* y, const float* a, const float* inv_b, const float* filt,
                         int64_t batch_stride, int64_t chunk_stride, int row0, int B, int C, int L,
@@ -247,6 +256,11 @@ int fh_snake_aa_chunked(const float* x, void* y, const float* a, const float* in
  * (alias_free_torch/act.py:23-28) between the two convolutions of an AMPBlock1 unit (bigvgan/models.py:63-72) */
 int fh_snake_aa_chunked_h(const void* x16, void* y, const float* a, const float* inv_b, const float* filt,
                           int64_t batch_stride, int64_t chunk_stride, int row0, int B, int C, int L, void* stream);
+/* Activation1d.forward with fp32 rows in and fp16 hi + lo rows out (precision "fp16x2"): y has 2 C channels per batch
+ * ([hi chunks | lo chunks], batch stride y_batch_stride); the input is split hi + lo inside the kernel as well. */
+int fh_snake_aa_chunked_split(const float* x, void* y, const float* a, const float* inv_b, const float* filt,
+                              int64_t x_batch_stride, int64_t y_batch_stride, int64_t chunk_stride, int row0,
+                              int B, int C, int L, void* stream);
 int fh_convpost_tanh_chunked(const float* x, int64_t batch_stride, int64_t chunk_stride, int row0,
                              const float* w, float bias, float* y, int B, int C, int L, void* stream);
 
