@@ -197,6 +197,103 @@ def cpu_baseline_subprocess(clip_seconds=10.0, steps=2, timeout=600):
         return {"error": repr(e)}
 
 
+# ------------------------------------------------------------------------------------------- sharded workloads
+def run_sharded_workload(args, model, eng, dev, world, rank, local):
+    """BASELINE configs[2] (`mixed512`) and configs[3] (`longform`): ONE job partitioned over the ranks (strong scaling),
+    through the public API from host buffers, the output gather (one ncclAllGather) and the D2H read inside the timed
+    region; time = max over ranks.  `value` = audio-seconds of the whole job per wall second."""
+    import torch
+    import torch.distributed as dist
+    from flowhigh_b200.synth import synth_speech
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    W = max(args.warmup, 3)
+    if args.workload == "mixed512":
+        rates = [8000, 12000, 16000, 24000]
+        base = {sr: [synth_speech(int(CLIP_SECONDS * sr), sr, seed=sr + i) for i in range(4)] for sr in rates}
+        srs = [rates[i % 4] for i in range(args.clips)]
+        audios = [base[srs[i]][(i // 4) % 4] for i in range(args.clips)]
+        N = int(CLIP_SECONDS * 48000) // 480
+        gen = torch.Generator(dev).manual_seed(99)
+        eps_all = torch.randn((args.clips, N, 256), device=dev, generator=gen)  # same on every rank
+        eps = [eps_all[i] for i in range(args.clips)]
+        out_host = torch.empty((args.clips, int(CLIP_SECONDS * 48000)), dtype=torch.float32).pin_memory() if rank == 0 else None
+        audio_s = args.clips * CLIP_SECONDS
+
+        def step():
+            out = model.generate_sharded(audios, srs, 48000, timestep=STEPS_ODE, eps=eps, gather=True)
+            if rank == 0:
+                out_host.copy_(out, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            return out
+        h2d = sum(a.size * 4 for a in audios)
+        d2h = args.clips * int(CLIP_SECONDS * 48000) * 4
+        wl = (f"configs[2]: {args.clips} x 10 s clips, 8/12/16/24 kHz mixed -> 48 kHz, sharded over {world} GPU(s) by assign_clips, "
+              "batches of <= 64 per rate group, outputs gathered with one all_gather_into_tensor (NCCL); basic_cfm, midpoint (2 NFE)")
+    else:
+        sr_in = 16000
+        ten = synth_speech(10 * sr_in, sr_in, seed=3)
+        reps = int(round(args.minutes * 6))
+        clip = np.concatenate([ten * (0.6 + 0.4 * np.cos(0.37 * k)) for k in range(reps)]).astype(np.float32)
+        T = clip.shape[0] * 3
+        clen, ov = 480000, 24000
+        K = -(-(T - clen) // (clen - ov)) + 1
+        eps_all = torch.randn((K, clen // 480, 256), device=dev, generator=torch.Generator(dev).manual_seed(7))
+        out_host = torch.empty((1, T), dtype=torch.float32).pin_memory() if rank == 0 else None
+        audio_s = T / 48000.0
+
+        def step():
+            out = model.generate_long(clip, sr_in, 48000, timestep=STEPS_ODE, chunk_seconds=10.0, overlap_seconds=0.5, eps=eps_all)
+            if rank == 0:
+                out_host.copy_(out, non_blocking=True)
+            torch.cuda.synchronize(dev)
+            return out
+        h2d, d2h = clip.size * 4, T * 4
+        wl = (f"configs[3]: one {args.minutes:g}-minute clip 16 kHz -> 48 kHz, {K} overlapped 10 s chunks (0.5 s overlap) in contiguous "
+              f"blocks over {world} GPU(s), one all_gather_into_tensor of the chunk waveforms, overlap-add + global post-processing; "
+              "basic_cfm, midpoint (2 NFE)")
+    for _ in range(W):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ts = []
+    for _ in range(args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        out = step()
+        barrier()
+        ts.append(time.perf_counter() - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor(ts, device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ts = [float(v) for v in t]
+    finite = bool(torch.isfinite(out).all())
+    if not finite:
+        raise RuntimeError("bench: non-finite output")
+    if rank == 0:
+        total = sum(ts)
+        med = statistics.median(ts)
+        line = {"metric": METRIC, "value": audio_s * args.steps / total, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": W, "ms_per_step": 1000 * total / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": {"workload": wl, "audio_seconds_per_step": audio_s, "sr_out": 48000, "nfe": 2,
+                           "parallelism": f"one job partitioned over {world} GPU(s); one NCCL all-gather of the outputs",
+                           "l2_policy": "per-step working set far exceeds the 126 MB L2; no flush needed"},
+                "e2e": {"value": audio_s * args.steps / total, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": int(d2h), "note": "the whole timed region IS the end-to-end path (host buffers in, "
+                        "gathered result read back on rank 0); max over ranks, wall clock around barriers"},
+                "latency_ms": {"p50": 1000 * med, "min": 1000 * min(ts), "max": 1000 * max(ts)},
+                "clocks": clocks, "self_check": {"finite": finite, "out_shape": list(out.shape)}}
+        print(json.dumps(line), flush=True)
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -213,6 +310,12 @@ def main():
     ap.add_argument("--no-latency", action="store_true")
     ap.add_argument("--latency-samples", type=int, default=200)
     ap.add_argument("--breakdown", default=None, help="write the per-kernel CUDA-event breakdown to this JSON file")
+    ap.add_argument("--workload", default="batch64", choices=["batch64", "mixed512", "longform"],
+                    help="batch64 = BASELINE configs[1] (the metric's configuration, default); mixed512 = configs[2]: 512 x 10 s "
+                         "clips, 8/12/16/24 kHz mixed, SHARDED over the ranks (strong scaling, outputs gathered with one "
+                         "ncclAllGather); longform = configs[3]: one 10-minute clip, overlapped chunks over the ranks + overlap-add")
+    ap.add_argument("--clips", type=int, default=512, help="mixed512: total number of clips")
+    ap.add_argument("--minutes", type=float, default=10.0, help="longform: clip length")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -246,6 +349,11 @@ def main():
 
     model = FlowHighSR.from_random(VocoderConfig.assumed_48k(), device=dev, seed=0, precision=args.precision)
     eng = model._engine()
+    if args.workload != "batch64":
+        run_sharded_workload(args, model, eng, dev, world, rank, local)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     n_in = int(CLIP_SECONDS * SR_IN)
     host = np.stack([synth_speech(n_in, SR_IN, seed=rank * B + i) for i in range(min(B, 8))])
     host = np.concatenate([host] * (-(-B // host.shape[0])))[:B]  # 8 distinct clips tiled (synthesis is slow)

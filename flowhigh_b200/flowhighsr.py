@@ -434,17 +434,30 @@ class FlowHighSR(nn.Module):
     @torch.no_grad()
     @_on_model_device
     def generate_long(self, audio, sr: int, target_sampling_rate=48000, timestep=1, chunk_seconds: float = 10.0,
-                      overlap_seconds: float = 0.5, eps: Optional[torch.Tensor] = None, max_batch: int = 64):
+                      overlap_seconds: float = 0.5, eps: Optional[torch.Tensor] = None, max_batch: int = 64,
+                      group=None, distributed: Optional[bool] = None):
         """Long-form generation by overlapped chunking + overlap-add (not in the reference,
         whose dense fp32 attention cannot hold a 10-minute clip).  The input is resampled and peak-normalised
         ONCE (global scalar), cut into uniform chunks in the 48 kHz domain, every chunk runs log-mel -> CFM ->
         vocoder as an independent clip, the vocoder outputs are cross-faded, and the STFT-domain
-        post-processing runs once over the stitched signal.  `eps` (optional) is [K, frames, 256]."""
+        post-processing (global cutoff bin, global output normalisation) runs once over the stitched signal.
+        `eps` (optional) is [K, frames, 256].
+
+        Multi-GPU (torch.distributed initialised, one process per GPU, every rank calls this with the same input):
+        rank r runs a contiguous block of the K chunks, ONE all_gather_into_tensor (ncclAllGather) puts all chunk
+        waveforms on every rank, and every rank stitches + post-processes (identical results, no second collective).
+        Per-chunk results do not depend on the batch they ran in, so the output is bit-identical to the 1-GPU call."""
+        import torch.distributed as dist
+        from . import sharding
         eng = self._engine()
         eng.new_call()
         eng.status_begin()
+        if distributed is None:
+            distributed = dist.is_available() and dist.is_initialized()
+        world = dist.get_world_size(group) if distributed else 1
+        rank = dist.get_rank(group) if distributed else 0
         x = torch.from_numpy(self._prep_input(audio))[None].to(eng.device)
-        cond = eng.resample_normalise(x, int(sr), target_sampling_rate)  # [1, T]
+        cond = eng.resample_normalise(x, int(sr), target_sampling_rate)  # [1, T]  (every rank: 0.1 % of the work)
         T = cond.shape[1]
         clen = int(round(chunk_seconds * 48000)) // 480 * 480
         ov = int(round(overlap_seconds * 48000)) // 480 * 480
@@ -455,22 +468,69 @@ class FlowHighSR(nn.Module):
         Tpad = (K - 1) * step + clen
         padded = torch.zeros((1, Tpad), dtype=torch.float32, device=eng.device)
         padded[:, :T] = cond
-        chunks = padded.unfold(1, clen, step)[0].contiguous()  # [K, clen] (views of overlapped spans, copied once)
-        waves = torch.empty((K, clen), dtype=torch.float32, device=eng.device)
-        for b0 in range(0, K, max_batch):
+        k0, k1, per = sharding.block_range(K, world, rank)
+        chunks = padded.unfold(1, clen, step)[0][k0:k1].contiguous()  # [K_local, clen] (overlapped spans, copied once)
+        waves = torch.empty((k1 - k0, clen), dtype=torch.float32, device=eng.device)
+        if eps is None:  # the same noise on every rank: rank 0's seed (an 8-byte broadcast), all K chunks drawn everywhere
+            seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64, device=eng.device)
+            if world > 1:
+                dist.broadcast(seed, 0, group=group)
+            g = torch.Generator(device=eng.device)
+            g.manual_seed(int(seed.item()))
+            eps = torch.randn((K, clen // 480, 256), dtype=torch.float32, device=eng.device, generator=g)
+        for b0 in range(0, k1 - k0, max_batch):
             c = chunks[b0: b0 + max_batch]
             mel_c = eng.encode(c)
-            e = None if eps is None else eps[b0: b0 + max_batch]
+            e = eps[k0 + b0: k0 + b0 + c.shape[0]]
             mel = eng.sample_mel(mel_c, self._noise_like(mel_c, e), steps=int(timestep),
                                  ode_method=self.odeint_kwargs["method"], cfm_method=self.cfm_method,
                                  sigma=float(self.sigma))
-            waves[b0: b0 + max_batch] = eng.vocoder(mel)
+            waves[b0: b0 + c.shape[0]] = eng.vocoder(mel)
+        if world > 1:
+            waves = sharding.gather_blocks(waves, per, K, group)  # the only collective of the path
         Tv = T // 480 * 480  # the vocoder emits whole frames (pred is shorter than src when T % 480 != 0)
         stitched = torch.empty((1, Tv), dtype=torch.float32, device=eng.device)
         eng._call("fh_ola_crossfade_f32", waves.data_ptr(), stitched.data_ptr(), K, clen, step, Tv, eng.stream)
         out = eng.postprocess(stitched, cond)
         self._check_status(eng)
         return out
+
+    @torch.no_grad()
+    @_on_model_device
+    def generate_sharded(self, audios: Sequence, sr: Union[int, Sequence[int]], target_sampling_rate=48000, timestep=1,
+                         eps: Optional[Sequence[torch.Tensor]] = None, max_batch: int = 64, group=None, gather: bool = True):
+        """A list of clips (mixed input rates allowed, equal OUTPUT length) over the GPUs of one box: every rank calls
+        this with the same list, `sharding.assign_clips` gives rank r its clips, they run through `generate_batch` in
+        batches of <= max_batch per (rate, length) group, and -- when `gather` -- ONE all_gather_into_tensor puts the
+        [n_clips, T] fp32 result on every rank in clip order.  No collective on the data path itself."""
+        import torch.distributed as dist
+        from . import sharding
+        distributed = dist.is_available() and dist.is_initialized()
+        world = dist.get_world_size(group) if distributed else 1
+        rank = dist.get_rank(group) if distributed else 0
+        srs = [sr] * len(audios) if isinstance(sr, int) else list(sr)
+        out_len = [-(-int(np.asarray(a).shape[-1]) * int(target_sampling_rate) // int(s)) for a, s in zip(audios, srs)]
+        parts = sharding.assign_clips(out_len, world)
+        mine = parts[rank]
+        results: List[Optional[torch.Tensor]] = [None] * len(mine)
+        by_rate: Dict[tuple, List[int]] = {}
+        for j, i in enumerate(mine):
+            by_rate.setdefault((int(srs[i]), int(np.asarray(audios[i]).shape[-1])), []).append(j)
+        for (s, _n), js in by_rate.items():
+            for b0 in range(0, len(js), max_batch):
+                sel = js[b0: b0 + max_batch]
+                outs = self.generate_batch([audios[mine[j]] for j in sel], s, target_sampling_rate, timestep,
+                                           eps=None if eps is None else [eps[mine[j]] for j in sel], pinned=True)
+                for j, o in zip(sel, outs):
+                    results[j] = o
+        if not gather:
+            return {i: results[j] for j, i in enumerate(mine)}
+        if len(set(out_len)) > 1:
+            raise ValueError("generate_sharded(gather=True) needs clips of one output length (use gather=False)")
+        T = out_len[0] if out_len else 0
+        eng = self._engine()
+        local = torch.cat(results, 0) if results else torch.empty((0, T), dtype=torch.float32, device=eng.device)
+        return sharding.gather_assigned(local, mine, parts, group)
 
     # ------------------------------------------------------------------ loaders
     @classmethod

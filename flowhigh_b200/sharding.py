@@ -4,7 +4,9 @@ Every clip is independent end to end (per-clip peak normalisation flowhighsr.py:
 attention, per-clip post-processing cutoff and normalisation postprocessing.py:26,40), so the path
 shards by clip with NO data-path collective: one process per GPU, weights replicated, rank r takes
 the clips `assign_clips` gives it.  A collective appears only when the caller wants all outputs
-on one rank (`gather_outputs`: torch.distributed all_gather_object of fp32 waveforms).
+on every rank: `gather_clip_tensor` / `gather_chunk_tensor` = ONE `all_gather_into_tensor` (ncclAllGather over
+NVLink / NVSwitch, or gloo on CPU) of the fp32 waveforms, padded to equal per-rank blocks.
+(`gather_outputs` is the ragged, pickling fallback for clips of unequal length.)
 
 Long-form audio (BASELINE config 4) is cut into overlapped chunks in the 48 kHz domain; every chunk
 runs the per-clip pipeline and the chunks are stitched by a linear cross-fade overlap-add.
@@ -72,6 +74,46 @@ def overlap_add(chunks: Sequence[np.ndarray], spans: Sequence[Tuple[int, int]], 
         out[s:e] += w * c
         wsum[s:e] += w
     return (out / np.maximum(wsum, 1e-12)).astype(np.float32)
+
+
+def block_range(n: int, world_size: int, rank: int) -> Tuple[int, int, int]:
+    """Contiguous block partition of n items: -> (start, end, per_rank) with per_rank = ceil(n / world_size);
+    ranks past the end get empty blocks.  Used for long-form chunks (neighbouring chunks stay on one GPU)."""
+    per = -(-n // world_size) if n > 0 else 0
+    s = min(rank * per, n)
+    return s, min(s + per, n), per
+
+
+def gather_blocks(local, per_rank: int, n: int, group=None):
+    """local: torch tensor [<= per_rank, ...] (this rank's block of `block_range`) -> [n, ...] on every rank with ONE
+    all_gather_into_tensor (ncclAllGather on CUDA tensors, gloo on CPU tensors).  Blocks are zero-padded to per_rank rows."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return local[:n]
+    pad = torch.zeros((per_rank,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    out = torch.empty((world * per_rank,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return out[:n]
+
+
+def gather_assigned(local, mine: Sequence[int], parts: Sequence[Sequence[int]], group=None):
+    """Clips distributed with `assign_clips` (all of one length): local [len(mine), T] -> [n_clips, T] in clip order on
+    every rank, one all_gather_into_tensor + an index permutation."""
+    import torch
+    n = sum(len(p) for p in parts)
+    per = max(len(p) for p in parts) if parts else 0
+    flat = gather_blocks(local, per, len(parts) * per, group) if len(parts) > 1 else local
+    if len(parts) == 1:
+        return local
+    out = torch.empty((n,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    for r, p in enumerate(parts):
+        if len(p):
+            idx = torch.as_tensor(list(p), device=local.device)
+            out[idx] = flat[r * per: r * per + len(p)]
+    return out
 
 
 def gather_outputs(local: Dict[int, np.ndarray], world_size: int, rank: int, group=None) -> Dict[int, np.ndarray]:

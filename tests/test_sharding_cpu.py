@@ -37,6 +37,13 @@ def test_chunk_plan_and_overlap_add_reconstruct(total, chunk, overlap):
     assert np.abs(y - x).max() <= 1e-6  # stitching identical chunks is the identity
 
 
+def test_block_range_covers_everything():
+    for n, w in ((64, 8), (5, 2), (3, 4), (0, 2), (61, 8)):
+        spans = [sharding.block_range(n, w, r) for r in range(w)]
+        assert [i for s, e, _ in spans for i in range(s, e)] == list(range(n))
+        assert len({p for _, _, p in spans}) == 1 and all(e - s <= p for s, e, p in spans)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -45,6 +52,16 @@ def _worker(rank, world, port, q):
     local = {i: np.full(lengths[i], float(i), np.float32) for i in mine}
     merged = sharding.gather_outputs(local, world, rank)
     ok = sorted(merged) == list(range(7)) and all(merged[i].shape[0] == lengths[i] and merged[i][0] == i for i in merged)
+    # tensor gathers (one all_gather_into_tensor each): contiguous blocks (long-form chunks) and assigned clips
+    K = 5
+    k0, k1, per = sharding.block_range(K, world, rank)
+    blk = torch.arange(k0, k1, dtype=torch.float32)[:, None].repeat(1, 3)
+    allc = sharding.gather_blocks(blk, per, K)
+    ok = ok and allc.shape == (K, 3) and torch.equal(allc[:, 0], torch.arange(K, dtype=torch.float32))
+    parts = sharding.assign_clips([480] * 7, world)
+    loc = torch.tensor([float(i) for i in parts[rank]])[:, None].repeat(1, 4)
+    allp = sharding.gather_assigned(loc, parts[rank], parts)
+    ok = ok and allp.shape == (7, 4) and torch.equal(allp[:, 1], torch.arange(7, dtype=torch.float32))
     t = torch.tensor([float(rank + 1)])  # bench.py reduces its timing the same way: max over ranks
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     q.put((rank, bool(ok and float(t) == world)))
