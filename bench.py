@@ -308,6 +308,7 @@ def main():
     ap.add_argument("--ref-clip-seconds", type=float, default=CLIP_SECONDS, help="reference arm: clip length per step")
     ap.add_argument("--ref-budget-seconds", type=float, default=240.0, help="reference arm: bound on the whole run")
     ap.add_argument("--no-latency", action="store_true")
+    ap.add_argument("--no-accurate", action="store_true", help="skip the fp16x2 (tolerance-on-every-fixture) leg")
     ap.add_argument("--latency-samples", type=int, default=200)
     ap.add_argument("--breakdown", default=None, help="write the per-kernel CUDA-event breakdown to this JSON file")
     ap.add_argument("--workload", default="batch64", choices=["batch64", "mixed512", "longform"],
@@ -520,6 +521,20 @@ def main():
                               "algorithmic_bytes_per_launch": sn["bytes"] / sn["launches"], "launches_per_step": sn["launches"],
                               "avg_launch_ms": sn["ms"] / sn["launches"], "share_of_step": sn["ms"] / tot_ms if tot_ms else None,
                               "note": "fp32 rows in (fp16 rows behind the first conv of an AMP unit), fp16 rows out; ncu: profiles/r1_ncu_snake.txt"}
+        # every other kernel class of the path: HBM roofline from its algorithmic bytes (attention: tensor roofline)
+        roofline_stages = {}
+        for k, v in breakdown.items():
+            if k.startswith("tc_conv") or k == "fh_snake_aa_chunked" or v["ms"] <= 0:
+                continue
+            if k == "fh_attention_tc" and v["flops"] > 0:
+                tf = v["flops"] / (v["ms"] / 1000.0) / 1e12
+                roofline_stages[k] = {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak,
+                                      "ms": v["ms"], "launches": v["launches"],
+                                      "note": "mma.sync m16n8k16 with the hi/lo operand split (3 MMAs per q k^T tile): algorithmic 4 N^2 Dh per head"}
+            elif v["bytes"] > 0:
+                gbs = v["bytes"] / (v["ms"] / 1000.0) / 1e9
+                roofline_stages[k] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                      "ms": v["ms"], "launches": v["launches"]}
         groups = {}
         for k, v in breakdown.items():
             gname = "tc_conv" if k.startswith("tc_conv") else k
@@ -533,6 +548,40 @@ def main():
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cpu = cpu_baseline_subprocess()
+        # ---- the same step in the mode that meets the LSD <= 0.05 dB bar on EVERY fixture (hi + lo activation operands):
+        #      reported beside the headline, never instead of it (tests: test_big_config_16bit_golden)
+        accurate = None
+        if world == 1 and args.precision == "fp16" and not args.no_accurate and B == BATCH:
+            del model, eng, step_resident, step_e2e
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            m2 = FlowHighSR.from_random(VocoderConfig.assumed_48k(), device=dev, seed=0, precision="fp16x2")
+            e2 = m2._engine()
+
+            def step_x2():
+                e2.new_call()
+                e2.status_begin()
+                cond = e2.resample_normalise(x_dev, SR_IN)
+                mel = e2.sample_mel(e2.encode(cond), eps, steps=STEPS_ODE, ode_method="midpoint", cfm_method="basic_cfm", sigma=0.0)
+                o = e2.postprocess(e2.vocoder(mel), cond)
+                e2.status_end()
+                return o
+            for _ in range(3):
+                step_x2()
+            torch.cuda.synchronize(dev)
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(3):
+                o2 = step_x2()
+            a1.record()
+            torch.cuda.synchronize(dev)
+            ams = a0.elapsed_time(a1) / 3
+            accurate = {"precision": "fp16x2", "ms_per_step": ams, "value": B * CLIP_SECONDS / (ams / 1000.0), "unit": UNIT,
+                        "finite": bool(torch.isfinite(o2).all()), "overflow_status": e2.status_read(),
+                        "note": "hi + lo fp16 activation operands against duplicated weights (2 x the vocoder MMAs): "
+                                "LSD 0.016-0.028 dB on every golden fixture; the default fp16 path meets 0.05 dB on this "
+                                "workload's own clip (0.019) and reaches 0.08 dB only on the high-dynamic-range configs[0] clip"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -540,8 +589,9 @@ def main():
             "per_gpu": value / world, "realtime_factor_per_gpu": value / world,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(host_t.numel() * 4),
                     "d2h_bytes_per_step": int(out_host.numel() * 4), "steps": e2e_steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_snake": roofline_snake, "cpu_baseline": cpu,
-            "latency": latency, "self_check": self_check,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_snake": roofline_snake,
+            "roofline_stages": roofline_stages, "cpu_baseline": cpu,
+            "latency": latency, "self_check": self_check, "accurate_mode": accurate,
             "stage_ms": {k: round(v["ms"], 3) for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])},
         }
         print(json.dumps(line), flush=True)

@@ -191,6 +191,8 @@ class Engine:
             work = {"bytes": float(args[8] * args[9] * args[10]) * (8.0 if args[11] == 0 else 6.0)}
         if work is None and name == "fh_snake_aa_chunked_h":  # fp16 in + fp16 out
             work = {"bytes": float(args[8] * args[9] * args[10]) * 4.0, "tag": "fh_snake_aa_chunked"}
+        if work is None and name == "fh_rmsnorm_f32":  # fp32 row in, fp32 / 16-bit row out  (args: ..., out_mode, rows, M, C, stream)
+            work = {"bytes": float(args[6] * args[7]) * (8.0 if args[4] == 0 else 6.0)}
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(self.device))
         _lib.check(getattr(self.lib, name)(*args), name)
@@ -354,9 +356,11 @@ class Engine:
             T_out = tables.resample_out_len(T_in, up, down)
             y = self.buf("rs_y", (B, T_out), zero=False)
             self._call("fh_resample_poly_f32", x.data_ptr(), y.data_ptr(), hd.data_ptr(), absmax.data_ptr(), B, T_in,
-                       T_out, hd.numel(), up, down, npp, npr, self.stream)
+                       T_out, hd.numel(), up, down, npp, npr, self.stream,
+                       work={"bytes": 4.0 * B * (T_in + T_out), "flops": 2.0 * B * T_out * (hd.numel() // up + 1)})
         cond = torch.empty((B, T_out), dtype=torch.float32, device=self.device)
-        self._call("fh_scale_by_absmax_f32", y.data_ptr(), cond.data_ptr(), absmax.data_ptr(), 1.0, B, T_out, self.stream)
+        self._call("fh_scale_by_absmax_f32", y.data_ptr(), cond.data_ptr(), absmax.data_ptr(), 1.0, B, T_out, self.stream,
+                   work={"bytes": 8.0 * B * T_out})
         return cond
 
     # ------------------------------------------------------------------ stage: log-mel
@@ -370,7 +374,8 @@ class Engine:
         mel = out if out is not None else torch.empty((B, N, 256), dtype=torch.float32, device=self.device)
         self._call("fh_stft_logmel_f32", audio.data_ptr(), mel.data_ptr(), self.window.data_ptr(), self.twiddle.data_ptr(),
                    self.mel_start.data_ptr(), self.mel_len.data_ptr(), self.mel_w.data_ptr(), self.mel_stride, B, T, N,
-                   1 if self.precise_mel else 0, self.stream)
+                   1 if self.precise_mel else 0, self.stream,
+                   work={"bytes": 4.0 * B * (T + N * 256), "flops": B * N * (5.0 * 2048 * 11 + 2.0 * 2030)})
         return mel
 
     # ------------------------------------------------------------------ stage: backbone
@@ -497,7 +502,7 @@ class Engine:
             self._sgemm(cond, Din, We.data_ptr() + Din * 4, 2 * Din, None, E, D, 1.0, 1.0, E, D, M, D, Din)
         wc = sd[FH + "conv_embed.dw_conv1d.0.weight"]
         self._call("fh_dwconv_gelu_res_f32", E.data_ptr(), wc.data_ptr(), sd[FH + "conv_embed.dw_conv1d.0.bias"].data_ptr(),
-                   h.data_ptr(), B, N, D, wc.shape[-1], st)
+                   h.data_ptr(), B, N, D, wc.shape[-1], st, work={"bytes": 8.0 * M * D, "flops": 2.0 * M * D * wc.shape[-1]})
         if b.architecture == "convnext":
             self._convnext_blocks(h, tcnd, B, N, M, D, act if self.tc else None, cs if self.tc else 0, Mp if self.tc else 0)
             fw, fb = sd[FH + "final_layer_norm.weight"], sd[FH + "final_layer_norm.bias"]
@@ -548,9 +553,11 @@ class Engine:
                 s16 = [self.buf(f"bb_{nm}16", (B, H, N, Dh), self.h16, zero=False) for nm in ("qh", "ql", "kh", "kl", "v")]
                 self._call("fh_qknorm_rope_split", qkv.data_ptr(), sd[p + "3.q_norm.gamma"].data_ptr(),
                            sd[p + "3.k_norm.gamma"].data_ptr(), sd[FH + "transformer.rotary_emb.inv_freq"].data_ptr(),
-                           *[t_.data_ptr() for t_ in s16], B, N, H, Dh, float(b.qk_norm_scale), self.fp16, st)
+                           *[t_.data_ptr() for t_ in s16], B, N, H, Dh, float(b.qk_norm_scale), self.fp16, st,
+                           work={"bytes": (12.0 + 10.0) * B * N * H * Dh})
+                # algorithmic: q k^T and p v, 2 N^2 Dh each per head; bytes: q (hi + lo), k (hi + lo), v in, out (all 16-bit)
                 self._call("fh_attention_tc", *[t_.data_ptr() for t_ in s16], act.data_ptr(), self.k16, Mp, B, H, N, Dh,
-                           self.fp16, st)
+                           self.fp16, st, work={"flops": 4.0 * B * H * N * N * Dh, "bytes": 2.0 * 6 * B * H * N * Dh})
             else:
                 self._call("fh_qknorm_rope_f32", qkv.data_ptr(), sd[p + "3.q_norm.gamma"].data_ptr(),
                            sd[p + "3.k_norm.gamma"].data_ptr(), sd[FH + "transformer.rotary_emb.inv_freq"].data_ptr(),
@@ -981,7 +988,7 @@ class Engine:
         self._call("fh_snake_aa_chunked", XS.data_ptr(), AP.data_ptr(), a.data_ptr(), ib.data_ptr(), f.data_ptr(), bs, cs,
                    HALO, B, ch, L, 0, st)
         self._call("fh_convpost_tanh_chunked", AP.data_ptr(), bs, cs, HALO, V["post_w"].data_ptr(), V["post_b"],
-                   wave.data_ptr(), B, ch, L, st)
+                   wave.data_ptr(), B, ch, L, st, work={"bytes": 4.0 * B * L * (ch + 1), "flops": 2.0 * B * L * ch * 7})
 
     # ------------------------------------------------------------------ stage: post-processing
     def postprocess(self, pred: torch.Tensor, src: torch.Tensor) -> torch.Tensor:
@@ -1002,10 +1009,12 @@ class Engine:
             # FFT(pred + i src) -> split -> splice -> inverse FFT
             ws = self.buf("pp_ws", (self.lib.fh_pp_energy_ws_bytes(B, NT) // 8,), torch.float64, zero=False)
             self._call("fh_pp_src_energy_f32", src.data_ptr(), en.data_ptr(), ws.data_ptr(), self.window.data_ptr(),
-                       self.twiddle.data_ptr(), B, T, NT, st)
+                       self.twiddle.data_ptr(), B, T, NT, st, work={"bytes": 4.0 * B * T, "flops": B * NT * 0.5 * 5.0 * 2048 * 11})
             self._call("fh_pp_cutoff", en.data_ptr(), cut.data_ptr(), B, 0.99, st)
+            # bytes: pred + src read once (algorithmic), windowed frames written (2048 per 480 new samples: the OLA input)
             self._call("fh_pp_fused_f32", pred.data_ptr(), src.data_ptr(), cut.data_ptr(), frames.data_ptr(),
-                       self.window.data_ptr(), self.twiddle.data_ptr(), B, Tp, T, NT, st)
+                       self.window.data_ptr(), self.twiddle.data_ptr(), B, Tp, T, NT, st,
+                       work={"bytes": 4.0 * B * (Tp + T) + 4.0 * B * NT * 2048, "flops": B * NT * 2.0 * 5.0 * 2048 * 11})
         else:
             sp = self.buf("pp_sp", (B, NTp, 1025, 2), zero=False)
             ss = self.buf("pp_ss", (B, NT, 1025, 2), zero=False)
@@ -1020,7 +1029,8 @@ class Engine:
         absmax = self.buf("pp_absmax", (B,), torch.int32)
         self._call("fh_fill_u32", absmax.data_ptr(), 0, B, st)
         self._call("fh_pp_overlap_add_f32", frames.data_ptr(), y.data_ptr(), self.window.data_ptr(), absmax.data_ptr(), B,
-                   nt, T, st)
+                   nt, T, st, work={"bytes": 4.0 * B * (nt * 2048 + T)})
         out = torch.empty((B, T), dtype=torch.float32, device=self.device)
-        self._call("fh_scale_by_absmax_f32", y.data_ptr(), out.data_ptr(), absmax.data_ptr(), 0.99, B, T, st)
+        self._call("fh_scale_by_absmax_f32", y.data_ptr(), out.data_ptr(), absmax.data_ptr(), 0.99, B, T, st,
+                   work={"bytes": 8.0 * B * T})
         return out
