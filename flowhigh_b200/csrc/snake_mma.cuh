@@ -38,8 +38,9 @@ struct SnakeMmaGeom {
   static constexpr int kXBytes = kXRows * 32;  // fp32 rows; fp16 input rows take half of it
   static constexpr int kWarpYBytes = kWarpRows * 16;
   // two input windows, per warp two output images, 128 control bytes: two mbarriers, two release counters, 2 x 12 taps
-  static constexpr int smem_bytes(bool in16, bool split_out = false) {
-    return 2 * (in16 ? kXBytes / 2 : kXBytes) + (split_out ? 4 : 2) * kWarps * kWarpYBytes + 128;
+  // wbuf input windows (2 = double buffered; 1 = single: a third CTA fits per SM and the other CTAs cover the refill)
+  static constexpr int smem_bytes(bool in16, bool split_out = false, int wbuf = 2) {
+    return wbuf * (in16 ? kXBytes / 2 : kXBytes) + (split_out ? 4 : 2) * kWarps * kWarpYBytes + 128;
   }
 };
 
@@ -309,16 +310,16 @@ __device__ __forceinline__ void snake_mma_unit(const SnakeFrags& F, float* xw, u
 // IN16: the input is already fp16 on the same chunked layout (16-byte rows, written by the 16-bit epilogue of the
 // preceding convolution): the A fragments of the up stage come straight from the window with one ldmatrix.x4.trans
 // per 8 up-samples (identity k-slot -> time map), no conversion instructions at all.
-template <bool SPLIT_X, bool SPLIT_F, int NB, bool IN16 = false, bool SPLIT_OUT = false>
+template <bool SPLIT_X, bool SPLIT_F, int NB, bool IN16 = false, bool SPLIT_OUT = false, int WBUF = 2>
 __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned char* smem, int tid, int cta, int nctas) {
   using G = SnakeMmaGeom<NB>;
   const int lane = tid & 31, warp = tid >> 5;
   constexpr int kXB = IN16 ? G::kXBytes / 2 : G::kXBytes;  // bytes of one input window
   float* xs0 = reinterpret_cast<float*>(smem);
-  float* xs1 = reinterpret_cast<float*>(smem + kXB);
+  float* xs1 = reinterpret_cast<float*>(smem + (WBUF - 1) * kXB);
   constexpr int kImg = SPLIT_OUT ? 2 : 1;  // images per buffer (hi, lo)
-  unsigned char* ys0 = smem + 2 * kXB + warp * 2 * kImg * G::kWarpYBytes;  // this warp's two output buffers
-  unsigned char* ctl = smem + 2 * kXB + 2 * kImg * G::kWarps * G::kWarpYBytes;
+  unsigned char* ys0 = smem + WBUF * kXB + warp * 2 * kImg * G::kWarpYBytes;  // this warp's two output buffers
+  unsigned char* ctl = smem + WBUF * kXB + 2 * kImg * G::kWarps * G::kWarpYBytes;
   const uint32_t bar0 = sw_u32(ctl);
   int* released = reinterpret_cast<int*>(ctl + 16);  // warps done with window 0 / 1
   float* s_taps = reinterpret_cast<float*>(ctl + 32);  // [0, 12): up-filter taps (2 f), [12, 24): down-filter taps (f)
@@ -330,7 +331,7 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
     snake_mma_make_taps<SPLIT_F>(S.filt, s_taps);
   }
   // rows a clipped copy does not fill must hold finite values (they only ever meet zero filter weights)
-  for (int i = tid; i < 2 * kXB / 16; i += 32 * G::kWarps) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = tid; i < WBUF * kXB / 16; i += 32 * G::kWarps) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
   const int rows_per_chunk = (int)(S.chunk_stride >> 3);
@@ -360,9 +361,9 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
   int item = cta;
   if (tid == 0) {
     if (item < S.total) issue(item, 0);
-    if (item + nctas < S.total) issue(item + nctas, 1);
+    if (WBUF == 2 && item + nctas < S.total) issue(item + nctas, 1);
   }
-  int buf = 0;
+  int buf = 0, ybuf = 0;
   uint32_t ph0 = 0, ph1 = 0;
   const int ssA = warp * G::kWarpRows;  // first tile row of this warp's half A; half B starts kSeg rows later
   for (; item < S.total; item += nctas) {
@@ -375,7 +376,7 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
     sw_mbar_wait(bar0 + 8 * buf, buf ? ph1 : ph0);
     if (buf) ph1 ^= 1; else ph0 ^= 1;
     float* xt = buf ? xs1 : xs0;
-    unsigned char* yt = ys0 + (size_t)buf * kImg * G::kWarpYBytes;
+    unsigned char* yt = ys0 + (size_t)ybuf * kImg * G::kWarpYBytes;
     if (active) {
       float* xw = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(xt) + (size_t)ssA * (IN16 ? 16 : 32));
       snake_mma_unit<SPLIT_X, SPLIT_F, NB, IN16, SPLIT_OUT>(F, xw, yt, qt + ssA, S.L, ch, S.a, S.inv_b, S.filt, edge, -ssA,
@@ -405,13 +406,14 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
       if (atomicAdd(&released[buf], 1) == G::kWarps - 1) {
         released[buf] = 0;  // next touched after the refill below has landed and been consumed
         __threadfence_block();
-        if (item + 2 * nctas < S.total) {
+        if (item + WBUF * nctas < S.total) {
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          issue(item + 2 * nctas, buf);
+          issue(item + WBUF * nctas, buf);
         }
       }
     }
-    buf ^= 1;
+    if (WBUF == 2) buf ^= 1;
+    ybuf ^= 1;
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   guard.commit(S.status, 1);

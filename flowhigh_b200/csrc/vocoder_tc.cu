@@ -22,49 +22,68 @@ __global__ void __launch_bounds__(128, 4) snake_aa_chunked_tma_kernel(const __gr
 
 // fp16 output mode: both FIR filters as Toeplitz MMAs (snake_mma.cuh).  MODE bit 0: hi/lo split of the input,
 // bit 1: hi/lo split of the filter taps.
-template <int MODE, int NB, int MINB, bool IN16, bool SPLIT_OUT>
+template <int MODE, int NB, int MINB, bool IN16, bool SPLIT_OUT, int WBUF>
 __global__ void __launch_bounds__(128, MINB) snake_aa_mma_kernel(const __grid_constant__ fh::SnakeParams S) {
   extern __shared__ __align__(128) unsigned char snake_smem[];
-  fh::snake_mma_cta<(MODE & 1) != 0, (MODE & 2) != 0, NB, IN16, SPLIT_OUT>(S, snake_smem, threadIdx.x, blockIdx.x, gridDim.x);
+  fh::snake_mma_cta<(MODE & 1) != 0, (MODE & 2) != 0, NB, IN16, SPLIT_OUT, WBUF>(S, snake_smem, threadIdx.x, blockIdx.x,
+                                                                                 gridDim.x);
 }
 
-template <int MODE, int NB, int MINB, bool IN16 = false, bool SPLIT_OUT = false>
+template <int MODE, int NB, int MINB, bool IN16 = false, bool SPLIT_OUT = false, int WBUF = 2>
 void launch_snake_mma(fh::SnakeParams sp, int B, int C, int L, int sms, cudaStream_t stream) {
   using G = fh::SnakeMmaGeom<NB>;
   static int smem_set[64] = {0};
-  fh::ensure_dyn_smem(snake_aa_mma_kernel<MODE, NB, MINB, IN16, SPLIT_OUT>, G::smem_bytes(IN16, SPLIT_OUT), smem_set);
+  fh::ensure_dyn_smem(snake_aa_mma_kernel<MODE, NB, MINB, IN16, SPLIT_OUT, WBUF>, G::smem_bytes(IN16, SPLIT_OUT, WBUF), smem_set);
   sp.ntile = (L + G::kRows - 1) / G::kRows;
   const long long total = (long long)sp.ntile * (C / 8) * B;
   sp.total = (int)total;
   const int grid = (int)(total < (long long)sms * MINB ? total : (long long)sms * MINB);
-  snake_aa_mma_kernel<MODE, NB, MINB, IN16, SPLIT_OUT><<<grid, 128, G::smem_bytes(IN16, SPLIT_OUT), stream>>>(sp);
+  snake_aa_mma_kernel<MODE, NB, MINB, IN16, SPLIT_OUT, WBUF><<<grid, 128, G::smem_bytes(IN16, SPLIT_OUT, WBUF), stream>>>(sp);
 }
 
-__global__ void convpost_tanh_chunked_kernel(const float* __restrict__ x, long long batch_stride,
-                                             long long chunk_stride, int row0, const float* __restrict__ w, float bias,
-                                             float* __restrict__ y, int C, int L) {
-  const int b = blockIdx.y;
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= L) return;
+// conv_post (C -> 1, k = 7, zero padding) + tanh on the chunked fp32 layout (bigvgan/models.py:190-192).  HBM-bound:
+// 4 (C + 1) bytes per output sample.  A CTA stages the (256 + 6)-row window of every 8-channel chunk in shared memory with
+// coalesced 16-byte loads (each input row is read from HBM once; the first version re-read it 7 times through L1 and
+// reached 1.6 TB/s), then one thread per output sample walks the 7 taps x C channels from shared memory; the 7 C weights
+// are broadcast reads of a shared table.
+constexpr int kCpT = 256;  // outputs per CTA
+__global__ void __launch_bounds__(kCpT) convpost_tanh_chunked_kernel(const float* __restrict__ x, long long batch_stride,
+                                                                     long long chunk_stride, int row0,
+                                                                     const float* __restrict__ w, float bias,
+                                                                     float* __restrict__ y, int C, int L) {
+  extern __shared__ __align__(16) float cp_smem[];
+  const int nchunk = C >> 3;
+  float* s_w = cp_smem;                              // [C][7] padded to a multiple of 4 floats
+  float* tile = cp_smem + ((C * 7 + 3) & ~3);        // [nchunk][kCpT + 6][8]
+  const int b = blockIdx.y, t0 = blockIdx.x * kCpT;
+  for (int i = threadIdx.x; i < C * 7; i += kCpT) s_w[i] = __ldg(w + i);
   const float* xb = x + (long long)b * batch_stride;
+  const int rows = kCpT + 6;
+  for (int i = threadIdx.x; i < nchunk * rows * 2; i += kCpT) {
+    const int h = i & 1, r = (i >> 1) % rows, ch = (i >> 1) / rows;
+    const int t = t0 - 3 + r;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < L) v = __ldg(reinterpret_cast<const float4*>(xb + (long long)ch * chunk_stride + (long long)(row0 + t) * 8) + h);
+    reinterpret_cast<float4*>(tile)[i] = v;  // same (chunk, row, half) order as the flat index
+  }
+  __syncthreads();
+  const int t = t0 + threadIdx.x;
+  if (t >= L) return;
   float acc = bias;
-  for (int c0 = 0; c0 < C; c0 += 8) {
-    const float* xc = xb + (long long)(c0 >> 3) * chunk_stride;
+  for (int ch = 0; ch < nchunk; ++ch) {
+    const float* tp = tile + ((size_t)ch * rows + threadIdx.x) * 8;
+    const float* wp = s_w + ch * 56;
 #pragma unroll
     for (int j = 0; j < 7; ++j) {
-      const int tt = t + j - 3;
-      if (tt < 0 || tt >= L) continue;
-      const float4* p = reinterpret_cast<const float4*>(xc + (long long)(row0 + tt) * 8);
-      const float4 v0 = __ldg(p), v1 = __ldg(p + 1);
-      const float* wj = w + c0 * 7 + j;
-      acc = fmaf(__ldg(wj), v0.x, acc);
-      acc = fmaf(__ldg(wj + 7), v0.y, acc);
-      acc = fmaf(__ldg(wj + 14), v0.z, acc);
-      acc = fmaf(__ldg(wj + 21), v0.w, acc);
-      acc = fmaf(__ldg(wj + 28), v1.x, acc);
-      acc = fmaf(__ldg(wj + 35), v1.y, acc);
-      acc = fmaf(__ldg(wj + 42), v1.z, acc);
-      acc = fmaf(__ldg(wj + 49), v1.w, acc);
+      const float4 v0 = *reinterpret_cast<const float4*>(tp + j * 8), v1 = *reinterpret_cast<const float4*>(tp + j * 8 + 4);
+      acc = fmaf(wp[j], v0.x, acc);
+      acc = fmaf(wp[7 + j], v0.y, acc);
+      acc = fmaf(wp[14 + j], v0.z, acc);
+      acc = fmaf(wp[21 + j], v0.w, acc);
+      acc = fmaf(wp[28 + j], v1.x, acc);
+      acc = fmaf(wp[35 + j], v1.y, acc);
+      acc = fmaf(wp[42 + j], v1.z, acc);
+      acc = fmaf(wp[49 + j], v1.w, acc);
     }
   }
   y[(long long)b * L + t] = tanhf(acc);
@@ -119,7 +138,13 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
       const char* e = getenv("FH_SNAKE_NB");
       nb16 = (e && atoi(e) == 8) ? 0 : 1;
     }
-    if (mma_mode == 0 && nb16) launch_snake_mma<0, 16, 2>(sp, B, C, L, sms, cs);
+    static int wbuf1 = -1;  // FH_SNAKE_WBUF=1: single input window, 3 CTAs (12 warps) per SM instead of 2
+    if (wbuf1 < 0) {
+      const char* e = getenv("FH_SNAKE_WBUF");
+      wbuf1 = (e && atoi(e) == 1) ? 1 : 0;
+    }
+    if (mma_mode == 0 && nb16 && wbuf1) launch_snake_mma<0, 16, 3, false, false, 1>(sp, B, C, L, sms, cs);
+    else if (mma_mode == 0 && nb16) launch_snake_mma<0, 16, 2>(sp, B, C, L, sms, cs);
     else if (mma_mode == 0) launch_snake_mma<0, 8, 4>(sp, B, C, L, sms, cs);
     else if (mma_mode == 3) launch_snake_mma<3, 8, 4>(sp, B, C, L, sms, cs);
     else launch_snake_mma<1, 8, 4>(sp, B, C, L, sms, cs);
@@ -188,7 +213,13 @@ extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked_h(
     const char* e = getenv("FH_SNAKE_NB");
     nb16 = (e && atoi(e) == 8) ? 0 : 1;
   }
-  if (nb16) launch_snake_mma<0, 16, 3, true>(sp, B, C, L, sms, (cudaStream_t)stream);
+  static int wbuf1 = -1;  // FH_SNAKE_WBUF=1: single input window, 4 CTAs (16 warps) per SM instead of 3
+  if (wbuf1 < 0) {
+    const char* e = getenv("FH_SNAKE_WBUF");
+    wbuf1 = (e && atoi(e) == 1) ? 1 : 0;
+  }
+  if (nb16 && wbuf1) launch_snake_mma<0, 16, 4, true, false, 1>(sp, B, C, L, sms, (cudaStream_t)stream);
+  else if (nb16) launch_snake_mma<0, 16, 3, true>(sp, B, C, L, sms, (cudaStream_t)stream);
   else if (per_sm == 5) launch_snake_mma<0, 8, 5, true>(sp, B, C, L, sms, (cudaStream_t)stream);
   else launch_snake_mma<0, 8, 4, true>(sp, B, C, L, sms, (cudaStream_t)stream);
   return fh::check_launch("fh_snake_aa_chunked_h");
@@ -199,7 +230,11 @@ extern "C" __attribute__((visibility("default"))) int fh_convpost_tanh_chunked(
     int C, int L, void* stream) {
   FH_REQUIRE(B > 0 && C > 0 && (C % 8) == 0 && L > 0 && B <= 65535, FH_ERR_BAD_SHAPE,
              "fh_convpost_tanh_chunked: bad shape");
-  convpost_tanh_chunked_kernel<<<dim3((L + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(x, batch_stride, chunk_stride,
-                                                                                        row0, w, bias, y, C, L);
+  const int smem = (((C * 7 + 3) & ~3) + (C / 8) * (kCpT + 6) * 8) * (int)sizeof(float);
+  FH_REQUIRE(smem <= 200 * 1024, FH_ERR_UNSUPPORTED_CFG, "fh_convpost_tanh_chunked: C=%d too wide for the shared-memory tile", C);
+  static int smem_set[64] = {0};
+  if (smem > 48 * 1024) fh::ensure_dyn_smem(convpost_tanh_chunked_kernel, smem, smem_set);
+  convpost_tanh_chunked_kernel<<<dim3((L + kCpT - 1) / kCpT, B), kCpT, smem, (cudaStream_t)stream>>>(x, batch_stride, chunk_stride,
+                                                                                               row0, w, bias, y, C, L);
   return fh::check_launch("fh_convpost_tanh_chunked");
 }

@@ -921,7 +921,9 @@ def test_fp16_overflow_is_reported_not_silent(cuda_device, case):
         wide = build(hot, precision)  # (keep the model alive: its sub-modules only hold a weak reference to it)
         out = wide.flowhigh.audio_enc_dec.decode(mel).cpu()
         assert torch.isfinite(out).all()
-        if precision == "fp32":
+        if precision == "fp32" and case == "weights":
+            # (beta -> e^-10.5 beta makes the net chaotic: 36000 x sin^2 terms, +-1 saturated tanh output; only the
+            #  linear "weights" case is comparable sample by sample)
             assert snr_db(ref, out) >= 40.0
     mild = build(variant(300.0, 0.0), "fp16")
     assert torch.isfinite(mild.sample(cond=mel, time_steps=1, decode_to_audio=True)).all()  # in range: guard silent
