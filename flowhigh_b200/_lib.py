@@ -88,6 +88,7 @@ SIGNATURES = {
     "fh_snake_aa_chunked_split": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i64, _i, _i, _i, _i, _p]),
     "fh_snake_aa_chunked": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _i, _p]),
     "fh_snake_aa_chunked_h": (_i, [_p, _p, _p, _p, _p, _i64, _i64, _i, _i, _i, _i, _p]),
+    "fh_snakepost_convpost_tanh": (_i, [_p, _i64, _i64, _i, _p, _p, _p, _p, _f, _p, _i, _i, _i, _p]),
     "fh_convpost_tanh_chunked": (_i, [_p, _i64, _i64, _i, _p, _f, _p, _i, _i, _i, _p]),
 }
 

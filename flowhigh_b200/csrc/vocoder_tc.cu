@@ -89,6 +89,143 @@ __global__ void __launch_bounds__(kCpT) convpost_tanh_chunked_kernel(const float
   y[(long long)b * L + t] = tanhf(acc);
 }
 
+// ------------------------------------------------------------------------------ activation_post + conv_post + tanh
+// The tail of BigVGAN.forward in ONE kernel (bigvgan/models.py:189-192): Activation1d(SnakeBeta) on the last stage's
+// fp32 rows, Conv1d(C -> 1, k = 7, zero padding) and tanh.  The activated tensor (4 C bytes per sample written and read
+// back by the two-kernel form) never leaves shared memory: HBM traffic is 4 C bytes in + 4 bytes out per sample.
+// A CTA of 128 threads owns 512 output samples.  Per 8-channel chunk it stages the (544 + 10)-row fp32 window
+// (replicate-clamped rows: the snake's own padding), runs the register-blocked scalar snake of snake_worker.cuh (one
+// thread = 2 channels x 17 rows, all taps packed FFMA2) and writes the activated rows, zeroed outside [0, L) (the conv's
+// zero padding), into a shared tile.  Then one thread = 4 consecutive outputs: it walks its 10 tile rows ONCE with the 56
+// weights of the chunk in registers (the two-kernel form re-read every row 7 times from L1).  Tile rows carry a 16-byte
+// pad every 4 rows so that the 128-byte row stride between neighbouring threads does not land on one bank group.
+constexpr int kSpR = 17, kSpRows = 32 * kSpR, kSpT = 512, kSpXRows = kSpRows + 10;
+constexpr int kSpTileBytes = kSpRows * 32 + (kSpRows / 4) * 16;  // one chunk's activated rows, padded
+__device__ __forceinline__ int sp_row_off(int a) { return a * 32 + (a >> 2) * 16; }
+
+__global__ void __launch_bounds__(128) snakepost_convpost_tanh_kernel(const float* __restrict__ x, long long batch_stride,
+                                                                      long long chunk_stride, int row0,
+                                                                      const float* __restrict__ sn_a,
+                                                                      const float* __restrict__ sn_inv_b,
+                                                                      const float* __restrict__ filt,
+                                                                      const float* __restrict__ w, float bias,
+                                                                      float* __restrict__ y, int C, int L) {
+  extern __shared__ __align__(16) unsigned char sp_smem[];
+  const int nchunk = C >> 3;
+  float* s_w = reinterpret_cast<float*>(sp_smem);                                    // [C][7]
+  float* xs = reinterpret_cast<float*>(sp_smem + (((C * 7 + 3) & ~3) * 4));          // [kSpXRows][8]
+  unsigned char* tile = reinterpret_cast<unsigned char*>(xs) + kSpXRows * 32;        // [nchunk][kSpTileBytes]
+  const int tid = threadIdx.x, b = blockIdx.y, t0 = blockIdx.x * kSpT;
+  const int tA0 = t0 - 3;  // time of tile row 0
+  for (int i = tid; i < C * 7; i += 128) s_w[i] = __ldg(w + i);
+  float2 fu[12], fd[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const float fk = __ldg(filt + k);
+    fu[k] = make_float2(2.0f * fk, 2.0f * fk);
+    fd[k] = make_float2(fk, fk);
+  }
+  const int e2 = tid & 3, g = tid >> 2;
+  const float* xb = x + (long long)b * batch_stride;
+  for (int ch = 0; ch < nchunk; ++ch) {
+    __syncthreads();  // the previous chunk's window has been consumed
+    for (int i = tid; i < kSpXRows * 2; i += 128) {
+      const int r = i >> 1, h = i & 1;
+      const int t = min(max(tA0 - 5 + r, 0), L - 1);  // replicate clamp (resample.py:27, filter.py:88)
+      reinterpret_cast<float4*>(xs)[i] = __ldg(reinterpret_cast<const float4*>(xb + (long long)ch * chunk_stride + (long long)(row0 + t) * 8) + h);
+    }
+    __syncthreads();
+    const int q0 = tA0 + g * kSpR;  // time of this thread's first row
+    unsigned char* tp = tile + (size_t)ch * kSpTileBytes;
+    if (q0 < L && q0 + kSpR > 0) {
+      const int c0 = ch * 8 + 2 * e2;
+      const float2 al2 = make_float2(2.0f * __ldg(sn_a + c0), 2.0f * __ldg(sn_a + c0 + 1));
+      const float2 hib = make_float2(0.5f * __ldg(sn_inv_b + c0), 0.5f * __ldg(sn_inv_b + c0 + 1));
+      const float2 nhib = make_float2(-hib.x, -hib.y);
+      float2 xv[kSpR + 10];
+      const float* xp = xs + g * (kSpR * 8) + 2 * e2;
+#pragma unroll
+      for (int j = 0; j < kSpR + 10; ++j) xv[j] = *reinterpret_cast<const float2*>(xp + j * 8);
+      float2 sv[2 * kSpR + 10];
+#pragma unroll
+      for (int i = 0; i < 2 * kSpR + 10; ++i) {
+        const int qq = (i - 5) >> 1;
+        float2 u = make_float2(0.f, 0.f);
+        if ((i & 1) == 0) {
+#pragma unroll
+          for (int d = -2; d <= 3; ++d) u = fh::sw_ffma2(xv[qq + d + 5], fu[6 - 2 * d], u);
+        } else {
+#pragma unroll
+          for (int d = -3; d <= 2; ++d) u = fh::sw_ffma2(xv[qq + d + 5], fu[5 - 2 * d], u);
+        }
+        const float2 z = fh::sw_fmul2(u, al2);
+        const float2 cz = make_float2(__cosf(z.x), __cosf(z.y));
+        sv[i] = fh::sw_ffma2(cz, nhib, u);
+      }
+      // replicate clamp of the 2x-rate signal: local index i holds s'[2 q0 - 5 + i]; s'[m < 0] = s'[0], s'[m > 2L-1] = s'[2L-1]
+      const int i_lo = 5 - 2 * q0, i_hi = 2 * (L - q0) + 4;
+      if (i_lo > 0 || i_hi < 2 * kSpR + 9) {
+        float2 lo_v = sv[0], hi_v = sv[2 * kSpR + 9];
+#pragma unroll
+        for (int i = 0; i < 2 * kSpR + 10; ++i) {
+          if (i == i_lo) lo_v = sv[i];
+          if (i == i_hi) hi_v = sv[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * kSpR + 10; ++i) {
+          if (i < i_lo) sv[i] = lo_v;
+          if (i > i_hi) sv[i] = hi_v;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kSpR; ++j) {
+        float2 acc = hib;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) acc = fh::sw_ffma2(fd[k], sv[2 * j + k], acc);
+        const int t = q0 + j;
+        if (t < 0 || t >= L) acc = make_float2(0.f, 0.f);  // conv_post zero padding
+        *reinterpret_cast<float2*>(tp + sp_row_off(g * kSpR + j) + 8 * e2) = acc;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < kSpR; ++j) *reinterpret_cast<float2*>(tp + sp_row_off(g * kSpR + j) + 8 * e2) = make_float2(0.f, 0.f);
+    }
+  }
+  __syncthreads();
+  // ---- conv_post + tanh: outputs t0 + 4 tid + {0..3} from tile rows 4 tid .. 4 tid + 9
+  const int o = 4 * tid;
+  if (t0 + o >= L) return;
+  float acc[4] = {bias, bias, bias, bias};
+  for (int ch = 0; ch < nchunk; ++ch) {
+    float wr[56];
+#pragma unroll
+    for (int i = 0; i < 56; ++i) wr[i] = s_w[ch * 56 + i];  // [c][7]
+    const unsigned char* tp = tile + (size_t)ch * kSpTileBytes;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+      const float4 v0 = *reinterpret_cast<const float4*>(tp + sp_row_off(o + r));
+      const float4 v1 = *reinterpret_cast<const float4*>(tp + sp_row_off(o + r) + 16);
+      const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int oo = 0; oo < 4; ++oo) {
+        const int j = r - oo;  // tap
+        if (j >= 0 && j < 7) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[oo] = fmaf(wr[c * 7 + j], v[c], acc[oo]);
+        }
+      }
+    }
+  }
+  float* yp = y + (long long)b * L + t0 + o;
+  if (t0 + o + 3 < L && ((((long long)b * L + t0 + o) & 3) == 0)) {
+    *reinterpret_cast<float4*>(yp) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
+  } else {
+#pragma unroll
+    for (int oo = 0; oo < 4; ++oo)
+      if (t0 + o + oo < L) yp[oo] = tanhf(acc[oo]);
+  }
+}
+
 }  // namespace
 
 extern "C" __attribute__((visibility("default"))) int fh_snake_aa_chunked(
@@ -237,4 +374,21 @@ extern "C" __attribute__((visibility("default"))) int fh_convpost_tanh_chunked(
   convpost_tanh_chunked_kernel<<<dim3((L + kCpT - 1) / kCpT, B), kCpT, smem, (cudaStream_t)stream>>>(x, batch_stride, chunk_stride,
                                                                                                row0, w, bias, y, C, L);
   return fh::check_launch("fh_convpost_tanh_chunked");
+}
+
+// activation_post + conv_post + tanh fused (bigvgan/models.py:189-192): x chunked fp32 [B][C/8][Lp][8] -> y [B, L]
+extern "C" __attribute__((visibility("default"))) int fh_snakepost_convpost_tanh(
+    const float* x, int64_t batch_stride, int64_t chunk_stride, int row0, const float* a, const float* inv_b,
+    const float* filt, const float* w, float bias, float* y, int B, int C, int L, void* stream) {
+  FH_REQUIRE(B > 0 && C > 0 && (C % 8) == 0 && C <= 64 && L > 0 && B <= 65535, FH_ERR_BAD_SHAPE,
+             "fh_snakepost_convpost_tanh: C must be a multiple of 8, <= 64");
+  FH_REQUIRE(((uintptr_t)x % 16) == 0 && (batch_stride % 8) == 0 && (chunk_stride % 8) == 0, FH_ERR_BAD_ALIGN,
+             "fh_snakepost_convpost_tanh: alignment");
+  const int smem = ((C * 7 + 3) & ~3) * 4 + kSpXRows * 32 + (C / 8) * kSpTileBytes;
+  static int smem_set[64] = {0};
+  cudaError_t e = fh::ensure_dyn_smem(snakepost_convpost_tanh_kernel, smem, smem_set);
+  FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_snakepost_convpost_tanh: cannot opt in to %d bytes of smem", smem);
+  snakepost_convpost_tanh_kernel<<<dim3((L + kSpT - 1) / kSpT, B), 128, smem, (cudaStream_t)stream>>>(
+      x, batch_stride, chunk_stride, row0, a, inv_b, filt, w, bias, y, C, L);
+  return fh::check_launch("fh_snakepost_convpost_tanh");
 }

@@ -113,6 +113,7 @@ class Engine:
             self._prep_backbone()
             self._prep_vocoder()
         torch.cuda.synchronize(dev)
+        self._bind_status()
 
     # ------------------------------------------------------------------ plumbing
     @property
@@ -124,7 +125,22 @@ class Engine:
         become evictable when the cache cap is hit, and the calling thread's launches report to this engine's
         status word."""
         self._buf_epoch += 1
+        self._bind_status()
+
+    _status_owner = None  # id of the engine whose status word the library currently holds (this thread)
+
+    def _bind_status(self):
         _lib.check(self.lib.fh_set_status_word(self.status.data_ptr()), "fh_set_status_word")
+        Engine._status_owner = id(self)
+
+    def __del__(self):
+        # never leave the library pointing at a status word that is about to be freed
+        try:
+            if Engine._status_owner == id(self):
+                self.lib.fh_set_status_word(None)
+                Engine._status_owner = None
+        except Exception:  # interpreter shutdown
+            pass
 
     def status_begin(self):
         """Zeroes the status word (stream-ordered; capturable)."""
@@ -922,12 +938,23 @@ class Engine:
                 a_in, a_cs, a_bs = XB, cs, bs
             elif par:
                 self._call("fh_sum_cast_f32", *ptrs, XS.data_ptr(), None, B * bs, self.fp16, st)
+        self._post(XS, bs, cs, B, ch, L, wave, self_cbuf)
+
+    def _post(self, XS, bs, cs, B, ch, L, wave, cbuf):
+        """activation_post -> conv_post -> tanh (bigvgan/models.py:189-192) on the last stage's fp32 rows: one fused kernel
+        (the activated tensor stays in shared memory); FH_FUSE_POST=0 or > 64 channels: two kernels through HBM."""
+        V, st = self.voc, self.stream
         a, ib, f = V["post_act"]
-        AP, _, _ = self_cbuf("vt_AP", B, ch, L, f32)
+        if ch <= 64 and _os_environ_get("FH_FUSE_POST", "1") != "0":
+            self._call("fh_snakepost_convpost_tanh", XS.data_ptr(), bs, cs, HALO, a.data_ptr(), ib.data_ptr(), f.data_ptr(),
+                       V["post_w"].data_ptr(), V["post_b"], wave.data_ptr(), B, ch, L, st,
+                       work={"bytes": 4.0 * B * L * (ch + 1), "flops": 2.0 * B * L * ch * (7 + 24)})
+            return
+        AP, _, _ = cbuf("vt_AP", B, ch, L, torch.float32)
         self._call("fh_snake_aa_chunked", XS.data_ptr(), AP.data_ptr(), a.data_ptr(), ib.data_ptr(), f.data_ptr(), bs, cs,
                    HALO, B, ch, L, 0, st)
         self._call("fh_convpost_tanh_chunked", AP.data_ptr(), bs, cs, HALO, V["post_w"].data_ptr(), V["post_b"],
-                   wave.data_ptr(), B, ch, L, st)
+                   wave.data_ptr(), B, ch, L, st, work={"bytes": 4.0 * B * L * (ch + 1), "flops": 2.0 * B * L * ch * 7})
 
     def _vocoder_tc_split(self, mel: torch.Tensor, wave: torch.Tensor):
         """precision "fp16x2": the same tcgen05 convolutions over hi + lo activation pairs.  Every MMA operand producer
@@ -983,12 +1010,7 @@ class Engine:
             if s + 1 < v.num_stages:
                 a_in, a_cs, a_bs2 = self._cbuf(f"vs_XB{s}", B, 2 * ch, L, h16)
                 self._call("fh_cast_f32_16_split", XS.data_ptr(), a_in.data_ptr(), cs, ch // 8, bs, a_bs2, B, self.fp16, st)
-        a, ib, f = V["post_act"]
-        AP, _, _ = self._cbuf("vs_AP", B, ch, L, f32)
-        self._call("fh_snake_aa_chunked", XS.data_ptr(), AP.data_ptr(), a.data_ptr(), ib.data_ptr(), f.data_ptr(), bs, cs,
-                   HALO, B, ch, L, 0, st)
-        self._call("fh_convpost_tanh_chunked", AP.data_ptr(), bs, cs, HALO, V["post_w"].data_ptr(), V["post_b"],
-                   wave.data_ptr(), B, ch, L, st, work={"bytes": 4.0 * B * L * (ch + 1), "flops": 2.0 * B * L * ch * 7})
+        self._post(XS, bs, cs, B, ch, L, wave, self._cbuf)
 
     # ------------------------------------------------------------------ stage: post-processing
     def postprocess(self, pred: torch.Tensor, src: torch.Tensor) -> torch.Tensor:

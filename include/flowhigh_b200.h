@@ -264,6 +264,12 @@ int fh_snake_aa_chunked_split(const float* x, void* y, const float* a, const flo
 int fh_convpost_tanh_chunked(const float* x, int64_t batch_stride, int64_t chunk_stride, int row0,
                              const float* w, float bias, float* y, int B, int C, int L, void* stream);
 
+/* The tail of BigVGAN.forward in one kernel (bigvgan/models.py:189-192): activation_post (Activation1d, fp32) ->
+ * conv_post (C -> 1, k = 7) -> tanh; x chunked fp32, y [B, L].  The activated tensor stays in shared memory. */
+int fh_snakepost_convpost_tanh(const float* x, int64_t batch_stride, int64_t chunk_stride, int row0,
+                               const float* a, const float* inv_b, const float* filt, const float* w, float bias,
+                               float* y, int B, int C, int L, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

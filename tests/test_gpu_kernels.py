@@ -992,3 +992,30 @@ def test_sample_passes_std_through(cuda_device, f32_model):
         assert torch.equal(a, b) and torch.equal(c, d) and not torch.equal(a, c)
     finally:
         f32_model.set_cfm_method("basic_cfm")
+
+
+@pytest.mark.parametrize("C,L,B", [(24, 480 * 7, 3), (8, 700, 2), (48, 1537, 1), (64, 513, 2)])
+def test_fused_post_matches_two_kernels_and_oracle(cuda_device, C, L, B):
+    """fh_snakepost_convpost_tanh (activation_post -> conv_post -> tanh in one kernel, bigvgan/models.py:189-192) against the
+    oracle's Activation1d + Conv1d + tanh on the same rows: tile boundaries at 512 outputs, sequence edges, odd lengths."""
+    eng, sd, vcfg, g = engine("voc_resblock1_snakebeta", "fp16")
+    torch.manual_seed(C + L)
+    x = torch.randn(B, C, L) * 1.5
+    alpha, beta = torch.randn(C) * 0.3, torch.randn(C) * 0.3
+    filt = eng.voc["post_act"][2].cpu()
+    w = torch.randn(1, C, 7) / (7 * C) ** 0.5
+    bias = 0.05
+    act = model.aa_activation(x, alpha, beta, filt.reshape(1, 1, 12), filt.reshape(1, 1, 12), True)
+    ref = torch.tanh(F.conv1d(act, w, torch.tensor([bias]), padding=3)).squeeze(1)
+    X, cs, bs = eng._cbuf("tp_X", B, C, L, torch.float32)
+    X.zero_()
+    X[: B * bs].view(B, C // 8, cs // 8, 8)[:, :, HALO:HALO + L, :] = x.view(B, C // 8, 8, L).permute(0, 1, 3, 2).cuda()
+    a = torch.exp(alpha).cuda()
+    ib = (1.0 / (torch.exp(beta) + 1e-9)).cuda()
+    wp = w[0].contiguous().cuda()
+    out = torch.empty(B, L, device="cuda")
+    eng._call("fh_snakepost_convpost_tanh", X.data_ptr(), bs, cs, HALO, a.data_ptr(), ib.data_ptr(), eng.voc["post_act"][2].data_ptr(),
+              wp.data_ptr(), bias, out.data_ptr(), B, C, L, eng.stream)
+    err = float((out.cpu() - ref).abs().max())
+    print(f"fused post C{C} L{L} B{B}: max-abs vs oracle {err:.3g}")
+    assert err <= 2e-5
