@@ -34,6 +34,7 @@ class TcConvArgs(C.Structure):
         ("act", _i),
         ("acc_src", _p),
         ("x_is_16", _i),
+        ("two_cta", _i),
     ]
 
 

@@ -64,6 +64,7 @@ struct TcParams {
   int tap_off[kMaxTapOff];
   unsigned int* err_flag;
   unsigned int* status;  // overflow / NaN status word of the caller (common.cuh Guard16) or nullptr
+  int two_cta;            // tc_conv2_kernel: CTA pairs share every weight slot (cta_group::2 MMA, M = 256)
   int m_stride, m_valid;  // output rows a tile advances by / keeps (128 msub unless the A window is aligned: fused snake)
   // fused anti-aliased snake prologue (tc_conv_snakepro_kernel): raw activations (fp32 or fp16 rows) + snake parameters
   const void* xf;
@@ -160,6 +161,51 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// ---- cluster / CTA-pair helpers (tc_conv2_kernel)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// 2-SM MMA: M = 256 (rows 0..127 from this CTA's A window and TMEM, 128..255 from the peer's), B halves from both CTAs
+__device__ __forceinline__ void umma2_f16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// completion of all prior MMAs of this thread -> the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((unsigned short)3)
+               : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor):
@@ -207,6 +253,19 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int id) {
   TileCoord c;
+  if (P.two_cta) {
+    // ids 2k / 2k + 1 = the two M tiles of one CTA pair (same batch, phase and N tile): a CTA steps by an even grid,
+    // so the parity of its ids is its rank in the pair.  m_tiles counts PAIRS here; mt may point past L (void tile).
+    const int r = id & 1;
+    id >>= 1;
+    c.nt = id % P.n_tiles;
+    id /= P.n_tiles;
+    c.mt = 2 * (id % P.m_tiles) + r;
+    id /= P.m_tiles;
+    c.p = id % P.P;
+    c.b = id / P.P;
+    return c;
+  }
   c.nt = id % P.n_tiles;
   id /= P.n_tiles;
   c.mt = id % P.m_tiles;
@@ -392,7 +451,10 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
     tmem_ld_wait();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+    if (lane == 0) {
+      if (P.two_cta) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * as, 0));  // the pair's MMA issuer lives in CTA 0
+      else mbar_arrive(tempty0 + 8 * as);
+    }
     if (++as == P.acc_stages) {
       as = 0;
       aphase ^= 1;
@@ -516,7 +578,10 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
     tmem_ld_wait();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(tempty0 + 8 * as);
+    if (lane == 0) {
+      if (P.two_cta) mbar_arrive_cluster(mapa_u32(tempty0 + 8 * as, 0));  // the pair's MMA issuer lives in CTA 0
+      else mbar_arrive(tempty0 + 8 * as);
+    }
     if (++as == P.acc_stages) {
       as = 0;
       aphase ^= 1;
@@ -530,14 +595,16 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
 // a shared-memory load + R2UR per tap, 64-bit descriptor arithmetic per MMA).  Here every per-stage and per-tap
 // quantity is a running 32-bit value: stage base, tap stride (taps of a phase are an arithmetic sequence for Conv1d,
 // dilated Conv1d and polyphase ConvTranspose1d), weight stride; the sub-tile loop is specialised outside the tap loop.
-template <int MSUB>
+template <int MSUB, bool TWO = false>
 __device__ __forceinline__ void issue_taps(uint32_t d_tmem, uint32_t bn, uint32_t a_lo, uint32_t a_step, uint32_t b_lo,
                                            uint32_t b_step, uint32_t hi, uint32_t idesc, uint32_t accum, int ntap) {
 #pragma unroll 1
   for (int j = 0; j < ntap; ++j) {
 #pragma unroll
-    for (int sub = 0; sub < MSUB; ++sub)
-      umma_f16_split(d_tmem + (uint32_t)sub * bn, a_lo + (uint32_t)sub * 128u, hi, b_lo, hi, idesc, accum);
+    for (int sub = 0; sub < MSUB; ++sub) {
+      if (TWO) umma2_f16_split(d_tmem + (uint32_t)sub * bn, a_lo + (uint32_t)sub * 128u, hi, b_lo, hi, idesc, accum);
+      else umma_f16_split(d_tmem + (uint32_t)sub * bn, a_lo + (uint32_t)sub * 128u, hi, b_lo, hi, idesc, accum);
+    }
     accum = 1;
     a_lo += a_step;
     b_lo += b_step;
@@ -765,6 +832,194 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// Same implicit GEMM with the two SMs of a TPC as one MMA unit: the pair owns two adjacent 128 msub-row M tiles (one per
+// CTA: own activation windows, own TMEM accumulators, own epilogue) and ONE weight stream -- each CTA fetches half of
+// every weight slot (bn / 2 rows) and `tcgen05.mma.cta_group::2` (M = 256), issued by CTA 0's MMA thread, reads the A
+// windows and the B halves of both CTAs.  Per SM the L2 -> SM weight traffic and the number of MMA instructions halve
+// (ncu: the 192 / 384-channel shapes and the Linear layers are paced by the weight stream, the <= 48-channel shapes by the
+// ~32-cycle fixed cost of an MMA).  Protocol on top of tc_conv_kernel's:
+//   * "stage full": CTA 0 waits for its own loads AND for the peer's -- a relay warp in CTA 1 waits on CTA 1's local full
+//     barrier and arrives remotely on CTA 0's `peerfull` barrier (bulk copies can only signal a barrier of their own CTA);
+//   * "stage consumed" and "accumulator complete": tcgen05.commit multicast to the same barrier offset in both CTAs;
+//   * "accumulator drained": the epilogue warps of both CTAs arrive on CTA 0's barrier (count 16);
+//   * cluster barrier after the mbarrier inits and before TMEM dealloc / exit.
+// Weights are packed per CTA rank ([p][nt][cp][rank][tap][2][bn / 2][8], packing.py two_cta).
+constexpr int kThreads2 = 352;  // + relay warp
+
+__device__ __forceinline__ uint32_t make_idesc2(int n, int fp16) {
+  const uint32_t fmt = fp16 ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads2, 1) tc_conv2_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * kMaxStages;
+  const uint32_t tfull0 = empty0 + 8 * kMaxStages, tempty0 = tfull0 + 16;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + 8 * (2 * kMaxStages + 4));
+  const uint32_t peerfull0 = smem_u32(smem + 192);
+  const uint32_t stage0 = smem_u32(smem + 1024);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int S = P.stages;
+
+  conv_cta_setup(P, smem, kThreads2, 16);  // tempty: 8 epilogue warps of each CTA arrive on CTA 0's barrier
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S; ++i) mbar_init(peerfull0 + 8 * i, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc2(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  cluster_sync_all();  // both CTAs' barriers exist before any remote arrive / multicast commit
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t a_chunk_bytes = (uint32_t)P.arows_pad * 16u;
+  const uint32_t a_slot_bytes = 2u * a_chunk_bytes;
+  const int tile_rows = 128 * P.msub;
+  const uint32_t acc_cols = (uint32_t)(P.msub * P.bn);
+  const uint32_t hbn = (uint32_t)P.bn >> 1;             // weight rows per CTA
+  const uint32_t b_tap_bytes = hbn * 32u;
+  const int steps_per_tile = ((P.ci_pairs + P.kc - 1) / P.kc) * P.n_groups;
+
+  if (warp == 0) {
+    // ===================================================================== producer: own A windows + own half of the weights
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TileCoord tc = decode_tile(P, tile);
+        const long long row = (long long)P.a_row0 + (long long)tc.mt * tile_rows + P.min_off[tc.p];
+        const bool has_a = (long long)tc.mt * tile_rows < P.L;  // void tile of an odd tail: weights only
+        const __nv_bfloat16* a_base = P.a + (long long)tc.b * P.a_batch + row * 8;
+        // packed weights: [p][nt][cp][rank][tap][2][bn / 2][8]
+        const __nv_bfloat16* w_base = P.w + ((long long)(tc.p * P.n_tiles + tc.nt) * P.ci_pairs) * ((long long)P.ntaps * P.bn * 16);
+        for (int cp = 0; cp < P.ci_pairs; cp += P.kc) {
+          const int nkc = min(P.kc, P.ci_pairs - cp);
+          for (int g = 0; g < P.n_groups; ++g) {
+            const int tap0 = g * P.tg;
+            const int nt_g = min(P.tg, P.ntaps - tap0);
+            mbar_wait(empty0 + 8 * stage, phase ^ 1, P.err_flag, 1);
+            const uint32_t sa = stage0 + (uint32_t)stage * (uint32_t)P.stage_bytes;
+            const uint32_t fb = full0 + 8 * stage;
+            const uint32_t a_bytes = (uint32_t)P.wrows * 16u;
+            const int nchunk = has_a ? 2 * nkc - ((P.ci_odd && cp + nkc == P.ci_pairs) ? 1 : 0) : 0;
+            const uint32_t w_bytes = (uint32_t)nt_g * b_tap_bytes;  // per ci-pair
+            mbar_expect_tx(fb, (uint32_t)nchunk * a_bytes + (uint32_t)nkc * w_bytes);
+            for (int c = 0; c < nchunk; ++c)
+              bulk_g2s(sa + (uint32_t)c * a_chunk_bytes, a_base + (long long)(2 * cp + c) * P.a_chunk, a_bytes, fb);
+            for (int c = 0; c < nkc; ++c)
+              bulk_g2s(sa + (uint32_t)P.kc * a_slot_bytes + (uint32_t)c * w_bytes,
+                       w_base + ((long long)((cp + c) * 2 + (int)rank) * P.ntaps + tap0) * ((long long)hbn * 16), w_bytes, fb);
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer: CTA 0 only
+    if (rank == 0) {
+      const bool leader = elect_one();
+      int stage = 0, phase = 0, as = 0, aphase = 0;
+      const int msub = P.msub, ntaps = P.ntaps, tg = P.tg, n_groups = P.n_groups, ci_pairs = P.ci_pairs, kc = P.kc;
+      const uint32_t bn = (uint32_t)P.bn;
+      const uint32_t idesc = make_idesc2(P.bn, P.fp16);
+      const uint32_t hi = (128u >> 4) | (1u << 14);
+      const uint32_t a_lbo = (a_chunk_bytes >> 4) << 16;
+      const uint32_t b_lbo = ((hbn * 16u) >> 4) << 16;
+      const uint32_t b_step = (hbn * 32u) >> 4;
+      const uint32_t a_slot_u = (2u * a_chunk_bytes) >> 4;
+      const uint32_t stage_u = (uint32_t)P.stage_bytes >> 4, stage0_u = stage0 >> 4;
+      const int* s_off = reinterpret_cast<const int*>(smem + 512);
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int ph = decode_tile(P, tile).p;
+        const uint32_t rel0 = (uint32_t)P.tap_rel0[ph], a_step = (uint32_t)P.tap_step[ph];
+        mbar_wait(tempty0 + 8 * as, aphase ^ 1, P.err_flag, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)as * acc_cols;
+        uint32_t accum = 0;
+        for (int cp = 0; cp < ci_pairs; cp += kc) {
+          const int nkc = min(kc, ci_pairs - cp);
+          int tap0 = 0;
+          for (int g = 0; g < n_groups; ++g, tap0 += tg) {
+            const int nt_g = min(tg, ntaps - tap0);
+            mbar_wait(full0 + 8 * stage, phase, P.err_flag, 3);
+            mbar_wait(peerfull0 + 8 * stage, phase, P.err_flag, 8);
+            tc_fence_after();
+            const uint32_t sa_u = stage0_u + (uint32_t)stage * stage_u;
+            if (leader) {
+              uint32_t b_lo = b_lbo | (sa_u + (uint32_t)kc * a_slot_u);
+              uint32_t a_base_lo = a_lbo | sa_u;
+              for (int c = 0; c < nkc; ++c) {
+                if (P.tap_arith) {  // same lean issue loop as the single-CTA kernel: running 32-bit descriptor words
+                  const uint32_t a_lo = a_base_lo + rel0 + (uint32_t)tap0 * a_step;
+                  if (msub == 2) issue_taps<2, true>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
+                  else if (msub == 4) issue_taps<4, true>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
+                  else if (msub == 8) issue_taps<8, true>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
+                  else issue_taps<1, true>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
+                } else {
+                  const int* offs = s_off + ph * ntaps + tap0;
+                  uint32_t bl = b_lo, acc = accum;
+                  for (int j = 0; j < nt_g; ++j) {
+                    const uint32_t a_lo = a_base_lo + (uint32_t)offs[j];
+                    for (int sub = 0; sub < msub; ++sub)
+                      umma2_f16_split(d_tmem + (uint32_t)sub * bn, a_lo + (uint32_t)sub * 128u, hi, bl, hi, idesc, acc);
+                    acc = 1;
+                    bl += b_step;
+                  }
+                }
+                accum = 1;
+                a_base_lo += a_slot_u;
+                b_lo += (uint32_t)nt_g * b_step;
+              }
+              umma2_commit(empty0 + 8 * stage);  // frees the stage in BOTH CTAs when these MMAs retire
+            }
+            accum = 1;
+            __syncwarp();
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        if (leader) umma2_commit(tfull0 + 8 * as);  // both CTAs' epilogues
+        __syncwarp();
+        if (++as == P.acc_stages) {
+          as = 0;
+          aphase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================================================================== relay (CTA 1): local "stage full" -> CTA 0
+    // one LANE per stage slot, each walking the generations of its own slot: a single relaying thread (wait, remote
+    // arrive, next stage) was as slow as a 14-MMA stage and paced every shape with fewer than ~20 MMAs per stage
+    if (rank == 1 && lane < S) {
+      int my_tiles = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) ++my_tiles;
+      const int total_steps = my_tiles * steps_per_tile;
+      const uint32_t remote = mapa_u32(peerfull0 + 8 * lane, 0);
+      for (int i = lane; i < total_steps; i += S) {
+        mbar_wait(full0 + 8 * lane, (uint32_t)((i / S) & 1), P.err_flag, 9);
+        mbar_arrive_cluster(remote);
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..9), own 128 msub rows
+    epilogue_dispatch(P, tmem_base, tfull0, tempty0, warp & 3, (warp - 2) >> 2, lane, tile_rows, acc_cols,
+                      reinterpret_cast<const float*>(smem + 1024 + (size_t)P.stages * P.stage_bytes));
+  }
+  tc_fence_before();
+  cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still read its smem / signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc2(tmem_base, 512);
   }
 }
 
@@ -1057,6 +1312,9 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   p.B = a->B, p.L = a->L, p.Cin = a->Cin, p.Cout = a->Cout, p.ntaps = a->ntaps, p.P = a->P, p.bn = a->bn;
   p.n_tiles = (a->Cout + a->bn - 1) / a->bn;
   const bool fused = a->x_f32 != nullptr;
+  const bool two = a->two_cta != 0;
+  FH_REQUIRE(!(two && fused), FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: the CTA-pair kernel has no fused snake prologue");
+  p.two_cta = two ? 1 : 0;
   if (fused) {
     FH_REQUIRE(a->P == 1 && p.n_tiles == 1 && a->bn <= 128 && a->Cin <= 128 && a->sn_a && a->sn_inv_b && a->sn_filt && !a->geglu,
                FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: fused snake needs P == 1 and one N tile of <= 128 columns");
@@ -1112,7 +1370,8 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
     p.m_stride = p.m_valid = 128 * msub - span;
     p.m_tiles = (a->L + p.m_stride - 1) / p.m_stride;
   }
-  const long long total = (long long)p.B * p.P * p.m_tiles * p.n_tiles;
+  if (two) p.m_tiles = (p.m_tiles + 1) / 2;  // CTA PAIRS along M (decode_tile); an odd tail leaves one void tile
+  const long long total = (long long)p.B * p.P * p.m_tiles * p.n_tiles * (two ? 2 : 1);
   FH_REQUIRE(total < (1ll << 31), FH_ERR_BAD_SHAPE, "fh_tc_conv: too many tiles");
   p.total_tiles = (int)total;
   {
@@ -1158,16 +1417,22 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
     const char* e = getenv("FH_TC_KC_MMAS");
     kc_target = e ? atoi(e) : 12;
   }
+  static int kc_target2 = -1;  // CTA pairs: a stage costs two barrier round trips more (relay, multicast commit)
+  if (kc_target2 < 0) {
+    const char* e = getenv("FH_TC_KC_MMAS2");
+    kc_target2 = e ? atoi(e) : 24;
+  }
   int kc = 1;
   if (!fused && p.n_groups == 1 && kc_target > 0) {
-    const int pair_bytes = 2 * p.arows_pad * 16 + a->ntaps * a->bn * 32;
-    kc = (kc_target + a->ntaps * msub - 1) / (a->ntaps * msub);
+    const int pair_bytes = 2 * p.arows_pad * 16 + a->ntaps * (two ? a->bn / 2 : a->bn) * 32;
+    const int kct = two ? kc_target2 : kc_target;
+    kc = (kct + a->ntaps * msub - 1) / (a->ntaps * msub);
     if (kc > 4) kc = 4;
     if (kc > p.ci_pairs) kc = p.ci_pairs;
     while (kc > 1 && (200 * 1024 - 1024 - 8192) / (kc * pair_bytes) < 4) --kc;
   }
   p.kc = kc;
-  p.stage_bytes = kc * (2 * p.arows_pad * 16 + tg * a->bn * 32);
+  p.stage_bytes = kc * (2 * p.arows_pad * 16 + tg * (two ? a->bn / 2 : a->bn) * 32);  // a CTA of a pair holds half of every weight slot
   p.stage_bytes = (p.stage_bytes + 127) & ~127;
   static int budget_kb = 0;
   if (!budget_kb) {
@@ -1266,6 +1531,14 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
     else { FH_PRO_LAUNCH(false, 8, set_d); }
 #undef FH_PRO_LAUNCH
     return fh::check_launch("fh_tc_conv(fused snake)");
+  }
+  if (p.two_cta) {
+    static int smem_set2[64] = {0};
+    cudaError_t e = fh::ensure_dyn_smem(tc_conv2_kernel, smem, smem_set2);
+    FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", smem, cudaGetErrorString(e));
+    int g2 = (p.total_tiles < (num_sms & ~1) ? p.total_tiles : (num_sms & ~1));  // total_tiles is even
+    tc_conv2_kernel<<<g2, kThreads2, smem, (cudaStream_t)stream>>>(p);
+    return fh::check_launch("fh_tc_conv(cta pair)");
   }
   static int smem_set[64] = {0};
   {

@@ -38,7 +38,7 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 class _TcWeight:
-    __slots__ = ("packed", "bias", "off", "off_c", "P", "ntaps", "cin", "cout", "cin_pad", "cout_pad", "bn")
+    __slots__ = ("packed", "bias", "off", "off_c", "P", "ntaps", "cin", "cout", "cin_pad", "cout_pad", "bn", "two_cta")
 
 
 class _F32Weight:
@@ -85,6 +85,11 @@ class Engine:
         # profiles/r2_ncu_fused_snake_conv.txt: the snake warps, not HBM, pace the kernel), so the separate launches
         # stay the default.
         self.fuse_snake = self.fp16 == 1 and not self.split and _os.environ.get("FH_FUSE_SNAKE", "0") != "0"
+        # CTA-pair kernel (tc_conv2_kernel: cta_group::2 MMA, M = 256, one weight stream per SM pair).  Decided per layer
+        # at load time because the packed weight layout differs.  FH_TC_2CTA: "auto" (default) = the shapes it wins on
+        # (_pair_wins, measured per shape on B200), "1" = every tcgen05 convolution / Linear, "0" = never.
+        self.two_cta_mode = _os.environ.get("FH_TC_2CTA", "auto") if (self.tc and not self.fuse_snake) else "0"
+        self.two_cta = self.two_cta_mode == "1"
         # fp16 path: the first convolution of an AMP unit writes fp16 rows and the snake behind it reads them as MMA
         # operands (fh_snake_aa_chunked_h) -- the fp32 round trip of that tensor disappears
         self.y16 = self.fp16 and not self.split and _os.environ.get("FH_Y16", "1") != "0"
@@ -241,14 +246,30 @@ class Engine:
         r.P, r.ntaps, r.cin, r.cout = tconv.P, tconv.ntaps, tconv.cin, tconv.cout
         return r
 
-    def _mk_tc(self, tconv: packing.TappedConv, cin_pad=None, cout_pad=None, bn=None, split=False) -> _TcWeight:
+    def _pair_wins(self, cout: int, ntaps: int, P: int, residual: bool) -> bool:
+        """Shapes on which the CTA-pair kernel beats the single-CTA kernel (B = 64 breakdowns of both in one gpurun call,
+        profiles/r2_pair_vs_single.txt): 192 / 384 output channels with >= 7 taps gain 14-25 % (their weight stream per SM
+        halves), the 96-channel k = 11 first convolutions 17 %; HBM-bound residual launches, k = 3 shapes, the upsamplers
+        and the Linear layers lose 3-20 % to the two extra barrier hops per stage; 768 channels are at the tensor peak
+        either way."""
+        if self.two_cta_mode != "auto":
+            return self.two_cta_mode == "1"
+        if P != 1:
+            return False
+        if 192 <= cout <= 384 and ntaps >= 7:
+            return True
+        return cout == 96 and ntaps >= 11 and not residual
+
+    def _mk_tc(self, tconv: packing.TappedConv, cin_pad=None, cout_pad=None, bn=None, split=False, two_cta=None) -> _TcWeight:
         r = _TcWeight()
         cin_alg = tconv.cin
+        r.two_cta = self.two_cta if two_cta is None else bool(two_cta)
         if split:  # hi + lo activation operand: doubled input channels, duplicated weights
             cin_pad = cin_pad or packing.round_up(tconv.cin, 8)
             tconv = packing.split_input(tconv, cin_pad)
             cin_pad = 2 * cin_pad
-        r.packed, r.cin_pad, r.cout_pad, r.bn = packing.pack_tc(tconv, self.device, cin_pad, cout_pad, bn, self.h16)
+        r.packed, r.cin_pad, r.cout_pad, r.bn = packing.pack_tc(tconv, self.device, cin_pad, cout_pad, bn, self.h16,
+                                                                 two_cta=r.two_cta)
         r.bias = None if tconv.bias is None else packing.pad_vec(tconv.bias.to(self.device), r.cout_pad)
         r.off = tconv.off.copy()
         r.off_c = (C.c_int * r.off.size)(*[int(v) for v in r.off.flatten()])
@@ -316,7 +337,8 @@ class Engine:
 
     def _prep_vocoder(self):
         sd, v = self.sd, self.vcfg
-        mk = (lambda t, **kw: self._mk_tc(t, split=self.split, **kw)) if self.tc else self._mk_f32
+        mk = (lambda t, residual=False, **kw: self._mk_tc(t, split=self.split, two_cta=self._pair_wins(
+            t.cout, t.ntaps, t.P, residual), **kw)) if self.tc else (lambda t, residual=False, **kw: self._mk_f32(t))
         pad = (lambda c: packing.round_up(c, 8)) if self.tc else (lambda c: c)  # whole 8-channel chunks
         self.cpad = pad
         V = {}
@@ -337,12 +359,12 @@ class Engine:
                         V[f"r{s}.{j}.c1.{i}"] = mk(packing.conv1d_taps(sd[p + f"convs1.{i}.weight"],
                                                                        sd[p + f"convs1.{i}.bias"], d), **kw)
                         V[f"r{s}.{j}.c2.{i}"] = mk(packing.conv1d_taps(sd[p + f"convs2.{i}.weight"],
-                                                                       sd[p + f"convs2.{i}.bias"], 1), **kw)
+                                                                       sd[p + f"convs2.{i}.bias"], 1), residual=True, **kw)
                         V[f"r{s}.{j}.a1.{i}"] = self._snake_params(p + f"activations.{2 * i}.", pad(cout))
                         V[f"r{s}.{j}.a2.{i}"] = self._snake_params(p + f"activations.{2 * i + 1}.", pad(cout))
                     else:
                         V[f"r{s}.{j}.c1.{i}"] = mk(packing.conv1d_taps(sd[p + f"convs.{i}.weight"],
-                                                                       sd[p + f"convs.{i}.bias"], d), **kw)
+                                                                       sd[p + f"convs.{i}.bias"], d), residual=True, **kw)
                         V[f"r{s}.{j}.a1.{i}"] = self._snake_params(p + f"activations.{i}.", pad(cout))
         clast = v.stage_channels(v.num_stages - 1)
         V["post_act"] = self._snake_params(VOC + "activation_post.", pad(clast))
@@ -456,6 +478,7 @@ class Engine:
         args.out_is_16, args.res_is_16, args.fp16 = int(out_bf16), int(res_bf16), self.fp16
         args.alpha, args.beta_res, args.accumulate, args.geglu = alpha, beta, int(accumulate), int(geglu)
         args.act = int(act)
+        args.two_cta = 1 if (rec.two_cta and xf is None) else 0
         args.acc_src = _ptr(acc_src)
         args.B, args.L, args.Cin, args.Cout = B, L, rec.cin_pad, rec.cout_pad
         args.ntaps, args.P, args.tap_off, args.bn = rec.ntaps, rec.P, rec.off_c, rec.bn

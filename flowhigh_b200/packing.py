@@ -115,8 +115,10 @@ def round_up(x: int, m: int) -> int:
 
 
 def pack_tc(tc: TappedConv, device, cin_pad: Optional[int] = None, cout_pad: Optional[int] = None,
-            bn: Optional[int] = None, dtype=torch.bfloat16) -> Tuple[torch.Tensor, int, int, int]:
-    """-> (packed 16-bit tensor (bf16 or fp16), cin_pad, cout_pad, bn)."""
+            bn: Optional[int] = None, dtype=torch.bfloat16, two_cta: bool = False) -> Tuple[torch.Tensor, int, int, int]:
+    """-> (packed 16-bit tensor (bf16 or fp16), cin_pad, cout_pad, bn).
+    two_cta: layout of the CTA-pair kernel, [P][nt][cp][rank][tap][2][bn/2][8] -- CTA `rank` of a pair fetches the
+    bn/2 output channels [rank bn/2, (rank + 1) bn/2) of every weight slot as one contiguous block per ci-pair."""
     P, ntaps, cout, cin = tc.w.shape
     cin_pad = cin_pad or round_up(cin, 8)     # channel counts of the activation buffers: whole 8-channel chunks
     cout_pad = cout_pad or round_up(cout, 8)
@@ -125,6 +127,10 @@ def pack_tc(tc: TappedConv, device, cin_pad: Optional[int] = None, cout_pad: Opt
     cin16 = round_up(cin_pad, 16)             # the weight image always carries whole ci-pairs (K = 16 per MMA)
     w = torch.zeros(P, ntaps, n_tiles * bn, cin16, dtype=torch.float32, device=tc.w.device)
     w[:, :, :cout, :cin] = tc.w
+    if two_cta:
+        # [P][tap][nt][rank][bn/2][cp][2][8] -> [P][nt][cp][rank][tap][2][bn/2][8]
+        w = w.reshape(P, ntaps, n_tiles, 2, bn // 2, cin16 // 16, 2, 8).permute(0, 2, 5, 3, 1, 6, 4, 7).contiguous()
+        return w.to(dtype).to(device), cin_pad, cout_pad, bn
     # [P][tap][nt][bn][cp][2][8] -> [P][nt][cp][tap][2][bn][8]
     w = w.reshape(P, ntaps, n_tiles, bn, cin16 // 16, 2, 8).permute(0, 2, 4, 1, 5, 3, 6).contiguous()
     return w.to(dtype).to(device), cin_pad, cout_pad, bn

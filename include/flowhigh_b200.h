@@ -235,6 +235,8 @@ typedef struct {
                            * Lets the last AMP branch of a stage (bigvgan/models.py:181-187, xs / num_kernels) write the
                            * mean directly as the 16-bit operand of the next upsampler (out_is_16 = 1). */
   int x_is_16;            /* fused prologue: x_f32 points to fp16 rows (the 16-bit output of the unit's first conv) */
+  int two_cta;            /* CTA-pair kernel (tcgen05 cta_group::2, M = 256): `w` must be packed per CTA rank
+                           * ([p][nt][ci-pair][rank][tap][2][bn/2][8], packing.pack_tc(two_cta=True)) */
 } fh_tc_conv_args;
 int fh_tc_conv(const fh_tc_conv_args* args, void* stream);
 /* bytes of the packed weight image for given shape (host helper, no GPU work) */

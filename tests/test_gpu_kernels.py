@@ -1019,3 +1019,40 @@ def test_fused_post_matches_two_kernels_and_oracle(cuda_device, C, L, B):
     err = float((out.cpu() - ref).abs().max())
     print(f"fused post C{C} L{L} B{B}: max-abs vs oracle {err:.3g}")
     assert err <= 2e-5
+
+
+@pytest.mark.parametrize("B,Ci,Co,L,k,d", [(2, 32, 32, 300, 3, 1), (2, 96, 96, 1000, 11, 5), (3, 24, 24, 700, 7, 3),
+                                           (1, 384, 384, 2000, 7, 1), (2, 192, 192, 5000, 3, 1), (1, 768, 768, 640, 11, 1),
+                                           (4, 1024, 3072, 4000, 1, 1), (1, 192, 192, 129, 11, 5), (5, 384, 384, 257, 7, 3)])
+def test_tc_conv_pair_matches_single(cuda_device, B, Ci, Co, L, k, d):
+    """tc_conv2_kernel (CTA pairs, tcgen05 cta_group::2, M = 256, one weight stream per pair, relay + multicast barriers)
+    against tc_conv_kernel on the same operands: bit-identical, incl. odd M-tile counts (void tile of the second CTA),
+    residual epilogues, Linear (k = 1) and multi-N-tile shapes; rows outside [0, L) untouched."""
+    eng, sd, vcfg, g = engine("voc_resblock1_snakebeta", "fp16")
+    torch.manual_seed(Ci + L)
+    w = torch.randn(Co, Ci, k) / (Ci * k) ** 0.5
+    b = torch.randn(Co) * 0.1
+    tconv = packing.conv1d_taps(w.cuda(), b.cuda(), d)
+    r1 = eng._mk_tc(tconv, cin_pad=Ci, cout_pad=Co, two_cta=False)
+    r2 = eng._mk_tc(tconv, cin_pad=Ci, cout_pad=Co, two_cta=True)
+    A, cs, bs = eng._cbuf("pp_A", B, Ci, L, eng.h16)
+    O1, ocs, obs = eng._cbuf("pp_O1", B, Co, L, torch.float32)
+    O2, _, _ = eng._cbuf("pp_O2", B, Co, L, torch.float32)
+    R, _, _ = eng._cbuf("pp_R", B, Co, L, torch.float32)
+    x = torch.randn(B, Ci, L).cuda()
+    A.zero_()
+    A[: B * bs].view(B, Ci // 8, cs // 8, 8)[:, :, HALO:HALO + L, :] = x.view(B, Ci // 8, 8, L).permute(0, 1, 3, 2).half()
+    R.normal_()
+    o = HALO * 8
+    for res in (False, True):
+        O1.zero_()
+        O2.zero_()
+        kw = dict(res=R[o:], res_strides=(obs, ocs, 8), beta=1.0) if res else {}
+        eng._tc_conv(r1, A, bs, cs, HALO, O1[o:], (obs, ocs, 8), 0, B, L, **kw)
+        eng._tc_conv(r2, A, bs, cs, HALO, O2[o:], (obs, ocs, 8), 0, B, L, **kw)
+        torch.cuda.synchronize()
+        assert torch.equal(O1, O2), (res, float((O1 - O2).abs().max()))
+    ref = F.conv1d(x.half().float(), w.half().float().cuda(), b.cuda(), dilation=d, padding=(k * d - d) // 2)
+    got = O2[: B * obs].view(B, Co // 8, ocs // 8, 8)[:, :, HALO:HALO + L].permute(0, 1, 3, 2).reshape(B, Co, L) - \
+        R[: B * obs].view(B, Co // 8, ocs // 8, 8)[:, :, HALO:HALO + L].permute(0, 1, 3, 2).reshape(B, Co, L)
+    assert float((got - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
