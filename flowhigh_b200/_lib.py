@@ -72,6 +72,8 @@ SIGNATURES = {
     "fh_attention_tc": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i, _p]),
     "fh_geglu_f32": (_i, [_p, _p, _i, _i64, _i, _i, _i, _p]),
     "fh_axpby_f32": (_i, [_p, _p, _f, _f, _p, _i64, _p]),
+    "fh_rk_lincomb_f32": (_i, [_p, _p, _i64, _i, C.POINTER(_f), _p, _i64, _p]),
+    "fh_rk_scaled_sumsq_f32": (_i, [_p, _p, _p, _f, _f, _i, _i64, _p, _p]),
     "fh_broadcast_row_f32": (_i, [_p, _p, _i64, _i, _p]),
     "fh_mel_cutoff_f32": (_i, [_p, _p, _i, _i, _i, _f, _p]),
     "fh_mel_splice_f32": (_i, [_p, _p, _p, _p, _i, _i, _i, _p]),

@@ -392,6 +392,44 @@ __global__ void broadcast_row_kernel(const float* __restrict__ row, float* __res
   if (i < M * C) out[i] = row[i % C];
 }
 
+// ------------------------------------------------------------------------------ adaptive Runge-Kutta helpers
+// (torchode path, cfm_superresolution.py:259-276: stage combination and the controller's scaled error norm)
+struct RkCoefs { float c[8]; };
+
+__global__ void rk_lincomb_kernel(const float* __restrict__ base, const float* __restrict__ k, int64_t kstride, int nk,
+                                  RkCoefs cf, float* __restrict__ out, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    if (j < nk && cf.c[j] != 0.f) acc = fmaf(cf.c[j], k[(size_t)j * kstride + i], acc);
+  out[i] = base ? base[i] + acc : acc;
+}
+
+// one block per problem instance: a fixed summation order, so accept / reject decisions are reproducible
+__global__ void rk_scaled_sumsq_kernel(const float* __restrict__ e, const float* __restrict__ y0,
+                                       const float* __restrict__ y1, float atol, float rtol, int64_t n,
+                                       double* __restrict__ out) {
+  __shared__ double part[32];
+  const int64_t off = (int64_t)blockIdx.x * n;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+    float m = fabsf(y0[off + i]);
+    if (y1) m = fmaxf(m, fabsf(y1[off + i]));
+    const float r = e[off + i] / fmaf(rtol, m, atol);
+    acc += (double)r * (double)r;
+  }
+  for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    acc = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.0;
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, s);
+    if (threadIdx.x == 0) out[blockIdx.x] = acc;
+  }
+}
+
 // cfm_superresolution.py:134-144 on exp(mel) of one clip [N, F]: e[f] = sum_n exp(mel[n,f]); cumsum;
 // scan from the top for the first bin whose cumulative energy is below percentile * total (bin 0 never tested)
 __global__ void mel_cutoff_kernel(const float* __restrict__ mel, int* __restrict__ cutoff, int N, int F,
@@ -559,6 +597,24 @@ extern "C" __attribute__((visibility("default"))) int fh_axpby_f32(const float* 
   if (n <= 0) return FH_OK;
   axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, z, a, b, y, n);
   return fh::check_launch("fh_axpby_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_rk_lincomb_f32(const float* base, const float* k, int64_t kstride,
+                                                                       int nk, const float* coef_host, float* out,
+                                                                       int64_t n, void* stream) {
+  FH_REQUIRE(nk >= 1 && nk <= 8 && coef_host != nullptr && n > 0, FH_ERR_BAD_SHAPE, "fh_rk_lincomb_f32: 1 <= nk <= 8");
+  RkCoefs cf;
+  for (int j = 0; j < 8; ++j) cf.c[j] = j < nk ? coef_host[j] : 0.f;
+  rk_lincomb_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(base, k, kstride, nk, cf, out, n);
+  return fh::check_launch("fh_rk_lincomb_f32");
+}
+
+extern "C" __attribute__((visibility("default"))) int fh_rk_scaled_sumsq_f32(const float* e, const float* y0,
+                                                                            const float* y1, float atol, float rtol,
+                                                                            int B, int64_t n, double* out, void* stream) {
+  FH_REQUIRE(B > 0 && n > 0 && e && y0 && out, FH_ERR_BAD_SHAPE, "fh_rk_scaled_sumsq_f32: bad arguments");
+  rk_scaled_sumsq_kernel<<<B, 1024, 0, (cudaStream_t)stream>>>(e, y0, y1, atol, rtol, n, out);
+  return fh::check_launch("fh_rk_scaled_sumsq_f32");
 }
 
 extern "C" __attribute__((visibility("default"))) int fh_broadcast_row_f32(const float* row, float* out, int64_t M, int C,

@@ -375,11 +375,15 @@ class Engine:
         self.voc = V
 
     # ------------------------------------------------------------------ stage: resample + normalise
-    def resample_normalise(self, x: torch.Tensor, sr_in: int, sr_out: int = 48000) -> torch.Tensor:
-        """x [B, T_in] fp32 on device -> cond [B, T] = resample_poly(x) / max|.|  (flowhighsr.py:68-69)."""
+    def resample_normalise(self, x: torch.Tensor, sr_in: int, sr_out: int = 48000, method: str = "scipy") -> torch.Tensor:
+        """x [B, T_in] fp32 on device -> cond [B, T] = resample(x) / max|.|: `method='scipy'` is
+        scipy.signal.resample_poly's filter (flowhighsr.py:68-69), `'soxr_hq'` the filter of the librosa branch
+        (flowhighsr.py:74-80; tables.resample_plan_soxr_hq) -- same polyphase kernel, different taps."""
         self._chk(x)
         B, T_in = x.shape
-        plan = tables.resample_plan(sr_in, sr_out)
+        if method not in ("scipy", "soxr_hq"):
+            raise ValueError(f"unknown resampling method {method!r} (scipy|soxr_hq)")
+        plan = tables.resample_plan(sr_in, sr_out) if method == "scipy" else tables.resample_plan_soxr_hq(sr_in, sr_out)
         absmax = self.buf("rs_absmax", (B,), torch.int32)
         self._call("fh_fill_u32", absmax.data_ptr(), 0, B, self.stream)
         if plan is None:
@@ -387,7 +391,7 @@ class Engine:
             self._call("fh_absmax_f32", y.data_ptr(), absmax.data_ptr(), B, T_out, self.stream)
         else:
             h, up, down, npp, npr = plan
-            key = (sr_in, sr_out)
+            key = (sr_in, sr_out, method)
             if key not in self._resample_taps:
                 self._resample_taps[key] = torch.from_numpy(h).to(self.device)
             hd = self._resample_taps[key]
@@ -694,9 +698,80 @@ class Engine:
         self._call("fh_axpby_f32", base.data_ptr(), vc.data_ptr(), 1.0, coef, out.data_ptr(), n, self.stream)
         return False
 
+    def _odeint_adaptive(self, y0: torch.Tensor, cond_mel: torch.Tensor, null, cond_scale: float, t0: float, t1: float, *,
+                         tableau, atol: float, rtol: float, max_steps: int = 10000) -> torch.Tensor:
+        """y(t1) by an embedded 5(4) Runge-Kutta pair under an integral step-size controller: the `use_torchode=True`
+        branch (cfm_superresolution.py:259-276: to.Tsit5 + to.IntegralController in to.AutoDiffAdjoint).  torchode gives
+        every clip of a batch its own time, step size and accept / reject history; the clips are independent, so they
+        are solved one after the other with a scalar time each (the time conditioning is one vector per launch).  Stage
+        states, the solution and the error estimate are `fh_rk_lincomb_f32` launches, the controller's error ratio is
+        `fh_rk_scaled_sumsq_f32` (fp64, fixed summation order) read back once per attempted step."""
+        from . import rk
+        B, N, Din = y0.shape
+        n = N * Din
+        ctl = rk.IntegralController(atol=float(atol), rtol=float(rtol), order=tableau.order)
+        out = torch.empty_like(y0)
+        K = self.buf("rk_k", (8, 1, N, Din), zero=False)   # k_0 .. k_6, slot 7 = scratch (error estimate / f1 - f0)
+        ys = self.buf("rk_ys", (1, N, Din), zero=False)
+        zero = self.buf("rk_zero", (1, N, Din))
+        ssq = self.buf("rk_ssq", (1,), torch.float64, zero=False)
+        nullb = None if null is None else null[:1]
+        st = self.stream
+        self.ode_stats = []
+
+        def field(x, cond, t, slot):  # K[slot] = v(t, x)
+            self._field_update(x, cond, nullb, float(np.float32(t)), zero, 1.0, K[slot], cond_scale, False)
+
+        def lincomb(base, coefs, dst):
+            arr = (C.c_float * len(coefs))(*[float(c) for c in coefs])
+            self._call("fh_rk_lincomb_f32", _ptr(base), K.data_ptr(), n, len(coefs), arr, dst.data_ptr(), n, st)
+
+        def norm(e, ya, yb):
+            self._call("fh_rk_scaled_sumsq_f32", e.data_ptr(), ya.data_ptr(), _ptr(yb), ctl.atol, ctl.rtol, 1, n,
+                       ssq.data_ptr(), st)
+            return float(np.sqrt(ssq.item() / n))
+
+        for b in range(B):
+            y = out[b: b + 1]
+            self._call("fh_axpby_f32", y0[b: b + 1].data_ptr(), None, 1.0, 0.0, y.data_ptr(), n, st)
+            cond = cond_mel[b: b + 1]
+            t, span = t0, t1 - t0
+            field(y, cond, t, 0)
+            nfe = 1
+            # Hairer's initial step: d0 = |y0|, d1 = |f0|, d2 = |f(t0 + h0, y0 + h0 f0) - f0| / h0 in the scaled rms norm
+            d0, d1 = norm(y, y, None), norm(K[0], y, None)
+            h0 = ctl.initial_dt(d0, d1, span)
+            lincomb(y, [h0], ys)
+            field(ys, cond, t + h0, 1)
+            nfe += 1
+            lincomb(None, [-1.0, 1.0], K[7])
+            dt = ctl.initial_dt_refine(h0, d1, norm(K[7], y, None) / h0, span)
+            n_steps = n_acc = 0
+            while t < t1:
+                if n_steps >= max_steps:
+                    raise RuntimeError(f"adaptive solve did not reach t_end in {max_steps} steps (clip {b}, t = {t})")
+                dt = min(dt, t1 - t)
+                last = dt >= t1 - t
+                for s in range(1, 7):
+                    lincomb(y, [dt * w for w in tableau.a[s]], ys)
+                    field(ys, cond, t + tableau.c[s] * dt, s)
+                    nfe += 1
+                # ys now holds the 5th-order solution (FSAL: the last stage is evaluated at it)
+                lincomb(None, [dt * w for w in tableau.e], K[7])
+                ratio = norm(K[7], y, ys)
+                n_steps += 1
+                if ctl.accept(ratio):
+                    t = t1 if last else t + dt
+                    self._call("fh_axpby_f32", ys.data_ptr(), None, 1.0, 0.0, y.data_ptr(), n, st)
+                    self._call("fh_axpby_f32", K[6].data_ptr(), None, 1.0, 0.0, K[0].data_ptr(), n, st)
+                    n_acc += 1
+                dt = ctl.next_dt(dt, ratio)
+            self.ode_stats.append({"n_steps": n_steps, "n_accepted": n_acc, "n_f_evals": nfe})
+        return out
+
     def sample_mel(self, cond_mel: torch.Tensor, eps: torch.Tensor, *, steps: int, ode_method: str, cfm_method: str,
                    sigma: float, cond_scale: float = 1.0, mel_pp: bool = False, std_1: Optional[float] = None,
-                   std_2: Optional[float] = None) -> torch.Tensor:
+                   std_2: Optional[float] = None, adaptive: Optional[dict] = None) -> torch.Tensor:
         """CFM sampler (cfm_superresolution.py:162-284 up to `sampled`): prior + fixed-grid ODE (+ mel_pp).
         std_1 / std_2: the reference falls back to (1.0, sigma) unless BOTH are given (:180-183)."""
         if std_1 is None or std_2 is None:
@@ -726,6 +801,9 @@ class Engine:
         tgrid = np.linspace(0.0, 1.0, steps + 1, dtype=np.float32)  # torch.linspace(0,1,steps+1) fp32
         ymid = torch.empty_like(y) if ode_method == "midpoint" else None
         packed = False
+        if adaptive is not None:  # use_torchode=True (cfm_superresolution.py:259-276): only t_eval[0] / t_eval[-1] matter
+            y = self._odeint_adaptive(y, cond_mel, null, cond_scale, float(tgrid[0]), float(tgrid[-1]), **adaptive)
+            steps = 0
         for i in range(steps):
             t0, t1 = tgrid[i], tgrid[i + 1]
             dt = np.float32(t1 - t0)

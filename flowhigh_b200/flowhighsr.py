@@ -186,12 +186,14 @@ class FlowHighSR(nn.Module):
                  cfm_method="basic_cfm", torchdiffeq_ode_method="midpoint", torchode_method_klass=None,
                  cond_drop_prob=0.0, upsampling_method="scipy", precision: str = "fp16"):
         super().__init__()
-        if use_torchode:
-            raise NotImplementedError("adaptive-step torchode sampling is a SURVEY 8f 'next' row")
         self.sigma = sigma
         self.flowhigh = flowhigh
         self.cond_drop_prob = cond_drop_prob
         self.use_torchode = use_torchode
+        # the reference passes a torchode class (default torchode.Tsit5, flowhighsr.py:31); a name works too
+        from . import rk
+        self.torchode_method_klass = torchode_method_klass
+        self._tableau = rk.resolve(torchode_method_klass) if use_torchode else None
         self.cfm_method = cfm_method
         self.odeint_kwargs = dict(atol=ode_atol, rtol=ode_rtol, method=torchdiffeq_ode_method)
         self.upsampling_method = upsampling_method
@@ -266,6 +268,23 @@ class FlowHighSR(nn.Module):
     def set_cfm_method(self, cfm_method):
         self.cfm_method = cfm_method
 
+    def _adaptive(self) -> Optional[dict]:
+        """cfm_superresolution.py:240,259-276: `use_torchode` swaps the fixed-grid torchdiffeq solve for the adaptive one
+        (atol / rtol from `odeint_kwargs`, the 5(4) pair from `torchode_method_klass`); `time_steps` then only fixes the
+        end points of `t_eval`.  The accept / reject loop is host-driven, so these calls are never graph-captured."""
+        if not self.use_torchode:
+            return None
+        return dict(tableau=self._tableau, atol=float(self.odeint_kwargs["atol"]), rtol=float(self.odeint_kwargs["rtol"]))
+
+    def _resample_method(self) -> str:
+        """flowhighsr.py:66-80: 'scipy' = resample_poly, 'librosa' = librosa.resample(res_type='soxr_hq').  Anything else
+        leaves `cond` undefined in the reference (NameError); here it is a ValueError."""
+        if self.upsampling_method == "scipy":
+            return "scipy"
+        if self.upsampling_method == "librosa":
+            return "soxr_hq"
+        raise ValueError(f"upsampling_method must be 'scipy' or 'librosa', got {self.upsampling_method!r}")
+
     def _noise_like(self, cond_mel: torch.Tensor, eps: Optional[torch.Tensor]) -> torch.Tensor:
         if eps is not None:
             return eps.to(cond_mel.device, torch.float32).reshape(cond_mel.shape).contiguous()
@@ -291,7 +310,8 @@ class FlowHighSR(nn.Module):
             cond = eng.encode(cond.reshape(cond.shape[0], -1))
         mel = eng.sample_mel(cond, self._noise_like(cond, eps), steps=int(time_steps),
                              ode_method=self.odeint_kwargs["method"], cfm_method=cfm_method, sigma=float(self.sigma),
-                             cond_scale=float(cond_scale), mel_pp=bool(mel_pp), std_1=float(std_1), std_2=float(std_2))
+                             cond_scale=float(cond_scale), mel_pp=bool(mel_pp), std_1=float(std_1), std_2=float(std_2),
+                             adaptive=self._adaptive())
         if not decode_to_audio:
             return mel
         out = eng.vocoder(mel).unsqueeze(1)
@@ -325,8 +345,7 @@ class FlowHighSR(nn.Module):
         """Batched `generate`: every clip is processed exactly as the reference processes it alone
         (per-clip peak normalisation, attention, cutoff and output normalisation).
         Clips sharing (sr, length) run as one batch through every kernel."""
-        if self.upsampling_method != "scipy":
-            raise NotImplementedError("upsampling_method='librosa' (soxr_hq) is a SURVEY 8f 'next' row")
+        self._resample_method()
         eng = self._engine()
         eng.new_call()
         srs = [sr] * len(audios) if isinstance(sr, int) else list(sr)
@@ -344,7 +363,7 @@ class FlowHighSR(nn.Module):
             if pinned:
                 host = host.pin_memory()
             e = None if eps is None else torch.cat([eps[i].reshape(1, -1, 256) for i in idxs])
-            if self.cuda_graphs and len(idxs) <= self.cuda_graph_max_batch:
+            if self.cuda_graphs and len(idxs) <= self.cuda_graph_max_batch and not self.use_torchode:
                 out = self._run_group_graphed(eng, host, s, int(target_sampling_rate), int(timestep), e)
             else:
                 x = host.to(eng.device, non_blocking=True)
@@ -359,10 +378,11 @@ class FlowHighSR(nn.Module):
     def _run_group(self, eng, x, sr, target_sr, timestep, eps_dev):
         """resample -> log-mel -> CFM -> vocoder -> post-processing for one batch of equal-length clips."""
         eng.status_begin()
-        cond = eng.resample_normalise(x, sr, target_sr)
+        cond = eng.resample_normalise(x, sr, target_sr, method=self._resample_method())
         cond_mel = eng.encode(cond)
         mel = eng.sample_mel(cond_mel, self._noise_like(cond_mel, eps_dev), steps=timestep,
-                             ode_method=self.odeint_kwargs["method"], cfm_method=self.cfm_method, sigma=float(self.sigma))
+                             ode_method=self.odeint_kwargs["method"], cfm_method=self.cfm_method, sigma=float(self.sigma),
+                             adaptive=self._adaptive())
         out = eng.postprocess(eng.vocoder(mel), cond)
         eng.status_end()
         return out
@@ -387,7 +407,8 @@ class FlowHighSR(nn.Module):
         for the `cuda_graph_min_hits`-th time; the cache holds `cuda_graph_cache_size` graphs, least recently used out
         (each entry owns its static buffers, its private pool and references to the engine buffers it replays into)."""
         B, n = host.shape
-        key = (B, n, sr, target_sr, timestep, self.odeint_kwargs["method"], self.cfm_method, float(self.sigma))
+        key = (B, n, sr, target_sr, timestep, self.odeint_kwargs["method"], self.cfm_method, float(self.sigma),
+               self.upsampling_method)
         ent = self._graphs.get(key)
         if ent is None:
             seen = self._graph_seen.get(key, 0) + 1
@@ -457,7 +478,7 @@ class FlowHighSR(nn.Module):
         world = dist.get_world_size(group) if distributed else 1
         rank = dist.get_rank(group) if distributed else 0
         x = torch.from_numpy(self._prep_input(audio))[None].to(eng.device)
-        cond = eng.resample_normalise(x, int(sr), target_sampling_rate)  # [1, T]  (every rank: 0.1 % of the work)
+        cond = eng.resample_normalise(x, int(sr), target_sampling_rate, method=self._resample_method())  # [1, T]  (every rank: 0.1 % of the work)
         T = cond.shape[1]
         clen = int(round(chunk_seconds * 48000)) // 480 * 480
         ov = int(round(overlap_seconds * 48000)) // 480 * 480
@@ -484,7 +505,7 @@ class FlowHighSR(nn.Module):
             e = eps[k0 + b0: k0 + b0 + c.shape[0]]
             mel = eng.sample_mel(mel_c, self._noise_like(mel_c, e), steps=int(timestep),
                                  ode_method=self.odeint_kwargs["method"], cfm_method=self.cfm_method,
-                                 sigma=float(self.sigma))
+                                 sigma=float(self.sigma), adaptive=self._adaptive())
             waves[b0: b0 + c.shape[0]] = eng.vocoder(mel)
         if world > 1:
             waves = sharding.gather_blocks(waves, per, K, group)  # the only collective of the path

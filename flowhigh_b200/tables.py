@@ -32,6 +32,41 @@ def resample_plan(sr_in: int, sr_out: int):
     return h, up, down, n_pre_pad, n_pre_remove
 
 
+def soxr_hq_spec():
+    """Band edges and rejection of libsoxr's HQ recipe (soxr.c `soxr_quality_spec`, quality 4 = SOXR_HQ as
+    `librosa.resample(..., res_type='soxr_hq')` selects it at flowhighsr.py:76): 20-bit precision => 120.4 dB rejection,
+    linear phase, stop band from 1.0 x the lower Nyquist, pass band to 1 - 0.05 / TO_3dB(rej) = 0.9136 x that."""
+    rej = 20 * 20.0 * math.log10(2.0)
+    to_3db = (1.6e-6 * rej - 7.5e-4) * rej + 0.646
+    return rej, 1.0 - 0.05 / to_3db, 1.0
+
+
+@lru_cache(maxsize=None)
+def resample_plan_soxr_hq(sr_in: int, sr_out: int):
+    """Same tuple as `resample_plan` for `upsampling_method='librosa'`: ONE linear-phase Kaiser-windowed-sinc polyphase
+    filter designed to soxr_hq's published band edges and rejection.  libsoxr itself (not installable offline, cannot
+    be pinned) reaches the same specification with a multi-stage half-band / polyphase cascade, so the two agree inside
+    the pass band and the stop band to the 20-bit precision the recipe promises and differ only in the shape of the
+    transition band (0.9136 .. 1.0 of the input Nyquist frequency) and in how the first / last filter-length of samples
+    is extrapolated (here: zero extension, as in the scipy path)."""
+    from scipy.signal import firwin
+    g = math.gcd(sr_out, sr_in)
+    up, down = sr_out // g, sr_in // g
+    if up == 1 and down == 1:
+        return None
+    rej, fp, fs = soxr_hq_spec()
+    q = max(up, down)
+    beta = 0.1102 * (rej - 8.7)
+    width = (fs - fp) / q                      # transition width as a fraction of the Nyquist rate of the up-rate grid
+    numtaps = int(math.ceil((rej - 7.95) / (2.285 * math.pi * width))) + 1
+    half = numtaps // 2 + 1
+    h = firwin(2 * half + 1, 0.5 * (fp + fs) / q, window=("kaiser", beta))
+    h = (h * up).astype(np.float32)
+    n_pre_pad = down - half % down
+    n_pre_remove = (half + n_pre_pad) // down
+    return h, up, down, n_pre_pad, n_pre_remove
+
+
 def resample_out_len(n_in: int, up: int, down: int) -> int:
     return -(-n_in * up // down)
 

@@ -157,6 +157,18 @@ int fh_geglu_f32(const float* u, void* g, int out_mode, int64_t out_rows, int M,
 /* y = a*x + b*z  elementwise (prior: y0 = cond + sigma*eps, cfm_superresolution.py:222-230) */
 int fh_axpby_f32(const float* x, const float* z, float a, float b, float* y, int64_t n, void* stream);
 
+/* Adaptive-step solver helpers (use_torchode=True: torchode.Tsit5 / Dopri5 + IntegralController,
+ * cfm_superresolution.py:259-276).
+ *   fh_rk_lincomb_f32:      out = (base ? base : 0) + sum_{j<nk} coef_host[j] * k[j*kstride + i]   (nk <= 8; coef_host is a
+ *                           HOST array, passed to the kernel by value) -- stage states, the solution and the error estimate
+ *   fh_rk_scaled_sumsq_f32: out[b] = sum_i (e[b,i] / (atol + rtol * max(|y0[b,i]|, |y1[b,i]|)))^2  in fp64, one block per
+ *                           problem instance (fixed summation order); y1 may be NULL.  The controller's error ratio is
+ *                           sqrt(out[b] / n). */
+int fh_rk_lincomb_f32(const float* base, const float* k, int64_t kstride, int nk, const float* coef_host, float* out,
+                      int64_t n, void* stream);
+int fh_rk_scaled_sumsq_f32(const float* e, const float* y0, const float* y1, float atol, float rtol, int B, int64_t n,
+                           double* out, void* stream);
+
 /* out[m, :] = row[:]  (null_cond broadcast for classifier-free guidance, flow.py:224-230) */
 int fh_broadcast_row_f32(const float* row, float* out, int64_t M, int C, void* stream);
 /* cutoff[b] = locate_cutoff_freq(exp(mel[b]))  cfm_superresolution.py:134-144,154-159 (percentile 0.9995) */

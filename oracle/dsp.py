@@ -83,14 +83,46 @@ def resample_poly(x: np.ndarray, sr_out: int, sr_in: int) -> np.ndarray:
     return y
 
 
-def preprocess_audio(audio: np.ndarray, sr: int, target_sr: int = 48000) -> np.ndarray:
-    """flowhighsr.py:59-69: squeeze, int16 heuristic, resample_poly, peak normalise."""
+def soxr_hq_filter(sr_in: int, sr_out: int):
+    """FIR taps (fp64, unit DC gain) meeting the specification of libsoxr's HQ recipe, the resampler behind
+    `librosa.resample(audio, sr, target, res_type='soxr_hq')` (flowhighsr.py:74-80).  libsoxr / librosa are third-party
+    dependencies (pyproject.toml:8 `librosa>=0.9.2`) that are NOT installed offline: PARITY UNPINNED.  Restated from
+    soxr.c `soxr_quality_spec`: quality HQ = 20-bit precision => rejection 20*6.02 = 120.4 dB, linear phase, stop band
+    from 1.0 x the lower Nyquist frequency, pass band to 1 - 0.05/TO_3dB(rej) of it, TO_3dB(a) = (1.6e-6 a - 7.5e-4) a + 0.646.
+    One Kaiser-windowed sinc (beta = 0.1102 (A - 8.7), length from Kaiser's formula) meets that specification; libsoxr
+    meets it with a multi-stage cascade, so the two differ only inside the transition band and at the clip edges."""
+    g = math.gcd(sr_out, sr_in)
+    up, down = sr_out // g, sr_in // g
+    rej = 20 * 20.0 * math.log10(2.0)
+    fp = 1.0 - 0.05 / ((1.6e-6 * rej - 7.5e-4) * rej + 0.646)
+    q = max(up, down)
+    width = (1.0 - fp) / q
+    numtaps = int(math.ceil((rej - 7.95) / (2.285 * math.pi * width))) + 1
+    half = numtaps // 2 + 1
+    return firwin_kaiser_lowpass(2 * half + 1, 0.5 * (fp + 1.0) / q, beta=0.1102 * (rej - 8.7)), up, down
+
+
+def resample_soxr_hq(x: np.ndarray, sr_out: int, sr_in: int) -> np.ndarray:
+    """Polyphase resampling with `soxr_hq_filter`, zero edge extension, ceil(n * ratio) output samples (librosa fixes the
+    length to that).  scipy's upfirdn (through resample_poly with an explicit FIR) does the arithmetic in x's dtype."""
+    from scipy.signal import resample_poly as _rp
+    x = np.asarray(x)
+    h, up, down = soxr_hq_filter(sr_in, sr_out)
+    if up == 1 and down == 1:
+        return x.copy()
+    dt = x.dtype if x.dtype in (np.float32, np.float64) else np.float64
+    return _rp(x.astype(dt), up, down, window=h.astype(dt))
+
+
+def preprocess_audio(audio: np.ndarray, sr: int, target_sr: int = 48000, method: str = "scipy") -> np.ndarray:
+    """flowhighsr.py:59-80: squeeze, int16 heuristic, resample (scipy branch :66-72 or librosa/soxr_hq branch :74-80),
+    peak normalise."""
     audio = np.asarray(audio)
     if audio.ndim == 2:
         audio = audio.squeeze(0)
     if audio.max() > 1:
         audio = audio / 32768.0
-    cond = resample_poly(audio, target_sr, sr)
+    cond = resample_poly(audio, target_sr, sr) if method == "scipy" else resample_soxr_hq(audio, target_sr, sr)
     cond = cond / np.max(np.abs(cond))
     return cond
 

@@ -175,11 +175,17 @@ def cfm_prior(cond_mel, eps, cfm_method, sigma):
 
 
 def cfm_sample_mel(sd, cond_mel, eps, *, steps, ode_method, cfm_method, sigma, cond_scale=1.0,
-                   mel_pp=False, depth=2, heads=16):
+                   mel_pp=False, depth=2, heads=16, adaptive=None):
     y0 = cfm_prior(cond_mel, eps, cfm_method, sigma)
     t = torch.linspace(0, 1, steps + 1)
     fn = lambda tt, yy: vector_field_cfg(sd, yy, cond_mel, tt, cond_scale=cond_scale, depth=depth, heads=heads)
-    out = odeint_fixed(fn, y0, t, ode_method)
+    if adaptive is not None:  # use_torchode (cfm_superresolution.py:259-276): every clip is its own problem instance
+        from . import ode_adaptive
+        fb = lambda b, tt, yy: vector_field_cfg(sd, yy, cond_mel[b: b + 1], tt.to(yy.dtype), cond_scale=cond_scale,
+                                                depth=depth, heads=heads)
+        out, _ = ode_adaptive.odeint_adaptive_batch(fb, y0, float(t[0]), float(t[-1]), **adaptive)
+    else:
+        out = odeint_fixed(fn, y0, t, ode_method)
     if mel_pp:  # cfm_superresolution.py:146-152,278-279
         res = torch.zeros_like(out)
         for i in range(out.shape[0]):

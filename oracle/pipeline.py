@@ -25,14 +25,20 @@ class OracleFlowHigh:
     sigma: float = 0.0
     cfm_method: str = "basic_cfm"
     ode_method: str = "midpoint"
+    upsampling_method: str = "scipy"   # 'librosa' = the soxr_hq branch (flowhighsr.py:74-80; dsp.resample_soxr_hq)
+    use_torchode: bool = False         # adaptive Tsit5 + IntegralController (cfm_superresolution.py:259-276; ode_adaptive.py)
+    torchode_method: str = "tsit5"
+    ode_atol: float = 1e-5
+    ode_rtol: float = 1e-5
 
     def sample(self, cond_audio: torch.Tensor, eps: torch.Tensor, time_steps: int, cfm_method: Optional[str] = None,
                cond_scale: float = 1.0, mel_pp: bool = False, decode: bool = True):
         cfm_method = cfm_method or self.cfm_method
         cond_mel = dsp.encode_logmel(cond_audio)
+        adaptive = dict(method=self.torchode_method, atol=self.ode_atol, rtol=self.ode_rtol) if self.use_torchode else None
         mel = model.cfm_sample_mel(self.sd, cond_mel, eps, steps=time_steps, ode_method=self.ode_method,
                                    cfm_method=cfm_method, sigma=self.sigma, cond_scale=cond_scale,
-                                   mel_pp=mel_pp, depth=self.depth, heads=self.heads)
+                                   mel_pp=mel_pp, depth=self.depth, heads=self.heads, adaptive=adaptive)
         if not decode:
             return mel
         return model.vocoder_forward(self.sd, self.vcfg, mel)
@@ -40,7 +46,8 @@ class OracleFlowHigh:
     @torch.no_grad()
     def generate(self, audio: np.ndarray, sr: int, eps: torch.Tensor, target_sampling_rate: int = 48000,
                  timestep: int = 1, return_stages: bool = False):
-        cond = dsp.preprocess_audio(audio, sr, target_sampling_rate)
+        cond = dsp.preprocess_audio(audio, sr, target_sampling_rate,
+                                    method="scipy" if self.upsampling_method == "scipy" else "soxr_hq")
         cond = torch.from_numpy(np.ascontiguousarray(cond)).float().unsqueeze(0)
         hr = self.sample(cond, eps, timestep).squeeze(1)
         out = dsp.postprocess(hr, cond, cond.shape[-1])

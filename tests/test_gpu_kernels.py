@@ -1056,3 +1056,128 @@ def test_tc_conv_pair_matches_single(cuda_device, B, Ci, Co, L, k, d):
     got = O2[: B * obs].view(B, Co // 8, ocs // 8, 8)[:, :, HALO:HALO + L].permute(0, 1, 3, 2).reshape(B, Co, L) - \
         R[: B * obs].view(B, Co // 8, ocs // 8, 8)[:, :, HALO:HALO + L].permute(0, 1, 3, 2).reshape(B, Co, L)
     assert float((got - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+# ------------------------------------------------------------------ soxr_hq branch, torchode branch
+def test_rk_helper_kernels(cuda_device):
+    """fh_rk_lincomb_f32 / fh_rk_scaled_sumsq_f32 against torch (stage combination, controller error norm)."""
+    import ctypes as C
+    eng, *_ = engine("gen_basic_midpoint", "fp32")
+    n = 75 * 256 + 3
+    g = torch.Generator().manual_seed(5)
+    K = torch.randn((8, n), generator=g)
+    K[5] = float("nan")  # a stage that is not part of the combination must not be read
+    base = torch.randn((n,), generator=g)
+    coefs = [0.3, -1.25, 0.0, 2.0, 0.0, 0.0, 1e-3]
+    Kd, bd, out = K.cuda(), base.cuda(), torch.empty(n, device="cuda:0")
+    arr = (C.c_float * 7)(*coefs)
+    eng._call("fh_rk_lincomb_f32", bd.data_ptr(), Kd.data_ptr(), n, 7, arr, out.data_ptr(), n, eng.stream)
+    ref = base.double() + sum(np.float32(c).item() * K[j].double() for j, c in enumerate(coefs) if c != 0.0)
+    assert float((out.cpu().double() - ref).abs().max()) <= 2e-6
+    eng._call("fh_rk_lincomb_f32", None, Kd.data_ptr(), n, 2, (C.c_float * 2)(-1.0, 1.0), out.data_ptr(), n, eng.stream)
+    assert torch.equal(out.cpu(), K[1] - K[0])
+    y0, y1 = torch.randn((2, n), generator=g) * 3, torch.randn((2, n), generator=g) * 3
+    e = torch.randn((2, n), generator=g) * 1e-4
+    ssq = torch.empty(2, dtype=torch.float64, device="cuda:0")
+    ed, y0d, y1d = e.cuda(), y0.cuda(), y1.cuda()
+    for yb in (y1, None):
+        eng._call("fh_rk_scaled_sumsq_f32", ed.data_ptr(), y0d.data_ptr(), None if yb is None else y1d.data_ptr(),
+                  1e-5, 1e-4, 2, n, ssq.data_ptr(), eng.stream)
+        m = y0.abs() if yb is None else torch.maximum(y0.abs(), yb.abs())
+        want = ((e / (1e-5 + 1e-4 * m)).double() ** 2).sum(1)
+        assert float(((ssq.cpu() - want) / want).abs().max()) <= 1e-5
+
+
+@pytest.mark.parametrize("method", ["tsit5", "dopri5"])
+def test_adaptive_sampler_f32_matches_oracle(cuda_device, method):
+    """use_torchode=True through the public sample(): the GPU's adaptive solve against the oracle's (same algorithm, fp64
+    and fp32), two clips of one batch with their own step sequences."""
+    g = load_golden("gen_basic_midpoint")
+    sd, vcfg = golden_weights(g)
+    cond = torch.from_numpy(np.ascontiguousarray(g["ref_cond_mel"]))[:, :48]
+    cond = torch.cat([cond, cond.flip(1) * 0.8 - 1.0]).contiguous()
+    eps = torch.from_numpy(np.ascontiguousarray(g["eps"])).reshape(1, -1, 256)[:, :48]
+    eps = torch.cat([eps, eps.flip(2)]).contiguous()
+
+    class Klass:  # the reference hands over a torchode class (flowhighsr.py:31)
+        pass
+    Klass.__name__ = {"tsit5": "Tsit5", "dopri5": "Dopri5"}[method]
+    m = FlowHighSR.from_random(vcfg, device="cuda:0", precision="fp32", use_torchode=True, torchode_method_klass=Klass,
+                               ode_atol=1e-5, ode_rtol=1e-5)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    out = m.sample(cond=cond, time_steps=4, decode_to_audio=False, eps=eps).cpu()
+    stats = m._engine().ode_stats
+    kw = dict(steps=4, ode_method="midpoint", cfm_method="basic_cfm", sigma=0.0)
+    ad = dict(method=method, atol=1e-5, rtol=1e-5)
+    sd64 = {k: v.double() for k, v in sd.items()}
+    fb = lambda b, t, y: model.vector_field(sd64, y, cond[b: b + 1].double(), t.double())
+    ref64, st64 = __import__("oracle.ode_adaptive", fromlist=["x"]).odeint_adaptive_batch(fb, eps.double(), 0.0, 1.0, **ad)
+    ref32 = model.cfm_sample_mel(sd, cond, eps, adaptive=ad, **kw)
+    floor = float((ref32.double() - ref64).abs().max())
+    e64 = float((out.double() - ref64).abs().max())
+    print(f"adaptive[{method}] fp32: max-abs vs oracle fp64 {e64:.3g} (oracle fp32's own {floor:.3g}); steps GPU "
+          f"{[s['n_steps'] for s in stats]} oracle {[s['n_steps'] for s in st64]}, NFE {[s['n_f_evals'] for s in stats]}")
+    assert len(stats) == 2
+    for a, b in zip(stats, st64):
+        assert abs(a["n_steps"] - b["n_steps"]) <= 2 and a["n_f_evals"] == 2 + 6 * a["n_steps"]
+    assert e64 <= 3 * floor + 2e-3
+    # the adaptive result is (much) closer to the oracle's adaptive solve than the fixed 4-step midpoint grid is
+    fixed = model.cfm_sample_mel(sd, cond, eps, **kw)
+    assert e64 < 0.2 * float((fixed.double() - ref64).abs().max())
+
+
+def test_adaptive_sampler_fp16_generate(cuda_device):
+    """The adaptive branch on the default 16-bit path, end to end through generate(): never graph-captured, finite, and
+    within the 16-bit bar of the oracle's adaptive pipeline at a tolerance the 11-bit field noise allows."""
+    g = load_golden("gen_basic_midpoint")
+    sd, vcfg = golden_weights(g)
+    m = FlowHighSR.from_random(vcfg, device="cuda:0", precision="fp16", use_torchode=True, torchode_method_klass="tsit5",
+                               ode_atol=1e-3, ode_rtol=1e-3)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    wav, sr = g["wav"], int(g["sr"])
+    eps = torch.from_numpy(g["eps"])
+    for _ in range(3):  # repeated shapes must not be captured into a CUDA graph (host-driven accept / reject loop)
+        out = m.generate(wav, sr, 48000, timestep=1, eps=eps).cpu()
+    assert len(m._graphs) == 0 and torch.isfinite(out).all()
+    o = pipeline.OracleFlowHigh({k: v.double() for k, v in sd.items()}, vcfg, use_torchode=True, ode_atol=1e-3, ode_rtol=1e-3)
+    ref = o.generate(wav.astype(np.float64), sr, eps.double(), timestep=1).float()
+    st = m._engine().ode_stats
+    print(f"adaptive fp16 generate: SNR vs oracle fp64 {snr_db(ref, out):.1f} dB, stats {st}")
+    assert out.shape == ref.shape and snr_db(ref, out) >= 30.0
+    assert st[0]["n_steps"] <= 12
+
+
+@pytest.mark.parametrize("sr", [12000, 16000, 22050, 44100])
+def test_soxr_hq_resample_normalise(cuda_device, sr):
+    eng, *_ = engine("gen_basic_midpoint", "fp32")
+    xs = np.stack([synth_speech(sr // 2 + 7, sr, s) * (0.3 + 0.2 * s) for s in range(2)])
+    y = eng.resample_normalise(dev(xs), sr, method="soxr_hq").cpu().numpy()
+    for i in range(2):
+        ref = dsp.preprocess_audio(xs[i].astype(np.float64), sr, method="soxr_hq")
+        assert y[i].shape == ref.shape
+        assert np.abs(y[i] - ref).max() <= 2e-5
+    with pytest.raises(ValueError):
+        eng.resample_normalise(dev(xs), sr, method="kaiser_best")
+
+
+def test_generate_librosa_branch(cuda_device):
+    """upsampling_method='librosa' (flowhighsr.py:74-80) end to end against the oracle pipeline with the same option."""
+    g = load_golden("gen_basic_midpoint")
+    sd, vcfg = golden_weights(g)
+    m = FlowHighSR.from_random(vcfg, device="cuda:0", precision="fp32", upsampling_method="librosa")
+    m.load_state_dict(sd)
+    m = m.cuda()
+    o = pipeline.OracleFlowHigh(sd, vcfg, cfm_method="basic_cfm", ode_method="midpoint", upsampling_method="librosa")
+    wav = synth_speech(6000, 16000, seed=4)
+    eps = _eps_for(6000, 16000)
+    out = m.generate(wav, 16000, 48000, timestep=1, eps=eps).cpu()
+    ref = o.generate(wav, 16000, eps, timestep=1)
+    o_scipy = pipeline.OracleFlowHigh(sd, vcfg, cfm_method="basic_cfm", ode_method="midpoint")
+    err = float((out - ref).abs().max())
+    print(f"generate librosa branch: max-abs vs oracle {err:.3g}; vs the scipy branch {float((out - o_scipy.generate(wav, 16000, eps, timestep=1)).abs().max()):.3g}")
+    assert out.shape == ref.shape and err <= 1e-3
+    m.upsampling_method = "sinc_best"
+    with pytest.raises(ValueError):
+        m.generate(wav, 16000, 48000, timestep=1, eps=eps)

@@ -1,0 +1,148 @@
+"""CPU suite for the SURVEY 8(f) rows whose third-party dependency is absent offline (torchode, libsoxr): the
+restatements are pinned against mathematics instead of goldens -- Runge-Kutta order conditions, closed-form ODE
+solutions at the requested tolerance, a fine fixed-grid solve of the (reference-pinned) FLowHigh field, and the
+published soxr_hq filter specification."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from flowhigh_b200 import rk, tables
+from flowhigh_b200.synth import synth_speech
+from oracle import dsp, model, ode_adaptive as oa
+from util import golden_weights, load_golden
+
+
+# ------------------------------------------------------------------ torchode restatement
+@pytest.mark.parametrize("name", ["tsit5", "dopri5"])
+def test_tableaux_satisfy_order_conditions(name):
+    res = oa.order_condition_residuals(oa.TABLEAUX[name])
+    assert max(res.values()) <= 5e-15, res  # b: all conditions through order 4 (+ two of order 5); b - b_hat: through order 3
+    prod = rk.TABLEAUX[name]  # the product's own copy of the pair agrees with the oracle's
+    assert np.abs(np.array(prod.e) - np.array(oa.TABLEAUX[name]["e"])).max() <= 1e-16
+    for rp, ro in zip(prod.a, oa.TABLEAUX[name]["a"]):
+        assert np.abs(np.array(rp) - np.array(ro)).max(initial=0.0) <= 1e-16
+    assert np.abs(np.array(prod.c) - np.array(oa.TABLEAUX[name]["c"])).max() <= 1e-16
+
+
+@pytest.mark.parametrize("name", ["tsit5", "dopri5"])
+def test_fixed_step_convergence_order_is_five(name):
+    """One step of the pair on y' = A y: local error O(h^6) for the solution, O(h^5) for the error estimate."""
+    tab = oa.TABLEAUX[name]
+    A = torch.tensor([[-0.5, 2.0], [-2.0, -0.3]], dtype=torch.float64)
+    y0 = torch.tensor([1.0, 0.5], dtype=torch.float64)
+    errs, ests = [], []
+    for h in (0.1, 0.05):
+        ks = []
+        ys = y0
+        for s in range(7):
+            ys = y0 + h * sum(w * k for w, k in zip(tab["a"][s], ks)) if s else y0
+            ks.append(A @ ys)
+        exact = torch.linalg.matrix_exp(A * h) @ y0
+        errs.append(float((ys - exact).norm()))
+        ests.append(float((h * sum(w * k for w, k in zip(tab["e"], ks))).norm()))
+    assert 5.5 <= math.log2(errs[0] / errs[1]) <= 7.0
+    assert 4.5 <= math.log2(ests[0] / ests[1]) <= 5.5
+
+
+@pytest.mark.parametrize("name", ["tsit5", "dopri5"])
+@pytest.mark.parametrize("tol", [1e-4, 1e-6, 1e-8])
+def test_adaptive_solver_meets_tolerance_on_closed_form(name, tol):
+    A = torch.tensor([[-0.5, 6.0], [-6.0, -0.3]], dtype=torch.float64)
+    y0 = torch.tensor([[1.0, 0.5]], dtype=torch.float64)
+    fn = lambda t, y: y @ A.T + torch.sin(3 * t) * 0.0
+    y, st = oa.odeint_adaptive(fn, y0, 0.0, 1.0, atol=tol, rtol=tol, method=name)
+    exact = y0 @ torch.linalg.matrix_exp(A).T
+    assert float((y - exact).abs().max()) <= 20 * tol
+    assert st["n_f_evals"] == 2 + 6 * st["n_steps"] and st["n_accepted"] <= st["n_steps"]
+    # a looser tolerance must not cost more work
+    _, st2 = oa.odeint_adaptive(fn, y0, 0.0, 1.0, atol=tol * 100, rtol=tol * 100, method=name)
+    assert st2["n_steps"] <= st["n_steps"]
+
+
+def test_adaptive_flowhigh_field_converges_to_fine_grid_solution():
+    """The oracle's adaptive solve of the reference-pinned vector field approaches a 96-step RK4 solve (fp64) as the
+    tolerance tightens; at the reference default 1e-5 it is far closer than the 2-NFE midpoint solve generate() uses."""
+    g = load_golden("gen_basic_midpoint")
+    sd, _ = golden_weights(g)
+    sd = {k: v.double() if v.is_floating_point() else v for k, v in sd.items()}
+    cond = torch.from_numpy(g["ref_cond_mel"]).double()[:, :40]
+    y0 = torch.from_numpy(g["eps"]).double().reshape(1, -1, 256)[:, :40]
+    fn = lambda t, y: model.vector_field(sd, y, cond, t.double())
+    y, n = y0, 96
+    for i in range(n):
+        t, h = torch.tensor(i / n, dtype=torch.float64), 1.0 / n
+        k1 = fn(t, y); k2 = fn(t + h / 2, y + h / 2 * k1); k3 = fn(t + h / 2, y + h / 2 * k2); k4 = fn(t + h, y + h * k3)
+        y = y + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+    fine = y
+    e = {}
+    for tol in (1e-3, 1e-5):
+        ya, st = oa.odeint_adaptive(fn, y0, 0.0, 1.0, atol=tol, rtol=tol)
+        e[tol] = float((ya - fine).abs().max())
+    mid = model.odeint_fixed(fn, y0, torch.linspace(0, 1, 2, dtype=torch.float64), "midpoint")
+    e_mid = float((mid - fine).abs().max())
+    print(f"adaptive vs fine grid: tol 1e-3 {e[1e-3]:.3g}, tol 1e-5 {e[1e-5]:.3g}; one midpoint step {e_mid:.3g}")
+    assert e[1e-5] < 0.2 * e[1e-3] and e[1e-5] <= 5e-3 and e[1e-5] < 0.05 * e_mid
+
+
+def test_pipeline_torchode_option_runs_per_clip():
+    g = load_golden("gen_basic_midpoint")
+    sd, _ = golden_weights(g)
+    cond = torch.from_numpy(g["ref_cond_mel"])[:, :24]
+    cond2 = torch.cat([cond, cond.flip(1)])
+    eps = torch.from_numpy(g["eps"]).reshape(1, -1, 256)[:, :24]
+    eps2 = torch.cat([eps, eps * 0.5])
+    kw = dict(steps=4, ode_method="midpoint", cfm_method="basic_cfm", sigma=0.0, adaptive=dict(method="tsit5", atol=1e-3, rtol=1e-3))
+    both = model.cfm_sample_mel(sd, cond2, eps2, **kw)
+    for b in range(2):  # every clip is an independent problem instance (torchode's batching semantics)
+        one = model.cfm_sample_mel(sd, cond2[b: b + 1], eps2[b: b + 1], **kw)
+        assert torch.equal(one, both[b: b + 1])
+
+
+def test_controller_matches_oracle_decisions():
+    ctl = rk.IntegralController(atol=1e-5, rtol=1e-5, order=5)
+    for ratio in (0.0, 1e-9, 0.3, 0.999, 1.0, 1.7, 1e6):
+        want = oa.FACTOR_MAX if ratio == 0 else min(oa.FACTOR_MAX, max(oa.FACTOR_MIN, oa.SAFETY * ratio ** -0.2))
+        assert ctl.next_dt(0.125, ratio) == pytest.approx(0.125 * want, rel=1e-15)
+        assert ctl.accept(ratio) == (ratio < 1.0)
+    assert rk.resolve(None).name == "tsit5" and rk.resolve("Dopri5").name == "dopri5"
+
+    class Tsit5:  # the reference passes the class (flowhighsr.py:31)
+        pass
+    assert rk.resolve(Tsit5).name == "tsit5"
+    with pytest.raises(NotImplementedError):
+        rk.resolve("Heun")
+
+
+# ------------------------------------------------------------------ soxr_hq restatement
+@pytest.mark.parametrize("sr", [8000, 12000, 16000, 24000, 22050, 44100])
+def test_soxr_hq_filter_meets_published_specification(sr):
+    h, up, down = dsp.soxr_hq_filter(sr, 48000)
+    rej, fp, fs = tables.soxr_hq_spec()
+    assert abs(rej - 120.41) < 0.01 and abs(fp - 0.9136) < 1e-3 and fs == 1.0
+    n = 1 << (22 if len(h) > 20000 else 20)
+    H = np.abs(np.fft.rfft(h, n))
+    f = np.arange(len(H)) / (n / 2) * max(up, down)  # in units of the lower Nyquist frequency
+    assert np.abs(20 * np.log10(H[f <= fp])).max() <= 2e-5          # pass band flat to 20 bits
+    assert 20 * np.log10(H[f >= fs].max()) <= -(rej - 1.0)           # stop band at the recipe's rejection
+    assert np.array_equal(h, h[::-1])                                # linear phase
+    plan = tables.resample_plan_soxr_hq(sr, 48000)                   # the product's table is the same design
+    assert plan[1:3] == (up, down) and np.abs(plan[0] - (h * up).astype(np.float32)).max() <= 1e-7
+
+
+@pytest.mark.parametrize("sr", [12000, 16000, 44100])
+def test_soxr_hq_resampling_preserves_in_band_tones_and_length(sr):
+    t = np.arange(sr // 2) / sr
+    f0 = 0.3 * sr / 2
+    x = np.sin(2 * np.pi * f0 * t)
+    y = dsp.resample_soxr_hq(x, 48000, sr)
+    assert y.shape[0] == -(-x.shape[0] * 48000 // sr)
+    t2 = np.arange(y.shape[0]) / 48000
+    mid = slice(4000, y.shape[0] - 4000)  # away from the zero-extended edges
+    assert np.abs(y[mid] - np.sin(2 * np.pi * f0 * t2)[mid]).max() <= 1e-5
+    # and it differs from the scipy branch only by that branch's much wider transition band
+    x2 = synth_speech(sr // 2, sr, seed=3)
+    a, b = dsp.preprocess_audio(x2, sr, method="soxr_hq"), dsp.preprocess_audio(x2, sr, method="scipy")
+    assert a.shape == b.shape and np.abs(a).max() == pytest.approx(1.0)
+    assert 1e-4 < np.abs(a - b).max() < 0.5
