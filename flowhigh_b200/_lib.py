@@ -70,6 +70,9 @@ SIGNATURES = {
     "fh_attention_f32": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _f, _p]),
     "fh_qknorm_rope_split": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
     "fh_attention_tc": (_i, [_p, _p, _p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i, _p]),
+    "fh_attention_tc5_operand_elems": (_i64, [_i, _i, _i, _i]),
+    "fh_qknorm_rope_tiles": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _p]),
+    "fh_attention_tc5": (_i, [_p, _p, _p, _p, _i, _i64, _i, _i, _i, _i, _i, _p]),
     "fh_geglu_f32": (_i, [_p, _p, _i, _i64, _i, _i, _i, _p]),
     "fh_axpby_f32": (_i, [_p, _p, _f, _f, _p, _i64, _p]),
     "fh_rk_lincomb_f32": (_i, [_p, _p, _i64, _i, C.POINTER(_f), _p, _i64, _p]),

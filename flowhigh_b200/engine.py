@@ -78,7 +78,8 @@ class Engine:
         self.profile = None
         import os as _os
         self.voc_streams = int(_os.environ.get("FH_VOC_STREAMS", "1"))
-        self.tc_attention = _os.environ.get("FH_TC_ATTENTION", "1") != "0"  # mma.sync split-operand attention
+        self.tc_attention = _os.environ.get("FH_TC_ATTENTION", "1") != "0"  # tensor-core split-operand attention
+        self.attn5 = _os.environ.get("FH_ATTN_TC5", "1") != "0"  # tcgen05 / TMEM kernel (0: the mma.sync kernel)
         # fp16 path, stages of <= 128 channels: FH_FUSE_SNAKE=1 runs the anti-aliased snake INSIDE the conv kernel as the
         # producer of its A operand (tc_conv_snakepro_kernel: 16 instead of 24 HBM bytes per element of an AMP unit).
         # Parity-tested, but measured at the same step time as the separate launches on B200 (311-319 vs 312 ms; ncu in
@@ -592,7 +593,18 @@ class Engine:
                 self._call("fh_rmsnorm_f32", h.data_ptr(), tcnd[(l, 2, "gamma")].data_ptr(), tcnd[(l, 2, "beta")].data_ptr(),
                            a.data_ptr(), 0, 0, M, D, st)
                 self._sgemm(a, D, sd[p + "3.to_qkv.weight"], D, None, None, 0, 0.0, 1.0, qkv, 3 * D, M, 3 * D, D)
-            if self.tc and self.tc_attention:
+            if self.tc and self.tc_attention and self.attn5:
+                # tcgen05 attention: q / k / v^T written directly as the MMA operand images (attention_tc5.cu)
+                ops = [self.buf(f"bb_{nm}5", (int(self.lib.fh_attention_tc5_operand_elems(w, B, H, N)),), self.h16)
+                       for w, nm in enumerate(("q", "k", "v"))]
+                self._call("fh_qknorm_rope_tiles", qkv.data_ptr(), sd[p + "3.q_norm.gamma"].data_ptr(),
+                           sd[p + "3.k_norm.gamma"].data_ptr(), sd[FH + "transformer.rotary_emb.inv_freq"].data_ptr(),
+                           *[t_.data_ptr() for t_ in ops], B, N, H, Dh, float(b.qk_norm_scale), self.fp16, st,
+                           work={"bytes": (12.0 + 10.0) * B * N * H * Dh, "tag": "fh_qknorm_rope_split"})
+                self._call("fh_attention_tc5", *[t_.data_ptr() for t_ in ops], act.data_ptr(), self.k16, Mp, B, H, N, Dh,
+                           self.fp16, st, work={"flops": 4.0 * B * H * N * N * Dh, "bytes": 2.0 * 6 * B * H * N * Dh,
+                                                "tag": "fh_attention_tc"})
+            elif self.tc and self.tc_attention:
                 s16 = [self.buf(f"bb_{nm}16", (B, H, N, Dh), self.h16, zero=False) for nm in ("qh", "ql", "kh", "kl", "v")]
                 self._call("fh_qknorm_rope_split", qkv.data_ptr(), sd[p + "3.q_norm.gamma"].data_ptr(),
                            sd[p + "3.k_norm.gamma"].data_ptr(), sd[FH + "transformer.rotary_emb.inv_freq"].data_ptr(),

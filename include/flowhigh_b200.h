@@ -151,6 +151,18 @@ int fh_qknorm_rope_split(const float* qkv, const float* qg, const float* kg, con
                          int B, int N, int H, int D, float scale, int fp16, void* stream);
 int fh_attention_tc(const void* qh, const void* ql, const void* kh, const void* kl, const void* v16, void* out,
                     int out_mode, int64_t out_rows, int B, int H, int N, int D, int fp16, void* stream);
+/* tcgen05 / TMEM form of the same attention (attention_tc5.cu; the default 16-bit path).  fh_qknorm_rope_tiles writes the
+ * operands as ready-made shared-memory images of the MMAs (no-swizzle K-major core matrices), one contiguous tile per
+ * 128-query tile / 64-key block:
+ *   q5 [B*H][ceil(N/128)][hi | lo][D/8][128][8]   k5 [B*H][ceil(N/64)][hi | lo][D/8][64][8]   v5 [B*H][ceil(N/64)][8][D][8]
+ * (v5 = V^T, keys past N zero-filled); fh_attention_tc5_operand_elems(which = 0 / 1 / 2, ...) gives their sizes in 16-bit
+ * elements.  fh_attention_tc5: S = qh.kh + ql.kh + qh.kl and P.V as tcgen05.mma into TMEM, softmax by one thread per
+ * query row, running output in registers; out / out_mode / out_rows as in fh_attention_f32. */
+int64_t fh_attention_tc5_operand_elems(int which, int B, int H, int N);
+int fh_qknorm_rope_tiles(const float* qkv, const float* qg, const float* kg, const float* inv_freq,
+                         void* q5, void* k5, void* v5, int B, int N, int H, int D, float scale, int fp16, void* stream);
+int fh_attention_tc5(const void* q5, const void* k5, const void* v5, void* out, int out_mode, int64_t out_rows,
+                     int B, int H, int N, int D, int fp16, void* stream);
 /* g[M,inner] = gelu(u[M, inner + i]) * u[M, i]    transformer.py:92-95 */
 int fh_geglu_f32(const float* u, void* g, int out_mode, int64_t out_rows, int M, int inner, int inner_pad,
                  void* stream);

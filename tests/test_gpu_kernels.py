@@ -513,6 +513,54 @@ def test_attention_tc_matches_fp32_attention(cuda_device, precision, N):
     assert rel <= (2e-3 if precision == "fp16" else 1e-2)
 
 
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+@pytest.mark.parametrize("N", [1, 51, 64, 128, 129, 333, 1000])
+def test_attention_tc5_matches_fp32_attention(cuda_device, precision, N):
+    """tcgen05 / TMEM attention (the default 16-bit path) against the fp32 CUDA-core attention on the same q/k/v: every
+    tile-boundary case (one key, a partial key block, exactly one / two blocks, a partial query tile, the N = 1000 of the
+    timed configuration), the chunked 16-bit output the backbone consumes, and stale operand buffers from a longer call."""
+    eng, sd, vcfg, g = engine("gen_basic_midpoint", precision)
+    torch.manual_seed(N)
+    B, H, D = 2, 16, 64
+    qkv = torch.randn(B * N, 3 * H * D, device="cuda:0")
+    qg = (1 + 0.1 * torch.randn(H, 1, D, device="cuda:0")).contiguous()
+    kg = (1 + 0.1 * torch.randn(H, 1, D, device="cuda:0")).contiguous()
+    inv_freq = eng.sd["flowhigh.transformer.rotary_emb.inv_freq"]
+    q, k, v = (torch.empty(B, H, N, D, device="cuda:0") for _ in range(3))
+    ref = torch.empty(B * N, H * D, device="cuda:0")
+    eng._call("fh_qknorm_rope_f32", qkv.data_ptr(), qg.data_ptr(), kg.data_ptr(), inv_freq.data_ptr(), q.data_ptr(),
+              k.data_ptr(), v.data_ptr(), B, N, H, D, eng.stream)
+    eng._call("fh_attention_f32", q.data_ptr(), k.data_ptr(), v.data_ptr(), ref.data_ptr(), 0, 0, B, H, N, D, 10.0, eng.stream)
+    # operand buffers pre-filled with NaN bit patterns: rows / keys past N must never reach a kept output
+    ops = [torch.full((int(eng.lib.fh_attention_tc5_operand_elems(w, B, H, N)),), float("nan"), device="cuda:0", dtype=eng.h16)
+           for w in range(3)]
+    out = torch.empty(B * N, H * D, device="cuda:0")
+    eng._call("fh_qknorm_rope_tiles", qkv.data_ptr(), qg.data_ptr(), kg.data_ptr(), inv_freq.data_ptr(),
+              *[t.data_ptr() for t in ops], B, N, H, D, 10.0, eng.fp16, eng.stream)
+    eng._call("fh_attention_tc5", *[t.data_ptr() for t in ops], out.data_ptr(), 0, 0, B, H, N, D, eng.fp16, eng.stream)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    err = float((out - ref).abs().max())
+    rel = float((out - ref).norm() / ref.norm())
+    # the mma.sync kernel on the same inputs: same arithmetic (split logits, 16-bit P), different summation order
+    s16 = [torch.empty(B, H, N, D, device="cuda:0", dtype=eng.h16) for _ in range(5)]
+    old = torch.empty(B * N, H * D, device="cuda:0")
+    eng._call("fh_qknorm_rope_split", qkv.data_ptr(), qg.data_ptr(), kg.data_ptr(), inv_freq.data_ptr(),
+              *[t.data_ptr() for t in s16], B, N, H, D, 10.0, eng.fp16, eng.stream)
+    eng._call("fh_attention_tc", *[t.data_ptr() for t in s16], old.data_ptr(), 0, 0, B, H, N, D, eng.fp16, eng.stream)
+    rel_old = float((old - ref).norm() / ref.norm())
+    print(f"attention_tc5 {precision} N={N}: max-abs {err:.3g}, rel-L2 {rel:.3g} (mma.sync kernel: {rel_old:.3g})")
+    assert rel <= (2e-3 if precision == "fp16" else 1e-2)
+    assert rel <= 1.5 * rel_old + 1e-4
+    # chunked 16-bit output (what the to_out GEMM reads)
+    Mp = packing.round_up(B * N, 128) + 64
+    act = torch.zeros((H * D // 8, Mp, 8), device="cuda:0", dtype=eng.h16)
+    eng._call("fh_attention_tc5", *[t.data_ptr() for t in ops], act.data_ptr(), eng.k16, Mp, B, H, N, D, eng.fp16, eng.stream)
+    got = act[:, : B * N].permute(1, 0, 2).reshape(B * N, H * D).float()
+    assert float((got - out).abs().max()) <= (2e-3 if precision == "fp16" else 2e-2) * float(out.abs().max())
+    assert float(act[:, B * N:].abs().max()) == 0.0
+
+
 def test_cuda_graph_generate_matches_eager(cuda_device):
     g = load_golden("gen_basic_midpoint")
     sd, vcfg = golden_weights(g)
