@@ -17,6 +17,7 @@
 //     memory with separate barriers (K is released when S is done, V when P.V is done); 97 KB + 256 columns per CTA,
 //     so two CTAs share an SM and one's softmax overlaps the other's MMAs.
 // Warps 0-3: softmax (TMEM lane groups 0-3), warp 4: producer, warp 5: MMA issuer + TMEM allocator.
+#include <type_traits>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -46,6 +47,11 @@ struct At5Params {
   unsigned int* err_flag;
 };
 
+__device__ __forceinline__ float max3f(float a, float b, float c) {
+  float y;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));
+  return y;
+}
 __device__ __forceinline__ float ex2f(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -182,10 +188,12 @@ __global__ void __launch_bounds__(kThreads5, 2) attention_tc5_kernel(const __gri
       tc_fence_before();
       mbar_arrive(bar(O_FREE, j & 1));
     };
-    for (int i = 0; i < nkb; ++i) {
+    // one key block; MASKED only for a last block with fewer than 64 keys (the index tests cost as much as the softmax)
+    auto block = [&](int i, auto masked_tag) {
+      constexpr bool MASKED = decltype(masked_tag)::value;
       const int s = i & 1;
       const uint32_t tS = tlane + (uint32_t)s * 64u;
-      const int nvalid = min(KB, P.N - i * KB);  // keys of this block that exist
+      const int nvalid = P.N - i * KB;  // keys of this block that exist (>= 64 unless MASKED)
       mbar_wait(bar(S_FULL, s), (uint32_t)((i >> 1) & 1), P.err_flag, 31);
       tc_fence_after();
       // ---- pass 1: row maximum
@@ -195,9 +203,14 @@ __global__ void __launch_bounds__(kThreads5, 2) attention_tc5_kernel(const __gri
         uint32_t v[16];
         tmem_ld16(tS + (uint32_t)c * 16u, v);
         tmem_ld_wait();
+        if (MASKED) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e)
-          if (c * 16 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+          for (int e = 0; e < 16; ++e)
+            if (c * 16 + e < nvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) mx = max3f(mx, __uint_as_float(v[e]), __uint_as_float(v[e + 1]));
+        }
       }
       const float m_new = fmaxf(m2, mx * kLog2e);
       const float corr = ex2f(m2 - m_new);
@@ -208,7 +221,7 @@ __global__ void __launch_bounds__(kThreads5, 2) attention_tc5_kernel(const __gri
         tc_fence_after();
       }
       // ---- pass 2: p = 2^(s log2e - m), packed into the A image of the P.V MMA
-      float psum = 0.f;
+      float psum0 = 0.f, psum1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[16];
@@ -219,9 +232,12 @@ __global__ void __launch_bounds__(kThreads5, 2) attention_tc5_kernel(const __gri
         for (int e = 0; e < 16; e += 2) {
           float p0 = ex2f(fmaf(__uint_as_float(v[e]), kLog2e, -m_new));
           float p1 = ex2f(fmaf(__uint_as_float(v[e + 1]), kLog2e, -m_new));
-          if (c * 16 + e >= nvalid) p0 = 0.f;
-          if (c * 16 + e + 1 >= nvalid) p1 = 0.f;
-          psum += p0 + p1;
+          if (MASKED) {
+            if (c * 16 + e >= nvalid) p0 = 0.f;
+            if (c * 16 + e + 1 >= nvalid) p1 = 0.f;
+          }
+          psum0 += p0;
+          psum1 += p1;
           pk[e >> 1] = fh::pack16(p0, p1, fp16);
         }
         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(prow + (uint32_t)(2 * c) * (QT * 16u)), "r"(pk[0]),
@@ -235,10 +251,13 @@ __global__ void __launch_bounds__(kThreads5, 2) attention_tc5_kernel(const __gri
       mbar_arrive(bar(S_FREE, s));
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy P stores before the MMA's async reads
       mbar_arrive(bar(P_FULL));
-      l = fmaf(l, corr, psum);
+      l = fmaf(l, corr, psum0 + psum1);
       if (i > 0) fold(i - 1);
       corr_pend = corr;
-    }
+    };
+    const int nfull = P.N / KB;  // blocks with all 64 keys
+    for (int i = 0; i < nfull; ++i) block(i, std::false_type{});
+    if (nfull < nkb) block(nfull, std::true_type{});
     mbar_wait(bar(O_FULL, (nkb - 1) & 1), (uint32_t)(((nkb - 1) >> 1) & 1), P.err_flag, 33);
     tc_fence_after();
     fold(nkb - 1);
