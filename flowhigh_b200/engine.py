@@ -79,6 +79,7 @@ class Engine:
         import os as _os
         self.voc_streams = int(_os.environ.get("FH_VOC_STREAMS", "1"))
         self.tc_attention = _os.environ.get("FH_TC_ATTENTION", "1") != "0"  # tensor-core split-operand attention
+        self._cool_ms = float(_os.environ.get("FH_PROFILE_COOL_MS", "0"))
         self.attn5 = _os.environ.get("FH_ATTN_TC5", "1") != "0"  # tcgen05 / TMEM kernel (0: the mma.sync kernel)
         # fp16 path, stages of <= 128 channels: FH_FUSE_SNAKE=1 runs the anti-aliased snake INSIDE the conv kernel as the
         # producer of its A operand (tc_conv_snakepro_kernel: 16 instead of 24 HBM bytes per element of an AMP unit).
@@ -215,11 +216,20 @@ class Engine:
             work = {"bytes": float(args[8] * args[9] * args[10]) * 4.0, "tag": "fh_snake_aa_chunked"}
         if work is None and name == "fh_rmsnorm_f32":  # fp32 row in, fp32 / 16-bit row out  (args: ..., out_mode, rows, M, C, stream)
             work = {"bytes": float(args[6] * args[7]) * (8.0 if args[4] == 0 else 6.0)}
+        self._profile_cool()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(self.device))
         _lib.check(getattr(self.lib, name)(*args), name)
         e1.record(torch.cuda.current_stream(self.device))
         self.profile.append((name, e0, e1, work or {}))
+
+    def _profile_cool(self):
+        """Profile mode only, FH_PROFILE_COOL_MS=x: drain the GPU and idle x ms before every launch, so each kernel is timed
+        alone on a chip that is not at its power cap (tools/cool_vs_hot.py: is a kernel slow, or is the step power-limited?)."""
+        if self._cool_ms > 0.0:
+            import time
+            torch.cuda.synchronize(self.device)
+            time.sleep(self._cool_ms * 1e-3)
 
     def start_profile(self):
         """Brackets every kernel launch with CUDA events on the launching stream (bench.py roofline leg)."""
@@ -501,6 +511,7 @@ class Engine:
         if self.profile is None:
             _lib.check(self.lib.fh_tc_conv(C.byref(args), self.stream), "fh_tc_conv")
             return
+        self._profile_cool()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(torch.cuda.current_stream(self.device))
         _lib.check(self.lib.fh_tc_conv(C.byref(args), self.stream), "fh_tc_conv")
