@@ -64,7 +64,7 @@ def peaks():
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
@@ -94,8 +94,20 @@ class ClockSampler:
         mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower() == "active" for r in self.rows)]
+        def col(i):
+            out = []
+            for r in self.rows:
+                try:
+                    out.append(float(r[i]))
+                except (IndexError, ValueError):
+                    pass
+            return out
+        pw, pl = col(6), col(7)
+        # the step is energy-bound at the board power cap: the draw belongs next to the clock
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "sm_mhz_min": min(sm) if sm else None, "sm_mhz_peak": max(sm) if sm else None,
+                "reasons": reasons, "samples": len(sm), "power_w": statistics.median(pw) if pw else None,
+                "power_limit_w": max(pl) if pl else None}
 
 
 # ------------------------------------------------------------------------------------------- CPU arm

@@ -16,7 +16,9 @@ vendored under /root/reference, so this file restates its published algorithm:
   * the step is clipped so the solver lands on t_end exactly, and only the final state is returned (the call site reads
     `sol.ys[:, -1]`; the interior t_eval points are never used).
 
-PARITY UNPINNED: no torchode golden can be generated in this container.  What the tests pin instead: the tableaux against
+PARITY UNPINNED against torchode itself: no torchode golden can be generated in this container.  The Dopri5 path IS pinned
+against an installed independent implementation of the same method and controller family, scipy.integrate.solve_ivp('RK45')
+(same step counts to +-2, same error; tests/test_next_rows_cpu.py).  What else the tests pin: the tableaux against
 the Runge-Kutta order conditions, the solver against closed-form solutions at the requested tolerance, and (for the FLowHigh
 field) against a 256-step fixed-grid solve of the already-pinned vector field.  Controller details that may differ from
 torchode 1.0.0 (exact clipping constants, dense-output evaluation of the last point instead of step clipping) move the

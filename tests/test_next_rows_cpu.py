@@ -146,3 +146,25 @@ def test_soxr_hq_resampling_preserves_in_band_tones_and_length(sr):
     a, b = dsp.preprocess_audio(x2, sr, method="soxr_hq"), dsp.preprocess_audio(x2, sr, method="scipy")
     assert a.shape == b.shape and np.abs(a).max() == pytest.approx(1.0)
     assert 1e-4 < np.abs(a - b).max() < 0.5
+
+
+@pytest.mark.parametrize("tol", [1e-4, 1e-6])
+def test_dopri5_adaptive_agrees_with_scipy_rk45(tol):
+    """scipy.integrate.solve_ivp(method='RK45') is an installed, independent Dormand-Prince 5(4) solver with the same
+    family of controller (rms-scaled error, safety 0.9, factors 0.2 .. 10, Hairer's first step): the restated Dopri5 path
+    must land on the same solution to O(tol) with a comparable number of steps (not identical: scipy's exponent is
+    1/5 on the first-step heuristic too and it forbids growth right after a rejection)."""
+    from scipy.integrate import solve_ivp
+
+    def vdp(t, y):  # Van der Pol, mu = 2: smooth but with a fast transient
+        return np.array([y[1], 2.0 * (1.0 - y[0] ** 2) * y[1] - y[0]])
+    y0 = np.array([2.0, 0.0])
+    ref = solve_ivp(vdp, (0.0, 3.0), y0, method="RK45", atol=tol, rtol=tol)
+    tight = solve_ivp(vdp, (0.0, 3.0), y0, method="DOP853", atol=1e-12, rtol=1e-12).y[:, -1]
+    fn = lambda t, y: torch.stack([y[0, 1], 2.0 * (1.0 - y[0, 0] ** 2) * y[0, 1] - y[0, 0]])[None]
+    y, st = oa.odeint_adaptive(fn, torch.tensor(y0)[None], 0.0, 3.0, atol=tol, rtol=tol, method="dopri5")
+    e_or, e_sp = np.abs(y[0].numpy() - tight).max(), np.abs(ref.y[:, -1] - tight).max()
+    n_sp = (ref.nfev - 2) // 6
+    print(f"dopri5 tol {tol:g}: oracle err {e_or:.3g} in {st['n_steps']} steps; scipy RK45 err {e_sp:.3g} in {n_sp} steps")
+    assert e_or <= max(5 * e_sp, 20 * tol)
+    assert abs(st["n_steps"] - n_sp) <= max(3, 0.25 * n_sp)
