@@ -542,7 +542,7 @@ def main():
                 tf = v["flops"] / (v["ms"] / 1000.0) / 1e12
                 roofline_stages[k] = {"bound": "tensor", "achieved": tf, "peak": tf_peak, "unit": "TFLOP/s", "frac": tf / tf_peak,
                                       "ms": v["ms"], "launches": v["launches"],
-                                      "note": "mma.sync m16n8k16 with the hi/lo operand split (3 MMAs per q k^T tile): algorithmic 4 N^2 Dh per head"}
+                                      "note": "attention_tc5_kernel (tcgen05 / TMEM; FH_ATTN_TC5=0: the mma.sync kernel) with the hi/lo operand split (q k^T executed 3 x): algorithmic 4 N^2 Dh per head"}
             elif v["bytes"] > 0:
                 gbs = v["bytes"] / (v["ms"] / 1000.0) / 1e9
                 roofline_stages[k] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
