@@ -276,6 +276,23 @@ class FlowHighSR(nn.Module):
             return None
         return dict(tableau=self._tableau, atol=float(self.odeint_kwargs["atol"]), rtol=float(self.odeint_kwargs["rtol"]))
 
+    def _staging(self, B: int, n: int) -> torch.Tensor:
+        """Page-locked [B, n] fp32 staging buffer of the batched host path, cached per shape (a few entries, least recently
+        used out).  The previous upload from it must have left the host before it is refilled."""
+        if getattr(self, "_stage_event", None) is None:
+            self._stage_event = torch.cuda.Event()
+            self._stage_bufs = collections.OrderedDict()
+        else:
+            self._stage_event.synchronize()
+        buf = self._stage_bufs.get((B, n))
+        if buf is None:
+            buf = self._stage_bufs[(B, n)] = torch.empty((B, n), dtype=torch.float32).pin_memory()
+            while len(self._stage_bufs) > 4:
+                self._stage_bufs.popitem(last=False)
+        else:
+            self._stage_bufs.move_to_end((B, n))
+        return buf
+
     def _resample_method(self) -> str:
         """flowhighsr.py:66-80: 'scipy' = resample_poly, 'librosa' = librosa.resample(res_type='soxr_hq').  Anything else
         leaves `cond` undefined in the reference (NameError); here it is a ValueError."""
@@ -359,16 +376,26 @@ class FlowHighSR(nn.Module):
         for gi, ((s, n), idxs) in enumerate(groups.items()):
             if check and gi > 0:
                 flags |= eng.status_read()  # one status word per engine: collect the previous group's before the next resets it
-            host = torch.from_numpy(np.stack([prepped[i] for i in idxs]))
-            if pinned:
-                host = host.pin_memory()
+            if pinned:  # one copy per clip into a cached page-locked staging buffer (no np.stack, no fresh cudaHostAlloc)
+                host = self._staging(len(idxs), n)
+                view = host.numpy()
+                for j, i in enumerate(idxs):
+                    view[j] = prepped[i]
+            else:
+                host = torch.from_numpy(np.stack([prepped[i] for i in idxs]))
             e = None if eps is None else torch.cat([eps[i].reshape(1, -1, 256) for i in idxs])
+            pinned_done = False
             if self.cuda_graphs and len(idxs) <= self.cuda_graph_max_batch and not self.use_torchode:
                 out = self._run_group_graphed(eng, host, s, int(target_sampling_rate), int(timestep), e)
             else:
                 x = host.to(eng.device, non_blocking=True)
+                if pinned:
+                    self._stage_event.record(torch.cuda.current_stream(eng.device))
                 out = self._run_group(eng, x, s, int(target_sampling_rate), int(timestep),
                                       None if e is None else e.to(eng.device))
+                pinned_done = True
+            if pinned and not pinned_done:  # graph path: the staging buffer is read by the copy in front of the replay
+                self._stage_event.record(torch.cuda.current_stream(eng.device))
             for j, i in enumerate(idxs):
                 results[i] = out[j: j + 1]
         if check:

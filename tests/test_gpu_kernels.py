@@ -1229,3 +1229,20 @@ def test_generate_librosa_branch(cuda_device):
     m.upsampling_method = "sinc_best"
     with pytest.raises(ValueError):
         m.generate(wav, 16000, 48000, timestep=1, eps=eps)
+
+
+def test_generate_batch_pinned_staging_reuse(cuda_device, f32_model):
+    """pinned=True stages the clips in a cached page-locked buffer: refilling it for the next call must not disturb the
+    upload of the previous one, and the results must equal the pageable path bit for bit (eager and graph-replay sizes)."""
+    m, _ = f32_model
+    for B in (3, 12):  # <= 8: CUDA-graph path, > 8: eager path
+        clips = [[synth_speech(4000, 16000, seed=10 * r + i) * (0.3 + 0.05 * i) for i in range(B)] for r in range(3)]
+        eps = [[_eps_for(4000, 16000, seed=100 * r + i) for i in range(B)] for r in range(3)]
+        ref = [torch.cat(m.generate_batch(c, 16000, 48000, timestep=1, eps=e)).clone() for c, e in zip(clips, eps)]
+        got = []
+        for c, e in zip(clips, eps):  # back to back, no synchronisation in between
+            got.append(torch.cat(m.generate_batch(c, 16000, 48000, timestep=1, eps=e, pinned=True)).clone())
+        torch.cuda.synchronize()
+        for r in range(3):
+            assert torch.equal(ref[r], got[r])
+    assert len(m._stage_bufs) <= 4
