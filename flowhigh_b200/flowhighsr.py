@@ -203,6 +203,10 @@ class FlowHighSR(nn.Module):
         # Graphs are keyed by the exact input shape.  A service rarely sees a length twice, so a shape is captured only
         # when it comes back (`cuda_graph_min_hits`-th sighting; the eager run costs a third of a capture), and at most
         # `cuda_graph_cache_size` graphs (with their static buffers and private pools) are kept, least recently used out.
+        # generate_batch(out_host=...): groups of >= 2 x this many clips run as two sub-batches so that the D2H copy of the first
+        # overlaps the second.  OFF by default: at 64 x 10 s the two 32-clip halves cost 6 ms more than the 4 ms of PCIe
+        # time they hide (tools/e2e_ab.py: 313.3 vs 310.9 ms per step; resident 303.9) -- worth it only for slower links.
+        self.overlap_min_batch = 1 << 30
         self.cuda_graph_min_hits = 2
         self.cuda_graph_cache_size = 8
         self._graphs: "collections.OrderedDict[tuple, tuple]" = collections.OrderedDict()
@@ -335,6 +339,15 @@ class FlowHighSR(nn.Module):
         self._check_status(eng)
         return out
 
+    @staticmethod
+    def _clip_len(audio) -> int:
+        shp = tuple(audio.shape) if hasattr(audio, "shape") else np.asarray(audio).shape
+        if len(shp) == 2 and shp[0] == 1:
+            return int(shp[1])
+        if len(shp) != 1:  # the reference's squeeze(0) would silently keep [C, T] and fail later
+            raise ValueError(f"generate() takes mono audio, [T] or [1, T]; got shape {shp}")
+        return int(shp[0])
+
     def _prep_input(self, audio) -> np.ndarray:
         if isinstance(audio, torch.Tensor):
             audio = audio.detach().cpu().numpy()
@@ -358,24 +371,51 @@ class FlowHighSR(nn.Module):
     @torch.no_grad()
     @_on_model_device
     def generate_batch(self, audios: Sequence, sr: Union[int, Sequence[int]], target_sampling_rate=48000, timestep=1,
-                       eps: Optional[Sequence[torch.Tensor]] = None, pinned: bool = False) -> List[torch.Tensor]:
+                       eps: Optional[Sequence[torch.Tensor]] = None, pinned: bool = False,
+                       out_host: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         """Batched `generate`: every clip is processed exactly as the reference processes it alone
         (per-clip peak normalisation, attention, cutoff and output normalisation).
-        Clips sharing (sr, length) run as one batch through every kernel."""
+        Clips sharing (sr, length) run as one batch through every kernel.
+
+        `out_host` (optional, page-locked `[n_clips, T]` fp32): every result is ALSO copied there, asynchronously, on a
+        side stream; groups of >= 2 * `overlap_min_batch` clips (off by default, see __init__) run as two sub-batches so
+        that the device -> host copy of the first overlaps the kernels of the second (the output of a 64 x 10 s batch is
+        123 MB, ~5 ms of PCIe time).  The caller synchronises the device (or `self.copy_stream`) before reading `out_host`."""
         self._resample_method()
         eng = self._engine()
         eng.new_call()
         srs = [sr] * len(audios) if isinstance(sr, int) else list(sr)
-        prepped = [self._prep_input(a) for a in audios]
+        # grouping needs the lengths only; the per-clip preparation (int16 heuristic = a pass over the samples, fp32 copy)
+        # runs sub-batch by sub-batch below, so the host work of sub-batch k + 1 hides behind the kernels of sub-batch k
+        prepped: List[Optional[np.ndarray]] = [None] * len(audios)
         groups: Dict[tuple, List[int]] = {}
-        for i, (a, s) in enumerate(zip(prepped, srs)):
-            groups.setdefault((int(s), a.shape[0]), []).append(i)
+        for i, (a, s) in enumerate(zip(audios, srs)):
+            groups.setdefault((int(s), self._clip_len(a)), []).append(i)
+        if out_host is not None:
+            if not (out_host.is_pinned() and out_host.dtype == torch.float32 and out_host.dim() == 2
+                    and out_host.shape[0] >= len(audios) and out_host.is_contiguous()):
+                raise ValueError("out_host must be a contiguous page-locked fp32 tensor [n_clips, T]")
+            if getattr(self, "copy_stream", None) is None:
+                self.copy_stream = torch.cuda.Stream(eng.device)
+            # sub-batches: [(rate, length), clip indices]
+            work = []
+            for key, idxs in groups.items():
+                if len(idxs) >= 2 * self.overlap_min_batch:
+                    h = (len(idxs) + 1) // 2
+                    work += [(key, idxs[:h]), (key, idxs[h:])]
+                else:
+                    work.append((key, idxs))
+        else:
+            work = list(groups.items())
         results: List[Optional[torch.Tensor]] = [None] * len(audios)
         flags = 0
         check = self.overflow_check != "off" and eng.tc
-        for gi, ((s, n), idxs) in enumerate(groups.items()):
-            if check and gi > 0:
+        main = torch.cuda.current_stream(eng.device)
+        for gi, ((s, n), idxs) in enumerate(work):
+            if check and gi > 0 and out_host is None:
                 flags |= eng.status_read()  # one status word per engine: collect the previous group's before the next resets it
+            for i in idxs:
+                prepped[i] = self._prep_input(audios[i])
             if pinned:  # one copy per clip into a cached page-locked staging buffer (no np.stack, no fresh cudaHostAlloc)
                 host = self._staging(len(idxs), n)
                 view = host.numpy()
@@ -385,26 +425,44 @@ class FlowHighSR(nn.Module):
                 host = torch.from_numpy(np.stack([prepped[i] for i in idxs]))
             e = None if eps is None else torch.cat([eps[i].reshape(1, -1, 256) for i in idxs])
             pinned_done = False
-            if self.cuda_graphs and len(idxs) <= self.cuda_graph_max_batch and not self.use_torchode:
+            # with out_host the status word is reset once and accumulates over all sub-batches (no host sync in between)
+            reset = out_host is None or gi == 0
+            if self.cuda_graphs and len(idxs) <= self.cuda_graph_max_batch and not self.use_torchode and reset:
                 out = self._run_group_graphed(eng, host, s, int(target_sampling_rate), int(timestep), e)
             else:
                 x = host.to(eng.device, non_blocking=True)
                 if pinned:
-                    self._stage_event.record(torch.cuda.current_stream(eng.device))
+                    self._stage_event.record(main)
                 out = self._run_group(eng, x, s, int(target_sampling_rate), int(timestep),
-                                      None if e is None else e.to(eng.device))
+                                      None if e is None else e.to(eng.device), reset_status=reset)
                 pinned_done = True
             if pinned and not pinned_done:  # graph path: the staging buffer is read by the copy in front of the replay
-                self._stage_event.record(torch.cuda.current_stream(eng.device))
+                self._stage_event.record(main)
             for j, i in enumerate(idxs):
                 results[i] = out[j: j + 1]
+            if out_host is not None:
+                if out.shape[1] > out_host.shape[1]:
+                    raise ValueError(f"out_host rows hold {out_host.shape[1]} samples, a result has {out.shape[1]}")
+                done = torch.cuda.Event()
+                done.record(main)
+                self.copy_stream.wait_event(done)
+                with torch.cuda.stream(self.copy_stream):
+                    run0 = 0  # consecutive clip indices go out as one copy
+                    while run0 < len(idxs):
+                        run1 = run0 + 1
+                        while run1 < len(idxs) and idxs[run1] == idxs[run1 - 1] + 1:
+                            run1 += 1
+                        out_host[idxs[run0]: idxs[run0] + (run1 - run0), : out.shape[1]].copy_(out[run0:run1], non_blocking=True)
+                        run0 = run1
+                out.record_stream(self.copy_stream)
         if check:
             self._check_status(eng, flags | eng.status_read())
         return results  # type: ignore[return-value]
 
-    def _run_group(self, eng, x, sr, target_sr, timestep, eps_dev):
+    def _run_group(self, eng, x, sr, target_sr, timestep, eps_dev, reset_status: bool = True):
         """resample -> log-mel -> CFM -> vocoder -> post-processing for one batch of equal-length clips."""
-        eng.status_begin()
+        if reset_status:
+            eng.status_begin()
         cond = eng.resample_normalise(x, sr, target_sr, method=self._resample_method())
         cond_mel = eng.encode(cond)
         mel = eng.sample_mel(cond_mel, self._noise_like(cond_mel, eps_dev), steps=timestep,

@@ -1246,3 +1246,27 @@ def test_generate_batch_pinned_staging_reuse(cuda_device, f32_model):
         for r in range(3):
             assert torch.equal(ref[r], got[r])
     assert len(m._stage_bufs) <= 4
+
+
+def test_generate_batch_out_host_overlapped_sub_batches(cuda_device, f32_model):
+    """out_host: results also land in the caller's page-locked buffer; a group of >= 2 x overlap_min_batch clips runs as two
+    sub-batches (the copy of the first overlaps the second).  Per-clip results must not depend on the split; mixed rates
+    and ragged output lengths keep their clip order."""
+    m, _ = f32_model
+    old = m.overlap_min_batch
+    try:
+        m.overlap_min_batch = 3
+        clips = [synth_speech(4000, 16000, seed=i) * (0.3 + 0.05 * i) for i in range(7)] + [synth_speech(2000, 8000, seed=50)]
+        srs = [16000] * 7 + [8000]
+        eps = [_eps_for(4000, 16000, seed=i) for i in range(7)] + [_eps_for(2000, 8000, seed=50)]
+        ref = m.generate_batch(clips, srs, 48000, timestep=1, eps=eps)
+        out_host = torch.zeros((8, 12000), dtype=torch.float32).pin_memory()
+        got = m.generate_batch(clips, srs, 48000, timestep=1, eps=eps, pinned=True, out_host=out_host)
+        torch.cuda.synchronize()
+        for i in range(8):
+            assert torch.equal(ref[i], got[i])
+            assert torch.equal(out_host[i: i + 1, : ref[i].shape[1]], ref[i].cpu())
+        with pytest.raises(ValueError):
+            m.generate_batch(clips, srs, 48000, timestep=1, eps=eps, out_host=torch.zeros((8, 12000)))
+    finally:
+        m.overlap_min_batch = old
