@@ -22,7 +22,8 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 
 def lib_path() -> str:
-    return os.path.join(LIBDIR, LIBNAME)
+    # FLOWHIGH_B200_LIB: an explicitly built variant (A/B of compile-time options, tools/build_variant.sh); never rebuilt
+    return os.environ.get("FLOWHIGH_B200_LIB") or os.path.join(LIBDIR, LIBNAME)
 
 
 def _needs_build() -> bool:
@@ -35,6 +36,8 @@ def _needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    if os.environ.get("FLOWHIGH_B200_LIB"):
+        return lib_path()
     if not force and not _needs_build():
         return lib_path()
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

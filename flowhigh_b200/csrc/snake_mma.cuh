@@ -24,6 +24,9 @@
 #pragma once
 #include <cuda_fp16.h>
 #include "snake_worker.cuh"
+#ifndef FH_SNAKE_K8
+#define FH_SNAKE_K8 1  // edge terms of the down filter as K = 8 MMAs (0: all three terms K = 16; A/B builds only)
+#endif
 
 namespace fh {
 
@@ -60,6 +63,14 @@ __device__ __forceinline__ void sm_mma(float (&d)[4], uint32_t a0, uint32_t a1, 
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%12,%13};"
       : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
+}
+
+// K = 8 form (A fragment = one 16 x 8 half of a 16 x 16 fragment: registers {a0, a1} = k 0..7, {a2, a3} = k 8..15)
+__device__ __forceinline__ void sm_mma_k8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t b0, float c0, float c1, float c2,
+                                          float c3) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%8,%9,%10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a0), "r"(a1), "r"(b0), "f"(c0), "f"(c1), "f"(c2), "f"(c3));
 }
 
 // ---- pieces shared by the standalone kernel (snake_mma_cta) and the fused conv prologue (tc_conv.cu) ----------------
@@ -234,20 +245,33 @@ __device__ __forceinline__ void snake_mma_unit(const SnakeFrags& F, float* xw, u
       else U[0] = U[1] = 0u;  // up-samples below 2 q0 - 8 only meet zero weights
       if (j < NB) U[2] = snake2(dd[cur][1][0], dd[cur][1][1]), U[3] = snake2(dd[cur][1][2], dd[cur][1][3]);
       else U[2] = U[3] = 0u;
-      if (j >= 1) {  // last term of down block j - 1, then store it
+      // The 12-tap down filter reaches 5 up-samples back and 6 forward of an output block's own 16: of the previous
+      // block only the LAST 8 up-samples carry non-zero weights and of the next block only the FIRST 8, so those two
+      // terms are K = 8 MMAs on half of the A fragment (the other half of the Toeplitz fragment is identically zero).
+      if (j >= 1) {  // last term of down block j - 1 (first 8 up-samples of step j), then store it
         float (&yy)[4] = y[(j - 1) % 3];
+#if FH_SNAKE_K8
+        sm_mma_k8(yy, U[0], U[1], F.bd[2][0], yy[0], yy[1], yy[2], yy[3]);
+        if (SPLIT_F) sm_mma_k8(yy, U[0], U[1], F.bdl[2][0], yy[0], yy[1], yy[2], yy[3]);
+#else
         sm_mma(yy, U[0], U[1], U[2], U[3], F.bd[2][0], F.bd[2][1], yy[0], yy[1], yy[2], yy[3]);
         if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], F.bdl[2][0], F.bdl[2][1], yy[0], yy[1], yy[2], yy[3]);
+#endif
       }
       if (j >= 0 && j < NB) {
         float (&yy)[4] = y[j % 3];
         sm_mma(yy, U[0], U[1], U[2], U[3], F.bd[1][0], F.bd[1][1], yy[0], yy[1], yy[2], yy[3]);
         if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], F.bdl[1][0], F.bdl[1][1], yy[0], yy[1], yy[2], yy[3]);
       }
-      if (j + 1 < NB) {
+      if (j + 1 < NB) {  // first term of down block j + 1 (last 8 up-samples of step j)
         float (&yy)[4] = y[(j + 1) % 3];
+#if FH_SNAKE_K8
+        sm_mma_k8(yy, U[2], U[3], F.bd[0][1], hib, hib, hib, hib);
+        if (SPLIT_F) sm_mma_k8(yy, U[2], U[3], F.bdl[0][1], yy[0], yy[1], yy[2], yy[3]);
+#else
         sm_mma(yy, U[0], U[1], U[2], U[3], F.bd[0][0], F.bd[0][1], hib, hib, hib, hib);
         if (SPLIT_F) sm_mma(yy, U[0], U[1], U[2], U[3], F.bdl[0][0], F.bdl[0][1], yy[0], yy[1], yy[2], yy[3]);
+#endif
       }
       if (j >= 1) {
         // outputs q0 + 8 i + {2 q, 2 q + 1} of channel g, both halves: the accumulator tile is an 8 x 8 [seq][time]
