@@ -80,27 +80,34 @@ __device__ __forceinline__ void sm_mma_k8(float (&d)[4], uint32_t a0, uint32_t a
 // tap, so the branch sums (the DC gains) stay exact to ~2^-20.  On low-pass signals the response error of the rounded
 // filters drops from -66 dB (round-to-nearest) to -83 dB (CPU experiment).
 // s_taps[0, 12): up-filter taps (2 f), [12, 24): down-filter taps (f).
+// Four independent (filter, polyphase branch) chains: called by threads 0..3 with part = thread index (the serial form cost
+// ~3 us at the start of every launch -- a tenth of a B = 1 snake launch).
 template <bool SPLIT_F>
-__device__ __forceinline__ void snake_mma_make_taps(const float* __restrict__ filt, float* s_taps) {
-  for (int w = 0; w < 2; ++w) {
-    const float scale = w ? 1.0f : 2.0f;
-    for (int ph = 0; ph < 2; ++ph) {
-      unsigned done = 0;
-      float carry = 0.f;
-      for (int n = 0; n < 6; ++n) {
-        int best = -1;
-        float bm = -1.f;
-        for (int c = 0; c < 6; ++c) {
-          const float m = fabsf(__ldg(filt + 2 * c + ph));
-          if (!((done >> c) & 1u) && m > bm) bm = m, best = c;
-        }
-        done |= 1u << best;
-        const float v = scale * __ldg(filt + 2 * best + ph) + carry;
-        const float h = SPLIT_F ? v : __half2float(__float2half_rn(v));  // the tap-split mode keeps exact taps
-        carry = v - h;
-        s_taps[12 * w + 2 * best + ph] = h;
-      }
+__device__ __forceinline__ void snake_mma_make_taps(const float* __restrict__ filt, float* s_taps, int part) {
+  const int w = part >> 1, ph = part & 1;
+  const float scale = w ? 1.0f : 2.0f;
+  float f[6];
+#pragma unroll
+  for (int c = 0; c < 6; ++c) f[c] = __ldg(filt + 2 * c + ph);
+  unsigned done = 0;
+  float carry = 0.f;
+#pragma unroll
+  for (int n = 0; n < 6; ++n) {
+    int best = 0;
+    float bm = -1.f;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+      const float m = fabsf(f[c]);
+      if (!((done >> c) & 1u) && m > bm) bm = m, best = c;
     }
+    done |= 1u << best;
+    float fb = f[0];
+#pragma unroll
+    for (int c = 1; c < 6; ++c) fb = best == c ? f[c] : fb;
+    const float v = scale * fb + carry;
+    const float h = SPLIT_F ? v : __half2float(__float2half_rn(v));  // the tap-split mode keeps exact taps
+    carry = v - h;
+    s_taps[12 * w + 2 * best + ph] = h;
   }
 }
 
@@ -352,8 +359,8 @@ __device__ __forceinline__ void snake_mma_cta(const SnakeParams& S, unsigned cha
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     released[0] = released[1] = 0;
-    snake_mma_make_taps<SPLIT_F>(S.filt, s_taps);
   }
+  if (tid < 4) snake_mma_make_taps<SPLIT_F>(S.filt, s_taps, tid);
   // rows a clipped copy does not fill must hold finite values (they only ever meet zero filter weights)
   for (int i = tid; i < WBUF * kXB / 16; i += 32 * G::kWarps) reinterpret_cast<float4*>(smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

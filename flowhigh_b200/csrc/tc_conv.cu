@@ -904,8 +904,8 @@ __global__ void __launch_bounds__(kProThreads, 1) tc_conv_snakepro_kernel(const 
       mbar_init(xempty0 + 8 * i, 1);
     }
     fence_barrier_init();
-    fh::snake_mma_make_taps<false>(P.sn_filt, s_taps);
   }
+  if (threadIdx.x < 4) fh::snake_mma_make_taps<false>(P.sn_filt, s_taps, threadIdx.x);
   // window rows a clipped copy does not fill, and the 64 spare rows behind every A window, must hold finite values
   for (uint32_t i = threadIdx.x; i < (uint32_t)XD * xwin_bytes / 16u; i += kProThreads)
     reinterpret_cast<uint4*>(xring)[i] = make_uint4(0u, 0u, 0u, 0u);
