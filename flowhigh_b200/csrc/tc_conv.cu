@@ -60,6 +60,9 @@ struct TcParams {
   int tap_rel0[16];     // (offset of tap 0) - min_off of the phase
   int tap_step[16];     // offset(tap j+1) - offset(tap j) when the taps of a phase form an arithmetic sequence
   int fast_epi;         // epilogue_fast applies (bias table in shared memory behind the stages)
+  int res_async;        // residual rows through the per-warp cp.async ring at ring_off (epilogue_fast<.., RES_ASYNC>)
+  int ring_off;
+  int epi_warps;        // 8 or 16 (tc_conv_kernel<EW>)
   int v8;               // fp32 output / residual rows are 32-byte aligned: 256-bit epilogue accesses
   int tap_arith;        // all phases arithmetic: the MMA issuer strides descriptors instead of reading the offset table
   int tap_off[kMaxTapOff];
@@ -298,66 +301,191 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
 // costs ~45 instructions:  o = fma(acc, alpha, alpha * bias) [+ beta * residual] [+ previous output].
 // OUT16: 16-bit output rows (16 bytes per chunk row, no residual / accumulate) -- the snake that follows a first AMP
 // convolution reads them as MMA operands directly.
-template <bool HAS_RES, bool ACCUM, bool OUT16 = false>
+//
+// Round 2, second pass (ncu source page of the C = 24 / 48 launches at B = 64, profiles/r2_ncu_hbm_convs.txt):
+//  * two thirds of the ~125 instructions a group still cost were index arithmetic -- three integer divisions
+//    (group -> sub-tile, column) and 64-bit address chains rebuilt from scratch for every group.  A group is now a
+//    running (sub, g) pair (GroupIter) and every address is tile base + sub * sub_stride + g * group_stride.
+//  * the residual launches sat on the first FFMA that consumes the residual row (39 % of all samples): with one group of
+//    LDGs in flight per warp the residual stream is latency-bound (12 KB in flight per SM against ~1 us of DRAM latency).
+//    RES_ASYNC: the residual rows of the next kResDepth groups are in flight as cp.async (LDGSTS) copies into a private
+//    per-warp ring in shared memory, across tile boundaries; depth is set by cp.async.wait_group, not by the compiler's
+//    scoreboard assignment (a register ring two groups deep measured no gain in round 2).  A warp's 32 rows of one
+//    8-channel chunk are 1 KB of contiguous global memory: lane i copies 16-byte pieces i and i + 32, the owner of row r
+//    reads pieces 2 r and 2 r + 1 back after wait_group + __syncwarp.
+constexpr int kResLevelBytes = 2048;          // one group: 2 chunks x 32 rows x 32 bytes
+// RD residual groups in flight per epilogue warp, RD + 1 ring levels (the level read in step k - 1 is refilled in step k):
+// 3 with eight epilogue warps, 2 with twelve or sixteen (48 - 64 KB in flight per SM either way)
+__host__ __device__ constexpr int res_depth(int epi_warps) { return epi_warps > 8 ? 2 : 3; }
+__host__ __device__ constexpr int res_ring_bytes(int epi_warps) { return epi_warps * (res_depth(epi_warps) + 1) * kResLevelBytes; }
+
+struct GroupIter {  // (sub-tile, 16-column group) of the groups one epilogue warp owns, in consumption order
+  int sub, g;
+  __device__ __forceinline__ void start(int first, int gps) {
+    sub = 0;
+    g = first;
+    norm(gps);
+  }
+  __device__ __forceinline__ void norm(int gps) {
+    while (g >= gps) {
+      g -= gps;
+      ++sub;
+    }
+  }
+  __device__ __forceinline__ void step(int by, int gps) {
+    g += by;
+    norm(gps);
+  }
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// residual copy stream of one epilogue warp: runs kResDepth groups ahead of the consumer, across tiles
+struct ResStream {
+  int tile, sub, g;
+  int t0, t_lim, n_base;
+  long long base;  // element index of (row t0, chunk n_base / 8) of this tile's batch item
+  bool live;
+  __device__ __forceinline__ void open(const TcParams& P, int tile_, int tile_rows, int lane_grp, int half, int gps) {
+    tile = tile_;
+    live = tile < P.total_tiles;
+    if (!live) return;
+    const TileCoord tc = decode_tile(P, tile);
+    n_base = tc.nt * P.bn;
+    t0 = tc.mt * tile_rows + lane_grp * 32;
+    t_lim = min(P.L, tc.mt * tile_rows + P.m_valid);
+    base = (long long)tc.b * P.res_batch + (long long)t0 * 8 + (long long)(n_base >> 3) * P.res_chunk;
+    sub = 0;
+    g = half;
+    while (g >= gps) {
+      g -= gps;
+      ++sub;
+    }
+  }
+  // copies the rows of group (sub, g) into ring level `dst` (shared address) and commits one cp.async group
+  __device__ __forceinline__ void issue(const TcParams& P, uint32_t dst, int lane) {
+    if (live) {
+      const int n0 = n_base + (g << 4);
+      if (n0 < P.Cout) {
+        const float* src = (const float*)P.res + base + (long long)sub * (128 * 8) + (long long)(2 * g) * P.res_chunk;
+        const int row = t0 + sub * 128 + (lane >> 1);
+        const bool two = n0 + 8 < P.Cout;
+        if (row < t_lim) {
+          cp_async16(dst + lane * 16, src + lane * 4);
+          if (two) cp_async16(dst + 1024 + lane * 16, src + P.res_chunk + lane * 4);
+        }
+        if (row + 16 < t_lim) {
+          cp_async16(dst + 512 + lane * 16, src + 128 + lane * 4);
+          if (two) cp_async16(dst + 1536 + lane * 16, src + P.res_chunk + 128 + lane * 4);
+        }
+      }
+    }
+    cp_async_commit();
+  }
+  __device__ __forceinline__ void next(const TcParams& P, int tile_rows, int lane_grp, int half, int gstep, int gps) {
+    if (!live) return;
+    g += gstep;
+    while (g >= gps) {
+      g -= gps;
+      ++sub;
+    }
+    if (sub >= P.msub) open(P, tile + gridDim.x, tile_rows, lane_grp, half, gps);
+  }
+};
+
+template <bool HAS_RES, bool ACCUM, bool OUT16 = false, int RD = 0>
 __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                               int lane_grp, int half, int gstep, int lane, int tile_rows, uint32_t acc_cols,
-                                              const float* s_bias) {
+                                              const float* s_bias, uint32_t ring) {
   const int r = lane_grp * 32 + lane;
   int as = 0, aphase = 0;
-  const int groups_per_sub = P.bn >> 4;
-  const int n_groups_total = P.msub * groups_per_sub;
+  const int gps = P.bn >> 4;  // 16-column groups per sub-tile
+  const int msub = P.msub;
   const float alpha = P.alpha, beta = P.beta_res;
   const int bmask = P.bias ? ~0 : 0;  // no bias: every group reads the 16 zeros at the head of the table
   const float* resp = (const float*)P.res;
   float* outp = (float*)P.out;
   const float* accp = P.acc_src ? P.acc_src : (const float*)P.out;  // "previous output" rows of the accumulate form
+  const long long res_rs = (long long)P.P * P.res_row, out_rs = (long long)P.P * P.out_row;
+  const long long res_sub = 128 * res_rs, out_sub = 128 * out_rs;       // one sub-tile down
+  const long long res_grp = 2 * P.res_chunk, out_grp = 2 * P.out_chunk;  // one 16-column group to the right
+  const int fp16 = P.fp16;
   fh::Guard16 guard;
+  constexpr bool RES_ASYNC = RD > 0;
+  constexpr int kResDepth = RD, kResLevels = RD + 1;
+
+  ResStream rs;
+  int lvl = 0;  // ring level the consumer reads next
+  if (RES_ASYNC) {
+    ring += (uint32_t)((lane_grp * gstep + half) * (kResLevels * kResLevelBytes));
+    rs.open(P, blockIdx.x, tile_rows, lane_grp, half, gps);
+#pragma unroll
+    for (int d = 0; d < kResDepth; ++d) {
+      rs.issue(P, ring + d * kResLevelBytes, lane);
+      rs.next(P, tile_rows, lane_grp, half, gstep, gps);
+    }
+  }
+
   for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
     const TileCoord tc = decode_tile(P, tile);
     const int n_base = tc.nt * P.bn;
     const int t_base = tc.mt * tile_rows + r;
     const int t_lim = min(P.L, tc.mt * tile_rows + P.m_valid);  // rows this tile keeps
-    const long long res_b = (long long)tc.b * P.res_batch + (long long)tc.p * P.res_row;
-    const long long out_b = (long long)tc.b * P.out_batch + (long long)tc.p * P.out_row;
-    const long long res_rs = (long long)P.P * P.res_row, out_rs = (long long)P.P * P.out_row;
+    // element indices of (row t_base, chunk n_base / 8) in the residual and the output
+    const long long res_0 = (long long)tc.b * P.res_batch + (long long)tc.p * P.res_row + (long long)t_base * res_rs +
+                            (long long)(n_base >> 3) * P.res_chunk;
+    const long long out_0 = (long long)tc.b * P.out_batch + (long long)tc.p * P.out_row + (long long)t_base * out_rs +
+                            (long long)(n_base >> 3) * P.out_chunk;
     const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)as * acc_cols;
 
-    auto coords = [&](int gi, int& c0, int& t) {
-      const int sub = gi / groups_per_sub;
-      c0 = (gi - sub * groups_per_sub) << 4;
-      t = t_base + sub * 128;
-      return (uint32_t)(sub * P.bn + c0);
-    };
-    auto prefetch = [&](int gi, float (&rr)[16], float (&pp)[16]) {
-      if (gi >= n_groups_total) return;
-      int c0, t;
-      coords(gi, c0, t);
-      const int n0 = n_base + c0;
-      if (n0 >= P.Cout || t >= t_lim) return;
-      const bool two = n0 + 8 < P.Cout;
-      if (HAS_RES) {
-        const float* q = resp + res_b + (long long)t * res_rs + (long long)(n0 >> 3) * P.res_chunk;
+    // a group is live for this thread when its columns exist and its row is kept
+    auto live = [&](const GroupIter& it) { return n_base + (it.g << 4) < P.Cout && t_base + (it.sub << 7) < t_lim; };
+    auto prefetch = [&](const GroupIter& it, float (&rr)[16], float (&pp)[16]) {
+      if (it.sub >= msub || !live(it)) return;
+      const bool two = n_base + (it.g << 4) + 8 < P.Cout;
+      if (HAS_RES && !RES_ASYNC) {
+        const float* q = resp + res_0 + it.sub * res_sub + it.g * res_grp;
         ldg_v8(q, *reinterpret_cast<float(*)[8]>(&rr[0]));
         if (two) ldg_v8(q + P.res_chunk, *reinterpret_cast<float(*)[8]>(&rr[8]));
       }
       if (ACCUM) {
-        const float* q = accp + out_b + (long long)t * out_rs + (long long)(n0 >> 3) * P.out_chunk;
+        const float* q = accp + out_0 + it.sub * out_sub + it.g * out_grp;
         ldg_v8(q, *reinterpret_cast<float(*)[8]>(&pp[0]));
         if (two) ldg_v8(q + P.out_chunk, *reinterpret_cast<float(*)[8]>(&pp[8]));
       }
     };
-    auto issue_ld = [&](int gi, uint32_t (&v)[16]) {
-      if (gi >= n_groups_total) return;
-      int c0, t;
-      const uint32_t col = coords(gi, c0, t);
-      if (n_base + c0 < P.Cout) tmem_ld16(taddr + col, v);  // warp-uniform
+    auto issue_ld = [&](const GroupIter& it, uint32_t (&v)[16]) {
+      if (it.sub >= msub) return;
+      if (n_base + (it.g << 4) < P.Cout) tmem_ld16(taddr + (uint32_t)(it.sub * P.bn + (it.g << 4)), v);  // warp-uniform
     };
-    auto finish = [&](int gi, const uint32_t (&v)[16], const float (&rr)[16], const float (&pp)[16]) {
-      int c0, t;
-      coords(gi, c0, t);
-      const int n0 = n_base + c0;
-      if (n0 >= P.Cout || t >= t_lim) return;
-      const long long oidx = out_b + (long long)t * out_rs + (long long)(n0 >> 3) * P.out_chunk;
+    // RES_ASYNC: residual rows of the group consumed now -> registers; the freed level is refilled kResDepth groups ahead
+    auto ring_step = [&](float (&rr)[16]) {
+      cp_async_wait<(RD > 0 ? RD - 1 : 0)>();
+      __syncwarp();
+      const int fill = lvl == 0 ? kResLevels - 1 : lvl - 1;
+      rs.issue(P, ring + (uint32_t)fill * kResLevelBytes, lane);
+      rs.next(P, tile_rows, lane_grp, half, gstep, gps);
+      const uint32_t src = ring + (uint32_t)lvl * kResLevelBytes + (uint32_t)lane * 32u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t a = src + (uint32_t)(q >> 1) * 1024u + (uint32_t)(q & 1) * 16u;
+        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                     : "=f"(rr[4 * q]), "=f"(rr[4 * q + 1]), "=f"(rr[4 * q + 2]), "=f"(rr[4 * q + 3])
+                     : "r"(a));
+      }
+      lvl = lvl == kResLevels - 1 ? 0 : lvl + 1;
+    };
+    auto finish = [&](const GroupIter& it, const uint32_t (&v)[16], const float (&rr)[16], const float (&pp)[16]) {
+      if (!live(it)) return;
+      const int n0 = n_base + (it.g << 4);
+      const long long oidx = out_0 + it.sub * out_sub + it.g * out_grp;
       float* dst = outp + oidx;
 #pragma unroll
       for (int hh = 0; hh < 2; ++hh) {
@@ -376,8 +504,8 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
           uint32_t h[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            h[i] = fh::pack16(o[2 * i], o[2 * i + 1], P.fp16);
-            guard.see(h[i], P.fp16);
+            h[i] = fh::pack16(o[2 * i], o[2 * i + 1], fp16);
+            guard.see(h[i], fp16);
           }
           *reinterpret_cast<uint4*>((unsigned short*)P.out + oidx + (long long)hh * P.out_chunk) = *reinterpret_cast<uint4*>(h);
         } else {
@@ -388,20 +516,29 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
 
     uint32_t va[16], vb[16];
     float ra[16], rb[16], pa[16], pb[16];
-    prefetch(half, ra, pa);  // requested BEFORE waiting for the accumulator
+    GroupIter ia, ib;
+    ia.start(half, gps);
+    prefetch(ia, ra, pa);  // requested BEFORE waiting for the accumulator
     mbar_wait(tfull0 + 8 * as, aphase, P.err_flag, 4);
     tc_fence_after();
-    issue_ld(half, va);
-    for (int gi = half; gi < n_groups_total; gi += 2 * gstep) {
+    issue_ld(ia, va);
+    while (true) {
       tmem_ld_wait();
-      issue_ld(gi + gstep, vb);
-      prefetch(gi + gstep, rb, pb);
-      finish(gi, va, ra, pa);
-      if (gi + gstep >= n_groups_total) break;
+      ib = ia;
+      ib.step(gstep, gps);
+      issue_ld(ib, vb);
+      prefetch(ib, rb, pb);
+      if (RES_ASYNC) ring_step(ra);
+      finish(ia, va, ra, pa);
+      if (ib.sub >= msub) break;
       tmem_ld_wait();
-      issue_ld(gi + 2 * gstep, va);
-      prefetch(gi + 2 * gstep, ra, pa);
-      finish(gi + gstep, vb, rb, pb);
+      ia = ib;
+      ia.step(gstep, gps);
+      issue_ld(ia, va);
+      prefetch(ia, ra, pa);
+      if (RES_ASYNC) ring_step(rb);
+      finish(ib, vb, rb, pb);
+      if (ia.sub >= msub) break;
     }
     tmem_ld_wait();
     tc_fence_before();
@@ -415,7 +552,8 @@ __device__ __forceinline__ void epilogue_fast(const TcParams& P, uint32_t tmem_b
       aphase ^= 1;
     }
   }
-  if (OUT16) guard.commit(P.status, P.fp16);
+  if (RES_ASYNC) cp_async_wait<0>();
+  if (OUT16) guard.commit(P.status, fp16);
 }
 
 // MMA issuer role, shared by both kernels.  The ncu source page of the first version showed this warp, not the tensor
@@ -562,25 +700,30 @@ __device__ __forceinline__ void producer_role(const TcParams& P, uint32_t full0,
   }
 }
 
+template <int EW = 8>
 __device__ __forceinline__ void epilogue_dispatch(const TcParams& P, uint32_t tmem_base, uint32_t tfull0, uint32_t tempty0,
                                                   int lg, int hf, int lane, int tile_rows, uint32_t acc_cols,
-                                                  const float* s_bias, int gstep = 2) {
+                                                  const float* s_bias, int gstep = 2, uint32_t ring = 0) {
+#define FH_EPI(...) epilogue_fast<__VA_ARGS__>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias, ring)
+  constexpr int RD = res_depth(EW);
   if (P.fast_epi) {
-    if (P.out_is_16 && P.accumulate)  // last AMP branch of a stage: mean of the branches written as the next stage's operand
-      epilogue_fast<true, true, true>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
-    else if (P.out_is_16)
-      epilogue_fast<false, false, true>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
-    else if (P.res != nullptr && P.accumulate)
-      epilogue_fast<true, true>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
-    else if (P.res != nullptr)
-      epilogue_fast<true, false>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
-    else if (P.accumulate)
-      epilogue_fast<false, true>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
-    else
-      epilogue_fast<false, false>(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols, s_bias);
-  } else {
+    if (P.res_async && ring != 0) {  // residual rows through the cp.async ring (plain kernel, P == 1, fp32 residual)
+      if (P.out_is_16 && P.accumulate) FH_EPI(true, true, true, RD);
+      else if (P.accumulate) FH_EPI(true, true, false, RD);
+      else FH_EPI(true, false, false, RD);
+    } else if (P.out_is_16 && P.accumulate)  // last AMP branch of a stage: mean of the branches written as the next stage's operand
+      FH_EPI(true, true, true);
+    else if (P.out_is_16) FH_EPI(false, false, true);
+    else if (P.res != nullptr && P.accumulate) FH_EPI(true, true);
+    else if (P.res != nullptr) FH_EPI(true, false);
+    else if (P.accumulate) FH_EPI(false, true);
+    else FH_EPI(false, false);
+  } else if (EW == 8) {
     epilogue_role(P, tmem_base, tfull0, tempty0, lg, hf, gstep, lane, tile_rows, acc_cols);
+  } else {
+    __trap();  // the 16-epilogue-warp kernel is only planned with the specialised epilogue
   }
+#undef FH_EPI
 }
 
 // Per-CTA setup shared by the conv kernels: mbarriers, tap-offset table, alpha * bias table, zeroed partner windows.
@@ -622,7 +765,10 @@ __device__ __forceinline__ void conv_cta_setup(const TcParams& P, unsigned char*
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
+// EW = epilogue warps: 8 (default), or 16 for the HBM-bound narrow shapes whose epilogue -- two warps per scheduler,
+// each issuing once every ~5 cycles (ncu: issue-active 40 %, stalls = fixed-latency dependencies) -- paced the launch.
+template <int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1) tc_conv_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // [0,256): barriers; [256,260): tmem base; [512,768): tap offsets; stages from 1024; bias table behind the stages
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -632,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
   const uint32_t stage0 = smem_u32(smem + 1024);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  conv_cta_setup(P, smem, kThreads, 8);
+  conv_cta_setup(P, smem, 64 + 32 * EW, EW);
   if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
@@ -652,8 +798,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc_conv_kernel(const __grid_const
     mma_role(P, tmem_base, full0, empty0, tfull0, tempty0, stage0, a_chunk_bytes, s_off);
   } else {
     // ===================================================================== epilogue (warps 2..9)
-    epilogue_dispatch(P, tmem_base, tfull0, tempty0, warp & 3, (warp - 2) >> 2, lane, tile_rows, acc_cols,
-                      reinterpret_cast<const float*>(smem + 1024 + (size_t)P.stages * P.stage_bytes));
+    epilogue_dispatch<EW>(P, tmem_base, tfull0, tempty0, warp & 3, (warp - 2) >> 2, lane, tile_rows, acc_cols,
+                          reinterpret_cast<const float*>(smem + 1024 + (size_t)P.stages * P.stage_bytes), EW / 4,
+                      P.res_async ? smem_u32(smem + P.ring_off) : 0u);
   }
   tc_fence_before();
   __syncthreads();
@@ -1329,13 +1476,40 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
     *smem_out = p.xs_off + xd * p.xs_bytes + 16 * kProXMax;
     return 1;
   }
-  int stages = (budget - 1024 - tail) / p.stage_bytes;
+  // residual rows through the cp.async ring (epilogue_fast<.., RES_ASYNC>): the HBM-bound launches (<= 96 output channels in
+  // one N tile, fp32 residual rows of 8 floats, P == 1) whose residual stream was latency-bound; the ring (64 KB) comes
+  // out of the stage budget, which these launches do not need (a tile is 2 - 6 stages)
+  static int res_async_on = -1, ew_max_bn = -1, ew16_mmas = 64;
+  if (res_async_on < 0) {
+    const char* e = getenv("FH_TC_RES_ASYNC");
+    res_async_on = e ? atoi(e) : 1;
+    const char* w = getenv("FH_TC_EW_BN");  // widest N tile that runs with more than eight epilogue warps (0 = never)
+    ew_max_bn = w ? atoi(w) : 96;
+    const char* n = getenv("FH_TC_EW16_MMAS");  // sixteen epilogue warps up to this many MMAs per tile, twelve above
+    if (n) ew16_mmas = atoi(n);
+  }
+  const int res_async_max = res_async_on > 1 ? res_async_on : 192;
+  // Epilogue warps.  The narrow (HBM-bound) shapes were paced by their eight epilogue warps: two per scheduler, each
+  // issuing once every ~5 cycles (fixed-latency dependencies), so more warps are more throughput -- sixteen reach the
+  // HBM roofline on the k = 3 shapes.  With many MMAs per tile (k >= 7) sixteen starve the single MMA-issuing warp of
+  // issue slots on its scheduler (measured 20 - 30 % slower than twelve), so those run with twelve.
+  p.epi_warps = 8;
+  if (p.fast_epi && !two && a->bn <= ew_max_bn && budget_bytes == 0)
+    p.epi_warps = (a->ntaps * p.ci_pairs * p.msub <= ew16_mmas) ? 16 : 12;
+  int ring = 0;
+  if (res_async_on && p.fast_epi && !two && a->res != nullptr && !a->res_is_16 && a->P == 1 && a->res_row == 8 &&
+      a->Cout <= res_async_max && p.msub * (a->bn >> 4) >= (p.epi_warps + 3) / 4 && budget_bytes == 0 &&
+      (216 * 1024 - 1024 - tail - 128 - res_ring_bytes(p.epi_warps)) / p.stage_bytes >= 2)
+    ring = res_ring_bytes(p.epi_warps);
+  int stages = ((ring ? 216 * 1024 - 128 - ring : budget) - 1024 - tail) / p.stage_bytes;
   if (stages > kMaxStages) stages = kMaxStages;
   FH_REQUIRE(stages >= 2, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: stage of %d bytes does not fit twice", p.stage_bytes);
   p.stages = stages;
   p.empty_ring = stages;
   p.err_flag = fh::err_word();
-  *smem_out = 1024 + stages * p.stage_bytes + tail;
+  p.res_async = ring ? 1 : 0;
+  p.ring_off = (1024 + stages * p.stage_bytes + tail + 127) & ~127;
+  *smem_out = ring ? p.ring_off + ring : 1024 + stages * p.stage_bytes + tail;
   return FH_OK;
 }
 
@@ -1368,13 +1542,17 @@ extern "C" __attribute__((visibility("default"))) int fh_tc_conv(const fh_tc_con
     tc_conv2_kernel<<<g2, kThreads2, smem, (cudaStream_t)stream>>>(p);
     return fh::check_launch("fh_tc_conv(cta pair)");
   }
-  static int smem_set[64] = {0};
+  static int smem_set[64] = {0}, smem_set12[64] = {0}, smem_set16[64] = {0};
   {
-    cudaError_t e = fh::ensure_dyn_smem(tc_conv_kernel, smem, smem_set);
+    cudaError_t e = p.epi_warps == 16   ? fh::ensure_dyn_smem(tc_conv_kernel<16>, smem, smem_set16)
+                    : p.epi_warps == 12 ? fh::ensure_dyn_smem(tc_conv_kernel<12>, smem, smem_set12)
+                                        : fh::ensure_dyn_smem(tc_conv_kernel<8>, smem, smem_set);
     FH_REQUIRE(e == cudaSuccess, FH_ERR_CUDA, "fh_tc_conv: cannot opt in to %d bytes of smem: %s", smem,
                cudaGetErrorString(e));
   }
-  tc_conv_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
+  if (p.epi_warps == 16) tc_conv_kernel<16><<<grid, 64 + 32 * 16, smem, (cudaStream_t)stream>>>(p);
+  else if (p.epi_warps == 12) tc_conv_kernel<12><<<grid, 64 + 32 * 12, smem, (cudaStream_t)stream>>>(p);
+  else tc_conv_kernel<8><<<grid, kThreads, smem, (cudaStream_t)stream>>>(p);
   return fh::check_launch("fh_tc_conv");
 }
 

@@ -1106,6 +1106,60 @@ def test_tc_conv_pair_matches_single(cuda_device, B, Ci, Co, L, k, d):
     assert float((got - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("B,C,L,k,d", [(4, 24, 80037, 3, 1), (4, 24, 80037, 11, 1), (3, 48, 60005, 7, 3), (2, 96, 50000, 3, 5),
+                                       (2, 192, 30001, 3, 1), (2, 96, 1000, 7, 1)])
+def test_tc_conv_residual_ring_persistent(cuda_device, B, C, L, k, d):
+    """The narrow (HBM-bound) shapes of the vocoder at sizes where every persistent CTA walks SEVERAL tiles: residual
+    rows through the per-warp cp.async ring that runs ahead across tile boundaries (epilogue_fast<.., RD>), twelve or
+    sixteen epilogue warps, partial last tile, odd chunk count (24 channels), two N tiles (192 channels).  Three
+    epilogue forms against torch on the same fp16-rounded operands: residual, residual + accumulate (fp32 rows),
+    residual + accumulate from acc_src into 16-bit rows (the last AMP branch of a stage).  Rows outside [0, L) untouched."""
+    eng, sd, vcfg, g = engine("voc_resblock1_snakebeta", "fp16")
+    torch.manual_seed(C + L + k)
+    w = torch.randn(C, C, k) / (C * k) ** 0.5
+    b = torch.randn(C) * 0.1
+    rec = eng._mk_tc(packing.conv1d_taps(w.cuda(), b.cuda(), d), cin_pad=C, cout_pad=C, two_cta=False)
+    A, cs, bs = eng._cbuf("rr_A", B, C, L, eng.h16)
+    O, ocs, obs = eng._cbuf("rr_O", B, C, L, torch.float32)
+    R, _, _ = eng._cbuf("rr_R", B, C, L, torch.float32)
+    S, _, _ = eng._cbuf("rr_S", B, C, L, torch.float32)
+    O16, hcs, hbs = eng._cbuf("rr_O16", B, C, L, eng.h16)
+    x = torch.randn(B, C, L).cuda()
+    A.zero_()
+    A[: B * bs].view(B, C // 8, cs // 8, 8)[:, :, HALO:HALO + L, :] = x.view(B, C // 8, 8, L).permute(0, 1, 3, 2).half()
+
+    def fill(buf, stride_b, stride_c):  # random rows [0, L), zeros elsewhere
+        buf.zero_()
+        v = torch.randn(B, C, L).cuda()
+        buf[: B * stride_b].view(B, C // 8, stride_c // 8, 8)[:, :, HALO:HALO + L, :] = v.view(B, C // 8, 8, L).permute(0, 1, 3, 2)
+        return v
+
+    def rows(buf, stride_b, stride_c):
+        full = buf[: B * stride_b].view(B, C // 8, stride_c // 8, 8)
+        assert float(full[:, :, :HALO].abs().max()) == 0 and float(full[:, :, HALO + L:].abs().max()) == 0, "halo rows written"
+        return full[:, :, HALO:HALO + L].permute(0, 1, 3, 2).reshape(B, C, L).float()
+
+    conv = F.conv1d(x.half().float(), w.half().float().cuda(), b.cuda(), dilation=d, padding=(k * d - d) // 2)
+    tol = 2e-3 * max(1.0, float(conv.abs().max()))
+    o = HALO * 8
+    r = fill(R, obs, ocs)
+    O.zero_()
+    eng._tc_conv(rec, A, bs, cs, HALO, O[o:], (obs, ocs, 8), 0, B, L, res=R[o:], res_strides=(obs, ocs, 8), beta=1.0)
+    torch.cuda.synchronize()
+    assert float((rows(O, obs, ocs) - (conv + r)).abs().max()) <= tol
+    prev = fill(O, obs, ocs)  # accumulate into the fp32 output itself
+    eng._tc_conv(rec, A, bs, cs, HALO, O[o:], (obs, ocs, 8), 0, B, L, res=R[o:], res_strides=(obs, ocs, 8), beta=1.0, accumulate=1)
+    torch.cuda.synchronize()
+    assert float((rows(O, obs, ocs) - (conv + r + prev)).abs().max()) <= tol
+    acc = fill(S, obs, ocs)  # accumulate from acc_src, 16-bit rows out
+    O16.zero_()
+    eng._tc_conv(rec, A, bs, cs, HALO, O16[o:], (hbs, hcs, 8), 1, B, L, res=R[o:], res_strides=(obs, ocs, 8), beta=1.0,
+                 accumulate=1, acc_src=S[o:], alpha=1.0 / 3)
+    torch.cuda.synchronize()
+    want = conv / 3 + r + acc
+    assert float((rows(O16, hbs, hcs) - want).abs().max()) <= 4e-3 * max(1.0, float(want.abs().max()))
+
+
 # ------------------------------------------------------------------ SURVEY 8f rows 3 / 4: soxr_hq branch, torchode branch
 def test_rk_helper_kernels(cuda_device):
     """fh_rk_lincomb_f32 / fh_rk_scaled_sumsq_f32 against torch (stage combination, controller error norm)."""
