@@ -66,10 +66,10 @@ __device__ __forceinline__ void sw_mbar_wait(uint32_t bar, uint32_t parity) {
   while (!ok) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(2000u)  // suspend-time hint (ns): a waiting warp sleeps instead of taking issue slots
         : "memory");
     if (!ok && clock64() - t0 > 4000000000LL) __trap();
   }

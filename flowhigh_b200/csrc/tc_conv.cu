@@ -143,6 +143,25 @@ __device__ __forceinline__ void load_res16(const TcParams& P, long long rbase, i
   }
 }
 
+struct GroupIter {  // (sub-tile, 16-column group) of the groups one epilogue warp owns, in consumption order
+  int sub, g;
+  __device__ __forceinline__ void start(int first, int gps) {
+    sub = 0;
+    g = first;
+    norm(gps);
+  }
+  __device__ __forceinline__ void norm(int gps) {
+    while (g >= gps) {
+      g -= gps;
+      ++sub;
+    }
+  }
+  __device__ __forceinline__ void step(int by, int gps) {
+    g += by;
+    norm(gps);
+  }
+};
+
 // Epilogue role, shared by both kernels.  `gstep` warps share one TMEM lane group (a warp may only touch lanes
 // 32*(warp%4)..+31) and split the 16-column groups of a tile round-robin (`half` = index within the share).
 // Per warp the groups are software-pipelined: tcgen05.ld and the residual loads of the next group are in flight
@@ -153,7 +172,6 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
   const int r = lane_grp * 32 + lane;
   int as = 0, aphase = 0;
   const int groups_per_sub = P.bn >> 4;
-  const int n_groups_total = P.msub * groups_per_sub;
   const bool use_res = P.res != nullptr && !P.geglu;
   fh::Guard16 guard;
   for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -165,27 +183,20 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
     const long long out_b = (long long)tc.b * P.out_batch;
     const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)as * acc_cols;
 
-    auto group_coords = [&](int gi, int& sub, int& c0, int& t) {
-      sub = gi / groups_per_sub;
-      c0 = (gi - sub * groups_per_sub) << 4;
-      t = t_base + sub * 128;
+    // a group is a running (sub-tile, 16-column group) pair: no division per group (see epilogue_fast)
+    auto fetch_res = [&](const GroupIter& it, float (&rr)[16]) {
+      if (!use_res || it.sub >= P.msub) return;
+      const int t = t_base + (it.sub << 7);
+      load_res16(P, res_b + ((long long)t * P.P + tc.p) * P.res_row, n_base + (it.g << 4), t < t_lim, rr);
     };
-    auto fetch_res = [&](int gi, float (&rr)[16]) {
-      if (!use_res || gi >= n_groups_total) return;
-      int sub, c0, t;
-      group_coords(gi, sub, c0, t);
-      load_res16(P, res_b + ((long long)t * P.P + tc.p) * P.res_row, n_base + c0, t < t_lim, rr);
+    auto issue_ld = [&](const GroupIter& it, uint32_t (&v)[16]) {
+      if (it.sub >= P.msub) return;
+      const int c0 = it.g << 4;
+      if (n_base + c0 < P.Cout) tmem_ld16(taddr + (uint32_t)(it.sub * P.bn + c0), v);  // warp-uniform
     };
-    auto issue_ld = [&](int gi, uint32_t (&v)[16]) {
-      if (gi >= n_groups_total) return;
-      int sub, c0, t;
-      group_coords(gi, sub, c0, t);
-      if (n_base + c0 < P.Cout) tmem_ld16(taddr + (uint32_t)(sub * P.bn + c0), v);  // warp-uniform
-    };
-    auto finish = [&](int gi, const uint32_t (&v)[16], const float (&rr)[16]) {
-      int sub, c0, t;
-      group_coords(gi, sub, c0, t);
-      if (n_base + c0 >= P.Cout || t >= t_lim) return;
+    auto finish = [&](const GroupIter& it, const uint32_t (&v)[16], const float (&rr)[16]) {
+      const int c0 = it.g << 4, t = t_base + (it.sub << 7);
+      if (it.sub >= P.msub || n_base + c0 >= P.Cout || t >= t_lim) return;
       const long long orow = (long long)t * P.P + tc.p;
       if (P.geglu) {
         // columns (2i, 2i+1) = (x_i, gate_i) -> gelu(gate) * x ; 16 columns -> one 8-channel chunk
@@ -263,20 +274,26 @@ __device__ __forceinline__ void epilogue_role(const TcParams& P, uint32_t tmem_b
 
     uint32_t va[16], vb[16];
     float ra[16], rb[16];
-    fetch_res(half, ra);  // residual of the first group is requested BEFORE waiting for the accumulator
+    GroupIter ia, ib;
+    ia.start(half, groups_per_sub);
+    fetch_res(ia, ra);  // residual of the first group is requested BEFORE waiting for the accumulator
     mbar_wait(tfull0 + 8 * as, aphase, P.err_flag, 4);
     tc_fence_after();
-    issue_ld(half, va);
-    for (int gi = half; gi < n_groups_total; gi += 2 * gstep) {
+    issue_ld(ia, va);
+    while (ia.sub < P.msub) {
       tmem_ld_wait();
-      issue_ld(gi + gstep, vb);
-      fetch_res(gi + gstep, rb);
-      finish(gi, va, ra);
-      if (gi + gstep >= n_groups_total) break;
+      ib = ia;
+      ib.step(gstep, groups_per_sub);
+      issue_ld(ib, vb);
+      fetch_res(ib, rb);
+      finish(ia, va, ra);
+      if (ib.sub >= P.msub) break;
       tmem_ld_wait();
-      issue_ld(gi + 2 * gstep, va);
-      fetch_res(gi + 2 * gstep, ra);
-      finish(gi + gstep, vb, rb);
+      ia = ib;
+      ia.step(gstep, groups_per_sub);
+      issue_ld(ia, va);
+      fetch_res(ia, ra);
+      finish(ib, vb, rb);
     }
     // all TMEM reads of this warp are complete (wait::ld above) -> release the accumulator
     tmem_ld_wait();
@@ -318,25 +335,6 @@ constexpr int kResLevelBytes = 2048;          // one group: 2 chunks x 32 rows x
 // 3 with eight epilogue warps, 2 with twelve or sixteen (48 - 64 KB in flight per SM either way)
 __host__ __device__ constexpr int res_depth(int epi_warps) { return epi_warps > 8 ? 2 : 3; }
 __host__ __device__ constexpr int res_ring_bytes(int epi_warps) { return epi_warps * (res_depth(epi_warps) + 1) * kResLevelBytes; }
-
-struct GroupIter {  // (sub-tile, 16-column group) of the groups one epilogue warp owns, in consumption order
-  int sub, g;
-  __device__ __forceinline__ void start(int first, int gps) {
-    sub = 0;
-    g = first;
-    norm(gps);
-  }
-  __device__ __forceinline__ void norm(int gps) {
-    while (g >= gps) {
-      g -= gps;
-      ++sub;
-    }
-  }
-  __device__ __forceinline__ void step(int by, int gps) {
-    g += by;
-    norm(gps);
-  }
-};
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
