@@ -507,12 +507,14 @@ def main():
         tot_ms = sum(v["ms"] for v in breakdown.values())
         achieved = tc_fl / (tc_ms / 1000.0) / 1e12 if tc_ms > 0 else 0.0
         traffic = None  # DRAM bytes per launch from the committed ncu capture of this same workload (B = 64)
-        tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic_b64.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_dram_traffic_b64.json")  # the final build's capture (tools/evidence_r2.sh)
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "r1_dram_traffic_b64.json")
         if B == BATCH and os.path.exists(tpath):
             tj = json.load(open(tpath))["tc_conv"]
             traffic = (tj["dram_read_bytes"] + tj["dram_write_bytes"]) / tj["launches"]
         tc_by = sum(v["bytes"] for v in tc.values())
-        roofline = {"kernel": "tc_conv_kernel (tcgen05 implicit-GEMM conv, all launches of one step)", "bound": "tensor",
+        roofline = {"kernel": "tc_conv_kernel<8|12|16> + tc_conv2_kernel (tcgen05 implicit-GEMM conv, all launches of one step)", "bound": "tensor",
                     "achieved": achieved, "peak": tf_peak, "unit": "TFLOP/s", "frac": achieved / tf_peak,
                     "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write, B=64 capture)",
                     "algorithmic_bytes_per_launch": tc_by / max(tc_n, 1),
@@ -532,7 +534,7 @@ def main():
                               "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "traffic": straffic,
                               "algorithmic_bytes_per_launch": sn["bytes"] / sn["launches"], "launches_per_step": sn["launches"],
                               "avg_launch_ms": sn["ms"] / sn["launches"], "share_of_step": sn["ms"] / tot_ms if tot_ms else None,
-                              "note": "fp32 rows in (fp16 rows behind the first conv of an AMP unit), fp16 rows out; ncu: profiles/r1_ncu_snake.txt"}
+                              "note": "fp32 rows in (fp16 rows behind the first conv of an AMP unit), fp16 rows out; ncu: profiles/r2_ncu_snake.txt"}
         # every other kernel class of the path: HBM roofline from its algorithmic bytes (attention: tensor roofline)
         roofline_stages = {}
         for k, v in breakdown.items():
