@@ -207,6 +207,7 @@ class FlowHighSR(nn.Module):
         # overlaps the second.  OFF by default: at 64 x 10 s the two 32-clip halves cost 6 ms more than the 4 ms of PCIe
         # time they hide (tools/e2e_ab.py: 313.3 vs 310.9 ms per step; resident 303.9) -- worth it only for slower links.
         self.overlap_min_batch = 1 << 30
+        self.readback_chunk = 16  # generate_batch(out_host=...): post-processing + read-back in chunks of this many clips (0: off)
         self.cuda_graph_min_hits = 2
         self.cuda_graph_cache_size = 8
         self._graphs: "collections.OrderedDict[tuple, tuple]" = collections.OrderedDict()
@@ -414,53 +415,83 @@ class FlowHighSR(nn.Module):
         for gi, ((s, n), idxs) in enumerate(work):
             if check and gi > 0 and out_host is None:
                 flags |= eng.status_read()  # one status word per engine: collect the previous group's before the next resets it
-            for i in idxs:
-                prepped[i] = self._prep_input(audios[i])
-            if pinned:  # one copy per clip into a cached page-locked staging buffer (no np.stack, no fresh cudaHostAlloc)
-                host = self._staging(len(idxs), n)
-                view = host.numpy()
-                for j, i in enumerate(idxs):
-                    view[j] = prepped[i]
-            else:
-                host = torch.from_numpy(np.stack([prepped[i] for i in idxs]))
+            graphed = self.cuda_graphs and len(idxs) <= self.cuda_graph_max_batch and not self.use_torchode
+            # Clips that already sit in page-locked fp32 memory go to the device directly, one asynchronous copy each: no
+            # staging copy, and no pass over the samples for the int16 heuristic (flowhighsr.py:62-63) -- dividing by
+            # 32768 is an exact power-of-two scaling that the peak normalisation behind the resampler cancels bit for bit
+            # (asserted by test_generate_batch_direct_pinned_and_chunked_readback).
+            direct = pinned and not graphed and all(self._is_direct(audios[i]) for i in idxs)
             e = None if eps is None else torch.cat([eps[i].reshape(1, -1, 256) for i in idxs])
             pinned_done = False
             # with out_host the status word is reset once and accumulates over all sub-batches (no host sync in between)
             reset = out_host is None or gi == 0
-            if self.cuda_graphs and len(idxs) <= self.cuda_graph_max_batch and not self.use_torchode and reset:
-                out = self._run_group_graphed(eng, host, s, int(target_sampling_rate), int(timestep), e)
+            if direct:
+                x = torch.empty((len(idxs), n), dtype=torch.float32, device=eng.device)
+                for j, i in enumerate(idxs):
+                    x[j].copy_(audios[i].reshape(-1), non_blocking=True)
+                host = None
             else:
-                x = host.to(eng.device, non_blocking=True)
-                if pinned:
-                    self._stage_event.record(main)
-                out = self._run_group(eng, x, s, int(target_sampling_rate), int(timestep),
-                                      None if e is None else e.to(eng.device), reset_status=reset)
-                pinned_done = True
-            if pinned and not pinned_done:  # graph path: the staging buffer is read by the copy in front of the replay
-                self._stage_event.record(main)
-            for j, i in enumerate(idxs):
-                results[i] = out[j: j + 1]
-            if out_host is not None:
-                if out.shape[1] > out_host.shape[1]:
-                    raise ValueError(f"out_host rows hold {out_host.shape[1]} samples, a result has {out.shape[1]}")
+                for i in idxs:
+                    prepped[i] = self._prep_input(audios[i])
+                if pinned:  # one copy per clip into a cached page-locked staging buffer (no np.stack, no fresh cudaHostAlloc)
+                    host = self._staging(len(idxs), n)
+                    view = host.numpy()
+                    for j, i in enumerate(idxs):
+                        view[j] = prepped[i]
+                else:
+                    host = torch.from_numpy(np.stack([prepped[i] for i in idxs]))
+
+            def read_back(first, chunk):  # results of clips idxs[first : first + len(chunk)] -> out_host, on the copy stream
+                if chunk.shape[1] > out_host.shape[1]:
+                    raise ValueError(f"out_host rows hold {out_host.shape[1]} samples, a result has {chunk.shape[1]}")
                 done = torch.cuda.Event()
                 done.record(main)
                 self.copy_stream.wait_event(done)
+                sub = idxs[first: first + chunk.shape[0]]
                 with torch.cuda.stream(self.copy_stream):
                     run0 = 0  # consecutive clip indices go out as one copy
-                    while run0 < len(idxs):
+                    while run0 < len(sub):
                         run1 = run0 + 1
-                        while run1 < len(idxs) and idxs[run1] == idxs[run1 - 1] + 1:
+                        while run1 < len(sub) and sub[run1] == sub[run1 - 1] + 1:
                             run1 += 1
-                        out_host[idxs[run0]: idxs[run0] + (run1 - run0), : out.shape[1]].copy_(out[run0:run1], non_blocking=True)
+                        out_host[sub[run0]: sub[run0] + (run1 - run0), : chunk.shape[1]].copy_(chunk[run0:run1], non_blocking=True)
                         run0 = run1
-                out.record_stream(self.copy_stream)
+                chunk.record_stream(self.copy_stream)
+
+            chunked = False
+            if graphed and reset:
+                outs = [self._run_group_graphed(eng, host, s, int(target_sampling_rate), int(timestep), e)]
+            else:
+                if not direct:
+                    x = host.to(eng.device, non_blocking=True)
+                    if pinned:
+                        self._stage_event.record(main)
+                # large batches with a host destination: post-processing in chunks of `readback_chunk` clips, so that the
+                # device -> host copy of a chunk overlaps the post-processing of the next (only the last chunk's copy is exposed)
+                chunked = out_host is not None and self.readback_chunk and len(idxs) >= 2 * self.readback_chunk
+                outs = self._run_group(eng, x, s, int(target_sampling_rate), int(timestep),
+                                       None if e is None else e.to(eng.device), reset_status=reset,
+                                       pp_chunk=self.readback_chunk if chunked else 0, on_chunk=read_back if chunked else None)
+                if not chunked:
+                    outs = [outs]
+                pinned_done = True
+            if pinned and not pinned_done:  # graph path: the staging buffer is read by the copy in front of the replay
+                self._stage_event.record(main)
+            j0 = 0
+            for chunk in outs:
+                for j in range(chunk.shape[0]):
+                    results[idxs[j0 + j]] = chunk[j: j + 1]
+                if out_host is not None and not chunked:
+                    read_back(j0, chunk)
+                j0 += chunk.shape[0]
         if check:
             self._check_status(eng, flags | eng.status_read())
         return results  # type: ignore[return-value]
 
-    def _run_group(self, eng, x, sr, target_sr, timestep, eps_dev, reset_status: bool = True):
-        """resample -> log-mel -> CFM -> vocoder -> post-processing for one batch of equal-length clips."""
+    def _run_group(self, eng, x, sr, target_sr, timestep, eps_dev, reset_status: bool = True, pp_chunk: int = 0, on_chunk=None):
+        """resample -> log-mel -> CFM -> vocoder -> post-processing for one batch of equal-length clips.
+        `pp_chunk` > 0: the post-processing (per clip anyway) runs in chunks of that many clips, `on_chunk(first, out)` is
+        called after each (the caller starts its device -> host copy there), and the list of chunk results is returned."""
         if reset_status:
             eng.status_begin()
         cond = eng.resample_normalise(x, sr, target_sr, method=self._resample_method())
@@ -468,9 +499,25 @@ class FlowHighSR(nn.Module):
         mel = eng.sample_mel(cond_mel, self._noise_like(cond_mel, eps_dev), steps=timestep,
                              ode_method=self.odeint_kwargs["method"], cfm_method=self.cfm_method, sigma=float(self.sigma),
                              adaptive=self._adaptive())
-        out = eng.postprocess(eng.vocoder(mel), cond)
-        eng.status_end()
-        return out
+        wave = eng.vocoder(mel)
+        if pp_chunk <= 0:
+            out = eng.postprocess(wave, cond)
+            eng.status_end()
+            return out
+        outs = []
+        for a in range(0, wave.shape[0], pp_chunk):
+            o = eng.postprocess(wave[a: a + pp_chunk], cond[a: a + pp_chunk])
+            if a + pp_chunk >= wave.shape[0]:
+                eng.status_end()
+            if on_chunk is not None:
+                on_chunk(a, o)
+            outs.append(o)
+        return outs
+
+    @staticmethod
+    def _is_direct(a) -> bool:
+        return (isinstance(a, torch.Tensor) and a.dtype == torch.float32 and a.device.type == "cpu" and a.is_pinned()
+                and a.is_contiguous() and (a.dim() == 1 or (a.dim() == 2 and a.shape[0] == 1)))
 
     def _check_status(self, eng, flags: int = None):
         """16-bit paths: raises when a tensor-core operand left the fp16 range (saturated at +-65504) or was inf / NaN --

@@ -1324,3 +1324,35 @@ def test_generate_batch_out_host_overlapped_sub_batches(cuda_device, f32_model):
             m.generate_batch(clips, srs, 48000, timestep=1, eps=eps, out_host=torch.zeros((8, 12000)))
     finally:
         m.overlap_min_batch = old
+
+
+def test_generate_batch_direct_pinned_and_chunked_readback(cuda_device, f32_model):
+    """generate_batch(pinned=True, out_host=...) with clips that already sit in page-locked fp32 tensors: uploaded directly
+    (no staging copy, no int16-heuristic pass over the samples) and, for groups of >= 2 x readback_chunk clips,
+    post-processed + read back in chunks.  Bit-identical to the plain path -- including a clip in int16 RANGE
+    (max > 1: the reference divides by 32768, flowhighsr.py:62-63; the peak normalisation cancels that power of two)."""
+    m, _ = f32_model
+    old_chunk, old_graphs = m.readback_chunk, m.cuda_graphs
+    try:
+        m.readback_chunk, m.cuda_graphs = 2, False
+        n = 7
+        clips = [synth_speech(4000, 16000, seed=10 + i) * (0.3 + 0.05 * i) for i in range(n)]
+        clips[3] = clips[3] * 20000.0  # int16-range samples in a float array
+        eps = [_eps_for(4000, 16000, seed=10 + i) for i in range(n)]
+        ref = m.generate_batch(clips, 16000, 48000, timestep=1, eps=eps)
+        host = torch.from_numpy(np.stack(clips)).pin_memory()
+        out_host = torch.zeros((n, 12000), dtype=torch.float32).pin_memory()
+        got = m.generate_batch(list(host), 16000, 48000, timestep=1, eps=eps, pinned=True, out_host=out_host)
+        torch.cuda.synchronize()
+        for i in range(n):
+            assert torch.equal(ref[i], got[i]), i
+            assert torch.equal(out_host[i: i + 1, : ref[i].shape[1]], ref[i].cpu()), i
+        # [1, T] rows and a non-pinned clip in the same group: falls back to the staging path, same result
+        mixed = [host[i: i + 1] for i in range(n - 1)] + [torch.from_numpy(clips[-1])]
+        out_host.zero_()
+        got = m.generate_batch(mixed, 16000, 48000, timestep=1, eps=eps, pinned=True, out_host=out_host)
+        torch.cuda.synchronize()
+        for i in range(n):
+            assert torch.equal(ref[i], got[i]) and torch.equal(out_host[i: i + 1, : ref[i].shape[1]], ref[i].cpu())
+    finally:
+        m.readback_chunk, m.cuda_graphs = old_chunk, old_graphs
