@@ -16,7 +16,8 @@
 // copy per stage.  Accumulators live in TMEM (2 x bn columns, double buffered across tiles);
 // the epilogue (bias, alpha, residual, accumulate, GEGLU, bf16/fp32, chunked or row-major output)
 // reads them with tcgen05.ld.  Warp roles: warp 0 = bulk-copy producer, warp 1 = MMA issuer +
-// TMEM allocator, warps 2..5 = epilogue.  Persistent CTAs, static tile striding.
+// TMEM allocator, warps 2.. = epilogue (8 by default; 12 / 16 for the narrow HBM-bound shapes, whose
+// residual rows additionally stream through a per-warp cp.async ring).  Persistent CTAs, static tile striding.
 #include <stdlib.h>
 #include "common.cuh"
 #include "snake_worker.cuh"
