@@ -49,6 +49,7 @@ struct TcParams {
   int m_tiles, n_tiles, total_tiles;
   int ci_pairs;        // ceil(Cin / 16)
   int ci_odd;          // Cin % 16 == 8: the last pair has one real 8-channel chunk; its partner is a zeroed smem window
+  int tap_pair;        // ci_odd: the odd chunk's taps are issued two per MMA (K halves = two taps; mma_role)
   int tg, n_groups;    // taps per smem stage, groups per ci-pair
   int kc;              // ci-pairs per smem stage (> 1 only when a stage holds all taps: few-tap convs, Linear)
   int msub;            // 128-row sub-tiles per CTA tile (1, 2, 4 or 8): B operand reuse + epilogue MLP
@@ -618,7 +619,31 @@ __device__ __forceinline__ void mma_role(const TcParams& P, uint32_t tmem_base, 
           uint32_t b_lo = b_lbo | (sa_u + (uint32_t)kc * a_slot_u);  // weights sit behind the kc activation slots
           uint32_t a_base_lo = a_lbo | sa_u;
           for (int c = 0; c < nkc; ++c) {
-            if (P.tap_arith) {
+            if (P.tap_pair && cp + c == ci_pairs - 1) {
+              // Odd chunk count (24 channels): the last ci-pair has ONE real 8-channel chunk.  Instead of K = 16 MMAs whose
+              // second K half is a zeroed partner window against zero weights, two TAPS share an MMA: K halves = (chunk @
+              // tap 2j, chunk @ tap 2j + 1).  Both are descriptor choices on the data already in shared memory -- A: LBO =
+              // one tap step on the same window, B: LBO = one tap slot (the first halves of two consecutive slots) -- so
+              // neither the weight image nor the producer changes.  ceil(k / 2) instead of k MMAs for this pair (k = 11,
+              // 24 channels: 17 instead of 22 per sub-tile; these launches are bound by MMA operand reads).  An odd last tap
+              // keeps the old form (zero partner window, zero second half).
+              const uint32_t a_pair = (a_step << 16) | ((a_base_lo & 0x3FFFu) + rel0 + (uint32_t)tap0 * a_step);
+              const uint32_t b_pair = ((2u * bn) << 16) | (b_lo & 0x3FFFu);
+              const int npair = nt_g >> 1;
+              if (msub == 2) issue_taps<2>(d_tmem, bn, a_pair, 2u * a_step, b_pair, 2u * b_step, hi, idesc, accum, npair);
+              else if (msub == 4) issue_taps<4>(d_tmem, bn, a_pair, 2u * a_step, b_pair, 2u * b_step, hi, idesc, accum, npair);
+              else if (msub == 8) issue_taps<8>(d_tmem, bn, a_pair, 2u * a_step, b_pair, 2u * b_step, hi, idesc, accum, npair);
+              else issue_taps<1>(d_tmem, bn, a_pair, 2u * a_step, b_pair, 2u * b_step, hi, idesc, accum, npair);
+              if (nt_g & 1) {
+                const uint32_t acc1 = npair > 0 ? 1u : accum;
+                const uint32_t a_lo = a_base_lo + rel0 + (uint32_t)(tap0 + nt_g - 1) * a_step;
+                const uint32_t b_1 = b_lo + (uint32_t)(nt_g - 1) * b_step;
+                if (msub == 2) issue_taps<2>(d_tmem, bn, a_lo, a_step, b_1, b_step, hi, idesc, acc1, 1);
+                else if (msub == 4) issue_taps<4>(d_tmem, bn, a_lo, a_step, b_1, b_step, hi, idesc, acc1, 1);
+                else if (msub == 8) issue_taps<8>(d_tmem, bn, a_lo, a_step, b_1, b_step, hi, idesc, acc1, 1);
+                else issue_taps<1>(d_tmem, bn, a_lo, a_step, b_1, b_step, hi, idesc, acc1, 1);
+              }
+            } else if (P.tap_arith) {
               const uint32_t a_lo = a_base_lo + rel0 + (uint32_t)tap0 * a_step;
               if (msub == 2) issue_taps<2>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
               else if (msub == 4) issue_taps<4>(d_tmem, bn, a_lo, a_step, b_lo, b_step, hi, idesc, accum, nt_g);
@@ -1343,6 +1368,14 @@ static int tc_plan(const fh_tc_conv_args* a, void* stream, int budget_bytes, TcP
   }
   FH_REQUIRE(span <= kMaxSpan, FH_ERR_UNSUPPORTED_CFG, "fh_tc_conv: tap span %d exceeds %d rows", span, kMaxSpan);
   p.tap_arith = arith;
+  {
+    static int tap_pair_on = -1;
+    if (tap_pair_on < 0) {
+      const char* e = getenv("FH_TC_TAP_PAIR");
+      tap_pair_on = e ? atoi(e) : 1;
+    }
+    p.tap_pair = (tap_pair_on && p.ci_odd && arith && a->P == 1 && a->ntaps >= 2 && p.tap_step[0] > 0 && !fused && !two) ? 1 : 0;
+  }
   if (fused) {  // aligned A window of exactly 128 msub rows: a tile keeps 128 msub - span output rows
     p.m_stride = p.m_valid = 128 * msub - span;
     p.m_tiles = (a->L + p.m_stride - 1) / p.m_stride;

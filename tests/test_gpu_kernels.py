@@ -1099,7 +1099,12 @@ def test_tc_conv_pair_matches_single(cuda_device, B, Ci, Co, L, k, d):
         eng._tc_conv(r1, A, bs, cs, HALO, O1[o:], (obs, ocs, 8), 0, B, L, **kw)
         eng._tc_conv(r2, A, bs, cs, HALO, O2[o:], (obs, ocs, 8), 0, B, L, **kw)
         torch.cuda.synchronize()
-        assert torch.equal(O1, O2), (res, float((O1 - O2).abs().max()))
+        if Ci % 16 == 8:
+            # odd chunk count: the single-CTA kernel issues the odd chunk's taps two per MMA (K halves = two taps), the
+            # pair kernel one per MMA against a zero partner window -- same products, different fp32 summation order
+            assert float((O1 - O2).abs().max()) <= 2e-5 * max(1.0, float(O1.abs().max())), res
+        else:
+            assert torch.equal(O1, O2), (res, float((O1 - O2).abs().max()))
     ref = F.conv1d(x.half().float(), w.half().float().cuda(), b.cuda(), dilation=d, padding=(k * d - d) // 2)
     got = O2[: B * obs].view(B, Co // 8, ocs // 8, 8)[:, :, HALO:HALO + L].permute(0, 1, 3, 2).reshape(B, Co, L) - \
         R[: B * obs].view(B, Co // 8, ocs // 8, 8)[:, :, HALO:HALO + L].permute(0, 1, 3, 2).reshape(B, Co, L)
