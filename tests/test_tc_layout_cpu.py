@@ -105,3 +105,55 @@ def test_tc_addressing_matches_conv(kind):
     # halo rows were never written
     full = torch.from_numpy(out).reshape(B, cout_pad // 8, Lp_out, 8)
     assert full[:, :, :HALO].abs().max() == 0 and full[:, :, HALO + Lo:].abs().max() == 0
+
+
+def _mma(D, a_img, a_start, a_lbo, b_img, b_start, b_lbo, bn):
+    """One 128 x bn x 16 MMA from flat shared-memory images of 8-element (16-byte) rows, addressed like the no-swizzle
+    K-major descriptors of tc_conv.cu: K half h of A row r = row (a_start + h * a_lbo + r), of B column n = row
+    (b_start + h * b_lbo + n); all offsets in 16-byte rows."""
+    for h in range(2):
+        A = a_img[a_start + h * a_lbo: a_start + h * a_lbo + 128]      # [128, 8]
+        Bm = b_img[b_start + h * b_lbo: b_start + h * b_lbo + bn]      # [bn, 8]
+        D += A @ Bm.T
+
+
+@pytest.mark.parametrize("k,d", [(7, 1), (11, 1), (3, 5), (4, 3), (2, 1)])
+def test_tc_tap_pair_addressing(k, d):
+    """Odd chunk count (24 channels): mma_role issues the taps of the odd chunk two per MMA -- A: LBO = one tap step on the
+    same window, B: LBO = one tap slot of the UNCHANGED weight image -- and an odd last tap in the old form (zero partner
+    window).  Emulated on flat shared-memory images against the plain convolution."""
+    torch.manual_seed(k * 10 + d)
+    Cin, Cout, L, bn = 24, 24, 128, 32
+    x = torch.randn(1, Cin, L)
+    w = torch.randn(Cout, Cin, k) * 0.2
+    tc = packing.conv1d_taps(w, None, d)
+    ref = F.conv1d(x.bfloat16().float(), w.bfloat16().float(), None, dilation=d, padding=(k * d - d) // 2)
+    packed, cin_pad, cout_pad, _ = packing.pack_tc(tc, "cpu", bn=bn)
+    offs = tc.off[0]
+    mn, span = int(offs.min()), int(offs.max() - offs.min())
+    step = int(offs[1] - offs[0])
+    assert step == d and all(int(offs[j + 1] - offs[j]) == step for j in range(k - 1))  # arithmetic taps (tap_arith)
+    wrows = 128 + span
+    arows_pad = 128 + 64
+    Lp = HALO + 128 + 64
+    a = to_chunked(x, cin_pad, Lp, HALO).float().numpy().reshape(cin_pad // 8, Lp, 8)
+    wimg = packed.float().numpy().reshape(2, k, 2, bn, 8)  # [ci-pair][tap][half][bn][8] (P = 1, one N tile)
+    D = np.zeros((128, bn), np.float32)
+    rel0 = int(offs[0]) - mn
+    for cp in range(2):
+        # stage image: two chunk windows of arows_pad rows (the partner of the odd chunk is a zeroed region), then the weights
+        slot = np.zeros((2 * arows_pad, 8), np.float32)
+        for c in range(2):
+            if 2 * cp + c < cin_pad // 8:
+                slot[c * arows_pad: c * arows_pad + wrows] = a[2 * cp + c, HALO + mn: HALO + mn + wrows]
+        bimg = wimg[cp].reshape(k * 2 * bn, 8)
+        if cp == 0:  # full pair: one MMA per tap, K halves = the two chunks (LBO = chunk window stride / half a tap slot)
+            for j in range(k):
+                _mma(D, slot, rel0 + j * step, arows_pad, bimg, j * 2 * bn, bn, bn)
+        else:        # odd chunk: two taps per MMA
+            for j in range(k // 2):
+                _mma(D, slot, rel0 + 2 * j * step, step, bimg, 2 * j * 2 * bn, 2 * bn, bn)
+            if k & 1:
+                _mma(D, slot, rel0 + (k - 1) * step, arows_pad, bimg, (k - 1) * 2 * bn, bn, bn)
+    got = torch.from_numpy(D[:, :Cout].T.copy())[None][..., : ref.shape[-1]]  # an even k yields one output less in torch
+    assert torch.allclose(got, ref, atol=2e-3, rtol=1e-3), (got - ref).abs().max()
